@@ -1,0 +1,91 @@
+/* libnfdpf -- C-ABI of the B200-native NF-DPF particle update (hand-written sm_100a CUDA kernels).
+ *
+ * The reference (xiongjiechen/Normalizing-Flows-DPFs) has no FFI: its boundary is the Python module API
+ * (SURVEY.md 8b).  The host-side mirror of that API lives in normalizing_flows_dpfs_b200/*.py and calls the
+ * entry points below through ctypes; every entry point names the reference code it replaces (file:line in
+ * the reference repository).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers to contiguous row-major fp32 (int64 where stated) owned by the
+ *     caller; the library never allocates caller-visible memory and never copies to the host.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and ordered on it.
+ *   - Return value: 0 on success, <0 on error (NFDPF_ERR_*); nfdpf_last_error() gives the message of the
+ *     last failure on the calling thread.  There is no CPU fallback and no silent dispatch: unsupported
+ *     shapes return NFDPF_ERR_UNSUPPORTED.
+ *   - B = trajectories (rows), N = particles per trajectory, P = B*N, d = state dimension.
+ *   - "packed stack": the parameters of a coupling stack as one flat fp32 vector in state_dict order
+ *     flows.k.{t1,s1,t2,s2}.network.{0,2,4}.{weight,bias}, k = 0..n_flows-1 (nf/flows.py:181-188,
+ *     nf/models.py:37-43), Linear weights row-major (out,in), in = D/2 + C, hidden = 8.
+ */
+#ifndef NFDPF_H
+#define NFDPF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFDPF_VERSION 100
+#define NFDPF_OK 0
+#define NFDPF_ERR_INVALID (-1)     /* bad argument (null pointer, non-positive size, alpha out of range) */
+#define NFDPF_ERR_UNSUPPORTED (-2) /* shape outside what the kernels are built for */
+#define NFDPF_ERR_CUDA (-3)        /* a CUDA runtime call or launch failed */
+
+#define NFDPF_HIDDEN 8 /* FCNN hidden width, nf/flows.py:123,183 */
+
+int nfdpf_version(void);
+const char* nfdpf_last_error(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+int64_t nfdpf_launch_count(void);
+
+/* ---- (K3) soft resampling: resamplers/resamplers.py:20-60 soft_resampler ---------------------------
+ * particles (B,N,d), probs (B,N), offsets (B,) the caller's U(0,1/N) draws (resamplers.py:43), markers (N,)
+ * the caller's linspace(0,(N-1)/N,N) (resamplers.py:42).  alpha as a double so that (float)alpha and
+ * (float)(1.0-alpha) are formed exactly as the reference's Python-scalar arithmetic does.
+ * Outputs: particles_out (B,N,d), probs_out (B,N), idx_out (B,N) int64 FLAT indices (j + N*b),
+ * saved (B,2) = {row sum of q before normalisation, row sum of the gathered importance weights}.
+ * Indices are bit-exact with the reference CPU path (ATen cascade row-sum + fp64-accumulated cumsum). */
+int nfdpf_soft_resample_fwd(const float* particles, const float* probs, const float* offsets, const float* markers,
+                            double alpha, int B, int N, int d, float* particles_out, float* probs_out,
+                            int64_t* idx_out, float* saved, void* stream);
+/* backward: g_particles (B,N,d), g_probs (B,N) (either may be NULL = zero) -> d_particles (B,N,d), d_probs (B,N) */
+int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_probs, const float* probs, const int64_t* idx,
+                            const float* saved, double alpha, int B, int N, int d, float* d_particles,
+                            float* d_probs, void* stream);
+
+/* ---- (K2, weight half) log-weight update + normalisation: DPFs.py:187-192, utils.py:39-44 ----------
+ * logw = logw_prev + lki + prior - propose (NULL terms are skipped); probs = softmax_N(logw) + add_eps;
+ * row_stats (B,2) = {sum_n logw (for obs_likelihood, DPFs.py:191), 1/sum_n probs^2 (ESS term, DPFs.py:163)}.
+ * logw_out may be NULL.  normalize_log_probs alone = logw_prev only, add_eps = 0. */
+int nfdpf_weight_update_fwd(const float* logw_prev, const float* lki, const float* prior, const float* propose,
+                            float add_eps, int B, int N, float* logw_out, float* probs_out, float* row_stats,
+                            void* stream);
+/* backward: g_probs (B,N) or NULL, g_logw (B,N) or NULL, g_rowsum (B,) or NULL (grad of row_stats[:,0]);
+ * probs = the forward output (with add_eps).  d_logw (B,N) is the gradient of every added term (negate for propose). */
+int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw, const float* g_rowsum, const float* probs,
+                            float add_eps, int B, int N, float* d_logw, void* stream);
+
+/* ---- (K1) fused coupling stack: nf/flows.py:155-179, 215-239; nf/models.py:11-30, 45-61 ---------------
+ * x (P,D); context = [row_ctx (B,C_row) broadcast over the N particles of a row | part_ctx (P,C_part)],
+ * C = C_row + C_part (either may be 0).  inverse=0: flows 0..n-1 forward; inverse=1: flows n-1..0 inverse.
+ * y (P,D), log_det (P,).  Supported: D = 2 with C_part = 0 (row-constant context hoisted out of layer 1);
+ * D even <= 32 with any C <= 64 (general path). */
+int nfdpf_coupling_fwd(const float* packed, int n_flows, int D, int C_row, int C_part, const float* x,
+                       const float* row_ctx, const float* part_ctx, int inverse, int B, int N, float* y,
+                       float* log_det, void* stream);
+/* backward from the OUTPUT y (coupling layers are invertible: activations are recomputed walking the stack
+ * backwards, nothing else is saved).  g_y (P,D), g_ld (P,) (NULL = 0).  d_x (P,D); d_row_ctx (B,C_row) /
+ * d_part_ctx (P,C_part) may be NULL (context detached: model/models.py:309-313, 338-339, 360-361).
+ * d_packed: fp32 vector of the packed-stack length, ACCUMULATED into (+=) in a fixed order (deterministic).
+ * workspace: nfdpf_coupling_bwd_workspace() bytes of device scratch. */
+int64_t nfdpf_coupling_bwd_workspace(int n_flows, int D, int C_row, int C_part, int B, int N);
+int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C_part, const float* y,
+                       const float* row_ctx, const float* part_ctx, int inverse, int B, int N, const float* g_y,
+                       const float* g_ld, float* d_x, float* d_row_ctx, float* d_part_ctx, float* d_packed,
+                       void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFDPF_H */

@@ -1,0 +1,108 @@
+// Shared device/host helpers for libnfdpf (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/nfdpf.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libnfdpf is written for sm_100a (B200) only"
+#endif
+
+namespace nfdpf {
+
+// ---- error plumbing (thread-local message, C-ABI returns negative codes) -------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> NFDPF_ERR_CUDA
+int sm_count();
+
+#define NFDPF_REQUIRE(cond, ...)              \
+    do {                                      \
+        if (!(cond)) {                        \
+            nfdpf::set_error(__VA_ARGS__);    \
+            return NFDPF_ERR_INVALID;         \
+        }                                     \
+    } while (0)
+
+#define NFDPF_CUDA(call)                                                              \
+    do {                                                                              \
+        cudaError_t e__ = (call);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            nfdpf::set_error("%s failed: %s", #call, cudaGetErrorString(e__));        \
+            return NFDPF_ERR_CUDA;                                                    \
+        }                                                                             \
+    } while (0)
+
+// ---- warp / block primitives ----------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Block-wide all-reduce through a 33-slot shared scratch (fixed order => deterministic).
+// All threads of the block must call; result is broadcast to every thread.
+template <typename T, typename Op>
+__device__ __forceinline__ T block_allreduce(T v, T* scratch, Op op, T identity) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(FULL, v, o));
+    __syncthreads();  // protect scratch from a previous use
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        T t = lane < nwarp ? scratch[lane] : identity;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = op(t, __shfl_xor_sync(FULL, t, o));
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+struct OpSum {
+    template <typename T>
+    __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }
+};
+struct OpMax {
+    __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); }
+};
+struct OpMin {
+    __device__ __forceinline__ float operator()(float a, float b) const { return fminf(a, b); }
+};
+
+// ---- transcendental helpers ------------------------------------------------------------------------------
+// tanh with ~1e-7 ABSOLUTE error from two MUFU ops (ex2 + rcp): tanh(x) = 1 - 2/(1+e^{2x}).
+// The parity bar is rtol 1e-4 / atol 1e-5 against fp32 torch; tanh.approx (2^-11) would not hold it.
+__device__ __forceinline__ float tanh_acc(float x) {
+    const float ax = fminf(fabsf(x), 15.0f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.885390081777927f));  // e^{2|x|}
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    const float t = fmaf(-2.0f, r, 1.0f);
+    // small |x|: 1 - 2/(1+e) cancels; use the odd Taylor series (abs err < 2e-8 for |x| < 0.125)
+    const float x2 = x * x;
+    const float s = x * fmaf(x2, fmaf(x2, fmaf(x2, -0.0539682540f, 0.1333333333f), -0.3333333333f), 1.0f);
+    return ax < 0.125f ? s : copysignf(t, x);
+}
+__device__ __forceinline__ float exp_acc(float x) { return __expf(x); }  // ex2.approx(x*log2e): 2 ulp + range error
+
+}  // namespace nfdpf

@@ -1,0 +1,384 @@
+// (K1) Fused conditional-RealNVP coupling stack: forward / inverse with log-det, and the backward of either.
+// Replaces ~90 ATen launches per stack pass (nf/flows.py:215-239 via nf/models.py:45-61) and the (P,C) context
+// materialisation of model/models.py:309-315, 338-346.  See coupling.cuh for the layout decisions.
+#include "coupling.cuh"
+
+namespace nfdpf {
+
+constexpr int TP = 128;           // particles per CTA batch (= threads per CTA)
+constexpr int TS = TP + 1;        // tile row stride (conflict-free for lane-distinct rows)
+constexpr int MAX_FCNN = 16;      // n_flows <= 4
+
+// ------------------------------------------------------------------------------------------------- forward
+template <int HALF, int CP>
+__global__ void __launch_bounds__(TP)
+coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ x,
+                    const float* __restrict__ row_ctx, const float* __restrict__ part_ctx, int inverse, int N, int chunk,
+                    float* __restrict__ y, float* __restrict__ log_det) {
+    using L = Lay<HALF, CP>;
+    constexpr int D = 2 * HALF;
+    extern __shared__ __align__(16) float smem[];
+    const int n_fcnn = 4 * n_flows, tid = threadIdx.x;
+    float* s_img = smem;                                  // [n_fcnn][L::SIZE]
+    float* s_hb = s_img + n_fcnn * L::SIZE;               // [n_fcnn][8]
+    float* s_w1r = s_hb + n_fcnn * H;                     // [n_fcnn][8][C_row]
+    const int b = blockIdx.y;
+    const int pf = packed_fcnn_size(HALF, C_row + CP);
+    for (int f = 0; f < n_fcnn; ++f)
+        load_fcnn_image<HALF, CP>(packed + (size_t)f * pf, C_row, s_img + f * L::SIZE, s_w1r + (size_t)f * H * C_row, tid, TP);
+    __syncthreads();
+    hoist_row_context<HALF, CP>(s_img, s_w1r, row_ctx + (size_t)b * C_row, C_row, n_fcnn, s_hb, tid, TP);
+    __syncthreads();
+    const int n0 = blockIdx.x * chunk, n1 = min(N, n0 + chunk);
+    for (int n = n0 + tid; n < n1; n += TP) {
+        const size_t p = (size_t)b * N + n;
+        float lo[HALF], up[HALF], pc[CP > 0 ? CP : 1], ld = 0.f;
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) { lo[i] = x[p * D + i]; up[i] = x[p * D + HALF + i]; }
+#pragma unroll
+        for (int i = 0; i < CP; ++i) pc[i] = part_ctx[p * CP + i];
+        if (!inverse) {
+#pragma unroll 1
+            for (int f = 0; f < n_flows; ++f) {
+                const float* im = s_img + 4 * f * L::SIZE;
+                const float* hb = s_hb + 4 * f * H;
+                stage_fwd<HALF, CP, false>(im, im + L::SIZE, hb, hb + H, lo, pc, up, ld);                          // t1,s1
+                stage_fwd<HALF, CP, false>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, up, pc, lo, ld);  // t2,s2
+            }
+        } else {
+#pragma unroll 1
+            for (int f = n_flows - 1; f >= 0; --f) {
+                const float* im = s_img + 4 * f * L::SIZE;
+                const float* hb = s_hb + 4 * f * H;
+                stage_fwd<HALF, CP, true>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, up, pc, lo, ld);
+                stage_fwd<HALF, CP, true>(im, im + L::SIZE, hb, hb + H, lo, pc, up, ld);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) { y[p * D + i] = lo[i]; y[p * D + HALF + i] = up[i]; }
+        log_det[p] = ld;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// Tile rows (one column per particle of the batch):
+template <int HALF, int CP>
+struct Rows {
+    static constexpr int ONE = 0, C = 1, PC = C + HALF, H1 = PC + CP, H2 = H1 + H, D1 = H2 + H, D2 = D1 + H, DO = D2 + H,
+                         COUNT = DO + HALF;
+    // per-FCNN gradient outputs, in packed order minus the row-context columns
+    static constexpr int NOUT = H * (HALF + CP) + H + H * H + H + HALF * H + HALF;
+};
+
+// entry e of the output table: (tile row of the delta, tile row of the activation, offset inside the packed FCNN)
+template <int HALF, int CP>
+__device__ void out_entry(int e, int C_row, int& ra, int& rb, int& poff) {
+    using R = Rows<HALF, CP>;
+    const int fin = HALF + C_row + CP;
+    int o = e;
+    if (o < H * (HALF + CP)) {
+        const int k = o / (HALF + CP), i = o % (HALF + CP);
+        ra = R::D1 + k;
+        rb = i < HALF ? R::C + i : R::PC + (i - HALF);
+        poff = k * fin + (i < HALF ? i : C_row + i);
+        return;
+    }
+    o -= H * (HALF + CP);
+    int base = H * fin;
+    if (o < H) { ra = R::D1 + o; rb = R::ONE; poff = base + o; return; }
+    o -= H; base += H;
+    if (o < H * H) { ra = R::D2 + o / H; rb = R::H1 + o % H; poff = base + o; return; }
+    o -= H * H; base += H * H;
+    if (o < H) { ra = R::D2 + o; rb = R::ONE; poff = base + o; return; }
+    o -= H; base += H;
+    if (o < HALF * H) { ra = R::DO + o / H; rb = R::H2 + o % H; poff = base + o; return; }
+    o -= HALF * H; base += HALF * H;
+    ra = R::DO + o; rb = R::ONE; poff = base + o;
+}
+
+template <int HALF, int CP>
+struct BwdSmem {
+    using L = Lay<HALF, CP>;
+    using R = Rows<HALF, CP>;
+    static size_t bytes(int n_fcnn, int C_row) {
+        size_t fl = (size_t)n_fcnn * L::SIZE + n_fcnn * H + (size_t)n_fcnn * H * C_row  // images, hb, w1r
+                    + (size_t)R::COUNT * TS                                              // tile
+                    + (size_t)n_fcnn * R::NOUT                                           // acc
+                    + (size_t)n_fcnn * H * C_row                                         // accR
+                    + n_fcnn * H                                                         // d1row
+                    + C_row + 4;                                                         // ctx
+        return fl * sizeof(float) + (size_t)R::NOUT * sizeof(int);                       // + table
+    }
+};
+
+// Backward of one stage for the particle held by this thread, plus the CTA-wide weight-gradient accumulation.
+// On entry (c, v) are the stage's OUTPUT values with gradients (gc, gv); on exit v / gv are the stage's input.
+template <int HALF, int CP, bool INV>
+__device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s, int f_t,
+                                          bool live, const float (&c)[HALF], float (&gc)[HALF], const float* pc, float* gpc,
+                                          float (&v)[HALF], float (&gv)[HALF], float gld, float* s_tile, float* s_acc,
+                                          float* s_d1row, const int* s_tab) {
+    using R = Rows<HALF, CP>;
+    const int tid = threadIdx.x;
+    float h1t[H], h2t[H], h1s[H], h2s[H], t[HALF], s[HALF], dt[HALF], ds[HALF];
+    fcnn_fwd<HALF, CP>(img_t, hb_t, c, pc, h1t, h2t, t);
+    fcnn_fwd<HALF, CP>(img_s, hb_s, c, pc, h1s, h2s, s);
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        if (!INV) {  // out = t + in*e^s
+            const float es = expf(s[i]);
+            const float vin = (v[i] - t[i]) * expf(-s[i]);
+            dt[i] = gv[i];
+            ds[i] = fmaf(gv[i] * vin, es, gld);
+            gv[i] = gv[i] * es;
+            v[i] = vin;
+        } else {     // out = (in - t) e^{-s}
+            const float es = expf(s[i]);
+            const float gin = gv[i] * expf(-s[i]);
+            dt[i] = -gin;
+            ds[i] = -fmaf(gv[i], v[i], gld);
+            v[i] = fmaf(v[i], es, t[i]);
+            gv[i] = gin;
+        }
+        if (!live) { dt[i] = 0.f; ds[i] = 0.f; }
+    }
+    // conditioning half is shared by both nets of the stage: stage it once
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) s_tile[(R::C + i) * TS + tid] = c[i];
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+        float d1[H], d2[H];
+        if (net == 0) fcnn_bwd<HALF, CP>(img_t, dt, h1t, h2t, d1, d2, gc, gpc);
+        else          fcnn_bwd<HALF, CP>(img_s, ds, h1s, h2s, d1, d2, gc, gpc);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            s_tile[(R::H1 + k) * TS + tid] = net == 0 ? h1t[k] : h1s[k];
+            s_tile[(R::H2 + k) * TS + tid] = net == 0 ? h2t[k] : h2s[k];
+            s_tile[(R::D1 + k) * TS + tid] = d1[k];
+            s_tile[(R::D2 + k) * TS + tid] = d2[k];
+        }
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) s_tile[(R::DO + i) * TS + tid] = net == 0 ? dt[i] : ds[i];
+        __syncthreads();
+        const int f = f_t + net;
+        for (int e = tid; e < R::NOUT; e += TP) {
+            const int tab = s_tab[e];
+            const float* ra = s_tile + (tab & 0xffff) * TS;
+            const float* rb = s_tile + (tab >> 16) * TS;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+            for (int p = 0; p < TP; p += 4) {
+                a0 = fmaf(ra[p], rb[p], a0);
+                a1 = fmaf(ra[p + 1], rb[p + 1], a1);
+                a2 = fmaf(ra[p + 2], rb[p + 2], a2);
+                a3 = fmaf(ra[p + 3], rb[p + 3], a3);
+            }
+            const float a = (a0 + a1) + (a2 + a3);
+            s_acc[f * R::NOUT + e] += a;
+            const int o = e - H * (HALF + CP);
+            if (o >= 0 && o < H) s_d1row[f * H + o] += a;  // b1 slot == sum of layer-1 deltas (row-context hoist)
+        }
+        __syncthreads();
+    }
+}
+
+template <int HALF, int CP>
+__global__ void __launch_bounds__(TP)
+coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ y,
+                    const float* __restrict__ row_ctx, const float* __restrict__ part_ctx, int inverse, int B, int N,
+                    const float* __restrict__ g_y, const float* __restrict__ g_ld, float* __restrict__ d_x,
+                    float* __restrict__ d_row_ctx, float* __restrict__ d_part_ctx, float* __restrict__ partials) {
+    using L = Lay<HALF, CP>;
+    using R = Rows<HALF, CP>;
+    constexpr int D = 2 * HALF;
+    extern __shared__ __align__(16) float smem[];
+    const int n_fcnn = 4 * n_flows, tid = threadIdx.x;
+    float* s_img = smem;
+    float* s_hb = s_img + n_fcnn * L::SIZE;
+    float* s_w1r = s_hb + n_fcnn * H;
+    float* s_tile = s_w1r + (size_t)n_fcnn * H * C_row;
+    float* s_acc = s_tile + R::COUNT * TS;
+    float* s_accR = s_acc + n_fcnn * R::NOUT;
+    float* s_d1row = s_accR + (size_t)n_fcnn * H * C_row;
+    float* s_ctx = s_d1row + n_fcnn * H;
+    int* s_tab = reinterpret_cast<int*>(s_ctx + C_row + 4);
+    const int pf = packed_fcnn_size(HALF, C_row + CP);
+    for (int f = 0; f < n_fcnn; ++f)
+        load_fcnn_image<HALF, CP>(packed + (size_t)f * pf, C_row, s_img + f * L::SIZE, s_w1r + (size_t)f * H * C_row, tid, TP);
+    for (int e = tid; e < R::NOUT; e += TP) {
+        int ra, rb, poff;
+        out_entry<HALF, CP>(e, C_row, ra, rb, poff);
+        s_tab[e] = ra | (rb << 16);
+    }
+    for (int e = tid; e < n_fcnn * R::NOUT; e += TP) s_acc[e] = 0.f;
+    for (int e = tid; e < n_fcnn * H * C_row; e += TP) s_accR[e] = 0.f;
+    s_tile[R::ONE * TS + tid] = 1.0f;
+    __syncthreads();
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        for (int e = tid; e < C_row; e += TP) s_ctx[e] = row_ctx[(size_t)b * C_row + e];
+        for (int e = tid; e < n_fcnn * H; e += TP) s_d1row[e] = 0.f;
+        __syncthreads();
+        hoist_row_context<HALF, CP>(s_img, s_w1r, s_ctx, C_row, n_fcnn, s_hb, tid, TP);
+        __syncthreads();
+        for (int n0 = 0; n0 < N; n0 += TP) {
+            const int n = n0 + tid;
+            const bool live = n < N;
+            const size_t p = (size_t)b * N + (live ? n : 0);
+            float lo[HALF], up[HALF], glo[HALF], gup[HALF], pc[CP > 0 ? CP : 1], gpc[CP > 0 ? CP : 1];
+#pragma unroll
+            for (int i = 0; i < HALF; ++i) {
+                lo[i] = y[p * D + i]; up[i] = y[p * D + HALF + i];
+                glo[i] = live && g_y ? g_y[p * D + i] : 0.f;
+                gup[i] = live && g_y ? g_y[p * D + HALF + i] : 0.f;
+            }
+            const float gld = live && g_ld ? g_ld[p] : 0.f;
+#pragma unroll
+            for (int i = 0; i < CP; ++i) { pc[i] = part_ctx[p * CP + i]; gpc[i] = 0.f; s_tile[(R::PC + i) * TS + tid] = pc[i]; }
+            if (!inverse) {  // forward pass ran flows 0..n-1 (t1/s1 then t2/s2): walk back n-1..0 (t2/s2 then t1/s1)
+#pragma unroll 1
+                for (int f = n_flows - 1; f >= 0; --f) {
+                    const float* im = s_img + 4 * f * L::SIZE;
+                    const float* hb = s_hb + 4 * f * H;
+                    stage_bwd<HALF, CP, false>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, 4 * f + 2, live, up, gup,
+                                               pc, gpc, lo, glo, gld, s_tile, s_acc, s_d1row, s_tab);
+                    stage_bwd<HALF, CP, false>(im, im + L::SIZE, hb, hb + H, 4 * f, live, lo, glo, pc, gpc, up, gup, gld, s_tile,
+                                               s_acc, s_d1row, s_tab);
+                }
+            } else {         // inverse pass ran flows n-1..0 (t2/s2 then t1/s1): walk back 0..n-1 (t1/s1 then t2/s2)
+#pragma unroll 1
+                for (int f = 0; f < n_flows; ++f) {
+                    const float* im = s_img + 4 * f * L::SIZE;
+                    const float* hb = s_hb + 4 * f * H;
+                    stage_bwd<HALF, CP, true>(im, im + L::SIZE, hb, hb + H, 4 * f, live, lo, glo, pc, gpc, up, gup, gld, s_tile,
+                                              s_acc, s_d1row, s_tab);
+                    stage_bwd<HALF, CP, true>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, 4 * f + 2, live, up, gup,
+                                              pc, gpc, lo, glo, gld, s_tile, s_acc, s_d1row, s_tab);
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < HALF; ++i) { d_x[p * D + i] = glo[i]; d_x[p * D + HALF + i] = gup[i]; }
+                if (CP > 0 && d_part_ctx) {
+#pragma unroll
+                    for (int i = 0; i < CP; ++i) d_part_ctx[p * CP + i] = gpc[i];
+                }
+            }
+        }
+        // row-context columns of W1 and the context gradient from this trajectory's layer-1 delta sums
+        for (int e = tid; e < n_fcnn * H * C_row; e += TP) s_accR[e] = fmaf(s_d1row[e / C_row], s_ctx[e % C_row], s_accR[e]);
+        if (d_row_ctx)
+            for (int cidx = tid; cidx < C_row; cidx += TP) {
+                float a = 0.f;
+                for (int fk = 0; fk < n_fcnn * H; ++fk) a = fmaf(s_w1r[(size_t)fk * C_row + cidx], s_d1row[fk], a);
+                d_row_ctx[(size_t)b * C_row + cidx] = a;
+            }
+        __syncthreads();
+    }
+    // per-CTA partial gradient in packed layout
+    float* out = partials + (size_t)blockIdx.x * n_fcnn * pf;
+    const int fin = HALF + C_row + CP;
+    for (int e = tid; e < n_fcnn * R::NOUT; e += TP) {
+        const int f = e / R::NOUT;
+        int ra, rb, poff;
+        out_entry<HALF, CP>(e % R::NOUT, C_row, ra, rb, poff);
+        out[(size_t)f * pf + poff] = s_acc[e];
+    }
+    for (int e = tid; e < n_fcnn * H * C_row; e += TP) {
+        const int fk = e / C_row, cidx = e % C_row;
+        out[(size_t)(fk / H) * pf + (fk % H) * fin + HALF + cidx] = s_accR[e];
+    }
+}
+
+// d_packed[i] += sum over CTAs (fixed order, fp64 accumulate)
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int n_params, float* __restrict__ d_packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_params) return;
+    double a = 0.0;
+    for (int c = 0; c < n_parts; ++c) a += (double)partials[(size_t)c * n_params + i];
+    d_packed[i] += (float)a;
+}
+
+static int bwd_grid(int B) { return min(B, 2 * sm_count()); }
+
+template <int HALF, int CP>
+static int launch_fwd(const float* packed, int n_flows, int C_row, const float* x, const float* row_ctx, const float* part_ctx,
+                      int inverse, int B, int N, float* y, float* log_det, cudaStream_t st) {
+    using L = Lay<HALF, CP>;
+    const int n_fcnn = 4 * n_flows;
+    const size_t smem = ((size_t)n_fcnn * L::SIZE + n_fcnn * H + (size_t)n_fcnn * H * C_row) * sizeof(float);
+    auto kern = coupling_fwd_kernel<HALF, CP>;
+    if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // enough CTAs to fill the GPU even when B is small: split rows into chunks of >= TP particles
+    int chunks = 1;
+    const int target = 4 * sm_count();
+    while (B * chunks < target && N / (chunks * 2) >= TP) chunks *= 2;
+    const int chunk = ((N + chunks - 1) / chunks + TP - 1) / TP * TP;
+    dim3 grid((N + chunk - 1) / chunk, B);
+    kern<<<grid, TP, smem, st>>>(packed, n_flows, C_row, x, row_ctx, part_ctx, inverse, N, chunk, y, log_det);
+    return check_launch("coupling_fwd");
+}
+
+template <int HALF, int CP>
+static int launch_bwd(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, const float* part_ctx,
+                      int inverse, int B, int N, const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx,
+                      float* d_part_ctx, float* d_packed, void* workspace, cudaStream_t st) {
+    const int n_fcnn = 4 * n_flows;
+    const size_t smem = BwdSmem<HALF, CP>::bytes(n_fcnn, C_row);
+    if (smem > 220 * 1024) { set_error("coupling_bwd: stack too large for shared memory (%zu bytes)", smem); return NFDPF_ERR_UNSUPPORTED; }
+    auto kern = coupling_bwd_kernel<HALF, CP>;
+    if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = bwd_grid(B);
+    const int n_params = n_fcnn * packed_fcnn_size(HALF, C_row + CP);
+    kern<<<grid, TP, smem, st>>>(packed, n_flows, C_row, y, row_ctx, part_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_part_ctx,
+                                 (float*)workspace);
+    int rc = check_launch("coupling_bwd");
+    if (rc) return rc;
+    reduce_partials_kernel<<<(n_params + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, n_params, d_packed);
+    return check_launch("coupling_bwd_reduce");
+}
+
+}  // namespace nfdpf
+
+using namespace nfdpf;
+
+#define NFDPF_COUPLING_SHAPES(X) X(1, 0) X(1, 4) X(1, 36) X(2, 0) X(2, 3) X(16, 0) X(16, 32)
+
+extern "C" int nfdpf_coupling_fwd(const float* packed, int n_flows, int D, int C_row, int C_part, const float* x,
+                                  const float* row_ctx, const float* part_ctx, int inverse, int B, int N, float* y, float* log_det,
+                                  void* stream) {
+    NFDPF_REQUIRE(packed && x && y && log_det, "coupling_fwd: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0 && D >= 2 && (D & 1) == 0, "coupling_fwd: need B,N > 0 and even D >= 2 (got %d,%d,%d)", B, N, D);
+    NFDPF_REQUIRE(n_flows >= 1 && 4 * n_flows <= MAX_FCNN, "coupling_fwd: n_flows must be in 1..4 (got %d)", n_flows);
+    NFDPF_REQUIRE(C_row >= 0 && C_part >= 0 && (C_row == 0 || row_ctx) && (C_part == 0 || part_ctx), "coupling_fwd: context pointers/sizes inconsistent");
+    NFDPF_REQUIRE(C_row <= 64, "coupling_fwd: C_row <= 64 supported (got %d)", C_row);
+#define X(HALF_, CP_) \
+    if (D == 2 * HALF_ && C_part == CP_) return launch_fwd<HALF_, CP_>(packed, n_flows, C_row, x, row_ctx, part_ctx, inverse, B, N, y, log_det, (cudaStream_t)stream);
+    NFDPF_COUPLING_SHAPES(X)
+#undef X
+    set_error("coupling_fwd: no kernel built for D=%d with %d per-particle context dims", D, C_part);
+    return NFDPF_ERR_UNSUPPORTED;
+}
+
+extern "C" int64_t nfdpf_coupling_bwd_workspace(int n_flows, int D, int C_row, int C_part, int B, int N) {
+    (void)N;
+    if (n_flows < 1 || D < 2 || B < 1) return 0;
+    return (int64_t)bwd_grid(B) * 4 * n_flows * packed_fcnn_size(D / 2, C_row + C_part) * (int64_t)sizeof(float);
+}
+
+extern "C" int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C_part, const float* y,
+                                  const float* row_ctx, const float* part_ctx, int inverse, int B, int N, const float* g_y,
+                                  const float* g_ld, float* d_x, float* d_row_ctx, float* d_part_ctx, float* d_packed,
+                                  void* workspace, void* stream) {
+    NFDPF_REQUIRE(packed && y && d_x && d_packed && workspace, "coupling_bwd: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0 && D >= 2 && (D & 1) == 0, "coupling_bwd: need B,N > 0 and even D >= 2");
+    NFDPF_REQUIRE(n_flows >= 1 && 4 * n_flows <= MAX_FCNN, "coupling_bwd: n_flows must be in 1..4 (got %d)", n_flows);
+    NFDPF_REQUIRE(C_row >= 0 && C_part >= 0 && (C_row == 0 || row_ctx) && (C_part == 0 || part_ctx), "coupling_bwd: context pointers/sizes inconsistent");
+    NFDPF_REQUIRE(C_row <= 64, "coupling_bwd: C_row <= 64 supported (got %d)", C_row);
+#define X(HALF_, CP_) \
+    if (D == 2 * HALF_ && C_part == CP_) return launch_bwd<HALF_, CP_>(packed, n_flows, C_row, y, row_ctx, part_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_part_ctx, d_packed, workspace, (cudaStream_t)stream);
+    NFDPF_COUPLING_SHAPES(X)
+#undef X
+    set_error("coupling_bwd: no kernel built for D=%d with %d per-particle context dims", D, C_part);
+    return NFDPF_ERR_UNSUPPORTED;
+}

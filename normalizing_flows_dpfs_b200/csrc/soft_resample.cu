@@ -1,0 +1,256 @@
+// (K3) Soft resampling -- one CTA per trajectory: mixture weights, ATen-order row sum, fp64 block scan,
+// binary search of the caller's markers, gather, renormalise.  Replaces resamplers/resamplers.py:20-60, whose
+// (B,N,N) bool compare (1 GiB at B=N=1024) is never materialised here.  HBM-bound: 32 B / particle forward.
+#include "common.cuh"
+
+namespace nfdpf {
+
+// Bit-exact emulation of ATen's CPU `sum(dim=-1)` for a contiguous fp32 row (SumKernel.cpp cascade_sum ->
+// vectorized_inner_sum -> row_sum -> multi_row_sum): 8 SIMD lanes x 4 ILP accumulators = 32 chains, chain c
+// sums elements c, c+32, c+64, ... through a 4-level cascade (level step 2^max(4, ceil_log2(rows)/4)); then
+// leftover whole vectors, ILP fold, scalar tail, lane fold.  One warp, lane = chain.  (oracle: cascade_row_sum)
+__device__ float aten_row_sum_warp(const float* __restrict__ q, int n) {
+    const int lane = threadIdx.x & 31;
+    const int lanes = n >= 8 ? 8 : 1;       // rows shorter than a vector take ATen's scalar path
+    const int chains = 4 * lanes;
+    const int vec = n / lanes, rows = vec / 4;
+    int lg = 0;
+    while ((1 << lg) < rows) ++lg;          // ceil_log2(rows)
+    const int p = max(4, lg / 4), step = 1 << p, mask = step - 1;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (lane < chains) {
+        int i = 0;
+        while (i + step <= rows) {
+            for (int j = 0; j < step; ++j, ++i) a0 = __fadd_rn(a0, q[i * chains + lane]);
+            a1 = __fadd_rn(a1, a0); a0 = 0.f;
+            if ((i & (mask << p)) == 0) {
+                a2 = __fadd_rn(a2, a1); a1 = 0.f;
+                if ((i & (mask << (2 * p))) == 0) { a3 = __fadd_rn(a3, a2); a2 = 0.f; }
+            }
+        }
+        for (; i < rows; ++i) a0 = __fadd_rn(a0, q[i * chains + lane]);
+        a0 = __fadd_rn(a0, a1); a0 = __fadd_rn(a0, a2); a0 = __fadd_rn(a0, a3);
+        if (lane < lanes)  // leftover whole vectors go to ILP accumulator 0
+            for (int v = rows * 4; v < vec; ++v) a0 = __fadd_rn(q[v * lanes + lane], a0);
+    }
+    // ILP fold: ps[0] += ps[k], k = 1..3 (chain k*lanes + l lives in lane k*lanes + l)
+    float t = a0;
+    for (int k = 1; k < 4; ++k) {
+        const float o = __shfl_sync(FULL, a0, (k * lanes + lane) & 31);
+        t = __fadd_rn(t, o);
+    }
+    float out = 0.f;
+    for (int k = vec * lanes; k < n; ++k) out = __fadd_rn(out, q[k]);  // scalar tail first
+    for (int l = 0; l < lanes; ++l) out = __fadd_rn(out, __shfl_sync(FULL, t, l));
+    return out;  // valid in every lane
+}
+
+// Block-wide inclusive scan in fp64 over s_q[0..n) (fp32 in, fp32-rounded prefixes out, in place).
+// ATen's CPU cumsum accumulates a float row sequentially in double and rounds each prefix; with alpha < 1 every
+// q_j >= (1-alpha)/(N*sum) so all partial sums are exactly representable in fp64 and the order is irrelevant.
+__device__ void scan_fp64_inplace(float* s_q, int n, double* s_warp) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+    const int per = (n + nt - 1) / nt;
+    const int lo = min(tid * per, n), hi = min(lo + per, n);
+    double local = 0.0;
+    for (int j = lo; j < hi; ++j) local += (double)s_q[j];
+    double inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        double w = lane < nwarp ? s_warp[lane] : 0.0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(FULL, wi, o);
+            if (lane >= o) wi += v;
+        }
+        if (lane < nwarp) s_warp[lane] = wi - w;  // exclusive warp offsets
+    }
+    __syncthreads();
+    double run = s_warp[warp] + (inc - local);
+    for (int j = lo; j < hi; ++j) {
+        run += (double)s_q[j];
+        s_q[j] = (float)run;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024)
+soft_resample_fwd_kernel(const float* __restrict__ particles, const float* __restrict__ probs,
+                         const float* __restrict__ offsets, const float* __restrict__ markers, float alpha_f,
+                         float one_minus_alpha_f, int hard, int N, int d, float* __restrict__ particles_out,
+                         float* __restrict__ probs_out, int64_t* __restrict__ idx_out, float* __restrict__ saved) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_q = reinterpret_cast<float*>(smem_raw);  // q -> normalised q -> cum
+    float* s_wis = s_q + N;                           // importance weights w / q
+    __shared__ double s_warp[32];
+    __shared__ float s_red[33];
+    __shared__ float s_sum;
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const float* w = probs + (size_t)b * N;
+    const float unif = __fdiv_rn(1.0f, (float)N);                  // ones/N, resamplers.py:26
+    const float uterm = __fmul_rn(unif, one_minus_alpha_f);        // uniform_probs*(1-alpha), :31
+    for (int j = tid; j < N; j += nt)
+        s_q[j] = hard ? w[j] : __fadd_rn(__fmul_rn(w[j], alpha_f), uterm);
+    __syncthreads();
+    float S = 1.0f;
+    if (!hard) {
+        if (tid < 32) {
+            const float s = aten_row_sum_warp(s_q, N);
+            if (tid == 0) s_sum = s;
+        }
+        __syncthreads();
+        S = s_sum;
+        for (int j = tid; j < N; j += nt) {
+            const float qn = __fdiv_rn(s_q[j], S);                 // q / q.sum, :33
+            s_q[j] = qn;
+            s_wis[j] = __fdiv_rn(w[j], qn);                        // w / q, :34
+        }
+    } else {
+        for (int j = tid; j < N; j += nt) s_wis[j] = unif;         // hard resampling, :36-38
+    }
+    __syncthreads();
+    scan_fp64_inplace(s_q, N, s_warp);                             // cumsum, :45
+    if (tid == 0) s_q[N - 1] = 1.0f;                               // cum[:, -1] = 1, :47
+    __syncthreads();
+    const float off = offsets[b];
+    float part = 0.f;
+    for (int i = tid; i < N; i += nt) {
+        const float m = __fadd_rn(off, markers[i]);                // :44
+        int lo = 0, hi = N - 1;  // count of cum[j] < m over the sorted prefix [0, N-1)  ('>' is strict, :49)
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_q[mid] < m) lo = mid + 1; else hi = mid;
+        }
+        const int j = lo + (m > 1.0f ? 1 : 0);                     // forced last entry; never true for m <= 1
+        idx_out[(size_t)b * N + i] = (int64_t)j + (int64_t)N * b;  // :52
+        const float* src = particles + ((size_t)b * N + j) * d;
+        float* dst = particles_out + ((size_t)b * N + i) * d;
+        if (d == 2) {
+            *reinterpret_cast<float2*>(dst) = *reinterpret_cast<const float2*>(src);
+        } else {
+            for (int k = 0; k < d; ++k) dst[k] = src[k];
+        }
+        const float v = s_wis[j];
+        probs_out[(size_t)b * N + i] = v;  // unnormalised for now (same thread rewrites it below)
+        part += v;
+    }
+    const float S2 = block_allreduce(part, s_red, OpSum(), 0.f);
+    for (int i = tid; i < N; i += nt) {
+        const size_t o = (size_t)b * N + i;
+        probs_out[o] = __fdiv_rn(probs_out[o], S2);               // :56
+    }
+    if (tid == 0) { saved[2 * b] = S; saved[2 * b + 1] = S2; }
+}
+
+// Backward: indices carry no gradient; gradients flow through the gathered particles and through
+// w/q (numerator and q), then the row renormalisation.  idx is monotone per row, so every source particle j owns
+// a contiguous run of destinations: thread j sums its run in order (deterministic, no atomics).
+__global__ void __launch_bounds__(1024)
+soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __restrict__ g_probs,
+                         const float* __restrict__ probs, const int64_t* __restrict__ idx,
+                         const float* __restrict__ saved, float alpha_f, float one_minus_alpha_f, int hard, int N, int d,
+                         float* __restrict__ d_particles, float* __restrict__ d_probs) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* s_idx = reinterpret_cast<int*>(smem_raw);           // local source index per destination
+    float* s_gv = reinterpret_cast<float*>(smem_raw) + N;    // dL/dv_i, v_i = w_is[idx_i]
+    __shared__ float s_red[33];
+    const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const float S = saved[2 * b], S2 = saved[2 * b + 1];
+    const float* w = probs + (size_t)b * N;
+    const float unif = __fdiv_rn(1.0f, (float)N), uterm = __fmul_rn(unif, one_minus_alpha_f);
+    auto qu = [&](int j) { return __fadd_rn(__fmul_rn(w[j], alpha_f), uterm); };
+    float part = 0.f;
+    for (int i = tid; i < N; i += nt) {
+        const int j = (int)(idx[(size_t)b * N + i] - (int64_t)N * b);
+        s_idx[i] = j;
+        if (g_probs && !hard) {
+            const float v = w[j] * S / qu(j);
+            part += g_probs[(size_t)b * N + i] * (v / S2);   // sum_m g_m w'_m
+        }
+    }
+    const float c = block_allreduce(part, s_red, OpSum(), 0.f);
+    for (int i = tid; i < N; i += nt)
+        s_gv[i] = (g_probs && !hard) ? (g_probs[(size_t)b * N + i] - c) / S2 : 0.f;
+    __syncthreads();
+    float third = 0.f;
+    for (int j = tid; j < N; j += nt) {
+        int lo = 0, hi = N;  // first destination with idx >= j
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_idx[mid] < j) lo = mid + 1; else hi = mid; }
+        float G = 0.f, gp[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = lo; i < N && s_idx[i] == j; ++i) {
+            G += s_gv[i];
+            if (g_particles) {
+                if (d <= 4) { for (int k = 0; k < d; ++k) gp[k] += g_particles[((size_t)b * N + i) * d + k]; }
+            }
+        }
+        if (d <= 4) {
+            for (int k = 0; k < d; ++k) d_particles[((size_t)b * N + j) * d + k] = gp[k];
+        } else {
+            for (int k = 0; k < d; ++k) {
+                float a = 0.f;
+                if (g_particles)
+                    for (int i = lo; i < N && s_idx[i] == j; ++i) a += g_particles[((size_t)b * N + i) * d + k];
+                d_particles[((size_t)b * N + j) * d + k] = a;
+            }
+        }
+        float dw = 0.f;
+        if (!hard) {
+            const float q = qu(j), wj = w[j];
+            dw = G * S / q - G * wj * S * alpha_f / (q * q);  // through w_is_j = w_j S / qu_j at fixed S
+            third += G * wj / q;                                 // through S = sum_k qu_k
+        }
+        d_probs[(size_t)b * N + j] = dw;  // the same thread adds the shared third term below
+    }
+    const float t3 = block_allreduce(third, s_red, OpSum(), 0.f);
+    if (!hard)
+        for (int j = tid; j < N; j += nt) d_probs[(size_t)b * N + j] += alpha_f * t3;
+}
+
+static int pick_threads(int N) {
+    int t = 128;
+    while (t < 1024 && t * 4 < N) t <<= 1;
+    return t;
+}
+
+}  // namespace nfdpf
+
+using namespace nfdpf;
+
+extern "C" int nfdpf_soft_resample_fwd(const float* particles, const float* probs, const float* offsets,
+                                       const float* markers, double alpha, int B, int N, int d, float* particles_out,
+                                       float* probs_out, int64_t* idx_out, float* saved, void* stream) {
+    NFDPF_REQUIRE(particles && probs && offsets && markers && particles_out && probs_out && idx_out && saved,
+                  "soft_resample_fwd: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_fwd: B, N, d must be positive (got %d, %d, %d)", B, N, d);
+    NFDPF_REQUIRE(alpha > 0.0 && alpha <= 1.0, "soft_resample_fwd: need 0 < alpha <= 1 (resamplers.py:21), got %g", alpha);
+    const size_t smem = (size_t)N * 2 * sizeof(float);
+    if (smem > 200 * 1024) { set_error("soft_resample_fwd: N=%d exceeds the shared-memory row limit (25600)", N); return NFDPF_ERR_UNSUPPORTED; }
+    if (smem > 48 * 1024)
+        NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    soft_resample_fwd_kernel<<<B, pick_threads(N), smem, (cudaStream_t)stream>>>(
+        particles, probs, offsets, markers, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, d, particles_out,
+        probs_out, idx_out, saved);
+    return check_launch("soft_resample_fwd");
+}
+
+extern "C" int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_probs, const float* probs,
+                                       const int64_t* idx, const float* saved, double alpha, int B, int N, int d,
+                                       float* d_particles, float* d_probs, void* stream) {
+    NFDPF_REQUIRE(probs && idx && saved && d_particles && d_probs, "soft_resample_bwd: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_bwd: B, N, d must be positive");
+    NFDPF_REQUIRE(alpha > 0.0 && alpha <= 1.0, "soft_resample_bwd: need 0 < alpha <= 1, got %g", alpha);
+    const size_t smem = (size_t)N * 2 * sizeof(float);
+    if (smem > 200 * 1024) { set_error("soft_resample_bwd: N=%d exceeds the shared-memory row limit", N); return NFDPF_ERR_UNSUPPORTED; }
+    if (smem > 48 * 1024)
+        NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    soft_resample_bwd_kernel<<<B, pick_threads(N), smem, (cudaStream_t)stream>>>(
+        g_particles, g_probs, probs, idx, saved, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, d, d_particles,
+        d_probs);
+    return check_launch("soft_resample_bwd");
+}

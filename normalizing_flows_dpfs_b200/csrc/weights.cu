@@ -1,0 +1,114 @@
+// (K2, weight half) log-weight update + max-shift softmax normalisation + ESS / log-likelihood row statistics.
+// Replaces DPFs.py:187-192 + utils.py:39-44 (about ten ATen launches) with one pass: 20 B / particle.
+// One warp per row when N <= 1024 (pure shuffle reductions), else one CTA per row.
+#include "common.cuh"
+
+namespace nfdpf {
+
+template <bool BLOCK_PER_ROW>
+__global__ void weight_update_fwd_kernel(const float* __restrict__ lw0, const float* __restrict__ lki,
+                                         const float* __restrict__ prior, const float* __restrict__ propose, float add_eps,
+                                         int B, int N, float* __restrict__ logw_out, float* __restrict__ probs_out,
+                                         float* __restrict__ row_stats) {
+    __shared__ float s_red[33];
+    const int lane = threadIdx.x & 31;
+    const int row = BLOCK_PER_ROW ? blockIdx.x : blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (!BLOCK_PER_ROW && row >= B) return;
+    const int t0 = BLOCK_PER_ROW ? threadIdx.x : lane, stride = BLOCK_PER_ROW ? blockDim.x : 32;
+    const size_t base = (size_t)row * N;
+    auto red = [&](float v, auto op, float id) {
+        if (BLOCK_PER_ROW) return block_allreduce(v, s_red, op, id);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(FULL, v, o));
+        return v;
+    };
+    float mx = -INFINITY, sl = 0.f;
+    for (int n = t0; n < N; n += stride) {
+        float v = lw0[base + n];
+        if (lki) v += lki[base + n];          // (logw + lki + prior) - propose, DPFs.py:187 evaluation order
+        if (prior) v += prior[base + n];
+        if (propose) v -= propose[base + n];
+        if (logw_out) logw_out[base + n] = v;
+        probs_out[base + n] = v;              // stash; re-read by the same thread below
+        mx = fmaxf(mx, v);
+        sl += v;
+    }
+    mx = red(mx, OpMax(), -INFINITY);
+    sl = red(sl, OpSum(), 0.f);
+    float se = 0.f;
+    for (int n = t0; n < N; n += stride) {
+        const float e = expf(probs_out[base + n] - mx);
+        probs_out[base + n] = e;
+        se += e;
+    }
+    se = red(se, OpSum(), 0.f);
+    float s2 = 0.f;
+    for (int n = t0; n < N; n += stride) {
+        const float p = __fdiv_rn(probs_out[base + n], se) + add_eps;   // utils.py:43, DPFs.py:192
+        probs_out[base + n] = p;
+        s2 += p * p;
+    }
+    s2 = red(s2, OpSum(), 0.f);
+    if (t0 == 0 && row_stats) { row_stats[2 * row] = sl; row_stats[2 * row + 1] = 1.0f / s2; }
+}
+
+// d logw = p (g - sum g p) + g_logw + g_rowsum, with p = softmax (the forward output minus add_eps).
+template <bool BLOCK_PER_ROW>
+__global__ void weight_update_bwd_kernel(const float* __restrict__ g_probs, const float* __restrict__ g_logw,
+                                         const float* __restrict__ g_rowsum, const float* __restrict__ probs, float add_eps,
+                                         int B, int N, float* __restrict__ d_logw) {
+    __shared__ float s_red[33];
+    const int lane = threadIdx.x & 31;
+    const int row = BLOCK_PER_ROW ? blockIdx.x : blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (!BLOCK_PER_ROW && row >= B) return;
+    const int t0 = BLOCK_PER_ROW ? threadIdx.x : lane, stride = BLOCK_PER_ROW ? blockDim.x : 32;
+    const size_t base = (size_t)row * N;
+    float dot = 0.f;
+    if (g_probs)
+        for (int n = t0; n < N; n += stride) dot += g_probs[base + n] * (probs[base + n] - add_eps);
+    if (BLOCK_PER_ROW) dot = block_allreduce(dot, s_red, OpSum(), 0.f);
+    else dot = warp_sum(dot);
+    const float gr = g_rowsum ? g_rowsum[row] : 0.f;
+    for (int n = t0; n < N; n += stride) {
+        float v = gr;
+        if (g_probs) v += (probs[base + n] - add_eps) * (g_probs[base + n] - dot);
+        if (g_logw) v += g_logw[base + n];
+        d_logw[base + n] = v;
+    }
+}
+
+}  // namespace nfdpf
+
+using namespace nfdpf;
+
+extern "C" int nfdpf_weight_update_fwd(const float* logw_prev, const float* lki, const float* prior, const float* propose,
+                                       float add_eps, int B, int N, float* logw_out, float* probs_out, float* row_stats,
+                                       void* stream) {
+    NFDPF_REQUIRE(logw_prev && probs_out, "weight_update_fwd: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0, "weight_update_fwd: B and N must be positive (got %d, %d)", B, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 1024) {
+        const int wpb = 8;
+        weight_update_fwd_kernel<false><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(logw_prev, lki, prior, propose, add_eps, B, N,
+                                                                                  logw_out, probs_out, row_stats);
+    } else {
+        weight_update_fwd_kernel<true><<<B, 512, 0, st>>>(logw_prev, lki, prior, propose, add_eps, B, N, logw_out, probs_out,
+                                                         row_stats);
+    }
+    return check_launch("weight_update_fwd");
+}
+
+extern "C" int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw, const float* g_rowsum, const float* probs,
+                                       float add_eps, int B, int N, float* d_logw, void* stream) {
+    NFDPF_REQUIRE(probs && d_logw, "weight_update_bwd: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0, "weight_update_bwd: B and N must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N <= 1024) {
+        const int wpb = 8;
+        weight_update_bwd_kernel<false><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N,
+                                                                                  d_logw);
+    } else {
+        weight_update_bwd_kernel<true><<<B, 512, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N, d_logw);
+    }
+    return check_launch("weight_update_bwd");
+}

@@ -1,0 +1,169 @@
+"""GPU parity tests: CUDA kernels (through the C-ABI) vs the CPU oracle and the reference-generated goldens.
+Tolerances (BASELINE.json north_star): indices bit-exact; everything else fp32 rtol 1e-4 / atol 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+import nfdpf_oracle as O
+from normalizing_flows_dpfs_b200 import ops
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-4, 1e-5
+T = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.asarray(a))
+cu = lambda a: T(a).cuda()
+
+
+def close(a, b, rtol=RTOL, atol=ATOL, what=""):
+    a = T(a).detach().cpu().double().numpy()
+    b = T(b).detach().cpu().double().numpy()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    err = np.abs(a - b) - (atol + rtol * np.abs(b))
+    assert (err <= 0).all(), "%s: max abs diff %.3e (worst excess %.3e)" % (what, np.abs(a - b).max(), err.max())
+
+
+def grad_close(a, b, what=""):
+    """gradients: rtol 1e-4 with atol scaled to the gradient's magnitude (sums of ~1e3..1e6 fp32 terms)."""
+    b_ = T(b).detach().cpu().double().numpy()
+    close(a, b, rtol=RTOL, atol=max(ATOL, 1e-4 * float(np.abs(b_).max())), what=what)
+
+
+# ------------------------------------------------------------------------------------------ soft resampling
+def _soft_case(p, w, off, alpha):
+    N = w.shape[1]
+    markers = torch.linspace(0.0, (N - 1.0) / N, N)
+    pg, wg = cu(p).requires_grad_(), cu(w).requires_grad_()
+    return pg, wg, ops.soft_resample(pg, wg, cu(off), cu(markers), alpha)
+
+
+def test_soft_resample_golden(golden):
+    G = golden("soft_resample")
+    for c in range(int(G["n_cases"])):
+        g = lambda k: G[f"c{c}_{k}"]
+        alpha = float(g("alpha"))
+        pg, wg, (p_res, w_res, idx) = _soft_case(g("particles"), g("probs"), g("offsets"), alpha)
+        assert np.array_equal(idx.cpu().numpy(), g("idx")), f"case {c}: resampled indices must be bit-exact"
+        assert np.array_equal(p_res.detach().cpu().numpy(), g("p_res"))
+        close(w_res, g("w_res"), what=f"case {c} weights")
+        tot = (p_res * cu(g("gp"))).sum()
+        if alpha < 1.0:
+            tot = tot + (w_res * cu(g("gw"))).sum()
+        tot.backward()
+        grad_close(pg.grad, g("d_particles"), f"case {c} d_particles")
+        grad_close(wg.grad, g("d_probs"), f"case {c} d_probs")
+
+
+@pytest.mark.parametrize("B,N,alpha,temp", [(1024, 1024, 0.5, 4.0), (256, 4096, 0.5, 8.0), (512, 100, 0.5, 2.0),
+                                            (37, 1000, 0.7, 3.0), (64, 1024, 1.0, 3.0), (3, 1, 0.5, 1.0)])
+def test_soft_resample_vs_oracle_full_size(B, N, alpha, temp):
+    g = torch.Generator().manual_seed(B + N)
+    w = torch.softmax(torch.randn(B, N, generator=g) * temp, -1)
+    p = torch.randn(B, N, 2, generator=g) * 20
+    off = torch.rand(B, generator=g) / N
+    pg, wg, (p_res, w_res, idx) = _soft_case(p, w, off, alpha)
+    po, wo, io = O.soft_resample(p, w, alpha, off)
+    assert np.array_equal(idx.cpu().numpy(), io.numpy()), "indices must be bit-exact (%d mismatches)" % int(
+        (idx.cpu() != io).sum())
+    assert torch.equal(p_res.detach().cpu(), po)
+    close(w_res, wo, what="weights")
+    # size-independent properties: weights sum to one, indices monotone and inside the row
+    assert torch.allclose(w_res.sum(-1), torch.ones(B, device="cuda"), atol=1e-5)
+    loc = idx - N * torch.arange(B, device="cuda")[:, None]
+    assert bool((loc[:, 1:] >= loc[:, :-1]).all()) and int(loc.min()) >= 0 and int(loc.max()) < N
+
+
+# --------------------------------------------------------------------------------------- weight update / norm
+@pytest.mark.parametrize("B,N", [(3, 40), (64, 1024), (5, 4096), (7, 1), (1024, 1024)])
+def test_weight_update_vs_oracle(B, N):
+    g = torch.Generator().manual_seed(B * 7 + N)
+    lw0 = torch.log_softmax(torch.randn(B, N, generator=g), -1)
+    lki, prior, prop = (torch.randn(B, N, generator=g) * s for s in (3.0, 1.0, 1.0))
+    leaves = [t.clone().requires_grad_() for t in (lw0, lki, prior, prop)]
+    lw_o = leaves[0] + leaves[1] + leaves[2] - leaves[3]
+    pr_o = O.normalize_log_probs(lw_o) + 1e-12
+    gl = [cu(t).requires_grad_() for t in (lw0, lki, prior, prop)]
+    logw, probs, row_sum, ess_inv = ops.weight_update(gl[0], gl[1], gl[2], gl[3], 1e-12)
+    close(logw, lw_o, what="logw")
+    close(probs, pr_o, rtol=1e-4, atol=1e-9, what="probs")
+    close(row_sum, lw_o.sum(-1), rtol=1e-4, atol=1e-3, what="row_sum")
+    close(ess_inv, 1.0 / (pr_o ** 2).sum(-1), what="ess")
+    gp, gs = torch.randn(B, N, generator=g), torch.randn(B, generator=g)
+    ((pr_o * gp).sum() + (lw_o.sum(-1) * gs).sum()).backward()
+    ((probs * cu(gp)).sum() + (row_sum * cu(gs)).sum()).backward()
+    for a, b, n in zip(gl, leaves, ("lw0", "lki", "prior", "propose")):
+        grad_close(a.grad, b.grad, "d_" + n)
+
+
+def test_normalize_golden(golden):
+    G = golden("glue")
+    _, probs, _, _ = ops.weight_update(cu(G["lw"]))
+    close(probs, G["normalize"], rtol=1e-4, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------- coupling stacks
+def test_coupling_golden(golden):
+    """per-particle context exactly as the reference passes it (P,C): kernels <HALF,CP> with C_row = 0."""
+    G = golden("flows")
+    for c in range(int(G["n_cases"])):
+        g = lambda k: G[f"c{c}_{k}"]
+        D, C = int(g("D")), int(g("C"))
+        P = g("x").shape[0]
+        for direction in ("forward", "inverse"):
+            pk = cu(g("params")).requires_grad_()
+            x = cu(g("x")).reshape(1, P, D).requires_grad_()
+            ctx = cu(g("ctx")).reshape(1, P, C).requires_grad_() if C else None
+            y, ld = ops.coupling_stack(pk, x, None, ctx, 2, direction == "inverse")
+            close(y.reshape(P, D), g(f"{direction}_y"), what=f"case {c} {direction} y")
+            close(ld.reshape(P), g(f"{direction}_ld"), what=f"case {c} {direction} log_det")
+            ((y.reshape(P, D) * cu(g(f"{direction}_gy"))).sum() + (ld.reshape(P) * cu(g(f"{direction}_gl"))).sum()).backward()
+            grad_close(x.grad.reshape(P, D), g(f"{direction}_dx"), f"case {c} {direction} dx")
+            grad_close(pk.grad, g(f"{direction}_dW"), f"case {c} {direction} dW")
+            if C:
+                grad_close(ctx.grad.reshape(P, C), g(f"{direction}_dctx"), f"case {c} {direction} dctx")
+
+
+@pytest.mark.parametrize("D,C_row,C_part,B,N,inverse", [(2, 4, 0, 5, 300, True), (2, 4, 0, 5, 300, False), (2, 36, 0, 4, 1024, True),
+                                                        (32, 0, 32, 3, 200, False), (2, 0, 0, 2, 64, False), (4, 2, 3, 3, 129, True),
+                                                        (32, 5, 0, 2, 100, False)])
+def test_coupling_row_context_vs_oracle(D, C_row, C_part, B, N, inverse):
+    """row-constant context hoisted into the layer-1 bias == the reference's materialised (P,C) concat."""
+    g = torch.Generator().manual_seed(D * 1000 + C_row * 10 + C_part + int(inverse))
+    C = C_row + C_part
+    pk = O.init_stack(g, D, C, std=0.3, bias_std=0.1)
+    x = torch.randn(B, N, D, generator=g) * 1.5
+    rc = torch.randn(B, C_row, generator=g) if C_row else None
+    pc = torch.randn(B, N, C_part, generator=g) if C_part else None
+    gy, gl = torch.randn(B, N, D, generator=g), torch.randn(B, N, generator=g)
+    # oracle: materialise the context like model/models.py:309-315 does
+    lo = [t.clone().requires_grad_() if t is not None else None for t in (pk, x, rc, pc)]
+    parts = ([lo[2][:, None, :].expand(B, N, C_row)] if C_row else []) + ([lo[3]] if C_part else [])
+    ctx = torch.cat(parts, -1).reshape(B * N, C) if parts else None
+    fn = O.stack_inverse if inverse else O.stack_forward
+    yo, ldo = fn(lo[1].reshape(B * N, D), ctx, O.unpack_stack(lo[0], D, C))
+    ((yo.reshape(B, N, D) * gy).sum() + (ldo.reshape(B, N) * gl).sum()).backward()
+    gt = [cu(t).requires_grad_() if t is not None else None for t in (pk, x, rc, pc)]
+    y, ld = ops.coupling_stack(gt[0], gt[1], gt[2], gt[3], 2, inverse)
+    close(y, yo.reshape(B, N, D), what="y")
+    close(ld, ldo.reshape(B, N), what="log_det")
+    ((y * cu(gy)).sum() + (ld * cu(gl)).sum()).backward()
+    for a, b, n in zip(gt, lo, ("dW", "dx", "d_row_ctx", "d_part_ctx")):
+        if a is not None:
+            grad_close(a.grad, b.grad, n)
+
+
+def test_coupling_roundtrip_full_size():
+    """size-independent property at BASELINE shape (B=N=1024): inverse(forward(x)) == x, log-dets cancel."""
+    g = torch.Generator().manual_seed(5)
+    B = N = 1024
+    pk = cu(O.init_stack(g, 2, 36, std=0.2, bias_std=0.1))
+    x = cu(torch.randn(B, N, 2, generator=g) * 2)
+    rc = cu(torch.randn(B, 36, generator=g))
+    z, ld_f = ops.coupling_stack(pk, x, rc, None, 2, False)
+    xr, ld_i = ops.coupling_stack(pk, z, rc, None, 2, True)
+    close(xr, x, rtol=1e-4, atol=1e-4, what="roundtrip")
+    close(ld_i, -ld_f, rtol=1e-4, atol=1e-5, what="log-det antisymmetry")
+
+
+def test_unsupported_shape_raises():
+    pk = torch.zeros(4 * 2 * (8 * (3 + 0) + 8 + 64 + 8 + 3 * 8 + 3), device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.coupling_stack(pk, torch.zeros(1, 4, 6, device="cuda"), None, None, 2, False)
