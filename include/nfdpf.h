@@ -85,6 +85,30 @@ int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C
                        const float* g_ld, float* d_x, float* d_row_ctx, float* d_part_ctx, float* d_packed,
                        void* workspace, void* stream);
 
+/* ---- (K2) measurement log-likelihood fused with the log-weight update and normalisation ----------------
+ * mode 0: measurement_model_Gaussian, model/models.py:237-254, with MultivariateNormal(loc = p0, cov = p1^2 I)
+ *         (DPFs.py:84-86 uses p0 = 1, p1 = 10);  mode 1: measurement_model_cosine_distance, models.py:206-219;
+ * mode 2: measurement_model_cnf, models.py:256-278: conditional RealNVP (D = C = hidden = 32, packed stack
+ *         cnf_packed, n_flows) with prior N(p0, p1^2 I) (DPFs.py:75-76: p0 = 0, p1 = 2.5).
+ * pe_packed: particle encoder Linear(2,16)-ReLU-Linear(16,32)-ReLU-Linear(32,32) (models.py:130-139) in
+ * state_dict order (1648 floats).  enc (B,hidden) observation encodings, particles (B,N,2).
+ * lki (B,N) = log-likelihood minus its row max (modes 0,2); argmax (B,) int32 = position of that max (needed
+ * by the backward; may be NULL if no backward will follow).
+ * If logw_prev != NULL the weight update of nfdpf_weight_update_fwd is fused in (prior / propose may be NULL):
+ * logw_out (B,N) (may be NULL), probs_out (B,N), row_stats (B,2). */
+int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
+                      const float* enc, const float* particles, int B, int N, int hidden, const float* logw_prev,
+                      const float* prior, const float* propose, float add_eps, float* lki, int32_t* argmax,
+                      float* logw_out, float* probs_out, float* row_stats, void* stream);
+/* backward of lki w.r.t. particles (B,N,2), enc (B,hidden; may be NULL: detached), particle-encoder and cnf
+ * parameters (d_pe / d_cnf ACCUMULATED into, deterministic).  g_lki (B,N) is the total gradient reaching lki
+ * (the caller adds the weight-update gradient from nfdpf_weight_update_bwd when the update was fused). */
+int64_t nfdpf_measure_bwd_workspace(int mode, int n_flows, int B, int N);
+int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
+                      const float* enc, const float* particles, int B, int N, int hidden, const float* g_lki,
+                      const int32_t* argmax, float* d_particles, float* d_enc, float* d_pe, float* d_cnf,
+                      void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,10 @@ namespace nfdpf {
 
 constexpr int H = NFDPF_HIDDEN;  // 8
 
+int bwd_grid(int B);  // persistent grid of the backward kernels (also sizes the partial-gradient workspace)
+// d_packed[i] += sum_c partials[c][i], fixed order, fp64 accumulate (coupling.cu)
+int launch_reduce_partials(const float* partials, int n_parts, int n_params, float* d_packed, cudaStream_t st);
+
 // Aligned shared-memory image of one FCNN (row-context columns of W1 excluded; they live in s_w1r).
 template <int HALF, int CP>
 struct Lay {
@@ -184,5 +188,140 @@ __device__ __forceinline__ void stage_fwd(const float* img_t, const float* img_s
         else      { v[i] = (v[i] - t[i]) * expf(-s[i]); ld -= s[i]; }
     }
 }
+
+
+// ---- CTA-wide weight-gradient accumulation through a transposed shared-memory tile --------------------------
+constexpr int TP = 128;           // particles per CTA batch (= threads per CTA)
+constexpr int TS = TP + 1;        // tile row stride (conflict-free for lane-distinct rows)
+
+// acc[e] += sum_p tile[ra(e)][p] * tile[rb(e)][p] for e < nout; entry e is owned by thread e % TP (no atomics,
+// fixed summation order).  Entries [row_lo, row_lo+8) are additionally added to row_acc (may be null).
+__device__ __forceinline__ void tile_accumulate(const int* __restrict__ s_tab, int nout, const float* __restrict__ s_tile,
+                                                float* __restrict__ acc, int row_lo, float* __restrict__ row_acc) {
+    for (int e = threadIdx.x; e < nout; e += TP) {
+        const int tab = s_tab[e];
+        const float* ra = s_tile + (tab & 0xffff) * TS;
+        const float* rb = s_tile + (tab >> 16) * TS;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+        for (int p = 0; p < TP; p += 4) {
+            a0 = fmaf(ra[p], rb[p], a0);
+            a1 = fmaf(ra[p + 1], rb[p + 1], a1);
+            a2 = fmaf(ra[p + 2], rb[p + 2], a2);
+            a3 = fmaf(ra[p + 3], rb[p + 3], a3);
+        }
+        const float a = (a0 + a1) + (a2 + a3);
+        acc[e] += a;
+        if (row_acc && e >= row_lo && e < row_lo + H) row_acc[e - row_lo] += a;
+    }
+}
+
+// ---- backward of one coupling stage ---------------------------------------------------------------------
+// Tile rows (one column per particle of the batch):
+template <int HALF, int CP>
+struct Rows {
+    static constexpr int ONE = 0, C = 1, PC = C + HALF, H1 = PC + CP, H2 = H1 + H, D1 = H2 + H, D2 = D1 + H, DO = D2 + H,
+                         COUNT = DO + HALF;
+    // per-FCNN gradient outputs, in packed order minus the row-context columns
+    static constexpr int NOUT = H * (HALF + CP) + H + H * H + H + HALF * H + HALF;
+};
+
+// entry e of the output table: (tile row of the delta, tile row of the activation, offset inside the packed FCNN)
+template <int HALF, int CP>
+__device__ void out_entry(int e, int C_row, int& ra, int& rb, int& poff) {
+    using R = Rows<HALF, CP>;
+    const int fin = HALF + C_row + CP;
+    int o = e;
+    if (o < H * (HALF + CP)) {
+        const int k = o / (HALF + CP), i = o % (HALF + CP);
+        ra = R::D1 + k;
+        rb = i < HALF ? R::C + i : R::PC + (i - HALF);
+        poff = k * fin + (i < HALF ? i : C_row + i);
+        return;
+    }
+    o -= H * (HALF + CP);
+    int base = H * fin;
+    if (o < H) { ra = R::D1 + o; rb = R::ONE; poff = base + o; return; }
+    o -= H; base += H;
+    if (o < H * H) { ra = R::D2 + o / H; rb = R::H1 + o % H; poff = base + o; return; }
+    o -= H * H; base += H * H;
+    if (o < H) { ra = R::D2 + o; rb = R::ONE; poff = base + o; return; }
+    o -= H; base += H;
+    if (o < HALF * H) { ra = R::DO + o / H; rb = R::H2 + o % H; poff = base + o; return; }
+    o -= HALF * H; base += HALF * H;
+    ra = R::DO + o; rb = R::ONE; poff = base + o;
+}
+
+template <int HALF, int CP>
+struct BwdSmem {
+    using L = Lay<HALF, CP>;
+    using R = Rows<HALF, CP>;
+    static size_t bytes(int n_fcnn, int C_row) {
+        size_t fl = (size_t)n_fcnn * L::SIZE + n_fcnn * H + (size_t)n_fcnn * H * C_row  // images, hb, w1r
+                    + (size_t)R::COUNT * TS                                              // tile
+                    + (size_t)n_fcnn * R::NOUT                                           // acc
+                    + (size_t)n_fcnn * H * C_row                                         // accR
+                    + n_fcnn * H                                                         // d1row
+                    + C_row + 4;                                                         // ctx
+        return fl * sizeof(float) + (size_t)R::NOUT * sizeof(int);                       // + table
+    }
+};
+
+// Backward of one stage for the particle held by this thread, plus the CTA-wide weight-gradient accumulation.
+// On entry (c, v) are the stage's OUTPUT values with gradients (gc, gv); on exit v / gv are the stage's input.
+template <int HALF, int CP, bool INV>
+__device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s, int f_t,
+                                          bool live, const float (&c)[HALF], float (&gc)[HALF], const float* pc, float* gpc,
+                                          float (&v)[HALF], float (&gv)[HALF], float gld, float* s_tile, float* s_acc,
+                                          float* s_d1row, const int* s_tab) {
+    using R = Rows<HALF, CP>;
+    const int tid = threadIdx.x;
+    float h1t[H], h2t[H], h1s[H], h2s[H], t[HALF], s[HALF], dt[HALF], ds[HALF];
+    fcnn_fwd<HALF, CP>(img_t, hb_t, c, pc, h1t, h2t, t);
+    fcnn_fwd<HALF, CP>(img_s, hb_s, c, pc, h1s, h2s, s);
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) {
+        if (!INV) {  // out = t + in*e^s
+            const float es = expf(s[i]);
+            const float vin = (v[i] - t[i]) * expf(-s[i]);
+            dt[i] = gv[i];
+            ds[i] = fmaf(gv[i] * vin, es, gld);
+            gv[i] = gv[i] * es;
+            v[i] = vin;
+        } else {     // out = (in - t) e^{-s}
+            const float es = expf(s[i]);
+            const float gin = gv[i] * expf(-s[i]);
+            dt[i] = -gin;
+            ds[i] = -fmaf(gv[i], v[i], gld);
+            v[i] = fmaf(v[i], es, t[i]);
+            gv[i] = gin;
+        }
+        if (!live) { dt[i] = 0.f; ds[i] = 0.f; }
+    }
+    // conditioning half is shared by both nets of the stage: stage it once
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) s_tile[(R::C + i) * TS + tid] = c[i];
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+        float d1[H], d2[H];
+        if (net == 0) fcnn_bwd<HALF, CP>(img_t, dt, h1t, h2t, d1, d2, gc, gpc);
+        else          fcnn_bwd<HALF, CP>(img_s, ds, h1s, h2s, d1, d2, gc, gpc);
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            s_tile[(R::H1 + k) * TS + tid] = net == 0 ? h1t[k] : h1s[k];
+            s_tile[(R::H2 + k) * TS + tid] = net == 0 ? h2t[k] : h2s[k];
+            s_tile[(R::D1 + k) * TS + tid] = d1[k];
+            s_tile[(R::D2 + k) * TS + tid] = d2[k];
+        }
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) s_tile[(R::DO + i) * TS + tid] = net == 0 ? dt[i] : ds[i];
+        __syncthreads();
+        const int f = f_t + net;
+        // b1 slots (first after the W1 block) double as the per-trajectory layer-1 delta sums (row-context hoist)
+        tile_accumulate(s_tab, R::NOUT, s_tile, s_acc + f * R::NOUT, H * (HALF + CP), s_d1row + f * H);
+        __syncthreads();
+    }
+}
+
 
 }  // namespace nfdpf

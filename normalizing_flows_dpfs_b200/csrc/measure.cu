@@ -1,0 +1,446 @@
+// (K2) Measurement log-likelihood fused with the log-weight update and the softmax normalisation.
+// One CTA per trajectory, one thread per particle:
+//   particle encoder MLP 2-16-32-32 (model/models.py:130-139)
+//   -> Gaussian (models.py:237-254) | cosine (206-219) | conditional-RealNVP (256-278, D=32, C=32) log-likelihood
+//   -> row max shift -> logw = logw_prev + lki + prior - propose (DPFs.py:187) -> softmax + eps, ESS term, sum logw.
+// The reference materialises the (B,N,32) encodings, the repeated (B,N,32) observation encodings and, for CRNVP,
+// eight (P,48) concatenations; here the only HBM traffic is particles in, (B,N) vectors out.
+#include "coupling.cuh"
+
+namespace nfdpf {
+
+enum { MODE_GAUSS = 0, MODE_COS = 1, MODE_CNF = 2 };
+constexpr int HID = 32;                      // encoding width (args.hiddensize)
+// packed particle encoder (state_dict order 0.weight,0.bias,2.weight,2.bias,4.weight,4.bias)
+constexpr int PE_W1 = 0, PE_B1 = 32, PE_W2 = 48, PE_B2 = 560, PE_W3 = 592, PE_B3 = 1616, PE_SIZE = 1648;
+using LC = Lay<16, 32>;
+using RC = Rows<16, 32>;
+
+__device__ __forceinline__ void pe_fwd(const float* __restrict__ w, float x0, float x1, float (&a1)[16], float (&a2)[32],
+                                       float (&e)[32]) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a1[k] = fmaxf(fmaf(w[PE_W1 + 2 * k + 1], x1, fmaf(w[PE_W1 + 2 * k], x0, w[PE_B1 + k])), 0.f);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float a = w[PE_B2 + j];
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(w + PE_W2 + j * 16 + k);
+            a = fmaf(q.x, a1[k], a); a = fmaf(q.y, a1[k + 1], a); a = fmaf(q.z, a1[k + 2], a); a = fmaf(q.w, a1[k + 3], a);
+        }
+        a2[j] = fmaxf(a, 0.f);
+    }
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        float a = w[PE_B3 + o];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(w + PE_W3 + o * 32 + j);
+            a = fmaf(q.x, a2[j], a); a = fmaf(q.y, a2[j + 1], a); a = fmaf(q.z, a2[j + 2], a); a = fmaf(q.w, a2[j + 3], a);
+        }
+        e[o] = a;
+    }
+}
+
+// log-likelihood of one particle given its encoding e; for MODE_CNF also returns z (= [lo|up]) for the backward.
+template <int MODE>
+__device__ __forceinline__ float loglik(const float (&e)[32], const float* __restrict__ s_enc, float p0, float p1,
+                                        const float* s_img, const float* s_hb, int n_flows, float (&lo)[16], float (&up)[16]) {
+    if (MODE == MODE_GAUSS) {   // MVN(loc = p0, cov = p1^2 I).log_prob(enc - e)
+        float m = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { const float u = s_enc[k] - e[k] - p0; m = fmaf(u, u, m); }
+        return -0.5f * m / (p1 * p1) - 32.0f * (logf(p1) + 0.91893853320467274f);
+    } else if (MODE == MODE_COS) {  // log(1 / (1e-7 + 1 - cos(enc, e))), F.normalize eps 1e-12
+        float ne = 0.f, dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { ne = fmaf(e[k], e[k], ne); dot = fmaf(s_enc[k], e[k], dot); }
+        const float cosd = 1.0f - dot / (fmaxf(sqrtf(ne), 1e-12f) * s_enc[32]);
+        return -logf(1e-7f + cosd);
+    } else {                    // conditional RealNVP: x = enc (row constant), context = e; prior N(p0, p1^2 I)
+        float ld = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { lo[i] = s_enc[i]; up[i] = s_enc[16 + i]; }
+#pragma unroll 1
+        for (int f = 0; f < n_flows; ++f) {
+            const float* im = s_img + 4 * f * LC::SIZE;
+            const float* hb = s_hb + 4 * f * H;
+            stage_fwd<16, 32, false>(im, im + LC::SIZE, hb, hb + H, lo, e, up, ld);
+            stage_fwd<16, 32, false>(im + 2 * LC::SIZE, im + 3 * LC::SIZE, hb + 2 * H, hb + 3 * H, up, e, lo, ld);
+        }
+        float m = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float a = lo[i] - p0, b = up[i] - p0; m = fmaf(a, a, m); m = fmaf(b, b, m); }
+        return -0.5f * m / (p1 * p1) - 32.0f * (logf(p1) + 0.91893853320467274f) + ld;
+    }
+}
+
+__device__ void load_enc(const float* __restrict__ enc_row, float* s_enc) {  // s_enc[32] = ||enc|| clamped (cos mode)
+    if (threadIdx.x < 32) {
+        const float v = enc_row[threadIdx.x];
+        s_enc[threadIdx.x] = v;
+        const float n2 = warp_sum(v * v);
+        if (threadIdx.x == 0) s_enc[32] = fmaxf(sqrtf(n2), 1e-12f);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TP)
+measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, int n_flows, float p0, float p1,
+                   const float* __restrict__ enc, const float* __restrict__ particles, int N, const float* __restrict__ lw0,
+                   const float* __restrict__ prior, const float* __restrict__ propose, float add_eps, float* __restrict__ lki,
+                   int* __restrict__ argmax, float* __restrict__ logw_out, float* __restrict__ probs_out,
+                   float* __restrict__ row_stats) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_red[33];
+    __shared__ int s_redi[33];
+    const int tid = threadIdx.x, b = blockIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
+    float* s_pe = smem;                       // [1648]
+    float* s_enc = s_pe + PE_SIZE;            // [36]
+    float* s_img = s_enc + 36;                // [n_fcnn][LC::SIZE]
+    float* s_hb = s_img + n_fcnn * LC::SIZE;  // [n_fcnn][8]
+    float* s_ll = s_hb + n_fcnn * H;          // [N]
+    for (int e = tid; e < PE_SIZE; e += TP) s_pe[e] = pe[e];
+    if (MODE == MODE_CNF) {
+        const int pf = packed_fcnn_size(16, 32);
+        for (int f = 0; f < n_fcnn; ++f) load_fcnn_image<16, 32>(cnf + (size_t)f * pf, 0, s_img + f * LC::SIZE, nullptr, tid, TP);
+    }
+    load_enc(enc + (size_t)b * HID, s_enc);
+    __syncthreads();
+    if (MODE == MODE_CNF) hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int n = tid; n < N; n += TP) {
+        const float2 x = *reinterpret_cast<const float2*>(particles + ((size_t)b * N + n) * 2);
+        float a1[16], a2[32], e[32], lo[16], up[16];
+        pe_fwd(s_pe, x.x, x.y, a1, a2, e);
+        const float ll = loglik<MODE>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
+        s_ll[n] = ll;
+        mx = fmaxf(mx, ll);
+    }
+    float shift = 0.f;
+    if (MODE != MODE_COS) {      // likelihood - likelihood.max(dim=-1), models.py:252, 276
+        shift = block_allreduce(mx, s_red, OpMax(), -INFINITY);
+        int am = 0x7fffffff;
+        for (int n = tid; n < N; n += TP) if (s_ll[n] == shift) am = min(am, n);
+        am = block_allreduce(am, s_redi, [] __device__(int a, int c) { return min(a, c); }, 0x7fffffff);
+        if (tid == 0 && argmax) argmax[b] = am;
+    } else {
+        __syncthreads();
+        if (tid == 0 && argmax) argmax[b] = -1;
+    }
+    const size_t base = (size_t)b * N;
+    if (!lw0) {
+        for (int n = tid; n < N; n += TP) lki[base + n] = s_ll[n] - shift;
+        return;
+    }
+    // fused weight update + normalisation (DPFs.py:187-192)
+    float vmx = -INFINITY, sl = 0.f;
+    for (int n = tid; n < N; n += TP) {
+        const float l = s_ll[n] - shift;
+        lki[base + n] = l;
+        float v = lw0[base + n] + l;
+        if (prior) v += prior[base + n];
+        if (propose) v -= propose[base + n];
+        if (logw_out) logw_out[base + n] = v;
+        s_ll[n] = v;
+        vmx = fmaxf(vmx, v);
+        sl += v;
+    }
+    vmx = block_allreduce(vmx, s_red, OpMax(), -INFINITY);
+    sl = block_allreduce(sl, s_red, OpSum(), 0.f);
+    float se = 0.f;
+    for (int n = tid; n < N; n += TP) { const float ex = expf(s_ll[n] - vmx); s_ll[n] = ex; se += ex; }
+    se = block_allreduce(se, s_red, OpSum(), 0.f);
+    float s2 = 0.f;
+    for (int n = tid; n < N; n += TP) { const float p = __fdiv_rn(s_ll[n], se) + add_eps; probs_out[base + n] = p; s2 = fmaf(p, p, s2); }
+    s2 = block_allreduce(s2, s_red, OpSum(), 0.f);
+    if (tid == 0 && row_stats) { row_stats[2 * b] = sl; row_stats[2 * b + 1] = 1.0f / s2; }
+}
+
+// ----------------------------------------------------------------------------------------------- backward
+// particle-encoder tile rows / outputs
+struct PR {
+    static constexpr int ONE = 0, X = 1, A1 = 3, A2 = 19, D1 = 51, D2 = 67, D3 = 99, COUNT = 131;
+};
+__device__ void pe_entry(int e, int& ra, int& rb) {  // e in packed PE order
+    if (e < PE_B1) { ra = PR::D1 + e / 2; rb = PR::X + e % 2; return; }
+    if (e < PE_W2) { ra = PR::D1 + (e - PE_B1); rb = PR::ONE; return; }
+    if (e < PE_B2) { ra = PR::D2 + (e - PE_W2) / 16; rb = PR::A1 + (e - PE_W2) % 16; return; }
+    if (e < PE_W3) { ra = PR::D2 + (e - PE_B2); rb = PR::ONE; return; }
+    if (e < PE_B3) { ra = PR::D3 + (e - PE_W3) / 32; rb = PR::A2 + (e - PE_W3) % 32; return; }
+    ra = PR::D3 + (e - PE_B3); rb = PR::ONE;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TP)
+measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, int n_flows, float p0, float p1,
+                   const float* __restrict__ enc, const float* __restrict__ particles, int B, int N,
+                   const float* __restrict__ g_lki, const int* __restrict__ argmax, float* __restrict__ d_particles,
+                   float* __restrict__ d_enc, float* __restrict__ part_pe, float* __restrict__ part_cnf) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_red[33];
+    const int tid = threadIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
+    constexpr int TROWS = MODE == MODE_CNF ? (RC::COUNT > PR::COUNT ? RC::COUNT : PR::COUNT) : PR::COUNT;
+    float* s_pe = smem;
+    float* s_enc = s_pe + PE_SIZE;
+    float* s_img = s_enc + 36;
+    float* s_hb = s_img + n_fcnn * LC::SIZE;
+    float* s_tile = s_hb + n_fcnn * H;                       // [TROWS][TS], PE and CNF phases alias
+    float* s_accpe = s_tile + TROWS * TS;                    // [1648]
+    float* s_acccnf = s_accpe + PE_SIZE;                     // [n_fcnn][RC::NOUT]
+    float* s_d1row = s_acccnf + n_fcnn * RC::NOUT;           // [n_fcnn][8] (unused sums; C_row = 0)
+    float* s_denc = s_d1row + n_fcnn * H + 4;                // [32]
+    int* s_tabpe = reinterpret_cast<int*>(s_denc + 32);      // [1648]
+    int* s_tabcnf = s_tabpe + PE_SIZE;                       // [RC::NOUT]
+    for (int e = tid; e < PE_SIZE; e += TP) {
+        s_pe[e] = pe[e];
+        s_accpe[e] = 0.f;
+        int ra, rb;
+        pe_entry(e, ra, rb);
+        s_tabpe[e] = ra | (rb << 16);
+    }
+    if (MODE == MODE_CNF) {
+        const int pf = packed_fcnn_size(16, 32);
+        for (int f = 0; f < n_fcnn; ++f) load_fcnn_image<16, 32>(cnf + (size_t)f * pf, 0, s_img + f * LC::SIZE, nullptr, tid, TP);
+        for (int e = tid; e < RC::NOUT; e += TP) {
+            int ra, rb, poff;
+            out_entry<16, 32>(e, 0, ra, rb, poff);
+            s_tabcnf[e] = ra | (rb << 16);
+        }
+        for (int e = tid; e < n_fcnn * RC::NOUT; e += TP) s_acccnf[e] = 0.f;
+        for (int e = tid; e < n_fcnn * H; e += TP) s_d1row[e] = 0.f;
+    }
+    __syncthreads();
+    if (MODE == MODE_CNF) hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        load_enc(enc + (size_t)b * HID, s_enc);
+        const size_t base = (size_t)b * N;
+        // row-max shift: d ll[n] = g[n] - [n == argmax] * sum_m g[m]
+        float gs = 0.f;
+        if (MODE != MODE_COS) {
+            for (int n = tid; n < N; n += TP) gs += g_lki[base + n];
+            gs = block_allreduce(gs, s_red, OpSum(), 0.f);
+        }
+        const int am = MODE != MODE_COS ? argmax[b] : -1;
+        float denc[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) denc[k] = 0.f;
+        __syncthreads();
+        for (int n0 = 0; n0 < N; n0 += TP) {
+            const int n = n0 + tid;
+            const bool live = n < N;
+            const size_t p = base + (live ? n : 0);
+            const float2 x = *reinterpret_cast<const float2*>(particles + p * 2);
+            float g = live ? g_lki[p] : 0.f;
+            if (live && n == am) g -= gs;
+            float a1[16], a2[32], e[32], de[32];
+            pe_fwd(s_pe, x.x, x.y, a1, a2, e);
+            if (MODE == MODE_GAUSS) {
+                const float c = g / (p1 * p1);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { de[k] = c * (s_enc[k] - e[k] - p0); denc[k] -= de[k]; }
+            } else if (MODE == MODE_COS) {
+                float ne = 0.f, dot = 0.f;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { ne = fmaf(e[k], e[k], ne); dot = fmaf(s_enc[k], e[k], dot); }
+                const float nrm = fmaxf(sqrtf(ne), 1e-12f), nenc = s_enc[32];
+                const float ab = dot / (nrm * nenc);
+                const float c = g / (1e-7f + 1.0f - ab);     // d lki / d(ab)
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float ah = s_enc[k] / nenc, bh = e[k] / nrm;
+                    de[k] = c * (ah - ab * bh) / nrm;
+                    denc[k] += c * (bh - ab * ah) / nenc;
+                }
+            } else {
+                float lo[16], up[16], glo[16], gup[16];
+                loglik<MODE_CNF>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
+                const float c = -g / (p1 * p1);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { glo[i] = c * (lo[i] - p0); gup[i] = c * (up[i] - p0); }
+#pragma unroll
+                for (int k = 0; k < 32; ++k) { de[k] = 0.f; s_tile[(RC::PC + k) * TS + tid] = e[k]; }
+                s_tile[RC::ONE * TS + tid] = 1.0f;
+#pragma unroll 1
+                for (int f = n_flows - 1; f >= 0; --f) {
+                    const float* im = s_img + 4 * f * LC::SIZE;
+                    const float* hb = s_hb + 4 * f * H;
+                    stage_bwd<16, 32, false>(im + 2 * LC::SIZE, im + 3 * LC::SIZE, hb + 2 * H, hb + 3 * H, 4 * f + 2, live, up, gup, e, de,
+                                             lo, glo, g, s_tile, s_acccnf, s_d1row, s_tabcnf);
+                    stage_bwd<16, 32, false>(im, im + LC::SIZE, hb, hb + H, 4 * f, live, lo, glo, e, de, up, gup, g, s_tile, s_acccnf,
+                                             s_d1row, s_tabcnf);
+                }
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { denc[i] += glo[i]; denc[16 + i] += gup[i]; }
+                }
+            }
+            // particle-encoder backward
+            float d2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) d2[j] = 0.f;
+#pragma unroll
+            for (int o = 0; o < 32; ++o) {
+                if (!live) de[o] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W3 + o * 32 + j);
+                    d2[j] = fmaf(q.x, de[o], d2[j]); d2[j + 1] = fmaf(q.y, de[o], d2[j + 1]);
+                    d2[j + 2] = fmaf(q.z, de[o], d2[j + 2]); d2[j + 3] = fmaf(q.w, de[o], d2[j + 3]);
+                }
+            }
+            float d1[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) d1[k] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                d2[j] = a2[j] > 0.f ? d2[j] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W2 + j * 16 + k);
+                    d1[k] = fmaf(q.x, d2[j], d1[k]); d1[k + 1] = fmaf(q.y, d2[j], d1[k + 1]);
+                    d1[k + 2] = fmaf(q.z, d2[j], d1[k + 2]); d1[k + 3] = fmaf(q.w, d2[j], d1[k + 3]);
+                }
+            }
+            float dx0 = 0.f, dx1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                d1[k] = a1[k] > 0.f ? d1[k] : 0.f;
+                dx0 = fmaf(s_pe[PE_W1 + 2 * k], d1[k], dx0);
+                dx1 = fmaf(s_pe[PE_W1 + 2 * k + 1], d1[k], dx1);
+            }
+            if (live) *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
+            // stage the PE tile (aliases the CNF tile: all CNF accumulation of this batch ended with a barrier)
+            s_tile[PR::ONE * TS + tid] = 1.0f;
+            s_tile[(PR::X + 0) * TS + tid] = x.x;
+            s_tile[(PR::X + 1) * TS + tid] = x.y;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { s_tile[(PR::A1 + k) * TS + tid] = a1[k]; s_tile[(PR::D1 + k) * TS + tid] = d1[k]; }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                s_tile[(PR::A2 + j) * TS + tid] = a2[j];
+                s_tile[(PR::D2 + j) * TS + tid] = d2[j];
+                s_tile[(PR::D3 + j) * TS + tid] = de[j];
+            }
+            __syncthreads();
+            tile_accumulate(s_tabpe, PE_SIZE, s_tile, s_accpe, 0, nullptr);
+            __syncthreads();
+        }
+        // d_enc[b][k] = sum over the row's particles (deterministic: through the tile)
+        if (d_enc) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) s_tile[k * TS + tid] = denc[k];
+            __syncthreads();
+            if (tid < 32) {
+                float a = 0.f;
+                for (int p = 0; p < TP; ++p) a += s_tile[tid * TS + p];
+                d_enc[(size_t)b * HID + tid] = a;
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < PE_SIZE; e += TP) part_pe[(size_t)blockIdx.x * PE_SIZE + e] = s_accpe[e];
+    if (MODE == MODE_CNF) {
+        const int pf = packed_fcnn_size(16, 32);
+        float* out = part_cnf + (size_t)blockIdx.x * n_fcnn * pf;
+        for (int e = tid; e < n_fcnn * RC::NOUT; e += TP) {
+            int ra, rb, poff;
+            out_entry<16, 32>(e % RC::NOUT, 0, ra, rb, poff);
+            out[(size_t)(e / RC::NOUT) * pf + poff] = s_acccnf[e];
+        }
+    }
+}
+
+static size_t fwd_smem(int mode, int n_flows, int N) {
+    const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
+    return ((size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + N) * sizeof(float);
+}
+static size_t bwd_smem(int mode, int n_flows) {
+    const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
+    const int trows = mode == MODE_CNF ? (RC::COUNT > PR::COUNT ? RC::COUNT : PR::COUNT) : PR::COUNT;
+    size_t fl = (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + (size_t)trows * TS + PE_SIZE + (size_t)n_fcnn * RC::NOUT +
+                n_fcnn * H + 4 + 32;
+    return fl * sizeof(float) + ((size_t)PE_SIZE + (mode == MODE_CNF ? RC::NOUT : 0)) * sizeof(int);
+}
+
+template <int MODE>
+static int launch_measure_fwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,
+                              int B, int N, const float* lw0, const float* prior, const float* propose, float add_eps, float* lki,
+                              int* argmax, float* logw_out, float* probs_out, float* row_stats, cudaStream_t st) {
+    const size_t smem = fwd_smem(MODE, n_flows, N);
+    if (smem > 220 * 1024) { set_error("measure_fwd: N=%d too large for the shared-memory row buffer", N); return NFDPF_ERR_UNSUPPORTED; }
+    auto kern = measure_fwd_kernel<MODE>;
+    if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, N, lw0, prior, propose, add_eps, lki, argmax, logw_out, probs_out,
+                              row_stats);
+    return check_launch("measure_fwd");
+}
+
+template <int MODE>
+static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,
+                              int B, int N, const float* g_lki, const int* argmax, float* d_particles, float* d_enc, float* d_pe,
+                              float* d_cnf, void* workspace, cudaStream_t st) {
+    const size_t smem = bwd_smem(MODE, n_flows);
+    auto kern = measure_bwd_kernel<MODE>;
+    if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = bwd_grid(B);
+    float* part_pe = (float*)workspace;
+    float* part_cnf = part_pe + (size_t)grid * PE_SIZE;
+    kern<<<grid, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, part_cnf);
+    int rc = check_launch("measure_bwd");
+    if (rc) return rc;
+    rc = launch_reduce_partials(part_pe, grid, PE_SIZE, d_pe, st);
+    if (rc) return rc;
+    if (MODE == MODE_CNF) rc = launch_reduce_partials(part_cnf, grid, 4 * n_flows * packed_fcnn_size(16, 32), d_cnf, st);
+    return rc;
+}
+
+}  // namespace nfdpf
+
+using namespace nfdpf;
+
+extern "C" int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
+                                 const float* enc, const float* particles, int B, int N, int hidden, const float* logw_prev,
+                                 const float* prior, const float* propose, float add_eps, float* lki, int32_t* argmax,
+                                 float* logw_out, float* probs_out, float* row_stats, void* stream) {
+    NFDPF_REQUIRE(pe_packed && enc && particles && lki, "measure_fwd: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0, "measure_fwd: B and N must be positive");
+    NFDPF_REQUIRE(mode >= 0 && mode <= 2, "measure_fwd: mode must be 0 (gaussian), 1 (cos) or 2 (CRNVP), got %d", mode);
+    NFDPF_REQUIRE(mode != MODE_CNF || (cnf_packed && n_flows >= 1 && n_flows <= 4), "measure_fwd: CRNVP needs a packed stack, 1..4 flows");
+    NFDPF_REQUIRE(!logw_prev || probs_out, "measure_fwd: fused update needs probs_out");
+    if (hidden != HID) { set_error("measure_fwd: kernels are built for hiddensize 32 (got %d)", hidden); return NFDPF_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, logw_prev, prior, propose, add_eps, lki, argmax, logw_out, probs_out, row_stats, st
+    if (mode == MODE_GAUSS) return launch_measure_fwd<MODE_GAUSS>(ARGS);
+    if (mode == MODE_COS) return launch_measure_fwd<MODE_COS>(ARGS);
+    return launch_measure_fwd<MODE_CNF>(ARGS);
+#undef ARGS
+}
+
+extern "C" int64_t nfdpf_measure_bwd_workspace(int mode, int n_flows, int B, int N) {
+    (void)N;
+    if (B < 1) return 0;
+    int64_t per = PE_SIZE + (mode == MODE_CNF ? 4 * n_flows * packed_fcnn_size(16, 32) : 0);
+    return (int64_t)bwd_grid(B) * per * (int64_t)sizeof(float);
+}
+
+extern "C" int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
+                                 const float* enc, const float* particles, int B, int N, int hidden, const float* g_lki,
+                                 const int32_t* argmax, float* d_particles, float* d_enc, float* d_pe, float* d_cnf, void* workspace,
+                                 void* stream) {
+    NFDPF_REQUIRE(pe_packed && enc && particles && g_lki && d_particles && d_pe && workspace, "measure_bwd: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0, "measure_bwd: B and N must be positive");
+    NFDPF_REQUIRE(mode >= 0 && mode <= 2, "measure_bwd: bad mode %d", mode);
+    NFDPF_REQUIRE(mode == MODE_COS || argmax, "measure_bwd: argmax required for max-shifted likelihoods");
+    NFDPF_REQUIRE(mode != MODE_CNF || (cnf_packed && d_cnf && n_flows >= 1 && n_flows <= 4), "measure_bwd: CRNVP needs packed stack + gradient buffer");
+    if (hidden != HID) { set_error("measure_bwd: kernels are built for hiddensize 32 (got %d)", hidden); return NFDPF_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, d_pe, d_cnf, workspace, st
+    if (mode == MODE_GAUSS) return launch_measure_bwd<MODE_GAUSS>(ARGS);
+    if (mode == MODE_COS) return launch_measure_bwd<MODE_COS>(ARGS);
+    return launch_measure_bwd<MODE_CNF>(ARGS);
+#undef ARGS
+}

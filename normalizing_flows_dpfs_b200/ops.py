@@ -129,3 +129,78 @@ def weight_update(logw_prev, lki=None, prior=None, propose=None, add_eps=0.0):
 
 def coupling_stack(packed, x, row_ctx=None, part_ctx=None, n_flows=2, inverse=False):
     return CouplingStack.apply(packed, x, row_ctx, part_ctx, n_flows, inverse)
+
+
+MEASURE_MODES = {"gaussian": 0, "cos": 1, "CRNVP": 2}
+
+
+class MeasureUpdate(torch.autograd.Function):
+    """Measurement log-likelihood (model/models.py:206-278) fused with DPFs.py:187-192 when logw_prev is given.
+
+    pe: packed particle encoder (1648,), cnf: packed D=32/C=32 stack or None, enc (B,32), particles (B,N,2).
+    Returns (lki, logw, probs, row_sum, ess_inv); the last four are None-like zeros-size when not fused."""
+
+    @staticmethod
+    def forward(ctx, pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows, p0, p1, add_eps):
+        B, N, d = particles.shape
+        if d != 2:
+            raise ValueError("measurement kernels take 2-d particle states (DPFs.py:31), got d=%d" % d)
+        hidden = enc.shape[-1]
+        pe_, enc_, x_ = L.f32(pe), L.f32(enc), L.f32(particles)
+        cnf_ = L.f32(cnf) if cnf is not None else None
+        if pe_.numel() != 1648:
+            raise ValueError("particle encoder must be Linear(2,16)-Linear(16,32)-Linear(32,32): 1648 parameters, got %d" % pe_.numel())
+        fused = logw_prev is not None
+        lw0 = L.f32(logw_prev) if fused else None
+        pr = L.f32(prior) if prior is not None else None
+        pp = L.f32(propose) if propose is not None else None
+        dev = x_.device
+        lki = torch.empty(B, N, dtype=torch.float32, device=dev)
+        argmax = torch.empty(B, dtype=torch.int32, device=dev)
+        logw = torch.empty(B, N, dtype=torch.float32, device=dev) if fused else None
+        probs = torch.empty(B, N, dtype=torch.float32, device=dev) if fused else None
+        stats = torch.empty(B, 2, dtype=torch.float32, device=dev) if fused else None
+        L.call("nfdpf_measure_fwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, float(p0), float(p1), L.ptr(enc_), L.ptr(x_), B, N, hidden,
+               L.ptr(lw0), L.ptr(pr), L.ptr(pp), float(add_eps), L.ptr(lki), L.ptr(argmax), L.ptr(logw), L.ptr(probs), L.ptr(stats),
+               L.stream())
+        ctx.save_for_backward(pe_, cnf_, enc_, x_, argmax, probs)
+        ctx.meta = (mode, n_flows, float(p0), float(p1), float(add_eps), B, N, hidden, fused, prior is not None, propose is not None)
+        if not fused:
+            return lki, None, None, None, None
+        ctx.mark_non_differentiable(stats[:, 1])
+        return lki, logw, probs, stats[:, 0], stats[:, 1]
+
+    @staticmethod
+    def backward(ctx, g_lki, g_logw, g_probs, g_rowsum, _g_ess):
+        pe_, cnf_, enc_, x_, argmax, probs = ctx.saved_tensors
+        mode, n_flows, p0, p1, add_eps, B, N, hidden, fused, has_prior, has_prop = ctx.meta
+        dev = x_.device
+        d_logw = None
+        g_total = L.f32(g_lki) if g_lki is not None else None
+        if fused and any(g is not None for g in (g_logw, g_probs, g_rowsum)):
+            d_logw = torch.empty(B, N, dtype=torch.float32, device=dev)
+            L.call("nfdpf_weight_update_bwd", L.ptr(L.f32(g_probs) if g_probs is not None else None),
+                   L.ptr(L.f32(g_logw) if g_logw is not None else None),
+                   L.ptr(L.f32(g_rowsum) if g_rowsum is not None else None), L.ptr(probs), add_eps, B, N, L.ptr(d_logw), L.stream())
+            g_total = d_logw if g_total is None else g_total + d_logw
+        if g_total is None:
+            g_total = torch.zeros(B, N, dtype=torch.float32, device=dev)
+        d_x = torch.empty_like(x_)
+        d_enc = torch.empty_like(enc_) if ctx.needs_input_grad[2] else None
+        d_pe = torch.zeros_like(pe_)
+        d_cnf = torch.zeros_like(cnf_) if cnf_ is not None else None
+        ws = torch.empty(L.load().nfdpf_measure_bwd_workspace(mode, n_flows, B, N) // 4, dtype=torch.float32, device=dev)
+        L.call("nfdpf_measure_bwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, p0, p1, L.ptr(enc_), L.ptr(x_), B, N, hidden,
+               L.ptr(g_total.contiguous()), L.ptr(argmax), L.ptr(d_x), L.ptr(d_enc), L.ptr(d_pe), L.ptr(d_cnf), L.ptr(ws), L.stream())
+        return (d_pe, d_cnf, d_enc, d_x, d_logw if fused else None, d_logw if has_prior else None,
+                (-d_logw if d_logw is not None else None) if has_prop else None, None, None, None, None, None)
+
+
+def measure(pe, cnf, enc, particles, mode, n_flows=2, p0=0.0, p1=1.0):
+    """lki (B,N) only -- the measurement_model_*.forward of the reference."""
+    return MeasureUpdate.apply(pe, cnf, enc, particles, None, None, None, MEASURE_MODES[mode], n_flows, p0, p1, 0.0)[0]
+
+
+def measure_update(pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows=2, p0=0.0, p1=1.0, add_eps=1e-12):
+    """(lki, logw, probs, row_sum_logw, ess_inv) -- measurement + DPFs.py:187-192 in one kernel."""
+    return MeasureUpdate.apply(pe, cnf, enc, particles, logw_prev, prior, propose, MEASURE_MODES[mode], n_flows, p0, p1, add_eps)

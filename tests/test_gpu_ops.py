@@ -167,3 +167,64 @@ def test_unsupported_shape_raises():
     pk = torch.zeros(4 * 2 * (8 * (3 + 0) + 8 + 64 + 8 + 3 * 8 + 3), device="cuda")
     with pytest.raises(RuntimeError):
         ops.coupling_stack(pk, torch.zeros(1, 4, 6, device="cuda"), None, None, 2, False)
+
+
+# --------------------------------------------------------------------------------------------- measurement
+def _pe_tuple(flat):
+    sizes = [(16, 2), (16,), (32, 16), (32,), (32, 32), (32,)]
+    o, parts = 0, []
+    for s in sizes:
+        n = int(np.prod(s))
+        parts.append(flat[o:o + n].reshape(*s))
+        o += n
+    return tuple(parts)
+
+
+def test_measurement_golden(golden):
+    G = golden("glue")
+    pe, cnf, enc, x = cu(G["pe"]), cu(G["cnf"]), cu(G["enc"]), cu(G["x"])
+    close(ops.measure(pe, None, enc, x, "gaussian", p0=1.0, p1=10.0), G["meas_gauss"], atol=1e-4, what="gaussian")
+    close(ops.measure(pe, None, enc, x, "cos"), G["meas_cos"], what="cos")
+    close(ops.measure(pe, cnf, enc, x, "CRNVP", p0=0.0, p1=2.5), G["meas_cnf"], atol=1e-4, what="CRNVP")
+
+
+@pytest.mark.parametrize("mode,B,N,fused", [("gaussian", 3, 200, True), ("cos", 3, 200, True), ("CRNVP", 3, 200, True),
+                                            ("gaussian", 2, 50, False), ("CRNVP", 2, 129, False), ("gaussian", 16, 1024, True),
+                                            ("CRNVP", 8, 1024, True)])
+def test_measure_update_vs_oracle(mode, B, N, fused):
+    g = torch.Generator().manual_seed(hash((mode, B, N)) % 1000)
+    pe = torch.cat([torch.randn(n, generator=g) * s for n, s in ((32, 0.3), (16, 0.1), (512, 0.3), (32, 0.1), (1024, 0.2), (32, 0.1))])
+    cnf = O.init_stack(g, 32, 32, std=0.1, bias_std=0.05) if mode == "CRNVP" else None
+    enc = torch.randn(B, 32, generator=g)
+    x = torch.randn(B, N, 2, generator=g) * 3
+    lw0 = torch.log_softmax(torch.randn(B, N, generator=g), -1)
+    prior, prop = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g)
+    p0, p1 = {"gaussian": (1.0, 10.0), "cos": (0.0, 1.0), "CRNVP": (0.0, 2.5)}[mode]
+    names = ("pe", "cnf", "enc", "x", "lw0", "prior", "prop")
+    lo = {k: (v.clone().requires_grad_() if v is not None else None) for k, v in zip(names, (pe, cnf, enc, x, lw0, prior, prop))}
+    if mode == "gaussian":
+        lki_o = O.measurement_gaussian(lo["enc"], lo["x"], _pe_tuple(lo["pe"]))
+    elif mode == "cos":
+        lki_o = O.measurement_cos(lo["enc"], lo["x"], _pe_tuple(lo["pe"]))
+    else:
+        lki_o = O.measurement_cnf(lo["enc"], lo["x"], _pe_tuple(lo["pe"]), O.unpack_stack(lo["cnf"], 32, 32), 2.5)
+    gt = {k: (cu(v).requires_grad_() if v is not None else None) for k, v in zip(names, (pe, cnf, enc, x, lw0, prior, prop))}
+    g1, g2, g3 = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g), torch.randn(B, generator=g)
+    if fused:
+        lw_o = lo["lw0"] + lki_o + lo["prior"] - lo["prop"]
+        pr_o = O.normalize_log_probs(lw_o) + 1e-12
+        ((lki_o * g1).sum() + (pr_o * g2).sum() * 50 + (lw_o.sum(-1) * g3).sum() * 0.01).backward()
+        lki, logw, probs, rs, ess = ops.measure_update(gt["pe"], gt["cnf"], gt["enc"], gt["x"], gt["lw0"], gt["prior"], gt["prop"], mode,
+                                                       p0=p0, p1=p1)
+        close(logw, lw_o, atol=1e-4, what="logw")
+        close(probs, pr_o, atol=1e-8, what="probs")
+        close(ess, 1.0 / (pr_o ** 2).sum(-1), what="ess")
+        ((lki * cu(g1)).sum() + (probs * cu(g2)).sum() * 50 + (rs * cu(g3)).sum() * 0.01).backward()
+    else:
+        (lki_o * g1).sum().backward()
+        lki = ops.measure(gt["pe"], gt["cnf"], gt["enc"], gt["x"], mode, p0=p0, p1=p1)
+        (lki * cu(g1)).sum().backward()
+    close(lki, lki_o, atol=1e-4, what="lki")
+    for k in names:
+        if gt[k] is not None and lo[k].grad is not None:
+            grad_close(gt[k].grad, lo[k].grad, "d_" + k)
