@@ -109,6 +109,11 @@ int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed,
                       const int32_t* argmax, float* d_particles, float* d_enc, float* d_pe, float* d_cnf,
                       void* workspace, void* stream);
 
+/* ---- per-trajectory particle moments: the detached flow context of model/models.py:309-310, 338-339 ----
+ * out[b, out_off + k] = mean_n x[b,n,k], out[b, out_off + d + k] = unbiased std_n x[b,n,k]; out has row stride
+ * out_stride floats (so the moments can be written straight into a wider (B,C_row) context buffer). */
+int nfdpf_row_moments(const float* x, int B, int N, int d, float* out, int out_stride, int out_off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,284 @@
+"""DPF: the differentiable particle filter module with the reference's constructor, attributes, state_dict keys
+and method signatures (reference DPFs.py:22-451).
+
+`filtering_pos` is the hot path (DPFs.py:144-216).  Per timestep it launches a handful of fused sm_100a kernels
+through libnfdpf (soft / OT resampling, coupling stacks, measurement + weight update) instead of the reference's
+6-17 thousand ATen calls, keeps the per-step lists as Python lists stacked once at the end (the reference
+re-concatenates them every step, O(T^2) copies), and never materialises a (B,N,N) or (P,C) tensor."""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .losses import autoencoder_loss, pseudolikelihood_loss, pseudolikelihood_loss_nf, supervised_loss
+from .model.models import (build_conditional_nf, build_decoder, build_decoder_cglow, build_encoder, build_encoder_cglow,
+                           build_likelihood, build_particle_encoder, build_particle_encoder_cglow, build_transition_model,
+                           measurement_model_cnf, measurement_model_cosine_distance, measurement_model_Gaussian,
+                           measurement_model_NN, motion_update, nf_dynamic_model, proposal_likelihood, _FusedMeasurement)
+from .resamplers.resamplers import resampler
+from .utils import checkpoint_state, compute_normal_density, load_model, normalize_log_probs, particle_initialization
+
+device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+
+
+class DPF(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.param = args
+        self.NF, self.NFcond = args.NF_dyn, args.NF_cond
+        self.measurement = args.measurement
+        self.hidden_size = args.hiddensize
+        self.state_dim = 2
+        self.lr, self.alpha = args.lr, args.alpha
+        self.seq_len, self.num_particle, self.batch_size = args.sequence_length, args.num_particles, args.batchsize
+        self.labeledRatio = args.labeledRatio
+        self.spring_force, self.drag_force = 0.1, 0.0075
+        self.pos_noise, self.vel_noise = args.pos_noise, args.vel_noise
+        self.NF_lr = args.NF_lr
+        self.n_sequence = 2
+        self.build_model()
+        self.eps, self.scaling, self.threshold, self.max_iter = args.epsilon, args.scaling, args.threshold, args.max_iter
+        self.resampler = resampler(self.param)
+        # optional hooks: injected random draws (parity tests / benchmarks) and a gate override
+        self.injected = None          # dict(init_particles, noise (B,T,N,2), offsets (B,T)) or None
+        self.force_resample = None    # None = the reference's ESS gate; True / False = always / never
+        self.fired = []
+
+    # ------------------------------------------------------------------------------------------ construction
+    def build_model(self):
+        cglow = self.measurement == "CGLOW"
+        self.encoder = (build_encoder_cglow if cglow else build_encoder)(self.hidden_size)
+        self.decoder = (build_decoder_cglow if cglow else build_decoder)(self.hidden_size)
+        self.build_particle_encoder = build_particle_encoder_cglow if cglow else build_particle_encoder
+        self.particle_encoder = self.build_particle_encoder(self.hidden_size, self.state_dim)
+        self.transition_model = build_transition_model(self.state_dim)  # built but unused, like the reference
+        self.motion_update = motion_update
+        self.nf_dyn = build_conditional_nf(self.n_sequence, 2 * self.state_dim, self.state_dim, init_var=0.01)
+        self.cond_model = build_conditional_nf(self.n_sequence, 2 * self.state_dim + self.hidden_size, self.state_dim, init_var=0.01)
+        if self.measurement == "CRNVP":
+            self.cnf_measurement = build_conditional_nf(self.n_sequence, self.hidden_size, self.hidden_size, init_var=0.01, prior_std=2.5)
+            self.measurement_model = measurement_model_cnf(self.particle_encoder, self.cnf_measurement)
+        elif self.measurement == "cos":
+            self.measurement_model = measurement_model_cosine_distance(self.particle_encoder)
+        elif self.measurement == "NN":
+            self.likelihood_est = build_likelihood(self.hidden_size, self.state_dim)
+            self.measurement_model = measurement_model_NN(self.particle_encoder, self.likelihood_est)
+        elif self.measurement == "gaussian":
+            self.gaussian_distribution = torch.distributions.MultivariateNormal(torch.ones(self.hidden_size).to(device),
+                                                                                100 * torch.eye(self.hidden_size).to(device))
+            self.measurement_model = measurement_model_Gaussian(self.particle_encoder, self.gaussian_distribution)
+        elif cglow:
+            raise NotImplementedError("--measurement CGLOW is outside the accelerated hot path")
+        self.prototype_density = compute_normal_density(pos_noise=self.pos_noise, vel_noise=self.vel_noise)
+        self.optim = torch.optim.Adam(self.parameters(), lr=self.lr)
+        self.optim_scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optim, milestones=[30 * (1 + x) for x in range(10)], gamma=1.0)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, inputs, train=True):
+        start_image, start_state, image, state, q, visible = inputs
+        state, start_state = state.to(device), start_state.to(device)
+        image = image.permute(0, 1, 4, 2, 3).to(device)
+        vel = state[:, :, 2:] + torch.normal(0.0, 4.0, state[:, :, 2:].shape).to(device)
+        (particle_list, particle_weight_list, noise_list, likelihood_list, init_weights_log, index_list, jac_list, prior_list,
+         obs_likelihood) = self.filtering_pos(image, start_state, vel)
+        mask = self.get_mask() if train else 1.0
+        loss_sup, predictions = supervised_loss(particle_list, particle_weight_list, state, mask, train)
+        loss_ae = autoencoder_loss(image, train, self.encoder, self.decoder)
+        lamda1, lamda2, lamda3 = 1.0, 0.01, 2.0
+        if self.param.trainType == "DPF":
+            loss_pseud_lik = None
+            total_loss = lamda1 * loss_sup + lamda3 * loss_ae
+        elif self.param.trainType == "SDPF":
+            if self.NF:
+                loss_pseud_lik = pseudolikelihood_loss_nf(particle_weight_list, noise_list, likelihood_list, index_list, jac_list,
+                                                          prior_list, self.param.block_length)
+            else:
+                loss_pseud_lik = pseudolikelihood_loss(particle_weight_list, noise_list, likelihood_list, index_list,
+                                                       self.param.block_length, self.param.pos_noise, self.param.vel_noise)
+            total_loss = lamda1 * loss_sup + lamda2 * loss_pseud_lik + lamda3 * loss_ae
+        else:
+            raise ValueError("Please select the training type in DPF (supervised learning) and SDPF (semi-supervised learning)")
+        return (total_loss, loss_sup, loss_pseud_lik, loss_ae, predictions, particle_list, particle_weight_list, state, start_state,
+                image, likelihood_list, noise_list, obs_likelihood)
+
+    # ----------------------------------------------------------------------------------------------- hot path
+    def filtering_pos(self, obs, start_state_vs, vel_input):
+        """The per-timestep particle update (reference DPFs.py:144-216).  `obs` is (B,T,3,H,W) images, or (B,T,h)
+        precomputed encodings when `self.encoder` is an Identity (benchmarks exclude the CNN)."""
+        start_state, vel = start_state_vs[:, :2], start_state_vs[:, 2:]
+        B, N, inj = start_state.shape[0], self.num_particle, self.injected
+        particles, init_weights_log = particle_initialization(start_state, self.param.width, N, self.state_dim,
+                                                              init_with_true_state=self.param.init_with_true_state)
+        if inj is not None and "init_particles" in inj:
+            particles = inj["init_particles"]
+        _, particle_probs, _, ess_inv = _weight_norm(init_weights_log)
+        identity_idx = torch.arange(B * N, device=particles.device, dtype=torch.int64).reshape(B, N)
+        fused = isinstance(self.measurement_model, _FusedMeasurement)
+        lists = {k: [] for k in ("particles", "probs", "noise", "lki", "index", "jac", "prior")}
+        obs_likelihood, self.fired = 0.0, []
+        for step in range(self.seq_len):
+            index_p = identity_idx
+            if self.force_resample is None:
+                fire = bool(ess_inv.mean() < 0.5 * N)          # whole-batch ESS gate, DPFs.py:163-165 (one D2H sync)
+            else:
+                fire = bool(self.force_resample)
+            self.fired.append(fire)
+            if fire:
+                if inj is not None and "offsets" in inj and self.param.resampler_type == "soft":
+                    particles, probs_res, index_p = self.resampler.resampling(particles, particle_probs, random_offset=inj["offsets"][:, step],
+                                                                              **self.resampler.kargs)
+                else:
+                    particles, probs_res, index_p = self.resampler(particles, particle_probs)
+                logw_prev = probs_res.log()
+            else:
+                logw_prev = particle_probs.log()
+            noise = inj["noise"][:, step] if inj is not None and "noise" in inj else None
+            particles_physical, noise = self.motion_update(particles, vel, pos_noise=self.pos_noise, noise=noise)
+            vel = vel_input[:, step, :]
+            particles_dynamical, jac = nf_dynamic_model(self.nf_dyn, particles_physical, particle_probs.shape, NF=self.NF)
+            encodings = self.encoder(obs[:, step].float())
+            if fused:    # measurement + weight update + normalisation in one kernel
+                propose_particle, prior_log, propose_log = _proposal_terms(self, particles_dynamical, particles_physical, encodings, noise, jac)
+                cancel = not self.NFcond   # prior == propose: they cancel exactly in DPFs.py:187
+                lki_log, logw, particle_probs, row_sum, ess_inv = self.measurement_model.forward_update(
+                    encodings, propose_particle, logw_prev, None if cancel else prior_log, None if cancel else propose_log)
+                obs_likelihood = obs_likelihood + row_sum.sum() / (B * N)
+            else:
+                propose_particle, lki_log, prior_log, propose_log = proposal_likelihood(
+                    self.cond_model, self.nf_dyn, self.measurement_model, particles_dynamical, particles_physical, encodings, noise, jac,
+                    self.NF, self.NFcond, prototype_density=self.prototype_density)
+                logw, particle_probs, row_sum, ess_inv = _weight_update(logw_prev, lki_log, prior_log, propose_log)
+                obs_likelihood = obs_likelihood + row_sum.sum() / (B * N)
+            particles = propose_particle
+            for k, v in (("particles", particles), ("probs", particle_probs), ("noise", noise), ("lki", lki_log), ("index", index_p)):
+                lists[k].append(v)
+            if self.NF:
+                lists["jac"].append(jac)
+                lists["prior"].append(prior_log)
+        stack = lambda k: torch.stack(lists[k], dim=1)
+        return (stack("particles"), stack("probs"), stack("noise"), stack("lki"), init_weights_log, stack("index"),
+                stack("jac") if self.NF else None, stack("prior") if self.NF else None, obs_likelihood)
+
+    def get_mask(self):
+        n1 = int(self.batch_size * self.seq_len * self.labeledRatio)
+        arr = np.array([0] * (self.batch_size * self.seq_len - n1) + [1] * n1)
+        np.random.shuffle(arr)
+        return torch.tensor(arr.reshape(self.batch_size, self.seq_len)).to(device)
+
+    # ------------------------------------------------------------------------- trainer glue (out of hot path)
+    def _run_epoch(self, loader, train):
+        sup, ae, last = [], [], None
+        for inputs in loader:
+            out = self.forward(inputs, train=train)
+            if train:
+                self.zero_grad()
+                out[0].backward()
+                self.optim.step()
+            sup.append(out[1].detach().cpu().numpy())
+            ae.append(out[3].detach().cpu().numpy())
+            last = out
+        return sup, ae, last
+
+    def pretrain_ae(self, train_loader, valid_loader, start_epoch=-1, epoch_num=100, logger=None):
+        best, ckpt_ae = 1e10, None
+        for epoch in range(start_epoch + 1, epoch_num):
+            for phase, loader in (("train", train_loader), ("val", valid_loader)):
+                self.train(phase == "train")
+                losses = []
+                with torch.set_grad_enabled(phase == "train"):
+                    for inputs in loader:
+                        img = inputs[2].permute(0, 1, 4, 2, 3).reshape(-1, 3, 128, 128).to(device)
+                        loss = nn.functional.mse_loss(self.decoder(self.encoder(img)), img)
+                        if phase == "train":
+                            self.zero_grad()
+                            loss.backward()
+                            self.optim.step()
+                        losses.append(loss.detach().cpu().numpy())
+                print(f"{phase} AE: Epoch: {epoch}, loss: {np.mean(losses)}")
+            if logger is not None:
+                logger.add_scalar("PretrainAE_loss_eval/loss", np.mean(losses), epoch)
+            if np.mean(losses) < best:
+                best = np.mean(losses)
+                ckpt_ae = {"model": self.state_dict(), "optim": self.optim.state_dict()}
+                torch.save(ckpt_ae, "./model/ae_pretrain.pth")
+        if ckpt_ae is not None:
+            self.load_state_dict(ckpt_ae["model"])
+            self.optim.load_state_dict(ckpt_ae["optim"])
+
+    def e2e_train(self, train_loader, valid_loader, start_epoch=-1, epoch_num=100, logger=None, run_id=None):
+        best, history = 1e10, []
+        if self.param.load_pretrainModel:
+            self.load_state_dict(torch.load("./model/ae_pretrain.pth")["model"])
+        for epoch in range(start_epoch + 1, epoch_num):
+            self.train()
+            sup, ae, last = self._run_epoch(train_loader, True)
+            self.optim_scheduler.step()
+            if logger is not None:
+                logger.add_scalar("Sup_loss/loss", np.mean(sup), epoch)
+            print(f"End-to-end loss: epoch: {epoch}, loss: {np.mean(sup)}, loss_ae: {np.mean(ae)}, obs_likelihood: {last[-1]}")
+            self.eval()
+            with torch.no_grad():
+                sup_eval, _, last = self._run_epoch(valid_loader, False)
+            eval_mean = np.mean(sup_eval)
+            if logger is not None:
+                logger.add_scalar("Sup_loss_eval/loss", eval_mean, epoch)
+            print(f"End-to-end loss evaluation: epoch: {epoch}, loss: {eval_mean}, obs_likelihood: {last[-1]}", self.NF)
+            history.append(eval_mean)
+            np.save(os.path.join("logs", run_id, "data", "eval_loss_epoch.npy"), history)
+            if eval_mean < best:
+                best = eval_mean
+                _dump(os.path.join("logs", run_id, "data", "eval_result_best.npz"), last, loss=sup_eval)
+                torch.save(checkpoint_state(self, epoch), os.path.join("logs", run_id, "models", "e2e_model_bestval_e2e.pth"))
+
+    def load_model(self, file_name):
+        ckpt = torch.load(file_name)
+        load_model(self, ckpt)
+        print(f"Load epcoh: {ckpt['epoch']}")
+
+    def train_val(self, train_loader, valid_loader, run_id):
+        from torch.utils.tensorboard import SummaryWriter
+        for d in ("result", "model", "checkpoint", "logger"):
+            os.makedirs(d, exist_ok=True)
+        logger = SummaryWriter("./logger")
+        if self.param.resume:
+            self.load_model("./model/e2e_model_bestval_e2e.pth")
+        if self.param.pretrain_ae:
+            self.pretrain_ae(train_loader, valid_loader, start_epoch=-1, epoch_num=300, logger=logger)
+        if self.param.e2e_train:
+            self.e2e_train(train_loader, valid_loader, start_epoch=-1, epoch_num=self.param.num_epochs, logger=logger, run_id=run_id)
+
+    def testing(self, test_loader, run_id, model_path="./model/e2e_model_bestval_e2e.pth"):
+        if self.param.testing:
+            self.load_model(os.path.join(model_path, "e2e_model_bestval_e2e.pth"))
+        self.eval()
+        with torch.no_grad():
+            sup_eval, _, last = self._run_epoch(test_loader, False)
+        np.save(os.path.join("logs", run_id, "data", "test_loss_epoch.npy"), sup_eval)
+        print(f"End-to-end loss testing: loss: {np.mean(sup_eval)}")
+        _dump(os.path.join("logs", run_id, "data", "test_result.npz"), last, images=last[9].detach().cpu().numpy(),
+              noise=last[11].detach().cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------------- helpers
+def _weight_norm(logw):
+    from . import ops
+    return ops.weight_update(logw)
+
+
+def _weight_update(logw_prev, lki, prior, propose):
+    from . import ops
+    return ops.weight_update(logw_prev, lki, prior, propose, 1e-12)
+
+
+def _proposal_terms(dpf, particles_dynamical, particles_physical, encodings, noise, jac):
+    """proposal_likelihood (reference models.py:358-379) minus the measurement call, which is fused downstream."""
+    out = proposal_likelihood(dpf.cond_model, dpf.nf_dyn, lambda enc, x: None, particles_dynamical, particles_physical, encodings,
+                              noise, jac, dpf.NF, dpf.NFcond, prototype_density=dpf.prototype_density)
+    return out[0], out[2], out[3]
+
+
+def _dump(path, out, **extra):
+    np.savez(path, particle_list=out[5].detach().cpu().numpy(), particle_weight_list=out[6].detach().cpu().numpy(),
+             likelihood_list=out[10].detach().cpu().numpy(), pred=out[4].detach().cpu().numpy(), state=out[7].detach().cpu().numpy(),
+             **extra)

@@ -112,3 +112,33 @@ extern "C" int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw
     }
     return check_launch("weight_update_bwd");
 }
+
+// ---- per-trajectory moments: the (detached) flow context of model/models.py:309-310, 338-339 -------------------
+// out[b, off + k] = mean_n x[b,n,k];  out[b, off + d + k] = std_n x[b,n,k] (unbiased, N-1), k < d.  One warp per row pair.
+namespace nfdpf {
+__global__ void row_moments_kernel(const float* __restrict__ x, int B, int N, int d, float* __restrict__ out, int out_stride,
+                                   int out_off) {
+    __shared__ float s_red[33];
+    const int b = blockIdx.x;
+    const float* xr = x + (size_t)b * N * d;
+    for (int k = 0; k < d; ++k) {
+        float s = 0.f;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) s += xr[(size_t)n * d + k];
+        const float mean = block_allreduce(s, s_red, OpSum(), 0.f) / (float)N;
+        float v = 0.f;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) { const float t = xr[(size_t)n * d + k] - mean; v = fmaf(t, t, v); }
+        v = block_allreduce(v, s_red, OpSum(), 0.f);
+        if (threadIdx.x == 0) {
+            out[(size_t)b * out_stride + out_off + k] = mean;
+            out[(size_t)b * out_stride + out_off + d + k] = sqrtf(v / (float)(N - 1));   // N == 1 -> NaN like torch.std
+        }
+    }
+}
+}  // namespace nfdpf
+
+extern "C" int nfdpf_row_moments(const float* x, int B, int N, int d, float* out, int out_stride, int out_off, void* stream) {
+    NFDPF_REQUIRE(x && out, "row_moments: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0 && d > 0 && out_stride >= out_off + 2 * d && out_off >= 0, "row_moments: bad sizes");
+    nfdpf::row_moments_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, B, N, d, out, out_stride, out_off);
+    return nfdpf::check_launch("row_moments");
+}

@@ -204,3 +204,13 @@ def measure(pe, cnf, enc, particles, mode, n_flows=2, p0=0.0, p1=1.0):
 def measure_update(pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows=2, p0=0.0, p1=1.0, add_eps=1e-12):
     """(lki, logw, probs, row_sum_logw, ess_inv) -- measurement + DPFs.py:187-192 in one kernel."""
     return MeasureUpdate.apply(pe, cnf, enc, particles, logw_prev, prior, propose, MEASURE_MODES[mode], n_flows, p0, p1, add_eps)
+
+
+def row_moments(x, out=None, out_off=0):
+    """[mean | unbiased std] over the particle axis, (B,N,d) -> (B,2d), no autograd (the reference detaches it)."""
+    B, N, d = x.shape
+    xx = L.f32(x)
+    if out is None:
+        out = torch.empty(B, 2 * d, dtype=torch.float32, device=xx.device)
+    L.call("nfdpf_row_moments", L.ptr(xx), B, N, d, L.ptr(out), out.shape[1], out_off, L.stream())
+    return out

@@ -1,0 +1,69 @@
+"""GPU parity of the whole filter loop (DPF.filtering_pos + supervised loss + backward) against the goldens the
+unmodified reference produced (tests/golden/filter.npz) with every random draw injected."""
+import numpy as np
+import pytest
+import torch
+
+from normalizing_flows_dpfs_b200.arguments import parse_args
+from normalizing_flows_dpfs_b200.DPFs import DPF
+from normalizing_flows_dpfs_b200.losses import supervised_loss
+from test_gpu_ops import close, cu, grad_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _set_flat(module, flat):
+    o = 0
+    with torch.no_grad():
+        for p in module.parameters():
+            n = p.numel()
+            p.copy_(torch.as_tensor(flat[o:o + n]).reshape(p.shape))
+            o += n
+    assert o == len(flat)
+
+
+def _flat_grad(module):
+    return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in module.parameters()])
+
+
+def build_from_golden(G, tag):
+    g = lambda k: G[f"{tag}_{k}"]
+    B, N, T = int(g("B")), int(g("N")), int(g("T"))
+    flags = str(g("flags")).split()
+    args = parse_args(["--num-particles", str(N), "--batchsize", str(B), "--sequence-length", str(T)] + flags)
+    dpf = DPF(args)
+    _set_flat(dpf.nf_dyn, g("dyn")), _set_flat(dpf.cond_model, g("cond")), _set_flat(dpf.particle_encoder, g("pe"))
+    if f"{tag}_cnf" in G:
+        _set_flat(dpf.cnf_measurement, g("cnf"))
+    dpf.encoder = torch.nn.Identity()
+    dpf = dpf.cuda()
+    dpf.injected = dict(init_particles=cu(g("init_particles")), noise=cu(g("noise")), offsets=cu(g("offsets")))
+    return dpf, g
+
+
+@pytest.mark.parametrize("tag", ["boot_gauss_soft", "cnf_gauss_soft", "crnvp_soft", "cnf_cos_soft", "full_crnvp_ot"])
+def test_filter_matches_reference(golden, tag):
+    G = golden("filter")
+    dpf, g = build_from_golden(G, tag)
+    start = cu(g("start"))
+    out = dpf.filtering_pos(cu(g("enc")), start, cu(g("vel_in")))
+    particles, probs, noise, lki, init_lw, index, jac, prior, obs_lik = out
+    assert dpf.fired == [bool(f) for f in g("fired")], "ESS gate decisions differ"
+    assert np.array_equal(index.cpu().numpy(), g("index")), "ancestor indices must be bit-exact"
+    ot = "ot" in tag
+    close(particles, g("particles"), rtol=1e-4, atol=5e-3 if ot else 1e-3, what="particles")   # particles are O(100)
+    close(probs, g("probs"), rtol=2e-3 if ot else 1e-4, atol=1e-7, what="probs")
+    close(lki, g("lki"), rtol=1e-4, atol=1e-3 if ot else 1e-4, what="lki")
+    if dpf.NF:
+        close(jac, g("jac"), what="jac")
+        close(prior, g("prior"), rtol=1e-4, atol=1e-3 if ot else 1e-4, what="prior")
+    close(obs_lik, g("obs_likelihood"), rtol=1e-4, atol=1e-4, what="obs_likelihood")
+    loss, pred = supervised_loss(particles, probs, cu(g("state")), 1.0, False)
+    close(loss, g("loss"), rtol=1e-4 if not ot else 1e-3, what="loss")      # north_star: final RMSE within 1%
+    loss.backward()
+    for name, mod in (("dyn", dpf.nf_dyn), ("cond", dpf.cond_model), ("pe", dpf.particle_encoder),
+                      ("cnf", getattr(dpf, "cnf_measurement", None))):
+        if mod is None or (name == "dyn" and not dpf.NF) or (name == "cond" and not dpf.NFcond):
+            continue
+        ref = g("d_" + name)
+        close(_flat_grad(mod), ref, rtol=1e-3, atol=(2e-3 if ot else 2e-4) * float(np.abs(ref).max()), what="d_" + name)
