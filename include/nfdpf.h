@@ -114,6 +114,23 @@ int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed,
  * out_stride floats (so the moments can be written straight into a wider (B,C_row) context buffer). */
 int nfdpf_row_moments(const float* x, int B, int N, int d, float* out, int out_stride, int out_off, void* stream);
 
+/* ---- (K4) entropy-regularised OT resampling: resamplers/resamplers.py:62-277 ---------------------------
+ * particles (B,N,2), logw (B,N) = log of the (normalised) weights.  Log-domain Sinkhorn with epsilon-scaling
+ * (eps_0 = squared extent of the scaled cloud, eps <- max(eps*scaling^2, eps)), simultaneous half-step updates,
+ * the reference's batch-wide stop rule (all rows must want to continue; max_iter cap) evaluated on the device,
+ * then particles_out = T particles with T column-normalised to N*w_j (resamplers.py:194-210, 254-264).
+ * All arithmetic is fp32 (the reference runs this part in fp64, resamplers.py:76).
+ * saved (B,N,4): what the backward needs (scaled positions and the row/column log-scalings of T, log2 units).
+ * iters_out: device int32 or NULL, receives the reference's `total_iter + 2`.  workspace: nfdpf_ot_workspace() bytes. */
+int64_t nfdpf_ot_workspace(int B, int N);
+int nfdpf_ot_resample_fwd(const float* particles, const float* logw, float eps, float scaling, float threshold,
+                          int max_iter, int B, int N, int d, float* particles_out, float* saved, int32_t* iters_out,
+                          void* workspace, void* stream);
+/* backward: d_particles = T^T g_out; the plan itself carries no gradient (transport.backward returns None,
+ * resamplers.py:240-245) and neither do the weights. */
+int nfdpf_ot_resample_bwd(const float* g_out, const float* saved, float eps, int B, int N, int d, float* d_particles,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

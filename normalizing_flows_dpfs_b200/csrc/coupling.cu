@@ -98,6 +98,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
         hoist_row_context<HALF, CP>(s_img, s_w1r, s_ctx, C_row, n_fcnn, s_hb, tid, TP);
         __syncthreads();
         for (int n0 = 0; n0 < N; n0 += TP) {
+            asm volatile("" ::: "memory");  // no LICM of shared-memory weight loads across particles
             const int n = n0 + tid;
             const bool live = n < N;
             const size_t p = (size_t)b * N + (live ? n : 0);

@@ -111,6 +111,7 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     __syncthreads();
     float mx = -INFINITY;
     for (int n = tid; n < N; n += TP) {
+        asm volatile("" ::: "memory");  // keep the shared-memory weight loads inside the loop (LICM would spill ~1.6k floats)
         const float2 x = *reinterpret_cast<const float2*>(particles + ((size_t)b * N + n) * 2);
         float a1[16], a2[32], e[32], lo[16], up[16];
         pe_fwd(s_pe, x.x, x.y, a1, a2, e);
@@ -230,6 +231,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         for (int k = 0; k < 32; ++k) denc[k] = 0.f;
         __syncthreads();
         for (int n0 = 0; n0 < N; n0 += TP) {
+            asm volatile("" ::: "memory");  // no LICM of shared-memory weight loads across particles
             const int n = n0 + tid;
             const bool live = n < N;
             const size_t p = base + (live ? n : 0);
@@ -278,7 +280,8 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                     for (int i = 0; i < 16; ++i) { denc[i] += glo[i]; denc[16 + i] += gup[i]; }
                 }
             }
-            // particle-encoder backward
+            // particle-encoder backward (the clobber stops the compiler from keeping the forward's weight loads alive: 6 KB of spills)
+            asm volatile("" ::: "memory");
             float d2[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) d2[j] = 0.f;

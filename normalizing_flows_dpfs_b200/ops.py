@@ -214,3 +214,37 @@ def row_moments(x, out=None, out_off=0):
         out = torch.empty(B, 2 * d, dtype=torch.float32, device=xx.device)
     L.call("nfdpf_row_moments", L.ptr(xx), B, N, d, L.ptr(out), out.shape[1], out_off, L.stream())
     return out
+
+
+class OtResample(torch.autograd.Function):
+    """particles' = T particles, T = Sinkhorn plan of (particles, logw) (resamplers.py:62-277); d out/d particles = T."""
+
+    last_iters = None  # device int32 tensor of the most recent call (the reference's total_iter + 2), for tests / reports
+
+    @staticmethod
+    def forward(ctx, particles, logw, eps, scaling, threshold, max_iter):
+        B, N, d = particles.shape
+        x, lw = L.f32(particles), L.f32(logw)
+        out = torch.empty_like(x)
+        saved = torch.empty(B, N, 4, dtype=torch.float32, device=x.device)
+        iters = torch.zeros(1, dtype=torch.int32, device=x.device)
+        ws = torch.empty(L.load().nfdpf_ot_workspace(B, N) // 4 + 1, dtype=torch.float32, device=x.device)
+        L.call("nfdpf_ot_resample_fwd", L.ptr(x), L.ptr(lw), float(eps), float(scaling), float(threshold), int(max_iter), B, N, d,
+               L.ptr(out), L.ptr(saved), L.ptr(iters), L.ptr(ws), L.stream())
+        OtResample.last_iters = iters
+        ctx.save_for_backward(saved)
+        ctx.meta = (float(eps), B, N, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        (saved,) = ctx.saved_tensors
+        eps, B, N, d = ctx.meta
+        g = L.f32(g_out)
+        dx = torch.empty_like(g)
+        L.call("nfdpf_ot_resample_bwd", L.ptr(g), L.ptr(saved), eps, B, N, d, L.ptr(dx), L.stream())
+        return dx, None, None, None, None, None
+
+
+def ot_resample(particles, logw, eps=0.1, scaling=0.75, threshold=1e-3, max_iter=100):
+    return OtResample.apply(particles, logw, eps, scaling, threshold, max_iter)

@@ -228,3 +228,51 @@ def test_measure_update_vs_oracle(mode, B, N, fused):
     for k in names:
         if gt[k] is not None and lo[k].grad is not None:
             grad_close(gt[k].grad, lo[k].grad, "d_" + k)
+
+
+# ------------------------------------------------------------------------------------------- OT resampling
+def test_ot_resample_golden(golden):
+    from normalizing_flows_dpfs_b200.resamplers.resamplers import resampler_ot
+    G = golden("ot_resample")
+    for c in range(int(G["n_cases"])):
+        g = lambda k: G[f"c{c}_{k}"]
+        x, w = cu(g("x")).requires_grad_(), cu(g("w")).requires_grad_()
+        p_res, w_res, idx = resampler_ot(x, w, eps=float(g("eps")))
+        assert int(ops.OtResample.last_iters.item()) == int(g("iters")), (c, int(ops.OtResample.last_iters.item()), int(g("iters")))
+        # particles here are O(50): rtol 1e-4 / atol 1e-5 on the cloud's own scale (the reference runs this in fp64)
+        close(p_res, g("p_res"), rtol=1e-4, atol=1e-5 * float(np.abs(g("x")).max()) * 10, what=f"case {c} particles")
+        assert np.array_equal(w_res.cpu().numpy(), g("w_res")) and np.array_equal(idx.cpu().numpy(), g("idx"))
+        (p_res * cu(g("gp"))).sum().backward()
+        grad_close(x.grad, g("dx"), f"case {c} dx")
+        assert w.grad is None or float(w.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,N", [(4, 100), (8, 1024), (2, 2500), (3, 37)])
+def test_ot_resample_vs_oracle(B, N):
+    g = torch.Generator().manual_seed(B * 31 + N)
+    w = torch.softmax(torch.randn(B, N, generator=g) * 2.0, -1)
+    x = torch.randn(B, N, 2, generator=g) * torch.tensor([15.0, 6.0]) + torch.tensor([10.0, -30.0])
+    xo = x.clone().requires_grad_()
+    po, wo, io, iters = O.ot_resample(xo, w, return_iters=True)
+    xg = cu(x).requires_grad_()
+    pg = ops.ot_resample(xg, cu(w).log())
+    assert int(ops.OtResample.last_iters.item()) == iters
+    close(pg, po, rtol=1e-4, atol=2e-3, what="particles")
+    gp = torch.randn(B, N, 2, generator=g)
+    (po * gp).sum().backward()
+    (pg * cu(gp)).sum().backward()
+    grad_close(xg.grad, xo.grad, "dx")
+
+
+def test_ot_resample_properties_full_size():
+    """B = N = 1024 (BASELINE config 3 shape): plan column sums = N w_j, so the weighted mean is preserved exactly:
+    (1/N) sum_i x'_i = sum_j w_j x_j; output stays inside the cloud's bounding box."""
+    g = torch.Generator().manual_seed(11)
+    B = N = 1024
+    w = cu(torch.softmax(torch.randn(B, N, generator=g) * 2.0, -1))
+    x = cu(torch.randn(B, N, 2, generator=g) * 20.0)
+    p = ops.ot_resample(x, w.log())
+    close(p.mean(1), (w[..., None] * x).sum(1), rtol=1e-3, atol=2e-2, what="weighted mean preserved")
+    assert bool((p.amax(1) <= x.amax(1) + 1e-3).all()) and bool((p.amin(1) >= x.amin(1) - 1e-3).all())
+    it = int(ops.OtResample.last_iters.item())
+    assert 10 < it <= 100, it
