@@ -1,0 +1,138 @@
+"""Roofline and CPU-baseline legs of bench.py (kept apart so a failure here can never lose the headline line).
+
+Algorithmic work per particle per launch (restated in DESIGN.md):
+  coupling stack pass, D=2, row context hoisted: 1280 FLOP forward, 2x that backward; 20 B of HBM traffic
+  particle encoder + Gaussian likelihood + weight update: 3136 + 96 FLOP forward; 2x backward
+  soft resampling: 32 B forward (4 w + 8 gather in, 8 + 4 + 8 out), 36 B backward; weight update: 20 B
+The kernels of the headline workload are FP32-pipe / SFU bound, not HBM or tensor bound (hidden width 8), so the
+denominator for them is the FP32 FFMA peak MEASURED on this GPU by libnfdpf's probe kernel; the HBM-bound kernels use
+MEASURED_PEAKS.json's copy bandwidth (fallback 6650 GB/s)."""
+import json
+import os
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _events(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e-3
+
+
+def measured_peaks(dev):
+    from normalizing_flows_dpfs_b200 import _lib as L
+    out = torch.zeros(4, device=dev)
+    peaks = {}
+    for kind, name, mult in ((0, "fp32_tflops", 2.0), (1, "sfu_tops", 1.0)):
+        ops = [0]
+
+        def run():
+            ops[0] = L.load().nfdpf_peak_probe(kind, 4096, L.ptr(out), L.stream())
+        sec = _events(run, n=5, warm=2)
+        peaks[name] = ops[0] * mult / sec / 1e12
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        peaks["hbm_gbs"], peaks["hbm_source"] = json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    else:
+        peaks["hbm_gbs"], peaks["hbm_source"] = 6650.0, "fallback (B200_PROFILING.md)"
+    return peaks
+
+
+def kernel_table(a, dpf, dev):
+    """Time each libnfdpf kernel of the workload alone at the workload's shapes (CUDA events on the current stream)."""
+    from normalizing_flows_dpfs_b200 import ops
+    from normalizing_flows_dpfs_b200.nf.flows import pack_parameters
+    B, N = a.B, a.N
+    P = B * N
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(B, N, 2, device=dev, generator=g) * 20
+    w = torch.softmax(torch.randn(B, N, device=dev, generator=g) * 3, -1)
+    ctx36, enc = torch.randn(B, 36, device=dev, generator=g), torch.randn(B, 32, device=dev, generator=g)
+    off = torch.rand(B, device=dev, generator=g) / N
+    mk = torch.linspace(0.0, (N - 1.0) / N, N).to(dev)
+    gy, gl = torch.randn(B, N, 2, device=dev, generator=g), torch.randn(B, N, device=dev, generator=g)
+    with torch.no_grad():
+        pk_c, pk_d = pack_parameters([dpf.cond_model]), pack_parameters([dpf.nf_dyn])
+        pe = pack_parameters([dpf.particle_encoder])
+    rows = []
+
+    def add(name, fwd, flops_f, bytes_f, flops_b, bytes_b, grads, per_step_f, per_step_b):
+        out = fwd()
+        outs = [o for o in (out if isinstance(out, tuple) else (out,)) if o is not None and o.requires_grad]
+        tf = _events(lambda: fwd(), n=5)
+        rows.append(dict(kernel=name + "_fwd", sec=tf, flops=flops_f * P, bytes=bytes_f * P, launches_per_step=per_step_f))
+        if outs:
+            gouts = [grads[tuple(o.shape)] for o in outs]
+
+            def bwd():
+                torch.autograd.backward(outs, gouts, retain_graph=True)
+            tb = _events(bwd, n=5)
+            rows.append(dict(kernel=name + "_bwd", sec=tb, flops=flops_b * P, bytes=bytes_b * P, launches_per_step=per_step_b))
+
+    grads = {(B, N, 2): gy, (B, N): gl}
+    pkc, pkd = pk_c.clone().requires_grad_(), pk_d.clone().requires_grad_()
+    xr = x.clone().requires_grad_()
+    add("coupling_D2_C36", lambda: ops.coupling_stack(pkc, xr, ctx36, None, 2, True), 1280, 20, 2560, 40, grads, 1, 1)
+    add("coupling_D2_C4", lambda: ops.coupling_stack(pkd, xr, ctx36[:, :4].contiguous(), None, 2, True), 1280, 20, 2560, 40, grads, 2, 2)
+    per = pe.clone().requires_grad_()
+    lw0 = w.log()
+    mode = a.measurement
+    p0, p1 = {"gaussian": (1.0, 10.0), "cos": (0.0, 1.0), "CRNVP": (0.0, 2.5)}[mode]
+    cnf = pack_parameters([dpf.cnf_measurement]).detach().clone().requires_grad_() if mode == "CRNVP" else None
+    mflop = 3136 + 96 + (9216 if mode == "CRNVP" else 0)
+
+    def meas():
+        o = ops.measure_update(per, cnf, enc, xr, lw0, gl, gl, mode, p0=p0, p1=p1)
+        return o[0], o[2]
+    add("measure_update_" + mode, meas, mflop, 28, 2 * mflop, 24, grads, 1, 1)
+    wr = w.clone().requires_grad_()
+    if a.resampler == "soft":
+        add("soft_resample", lambda: ops.soft_resample(xr, wr, off, mk, 0.5)[:2], 0, 32, 0, 36, grads, 1, 1)
+    else:
+        add("ot_resample", lambda: ops.ot_resample(xr, lw0), 0, 0, 0, 0, grads, 1, 1)
+    return rows
+
+
+def roofline_and_cpu(a, dpf, resident, dev, ms_per_step):
+    peaks = measured_peaks(dev)
+    rows = kernel_table(a, dpf, dev)
+    step_sec = ms_per_step * 1e-3 / a.T          # one filter timestep, forward + backward
+    for r in rows:
+        r["share_of_step"] = r["sec"] * r["launches_per_step"] / step_sec
+        if r["flops"] > 0 and r["flops"] / max(r["bytes"], 1) > 10:   # arithmetic intensity >> machine balance: compute bound
+            r.update(bound="fp32", achieved=r["flops"] / r["sec"] / 1e12, peak=peaks["fp32_tflops"], unit="TFLOP/s")
+        else:
+            r.update(bound="hbm", achieved=r["bytes"] / r["sec"] / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
+        r["frac"] = r["achieved"] / r["peak"]
+    top = max(rows, key=lambda r: r["share_of_step"])
+    out = {"roofline": {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
+                        "frac": top["frac"], "traffic": None, "peak_source": "FFMA probe kernel measured in this run" if top["bound"] == "fp32"
+                        else peaks["hbm_source"], "share_of_step": top["share_of_step"]},
+           "roofline_kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()} for r in rows],
+           "peaks": peaks}
+    if not a.no_cpu_baseline:
+        from bench_reference import cpu_filter_step, sample_shape
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        B, T = sample_shape(a)
+        cpu_filter_step(a, min(B, 2), 1)   # warm-up
+        t0 = time.perf_counter()
+        n = 0
+        while n < 2 and time.perf_counter() - t0 < 25:
+            cpu_filter_step(a, B, T, n)
+            n += 1
+        sec = (time.perf_counter() - t0) / n
+        out["cpu_baseline"] = {"value": B * a.N * T / sec, "unit": "particle-steps/s", "cores": cores, "kind": "port",
+                               "sample": "oracle port (torch CPU, %d threads) of the same filter step fwd+bwd on B=%d of %d trajectories x T=%d of %d "
+                                         "steps at N=%d, mean of %d runs" % (cores, B, a.B, T, a.T, a.N, n)}
+    return out

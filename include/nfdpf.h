@@ -131,6 +131,10 @@ int nfdpf_ot_resample_fwd(const float* particles, const float* logw, float eps, 
 int nfdpf_ot_resample_bwd(const float* g_out, const float* saved, float eps, int B, int N, int d, float* d_particles,
                           void* stream);
 
+/* ---- pipe-peak probe (measurement aid for bench.py): launches streams of independent FFMA (kind 0) or
+ * ex2.approx (kind 1) instructions; returns the number of instructions issued (time it with CUDA events). */
+int64_t nfdpf_peak_probe(int kind, int iters, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ SIGNATURES = {
     "nfdpf_ot_workspace": (_I64, [_I, _I]),
     "nfdpf_ot_resample_fwd": (_I, [_P, _P, _F, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "nfdpf_ot_resample_bwd": (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
+    "nfdpf_peak_probe": (_I64, [_I, _I, _P, _P]),
     "nfdpf_coupling_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "nfdpf_coupling_bwd_workspace": (_I64, [_I, _I, _I, _I, _I, _I]),
     "nfdpf_measure_fwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
