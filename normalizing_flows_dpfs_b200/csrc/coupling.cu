@@ -256,6 +256,9 @@ extern "C" int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C
     NFDPF_REQUIRE(n_flows >= 1 && 4 * n_flows <= MAX_FCNN, "coupling_bwd: n_flows must be in 1..4 (got %d)", n_flows);
     NFDPF_REQUIRE(C_row >= 0 && C_part >= 0 && (C_row == 0 || row_ctx) && (C_part == 0 || part_ctx), "coupling_bwd: context pointers/sizes inconsistent");
     NFDPF_REQUIRE(C_row <= 64, "coupling_bwd: C_row <= 64 supported (got %d)", C_row);
+    if (D == 2 && C_part == 0)  // headline shape: register-accumulating kernel
+        return launch_coupling_bwd_d2(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace,
+                                      (cudaStream_t)stream);
 #define X(HALF_, CP_) \
     if (D == 2 * HALF_ && C_part == CP_) return launch_bwd<HALF_, CP_>(packed, n_flows, C_row, y, row_ctx, part_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_part_ctx, d_packed, workspace, (cudaStream_t)stream);
     NFDPF_COUPLING_SHAPES(X)
