@@ -6,6 +6,7 @@
 // The reference materialises the (B,N,32) encodings, the repeated (B,N,32) observation encodings and, for CRNVP,
 // eight (P,48) concatenations; here the only HBM traffic is particles in, (B,N) vectors out.
 #include "coupling.cuh"
+#include "mma_tile.cuh"
 
 namespace nfdpf {
 
@@ -160,17 +161,50 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 }
 
 // ----------------------------------------------------------------------------------------------- backward
-// particle-encoder tile rows / outputs
+// particle-encoder tile rows (row = feature, column = particle of the CTA batch; stride TSM, see mma_tile.cuh)
 struct PR {
-    static constexpr int ONE = 0, X = 1, A1 = 3, A2 = 19, D1 = 51, D2 = 67, D3 = 99, COUNT = 131;
+    static constexpr int ONE = 0, ZERO = 1, X = 2, A1 = 4, A2 = 20, D1 = 52, D2 = 68, D3 = 100, COUNT = 132;
 };
-__device__ void pe_entry(int e, int& ra, int& rb) {  // e in packed PE order
-    if (e < PE_B1) { ra = PR::D1 + e / 2; rb = PR::X + e % 2; return; }
-    if (e < PE_W2) { ra = PR::D1 + (e - PE_B1); rb = PR::ONE; return; }
-    if (e < PE_B2) { ra = PR::D2 + (e - PE_W2) / 16; rb = PR::A1 + (e - PE_W2) % 16; return; }
-    if (e < PE_W3) { ra = PR::D2 + (e - PE_B2); rb = PR::ONE; return; }
-    if (e < PE_B3) { ra = PR::D3 + (e - PE_W3) / 32; rb = PR::A2 + (e - PE_W3) % 32; return; }
-    ra = PR::D3 + (e - PE_B3); rb = PR::ONE;
+
+// Particle-encoder weight gradients of one batch on the tensor path (3xTF32), added into s_accpe (packed PE order).
+//   warps 0,1: dW3 | db3 = delta3(16 rows each) x [a2 (4 n-tiles) | 1]
+//   warps 2,3: dW2 | db2 = delta2(16 rows each) x [a1 (2 n-tiles) | 1];  warp 2 also dW1 | db1 = delta1 x [x0 x1 1]
+__device__ __forceinline__ void pe_weight_grads_mma(const float* __restrict__ s_tile, float* __restrict__ s_accpe) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    if (warp < 2) {
+        float c[5][4] = {};
+        const int rowB[5] = {PR::A2 + g, PR::A2 + 8 + g, PR::A2 + 16 + g, PR::A2 + 24 + g, g == 0 ? PR::ONE : PR::ZERO};
+        mma_outer<5>(s_tile, PR::D3 + 16 * warp, rowB, TP, c);
+        const int o = 16 * warp + g;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            float* w = s_accpe + PE_W3 + o * 32 + 8 * n + 2 * t;
+            w[0] += c[n][0]; w[1] += c[n][1]; w[8 * 32] += c[n][2]; w[8 * 32 + 1] += c[n][3];
+        }
+        if (t == 0) { s_accpe[PE_B3 + o] += c[4][0]; s_accpe[PE_B3 + o + 8] += c[4][2]; }
+    } else {
+        float c[3][4] = {};
+        const int rowB[3] = {PR::A1 + g, PR::A1 + 8 + g, g == 0 ? PR::ONE : PR::ZERO};
+        mma_outer<3>(s_tile, PR::D2 + 16 * (warp - 2), rowB, TP, c);
+        const int o = 16 * (warp - 2) + g;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+            float* w = s_accpe + PE_W2 + o * 16 + 8 * n + 2 * t;
+            w[0] += c[n][0]; w[1] += c[n][1]; w[8 * 16] += c[n][2]; w[8 * 16 + 1] += c[n][3];
+        }
+        if (t == 0) { s_accpe[PE_B2 + o] += c[2][0]; s_accpe[PE_B2 + o + 8] += c[2][2]; }
+        if (warp == 2) {
+            float c1[1][4] = {};
+            const int rowX[1] = {g < 2 ? PR::X + g : (g == 2 ? PR::ONE : PR::ZERO)};
+            mma_outer<1>(s_tile, PR::D1, rowX, TP, c1);
+            if (t == 0) {   // columns 0,1 = dW1[o][0..1]
+                s_accpe[PE_W1 + 2 * g] += c1[0][0]; s_accpe[PE_W1 + 2 * g + 1] += c1[0][1];
+                s_accpe[PE_W1 + 2 * (g + 8)] += c1[0][2]; s_accpe[PE_W1 + 2 * (g + 8) + 1] += c1[0][3];
+            } else if (t == 1) {  // column 2 = db1[o]
+                s_accpe[PE_B1 + g] += c1[0][0]; s_accpe[PE_B1 + g + 8] += c1[0][2];
+            }
+        }
+    }
 }
 
 template <int MODE>
@@ -182,24 +216,20 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_red[33];
     const int tid = threadIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
-    constexpr int TROWS = MODE == MODE_CNF ? (RC::COUNT > PR::COUNT ? RC::COUNT : PR::COUNT) : PR::COUNT;
+    constexpr int TILE_FLOATS = MODE == MODE_CNF && RC::COUNT * TS > PR::COUNT * TSM ? RC::COUNT * TS : PR::COUNT * TSM;
     float* s_pe = smem;
     float* s_enc = s_pe + PE_SIZE;
     float* s_img = s_enc + 36;
     float* s_hb = s_img + n_fcnn * LC::SIZE;
-    float* s_tile = s_hb + n_fcnn * H;                       // [TROWS][TS], PE and CNF phases alias
-    float* s_accpe = s_tile + TROWS * TS;                    // [1648]
+    float* s_tile = s_hb + n_fcnn * H;                       // PE tile [PR::COUNT][TSM]; the CNF tile [RC::COUNT][TS] aliases it
+    float* s_accpe = s_tile + TILE_FLOATS;                   // [1648]
     float* s_acccnf = s_accpe + PE_SIZE;                     // [n_fcnn][RC::NOUT]
     float* s_d1row = s_acccnf + n_fcnn * RC::NOUT;           // [n_fcnn][8] (unused sums; C_row = 0)
     float* s_denc = s_d1row + n_fcnn * H + 4;                // [32]
-    int* s_tabpe = reinterpret_cast<int*>(s_denc + 32);      // [1648]
-    int* s_tabcnf = s_tabpe + PE_SIZE;                       // [RC::NOUT]
+    int* s_tabcnf = reinterpret_cast<int*>(s_denc + 32);     // [RC::NOUT]
     for (int e = tid; e < PE_SIZE; e += TP) {
         s_pe[e] = pe[e];
         s_accpe[e] = 0.f;
-        int ra, rb;
-        pe_entry(e, ra, rb);
-        s_tabpe[e] = ra | (rb << 16);
     }
     if (MODE == MODE_CNF) {
         const int pf = packed_fcnn_size(16, 32);
@@ -317,19 +347,20 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
             }
             if (live) *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
             // stage the PE tile (aliases the CNF tile: all CNF accumulation of this batch ended with a barrier)
-            s_tile[PR::ONE * TS + tid] = 1.0f;
-            s_tile[(PR::X + 0) * TS + tid] = x.x;
-            s_tile[(PR::X + 1) * TS + tid] = x.y;
+            s_tile[PR::ONE * TSM + tid] = 1.0f;
+            s_tile[PR::ZERO * TSM + tid] = 0.0f;
+            s_tile[(PR::X + 0) * TSM + tid] = x.x;
+            s_tile[(PR::X + 1) * TSM + tid] = x.y;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { s_tile[(PR::A1 + k) * TS + tid] = a1[k]; s_tile[(PR::D1 + k) * TS + tid] = d1[k]; }
+            for (int k = 0; k < 16; ++k) { s_tile[(PR::A1 + k) * TSM + tid] = a1[k]; s_tile[(PR::D1 + k) * TSM + tid] = d1[k]; }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                s_tile[(PR::A2 + j) * TS + tid] = a2[j];
-                s_tile[(PR::D2 + j) * TS + tid] = d2[j];
-                s_tile[(PR::D3 + j) * TS + tid] = de[j];
+                s_tile[(PR::A2 + j) * TSM + tid] = a2[j];
+                s_tile[(PR::D2 + j) * TSM + tid] = d2[j];
+                s_tile[(PR::D3 + j) * TSM + tid] = de[j];
             }
             __syncthreads();
-            tile_accumulate(s_tabpe, PE_SIZE, s_tile, s_accpe, 0, nullptr);
+            pe_weight_grads_mma(s_tile, s_accpe);
             __syncthreads();
         }
         // d_enc[b][k] = sum over the row's particles (deterministic: through the tile)
@@ -363,10 +394,9 @@ static size_t fwd_smem(int mode, int n_flows, int N) {
 }
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    const int trows = mode == MODE_CNF ? (RC::COUNT > PR::COUNT ? RC::COUNT : PR::COUNT) : PR::COUNT;
-    size_t fl = (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + (size_t)trows * TS + PE_SIZE + (size_t)n_fcnn * RC::NOUT +
-                n_fcnn * H + 4 + 32;
-    return fl * sizeof(float) + ((size_t)PE_SIZE + (mode == MODE_CNF ? RC::NOUT : 0)) * sizeof(int);
+    const size_t tile = mode == MODE_CNF && (size_t)RC::COUNT * TS > (size_t)PR::COUNT * TSM ? (size_t)RC::COUNT * TS : (size_t)PR::COUNT * TSM;
+    size_t fl = (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + tile + PE_SIZE + (size_t)n_fcnn * RC::NOUT + n_fcnn * H + 4 + 32;
+    return fl * sizeof(float) + (size_t)(mode == MODE_CNF ? RC::NOUT : 0) * sizeof(int);
 }
 
 template <int MODE>

@@ -1,0 +1,53 @@
+// Weight-gradient contractions on the (legacy, warp-level) tensor path: dW[o][i] = sum_p delta[p][o] * act[p][i].
+// K = particles is the long dimension; the deltas / activations of the CTA's batch sit transposed in a shared-memory
+// tile (row = feature, column = particle).  mma.sync.m16n8k8 TF32 with the 3xTF32 split (hi*hi + hi*lo + lo*hi) keeps
+// ~2^-21 relative accuracy, which the rtol 1e-4 gradient bar needs (plain TF32 is 2^-11).  These contractions are the
+// only "dense" GEMMs on the path (M,N <= 48); tcgen05 tiles (M >= 64) would be >85 % padding here.
+#pragma once
+#include "common.cuh"
+
+namespace nfdpf {
+
+constexpr int TSM = 132;  // tile row stride in floats: == 4 (mod 32) makes the m16n8k8 fragment loads conflict-free
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// One warp: c[n] (16 x 8 accumulator fragments) += A(16 delta rows starting at tile row rowA) x B_n over all particles
+// [0, np) (np multiple of 8).  rowB[n] is THIS LANE's tile row for column (lane >> 2) of n-tile n -- callers build it so
+// that bias / padding columns point at the ONE / ZERO rows of the tile.
+template <int NT>
+__device__ __forceinline__ void mma_outer(const float* __restrict__ tile, int rowA, const int (&rowB)[NT], int np, float (&c)[NT][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* a_lo = tile + (rowA + g) * TSM + t;
+    const float* a_hi = tile + (rowA + g + 8) * TSM + t;
+#pragma unroll 2
+    for (int k0 = 0; k0 < np; k0 += 8) {
+        uint32_t ah[4], al[4];
+        split_tf32(a_lo[k0], ah[0], al[0]);
+        split_tf32(a_hi[k0], ah[1], al[1]);
+        split_tf32(a_lo[k0 + 4], ah[2], al[2]);
+        split_tf32(a_hi[k0 + 4], ah[3], al[3]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const float* b = tile + rowB[n] * TSM + k0 + t;
+            uint32_t bh[2], bl[2];
+            split_tf32(b[0], bh[0], bl[0]);
+            split_tf32(b[4], bh[1], bl[1]);
+            mma_tf32(c[n], ah, bh);
+            mma_tf32(c[n], ah, bl);
+            mma_tf32(c[n], al, bh);
+        }
+    }
+}
+
+}  // namespace nfdpf
