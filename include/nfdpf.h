@@ -48,11 +48,13 @@ int64_t nfdpf_launch_count(void);
  * Indices are bit-exact with the reference CPU path (ATen cascade row-sum + fp64-accumulated cumsum). */
 int nfdpf_soft_resample_fwd(const float* particles, const float* probs, const float* offsets, const float* markers,
                             double alpha, int B, int N, int d, float* particles_out, float* probs_out,
-                            int64_t* idx_out, float* saved, void* stream);
-/* backward: g_particles (B,N,d), g_probs (B,N) (either may be NULL = zero) -> d_particles (B,N,d), d_probs (B,N) */
+                            int64_t* idx_out, float* saved, float* logprobs_out, void* stream);
+/* logprobs_out (B,N) or NULL: log of probs_out (DPFs.py:167), saves the filter loop one elementwise pass.
+ * backward: g_particles (B,N,d), g_probs (B,N), g_logprobs (B,N) (each may be NULL = zero)
+ * -> d_particles (B,N,d), d_probs (B,N) */
 int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_probs, const float* probs, const int64_t* idx,
                             const float* saved, double alpha, int B, int N, int d, float* d_particles,
-                            float* d_probs, void* stream);
+                            float* d_probs, const float* g_logprobs, void* stream);
 
 /* ---- (K2, weight half) log-weight update + normalisation: DPFs.py:187-192, utils.py:39-44 ----------
  * logw = logw_prev + lki + prior - propose (NULL terms are skipped); probs = softmax_N(logw) + add_eps;
@@ -68,7 +70,9 @@ int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw, const flo
 
 /* ---- (K1) fused coupling stack: nf/flows.py:155-179, 215-239; nf/models.py:11-30, 45-61 ---------------
  * x (P,D); context = [row_ctx (B,C_row) broadcast over the N particles of a row | part_ctx (P,C_part)],
- * C = C_row + C_part (either may be 0).  inverse=0: flows 0..n-1 forward; inverse=1: flows n-1..0 inverse.
+ * C = C_row + C_part (either may be 0).  `inverse` is a bit field: bit 0 clear = flows 0..n-1 forward, set = flows
+ * n-1..0 inverse; bit 1 set = return jac = -log_det in `log_det` (model/models.py:325, 350) -- the backward must be
+ * called with the same value.
  * y (P,D), log_det (P,).  Supported: D = 2 with C_part = 0 (row-constant context hoisted out of layer 1);
  * D even <= 32 with any C <= 64 (general path). */
 int nfdpf_coupling_fwd(const float* packed, int n_flows, int D, int C_row, int C_part, const float* x,
@@ -134,6 +138,20 @@ int nfdpf_ot_resample_bwd(const float* g_out, const float* saved, float eps, int
 /* ---- pipe-peak probe (measurement aid for bench.py): launches streams of independent FFMA (kind 0) or
  * ex2.approx (kind 1) instructions; returns the number of instructions issued (time it with CUDA events). */
 int64_t nfdpf_peak_probe(int kind, int iters, float* out, void* stream);
+
+/* ---- per-step glue --------------------------------------------------------------------------------------
+ * motion_moments: out = (particles + vel_b) + noise (model/models.py:191-204, noise injected by the caller) and, if
+ * ctx != NULL, ctx[b, ctx_off .. ctx_off+3] = [mean_x, mean_y, std_x, std_y] of out (unbiased; models.py:309-310).
+ * proposal_terms: prior = dens(back - (phys - noise)) - jac_back, propose = dens(noise) + jac_dyn + jac_prop with
+ * dens the 2-d N(0, sigma^2 I) log-density (utils.py:17-37; model/models.py:369-376); jac_* may be NULL (= 0).
+ * backward: d_back = -g_prior (back - phys + noise)/sigma^2, d_phys = -d_back, neg_g_prior = -g_prior (may be NULL). */
+int nfdpf_motion_moments(const float* particles, const float* vel, const float* noise, int B, int N, int d, float* out,
+                         float* ctx, int ctx_stride, int ctx_off, void* stream);
+int nfdpf_proposal_terms_fwd(const float* back, const float* phys, const float* noise, const float* jac_back,
+                             const float* jac_dyn, const float* jac_prop, float sigma, int64_t P, float* prior,
+                             float* propose, void* stream);
+int nfdpf_proposal_terms_bwd(const float* g_prior, const float* back, const float* phys, const float* noise, float sigma,
+                             int64_t P, float* d_back, float* d_phys, float* neg_g_prior, void* stream);
 
 #ifdef __cplusplus
 }

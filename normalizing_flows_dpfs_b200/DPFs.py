@@ -117,6 +117,8 @@ class DPF(nn.Module):
         fused = isinstance(self.measurement_model, _FusedMeasurement)
         lists = {k: [] for k in ("particles", "probs", "noise", "lki", "index", "jac", "prior")}
         obs_likelihood, self.fired = 0.0, []
+        from . import ops
+        soft = self.param.resampler_type == "soft"
         for step in range(self.seq_len):
             index_p = identity_idx
             if self.force_resample is None:
@@ -124,27 +126,53 @@ class DPF(nn.Module):
             else:
                 fire = bool(self.force_resample)
             self.fired.append(fire)
-            if fire:
-                if inj is not None and "offsets" in inj and self.param.resampler_type == "soft":
-                    particles, probs_res, index_p = self.resampler.resampling(particles, particle_probs, random_offset=inj["offsets"][:, step],
-                                                                              **self.resampler.kargs)
-                else:
-                    particles, probs_res, index_p = self.resampler(particles, particle_probs)
+            if fire and soft:   # one kernel: scan + search + gather + renormalise (+ log of the new weights, DPFs.py:167)
+                off = inj["offsets"][:, step] if inj is not None and "offsets" in inj else None
+                particles, probs_res, index_p, logw_prev = self.resampler.resampling(particles, particle_probs, random_offset=off,
+                                                                                     want_log=True, **self.resampler.kargs)
+            elif fire:
+                particles, probs_res, index_p = self.resampler(particles, particle_probs)
                 logw_prev = probs_res.log()
             else:
                 logw_prev = particle_probs.log()
             noise = inj["noise"][:, step] if inj is not None and "noise" in inj else None
-            particles_physical, noise = self.motion_update(particles, vel, pos_noise=self.pos_noise, noise=noise)
-            vel = vel_input[:, step, :]
-            particles_dynamical, jac = nf_dynamic_model(self.nf_dyn, particles_physical, particle_probs.shape, NF=self.NF)
             encodings = self.encoder(obs[:, step].float())
-            if fused:    # measurement + weight update + normalisation in one kernel
-                propose_particle, prior_log, propose_log = _proposal_terms(self, particles_dynamical, particles_physical, encodings, noise, jac)
-                cancel = not self.NFcond   # prior == propose: they cancel exactly in DPFs.py:187
-                lki_log, logw, particle_probs, row_sum, ess_inv = self.measurement_model.forward_update(
-                    encodings, propose_particle, logw_prev, None if cancel else prior_log, None if cancel else propose_log)
+            if fused:
+                # ---- fused step: 6 libnfdpf launches (motion+moments, 3 coupling stacks, densities, measurement+update)
+                if noise is None:
+                    noise = torch.normal(mean=0.0, std=self.pos_noise, size=(B, N, 2)).to(particles.device, non_blocking=True)
+                ctx_phys = torch.empty(B, 4, dtype=torch.float32, device=particles.device) if self.NF else None
+                particles_physical = ops.motion_moments(particles, vel, noise, ctx_phys, 0)
+                vel = vel_input[:, step, :]
+                if self.NF:
+                    particles_dynamical, jac = self.nf_dyn.run_stack(particles_physical, row_ctx=ctx_phys, inverse=True, neg_logdet=True)
+                else:
+                    particles_dynamical, jac = particles_physical, None
+                if self.NFcond:
+                    ctx_prop = torch.empty(B, self.hidden_size + 4, dtype=torch.float32, device=particles.device)
+                    ctx_prop[:, :self.hidden_size] = encodings.detach()      # proposal sees a detached encoding, models.py:360-361
+                    ops.row_moments(particles_dynamical, ctx_prop, self.hidden_size)
+                    propose_particle, jac_prop = self.cond_model.run_stack(particles_dynamical, row_ctx=ctx_prop, inverse=True, neg_logdet=True)
+                    if self.NF:   # push the proposal back through the dynamics flow (context: moments of the physical cloud)
+                        back, jac_back = self.nf_dyn.run_stack(propose_particle, row_ctx=ctx_phys, inverse=False, neg_logdet=True)
+                    else:
+                        back, jac_back = propose_particle, None
+                    prior_log, propose_log = ops.proposal_terms(back, particles_physical, noise, jac_back, jac, jac_prop, self.pos_noise)
+                    lki_log, logw, particle_probs, row_sum, ess_inv = self.measurement_model.forward_update(
+                        encodings, propose_particle, logw_prev, prior_log, propose_log)
+                else:             # prior == proposal density: the two cancel exactly in DPFs.py:187
+                    propose_particle = particles_dynamical
+                    if self.NF:
+                        _, prior_log = ops.proposal_terms(particles_physical, particles_physical, noise, None, jac, None, self.pos_noise)
+                    lki_log, logw, particle_probs, row_sum, ess_inv = self.measurement_model.forward_update(
+                        encodings, propose_particle, logw_prev, None, None)
+                if jac is None:
+                    jac = torch.zeros(B, N, device=particles.device)
                 obs_likelihood = obs_likelihood + row_sum.sum() / (B * N)
             else:
+                particles_physical, noise = self.motion_update(particles, vel, pos_noise=self.pos_noise, noise=noise)
+                vel = vel_input[:, step, :]
+                particles_dynamical, jac = nf_dynamic_model(self.nf_dyn, particles_physical, particle_probs.shape, NF=self.NF)
                 propose_particle, lki_log, prior_log, propose_log = proposal_likelihood(
                     self.cond_model, self.nf_dyn, self.measurement_model, particles_dynamical, particles_physical, encodings, noise, jac,
                     self.NF, self.NFcond, prototype_density=self.prototype_density)
@@ -269,13 +297,6 @@ def _weight_norm(logw):
 def _weight_update(logw_prev, lki, prior, propose):
     from . import ops
     return ops.weight_update(logw_prev, lki, prior, propose, 1e-12)
-
-
-def _proposal_terms(dpf, particles_dynamical, particles_physical, encodings, noise, jac):
-    """proposal_likelihood (reference models.py:358-379) minus the measurement call, which is fused downstream."""
-    out = proposal_likelihood(dpf.cond_model, dpf.nf_dyn, lambda enc, x: None, particles_dynamical, particles_physical, encodings,
-                              noise, jac, dpf.NF, dpf.NFcond, prototype_density=dpf.prototype_density)
-    return out[0], out[2], out[3]
 
 
 def _dump(path, out, **extra):

@@ -15,8 +15,11 @@ SIGNATURES = {
     "nfdpf_version": (_I, []),
     "nfdpf_last_error": (C.c_char_p, []),
     "nfdpf_launch_count": (_I64, []),
-    "nfdpf_soft_resample_fwd": (_I, [_P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "nfdpf_soft_resample_bwd": (_I, [_P, _P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P]),
+    "nfdpf_soft_resample_fwd": (_I, [_P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "nfdpf_soft_resample_bwd": (_I, [_P, _P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P, _P]),
+    "nfdpf_motion_moments": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P]),
+    "nfdpf_proposal_terms_fwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _I64, _P, _P, _P]),
+    "nfdpf_proposal_terms_bwd": (_I, [_P, _P, _P, _P, _F, _I64, _P, _P, _P, _P]),
     "nfdpf_weight_update_fwd": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P]),
     "nfdpf_weight_update_bwd": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P]),
     "nfdpf_row_moments": (_I, [_P, _I, _I, _I, _P, _I, _I, _P]),

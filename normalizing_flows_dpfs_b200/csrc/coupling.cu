@@ -11,7 +11,7 @@ constexpr int MAX_FCNN = 16;      // n_flows <= 4
 template <int HALF, int CP>
 __global__ void __launch_bounds__(TP)
 coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ x,
-                    const float* __restrict__ row_ctx, const float* __restrict__ part_ctx, int inverse, int N, int chunk,
+                    const float* __restrict__ row_ctx, const float* __restrict__ part_ctx, int flags, int N, int chunk,
                     float* __restrict__ y, float* __restrict__ log_det) {
     using L = Lay<HALF, CP>;
     constexpr int D = 2 * HALF;
@@ -27,6 +27,7 @@ coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     __syncthreads();
     hoist_row_context<HALF, CP>(s_img, s_w1r, row_ctx + (size_t)b * C_row, C_row, n_fcnn, s_hb, tid, TP);
     __syncthreads();
+    const int inverse = flags & 1;  // bit 1: emit jac = -log_det instead of log_det
     const int n0 = blockIdx.x * chunk, n1 = min(N, n0 + chunk);
     for (int n = n0 + tid; n < n1; n += TP) {
         const size_t p = (size_t)b * N + n;
@@ -54,21 +55,21 @@ coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
         }
 #pragma unroll
         for (int i = 0; i < HALF; ++i) { y[p * D + i] = lo[i]; y[p * D + HALF + i] = up[i]; }
-        log_det[p] = ld;
+        log_det[p] = (flags & 2) ? -ld : ld;
     }
 }
 
 template <int HALF, int CP>
 __global__ void __launch_bounds__(TP)
 coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ y,
-                    const float* __restrict__ row_ctx, const float* __restrict__ part_ctx, int inverse, int B, int N,
+                    const float* __restrict__ row_ctx, const float* __restrict__ part_ctx, int flags, int B, int N,
                     const float* __restrict__ g_y, const float* __restrict__ g_ld, float* __restrict__ d_x,
                     float* __restrict__ d_row_ctx, float* __restrict__ d_part_ctx, float* __restrict__ partials) {
     using L = Lay<HALF, CP>;
     using R = Rows<HALF, CP>;
     constexpr int D = 2 * HALF;
     extern __shared__ __align__(16) float smem[];
-    const int n_fcnn = 4 * n_flows, tid = threadIdx.x;
+    const int n_fcnn = 4 * n_flows, tid = threadIdx.x, inverse = flags & 1;
     float* s_img = smem;
     float* s_hb = s_img + n_fcnn * L::SIZE;
     float* s_w1r = s_hb + n_fcnn * H;
@@ -109,7 +110,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
                 glo[i] = live && g_y ? g_y[p * D + i] : 0.f;
                 gup[i] = live && g_y ? g_y[p * D + HALF + i] : 0.f;
             }
-            const float gld = live && g_ld ? g_ld[p] : 0.f;
+            const float gld = live && g_ld ? ((flags & 2) ? -g_ld[p] : g_ld[p]) : 0.f;
 #pragma unroll
             for (int i = 0; i < CP; ++i) { pc[i] = part_ctx[p * CP + i]; gpc[i] = 0.f; s_tile[(R::PC + i) * TS + tid] = pc[i]; }
             if (!inverse) {  // forward pass ran flows 0..n-1 (t1/s1 then t2/s2): walk back n-1..0 (t2/s2 then t1/s1)

@@ -114,11 +114,11 @@ __device__ __forceinline__ void stage_bwd_d2(const float* img_t, const float* im
 
 __global__ void __launch_bounds__(TP)
 coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ y,
-                       const float* __restrict__ row_ctx, int inverse, int B, int N, const float* __restrict__ g_y,
+                       const float* __restrict__ row_ctx, int flags, int B, int N, const float* __restrict__ g_y,
                        const float* __restrict__ g_ld, float* __restrict__ d_x, float* __restrict__ d_row_ctx,
                        float* __restrict__ partials) {
     extern __shared__ __align__(16) float smem[];
-    const int n_fcnn = 4 * n_flows, tid = threadIdx.x;
+    const int n_fcnn = 4 * n_flows, tid = threadIdx.x, inverse = flags & 1;
     float* s_img = smem;
     float* s_hb = s_img + n_fcnn * L2_::SIZE;
     float* s_w1r = s_hb + n_fcnn * H;
@@ -155,7 +155,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
                 const float2 yy = live ? reinterpret_cast<const float2*>(y)[p0 + q] : make_float2(0.f, 0.f);
                 const float2 gg = live && g_y ? reinterpret_cast<const float2*>(g_y)[p0 + q] : make_float2(0.f, 0.f);
                 s_lo[q] = yy.x; s_up[q] = yy.y; s_glo[q] = gg.x; s_gup[q] = gg.y;
-                s_gld[q] = live && g_ld ? g_ld[p0 + q] : 0.f;
+                s_gld[q] = live && g_ld ? ((flags & 2) ? -g_ld[p0 + q] : g_ld[p0 + q]) : 0.f;
             }
             if (!inverse) {
 #pragma unroll 1

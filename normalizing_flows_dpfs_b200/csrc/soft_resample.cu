@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(1024)
 soft_resample_fwd_kernel(const float* __restrict__ particles, const float* __restrict__ probs,
                          const float* __restrict__ offsets, const float* __restrict__ markers, float alpha_f,
                          float one_minus_alpha_f, int hard, int N, int d, float* __restrict__ particles_out,
-                         float* __restrict__ probs_out, int64_t* __restrict__ idx_out, float* __restrict__ saved) {
+                         float* __restrict__ probs_out, int64_t* __restrict__ idx_out, float* __restrict__ saved,
+                         float* __restrict__ logprobs_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* s_q = reinterpret_cast<float*>(smem_raw);  // q -> normalised q -> cum
     float* s_wis = s_q + N;                           // importance weights w / q
@@ -143,7 +144,9 @@ soft_resample_fwd_kernel(const float* __restrict__ particles, const float* __res
     const float S2 = block_allreduce(part, s_red, OpSum(), 0.f);
     for (int i = tid; i < N; i += nt) {
         const size_t o = (size_t)b * N + i;
-        probs_out[o] = __fdiv_rn(probs_out[o], S2);               // :56
+        const float pn = __fdiv_rn(probs_out[o], S2);             // :56
+        probs_out[o] = pn;
+        if (logprobs_out) logprobs_out[o] = logf(pn);             // DPFs.py:167 (particle_probs_resampled.log())
     }
     if (tid == 0) { saved[2 * b] = S; saved[2 * b + 1] = S2; }
 }
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(1024)
 soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __restrict__ g_probs,
                          const float* __restrict__ probs, const int64_t* __restrict__ idx,
                          const float* __restrict__ saved, float alpha_f, float one_minus_alpha_f, int hard, int N, int d,
-                         float* __restrict__ d_particles, float* __restrict__ d_probs) {
+                         float* __restrict__ d_particles, float* __restrict__ d_probs, const float* __restrict__ g_logprobs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* s_idx = reinterpret_cast<int*>(smem_raw);           // local source index per destination
     float* s_gv = reinterpret_cast<float*>(smem_raw) + N;    // dL/dv_i, v_i = w_is[idx_i]
@@ -169,14 +172,17 @@ soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __r
     for (int i = tid; i < N; i += nt) {
         const int j = (int)(idx[(size_t)b * N + i] - (int64_t)N * b);
         s_idx[i] = j;
-        if (g_probs && !hard) {
-            const float v = w[j] * S / qu(j);
-            part += g_probs[(size_t)b * N + i] * (v / S2);   // sum_m g_m w'_m
+        float g = 0.f;   // total gradient reaching w'_i: direct + through log(w'_i)
+        if (!hard && (g_probs || g_logprobs)) {
+            const float wp = (w[j] * S / qu(j)) / S2;
+            if (g_probs) g = g_probs[(size_t)b * N + i];
+            if (g_logprobs) g += g_logprobs[(size_t)b * N + i] / wp;
+            part += g * wp;                                  // sum_m g_m w'_m
         }
+        s_gv[i] = g;
     }
     const float c = block_allreduce(part, s_red, OpSum(), 0.f);
-    for (int i = tid; i < N; i += nt)
-        s_gv[i] = (g_probs && !hard) ? (g_probs[(size_t)b * N + i] - c) / S2 : 0.f;
+    for (int i = tid; i < N; i += nt) s_gv[i] = hard ? 0.f : (s_gv[i] - c) / S2;
     __syncthreads();
     float third = 0.f;
     for (int j = tid; j < N; j += nt) {
@@ -224,7 +230,7 @@ using namespace nfdpf;
 
 extern "C" int nfdpf_soft_resample_fwd(const float* particles, const float* probs, const float* offsets,
                                        const float* markers, double alpha, int B, int N, int d, float* particles_out,
-                                       float* probs_out, int64_t* idx_out, float* saved, void* stream) {
+                                       float* probs_out, int64_t* idx_out, float* saved, float* logprobs_out, void* stream) {
     NFDPF_REQUIRE(particles && probs && offsets && markers && particles_out && probs_out && idx_out && saved,
                   "soft_resample_fwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_fwd: B, N, d must be positive (got %d, %d, %d)", B, N, d);
@@ -235,13 +241,13 @@ extern "C" int nfdpf_soft_resample_fwd(const float* particles, const float* prob
         NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     soft_resample_fwd_kernel<<<B, pick_threads(N), smem, (cudaStream_t)stream>>>(
         particles, probs, offsets, markers, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, d, particles_out,
-        probs_out, idx_out, saved);
+        probs_out, idx_out, saved, logprobs_out);
     return check_launch("soft_resample_fwd");
 }
 
 extern "C" int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_probs, const float* probs,
                                        const int64_t* idx, const float* saved, double alpha, int B, int N, int d,
-                                       float* d_particles, float* d_probs, void* stream) {
+                                       float* d_particles, float* d_probs, const float* g_logprobs, void* stream) {
     NFDPF_REQUIRE(probs && idx && saved && d_particles && d_probs, "soft_resample_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_bwd: B, N, d must be positive");
     NFDPF_REQUIRE(alpha > 0.0 && alpha <= 1.0, "soft_resample_bwd: need 0 < alpha <= 1, got %g", alpha);
@@ -251,6 +257,6 @@ extern "C" int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_
         NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     soft_resample_bwd_kernel<<<B, pick_threads(N), smem, (cudaStream_t)stream>>>(
         g_particles, g_probs, probs, idx, saved, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, d, d_particles,
-        d_probs);
+        d_probs, g_logprobs);
     return check_launch("soft_resample_bwd");
 }

@@ -120,15 +120,13 @@ def nf_dynamic_model(dynamical_nf, dynamic_particles, jac_shape, NF=False, forwa
     if not NF:
         return dynamic_particles, torch.zeros(jac_shape, device=dynamic_particles.device)
     ctx = _moments_context(dynamic_particles, mean, std)
-    out, log_det = dynamical_nf.run_stack(dynamic_particles, row_ctx=ctx, inverse=not forward)
-    return out, -log_det
+    return dynamical_nf.run_stack(dynamic_particles, row_ctx=ctx, inverse=not forward, neg_logdet=True)
 
 
 def normalising_flow_propose(cond_model, particles_pred, obs, flow=RealNVP_cond, n_sequence=2, hidden_dimension=8, obser_dim=None):
     """Proposal flow with context [obs encoding, mean_N, std_N] (reference models.py:334-356)."""
     ctx = _moments_context(particles_pred, lead=obs)
-    out, log_det = cond_model.run_stack(particles_pred, row_ctx=ctx, inverse=True)
-    return out, -log_det
+    return cond_model.run_stack(particles_pred, row_ctx=ctx, inverse=True, neg_logdet=True)
 
 
 def proposal_likelihood(cond_model, dynamical_nf, measurement_model, particles_dynamic, particles_physical, encodings, noise,

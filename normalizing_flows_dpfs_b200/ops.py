@@ -14,35 +14,37 @@ def _stack_dims(packed, D, C, n_flows):
 
 
 class SoftResample(torch.autograd.Function):
-    """soft_resampler, resamplers/resamplers.py:20-60."""
+    """soft_resampler, resamplers/resamplers.py:20-60 (+ the log of the new weights, DPFs.py:167, when want_log)."""
 
     @staticmethod
-    def forward(ctx, particles, probs, offsets, markers, alpha):
+    def forward(ctx, particles, probs, offsets, markers, alpha, want_log):
         B, N, d = particles.shape
         p, w = L.f32(particles), L.f32(probs)
         off, mk = L.f32(offsets), L.f32(markers)
         p_out = torch.empty_like(p)
         w_out = torch.empty_like(w)
+        lw_out = torch.empty_like(w) if want_log else None
         idx = torch.empty(B, N, dtype=torch.int64, device=p.device)
         saved = torch.empty(B, 2, dtype=torch.float32, device=p.device)
         L.call("nfdpf_soft_resample_fwd", L.ptr(p), L.ptr(w), L.ptr(off), L.ptr(mk), float(alpha), B, N, d, L.ptr(p_out),
-               L.ptr(w_out), L.ptr(idx), L.ptr(saved), L.stream())
+               L.ptr(w_out), L.ptr(idx), L.ptr(saved), L.ptr(lw_out), L.stream())
         ctx.save_for_backward(w, idx, saved)
         ctx.alpha, ctx.shape = float(alpha), (B, N, d)
         ctx.mark_non_differentiable(idx)
-        return p_out, w_out, idx
+        return p_out, w_out, idx, lw_out
 
     @staticmethod
-    def backward(ctx, g_p, g_w, _g_idx):
+    def backward(ctx, g_p, g_w, _g_idx, g_lw):
         w, idx, saved = ctx.saved_tensors
         B, N, d = ctx.shape
         g_p = L.f32(g_p) if g_p is not None else None
         g_w = L.f32(g_w) if g_w is not None else None
+        g_lw = L.f32(g_lw) if g_lw is not None else None
         d_p = torch.empty(B, N, d, dtype=torch.float32, device=w.device)
         d_w = torch.empty(B, N, dtype=torch.float32, device=w.device)
         L.call("nfdpf_soft_resample_bwd", L.ptr(g_p), L.ptr(g_w), L.ptr(w), L.ptr(idx), L.ptr(saved), ctx.alpha, B, N, d,
-               L.ptr(d_p), L.ptr(d_w), L.stream())
-        return d_p, d_w, None, None, None
+               L.ptr(d_p), L.ptr(d_w), L.ptr(g_lw), L.stream())
+        return d_p, d_w, None, None, None, None
 
 
 class WeightUpdate(torch.autograd.Function):
@@ -84,7 +86,7 @@ class CouplingStack(torch.autograd.Function):
     x (B,N,D); row_ctx (B,C_row) or None; part_ctx (B,N,C_part) or None; packed = flat parameters."""
 
     @staticmethod
-    def forward(ctx, packed, x, row_ctx, part_ctx, n_flows, inverse):
+    def forward(ctx, packed, x, row_ctx, part_ctx, n_flows, inverse, neg_logdet=False):
         B, N, D = x.shape
         C_row = 0 if row_ctx is None else row_ctx.shape[-1]
         C_part = 0 if part_ctx is None else part_ctx.shape[-1]
@@ -94,10 +96,11 @@ class CouplingStack(torch.autograd.Function):
         pc = L.f32(part_ctx) if part_ctx is not None else None
         y = torch.empty_like(xx)
         ld = torch.empty(B, N, dtype=torch.float32, device=xx.device)
-        L.call("nfdpf_coupling_fwd", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(xx), L.ptr(rc), L.ptr(pc), int(inverse), B, N,
+        flags = int(bool(inverse)) | (2 if neg_logdet else 0)
+        L.call("nfdpf_coupling_fwd", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(xx), L.ptr(rc), L.ptr(pc), flags, B, N,
                L.ptr(y), L.ptr(ld), L.stream())
         ctx.save_for_backward(pk, y, rc, pc)
-        ctx.meta = (n_flows, D, C_row, C_part, int(inverse), B, N)
+        ctx.meta = (n_flows, D, C_row, C_part, flags, B, N)
         return y, ld
 
     @staticmethod
@@ -116,19 +119,22 @@ class CouplingStack(torch.autograd.Function):
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=y.device)
         L.call("nfdpf_coupling_bwd", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(y), L.ptr(rc), L.ptr(pc), inverse, B, N,
                L.ptr(g_y), L.ptr(g_ld), L.ptr(d_x), L.ptr(d_rc), L.ptr(d_pc), L.ptr(d_pk), L.ptr(ws), L.stream())
-        return d_pk, d_x, d_rc, d_pc, None, None
+        return d_pk, d_x, d_rc, d_pc, None, None, None
 
 
-def soft_resample(particles, probs, offsets, markers, alpha):
-    return SoftResample.apply(particles, probs, offsets, markers, alpha)
+def soft_resample(particles, probs, offsets, markers, alpha, want_log=False):
+    """(particles', probs', flat idx) or, with want_log, (particles', probs', flat idx, log probs')."""
+    out = SoftResample.apply(particles, probs, offsets, markers, alpha, want_log)
+    return out if want_log else out[:3]
 
 
 def weight_update(logw_prev, lki=None, prior=None, propose=None, add_eps=0.0):
     return WeightUpdate.apply(logw_prev, lki, prior, propose, add_eps)
 
 
-def coupling_stack(packed, x, row_ctx=None, part_ctx=None, n_flows=2, inverse=False):
-    return CouplingStack.apply(packed, x, row_ctx, part_ctx, n_flows, inverse)
+def coupling_stack(packed, x, row_ctx=None, part_ctx=None, n_flows=2, inverse=False, neg_logdet=False):
+    """(y, log_det) -- or (y, jac = -log_det) with neg_logdet (model/models.py:325, 350)."""
+    return CouplingStack.apply(packed, x, row_ctx, part_ctx, n_flows, inverse, neg_logdet)
 
 
 MEASURE_MODES = {"gaussian": 0, "cos": 1, "CRNVP": 2}
@@ -248,3 +254,59 @@ class OtResample(torch.autograd.Function):
 
 def ot_resample(particles, logw, eps=0.1, scaling=0.75, threshold=1e-3, max_iter=100):
     return OtResample.apply(particles, logw, eps, scaling, threshold, max_iter)
+
+
+class MotionMoments(torch.autograd.Function):
+    """x' = (x + vel_b) + noise (model/models.py:191-204); writes the detached [mean | std] context of x' into ctx."""
+
+    @staticmethod
+    def forward(ctx, particles, vel, noise, ctx_buf, ctx_off):
+        B, N, d = particles.shape
+        x, v, e = L.f32(particles), L.f32(vel), L.f32(noise)
+        out = torch.empty_like(x)
+        L.call("nfdpf_motion_moments", L.ptr(x), L.ptr(v), L.ptr(e), B, N, d, L.ptr(out), L.ptr(ctx_buf),
+               0 if ctx_buf is None else ctx_buf.shape[1], ctx_off, L.stream())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None, None, None
+
+
+class ProposalTerms(torch.autograd.Function):
+    """prior / proposal log-densities of proposal_likelihood (model/models.py:369-376)."""
+
+    @staticmethod
+    def forward(ctx, back, phys, noise, jac_back, jac_dyn, jac_prop, sigma):
+        bk, ph, nz = L.f32(back), L.f32(phys), L.f32(noise)
+        B, N, _ = bk.shape
+        jb, jd, jp = (L.f32(t) if t is not None else None for t in (jac_back, jac_dyn, jac_prop))
+        prior = torch.empty(B, N, dtype=torch.float32, device=bk.device)
+        propose = torch.empty_like(prior)
+        L.call("nfdpf_proposal_terms_fwd", L.ptr(bk), L.ptr(ph), L.ptr(nz), L.ptr(jb), L.ptr(jd), L.ptr(jp), float(sigma), B * N,
+               L.ptr(prior), L.ptr(propose), L.stream())
+        ctx.save_for_backward(bk, ph, nz)
+        ctx.sigma, ctx.has = float(sigma), (jac_back is not None, jac_dyn is not None, jac_prop is not None)
+        return prior, propose
+
+    @staticmethod
+    def backward(ctx, g_prior, g_prop):
+        bk, ph, nz = ctx.saved_tensors
+        B, N, _ = bk.shape
+        has_b, has_d, has_p = ctx.has
+        d_back = d_phys = neg = None
+        if g_prior is not None:
+            gp = L.f32(g_prior)
+            d_back, d_phys = torch.empty_like(bk), torch.empty_like(bk)
+            neg = torch.empty_like(gp) if has_b else None
+            L.call("nfdpf_proposal_terms_bwd", L.ptr(gp), L.ptr(bk), L.ptr(ph), L.ptr(nz), ctx.sigma, B * N, L.ptr(d_back), L.ptr(d_phys),
+                   L.ptr(neg), L.stream())
+        return d_back, d_phys, None, neg, (g_prop if has_d else None), (g_prop if has_p else None), None
+
+
+def motion_moments(particles, vel, noise, ctx_buf=None, ctx_off=0):
+    return MotionMoments.apply(particles, vel, noise, ctx_buf, ctx_off)
+
+
+def proposal_terms(back, phys, noise, jac_back, jac_dyn, jac_prop, sigma):
+    return ProposalTerms.apply(back, phys, noise, jac_back, jac_dyn, jac_prop, sigma)

@@ -38,7 +38,7 @@ def _markers(n, dev):
     return _marker_cache[key]
 
 
-def soft_resampler(particles, particle_probs, alpha, num_resampled, index=True, device="cuda", random_offset=None):
+def soft_resampler(particles, particle_probs, alpha, num_resampled, index=True, device="cuda", random_offset=None, want_log=False):
     """Soft (mixture-with-uniform) systematic resampling.  `random_offset` (B,) may be injected; by default it is
     drawn exactly like the reference does (CPU generator, U(0, 1/N), resamplers.py:43)."""
     assert 0.0 < alpha <= 1.0
@@ -48,8 +48,10 @@ def soft_resampler(particles, particle_probs, alpha, num_resampled, index=True, 
     if random_offset is None:
         random_offset = torch.FloatTensor(batch).uniform_(0.0, 1.0 / num_resampled)
     off = random_offset.to(particles.device, non_blocking=True)
-    p, w, idx = ops.soft_resample(particles, particle_probs, off, _markers(n, particles.device), alpha)
-    return (p, w, idx) if index else (p, w)
+    out = ops.soft_resample(particles, particle_probs, off, _markers(n, particles.device), alpha, want_log)
+    if want_log:  # (particles, probs, idx, log probs): the filter loop's fused path
+        return out
+    return out if index else out[:2]
 
 
 def resampler_ot(particles, weights, eps=0.1, scaling=0.75, threshold=1e-3, max_iter=100, device="cuda",

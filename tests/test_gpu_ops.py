@@ -276,3 +276,51 @@ def test_ot_resample_properties_full_size():
     assert bool(torch.isfinite(p).all())
     it = int(ops.OtResample.last_iters.item())
     assert 10 < it <= 100, it
+
+
+# ------------------------------------------------------------------------------------------------- step glue
+def test_motion_moments_and_proposal_terms_vs_oracle():
+    g = torch.Generator().manual_seed(9)
+    B, N = 5, 300
+    x, noise = torch.randn(B, N, 2, generator=g) * 30, torch.randn(B, N, 2, generator=g) * 20
+    vel = torch.randn(B, 2, generator=g) * 3
+    ctx = torch.zeros(B, 9, device="cuda")
+    out = ops.motion_moments(cu(x), cu(vel), cu(noise), ctx, 3)
+    ref = O.motion_update(x, vel, noise)
+    close(out, ref, atol=1e-4, what="motion")
+    mean, std = O.row_stats(ref)
+    close(ctx[:, 3:5], mean[:, 0], atol=1e-4, what="mean")
+    close(ctx[:, 5:7], std[:, 0], atol=1e-4, what="std")
+    assert float(ctx[:, :3].abs().max()) == 0 and float(ctx[:, 7:].abs().max()) == 0
+    back = torch.randn(B, N, 2, generator=g) * 30
+    jb, jd, jp = (torch.randn(B, N, generator=g) for _ in range(3))
+    lo = [t.clone().requires_grad_() for t in (back, ref, jb, jd, jp)]
+    prior_o = O.normal_density(lo[0] - (lo[1] - noise), 20.0) - lo[2]
+    prop_o = O.normal_density(noise, 20.0) + lo[3] + lo[4]
+    gt = [cu(t).requires_grad_() for t in (back, ref, jb, jd, jp)]
+    prior, prop = ops.proposal_terms(gt[0], gt[1], cu(noise), gt[2], gt[3], gt[4], 20.0)
+    close(prior, prior_o, atol=1e-4, what="prior")
+    close(prop, prop_o, atol=1e-4, what="propose")
+    g1, g2 = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g)
+    ((prior_o * g1).sum() + (prop_o * g2).sum()).backward()
+    ((prior * cu(g1)).sum() + (prop * cu(g2)).sum()).backward()
+    for a, b, n in zip(gt, lo, ("back", "phys", "jac_back", "jac_dyn", "jac_prop")):
+        grad_close(a.grad, b.grad, "d_" + n)
+
+
+def test_soft_resample_log_output_gradient():
+    g = torch.Generator().manual_seed(4)
+    B, N = 6, 257
+    w = torch.softmax(torch.randn(B, N, generator=g) * 2, -1)
+    p = torch.randn(B, N, 2, generator=g)
+    off = torch.rand(B, generator=g) / N
+    mk = torch.linspace(0.0, (N - 1.0) / N, N)
+    wo = w.clone().requires_grad_()
+    _, w_res, _ = O.soft_resample(p, wo, 0.5, off)
+    g1, g2 = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g)
+    ((w_res * g1).sum() + (w_res.log() * g2).sum()).backward()
+    wg = cu(w).requires_grad_()
+    _, w2, _, lw2 = ops.soft_resample(cu(p), wg, cu(off), cu(mk), 0.5, want_log=True)
+    close(lw2, w_res.log(), what="log weights")
+    ((w2 * cu(g1)).sum() + (lw2 * cu(g2)).sum()).backward()
+    grad_close(wg.grad, wo.grad, "d_probs through log output")
