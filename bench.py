@@ -105,7 +105,7 @@ def build_b200(a, dev):
     return dpf
 
 
-def step_b200(dpf, batch, dev, host_inputs):
+def step_b200(dpf, batch, dev, host_inputs, bucket=None):
     """One filter forward + backward.  host_inputs=True: inputs start in pinned host memory and the loss is read
     back (the e2e number); False: inputs are resident device tensors (the kernel-side `value`)."""
     from normalizing_flows_dpfs_b200.losses import supervised_loss
@@ -115,6 +115,8 @@ def step_b200(dpf, batch, dev, host_inputs):
     out = dpf.filtering_pos(d["enc"], d["start"], d["vel_in"])
     loss, _ = supervised_loss(out[0], out[1], d["state"], 1.0, False)
     loss.backward()
+    if bucket is not None:      # multi-GPU training step: the one collective (flat gradient all-reduce over NCCL)
+        bucket.allreduce()
     return loss.item() if host_inputs else loss
 
 
@@ -134,6 +136,10 @@ def main():
     dpf = build_b200(a, dev)
     host = synth_batch(a.B, a.T, a.N, 100 + rank, pinned=True)     # weak scaling: every rank owns B trajectories
     resident = {k: v.to(dev) for k, v in host.items()}
+    bucket = None
+    if world > 1:
+        from normalizing_flows_dpfs_b200.distributed import GradBucket
+        bucket = GradBucket(dpf)
 
     def barrier():
         if world > 1:
@@ -154,15 +160,15 @@ def main():
         return float(ms)
 
     for _ in range(a.warmup):
-        step_b200(dpf, resident, dev, False)
+        step_b200(dpf, resident, dev, False, bucket)
     clocks = ClockSampler(local)
     l0 = _lib.launch_count()
-    ms = timed(lambda: step_b200(dpf, resident, dev, False), a.steps)
+    ms = timed(lambda: step_b200(dpf, resident, dev, False, bucket), a.steps)
     launches = _lib.launch_count() - l0
     clk = clocks.stop()
     for _ in range(min(a.warmup, 2)):
-        step_b200(dpf, host, dev, True)
-    ms_e2e = timed(lambda: step_b200(dpf, host, dev, True), a.steps)
+        step_b200(dpf, host, dev, True, bucket)
+    ms_e2e = timed(lambda: step_b200(dpf, host, dev, True, bucket), a.steps)
     units = a.B * a.N * a.T * world
     if rank != 0:
         return
@@ -173,7 +179,7 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "CNF-DPF (--NF-dyn --NF-cond) %s measurement, %s resampling forced every step, N=%d, B=%d per GPU, T=%d, "
                                "precomputed encodings (CNN encoder excluded)" % (a.measurement, a.resampler, a.N, a.B, a.T),
-                   "l2": "per-step working set (particles, noise, lists: >300 MB) exceeds the 126 MB L2", "parallelism": "batch-sharded x%d" % world},
+                   "l2": "per-step working set (particles, noise, lists: >300 MB) exceeds the 126 MB L2", "parallelism": "batch-sharded x%d%s" % (world, ", NCCL flat-gradient all-reduce per step" if world > 1 else "")},
         "e2e": {"value": units * a.steps / (ms_e2e / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clk,
     }

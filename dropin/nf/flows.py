@@ -1,0 +1,2 @@
+import _path  # noqa: F401
+from normalizing_flows_dpfs_b200.nf.flows import *  # noqa: F401,F403 -- drop-in shim for the reference's 'nf.flows' module

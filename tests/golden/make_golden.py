@@ -289,9 +289,24 @@ def gen_filter():
     np.savez_compressed(os.path.join(OUT, "filter.npz"), **out)
 
 
+def gen_state_dict():
+    """state_dict keys + shapes of the reference DPF for the accelerated configurations (checkpoint compatibility)."""
+    import json
+    sys.argv = ["main.py"]
+    import arguments as ref_args
+    import DPFs as ref_dpfs
+    out = {}
+    for meas in ("gaussian", "cos", "CRNVP", "NN"):
+        sys.argv = ["main.py", "--measurement", meas]
+        dpf = ref_dpfs.DPF(ref_args.parse_args())
+        out[meas] = {k: list(v.shape) for k, v in dpf.state_dict().items()}
+    with open(os.path.join(OUT, "state_dict.json"), "w") as fh:
+        json.dump(out, fh, indent=0, sort_keys=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["soft", "flows", "glue", "ot", "filter"]
+    which = sys.argv[1:] or ["soft", "flows", "glue", "ot", "filter", "state_dict"]
     sys.argv = sys.argv[:1]
     for w in which:
-        {"soft": gen_soft, "flows": gen_flows, "glue": gen_glue, "ot": gen_ot, "filter": gen_filter}[w]()
+        {"soft": gen_soft, "flows": gen_flows, "glue": gen_glue, "ot": gen_ot, "filter": gen_filter, "state_dict": gen_state_dict}[w]()
         print("wrote", w)
