@@ -189,6 +189,8 @@ def main():
     except Exception as e:  # never lose the headline line
         line["roofline_error"] = repr(e)
     print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -17,13 +17,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 
 
 def _events(fn, n=10, warm=3):
+    """Mean device time of fn() in seconds.  The launches are captured into a CUDA graph and replayed so that the
+    ~30 us of Python/ctypes launch overhead does not pollute kernels that run for 10-100 us; falls back to plain
+    back-to-back launches if capture is not possible."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        graph.replay()
+        torch.cuda.synchronize()
+    except Exception:
+        graph = None
+        torch.cuda.synchronize()
+    run = graph.replay if graph is not None else fn
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
-        fn()
+        run()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e-3

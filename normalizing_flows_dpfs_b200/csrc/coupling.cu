@@ -168,19 +168,21 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     }
 }
 
-// d_packed[i] += sum over CTAs (fixed order, fp64 accumulate)
+// d_packed[i] += sum over CTAs.  One warp per parameter: lane l sums partials l, l+32, ... in fp64, then a fixed
+// butterfly -- the order depends only on (n_parts), so results are run-to-run deterministic.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int n_params, float* __restrict__ d_packed) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n_params) return;
     double a = 0.0;
-    for (int c = 0; c < n_parts; ++c) a += (double)partials[(size_t)c * n_params + i];
-    d_packed[i] += (float)a;
+    for (int c = lane; c < n_parts; c += 32) a += (double)partials[(size_t)c * n_params + i];
+    a = warp_sum(a);
+    if (lane == 0) d_packed[i] += (float)a;
 }
 
 int bwd_grid(int B) { return min(B, 2 * sm_count()); }
 
 int launch_reduce_partials(const float* partials, int n_parts, int n_params, float* d_packed, cudaStream_t st) {
-    reduce_partials_kernel<<<(n_params + 255) / 256, 256, 0, st>>>(partials, n_parts, n_params, d_packed);
+    reduce_partials_kernel<<<(n_params + 7) / 8, 256, 0, st>>>(partials, n_parts, n_params, d_packed);
     return check_launch("reduce_partials");
 }
 

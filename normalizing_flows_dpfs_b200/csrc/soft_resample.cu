@@ -152,70 +152,88 @@ soft_resample_fwd_kernel(const float* __restrict__ particles, const float* __res
 }
 
 // Backward: indices carry no gradient; gradients flow through the gathered particles and through
-// w/q (numerator and q), then the row renormalisation.  idx is monotone per row, so every source particle j owns
-// a contiguous run of destinations: thread j sums its run in order (deterministic, no atomics).
+// w/q (numerator and q), then the row renormalisation.  idx is monotone per row, so every source particle owns a
+// contiguous run of destinations: the per-source sums are a SEGMENTED inclusive scan over the destinations
+// (Hillis-Steele in shared memory; "same segment" == equal key because the keys are sorted), read off at the last
+// element of each run.  fp32, fixed order, no atomics; work is balanced however peaked the weights are.
 __global__ void __launch_bounds__(1024)
 soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __restrict__ g_probs,
                          const float* __restrict__ probs, const int64_t* __restrict__ idx,
                          const float* __restrict__ saved, float alpha_f, float one_minus_alpha_f, int hard, int N, int d,
                          float* __restrict__ d_particles, float* __restrict__ d_probs, const float* __restrict__ g_logprobs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int* s_idx = reinterpret_cast<int*>(smem_raw);           // local source index per destination
-    float* s_gv = reinterpret_cast<float*>(smem_raw) + N;    // dL/dv_i, v_i = w_is[idx_i]
+    int* s_idx = reinterpret_cast<int*>(smem_raw);                    // [N] local source index per destination
+    float4* s_a = reinterpret_cast<float4*>(s_idx + ((N + 3) & ~3));  // [N] (dL/dv, g_x, g_y, -) ping
+    float4* s_b = s_a + N;                                            // [N] pong
     __shared__ float s_red[33];
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const float S = saved[2 * b], S2 = saved[2 * b + 1];
     const float* w = probs + (size_t)b * N;
+    const size_t base = (size_t)b * N;
     const float unif = __fdiv_rn(1.0f, (float)N), uterm = __fmul_rn(unif, one_minus_alpha_f);
     auto qu = [&](int j) { return __fadd_rn(__fmul_rn(w[j], alpha_f), uterm); };
     float part = 0.f;
     for (int i = tid; i < N; i += nt) {
-        const int j = (int)(idx[(size_t)b * N + i] - (int64_t)N * b);
+        const int j = (int)(idx[base + i] - (int64_t)N * b);
         s_idx[i] = j;
         float g = 0.f;   // total gradient reaching w'_i: direct + through log(w'_i)
         if (!hard && (g_probs || g_logprobs)) {
             const float wp = (w[j] * S / qu(j)) / S2;
-            if (g_probs) g = g_probs[(size_t)b * N + i];
-            if (g_logprobs) g += g_logprobs[(size_t)b * N + i] / wp;
+            if (g_probs) g = g_probs[base + i];
+            if (g_logprobs) g += g_logprobs[base + i] / wp;
             part += g * wp;                                  // sum_m g_m w'_m
         }
-        s_gv[i] = g;
+        float2 gp = make_float2(0.f, 0.f);
+        if (g_particles && d == 2) gp = reinterpret_cast<const float2*>(g_particles)[base + i];
+        s_a[i] = make_float4(g, gp.x, gp.y, 0.f);
     }
     const float c = block_allreduce(part, s_red, OpSum(), 0.f);
-    for (int i = tid; i < N; i += nt) s_gv[i] = hard ? 0.f : (s_gv[i] - c) / S2;
+    for (int i = tid; i < N; i += nt) s_a[i].x = hard ? 0.f : (s_a[i].x - c) / S2;   // dL/dv_i, v_i = w_is[idx_i]
+    __syncthreads();
+    float4* src = s_a;
+    float4* dst = s_b;
+    for (int o = 1; o < N; o <<= 1) {
+        for (int i = tid; i < N; i += nt) {
+            float4 v = src[i];
+            if (i >= o && s_idx[i - o] == s_idx[i]) { const float4 u = src[i - o]; v.x += u.x; v.y += u.y; v.z += u.z; }
+            dst[i] = v;
+        }
+        __syncthreads();
+        float4* t = src; src = dst; dst = t;
+    }
+    // src[i] = inclusive segmented sums; a run ends at i when the next key differs
+    for (int j = tid; j < N; j += nt) {
+        d_probs[base + j] = 0.f;
+        if (d == 2) reinterpret_cast<float2*>(d_particles)[base + j] = make_float2(0.f, 0.f);
+    }
     __syncthreads();
     float third = 0.f;
-    for (int j = tid; j < N; j += nt) {
-        int lo = 0, hi = N;  // first destination with idx >= j
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_idx[mid] < j) lo = mid + 1; else hi = mid; }
-        float G = 0.f, gp[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int i = lo; i < N && s_idx[i] == j; ++i) {
-            G += s_gv[i];
-            if (g_particles) {
-                if (d <= 4) { for (int k = 0; k < d; ++k) gp[k] += g_particles[((size_t)b * N + i) * d + k]; }
-            }
+    for (int i = tid; i < N; i += nt) {
+        const int j = s_idx[i];
+        if (i + 1 < N && s_idx[i + 1] == j) continue;
+        const float4 v = src[i];
+        if (d == 2) reinterpret_cast<float2*>(d_particles)[base + j] = make_float2(v.y, v.z);
+        if (!hard) {
+            const float q = qu(j), wj = w[j], G = v.x;
+            d_probs[base + j] = G * S / q - G * wj * S * alpha_f / (q * q);   // through w_is_j = w_j S / qu_j at fixed S
+            third += G * wj / q;                                               // through S = sum_k qu_k
         }
-        if (d <= 4) {
-            for (int k = 0; k < d; ++k) d_particles[((size_t)b * N + j) * d + k] = gp[k];
-        } else {
+    }
+    if (d != 2) {  // generic state dimension: per-source ordered run sums (rare path)
+        for (int j = tid; j < N; j += nt) {
+            int lo = 0, hi = N;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_idx[mid] < j) lo = mid + 1; else hi = mid; }
             for (int k = 0; k < d; ++k) {
                 float a = 0.f;
                 if (g_particles)
-                    for (int i = lo; i < N && s_idx[i] == j; ++i) a += g_particles[((size_t)b * N + i) * d + k];
-                d_particles[((size_t)b * N + j) * d + k] = a;
+                    for (int i = lo; i < N && s_idx[i] == j; ++i) a += g_particles[(base + i) * d + k];
+                d_particles[(base + j) * d + k] = a;
             }
         }
-        float dw = 0.f;
-        if (!hard) {
-            const float q = qu(j), wj = w[j];
-            dw = G * S / q - G * wj * S * alpha_f / (q * q);  // through w_is_j = w_j S / qu_j at fixed S
-            third += G * wj / q;                                 // through S = sum_k qu_k
-        }
-        d_probs[(size_t)b * N + j] = dw;  // the same thread adds the shared third term below
     }
-    const float t3 = block_allreduce(third, s_red, OpSum(), 0.f);
+    const float t3 = block_allreduce(third, s_red, OpSum(), 0.f);   // (its barriers also order the zero-fill above)
     if (!hard)
-        for (int j = tid; j < N; j += nt) d_probs[(size_t)b * N + j] += alpha_f * t3;
+        for (int j = tid; j < N; j += nt) d_probs[base + j] += alpha_f * t3;
 }
 
 static int pick_threads(int N) {
@@ -251,8 +269,8 @@ extern "C" int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_
     NFDPF_REQUIRE(probs && idx && saved && d_particles && d_probs, "soft_resample_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_bwd: B, N, d must be positive");
     NFDPF_REQUIRE(alpha > 0.0 && alpha <= 1.0, "soft_resample_bwd: need 0 < alpha <= 1, got %g", alpha);
-    const size_t smem = (size_t)N * 2 * sizeof(float);
-    if (smem > 200 * 1024) { set_error("soft_resample_bwd: N=%d exceeds the shared-memory row limit", N); return NFDPF_ERR_UNSUPPORTED; }
+    const size_t smem = (size_t)((N + 3) & ~3) * sizeof(int) + (size_t)N * 2 * sizeof(float4);
+    if (smem > 200 * 1024) { set_error("soft_resample_bwd: N=%d exceeds the shared-memory row limit (5600)", N); return NFDPF_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024)
         NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     soft_resample_bwd_kernel<<<B, pick_threads(N), smem, (cudaStream_t)stream>>>(
