@@ -247,7 +247,8 @@ extern "C" int nfdpf_coupling_fwd(const float* packed, int n_flows, int D, int C
 extern "C" int64_t nfdpf_coupling_bwd_workspace(int n_flows, int D, int C_row, int C_part, int B, int N) {
     (void)N;
     if (n_flows < 1 || D < 2 || B < 1) return 0;
-    return (int64_t)bwd_grid(B) * 4 * n_flows * packed_fcnn_size(D / 2, C_row + C_part) * (int64_t)sizeof(float);
+    // per-CTA partial gradients + per-trajectory layer-1 delta sums (row-context gradient, D = 2 path)
+    return ((int64_t)bwd_grid(B) * 4 * n_flows * packed_fcnn_size(D / 2, C_row + C_part) + (int64_t)B * 4 * n_flows * H) * (int64_t)sizeof(float);
 }
 
 extern "C" int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C_part, const float* y,

@@ -179,6 +179,24 @@ __device__ void hoist_row_context(const float* __restrict__ imgs, const float* _
     }
 }
 
+// Same, with every thread of the CTA participating: (f,k) pairs are spread over groups of 4 lanes.
+template <int HALF, int CP>
+__device__ void hoist_row_context_par(const float* __restrict__ imgs, const float* __restrict__ w1r, const float* __restrict__ ctx,
+                                      int C_row, int n_fcnn, float* __restrict__ hb) {
+    using L = Lay<HALF, CP>;
+    const int sub = threadIdx.x & 3, nt = blockDim.x >> 2;
+    for (int e = threadIdx.x >> 2; e < ((n_fcnn * H + nt - 1) / nt) * nt; e += nt) {
+        float a = 0.f;
+        if (e < n_fcnn * H) {
+            const float* w = w1r + (size_t)e * C_row;
+            for (int c = sub; c < C_row; c += 4) a = fmaf(w[c], ctx[c], a);
+        }
+        a += __shfl_xor_sync(FULL, a, 1);
+        a += __shfl_xor_sync(FULL, a, 2);
+        if (e < n_fcnn * H && sub == 0) hb[e] = a + imgs[(e / H) * L::SIZE + L::B1 + (e % H)];
+    }
+}
+
 // One coupling stage, forward evaluation.  INV=false: v = t(c) + v*exp(s(c)); INV=true: v = (v - t(c))*exp(-s(c)).
 template <int HALF, int CP, bool INV>
 __device__ __forceinline__ void stage_fwd(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s,

@@ -24,7 +24,7 @@ struct D2Smem {
                     + 6 * (size_t)CHUNK                                                     // lo, up, glo, gup, gld, ds
                     + 16 * (size_t)CHUNK                                                    // s-net activations (h1, h2) stash
                     + NWARP * 100                                                            // per-warp reduction slots
-                    + (size_t)n_fcnn * NACC + (size_t)n_fcnn * H * C_row + n_fcnn * H + C_row + 4;
+                    + (size_t)n_fcnn * NACC + n_fcnn * H + C_row + 4;
         return fl * sizeof(float);
     }
 };
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(TPD)
 coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ y,
                        const float* __restrict__ row_ctx, int flags, int B, int N, const float* __restrict__ g_y,
                        const float* __restrict__ g_ld, float* __restrict__ d_x, float* __restrict__ d_row_ctx,
-                       float* __restrict__ partials) {
+                       float* __restrict__ partials, float* __restrict__ d1rows) {
     extern __shared__ __align__(16) float smem[];
     const int n_fcnn = 4 * n_flows, tid = threadIdx.x, inverse = flags & 1;
     float* s_img = smem;
@@ -153,21 +153,19 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
     float* s_stash = s_ds + CHUNK;
     float* s_part = s_stash + 16 * CHUNK;
     float* s_acc = s_part + NWARP * 100;
-    float* s_accR = s_acc + n_fcnn * NACC;
-    float* s_d1row = s_accR + (size_t)n_fcnn * H * C_row;
+    float* s_d1row = s_acc + n_fcnn * NACC;
     float* s_ctx = s_d1row + n_fcnn * H;
     const int pf = packed_fcnn_size(1, C_row);
     for (int f = 0; f < n_fcnn; ++f)
         load_fcnn_image<1, 0>(packed + (size_t)f * pf, C_row, s_img + f * L2_::SIZE, s_w1r + (size_t)f * H * C_row, tid, TPD);
     for (int e = tid; e < n_fcnn * NACC; e += TPD) s_acc[e] = 0.f;
-    for (int e = tid; e < n_fcnn * H * C_row; e += TPD) s_accR[e] = 0.f;
     __syncthreads();
 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         for (int e = tid; e < C_row; e += TPD) s_ctx[e] = row_ctx[(size_t)b * C_row + e];
         for (int e = tid; e < n_fcnn * H; e += TPD) s_d1row[e] = 0.f;
         __syncthreads();
-        hoist_row_context<1, 0>(s_img, s_w1r, s_ctx, C_row, n_fcnn, s_hb, tid, TPD);
+        hoist_row_context_par<1, 0>(s_img, s_w1r, s_ctx, C_row, n_fcnn, s_hb);
         __syncthreads();
         for (int c0 = 0; c0 < N; c0 += CHUNK) {
             const int n_live = min(CHUNK, N - c0);
@@ -193,25 +191,43 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
             }
             for (int q = tid; q < n_live; q += TPD) reinterpret_cast<float2*>(d_x)[p0 + q] = make_float2(s_glo[q], s_gup[q]);
         }
-        for (int e = tid; e < n_fcnn * H * C_row; e += TPD) s_accR[e] = fmaf(s_d1row[e / C_row], s_ctx[e % C_row], s_accR[e]);
-        if (d_row_ctx)
-            for (int cidx = tid; cidx < C_row; cidx += TPD) {
-                float a = 0.f;
-                for (int fk = 0; fk < n_fcnn * H; ++fk) a = fmaf(s_w1r[(size_t)fk * C_row + cidx], s_d1row[fk], a);
-                d_row_ctx[(size_t)b * C_row + cidx] = a;
-            }
+        // per-trajectory layer-1 delta sums: the row-context columns of dW1 and d(row_ctx) are formed from them by
+        // rowctx_grad_kernel after this kernel (keeps the 8 x C_row outer products out of the persistent loop)
+        for (int e = tid; e < n_fcnn * H; e += TPD) d1rows[(size_t)b * n_fcnn * H + e] = s_d1row[e];
         __syncthreads();
     }
     float* out = partials + (size_t)blockIdx.x * n_fcnn * pf;
-    const int fin = 1 + C_row;
     for (int e = tid; e < n_fcnn * NACC; e += TPD) {
         int ra, rb, poff;
         out_entry<1, 0>(e % NACC, C_row, ra, rb, poff);
         out[(size_t)(e / NACC) * pf + poff] = s_acc[e];
     }
-    for (int e = tid; e < n_fcnn * H * C_row; e += TPD) {
-        const int fk = e / C_row, cidx = e % C_row;
-        out[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + cidx] = s_accR[e];
+    const int fin = 1 + C_row;
+    for (int e = tid; e < n_fcnn * H * C_row; e += TPD)   // row-context columns are produced by rowctx_grad_kernel
+        out[(size_t)(e / (H * C_row)) * pf + ((e / C_row) % H) * fin + 1 + (e % C_row)] = 0.f;
+}
+
+// dW1[f][k][1 + c] += sum_b D1[b][f][k] * ctx[b][c]   (one warp per output, fp64, fixed order)
+// d_row_ctx[b][c]   = sum_{f,k} W1[f][k][1 + c] * D1[b][f][k]
+__global__ void rowctx_grad_kernel(const float* __restrict__ packed, const float* __restrict__ d1rows, const float* __restrict__ row_ctx,
+                                   int n_fcnn, int C_row, int B, float* __restrict__ d_packed, float* __restrict__ d_row_ctx) {
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int n_w = n_fcnn * H * C_row, pf = packed_fcnn_size(1, C_row), fin = 1 + C_row;
+    if (warp < n_w) {
+        const int fk = warp / C_row, c = warp % C_row;
+        double a = 0.0;
+        for (int b = lane; b < B; b += 32) a += (double)d1rows[(size_t)b * n_fcnn * H + fk] * (double)row_ctx[(size_t)b * C_row + c];
+        a = warp_sum(a);
+        if (lane == 0) d_packed[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + c] += (float)a;
+    } else if (d_row_ctx) {
+        const int e = warp - n_w;            // one warp per (b, c)
+        if (e >= B * C_row) return;
+        const int b = e / C_row, c = e % C_row;
+        float a = 0.f;
+        for (int fk = lane; fk < n_fcnn * H; fk += 32)
+            a = fmaf(packed[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + c], d1rows[(size_t)b * n_fcnn * H + fk], a);
+        a = warp_sum(a);
+        if (lane == 0) d_row_ctx[(size_t)b * C_row + c] = a;
     }
 }
 
@@ -223,11 +239,16 @@ int launch_coupling_bwd_d2(const float* packed, int n_flows, int C_row, const fl
     if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(coupling_bwd_d2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = min(B, sm_count());   // one 8-warp CTA per SM (registers), persistent over trajectories
     const int n_params = n_fcnn * packed_fcnn_size(1, C_row);
+    float* d1rows = (float*)workspace + (size_t)bwd_grid(B) * n_params;
     coupling_bwd_d2_kernel<<<grid, TPD, smem, st>>>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx,
-                                                    (float*)workspace);
+                                                    (float*)workspace, d1rows);
     int rc = check_launch("coupling_bwd_d2");
     if (rc) return rc;
-    return launch_reduce_partials((const float*)workspace, grid, n_params, d_packed, st);
+    rc = launch_reduce_partials((const float*)workspace, grid, n_params, d_packed, st);
+    if (rc || C_row == 0) return rc;
+    const int warps = n_fcnn * H * C_row + (d_row_ctx ? B * C_row : 0);
+    rowctx_grad_kernel<<<(warps + 7) / 8, 256, 0, st>>>(packed, d1rows, row_ctx, n_fcnn, C_row, B, d_packed, d_row_ctx);
+    return check_launch("rowctx_grad");
 }
 
 }  // namespace nfdpf
