@@ -33,6 +33,7 @@ def parse():
     ap.add_argument("--measurement", default="gaussian")
     ap.add_argument("--resampler", default="soft")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph per step")
     return ap.parse_args()
 
 
@@ -161,14 +162,38 @@ def main():
 
     for _ in range(a.warmup):
         step_b200(dpf, resident, dev, False, bucket)
-    clocks = ClockSampler(local)
     l0 = _lib.launch_count()
-    ms = timed(lambda: step_b200(dpf, resident, dev, False, bucket), a.steps)
-    launches = _lib.launch_count() - l0
+    step_b200(dpf, resident, dev, False, bucket)
+    launches_per_step = _lib.launch_count() - l0          # kernels of ours in one step (a graph replay re-issues all of them)
+    graphed = None
+    if not a.no_graph:
+        from normalizing_flows_dpfs_b200.graphs import GraphedFilterStep
+        graphed = GraphedFilterStep(dpf, resident)
+
+    def run_resident():
+        if graphed is None:
+            return step_b200(dpf, resident, dev, False, bucket)
+        graphed.run()
+        if bucket is not None:
+            bucket.allreduce()
+
+    def run_host():
+        if graphed is None:
+            return step_b200(dpf, host, dev, True, bucket)
+        loss = graphed.run(host)                       # H2D of every input of the step from pinned memory, then replay
+        if bucket is not None:
+            bucket.allreduce()
+        return loss.item()                             # D2H read of the step's result
+
+    for _ in range(a.warmup):
+        run_resident()
+    clocks = ClockSampler(local)
+    ms = timed(run_resident, a.steps)
+    launches = launches_per_step * a.steps
     clk = clocks.stop()
     for _ in range(min(a.warmup, 2)):
-        step_b200(dpf, host, dev, True, bucket)
-    ms_e2e = timed(lambda: step_b200(dpf, host, dev, True, bucket), a.steps)
+        run_host()
+    ms_e2e = timed(run_host, a.steps)
     units = a.B * a.N * a.T * world
     if rank != 0:
         return
@@ -179,7 +204,8 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "CNF-DPF (--NF-dyn --NF-cond) %s measurement, %s resampling forced every step, N=%d, B=%d per GPU, T=%d, "
                                "precomputed encodings (CNN encoder excluded)" % (a.measurement, a.resampler, a.N, a.B, a.T),
-                   "l2": "per-step working set (particles, noise, lists: >300 MB) exceeds the 126 MB L2", "parallelism": "batch-sharded x%d%s" % (world, ", NCCL flat-gradient all-reduce per step" if world > 1 else "")},
+                   "l2": "per-step working set (particles, noise, lists: >300 MB) exceeds the 126 MB L2", "parallelism": "batch-sharded x%d%s" % (world, ", NCCL flat-gradient all-reduce per step" if world > 1 else ""),
+                   "execution": "eager launches" if a.no_graph else "one CUDA graph replay per step (forward over T + loss + backward)"},
         "e2e": {"value": units * a.steps / (ms_e2e / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "clocks": clk,
     }

@@ -1,0 +1,52 @@
+"""CUDA-graph execution of a whole filter training step (forward over T timesteps + loss + backward).
+
+The per-timestep update is a chain of ~15 short libnfdpf launches (forward) plus as many in backward; at
+B = N = 1024 each runs 20-400 us, so Python/ctypes/autograd dispatch (~40 us per launch) is comparable to the GPU
+time of the forward pass.  Capturing the step once and replaying it removes the host from the loop: one
+cudaGraphLaunch per training step.  Requirements (checked): the ESS gate must not need the host
+(`force_resample` set), and random draws must be injected or generated on the device."""
+import torch
+
+from .losses import supervised_loss
+
+
+class GraphedFilterStep:
+    """graph = GraphedFilterStep(dpf, batch)   # batch: dict of device tensors enc, start, vel_in, state,
+                                               #        init_particles, noise, offsets (static shapes)
+       loss = graph.run(new_batch)              # copies new_batch into the static buffers, replays, returns the
+                                               # (static) loss tensor; parameter .grad tensors hold the gradients."""
+
+    KEYS = ("enc", "start", "vel_in", "state", "init_particles", "noise", "offsets")
+
+    def __init__(self, dpf, batch, warmup=2):
+        if dpf.force_resample is None:
+            raise ValueError("graph capture needs a host-free ESS gate: set dpf.force_resample to True or False")
+        self.dpf = dpf
+        self.static = {k: batch[k].clone() for k in self.KEYS}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        dpf.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+
+    def _step(self):
+        d, dpf = self.static, self.dpf
+        dpf.injected = dict(init_particles=d["init_particles"], noise=d["noise"], offsets=d["offsets"])
+        dpf.zero_grad(set_to_none=False) if any(p.grad is not None for p in dpf.parameters()) else None
+        out = dpf.filtering_pos(d["enc"], d["start"], d["vel_in"])
+        loss, _ = supervised_loss(out[0], out[1], d["state"], 1.0, False)
+        loss.backward()
+        return loss
+
+    def run(self, batch=None):
+        if batch is not None:
+            for k in self.KEYS:
+                self.static[k].copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        return self.loss
