@@ -108,10 +108,12 @@ class DPF(nn.Module):
         precomputed encodings when `self.encoder` is an Identity (benchmarks exclude the CNN)."""
         start_state, vel = start_state_vs[:, :2], start_state_vs[:, 2:]
         B, N, inj = start_state.shape[0], self.num_particle, self.injected
-        particles, init_weights_log = particle_initialization(start_state, self.param.width, N, self.state_dim,
-                                                              init_with_true_state=self.param.init_with_true_state)
-        if inj is not None and "init_particles" in inj:
+        if inj is not None and "init_particles" in inj:   # injected cloud: no host RNG, no H2D copy (graph-capturable)
             particles = inj["init_particles"]
+            init_weights_log = torch.log(torch.ones(B, N, device=particles.device) / N)
+        else:
+            particles, init_weights_log = particle_initialization(start_state, self.param.width, N, self.state_dim,
+                                                                  init_with_true_state=self.param.init_with_true_state)
         _, particle_probs, _, ess_inv = _weight_norm(init_weights_log)
         identity_idx = torch.arange(B * N, device=particles.device, dtype=torch.int64).reshape(B, N)
         fused = isinstance(self.measurement_model, _FusedMeasurement)
