@@ -33,7 +33,10 @@ class _PackCache:
 
     def get(self, modules):
         params = [p for m in modules for p in m.parameters()]
-        key = (torch.is_grad_enabled(),) + tuple((p.data_ptr(), p._version) for p in params)
+        # the packed tensor carries an autograd node bound to the stream it was built on: never reuse it across
+        # streams (CUDA-graph capture runs on a side stream)
+        stream = torch.cuda.current_stream().cuda_stream if params and params[0].is_cuda else 0
+        key = (torch.is_grad_enabled(), stream) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self.key:
             self.key, self.value = key, torch.cat([p.reshape(-1) for p in params])
         return self.value
