@@ -23,6 +23,10 @@ class GraphedFilterStep:
             raise ValueError("graph capture needs a host-free ESS gate: set dpf.force_resample to True or False")
         self.dpf = dpf
         self.static = {k: batch[k].clone() for k in self.KEYS}
+        for m in dpf.modules():   # packed-parameter caches pin autograd state of the stream they were built on
+            for name in ("_cache", "_pe_cache"):
+                if hasattr(m, name):
+                    getattr(m, name).clear()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -38,8 +38,14 @@ class _PackCache:
         stream = torch.cuda.current_stream().cuda_stream if params and params[0].is_cuda else 0
         key = (torch.is_grad_enabled(), stream) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self.key:
+            # drop the old packed tensor FIRST: its cat node keeps the parameters' AccumulateGrad nodes alive, and those
+            # are bound to the stream they were first used on (a legacy-stream accumulator breaks graph capture)
+            self.key = self.value = None
             self.key, self.value = key, torch.cat([p.reshape(-1) for p in params])
         return self.value
+
+    def clear(self):
+        self.key = self.value = None
 
 
 class _Coupling(nn.Module):
