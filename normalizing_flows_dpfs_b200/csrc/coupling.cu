@@ -74,7 +74,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     float* s_hb = s_img + n_fcnn * L::SIZE;
     float* s_w1r = s_hb + n_fcnn * H;
     float* s_tile = s_w1r + (size_t)n_fcnn * H * C_row;
-    float* s_acc = s_tile + R::COUNT * TS;
+    float* s_acc = s_tile + R::TROWS * TSM;
     float* s_accR = s_acc + n_fcnn * R::NOUT;
     float* s_d1row = s_accR + (size_t)n_fcnn * H * C_row;
     float* s_ctx = s_d1row + n_fcnn * H;
@@ -89,7 +89,8 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     }
     for (int e = tid; e < n_fcnn * R::NOUT; e += TP) s_acc[e] = 0.f;
     for (int e = tid; e < n_fcnn * H * C_row; e += TP) s_accR[e] = 0.f;
-    s_tile[R::ONE * TS + tid] = 1.0f;
+    s_tile[R::ONE * TSM + tid] = 1.0f;
+    for (int r = R::COUNT; r < R::TROWS; ++r) s_tile[r * TSM + tid] = 0.0f;   // padding rows of the dout tile + the ZERO row
     __syncthreads();
 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -112,7 +113,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
             }
             const float gld = live && g_ld ? ((flags & 2) ? -g_ld[p] : g_ld[p]) : 0.f;
 #pragma unroll
-            for (int i = 0; i < CP; ++i) { pc[i] = part_ctx[p * CP + i]; gpc[i] = 0.f; s_tile[(R::PC + i) * TS + tid] = pc[i]; }
+            for (int i = 0; i < CP; ++i) { pc[i] = part_ctx[p * CP + i]; gpc[i] = 0.f; s_tile[(R::PC + i) * TSM + tid] = pc[i]; }
             if (!inverse) {  // forward pass ran flows 0..n-1 (t1/s1 then t2/s2): walk back n-1..0 (t2/s2 then t1/s1)
 #pragma unroll 1
                 for (int f = n_flows - 1; f >= 0; --f) {

@@ -15,6 +15,7 @@
 //     thread per parameter => no atomics, fixed order => deterministic) and across CTAs by a second kernel.
 #pragma once
 #include "common.cuh"
+#include "mma_tile.cuh"
 
 namespace nfdpf {
 
@@ -243,10 +244,62 @@ __device__ __forceinline__ void tile_accumulate(const int* __restrict__ s_tab, i
 template <int HALF, int CP>
 struct Rows {
     static constexpr int ONE = 0, C = 1, PC = C + HALF, H1 = PC + CP, H2 = H1 + H, D1 = H2 + H, D2 = D1 + H, DO = D2 + H,
-                         COUNT = DO + HALF;
+                         COUNT = DO + HALF,
+                         ZERO = DO + 16,       // all-zero row (padding columns of the mma B tiles); DO's m16 tile may read up to here
+                         TROWS = DO + 17;      // rows to allocate (stride TSM)
     // per-FCNN gradient outputs, in packed order minus the row-context columns
     static constexpr int NOUT = H * (HALF + CP) + H + H * H + H + HALF * H + HALF;
 };
+
+// Weight gradients of ONE FCNN for the CTA's batch on the tensor path (3xTF32 mma.sync, see mma_tile.cuh), added into
+// acc_f[NOUT] (packed order minus row-context columns) and, for the b1 block, into d1row_f (row-context hoist).
+//   A1 = [delta1 (8 rows); delta2 (8 rows)]   x  B tiles: inputs [c | pc] (NIN tiles), ONE, h1
+//        rows 0-7 x inputs -> dW1, rows 0-7 x ONE -> db1, rows 8-15 x ONE -> db2, rows 8-15 x h1 -> dW2
+//   A2 = [dout (HALF rows, padded)]            x  B tiles: h2 -> dW3, ONE -> db3
+// Tiles are dealt round-robin to the 4 warps; every accumulator entry has exactly one owner lane (no atomics).
+template <int HALF, int CP>
+__device__ __forceinline__ void stage_weight_grads_mma(const float* __restrict__ s_tile, float* __restrict__ acc_f,
+                                                       float* __restrict__ d1row_f) {
+    using R = Rows<HALF, CP>;
+    constexpr int IN = HALF + CP, NIN = (IN + 7) / 8, NT = NIN + 4;   // + ONE, h1 (on A1), h2, ONE (on A2)
+    constexpr int B1 = H * IN, W2 = B1 + H, B2 = W2 + H * H, W3 = B2 + H, B3 = W3 + HALF * H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+    for (int ti = warp; ti < NT; ti += TP / 32) {
+        const bool second = ti >= NIN + 2;                 // tiles on A2 = dout
+        int rowB;
+        if (ti < NIN) rowB = (8 * ti + g < IN) ? R::C + 8 * ti + g : R::ZERO;
+        else if (ti == NIN || ti == NIN + 3) rowB = g == 0 ? R::ONE : R::ZERO;
+        else if (ti == NIN + 1) rowB = R::H1 + g;
+        else rowB = R::H2 + g;
+        float c[1][4] = {};
+        const int rb[1] = {rowB};
+        mma_outer<1>(s_tile, second ? R::DO : R::D1, rb, TP, c);
+        const int col = 2 * t;
+        if (ti < NIN) {                                     // rows g (< 8): dW1[k = g][i]
+            const int i = 8 * ti + col;
+            if (i < IN) acc_f[g * IN + i] += c[0][0];
+            if (i + 1 < IN) acc_f[g * IN + i + 1] += c[0][1];
+        } else if (ti == NIN) {                             // ONE on A1: col 0 -> db1 (rows 0-7), db2 (rows 8-15)
+            if (t == 0) {
+                acc_f[B1 + g] += c[0][0];
+                if (d1row_f) d1row_f[g] += c[0][0];
+                acc_f[B2 + g] += c[0][2];
+            }
+        } else if (ti == NIN + 1) {                         // h1 on A1: rows 8-15 -> dW2[j = g][k]
+            acc_f[W2 + g * H + col] += c[0][2];
+            acc_f[W2 + g * H + col + 1] += c[0][3];
+        } else if (ti == NIN + 2) {                         // h2 on A2: dW3[o][j], o = g and g + 8
+            if (g < HALF) { acc_f[W3 + g * H + col] += c[0][0]; acc_f[W3 + g * H + col + 1] += c[0][1]; }
+            if (g + 8 < HALF) { acc_f[W3 + (g + 8) * H + col] += c[0][2]; acc_f[W3 + (g + 8) * H + col + 1] += c[0][3]; }
+        } else {                                            // ONE on A2: db3[o]
+            if (t == 0) {
+                if (g < HALF) acc_f[B3 + g] += c[0][0];
+                if (g + 8 < HALF) acc_f[B3 + g + 8] += c[0][2];
+            }
+        }
+    }
+}
 
 // entry e of the output table: (tile row of the delta, tile row of the activation, offset inside the packed FCNN)
 template <int HALF, int CP>
@@ -280,7 +333,7 @@ struct BwdSmem {
     using R = Rows<HALF, CP>;
     static size_t bytes(int n_fcnn, int C_row) {
         size_t fl = (size_t)n_fcnn * L::SIZE + n_fcnn * H + (size_t)n_fcnn * H * C_row  // images, hb, w1r
-                    + (size_t)R::COUNT * TS                                              // tile
+                    + (size_t)R::TROWS * TSM                                             // tile
                     + (size_t)n_fcnn * R::NOUT                                           // acc
                     + (size_t)n_fcnn * H * C_row                                         // accR
                     + n_fcnn * H                                                         // d1row
@@ -322,7 +375,7 @@ __device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s
     }
     // conditioning half is shared by both nets of the stage: stage it once
 #pragma unroll
-    for (int i = 0; i < HALF; ++i) s_tile[(R::C + i) * TS + tid] = c[i];
+    for (int i = 0; i < HALF; ++i) s_tile[(R::C + i) * TSM + tid] = c[i];
 #pragma unroll
     for (int net = 0; net < 2; ++net) {
         float d1[H], d2[H];
@@ -330,17 +383,18 @@ __device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s
         else          fcnn_bwd<HALF, CP>(img_s, ds, h1s, h2s, d1, d2, gc, gpc);
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-            s_tile[(R::H1 + k) * TS + tid] = net == 0 ? h1t[k] : h1s[k];
-            s_tile[(R::H2 + k) * TS + tid] = net == 0 ? h2t[k] : h2s[k];
-            s_tile[(R::D1 + k) * TS + tid] = d1[k];
-            s_tile[(R::D2 + k) * TS + tid] = d2[k];
+            s_tile[(R::H1 + k) * TSM + tid] = net == 0 ? h1t[k] : h1s[k];
+            s_tile[(R::H2 + k) * TSM + tid] = net == 0 ? h2t[k] : h2s[k];
+            s_tile[(R::D1 + k) * TSM + tid] = d1[k];
+            s_tile[(R::D2 + k) * TSM + tid] = d2[k];
         }
 #pragma unroll
-        for (int i = 0; i < HALF; ++i) s_tile[(R::DO + i) * TS + tid] = net == 0 ? dt[i] : ds[i];
+        for (int i = 0; i < HALF; ++i) s_tile[(R::DO + i) * TSM + tid] = net == 0 ? dt[i] : ds[i];
         __syncthreads();
         const int f = f_t + net;
         // b1 slots (first after the W1 block) double as the per-trajectory layer-1 delta sums (row-context hoist)
-        tile_accumulate(s_tab, R::NOUT, s_tile, s_acc + f * R::NOUT, H * (HALF + CP), s_d1row + f * H);
+        stage_weight_grads_mma<HALF, CP>(s_tile, s_acc + f * R::NOUT, s_d1row + f * H);
+        (void)s_tab;
         __syncthreads();
     }
 }

@@ -216,7 +216,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_red[33];
     const int tid = threadIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
-    constexpr int TILE_FLOATS = MODE == MODE_CNF && RC::COUNT * TS > PR::COUNT * TSM ? RC::COUNT * TS : PR::COUNT * TSM;
+    constexpr int TILE_FLOATS = (MODE == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT) * TSM;
     float* s_pe = smem;
     float* s_enc = s_pe + PE_SIZE;
     float* s_img = s_enc + 36;
@@ -294,8 +294,9 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { glo[i] = c * (lo[i] - p0); gup[i] = c * (up[i] - p0); }
 #pragma unroll
-                for (int k = 0; k < 32; ++k) { de[k] = 0.f; s_tile[(RC::PC + k) * TS + tid] = e[k]; }
-                s_tile[RC::ONE * TS + tid] = 1.0f;
+                for (int k = 0; k < 32; ++k) { de[k] = 0.f; s_tile[(RC::PC + k) * TSM + tid] = e[k]; }
+                s_tile[RC::ONE * TSM + tid] = 1.0f;
+                for (int r = RC::COUNT; r < RC::TROWS; ++r) s_tile[r * TSM + tid] = 0.0f;   // (the PE tile aliases these rows)
 #pragma unroll 1
                 for (int f = n_flows - 1; f >= 0; --f) {
                     const float* im = s_img + 4 * f * LC::SIZE;
@@ -366,11 +367,11 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         // d_enc[b][k] = sum over the row's particles (deterministic: through the tile)
         if (d_enc) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) s_tile[k * TS + tid] = denc[k];
+            for (int k = 0; k < 32; ++k) s_tile[k * TSM + tid] = denc[k];
             __syncthreads();
             if (tid < 32) {
                 float a = 0.f;
-                for (int p = 0; p < TP; ++p) a += s_tile[tid * TS + p];
+                for (int p = 0; p < TP; ++p) a += s_tile[tid * TSM + p];
                 d_enc[(size_t)b * HID + tid] = a;
             }
         }
@@ -394,7 +395,7 @@ static size_t fwd_smem(int mode, int n_flows, int N) {
 }
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    const size_t tile = mode == MODE_CNF && (size_t)RC::COUNT * TS > (size_t)PR::COUNT * TSM ? (size_t)RC::COUNT * TS : (size_t)PR::COUNT * TSM;
+    const size_t tile = (size_t)(mode == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT) * TSM;
     size_t fl = (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + tile + PE_SIZE + (size_t)n_fcnn * RC::NOUT + n_fcnn * H + 4 + 32;
     return fl * sizeof(float) + (size_t)(mode == MODE_CNF ? RC::NOUT : 0) * sizeof(int);
 }
