@@ -33,6 +33,8 @@ def parse():
     ap.add_argument("--measurement", default="gaussian")
     ap.add_argument("--resampler", default="soft")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inject-noise", action="store_true",
+                    help="feed the motion noise / resampling offsets from the host batch (as the parity tests do) instead of drawing them on the device")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph per step")
     return ap.parse_args()
 
@@ -56,6 +58,13 @@ def synth_batch(B, T, N, seed, pinned):
     if pinned:
         d = {k: v.contiguous().pin_memory() for k, v in d.items()}
     return d
+
+
+def workload_string(a):
+    return ("CNF-DPF (--NF-dyn --NF-cond) %s measurement, %s resampling forced every step, N=%d, B=%d per GPU, T=%d, precomputed encodings "
+            "(CNN encoder excluded), %s" % (a.measurement, a.resampler, a.N, a.B, a.T,
+                                            "motion noise / offsets injected from the batch" if a.inject_noise else
+                                            "motion noise / offsets drawn on the device"))
 
 
 class ClockSampler:
@@ -111,7 +120,7 @@ def step_b200(dpf, batch, dev, host_inputs, bucket=None):
     back (the e2e number); False: inputs are resident device tensors (the kernel-side `value`)."""
     from normalizing_flows_dpfs_b200.losses import supervised_loss
     d = {k: v.to(dev, non_blocking=True) for k, v in batch.items()} if host_inputs else batch
-    dpf.injected = dict(init_particles=d["init_particles"], noise=d["noise"], offsets=d["offsets"])
+    dpf.injected = {k: d[k] for k in ("init_particles", "noise", "offsets") if k in d}
     dpf.zero_grad(set_to_none=True)
     out = dpf.filtering_pos(d["enc"], d["start"], d["vel_in"])
     loss, _ = supervised_loss(out[0], out[1], d["state"], 1.0, False)
@@ -136,6 +145,9 @@ def main():
     from normalizing_flows_dpfs_b200 import _lib
     dpf = build_b200(a, dev)
     host = synth_batch(a.B, a.T, a.N, 100 + rank, pinned=True)     # weak scaling: every rank owns B trajectories
+    if not a.inject_noise:       # production setting: random draws on the device (Philox), nothing but observations cross PCIe
+        dpf.rng_device = "cuda"
+        host.pop("noise"), host.pop("offsets")
     resident = {k: v.to(dev) for k, v in host.items()}
     bucket = None
     if world > 1:
@@ -202,8 +214,7 @@ def main():
         "metric": "particle-steps/sec, NF-DPF filter fwd+bwd, N=%d" % a.N, "value": units * a.steps / (ms / 1e3), "unit": "particle-steps/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "CNF-DPF (--NF-dyn --NF-cond) %s measurement, %s resampling forced every step, N=%d, B=%d per GPU, T=%d, "
-                               "precomputed encodings (CNN encoder excluded)" % (a.measurement, a.resampler, a.N, a.B, a.T),
+        "config": {"workload": workload_string(a),
                    "l2": "per-step working set (particles, noise, lists: >300 MB) exceeds the 126 MB L2", "parallelism": "batch-sharded x%d%s" % (world, ", NCCL flat-gradient all-reduce per step" if world > 1 else ""),
                    "execution": "eager launches" if a.no_graph else "one CUDA graph replay per step (forward over T + loss + backward)"},
         "e2e": {"value": units * a.steps / (ms_e2e / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},

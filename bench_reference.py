@@ -53,6 +53,7 @@ def sample_shape(a):
 def run_reference(a, rank, world):
     if rank != 0:
         return
+    from bench import workload_string
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B, T = sample_shape(a)
@@ -65,8 +66,7 @@ def run_reference(a, rank, world):
     line = {"impl": "reference", "metric": "particle-steps/sec, NF-DPF filter fwd+bwd, N=%d" % a.N, "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "CNF-DPF (--NF-dyn --NF-cond) %s measurement, %s resampling forced every step, N=%d, B=%d per GPU, T=%d, "
-                                   "precomputed encodings (CNN encoder excluded)" % (a.measurement, a.resampler, a.N, a.B, a.T)},
+            "config": {"workload": workload_string(a)},
             "cpu_baseline": {"value": value, "unit": "particle-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

@@ -43,6 +43,9 @@ class DPF(nn.Module):
         # optional hooks: injected random draws (parity tests / benchmarks) and a gate override
         self.injected = None          # dict(init_particles, noise (B,T,N,2), offsets (B,T)) or None
         self.force_resample = None    # None = the reference's ESS gate; True / False = always / never
+        self.rng_device = "cpu"       # "cpu": draws come from the CPU generator in the reference's order (seed-compatible);
+                                      # "cuda": motion noise / resampling offsets are drawn on the device (no per-step H2D,
+                                      #         CUDA-graph capturable) -- SURVEY 8(f2)
         self.fired = []
 
     # ------------------------------------------------------------------------------------------ construction
@@ -130,6 +133,8 @@ class DPF(nn.Module):
             self.fired.append(fire)
             if fire and soft:   # one kernel: scan + search + gather + renormalise (+ log of the new weights, DPFs.py:167)
                 off = inj["offsets"][:, step] if inj is not None and "offsets" in inj else None
+                if off is None and self.rng_device == "cuda":
+                    off = torch.rand(B, device=particles.device) / N
                 particles, probs_res, index_p, logw_prev = self.resampler.resampling(particles, particle_probs, random_offset=off,
                                                                                      want_log=True, **self.resampler.kargs)
             elif fire:
@@ -141,7 +146,9 @@ class DPF(nn.Module):
             encodings = self.encoder(obs[:, step].float())
             if fused:
                 # ---- fused step: 6 libnfdpf launches (motion+moments, 3 coupling stacks, densities, measurement+update)
-                if noise is None:
+                if noise is None and self.rng_device == "cuda":
+                    noise = torch.randn(B, N, 2, device=particles.device) * self.pos_noise
+                elif noise is None:
                     noise = torch.normal(mean=0.0, std=self.pos_noise, size=(B, N, 2)).to(particles.device, non_blocking=True)
                 ctx_phys = torch.empty(B, 4, dtype=torch.float32, device=particles.device) if self.NF else None
                 particles_physical = ops.motion_moments(particles, vel, noise, ctx_phys, 0)

@@ -19,6 +19,9 @@ class GraphedFilterStep:
     KEYS = ("enc", "start", "vel_in", "state", "init_particles", "noise", "offsets")
 
     def __init__(self, dpf, batch, warmup=2):
+        self.KEYS = tuple(k for k in self.KEYS if k in batch)   # noise / offsets may be left to the device RNG
+        if ("noise" not in batch or "offsets" not in batch) and dpf.rng_device != "cuda":
+            raise ValueError("graph capture without injected noise / offsets needs dpf.rng_device = 'cuda'")
         if dpf.force_resample is None:
             raise ValueError("graph capture needs a host-free ESS gate: set dpf.force_resample to True or False")
         self.dpf = dpf
@@ -41,7 +44,7 @@ class GraphedFilterStep:
 
     def _step(self):
         d, dpf = self.static, self.dpf
-        dpf.injected = dict(init_particles=d["init_particles"], noise=d["noise"], offsets=d["offsets"])
+        dpf.injected = {k: d[k] for k in ("init_particles", "noise", "offsets") if k in d}
         dpf.zero_grad(set_to_none=False) if any(p.grad is not None for p in dpf.parameters()) else None
         out = dpf.filtering_pos(d["enc"], d["start"], d["vel_in"])
         loss, _ = supervised_loss(out[0], out[1], d["state"], 1.0, False)
