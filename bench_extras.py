@@ -126,6 +126,37 @@ def kernel_table(a, dpf, dev):
     return rows
 
 
+def ot_metric(dev, peaks):
+    """Second half of the BASELINE metric: OT-resample time per call (forward and backward) at the BASELINE shapes,
+    with the SFU roofline: useful pair evaluations (2 per loop iteration + 2 init + 2 final + 1 transport,
+    one ex2 each) / duration against the ex2 rate measured by the probe kernel."""
+    from normalizing_flows_dpfs_b200 import ops
+    out = []
+    for B, N in ((1024, 1024), (256, 4096)):
+        g = torch.Generator(device=dev).manual_seed(5)
+        w = torch.softmax(torch.randn(B, N, device=dev, generator=g) * 2, -1)
+        x = (torch.randn(B, N, 2, device=dev, generator=g) * 20).requires_grad_()
+        gy = torch.randn(B, N, 2, device=dev, generator=g)
+        lw = w.log()
+        p = ops.ot_resample(x, lw)
+        p.backward(gy)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        p = ops.ot_resample(x, lw)
+        ev[1].record()
+        p.backward(gy)
+        ev[2].record()
+        torch.cuda.synchronize()
+        iters = int(ops.OtResample.last_iters.item())
+        pairs = B * N * N * (2 * (iters - 2) + 2 + 2 + 1)
+        fwd_s = ev[0].elapsed_time(ev[1]) * 1e-3
+        out.append({"B": B, "N": N, "sinkhorn_iterations": iters, "fwd_us": fwd_s * 1e6, "bwd_us": ev[1].elapsed_time(ev[2]) * 1e3,
+                    "pair_evals": pairs, "achieved_tops": pairs / fwd_s / 1e12, "sfu_peak_tops": peaks["sfu_tops"],
+                    "frac_of_sfu_peak": pairs / fwd_s / 1e12 / peaks["sfu_tops"]})
+    return out
+
+
 def roofline_and_cpu(a, dpf, resident, dev, ms_per_step):
     peaks = measured_peaks(dev)
     rows = kernel_table(a, dpf, dev)
@@ -143,6 +174,10 @@ def roofline_and_cpu(a, dpf, resident, dev, ms_per_step):
                         else peaks["hbm_source"], "share_of_step": top["share_of_step"]},
            "roofline_kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()} for r in rows],
            "peaks": peaks}
+    try:
+        out["ot_resample"] = ot_metric(dev, peaks)
+    except Exception as e:
+        out["ot_resample"] = {"error": repr(e)}
     if not a.no_cpu_baseline:
         from bench_reference import cpu_filter_step, sample_shape
         cores = os.cpu_count() or 1

@@ -43,6 +43,22 @@ __device__ __forceinline__ void pe_fwd(const float* __restrict__ w, float x0, fl
     }
 }
 
+// layers 1-2 only (the Gaussian backward fuses layer 3 forward with its transposed backward in one rolled loop)
+__device__ __forceinline__ void pe_fwd_l12(const float* __restrict__ w, float x0, float x1, float (&a1)[16], float (&a2)[32]) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a1[k] = fmaxf(fmaf(w[PE_W1 + 2 * k + 1], x1, fmaf(w[PE_W1 + 2 * k], x0, w[PE_B1 + k])), 0.f);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float a = w[PE_B2 + j];
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+            const float4 q = *reinterpret_cast<const float4*>(w + PE_W2 + j * 16 + k);
+            a = fmaf(q.x, a1[k], a); a = fmaf(q.y, a1[k + 1], a); a = fmaf(q.z, a1[k + 2], a); a = fmaf(q.w, a1[k + 3], a);
+        }
+        a2[j] = fmaxf(a, 0.f);
+    }
+}
+
 // log-likelihood of one particle given its encoding e; for MODE_CNF also returns z (= [lo|up]) for the backward.
 template <int MODE>
 __device__ __forceinline__ float loglik(const float (&e)[32], const float* __restrict__ s_enc, float p0, float p1,
@@ -169,7 +185,8 @@ struct PR {
 // Particle-encoder weight gradients of one batch on the tensor path (3xTF32), added into s_accpe (packed PE order).
 //   warps 0,1: dW3 | db3 = delta3(16 rows each) x [a2 (4 n-tiles) | 1]
 //   warps 2,3: dW2 | db2 = delta2(16 rows each) x [a1 (2 n-tiles) | 1];  warp 2 also dW1 | db1 = delta1 x [x0 x1 1]
-__device__ __forceinline__ void pe_weight_grads_mma(const float* __restrict__ s_tile, float* __restrict__ s_accpe) {
+__device__ __forceinline__ void pe_weight_grads_mma(const float* __restrict__ s_tile, float* __restrict__ s_accpe,
+                                                    float* __restrict__ rowsum3) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     if (warp < 2) {
         float c[5][4] = {};
@@ -181,7 +198,10 @@ __device__ __forceinline__ void pe_weight_grads_mma(const float* __restrict__ s_
             float* w = s_accpe + PE_W3 + o * 32 + 8 * n + 2 * t;
             w[0] += c[n][0]; w[1] += c[n][1]; w[8 * 32] += c[n][2]; w[8 * 32 + 1] += c[n][3];
         }
-        if (t == 0) { s_accpe[PE_B3 + o] += c[4][0]; s_accpe[PE_B3 + o + 8] += c[4][2]; }
+        if (t == 0) {
+            s_accpe[PE_B3 + o] += c[4][0]; s_accpe[PE_B3 + o + 8] += c[4][2];
+            if (rowsum3) { rowsum3[o] += c[4][0]; rowsum3[o + 8] += c[4][2]; }   // per-trajectory sum of delta3 (Gaussian: = -d enc)
+        }
     } else {
         float c[3][4] = {};
         const int rowB[3] = {PR::A1 + g, PR::A1 + 8 + g, g == 0 ? PR::ONE : PR::ZERO};
@@ -259,6 +279,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         float denc[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) denc[k] = 0.f;
+        if (tid < 32) s_denc[tid] = 0.f;
         __syncthreads();
         for (int n0 = 0; n0 < N; n0 += TP) {
             asm volatile("" ::: "memory");  // no LICM of shared-memory weight loads across particles
@@ -268,13 +289,36 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
             const float2 x = *reinterpret_cast<const float2*>(particles + p * 2);
             float g = live ? g_lki[p] : 0.f;
             if (live && n == am) g -= gs;
-            float a1[16], a2[32], e[32], de[32];
-            pe_fwd(s_pe, x.x, x.y, a1, a2, e);
-            if (MODE == MODE_GAUSS) {
-                const float c = g / (p1 * p1);
+            float a1[16], a2[32], e[32], de[32], d2[32];
 #pragma unroll
-                for (int k = 0; k < 32; ++k) { de[k] = c * (s_enc[k] - e[k] - p0); denc[k] -= de[k]; }
+            for (int j = 0; j < 32; ++j) d2[j] = 0.f;
+            if (MODE == MODE_GAUSS) {
+                // layer 3 forward fused with its transposed backward: one pass over W3 (rolled: small code, half the LDS);
+                // delta3 goes straight into the tile (free here: the previous batch's mma phase ended with a barrier)
+                pe_fwd_l12(s_pe, x.x, x.y, a1, a2);
+                const float c = live ? g / (p1 * p1) : 0.f;
+#pragma unroll 4
+                for (int o = 0; o < 32; ++o) {
+                    float w[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W3 + o * 32 + j);
+                        w[j] = q.x; w[j + 1] = q.y; w[j + 2] = q.z; w[j + 3] = q.w;
+                    }
+                    float e0 = s_pe[PE_B3 + o], e1 = 0.f, e2 = 0.f, e3 = 0.f;   // four chains: the rolled loop has no other ILP
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        e0 = fmaf(w[j], a2[j], e0); e1 = fmaf(w[j + 1], a2[j + 1], e1);
+                        e2 = fmaf(w[j + 2], a2[j + 2], e2); e3 = fmaf(w[j + 3], a2[j + 3], e3);
+                    }
+                    const float eo = (e0 + e1) + (e2 + e3);
+                    const float deo = c * (s_enc[o] - eo - p0);
+                    s_tile[(PR::D3 + o) * TSM + tid] = deo;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) d2[j] = fmaf(w[j], deo, d2[j]);
+                }
             } else if (MODE == MODE_COS) {
+                pe_fwd(s_pe, x.x, x.y, a1, a2, e);
                 float ne = 0.f, dot = 0.f;
 #pragma unroll
                 for (int k = 0; k < 32; ++k) { ne = fmaf(e[k], e[k], ne); dot = fmaf(s_enc[k], e[k], dot); }
@@ -288,6 +332,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                     denc[k] += c * (bh - ab * ah) / nenc;
                 }
             } else {
+                pe_fwd(s_pe, x.x, x.y, a1, a2, e);
                 float lo[16], up[16], glo[16], gup[16];
                 loglik<MODE_CNF>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
                 const float c = -g / (p1 * p1);
@@ -313,9 +358,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
             }
             // particle-encoder backward (the clobber stops the compiler from keeping the forward's weight loads alive: 6 KB of spills)
             asm volatile("" ::: "memory");
-            float d2[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) d2[j] = 0.f;
+            if (MODE != MODE_GAUSS) {
 #pragma unroll
             for (int o = 0; o < 32; ++o) {
                 if (!live) de[o] = 0.f;
@@ -325,6 +368,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                     d2[j] = fmaf(q.x, de[o], d2[j]); d2[j + 1] = fmaf(q.y, de[o], d2[j + 1]);
                     d2[j + 2] = fmaf(q.z, de[o], d2[j + 2]); d2[j + 3] = fmaf(q.w, de[o], d2[j + 3]);
                 }
+            }
             }
             float d1[16];
 #pragma unroll
@@ -358,14 +402,16 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
             for (int j = 0; j < 32; ++j) {
                 s_tile[(PR::A2 + j) * TSM + tid] = a2[j];
                 s_tile[(PR::D2 + j) * TSM + tid] = d2[j];
-                s_tile[(PR::D3 + j) * TSM + tid] = de[j];
+                if (MODE != MODE_GAUSS) s_tile[(PR::D3 + j) * TSM + tid] = de[j];
             }
             __syncthreads();
-            pe_weight_grads_mma(s_tile, s_accpe);
+            pe_weight_grads_mma(s_tile, s_accpe, MODE == MODE_GAUSS ? s_denc : nullptr);
             __syncthreads();
         }
         // d_enc[b][k] = sum over the row's particles (deterministic: through the tile)
-        if (d_enc) {
+        if (d_enc && MODE == MODE_GAUSS) {
+            if (tid < 32) d_enc[(size_t)b * HID + tid] = -s_denc[tid];   // d ll / d enc = -sum_p delta3
+        } else if (d_enc) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) s_tile[k * TSM + tid] = denc[k];
             __syncthreads();
