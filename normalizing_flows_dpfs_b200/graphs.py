@@ -4,7 +4,8 @@ The per-timestep update is a chain of ~15 short libnfdpf launches (forward) plus
 B = N = 1024 each runs 20-400 us, so Python/ctypes/autograd dispatch (~40 us per launch) is comparable to the GPU
 time of the forward pass.  Capturing the step once and replaying it removes the host from the loop: one
 cudaGraphLaunch per training step.  Requirements (checked): the ESS gate must not need the host
-(`force_resample` set), and random draws must be injected or generated on the device."""
+(`force_resample` set), and random draws must be injected or generated on the device.  Drop every reference to the
+outputs / loss of earlier eager steps before capturing (they keep autograd nodes bound to the default stream)."""
 import torch
 
 from .losses import supervised_loss
@@ -39,8 +40,14 @@ class GraphedFilterStep:
         torch.cuda.synchronize()
         dpf.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._step()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step()
+        except RuntimeError as err:
+            raise RuntimeError(
+                "CUDA-graph capture of the filter step failed.  The usual cause: tensors from an earlier eager step (loss, "
+                "filter outputs) are still alive and pin the parameters' AccumulateGrad nodes to the default stream -- delete "
+                "them before constructing GraphedFilterStep.  Original error: %s" % (err,)) from err
 
     def _step(self):
         d, dpf = self.static, self.dpf

@@ -80,11 +80,13 @@ def test_cuda_graph_step_equals_eager():
     dpf.zero_grad(set_to_none=True)
     loss.backward()
     eager = [p.grad.clone() for p in dpf.nf_dyn.parameters()]
+    loss = loss.detach().clone()
+    del out                                              # nothing of the eager autograd graph may outlive this point
     step = GraphedFilterStep(dpf, batch)
     for _ in range(2):                                   # replays are idempotent for fixed inputs
         g_loss = step.run(batch)
         torch.cuda.synchronize()
-        assert torch.allclose(g_loss, loss.detach(), rtol=1e-6, atol=0)
+        assert torch.allclose(g_loss, loss, rtol=1e-6, atol=0)
         for a, p in zip(eager, dpf.nf_dyn.parameters()):
             assert torch.equal(a, p.grad), "graph replay must reproduce the eager gradients bit for bit (deterministic reductions)"
 
