@@ -52,10 +52,14 @@ class GraphedFilterStep:
     def _step(self):
         d, dpf = self.static, self.dpf
         dpf.injected = {k: d[k] for k in ("init_particles", "noise", "offsets") if k in d}
-        dpf.zero_grad(set_to_none=False) if any(p.grad is not None for p in dpf.parameters()) else None
         out = dpf.filtering_pos(d["enc"], d["start"], d["vel_in"])
         loss, _ = supervised_loss(out[0], out[1], d["state"], 1.0, False)
-        loss.backward()
+        # torch.autograd.grad instead of .backward(): no AccumulateGrad nodes run, so the capture does not depend on
+        # which stream the parameters' accumulators were first created on; .grad is (re)bound to the static outputs
+        params = [p for p in dpf.parameters() if p.requires_grad]
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        for p, g in zip(params, grads):
+            p.grad = g
         return loss
 
     def run(self, batch=None):
