@@ -7,6 +7,7 @@ cudaGraphLaunch per training step.  Requirements (checked): the ESS gate must no
 (`force_resample` set), and random draws must be injected or generated on the device.  Drop every reference to the
 outputs / loss of earlier eager steps before capturing (they keep autograd nodes bound to the default stream)."""
 import torch
+from torch.nn.utils.stateless import _reparametrize_module
 
 from .losses import supervised_loss
 
@@ -52,14 +53,18 @@ class GraphedFilterStep:
     def _step(self):
         d, dpf = self.static, self.dpf
         dpf.injected = {k: d[k] for k in ("init_particles", "noise", "offsets") if k in d}
-        out = dpf.filtering_pos(d["enc"], d["start"], d["vel_in"])
-        loss, _ = supervised_loss(out[0], out[1], d["state"], 1.0, False)
-        # torch.autograd.grad instead of .backward(): no AccumulateGrad nodes run, so the capture does not depend on
-        # which stream the parameters' accumulators were first created on; .grad is (re)bound to the static outputs
-        params = [p for p in dpf.parameters() if p.requires_grad]
-        grads = torch.autograd.grad(loss, params, allow_unused=True)
-        for p, g in zip(params, grads):
-            p.grad = g
+        # Run on fresh leaf views of the parameters (same storage): their AccumulateGrad nodes are created on the current
+        # (side / capture) stream.  The real parameters' accumulators may be pinned to the legacy default stream by any
+        # still-alive tensor of an earlier eager step, which would make the capture illegal.
+        names = [n for n, p in dpf.named_parameters() if p.requires_grad]
+        real = dict(dpf.named_parameters())
+        proxies = {n: real[n].detach().requires_grad_() for n in names}
+        with _reparametrize_module(dpf, proxies):
+            out = dpf.filtering_pos(d["enc"], d["start"], d["vel_in"])
+            loss, _ = supervised_loss(out[0], out[1], d["state"], 1.0, False)
+            grads = torch.autograd.grad(loss, [proxies[n] for n in names], allow_unused=True)
+        for n, g in zip(names, grads):
+            real[n].grad = g          # static graph outputs: every replay refreshes them in place
         return loss
 
     def run(self, batch=None):
