@@ -88,18 +88,6 @@ struct OpMin {
     __device__ __forceinline__ float operator()(float a, float b) const { return fminf(a, b); }
 };
 
-// ---- packed fp32x2 FMA (sm_100a FFMA2: two IEEE fp32 FMAs per issue slot; ptxas folds a (s,s) operand into a scalar
-// broadcast).  The kernels on this path are issue-bound, not FMA-pipe-bound, so halving the FMA instruction count pays.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;"
-        : "=l"(d)
-        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
-          "l"(*reinterpret_cast<unsigned long long*>(&c)));
-    return *reinterpret_cast<float2*>(&d);
-}
-__device__ __forceinline__ float2 ffma2(float2 a, float s, float2 c) { return ffma2(a, make_float2(s, s), c); }
-
 // ---- transcendental helpers ------------------------------------------------------------------------------
 // tanh with ~2e-7 ABSOLUTE error from two MUFU ops: t = 2^(-2|x| log2 e) in (0,1], tanh|x| = (1 - t) / (1 + t).
 // The parity bar is rtol 1e-4 / atol 1e-5 against fp32 torch; tanh.approx.f32 (2^-11 relative) would not hold it.

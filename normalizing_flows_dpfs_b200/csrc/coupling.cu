@@ -8,8 +8,10 @@ namespace nfdpf {
 constexpr int MAX_FCNN = 16;      // n_flows <= 4
 
 // ------------------------------------------------------------------------------------------------- forward
+constexpr int TPF = 256;          // forward: 8 warps per CTA (no tile, 50-80 registers): more resident warps to cover MUFU / LDS latency
+
 template <int HALF, int CP>
-__global__ void __launch_bounds__(TP)
+__global__ void __launch_bounds__(TPF)
 coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ x,
                     const float* __restrict__ row_ctx, const float* __restrict__ part_ctx, int flags, int N, int chunk,
                     float* __restrict__ y, float* __restrict__ log_det) {
@@ -23,13 +25,13 @@ coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     const int b = blockIdx.y;
     const int pf = packed_fcnn_size(HALF, C_row + CP);
     for (int f = 0; f < n_fcnn; ++f)
-        load_fcnn_image<HALF, CP>(packed + (size_t)f * pf, C_row, s_img + f * L::SIZE, s_w1r + (size_t)f * H * C_row, tid, TP);
+        load_fcnn_image<HALF, CP>(packed + (size_t)f * pf, C_row, s_img + f * L::SIZE, s_w1r + (size_t)f * H * C_row, tid, TPF);
     __syncthreads();
-    hoist_row_context<HALF, CP>(s_img, s_w1r, row_ctx + (size_t)b * C_row, C_row, n_fcnn, s_hb, tid, TP);
+    hoist_row_context<HALF, CP>(s_img, s_w1r, row_ctx + (size_t)b * C_row, C_row, n_fcnn, s_hb, tid, TPF);
     __syncthreads();
     const int inverse = flags & 1;  // bit 1: emit jac = -log_det instead of log_det
     const int n0 = blockIdx.x * chunk, n1 = min(N, n0 + chunk);
-    for (int n = n0 + tid; n < n1; n += TP) {
+    for (int n = n0 + tid; n < n1; n += TPF) {
         const size_t p = (size_t)b * N + n;
         float lo[HALF], up[HALF], pc[CP > 0 ? CP : 1], ld = 0.f;
 #pragma unroll
@@ -198,10 +200,10 @@ static int launch_fwd(const float* packed, int n_flows, int C_row, const float* 
     // enough CTAs to fill the GPU even when B is small: split rows into chunks of >= TP particles
     int chunks = 1;
     const int target = 4 * sm_count();
-    while (B * chunks < target && N / (chunks * 2) >= TP) chunks *= 2;
-    const int chunk = ((N + chunks - 1) / chunks + TP - 1) / TP * TP;
+    while (B * chunks < target && N / (chunks * 2) >= TPF) chunks *= 2;
+    const int chunk = ((N + chunks - 1) / chunks + TPF - 1) / TPF * TPF;
     dim3 grid((N + chunk - 1) / chunk, B);
-    kern<<<grid, TP, smem, st>>>(packed, n_flows, C_row, x, row_ctx, part_ctx, inverse, N, chunk, y, log_det);
+    kern<<<grid, TPF, smem, st>>>(packed, n_flows, C_row, x, row_ctx, part_ctx, inverse, N, chunk, y, log_det);
     return check_launch("coupling_fwd");
 }
 
