@@ -33,6 +33,7 @@ def parse():
     ap.add_argument("--measurement", default="gaussian")
     ap.add_argument("--resampler", default="soft")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the roofline / OT / cpu_baseline legs (profiling runs)")
     ap.add_argument("--inject-noise", action="store_true",
                     help="feed the motion noise / resampling offsets from the host batch (as the parity tests do) instead of drawing them on the device")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph per step")
@@ -221,8 +222,9 @@ def main():
         "gpu_launches": int(launches), "clocks": clk,
     }
     try:
-        from bench_extras import roofline_and_cpu
-        line.update(roofline_and_cpu(a, dpf, resident, dev, ms / a.steps))
+        if not a.no_extras:
+            from bench_extras import roofline_and_cpu
+            line.update(roofline_and_cpu(a, dpf, resident, dev, ms / a.steps))
     except Exception as e:  # never lose the headline line
         line["roofline_error"] = repr(e)
     print(json.dumps(line))

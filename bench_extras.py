@@ -52,6 +52,14 @@ def _events(fn, n=10, warm=3):
     return best
 
 
+def _traffic(kernel):
+    """dram__bytes_read + dram__bytes_write per launch from the committed ncu capture (profiles/r1_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(kernel)
+    except OSError:
+        return None
+
+
 def measured_peaks(dev):
     from normalizing_flows_dpfs_b200 import _lib as L
     out = torch.zeros(4, device=dev)
@@ -89,24 +97,25 @@ def kernel_table(a, dpf, dev):
         pe = pack_parameters([dpf.particle_encoder])
     rows = []
 
-    def add(name, fwd, flops_f, bytes_f, flops_b, bytes_b, grads, per_step_f, per_step_b):
+    def add(name, fwd, flops_f, bytes_f, flops_b, bytes_b, grads, per_step_f, per_step_b, sfu=0):
         out = fwd()
         outs = [o for o in (out if isinstance(out, tuple) else (out,)) if o is not None and o.requires_grad]
         tf = _events(lambda: fwd(), n=5)
-        rows.append(dict(kernel=name + "_fwd", sec=tf, flops=flops_f * P, bytes=bytes_f * P, launches_per_step=per_step_f))
+        rows.append(dict(kernel=name + "_fwd", sec=tf, flops=flops_f * P, bytes=bytes_f * P, sfu_ops=sfu * P, launches_per_step=per_step_f))
         if outs:
             gouts = [grads[tuple(o.shape)] for o in outs]
 
             def bwd():
                 torch.autograd.backward(outs, gouts, retain_graph=True)
             tb = _events(bwd, n=5)
-            rows.append(dict(kernel=name + "_bwd", sec=tb, flops=flops_b * P, bytes=bytes_b * P, launches_per_step=per_step_b))
+            rows.append(dict(kernel=name + "_bwd", sec=tb, flops=flops_b * P, bytes=bytes_b * P, sfu_ops=sfu * P, launches_per_step=per_step_b))
 
     grads = {(B, N, 2): gy, (B, N): gl}
     pkc, pkd = pk_c.clone().requires_grad_(), pk_d.clone().requires_grad_()
     xr = x.clone().requires_grad_()
-    add("coupling_D2_C36", lambda: ops.coupling_stack(pkc, xr, ctx36, None, 2, True), 1280, 20, 2560, 40, grads, 1, 1)
-    add("coupling_D2_C4", lambda: ops.coupling_stack(pkd, xr, ctx36[:, :4].contiguous(), None, 2, True), 1280, 20, 2560, 40, grads, 2, 2)
+    # 128 tanh (2 MUFU each: ex2 + rcp) + 4 exp per stack pass; the backward re-evaluates every FCNN once
+    add("coupling_D2_C36", lambda: ops.coupling_stack(pkc, xr, ctx36, None, 2, True), 1280, 20, 2560, 40, grads, 1, 1, sfu=260)
+    add("coupling_D2_C4", lambda: ops.coupling_stack(pkd, xr, ctx36[:, :4].contiguous(), None, 2, True), 1280, 20, 2560, 40, grads, 2, 2, sfu=260)
     per = pe.clone().requires_grad_()
     lw0 = w.log()
     mode = a.measurement
@@ -166,14 +175,20 @@ def roofline_and_cpu(a, dpf, resident, dev, ms_per_step):
     for r in rows:
         r["share_of_step"] = r["sec"] * r["launches_per_step"] / step_sec
         if r["flops"] > 0 and r["flops"] / max(r["bytes"], 1) > 10:   # arithmetic intensity >> machine balance: compute bound
-            r.update(bound="fp32", achieved=r["flops"] / r["sec"] / 1e12, peak=peaks["fp32_tflops"], unit="TFLOP/s")
+            f_fp32 = r["flops"] / r["sec"] / 1e12 / peaks["fp32_tflops"]
+            f_sfu = r.get("sfu_ops", 0) / r["sec"] / 1e12 / peaks["sfu_tops"]
+            r["frac_fp32"], r["frac_sfu"] = f_fp32, f_sfu
+            if f_sfu > f_fp32:   # the MUFU pipe (16 lanes/clk/SM) binds before the FP32 pipe (128 lanes/clk/SM)
+                r.update(bound="sfu", achieved=r["sfu_ops"] / r["sec"] / 1e12, peak=peaks["sfu_tops"], unit="Tops/s (MUFU)")
+            else:
+                r.update(bound="fp32", achieved=r["flops"] / r["sec"] / 1e12, peak=peaks["fp32_tflops"], unit="TFLOP/s")
         else:
             r.update(bound="hbm", achieved=r["bytes"] / r["sec"] / 1e9, peak=peaks["hbm_gbs"], unit="GB/s")
         r["frac"] = r["achieved"] / r["peak"]
     top = max(rows, key=lambda r: r["share_of_step"])
     out = {"roofline": {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"],
-                        "frac": top["frac"], "traffic": None, "peak_source": "FFMA probe kernel measured in this run" if top["bound"] == "fp32"
-                        else peaks["hbm_source"], "share_of_step": top["share_of_step"]},
+                        "frac": top["frac"], "traffic": _traffic(top["kernel"]), "peak_source": peaks["hbm_source"] if top["bound"] == "hbm"
+                        else "FFMA / MUFU probe kernel (nfdpf_peak_probe) measured in this run", "share_of_step": top["share_of_step"]},
            "roofline_kernels": [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items()} for r in rows],
            "peaks": peaks}
     try:
