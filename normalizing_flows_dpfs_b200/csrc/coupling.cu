@@ -80,15 +80,9 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     float* s_accR = s_acc + n_fcnn * R::NOUT;
     float* s_d1row = s_accR + (size_t)n_fcnn * H * C_row;
     float* s_ctx = s_d1row + n_fcnn * H;
-    int* s_tab = reinterpret_cast<int*>(s_ctx + C_row + 4);
     const int pf = packed_fcnn_size(HALF, C_row + CP);
     for (int f = 0; f < n_fcnn; ++f)
         load_fcnn_image<HALF, CP>(packed + (size_t)f * pf, C_row, s_img + f * L::SIZE, s_w1r + (size_t)f * H * C_row, tid, TP);
-    for (int e = tid; e < R::NOUT; e += TP) {
-        int ra, rb, poff;
-        out_entry<HALF, CP>(e, C_row, ra, rb, poff);
-        s_tab[e] = ra | (rb << 16);
-    }
     for (int e = tid; e < n_fcnn * R::NOUT; e += TP) s_acc[e] = 0.f;
     for (int e = tid; e < n_fcnn * H * C_row; e += TP) s_accR[e] = 0.f;
     s_tile[R::ONE * TSM + tid] = 1.0f;
@@ -122,9 +116,9 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
                     const float* im = s_img + 4 * f * L::SIZE;
                     const float* hb = s_hb + 4 * f * H;
                     stage_bwd<HALF, CP, false>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, 4 * f + 2, live, up, gup,
-                                               pc, gpc, lo, glo, gld, s_tile, s_acc, s_d1row, s_tab);
+                                               pc, gpc, lo, glo, gld, s_tile, s_acc, s_d1row);
                     stage_bwd<HALF, CP, false>(im, im + L::SIZE, hb, hb + H, 4 * f, live, lo, glo, pc, gpc, up, gup, gld, s_tile,
-                                               s_acc, s_d1row, s_tab);
+                                               s_acc, s_d1row);
                 }
             } else {         // inverse pass ran flows n-1..0 (t2/s2 then t1/s1): walk back 0..n-1 (t1/s1 then t2/s2)
 #pragma unroll 1
@@ -132,9 +126,9 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
                     const float* im = s_img + 4 * f * L::SIZE;
                     const float* hb = s_hb + 4 * f * H;
                     stage_bwd<HALF, CP, true>(im, im + L::SIZE, hb, hb + H, 4 * f, live, lo, glo, pc, gpc, up, gup, gld, s_tile,
-                                              s_acc, s_d1row, s_tab);
+                                              s_acc, s_d1row);
                     stage_bwd<HALF, CP, true>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, 4 * f + 2, live, up, gup,
-                                              pc, gpc, lo, glo, gld, s_tile, s_acc, s_d1row, s_tab);
+                                              pc, gpc, lo, glo, gld, s_tile, s_acc, s_d1row);
                 }
             }
             if (live) {
@@ -160,10 +154,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     float* out = partials + (size_t)blockIdx.x * n_fcnn * pf;
     const int fin = HALF + C_row + CP;
     for (int e = tid; e < n_fcnn * R::NOUT; e += TP) {
-        const int f = e / R::NOUT;
-        int ra, rb, poff;
-        out_entry<HALF, CP>(e % R::NOUT, C_row, ra, rb, poff);
-        out[(size_t)f * pf + poff] = s_acc[e];
+        out[(size_t)(e / R::NOUT) * pf + packed_offset<HALF, CP>(e % R::NOUT, C_row)] = s_acc[e];
     }
     for (int e = tid; e < n_fcnn * H * C_row; e += TP) {
         const int fk = e / C_row, cidx = e % C_row;

@@ -213,31 +213,10 @@ __device__ __forceinline__ void stage_fwd(const float* img_t, const float* img_s
 }
 
 
-// ---- CTA-wide weight-gradient accumulation through a transposed shared-memory tile --------------------------
+// ---- CTA batch geometry of the backward kernels (deltas / activations are staged transposed in a shared-memory tile,
+// row = feature, column = particle; stride TSM, see mma_tile.cuh) -------------------------------------------------
 constexpr int TP = 128;           // particles per CTA batch (= threads per CTA)
-constexpr int TS = TP + 1;        // tile row stride (conflict-free for lane-distinct rows)
 
-// acc[e] += sum_p tile[ra(e)][p] * tile[rb(e)][p] for e < nout; entry e is owned by thread e % TP (no atomics,
-// fixed summation order).  Entries [row_lo, row_lo+8) are additionally added to row_acc (may be null).
-__device__ __forceinline__ void tile_accumulate(const int* __restrict__ s_tab, int nout, const float* __restrict__ s_tile,
-                                                float* __restrict__ acc, int row_lo, float* __restrict__ row_acc) {
-    for (int e = threadIdx.x; e < nout; e += TP) {
-        const int tab = s_tab[e];
-        const float* ra = s_tile + (tab & 0xffff) * TS;
-        const float* rb = s_tile + (tab >> 16) * TS;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-        for (int p = 0; p < TP; p += 4) {
-            a0 = fmaf(ra[p], rb[p], a0);
-            a1 = fmaf(ra[p + 1], rb[p + 1], a1);
-            a2 = fmaf(ra[p + 2], rb[p + 2], a2);
-            a3 = fmaf(ra[p + 3], rb[p + 3], a3);
-        }
-        const float a = (a0 + a1) + (a2 + a3);
-        acc[e] += a;
-        if (row_acc && e >= row_lo && e < row_lo + H) row_acc[e - row_lo] += a;
-    }
-}
 
 // ---- backward of one coupling stage ---------------------------------------------------------------------
 // Tile rows (one column per particle of the batch):
@@ -301,30 +280,15 @@ __device__ __forceinline__ void stage_weight_grads_mma(const float* __restrict__
     }
 }
 
-// entry e of the output table: (tile row of the delta, tile row of the activation, offset inside the packed FCNN)
+// packed-FCNN offset (row-context columns skipped) of gradient entry e, e in [0, NOUT): the order of acc_f above
 template <int HALF, int CP>
-__device__ void out_entry(int e, int C_row, int& ra, int& rb, int& poff) {
-    using R = Rows<HALF, CP>;
+__device__ int packed_offset(int e, int C_row) {
     const int fin = HALF + C_row + CP;
-    int o = e;
-    if (o < H * (HALF + CP)) {
-        const int k = o / (HALF + CP), i = o % (HALF + CP);
-        ra = R::D1 + k;
-        rb = i < HALF ? R::C + i : R::PC + (i - HALF);
-        poff = k * fin + (i < HALF ? i : C_row + i);
-        return;
+    if (e < H * (HALF + CP)) {
+        const int k = e / (HALF + CP), i = e % (HALF + CP);
+        return k * fin + (i < HALF ? i : C_row + i);
     }
-    o -= H * (HALF + CP);
-    int base = H * fin;
-    if (o < H) { ra = R::D1 + o; rb = R::ONE; poff = base + o; return; }
-    o -= H; base += H;
-    if (o < H * H) { ra = R::D2 + o / H; rb = R::H1 + o % H; poff = base + o; return; }
-    o -= H * H; base += H * H;
-    if (o < H) { ra = R::D2 + o; rb = R::ONE; poff = base + o; return; }
-    o -= H; base += H;
-    if (o < HALF * H) { ra = R::DO + o / H; rb = R::H2 + o % H; poff = base + o; return; }
-    o -= HALF * H; base += HALF * H;
-    ra = R::DO + o; rb = R::ONE; poff = base + o;
+    return e - H * (HALF + CP) + H * fin;   // b1, W2, b2, W3, b3 follow contiguously in both layouts
 }
 
 template <int HALF, int CP>
@@ -338,7 +302,7 @@ struct BwdSmem {
                     + (size_t)n_fcnn * H * C_row                                         // accR
                     + n_fcnn * H                                                         // d1row
                     + C_row + 4;                                                         // ctx
-        return fl * sizeof(float) + (size_t)R::NOUT * sizeof(int);                       // + table
+        return fl * sizeof(float);
     }
 };
 
@@ -348,7 +312,7 @@ template <int HALF, int CP, bool INV>
 __device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s, int f_t,
                                           bool live, const float (&c)[HALF], float (&gc)[HALF], const float* pc, float* gpc,
                                           float (&v)[HALF], float (&gv)[HALF], float gld, float* s_tile, float* s_acc,
-                                          float* s_d1row, const int* s_tab) {
+                                          float* s_d1row) {
     using R = Rows<HALF, CP>;
     const int tid = threadIdx.x;
     float h1t[H], h2t[H], h1s[H], h2s[H], t[HALF], s[HALF], dt[HALF], ds[HALF];
@@ -394,7 +358,6 @@ __device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s
         const int f = f_t + net;
         // b1 slots (first after the W1 block) double as the per-trajectory layer-1 delta sums (row-context hoist)
         stage_weight_grads_mma<HALF, CP>(s_tile, s_acc + f * R::NOUT, s_d1row + f * H);
-        (void)s_tab;
         __syncthreads();
     }
 }

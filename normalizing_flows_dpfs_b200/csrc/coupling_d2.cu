@@ -12,7 +12,7 @@
 namespace nfdpf {
 
 using L2_ = Lay<1, 0>;
-constexpr int NACC = 97;          // == Rows<1,0>::NOUT, same ordering as out_entry<1,0>
+constexpr int NACC = 97;          // == Rows<1,0>::NOUT, same ordering as packed_offset<1,0>
 constexpr int TPD = 256;          // threads per CTA (8 warps walking the same code: one CTA per SM, instruction-cache friendly)
 constexpr int CHUNK_M = 4;        // particles per thread per chunk (chunk = 1024 particles)
 constexpr int CHUNK = CHUNK_M * TPD;
@@ -198,9 +198,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
     }
     float* out = partials + (size_t)blockIdx.x * n_fcnn * pf;
     for (int e = tid; e < n_fcnn * NACC; e += TPD) {
-        int ra, rb, poff;
-        out_entry<1, 0>(e % NACC, C_row, ra, rb, poff);
-        out[(size_t)(e / NACC) * pf + poff] = s_acc[e];
+        out[(size_t)(e / NACC) * pf + packed_offset<1, 0>(e % NACC, C_row)] = s_acc[e];
     }
     const int fin = 1 + C_row;
     for (int e = tid; e < n_fcnn * H * C_row; e += TPD)   // row-context columns are produced by rowctx_grad_kernel

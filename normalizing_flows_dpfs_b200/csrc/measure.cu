@@ -241,12 +241,11 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     float* s_enc = s_pe + PE_SIZE;
     float* s_img = s_enc + 36;
     float* s_hb = s_img + n_fcnn * LC::SIZE;
-    float* s_tile = s_hb + n_fcnn * H;                       // PE tile [PR::COUNT][TSM]; the CNF tile [RC::COUNT][TS] aliases it
+    float* s_tile = s_hb + n_fcnn * H;                       // PE tile [PR::COUNT][TSM]; the CNF tile [RC::TROWS][TSM] aliases it
     float* s_accpe = s_tile + TILE_FLOATS;                   // [1648]
     float* s_acccnf = s_accpe + PE_SIZE;                     // [n_fcnn][RC::NOUT]
     float* s_d1row = s_acccnf + n_fcnn * RC::NOUT;           // [n_fcnn][8] (unused sums; C_row = 0)
     float* s_denc = s_d1row + n_fcnn * H + 4;                // [32]
-    int* s_tabcnf = reinterpret_cast<int*>(s_denc + 32);     // [RC::NOUT]
     for (int e = tid; e < PE_SIZE; e += TP) {
         s_pe[e] = pe[e];
         s_accpe[e] = 0.f;
@@ -254,11 +253,6 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     if (MODE == MODE_CNF) {
         const int pf = packed_fcnn_size(16, 32);
         for (int f = 0; f < n_fcnn; ++f) load_fcnn_image<16, 32>(cnf + (size_t)f * pf, 0, s_img + f * LC::SIZE, nullptr, tid, TP);
-        for (int e = tid; e < RC::NOUT; e += TP) {
-            int ra, rb, poff;
-            out_entry<16, 32>(e, 0, ra, rb, poff);
-            s_tabcnf[e] = ra | (rb << 16);
-        }
         for (int e = tid; e < n_fcnn * RC::NOUT; e += TP) s_acccnf[e] = 0.f;
         for (int e = tid; e < n_fcnn * H; e += TP) s_d1row[e] = 0.f;
     }
@@ -347,9 +341,9 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                     const float* im = s_img + 4 * f * LC::SIZE;
                     const float* hb = s_hb + 4 * f * H;
                     stage_bwd<16, 32, false>(im + 2 * LC::SIZE, im + 3 * LC::SIZE, hb + 2 * H, hb + 3 * H, 4 * f + 2, live, up, gup, e, de,
-                                             lo, glo, g, s_tile, s_acccnf, s_d1row, s_tabcnf);
+                                             lo, glo, g, s_tile, s_acccnf, s_d1row);
                     stage_bwd<16, 32, false>(im, im + LC::SIZE, hb, hb + H, 4 * f, live, lo, glo, e, de, up, gup, g, s_tile, s_acccnf,
-                                             s_d1row, s_tabcnf);
+                                             s_d1row);
                 }
                 if (live) {
 #pragma unroll
@@ -428,9 +422,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         const int pf = packed_fcnn_size(16, 32);
         float* out = part_cnf + (size_t)blockIdx.x * n_fcnn * pf;
         for (int e = tid; e < n_fcnn * RC::NOUT; e += TP) {
-            int ra, rb, poff;
-            out_entry<16, 32>(e % RC::NOUT, 0, ra, rb, poff);
-            out[(size_t)(e / RC::NOUT) * pf + poff] = s_acccnf[e];
+            out[(size_t)(e / RC::NOUT) * pf + packed_offset<16, 32>(e % RC::NOUT, 0)] = s_acccnf[e];
         }
     }
 }
@@ -443,7 +435,7 @@ static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
     const size_t tile = (size_t)(mode == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT) * TSM;
     size_t fl = (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + tile + PE_SIZE + (size_t)n_fcnn * RC::NOUT + n_fcnn * H + 4 + 32;
-    return fl * sizeof(float) + (size_t)(mode == MODE_CNF ? RC::NOUT : 0) * sizeof(int);
+    return fl * sizeof(float);
 }
 
 template <int MODE>
