@@ -193,7 +193,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
         }
         // per-trajectory layer-1 delta sums: the row-context columns of dW1 and d(row_ctx) are formed from them by
         // rowctx_grad_kernel after this kernel (keeps the 8 x C_row outer products out of the persistent loop)
-        for (int e = tid; e < n_fcnn * H; e += TPD) d1rows[(size_t)b * n_fcnn * H + e] = s_d1row[e];
+        for (int e = tid; e < n_fcnn * H; e += TPD) d1rows[(size_t)e * B + b] = s_d1row[e];   // [f*8+k][b]: coalesced for rowctx_grad
         __syncthreads();
     }
     float* out = partials + (size_t)blockIdx.x * n_fcnn * pf;
@@ -214,7 +214,7 @@ __global__ void rowctx_grad_kernel(const float* __restrict__ packed, const float
     if (warp < n_w) {
         const int fk = warp / C_row, c = warp % C_row;
         double a = 0.0;
-        for (int b = lane; b < B; b += 32) a += (double)d1rows[(size_t)b * n_fcnn * H + fk] * (double)row_ctx[(size_t)b * C_row + c];
+        for (int b = lane; b < B; b += 32) a += (double)d1rows[(size_t)fk * B + b] * (double)row_ctx[(size_t)b * C_row + c];
         a = warp_sum(a);
         if (lane == 0) d_packed[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + c] += (float)a;
     } else if (d_row_ctx) {
@@ -223,7 +223,7 @@ __global__ void rowctx_grad_kernel(const float* __restrict__ packed, const float
         const int b = e / C_row, c = e % C_row;
         float a = 0.f;
         for (int fk = lane; fk < n_fcnn * H; fk += 32)
-            a = fmaf(packed[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + c], d1rows[(size_t)b * n_fcnn * H + fk], a);
+            a = fmaf(packed[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + c], d1rows[(size_t)fk * B + b], a);
         a = warp_sum(a);
         if (lane == 0) d_row_ctx[(size_t)b * C_row + c] = a;
     }
