@@ -10,7 +10,7 @@ constexpr int MAX_FCNN = 16;      // n_flows <= 4
 // ------------------------------------------------------------------------------------------------- forward
 constexpr int TPF = 256;          // forward: 8 warps per CTA (no tile, 50-80 registers): more resident warps to cover MUFU / LDS latency
 
-template <int HALF, int CP>
+template <int HALF, int CP, bool INVERSE>
 __global__ void __launch_bounds__(TPF)
 coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ x,
                     const float* __restrict__ row_ctx, const float* __restrict__ part_ctx, int flags, int N, int chunk,
@@ -29,7 +29,7 @@ coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     __syncthreads();
     hoist_row_context<HALF, CP>(s_img, s_w1r, row_ctx + (size_t)b * C_row, C_row, n_fcnn, s_hb, tid, TPF);
     __syncthreads();
-    const int inverse = flags & 1;  // bit 1: emit jac = -log_det instead of log_det
+    constexpr int inverse = INVERSE ? 1 : 0;  // flags bit 0 (compile-time here); bit 1: emit jac = -log_det instead of log_det
     const int n0 = blockIdx.x * chunk, n1 = min(N, n0 + chunk);
     for (int n = n0 + tid; n < n1; n += TPF) {
         const size_t p = (size_t)b * N + n;
@@ -38,23 +38,20 @@ coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
         for (int i = 0; i < HALF; ++i) { lo[i] = x[p * D + i]; up[i] = x[p * D + HALF + i]; }
 #pragma unroll
         for (int i = 0; i < CP; ++i) pc[i] = part_ctx[p * CP + i];
-        if (!inverse) {
+        // stage order: forward = flows 0..n-1, (t1,s1 | c = lower) then (t2,s2 | c = upper); inverse = the reverse walk.
+        // A = conditioning half, Bv = transformed half; they swap after every stage (one inlined stage body).
+        if (inverse) swap_halves<HALF>(lo, up);          // inverse starts with pair 1: c = upper
 #pragma unroll 1
-            for (int f = 0; f < n_flows; ++f) {
-                const float* im = s_img + 4 * f * L::SIZE;
-                const float* hb = s_hb + 4 * f * H;
-                stage_fwd<HALF, CP, false>(im, im + L::SIZE, hb, hb + H, lo, pc, up, ld);                          // t1,s1
-                stage_fwd<HALF, CP, false>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, up, pc, lo, ld);  // t2,s2
-            }
-        } else {
-#pragma unroll 1
-            for (int f = n_flows - 1; f >= 0; --f) {
-                const float* im = s_img + 4 * f * L::SIZE;
-                const float* hb = s_hb + 4 * f * H;
-                stage_fwd<HALF, CP, true>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, up, pc, lo, ld);
-                stage_fwd<HALF, CP, true>(im, im + L::SIZE, hb, hb + H, lo, pc, up, ld);
-            }
+        for (int st = 0; st < 2 * n_flows; ++st) {
+            const int f = inverse ? n_flows - 1 - st / 2 : st / 2;
+            const int pair = inverse ? 1 - (st & 1) : (st & 1);
+            const float* im = s_img + (4 * f + 2 * pair) * L::SIZE;
+            const float* hb = s_hb + (4 * f + 2 * pair) * H;
+            stage_fwd<HALF, CP>(im, im + L::SIZE, hb, hb + H, inverse != 0, lo, pc, up, ld);   // (c, v) = (lo, up) slots
+            swap_halves<HALF>(lo, up);
         }
+        // an even number of swaps leaves the slots in place for the forward walk; the inverse walk did one extra swap up front
+        if (inverse) swap_halves<HALF>(lo, up);
 #pragma unroll
         for (int i = 0; i < HALF; ++i) { y[p * D + i] = lo[i]; y[p * D + HALF + i] = up[i]; }
         log_det[p] = (flags & 2) ? -ld : ld;
@@ -110,27 +107,22 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
             const float gld = live && g_ld ? ((flags & 2) ? -g_ld[p] : g_ld[p]) : 0.f;
 #pragma unroll
             for (int i = 0; i < CP; ++i) { pc[i] = part_ctx[p * CP + i]; gpc[i] = 0.f; s_tile[(R::PC + i) * TSM + tid] = pc[i]; }
-            if (!inverse) {  // forward pass ran flows 0..n-1 (t1/s1 then t2/s2): walk back n-1..0 (t2/s2 then t1/s1)
+            // forward pass ran flows 0..n-1 (t1/s1 then t2/s2): walk back n-1..0 (t2/s2 then t1/s1);
+            // inverse pass ran flows n-1..0 (t2/s2 then t1/s1): walk back 0..n-1 (t1/s1 then t2/s2).
+            // (lo, glo) / (up, gup) are the (c, v) slots of the single stage body and swap after every stage.
+            if (!inverse) { swap_halves<HALF>(lo, up); swap_halves<HALF>(glo, gup); }   // first stage has c = upper
 #pragma unroll 1
-                for (int f = n_flows - 1; f >= 0; --f) {
-                    const float* im = s_img + 4 * f * L::SIZE;
-                    const float* hb = s_hb + 4 * f * H;
-                    stage_bwd<HALF, CP, false>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, 4 * f + 2, live, up, gup,
-                                               pc, gpc, lo, glo, gld, s_tile, s_acc, s_d1row);
-                    stage_bwd<HALF, CP, false>(im, im + L::SIZE, hb, hb + H, 4 * f, live, lo, glo, pc, gpc, up, gup, gld, s_tile,
-                                               s_acc, s_d1row);
-                }
-            } else {         // inverse pass ran flows n-1..0 (t2/s2 then t1/s1): walk back 0..n-1 (t1/s1 then t2/s2)
-#pragma unroll 1
-                for (int f = 0; f < n_flows; ++f) {
-                    const float* im = s_img + 4 * f * L::SIZE;
-                    const float* hb = s_hb + 4 * f * H;
-                    stage_bwd<HALF, CP, true>(im, im + L::SIZE, hb, hb + H, 4 * f, live, lo, glo, pc, gpc, up, gup, gld, s_tile,
-                                              s_acc, s_d1row);
-                    stage_bwd<HALF, CP, true>(im + 2 * L::SIZE, im + 3 * L::SIZE, hb + 2 * H, hb + 3 * H, 4 * f + 2, live, up, gup,
-                                              pc, gpc, lo, glo, gld, s_tile, s_acc, s_d1row);
-                }
+            for (int st = 0; st < 2 * n_flows; ++st) {
+                const int f = inverse ? st / 2 : n_flows - 1 - st / 2;
+                const int pair = inverse ? (st & 1) : 1 - (st & 1);
+                const float* im = s_img + (4 * f + 2 * pair) * L::SIZE;
+                const float* hb = s_hb + (4 * f + 2 * pair) * H;
+                stage_bwd<HALF, CP>(im, im + L::SIZE, hb, hb + H, 4 * f + 2 * pair, inverse != 0, live, lo, glo, pc, gpc, up, gup, gld,
+                                    s_tile, s_acc, s_d1row);
+                swap_halves<HALF>(lo, up);
+                swap_halves<HALF>(glo, gup);
             }
+            if (!inverse) { swap_halves<HALF>(lo, up); swap_halves<HALF>(glo, gup); }
             if (live) {
 #pragma unroll
                 for (int i = 0; i < HALF; ++i) { d_x[p * D + i] = glo[i]; d_x[p * D + HALF + i] = gup[i]; }
@@ -186,7 +178,7 @@ static int launch_fwd(const float* packed, int n_flows, int C_row, const float* 
     using L = Lay<HALF, CP>;
     const int n_fcnn = 4 * n_flows;
     const size_t smem = ((size_t)n_fcnn * L::SIZE + n_fcnn * H + (size_t)n_fcnn * H * C_row) * sizeof(float);
-    auto kern = coupling_fwd_kernel<HALF, CP>;
+    auto kern = (inverse & 1) ? coupling_fwd_kernel<HALF, CP, true> : coupling_fwd_kernel<HALF, CP, false>;
     if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // enough CTAs to fill the GPU even when B is small: split rows into chunks of >= TP particles
     int chunks = 1;

@@ -198,18 +198,25 @@ __device__ void hoist_row_context_par(const float* __restrict__ imgs, const floa
     }
 }
 
-// One coupling stage, forward evaluation.  INV=false: v = t(c) + v*exp(s(c)); INV=true: v = (v - t(c))*exp(-s(c)).
-template <int HALF, int CP, bool INV>
-__device__ __forceinline__ void stage_fwd(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s,
+// One coupling stage, forward evaluation.  inv = false: v = t(c) + v*exp(s(c)); inv = true: v = (v - t(c))*exp(-s(c)).
+template <int HALF, int CP>
+__device__ __forceinline__ void stage_fwd(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s, bool inv,
                                           const float (&c)[HALF], const float* pc, float (&v)[HALF], float& ld) {
     float h1[H], h2[H], t[HALF], s[HALF];
     fcnn_fwd<HALF, CP>(img_t, hb_t, c, pc, h1, h2, t);
     fcnn_fwd<HALF, CP>(img_s, hb_s, c, pc, h1, h2, s);
 #pragma unroll
     for (int i = 0; i < HALF; ++i) {
-        if (!INV) { v[i] = fmaf(v[i], expf(s[i]), t[i]); ld += s[i]; }
+        if (!inv) { v[i] = fmaf(v[i], expf(s[i]), t[i]); ld += s[i]; }
         else      { v[i] = (v[i] - t[i]) * expf(-s[i]); ld -= s[i]; }
     }
+}
+
+// Exchange the roles of the two halves between stages so that ONE inlined copy of the stage code serves every stage.
+template <int HALF>
+__device__ __forceinline__ void swap_halves(float (&a)[HALF], float (&b)[HALF]) {
+#pragma unroll
+    for (int i = 0; i < HALF; ++i) { const float t = a[i]; a[i] = b[i]; b[i] = t; }
 }
 
 
@@ -308,28 +315,28 @@ struct BwdSmem {
 
 // Backward of one stage for the particle held by this thread, plus the CTA-wide weight-gradient accumulation.
 // On entry (c, v) are the stage's OUTPUT values with gradients (gc, gv); on exit v / gv are the stage's input.
-template <int HALF, int CP, bool INV>
+template <int HALF, int CP>
 __device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s, int f_t,
-                                          bool live, const float (&c)[HALF], float (&gc)[HALF], const float* pc, float* gpc,
+                                          bool inv, bool live, const float (&c)[HALF], float (&gc)[HALF], const float* pc, float* gpc,
                                           float (&v)[HALF], float (&gv)[HALF], float gld, float* s_tile, float* s_acc,
                                           float* s_d1row) {
     using R = Rows<HALF, CP>;
+    using L = Lay<HALF, CP>;
     const int tid = threadIdx.x;
     float h1t[H], h2t[H], h1s[H], h2s[H], t[HALF], s[HALF], dt[HALF], ds[HALF];
     fcnn_fwd<HALF, CP>(img_t, hb_t, c, pc, h1t, h2t, t);
     fcnn_fwd<HALF, CP>(img_s, hb_s, c, pc, h1s, h2s, s);
 #pragma unroll
     for (int i = 0; i < HALF; ++i) {
-        if (!INV) {  // out = t + in*e^s
-            const float es = expf(s[i]);
-            const float vin = (v[i] - t[i]) * expf(-s[i]);
+        const float es = expf(s[i]), ies = expf(-s[i]);
+        if (!inv) {  // out = t + in*e^s
+            const float vin = (v[i] - t[i]) * ies;
             dt[i] = gv[i];
             ds[i] = fmaf(gv[i] * vin, es, gld);
             gv[i] = gv[i] * es;
             v[i] = vin;
         } else {     // out = (in - t) e^{-s}
-            const float es = expf(s[i]);
-            const float gin = gv[i] * expf(-s[i]);
+            const float gin = gv[i] * ies;
             dt[i] = -gin;
             ds[i] = -fmaf(gv[i], v[i], gld);
             v[i] = fmaf(v[i], es, t[i]);
@@ -340,26 +347,32 @@ __device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s
     // conditioning half is shared by both nets of the stage: stage it once
 #pragma unroll
     for (int i = 0; i < HALF; ++i) s_tile[(R::C + i) * TSM + tid] = c[i];
-#pragma unroll
+    // the two nets share ONE copy of the backward code (rolled loop, operands selected): for the wide D = 32 stack the
+    // unrolled version is > 18 k SASS instructions and the kernel stalls on instruction fetch
+#pragma unroll 1
     for (int net = 0; net < 2; ++net) {
-        float d1[H], d2[H];
-        if (net == 0) fcnn_bwd<HALF, CP>(img_t, dt, h1t, h2t, d1, d2, gc, gpc);
-        else          fcnn_bwd<HALF, CP>(img_s, ds, h1s, h2s, d1, d2, gc, gpc);
+        float d1[H], d2[H], ha[H], hb2[H], dout[HALF];
+#pragma unroll
+        for (int k = 0; k < H; ++k) { ha[k] = net ? h1s[k] : h1t[k]; hb2[k] = net ? h2s[k] : h2t[k]; }
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) dout[i] = net ? ds[i] : dt[i];
+        fcnn_bwd<HALF, CP>(net ? img_s : img_t, dout, ha, hb2, d1, d2, gc, gpc);
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-            s_tile[(R::H1 + k) * TSM + tid] = net == 0 ? h1t[k] : h1s[k];
-            s_tile[(R::H2 + k) * TSM + tid] = net == 0 ? h2t[k] : h2s[k];
+            s_tile[(R::H1 + k) * TSM + tid] = ha[k];
+            s_tile[(R::H2 + k) * TSM + tid] = hb2[k];
             s_tile[(R::D1 + k) * TSM + tid] = d1[k];
             s_tile[(R::D2 + k) * TSM + tid] = d2[k];
         }
 #pragma unroll
-        for (int i = 0; i < HALF; ++i) s_tile[(R::DO + i) * TSM + tid] = net == 0 ? dt[i] : ds[i];
+        for (int i = 0; i < HALF; ++i) s_tile[(R::DO + i) * TSM + tid] = dout[i];
         __syncthreads();
         const int f = f_t + net;
         // b1 slots (first after the W1 block) double as the per-trajectory layer-1 delta sums (row-context hoist)
         stage_weight_grads_mma<HALF, CP>(s_tile, s_acc + f * R::NOUT, s_d1row + f * H);
         __syncthreads();
     }
+    (void)sizeof(L);
 }
 
 

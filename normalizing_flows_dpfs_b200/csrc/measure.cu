@@ -79,11 +79,11 @@ __device__ __forceinline__ float loglik(const float (&e)[32], const float* __res
 #pragma unroll
         for (int i = 0; i < 16; ++i) { lo[i] = s_enc[i]; up[i] = s_enc[16 + i]; }
 #pragma unroll 1
-        for (int f = 0; f < n_flows; ++f) {
-            const float* im = s_img + 4 * f * LC::SIZE;
-            const float* hb = s_hb + 4 * f * H;
-            stage_fwd<16, 32, false>(im, im + LC::SIZE, hb, hb + H, lo, e, up, ld);
-            stage_fwd<16, 32, false>(im + 2 * LC::SIZE, im + 3 * LC::SIZE, hb + 2 * H, hb + 3 * H, up, e, lo, ld);
+        for (int st = 0; st < 2 * n_flows; ++st) {        // one inlined stage body; the halves swap roles after every stage
+            const float* im = s_img + 2 * st * LC::SIZE;
+            const float* hb = s_hb + 2 * st * H;
+            stage_fwd<16, 32>(im, im + LC::SIZE, hb, hb + H, false, lo, e, up, ld);
+            swap_halves<16>(lo, up);
         }
         float m = 0.f;
 #pragma unroll
@@ -336,15 +336,16 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                 for (int k = 0; k < 32; ++k) { de[k] = 0.f; s_tile[(RC::PC + k) * TSM + tid] = e[k]; }
                 s_tile[RC::ONE * TSM + tid] = 1.0f;
                 for (int r = RC::COUNT; r < RC::TROWS; ++r) s_tile[r * TSM + tid] = 0.0f;   // (the PE tile aliases these rows)
+                swap_halves<16>(lo, up); swap_halves<16>(glo, gup);     // the last forward stage had c = upper
 #pragma unroll 1
-                for (int f = n_flows - 1; f >= 0; --f) {
-                    const float* im = s_img + 4 * f * LC::SIZE;
-                    const float* hb = s_hb + 4 * f * H;
-                    stage_bwd<16, 32, false>(im + 2 * LC::SIZE, im + 3 * LC::SIZE, hb + 2 * H, hb + 3 * H, 4 * f + 2, live, up, gup, e, de,
-                                             lo, glo, g, s_tile, s_acccnf, s_d1row);
-                    stage_bwd<16, 32, false>(im, im + LC::SIZE, hb, hb + H, 4 * f, live, lo, glo, e, de, up, gup, g, s_tile, s_acccnf,
-                                             s_d1row);
+                for (int st = 2 * n_flows - 1; st >= 0; --st) {         // walk the forward stages back; one inlined stage body
+                    const float* im = s_img + 2 * st * LC::SIZE;
+                    const float* hb = s_hb + 2 * st * H;
+                    stage_bwd<16, 32>(im, im + LC::SIZE, hb, hb + H, 2 * st, false, live, lo, glo, e, de, up, gup, g, s_tile, s_acccnf,
+                                      s_d1row);
+                    swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
                 }
+                swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
                 if (live) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { denc[i] += glo[i]; denc[16 + i] += gup[i]; }
