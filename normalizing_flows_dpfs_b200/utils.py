@@ -60,22 +60,29 @@ def particle_initialization(start_state, width, num_particles, state_dim=2, init
     return particles, log_w
 
 
+def _set_trainable(model, flag):
+    for tensor in model.parameters():
+        tensor.requires_grad = flag
+
+
 def freeze_model(model):
-    for p in model.parameters():
-        p.requires_grad = False
+    _set_trainable(model, False)
 
 
 def unfreeze_model(model):
-    for p in model.parameters():
-        p.requires_grad = True
+    _set_trainable(model, True)
+
+
+_CKPT_PARTS = (("model", lambda m: m), ("model_optim", lambda m: m.optim), ("model_optim_scheduler", lambda m: m.optim_scheduler))
 
 
 def checkpoint_state(model, epoch):
-    return {"model": model.state_dict(), "model_optim": model.optim.state_dict(),
-            "model_optim_scheduler": model.optim_scheduler.state_dict(), "epoch": epoch}
+    """{'model', 'model_optim', 'model_optim_scheduler', 'epoch'}: the checkpoint layout of the reference (utils.py:72-79)."""
+    state = {key: pick(model).state_dict() for key, pick in _CKPT_PARTS}
+    state["epoch"] = epoch
+    return state
 
 
 def load_model(model, ckpt_e2e):
-    model.load_state_dict(ckpt_e2e["model"])
-    model.optim.load_state_dict(ckpt_e2e["model_optim"])
-    model.optim_scheduler.load_state_dict(ckpt_e2e["model_optim_scheduler"])
+    for key, pick in _CKPT_PARTS:
+        pick(model).load_state_dict(ckpt_e2e[key])
