@@ -73,14 +73,16 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     float* s_hb = s_img + n_fcnn * L::SIZE;
     float* s_w1r = s_hb + n_fcnn * H;
     float* s_tile = s_w1r + (size_t)n_fcnn * H * C_row;
-    float* s_acc = s_tile + R::TROWS * TSM;
-    float* s_accR = s_acc + n_fcnn * R::NOUT;
-    float* s_d1row = s_accR + (size_t)n_fcnn * H * C_row;
-    float* s_ctx = s_d1row + n_fcnn * H;
+    constexpr int NW = TP / 32;
+    const int warp = tid >> 5;
+    float* s_acc = s_tile + R::TROWS * TSM;                      // [NW][n_fcnn][NOUT]: one accumulator copy per warp
+    float* s_accR = s_acc + NW * n_fcnn * R::NOUT;
+    float* s_d1row = s_accR + (size_t)n_fcnn * H * C_row;        // [NW][n_fcnn][8]
+    float* s_ctx = s_d1row + NW * n_fcnn * H;
     const int pf = packed_fcnn_size(HALF, C_row + CP);
     for (int f = 0; f < n_fcnn; ++f)
         load_fcnn_image<HALF, CP>(packed + (size_t)f * pf, C_row, s_img + f * L::SIZE, s_w1r + (size_t)f * H * C_row, tid, TP);
-    for (int e = tid; e < n_fcnn * R::NOUT; e += TP) s_acc[e] = 0.f;
+    for (int e = tid; e < NW * n_fcnn * R::NOUT; e += TP) s_acc[e] = 0.f;
     for (int e = tid; e < n_fcnn * H * C_row; e += TP) s_accR[e] = 0.f;
     s_tile[R::ONE * TSM + tid] = 1.0f;
     for (int r = R::COUNT; r < R::TROWS; ++r) s_tile[r * TSM + tid] = 0.0f;   // padding rows of the dout tile + the ZERO row
@@ -88,7 +90,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         for (int e = tid; e < C_row; e += TP) s_ctx[e] = row_ctx[(size_t)b * C_row + e];
-        for (int e = tid; e < n_fcnn * H; e += TP) s_d1row[e] = 0.f;
+        for (int e = tid; e < NW * n_fcnn * H; e += TP) s_d1row[e] = 0.f;
         __syncthreads();
         hoist_row_context<HALF, CP>(s_img, s_w1r, s_ctx, C_row, n_fcnn, s_hb, tid, TP);
         __syncthreads();
@@ -118,7 +120,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
                 const float* im = s_img + (4 * f + 2 * pair) * L::SIZE;
                 const float* hb = s_hb + (4 * f + 2 * pair) * H;
                 stage_bwd<HALF, CP>(im, im + L::SIZE, hb, hb + H, 4 * f + 2 * pair, inverse != 0, live, lo, glo, pc, gpc, up, gup, gld,
-                                    s_tile, s_acc, s_d1row);
+                                    s_tile, s_acc + warp * n_fcnn * R::NOUT, s_d1row + warp * n_fcnn * H);
                 swap_halves<HALF>(lo, up);
                 swap_halves<HALF>(glo, gup);
             }
@@ -133,6 +135,13 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
             }
         }
         // row-context columns of W1 and the context gradient from this trajectory's layer-1 delta sums
+        __syncthreads();   // every warp's delta sums of this trajectory are complete
+        for (int e = tid; e < n_fcnn * H; e += TP) {   // fold the per-warp copies into copy 0 (fixed order)
+            float a = s_d1row[e];
+            for (int w = 1; w < NW; ++w) a += s_d1row[w * n_fcnn * H + e];
+            s_d1row[e] = a;
+        }
+        __syncthreads();
         for (int e = tid; e < n_fcnn * H * C_row; e += TP) s_accR[e] = fmaf(s_d1row[e / C_row], s_ctx[e % C_row], s_accR[e]);
         if (d_row_ctx)
             for (int cidx = tid; cidx < C_row; cidx += TP) {
@@ -146,7 +155,9 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     float* out = partials + (size_t)blockIdx.x * n_fcnn * pf;
     const int fin = HALF + C_row + CP;
     for (int e = tid; e < n_fcnn * R::NOUT; e += TP) {
-        out[(size_t)(e / R::NOUT) * pf + packed_offset<HALF, CP>(e % R::NOUT, C_row)] = s_acc[e];
+        float a = s_acc[e];
+        for (int w = 1; w < NW; ++w) a += s_acc[w * n_fcnn * R::NOUT + e];
+        out[(size_t)(e / R::NOUT) * pf + packed_offset<HALF, CP>(e % R::NOUT, C_row)] = a;
     }
     for (int e = tid; e < n_fcnn * H * C_row; e += TP) {
         const int fk = e / C_row, cidx = e % C_row;

@@ -237,53 +237,75 @@ struct Rows {
     static constexpr int NOUT = H * (HALF + CP) + H + H * H + H + HALF * H + HALF;
 };
 
-// Weight gradients of ONE FCNN for the CTA's batch on the tensor path (3xTF32 mma.sync, see mma_tile.cuh), added into
-// acc_f[NOUT] (packed order minus row-context columns) and, for the b1 block, into d1row_f (row-context hoist).
+// Weight gradients of ONE FCNN on the tensor path (3xTF32 mma.sync, see mma_tile.cuh).  Each warp contracts over the
+// 32 particles its own threads staged (no CTA barrier) and adds the result into ITS OWN accumulator copy acc_f[NOUT]
+// (packed order minus row-context columns) and, for the b1 block, d1row_f (row-context hoist); the copies are summed
+// in a fixed order when the CTA writes its partial gradient.
 //   A1 = [delta1 (8 rows); delta2 (8 rows)]   x  B tiles: inputs [c | pc] (NIN tiles), ONE, h1
 //        rows 0-7 x inputs -> dW1, rows 0-7 x ONE -> db1, rows 8-15 x ONE -> db2, rows 8-15 x h1 -> dW2
 //   A2 = [dout (HALF rows, padded)]            x  B tiles: h2 -> dW3, ONE -> db3
-// Tiles are dealt round-robin to the 4 warps; every accumulator entry has exactly one owner lane (no atomics).
+template <int HALF, int CP, int T0, int NTG>
+__device__ __forceinline__ void a1_tile_group(const float* __restrict__ s_tile, float* __restrict__ acc_f, float* __restrict__ d1row_f,
+                                              int k0) {
+    using R = Rows<HALF, CP>;
+    constexpr int IN = HALF + CP, NIN = (IN + 7) / 8;
+    constexpr int B1 = H * IN, W2 = B1 + H, B2 = W2 + H * H;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, col = 2 * t;
+    int rowB[NTG];
+#pragma unroll
+    for (int n = 0; n < NTG; ++n) {
+        const int ti = T0 + n;
+        rowB[n] = ti < NIN ? ((8 * ti + g < IN) ? R::C + 8 * ti + g : R::ZERO) : (ti == NIN ? (g == 0 ? R::ONE : R::ZERO) : R::H1 + g);
+    }
+    float c[NTG][4] = {};
+    mma_outer<NTG>(s_tile, R::D1, rowB, k0, k0 + 32, c);
+#pragma unroll
+    for (int n = 0; n < NTG; ++n) {
+        const int ti = T0 + n;
+        if (ti < NIN) {                                     // rows g (< 8): dW1[k = g][i]
+            const int i = 8 * ti + col;
+            if (i < IN) acc_f[g * IN + i] += c[n][0];
+            if (i + 1 < IN) acc_f[g * IN + i + 1] += c[n][1];
+        } else if (ti == NIN) {                             // ONE: col 0 -> db1 (rows 0-7), db2 (rows 8-15)
+            if (t == 0) {
+                acc_f[B1 + g] += c[n][0];
+                if (d1row_f) d1row_f[g] += c[n][0];
+                acc_f[B2 + g] += c[n][2];
+            }
+        } else {                                            // h1: rows 8-15 -> dW2[j = g][k]
+            acc_f[W2 + g * H + col] += c[n][2];
+            acc_f[W2 + g * H + col + 1] += c[n][3];
+        }
+    }
+}
+
+template <int HALF, int CP, int T0>
+__device__ __forceinline__ void a1_tiles(const float* __restrict__ s_tile, float* __restrict__ acc_f, float* __restrict__ d1row_f, int k0) {
+    constexpr int NT1 = (HALF + CP + 7) / 8 + 2;            // input tiles + ONE + h1
+    if constexpr (T0 < NT1) {
+        constexpr int NTG = NT1 - T0 < 4 ? NT1 - T0 : 4;    // at most four accumulator fragments live at a time
+        a1_tile_group<HALF, CP, T0, NTG>(s_tile, acc_f, d1row_f, k0);
+        a1_tiles<HALF, CP, T0 + NTG>(s_tile, acc_f, d1row_f, k0);
+    }
+}
+
 template <int HALF, int CP>
 __device__ __forceinline__ void stage_weight_grads_mma(const float* __restrict__ s_tile, float* __restrict__ acc_f,
                                                        float* __restrict__ d1row_f) {
     using R = Rows<HALF, CP>;
-    constexpr int IN = HALF + CP, NIN = (IN + 7) / 8, NT = NIN + 4;   // + ONE, h1 (on A1), h2, ONE (on A2)
-    constexpr int B1 = H * IN, W2 = B1 + H, B2 = W2 + H * H, W3 = B2 + H, B3 = W3 + HALF * H;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-#pragma unroll 1
-    for (int ti = warp; ti < NT; ti += TP / 32) {
-        const bool second = ti >= NIN + 2;                 // tiles on A2 = dout
-        int rowB;
-        if (ti < NIN) rowB = (8 * ti + g < IN) ? R::C + 8 * ti + g : R::ZERO;
-        else if (ti == NIN || ti == NIN + 3) rowB = g == 0 ? R::ONE : R::ZERO;
-        else if (ti == NIN + 1) rowB = R::H1 + g;
-        else rowB = R::H2 + g;
-        float c[1][4] = {};
-        const int rb[1] = {rowB};
-        mma_outer<1>(s_tile, second ? R::DO : R::D1, rb, TP, c);
-        const int col = 2 * t;
-        if (ti < NIN) {                                     // rows g (< 8): dW1[k = g][i]
-            const int i = 8 * ti + col;
-            if (i < IN) acc_f[g * IN + i] += c[0][0];
-            if (i + 1 < IN) acc_f[g * IN + i + 1] += c[0][1];
-        } else if (ti == NIN) {                             // ONE on A1: col 0 -> db1 (rows 0-7), db2 (rows 8-15)
-            if (t == 0) {
-                acc_f[B1 + g] += c[0][0];
-                if (d1row_f) d1row_f[g] += c[0][0];
-                acc_f[B2 + g] += c[0][2];
-            }
-        } else if (ti == NIN + 1) {                         // h1 on A1: rows 8-15 -> dW2[j = g][k]
-            acc_f[W2 + g * H + col] += c[0][2];
-            acc_f[W2 + g * H + col + 1] += c[0][3];
-        } else if (ti == NIN + 2) {                         // h2 on A2: dW3[o][j], o = g and g + 8
-            if (g < HALF) { acc_f[W3 + g * H + col] += c[0][0]; acc_f[W3 + g * H + col + 1] += c[0][1]; }
-            if (g + 8 < HALF) { acc_f[W3 + (g + 8) * H + col] += c[0][2]; acc_f[W3 + (g + 8) * H + col + 1] += c[0][3]; }
-        } else {                                            // ONE on A2: db3[o]
-            if (t == 0) {
-                if (g < HALF) acc_f[B3 + g] += c[0][0];
-                if (g + 8 < HALF) acc_f[B3 + g + 8] += c[0][2];
-            }
-        }
+    constexpr int IN = HALF + CP;
+    constexpr int W3 = H * IN + H + H * H + H, B3 = W3 + HALF * H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3, col = 2 * t;
+    const int k0 = 32 * warp;
+    a1_tiles<HALF, CP, 0>(s_tile, acc_f, d1row_f, k0);
+    float c[2][4] = {};
+    const int rowB[2] = {R::H2 + g, g == 0 ? R::ONE : R::ZERO};
+    mma_outer<2>(s_tile, R::DO, rowB, k0, k0 + 32, c);
+    if (g < HALF) { acc_f[W3 + g * H + col] += c[0][0]; acc_f[W3 + g * H + col + 1] += c[0][1]; }                       // dW3[o][j]
+    if (g + 8 < HALF) { acc_f[W3 + (g + 8) * H + col] += c[0][2]; acc_f[W3 + (g + 8) * H + col + 1] += c[0][3]; }
+    if (t == 0) {                                                                                                         // db3[o]
+        if (g < HALF) acc_f[B3 + g] += c[1][0];
+        if (g + 8 < HALF) acc_f[B3 + g + 8] += c[1][2];
     }
 }
 
@@ -305,9 +327,9 @@ struct BwdSmem {
     static size_t bytes(int n_fcnn, int C_row) {
         size_t fl = (size_t)n_fcnn * L::SIZE + n_fcnn * H + (size_t)n_fcnn * H * C_row  // images, hb, w1r
                     + (size_t)R::TROWS * TSM                                             // tile
-                    + (size_t)n_fcnn * R::NOUT                                           // acc
+                    + (size_t)(TP / 32) * n_fcnn * R::NOUT                               // acc (one copy per warp)
                     + (size_t)n_fcnn * H * C_row                                         // accR
-                    + n_fcnn * H                                                         // d1row
+                    + (TP / 32) * n_fcnn * H                                             // d1row (one copy per warp)
                     + C_row + 4;                                                         // ctx
         return fl * sizeof(float);
     }
@@ -366,11 +388,11 @@ __device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s
         }
 #pragma unroll
         for (int i = 0; i < HALF; ++i) s_tile[(R::DO + i) * TSM + tid] = dout[i];
-        __syncthreads();
+        __syncwarp();   // the warp contracts over its own 32 columns only: no CTA barrier in the gradient phase
         const int f = f_t + net;
         // b1 slots (first after the W1 block) double as the per-trajectory layer-1 delta sums (row-context hoist)
         stage_weight_grads_mma<HALF, CP>(s_tile, s_acc + f * R::NOUT, s_d1row + f * H);
-        __syncthreads();
+        __syncwarp();
     }
     (void)sizeof(L);
 }

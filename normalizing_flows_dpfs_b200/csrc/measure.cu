@@ -182,48 +182,51 @@ struct PR {
     static constexpr int ONE = 0, ZERO = 1, X = 2, A1 = 4, A2 = 20, D1 = 52, D2 = 68, D3 = 100, COUNT = 132;
 };
 
-// Particle-encoder weight gradients of one batch on the tensor path (3xTF32), added into s_accpe (packed PE order).
-//   warps 0,1: dW3 | db3 = delta3(16 rows each) x [a2 (4 n-tiles) | 1]
-//   warps 2,3: dW2 | db2 = delta2(16 rows each) x [a1 (2 n-tiles) | 1];  warp 2 also dW1 | db1 = delta1 x [x0 x1 1]
-__device__ __forceinline__ void pe_weight_grads_mma(const float* __restrict__ s_tile, float* __restrict__ s_accpe,
+// Particle-encoder weight gradients on the tensor path (3xTF32): every warp contracts over the 32 particles its own
+// threads staged and adds into ITS OWN accumulator copy accpe[PE_SIZE] (packed PE order) -- no CTA barrier.
+//   dW3 | db3 = delta3 (2 m-tiles) x [a2 (4 n-tiles) | 1];  dW2 | db2 = delta2 (2 m-tiles) x [a1 (2 n-tiles) | 1];
+//   dW1 | db1 = delta1 x [x0 x1 1].   rowsum3 (may be null): per-trajectory sum of delta3 (Gaussian mode: = -d enc).
+__device__ __forceinline__ void pe_weight_grads_mma(const float* __restrict__ s_tile, float* __restrict__ accpe,
                                                     float* __restrict__ rowsum3) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    if (warp < 2) {
+    const int k0 = 32 * warp;
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
         float c[5][4] = {};
         const int rowB[5] = {PR::A2 + g, PR::A2 + 8 + g, PR::A2 + 16 + g, PR::A2 + 24 + g, g == 0 ? PR::ONE : PR::ZERO};
-        mma_outer<5>(s_tile, PR::D3 + 16 * warp, rowB, TP, c);
-        const int o = 16 * warp + g;
+        mma_outer<5>(s_tile, PR::D3 + 16 * mt, rowB, k0, k0 + 32, c);
+        const int o = 16 * mt + g;
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
-            float* w = s_accpe + PE_W3 + o * 32 + 8 * n + 2 * t;
+            float* w = accpe + PE_W3 + o * 32 + 8 * n + 2 * t;
             w[0] += c[n][0]; w[1] += c[n][1]; w[8 * 32] += c[n][2]; w[8 * 32 + 1] += c[n][3];
         }
         if (t == 0) {
-            s_accpe[PE_B3 + o] += c[4][0]; s_accpe[PE_B3 + o + 8] += c[4][2];
-            if (rowsum3) { rowsum3[o] += c[4][0]; rowsum3[o + 8] += c[4][2]; }   // per-trajectory sum of delta3 (Gaussian: = -d enc)
+            accpe[PE_B3 + o] += c[4][0]; accpe[PE_B3 + o + 8] += c[4][2];
+            if (rowsum3) { rowsum3[o] += c[4][0]; rowsum3[o + 8] += c[4][2]; }
         }
-    } else {
+    }
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
         float c[3][4] = {};
         const int rowB[3] = {PR::A1 + g, PR::A1 + 8 + g, g == 0 ? PR::ONE : PR::ZERO};
-        mma_outer<3>(s_tile, PR::D2 + 16 * (warp - 2), rowB, TP, c);
-        const int o = 16 * (warp - 2) + g;
+        mma_outer<3>(s_tile, PR::D2 + 16 * mt, rowB, k0, k0 + 32, c);
+        const int o = 16 * mt + g;
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
-            float* w = s_accpe + PE_W2 + o * 16 + 8 * n + 2 * t;
+            float* w = accpe + PE_W2 + o * 16 + 8 * n + 2 * t;
             w[0] += c[n][0]; w[1] += c[n][1]; w[8 * 16] += c[n][2]; w[8 * 16 + 1] += c[n][3];
         }
-        if (t == 0) { s_accpe[PE_B2 + o] += c[2][0]; s_accpe[PE_B2 + o + 8] += c[2][2]; }
-        if (warp == 2) {
-            float c1[1][4] = {};
-            const int rowX[1] = {g < 2 ? PR::X + g : (g == 2 ? PR::ONE : PR::ZERO)};
-            mma_outer<1>(s_tile, PR::D1, rowX, TP, c1);
-            if (t == 0) {   // columns 0,1 = dW1[o][0..1]
-                s_accpe[PE_W1 + 2 * g] += c1[0][0]; s_accpe[PE_W1 + 2 * g + 1] += c1[0][1];
-                s_accpe[PE_W1 + 2 * (g + 8)] += c1[0][2]; s_accpe[PE_W1 + 2 * (g + 8) + 1] += c1[0][3];
-            } else if (t == 1) {  // column 2 = db1[o]
-                s_accpe[PE_B1 + g] += c1[0][0]; s_accpe[PE_B1 + g + 8] += c1[0][2];
-            }
-        }
+        if (t == 0) { accpe[PE_B2 + o] += c[2][0]; accpe[PE_B2 + o + 8] += c[2][2]; }
+    }
+    float c1[1][4] = {};
+    const int rowX[1] = {g < 2 ? PR::X + g : (g == 2 ? PR::ONE : PR::ZERO)};
+    mma_outer<1>(s_tile, PR::D1, rowX, k0, k0 + 32, c1);
+    if (t == 0) {          // columns 0,1 = dW1[o][0..1]
+        accpe[PE_W1 + 2 * g] += c1[0][0]; accpe[PE_W1 + 2 * g + 1] += c1[0][1];
+        accpe[PE_W1 + 2 * (g + 8)] += c1[0][2]; accpe[PE_W1 + 2 * (g + 8) + 1] += c1[0][3];
+    } else if (t == 1) {   // column 2 = db1[o]
+        accpe[PE_B1 + g] += c1[0][0]; accpe[PE_B1 + g + 8] += c1[0][2];
     }
 }
 
@@ -242,19 +245,21 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     float* s_img = s_enc + 36;
     float* s_hb = s_img + n_fcnn * LC::SIZE;
     float* s_tile = s_hb + n_fcnn * H;                       // PE tile [PR::COUNT][TSM]; the CNF tile [RC::TROWS][TSM] aliases it
-    float* s_accpe = s_tile + TILE_FLOATS;                   // [1648]
-    float* s_acccnf = s_accpe + PE_SIZE;                     // [n_fcnn][RC::NOUT]
-    float* s_d1row = s_acccnf + n_fcnn * RC::NOUT;           // [n_fcnn][8] (unused sums; C_row = 0)
-    float* s_denc = s_d1row + n_fcnn * H + 4;                // [32]
+    constexpr int NW = TP / 32;
+    const int warp = tid >> 5;
+    float* s_accpe = s_tile + TILE_FLOATS;                   // [NW][1648]   one accumulator copy per warp
+    float* s_acccnf = s_accpe + NW * PE_SIZE;                // [NW][n_fcnn][RC::NOUT]
+    float* s_d1row = s_acccnf + NW * n_fcnn * RC::NOUT;      // [NW][n_fcnn][8] (unused sums; C_row = 0)
+    float* s_denc = s_d1row + NW * n_fcnn * H + 4;           // [NW][32]
     for (int e = tid; e < PE_SIZE; e += TP) {
         s_pe[e] = pe[e];
-        s_accpe[e] = 0.f;
     }
+    for (int e = tid; e < NW * PE_SIZE; e += TP) s_accpe[e] = 0.f;
     if (MODE == MODE_CNF) {
         const int pf = packed_fcnn_size(16, 32);
         for (int f = 0; f < n_fcnn; ++f) load_fcnn_image<16, 32>(cnf + (size_t)f * pf, 0, s_img + f * LC::SIZE, nullptr, tid, TP);
-        for (int e = tid; e < n_fcnn * RC::NOUT; e += TP) s_acccnf[e] = 0.f;
-        for (int e = tid; e < n_fcnn * H; e += TP) s_d1row[e] = 0.f;
+        for (int e = tid; e < NW * n_fcnn * RC::NOUT; e += TP) s_acccnf[e] = 0.f;
+        for (int e = tid; e < NW * n_fcnn * H; e += TP) s_d1row[e] = 0.f;
     }
     __syncthreads();
     if (MODE == MODE_CNF) hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
@@ -273,7 +278,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         float denc[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) denc[k] = 0.f;
-        if (tid < 32) s_denc[tid] = 0.f;
+        s_denc[tid] = 0.f;   // NW * 32 == TP entries
         __syncthreads();
         for (int n0 = 0; n0 < N; n0 += TP) {
             asm volatile("" ::: "memory");  // no LICM of shared-memory weight loads across particles
@@ -341,8 +346,8 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                 for (int st = 2 * n_flows - 1; st >= 0; --st) {         // walk the forward stages back; one inlined stage body
                     const float* im = s_img + 2 * st * LC::SIZE;
                     const float* hb = s_hb + 2 * st * H;
-                    stage_bwd<16, 32>(im, im + LC::SIZE, hb, hb + H, 2 * st, false, live, lo, glo, e, de, up, gup, g, s_tile, s_acccnf,
-                                      s_d1row);
+                    stage_bwd<16, 32>(im, im + LC::SIZE, hb, hb + H, 2 * st, false, live, lo, glo, e, de, up, gup, g, s_tile,
+                                      s_acccnf + warp * n_fcnn * RC::NOUT, s_d1row + warp * n_fcnn * H);
                     swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
                 }
                 swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
@@ -399,13 +404,14 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                 s_tile[(PR::D2 + j) * TSM + tid] = d2[j];
                 if (MODE != MODE_GAUSS) s_tile[(PR::D3 + j) * TSM + tid] = de[j];
             }
-            __syncthreads();
-            pe_weight_grads_mma(s_tile, s_accpe, MODE == MODE_GAUSS ? s_denc : nullptr);
-            __syncthreads();
+            __syncwarp();   // the warp contracts over its own 32 tile columns: no CTA barrier in the batch loop
+            pe_weight_grads_mma(s_tile, s_accpe + warp * PE_SIZE, MODE == MODE_GAUSS ? s_denc + warp * 32 : nullptr);
+            __syncwarp();
         }
         // d_enc[b][k] = sum over the row's particles (deterministic: through the tile)
+        __syncthreads();   // all warps are done with this trajectory (tile columns, per-warp sums)
         if (d_enc && MODE == MODE_GAUSS) {
-            if (tid < 32) d_enc[(size_t)b * HID + tid] = -s_denc[tid];   // d ll / d enc = -sum_p delta3
+            if (tid < 32) d_enc[(size_t)b * HID + tid] = -((s_denc[tid] + s_denc[32 + tid]) + (s_denc[64 + tid] + s_denc[96 + tid]));   // -sum_p delta3
         } else if (d_enc) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) s_tile[k * TSM + tid] = denc[k];
@@ -418,12 +424,15 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         }
     }
     __syncthreads();
-    for (int e = tid; e < PE_SIZE; e += TP) part_pe[(size_t)blockIdx.x * PE_SIZE + e] = s_accpe[e];
+    for (int e = tid; e < PE_SIZE; e += TP)
+        part_pe[(size_t)blockIdx.x * PE_SIZE + e] = (s_accpe[e] + s_accpe[PE_SIZE + e]) + (s_accpe[2 * PE_SIZE + e] + s_accpe[3 * PE_SIZE + e]);
     if (MODE == MODE_CNF) {
         const int pf = packed_fcnn_size(16, 32);
         float* out = part_cnf + (size_t)blockIdx.x * n_fcnn * pf;
         for (int e = tid; e < n_fcnn * RC::NOUT; e += TP) {
-            out[(size_t)(e / RC::NOUT) * pf + packed_offset<16, 32>(e % RC::NOUT, 0)] = s_acccnf[e];
+            float a = s_acccnf[e];
+            for (int w = 1; w < NW; ++w) a += s_acccnf[w * n_fcnn * RC::NOUT + e];
+            out[(size_t)(e / RC::NOUT) * pf + packed_offset<16, 32>(e % RC::NOUT, 0)] = a;
         }
     }
 }
@@ -435,7 +444,9 @@ static size_t fwd_smem(int mode, int n_flows, int N) {
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
     const size_t tile = (size_t)(mode == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT) * TSM;
-    size_t fl = (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + tile + PE_SIZE + (size_t)n_fcnn * RC::NOUT + n_fcnn * H + 4 + 32;
+    const int nw = TP / 32;   // per-warp accumulator copies
+    size_t fl = (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + tile + (size_t)nw * PE_SIZE + (size_t)nw * n_fcnn * RC::NOUT +
+                (size_t)nw * n_fcnn * H + 4 + nw * 32;
     return fl * sizeof(float);
 }
 

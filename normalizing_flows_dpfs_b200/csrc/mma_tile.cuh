@@ -22,16 +22,18 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// One warp: c[n] (16 x 8 accumulator fragments) += A(16 delta rows starting at tile row rowA) x B_n over all particles
-// [0, np) (np multiple of 8).  rowB[n] is THIS LANE's tile row for column (lane >> 2) of n-tile n -- callers build it so
-// that bias / padding columns point at the ONE / ZERO rows of the tile.
+// One warp: c[n] (16 x 8 accumulator fragments) += A(16 delta rows starting at tile row rowA) x B_n over the particles
+// (tile columns) [k_begin, k_end) (multiples of 8).  rowB[n] is THIS LANE's tile row for column (lane >> 2) of n-tile n --
+// callers build it so that bias / padding columns point at the ONE / ZERO rows of the tile.  Every warp contracts over
+// ITS OWN 32 particles (the columns its threads staged), so the weight-gradient phase needs no CTA barrier.
 template <int NT>
-__device__ __forceinline__ void mma_outer(const float* __restrict__ tile, int rowA, const int (&rowB)[NT], int np, float (&c)[NT][4]) {
+__device__ __forceinline__ void mma_outer(const float* __restrict__ tile, int rowA, const int (&rowB)[NT], int k_begin, int k_end,
+                                          float (&c)[NT][4]) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const float* a_lo = tile + (rowA + g) * TSM + t;
     const float* a_hi = tile + (rowA + g + 8) * TSM + t;
-#pragma unroll 2
-    for (int k0 = 0; k0 < np; k0 += 8) {
+#pragma unroll
+    for (int k0 = k_begin; k0 < k_end; k0 += 8) {
         uint32_t ah[4], al[4];
         split_tf32(a_lo[k0], ah[0], al[0]);
         split_tf32(a_hi[k0], ah[1], al[1]);
