@@ -29,9 +29,9 @@ SIGNATURES = {
     "nfdpf_peak_probe": (_I64, [_I, _I, _P, _P]),
     "nfdpf_coupling_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "nfdpf_coupling_bwd_workspace": (_I64, [_I, _I, _I, _I, _I, _I]),
-    "nfdpf_measure_fwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
+    "nfdpf_measure_fwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P]),
     "nfdpf_measure_bwd_workspace": (_I64, [_I, _I, _I, _I]),
-    "nfdpf_measure_bwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nfdpf_measure_bwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nfdpf_coupling_bwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 _lib = None

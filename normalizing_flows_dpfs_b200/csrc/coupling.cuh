@@ -155,13 +155,17 @@ __device__ __forceinline__ void fcnn_bwd(const float* __restrict__ img, const fl
 #pragma unroll
     for (int k = 0; k < H; ++k) d1[k] = da1[k] * fmaf(-h1[k], h1[k], 1.0f);
 #pragma unroll
-    for (int k = 0; k < H; ++k) {
+    for (int k = 0; k < H; ++k) {   // d in = W1^T d1, 128-bit weight loads (rows are zero-padded to a multiple of 4)
         const float* w = img + L::W1 + k * L::S1;
 #pragma unroll
-        for (int i = 0; i < HALF; ++i) dc[i] = fmaf(w[i], d1[k], dc[i]);
-        if constexpr (CP > 0) {
+        for (int i = 0; i < L::S1; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(w + i);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int i = 0; i < CP; ++i) dpc[i] = fmaf(w[HALF + i], d1[k], dpc[i]);
+            for (int u = 0; u < 4; ++u) {
+                if (i + u < HALF) dc[i + u < HALF ? i + u : 0] = fmaf(wv[u], d1[k], dc[i + u < HALF ? i + u : 0]);
+                else if (i + u < HALF + CP) dpc[i + u >= HALF ? i + u - HALF : 0] = fmaf(wv[u], d1[k], dpc[i + u >= HALF ? i + u - HALF : 0]);
+            }
         }
     }
 }

@@ -107,7 +107,7 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                    const float* __restrict__ enc, const float* __restrict__ particles, int N, const float* __restrict__ lw0,
                    const float* __restrict__ prior, const float* __restrict__ propose, float add_eps, float* __restrict__ lki,
                    int* __restrict__ argmax, float* __restrict__ logw_out, float* __restrict__ probs_out,
-                   float* __restrict__ row_stats) {
+                   float* __restrict__ row_stats, float* __restrict__ z_out) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_red[33];
     __shared__ int s_redi[33];
@@ -133,6 +133,14 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         float a1[16], a2[32], e[32], lo[16], up[16];
         pe_fwd(s_pe, x.x, x.y, a1, a2, e);
         const float ll = loglik<MODE>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
+        if (MODE == MODE_CNF && z_out) {   // the flow output: lets the backward walk the stack from z without re-running it
+            float4* zo = reinterpret_cast<float4*>(z_out + ((size_t)b * N + n) * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                zo[i] = make_float4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                zo[4 + i] = make_float4(up[4 * i], up[4 * i + 1], up[4 * i + 2], up[4 * i + 3]);
+            }
+        }
         s_ll[n] = ll;
         mx = fmaxf(mx, ll);
     }
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(TP)
 measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, int n_flows, float p0, float p1,
                    const float* __restrict__ enc, const float* __restrict__ particles, int B, int N,
                    const float* __restrict__ g_lki, const int* __restrict__ argmax, float* __restrict__ d_particles,
-                   float* __restrict__ d_enc, float* __restrict__ part_pe, float* __restrict__ part_cnf) {
+                   float* __restrict__ d_enc, float* __restrict__ part_pe, float* __restrict__ part_cnf, const float* __restrict__ z_saved) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_red[33];
     const int tid = threadIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
@@ -333,7 +341,17 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
             } else {
                 pe_fwd(s_pe, x.x, x.y, a1, a2, e);
                 float lo[16], up[16], glo[16], gup[16];
-                loglik<MODE_CNF>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
+                if (z_saved) {
+                    const float4* zi = reinterpret_cast<const float4*>(z_saved + p * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a = zi[i], c4 = zi[4 + i];
+                        lo[4 * i] = a.x; lo[4 * i + 1] = a.y; lo[4 * i + 2] = a.z; lo[4 * i + 3] = a.w;
+                        up[4 * i] = c4.x; up[4 * i + 1] = c4.y; up[4 * i + 2] = c4.z; up[4 * i + 3] = c4.w;
+                    }
+                } else {
+                    loglik<MODE_CNF>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
+                }
                 const float c = -g / (p1 * p1);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { glo[i] = c * (lo[i] - p0); gup[i] = c * (up[i] - p0); }
@@ -453,27 +471,27 @@ static size_t bwd_smem(int mode, int n_flows) {
 template <int MODE>
 static int launch_measure_fwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,
                               int B, int N, const float* lw0, const float* prior, const float* propose, float add_eps, float* lki,
-                              int* argmax, float* logw_out, float* probs_out, float* row_stats, cudaStream_t st) {
+                              int* argmax, float* logw_out, float* probs_out, float* row_stats, float* z_out, cudaStream_t st) {
     const size_t smem = fwd_smem(MODE, n_flows, N);
     if (smem > 220 * 1024) { set_error("measure_fwd: N=%d too large for the shared-memory row buffer", N); return NFDPF_ERR_UNSUPPORTED; }
     auto kern = measure_fwd_kernel<MODE>;
     if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, N, lw0, prior, propose, add_eps, lki, argmax, logw_out, probs_out,
-                              row_stats);
+                              row_stats, z_out);
     return check_launch("measure_fwd");
 }
 
 template <int MODE>
 static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,
                               int B, int N, const float* g_lki, const int* argmax, float* d_particles, float* d_enc, float* d_pe,
-                              float* d_cnf, void* workspace, cudaStream_t st) {
+                              float* d_cnf, void* workspace, const float* z_saved, cudaStream_t st) {
     const size_t smem = bwd_smem(MODE, n_flows);
     auto kern = measure_bwd_kernel<MODE>;
     if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = bwd_grid(B);
     float* part_pe = (float*)workspace;
     float* part_cnf = part_pe + (size_t)grid * PE_SIZE;
-    kern<<<grid, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, part_cnf);
+    kern<<<grid, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, part_cnf, z_saved);
     int rc = check_launch("measure_bwd");
     if (rc) return rc;
     rc = launch_reduce_partials(part_pe, grid, PE_SIZE, d_pe, st);
@@ -489,7 +507,7 @@ using namespace nfdpf;
 extern "C" int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
                                  const float* enc, const float* particles, int B, int N, int hidden, const float* logw_prev,
                                  const float* prior, const float* propose, float add_eps, float* lki, int32_t* argmax,
-                                 float* logw_out, float* probs_out, float* row_stats, void* stream) {
+                                 float* logw_out, float* probs_out, float* row_stats, float* z_out, void* stream) {
     NFDPF_REQUIRE(pe_packed && enc && particles && lki, "measure_fwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0, "measure_fwd: B and N must be positive");
     NFDPF_REQUIRE(mode >= 0 && mode <= 2, "measure_fwd: mode must be 0 (gaussian), 1 (cos) or 2 (CRNVP), got %d", mode);
@@ -497,7 +515,7 @@ extern "C" int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* 
     NFDPF_REQUIRE(!logw_prev || probs_out, "measure_fwd: fused update needs probs_out");
     if (hidden != HID) { set_error("measure_fwd: kernels are built for hiddensize 32 (got %d)", hidden); return NFDPF_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
-#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, logw_prev, prior, propose, add_eps, lki, argmax, logw_out, probs_out, row_stats, st
+#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, logw_prev, prior, propose, add_eps, lki, argmax, logw_out, probs_out, row_stats, z_out, st
     if (mode == MODE_GAUSS) return launch_measure_fwd<MODE_GAUSS>(ARGS);
     if (mode == MODE_COS) return launch_measure_fwd<MODE_COS>(ARGS);
     return launch_measure_fwd<MODE_CNF>(ARGS);
@@ -514,7 +532,7 @@ extern "C" int64_t nfdpf_measure_bwd_workspace(int mode, int n_flows, int B, int
 extern "C" int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
                                  const float* enc, const float* particles, int B, int N, int hidden, const float* g_lki,
                                  const int32_t* argmax, float* d_particles, float* d_enc, float* d_pe, float* d_cnf, void* workspace,
-                                 void* stream) {
+                                 const float* z_saved, void* stream) {
     NFDPF_REQUIRE(pe_packed && enc && particles && g_lki && d_particles && d_pe && workspace, "measure_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0, "measure_bwd: B and N must be positive");
     NFDPF_REQUIRE(mode >= 0 && mode <= 2, "measure_bwd: bad mode %d", mode);
@@ -522,7 +540,7 @@ extern "C" int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* 
     NFDPF_REQUIRE(mode != MODE_CNF || (cnf_packed && d_cnf && n_flows >= 1 && n_flows <= 4), "measure_bwd: CRNVP needs packed stack + gradient buffer");
     if (hidden != HID) { set_error("measure_bwd: kernels are built for hiddensize 32 (got %d)", hidden); return NFDPF_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
-#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, d_pe, d_cnf, workspace, st
+#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, d_pe, d_cnf, workspace, z_saved, st
     if (mode == MODE_GAUSS) return launch_measure_bwd<MODE_GAUSS>(ARGS);
     if (mode == MODE_COS) return launch_measure_bwd<MODE_COS>(ARGS);
     return launch_measure_bwd<MODE_CNF>(ARGS);

@@ -166,10 +166,12 @@ class MeasureUpdate(torch.autograd.Function):
         logw = torch.empty(B, N, dtype=torch.float32, device=dev) if fused else None
         probs = torch.empty(B, N, dtype=torch.float32, device=dev) if fused else None
         stats = torch.empty(B, 2, dtype=torch.float32, device=dev) if fused else None
+        need_grad = any(ctx.needs_input_grad[:4])
+        z = torch.empty(B, N, hidden, dtype=torch.float32, device=dev) if (mode == 2 and need_grad) else None   # flow output, for the backward
         L.call("nfdpf_measure_fwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, float(p0), float(p1), L.ptr(enc_), L.ptr(x_), B, N, hidden,
                L.ptr(lw0), L.ptr(pr), L.ptr(pp), float(add_eps), L.ptr(lki), L.ptr(argmax), L.ptr(logw), L.ptr(probs), L.ptr(stats),
-               L.stream())
-        ctx.save_for_backward(pe_, cnf_, enc_, x_, argmax, probs)
+               L.ptr(z), L.stream())
+        ctx.save_for_backward(pe_, cnf_, enc_, x_, argmax, probs, z)
         ctx.meta = (mode, n_flows, float(p0), float(p1), float(add_eps), B, N, hidden, fused, prior is not None, propose is not None)
         if not fused:
             return lki, None, None, None, None
@@ -178,7 +180,7 @@ class MeasureUpdate(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_lki, g_logw, g_probs, g_rowsum, _g_ess):
-        pe_, cnf_, enc_, x_, argmax, probs = ctx.saved_tensors
+        pe_, cnf_, enc_, x_, argmax, probs, z = ctx.saved_tensors
         mode, n_flows, p0, p1, add_eps, B, N, hidden, fused, has_prior, has_prop = ctx.meta
         dev = x_.device
         d_logw = None
@@ -197,7 +199,7 @@ class MeasureUpdate(torch.autograd.Function):
         d_cnf = torch.zeros_like(cnf_) if cnf_ is not None else None
         ws = torch.empty(L.load().nfdpf_measure_bwd_workspace(mode, n_flows, B, N) // 4, dtype=torch.float32, device=dev)
         L.call("nfdpf_measure_bwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, p0, p1, L.ptr(enc_), L.ptr(x_), B, N, hidden,
-               L.ptr(g_total.contiguous()), L.ptr(argmax), L.ptr(d_x), L.ptr(d_enc), L.ptr(d_pe), L.ptr(d_cnf), L.ptr(ws), L.stream())
+               L.ptr(g_total.contiguous()), L.ptr(argmax), L.ptr(d_x), L.ptr(d_enc), L.ptr(d_pe), L.ptr(d_cnf), L.ptr(ws), L.ptr(z), L.stream())
         return (d_pe, d_cnf, d_enc, d_x, d_logw if fused else None, d_logw if has_prior else None,
                 (-d_logw if d_logw is not None else None) if has_prop else None, None, None, None, None, None)
 
