@@ -17,7 +17,7 @@ namespace nfdpf {
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr int OT_T = 256;      // threads per CTA = rows i per CTA
 constexpr int OT_J = 1024;     // columns j staged per shared-memory tile
-constexpr int OT_CH = 8;       // columns per online-LSE rescale
+constexpr int OT_CH = 16;      // columns per online-LSE rescale (one extra ex2 per chain per 16 pair evaluations)
 
 struct OtCtrl { int iter; int go; unsigned ticket; int pad; };
 
@@ -119,14 +119,16 @@ ot_pass_kernel(const float2* __restrict__ sx, const float* __restrict__ logw, co
                 c1 = fmaxf(c1, v1[u]);
                 cm2 = fmaxf(cm2, v2[u]);
             }
+            // every chunk of a tile holds at least one real column (tiles start on real columns, padding is at the tail) and
+            // log-weights are finite (the filter adds 1e-12 to every weight, DPFs.py:192), so n is finite and no
+            // inf - inf can form: the first chunk sees s * 2^(-inf - n) = 0 * 0, padding terms are 2^(-inf) = 0.
             const float n1 = fmaxf(m1, c1), n2 = fmaxf(m2, cm2);
-            // n == -inf only while every term so far is exp(-inf): keep the sum at 0 without forming inf - inf
-            s1 = n1 == -INFINITY ? 0.f : s1 * ex2f(m1 - n1);
-            s2 = n2 == -INFINITY ? 0.f : s2 * ex2f(m2 - n2);
+            s1 *= ex2f(m1 - n1);
+            s2 *= ex2f(m2 - n2);
 #pragma unroll
             for (int u = 0; u < OT_CH; ++u) {
-                s1 += n1 == -INFINITY ? 0.f : ex2f(v1[u] - n1);
-                s2 += n2 == -INFINITY ? 0.f : ex2f(v2[u] - n2);
+                s1 += ex2f(v1[u] - n1);
+                s2 += ex2f(v2[u] - n2);
             }
             m1 = n1; m2 = n2;
         }
@@ -213,9 +215,9 @@ ot_colnorm_kernel(const float2* __restrict__ sx, const float* __restrict__ logw,
                 cm = fmaxf(cm, v[u]);
             }
             const float n = fmaxf(m, cm);
-            s = n == -INFINITY ? 0.f : s * ex2f(m - n);
+            s *= ex2f(m - n);
 #pragma unroll
-            for (int u = 0; u < OT_CH; ++u) s += n == -INFINITY ? 0.f : ex2f(v[u] - n);
+            for (int u = 0; u < OT_CH; ++u) s += ex2f(v[u] - n);
             m = n;
         }
     }
