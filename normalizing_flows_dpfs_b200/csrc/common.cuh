@@ -89,14 +89,16 @@ struct OpMin {
 };
 
 // ---- transcendental helpers ------------------------------------------------------------------------------
-// tanh with ~2e-7 ABSOLUTE error from two MUFU ops: t = 2^(-2|x| log2 e) in (0,1], tanh|x| = (1 - t) / (1 + t).
-// The parity bar is rtol 1e-4 / atol 1e-5 against fp32 torch; tanh.approx.f32 (2^-11 relative) would not hold it.
-// Seven instructions (FMUL, MUFU.EX2, 2 FADD, MUFU.RCP, FMUL, LOP3 sign copy); no clamp needed: t underflows to 0.
-__device__ __forceinline__ float tanh_acc(float x) {
+// tanh with ~2e-7 ABSOLUTE error from two MUFU ops (ex2 + rcp).  The parity bar is rtol 1e-4 / atol 1e-5 against fp32
+// torch; tanh.approx.f32 (2^-11 relative) would not hold it.  The argument arrives PRE-SCALED, a = 2 log2(e) x (the scale
+// is folded into the weights that feed the tanh):
+// tanh(x) = 1 - 2 / (2^a + 1).  Four instructions (MUFU.EX2, FADD, MUFU.RCP, FFMA); 2^a = inf gives rcp = 0 -> 1, 2^a = 0 -> -1.
+constexpr float TANH_SCALE = 2.885390081777927f, TANH_ISCALE = 0.34657359027997264f;
+__device__ __forceinline__ float tanh_prescaled(float a) {
     float t, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * -2.885390081777927f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
-    return copysignf((1.0f - t) * r, x);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(a));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
 }
 __device__ __forceinline__ float exp_acc(float x) { return __expf(x); }  // ex2.approx(x*log2e): 2 ulp + range error
 

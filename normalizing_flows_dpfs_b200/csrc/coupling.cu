@@ -157,11 +157,11 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     for (int e = tid; e < n_fcnn * R::NOUT; e += TP) {
         float a = s_acc[e];
         for (int w = 1; w < NW; ++w) a += s_acc[w * n_fcnn * R::NOUT + e];
-        out[(size_t)(e / R::NOUT) * pf + packed_offset<HALF, CP>(e % R::NOUT, C_row)] = a;
+        out[(size_t)(e / R::NOUT) * pf + packed_offset<HALF, CP>(e % R::NOUT, C_row)] = a * grad_out_scale<HALF, CP>(e % R::NOUT);
     }
     for (int e = tid; e < n_fcnn * H * C_row; e += TP) {
         const int fk = e / C_row, cidx = e % C_row;
-        out[(size_t)(fk / H) * pf + (fk % H) * fin + HALF + cidx] = s_accR[e];
+        out[(size_t)(fk / H) * pf + (fk % H) * fin + HALF + cidx] = TANH_SCALE * s_accR[e];   // built from delta1 / scale
     }
 }
 

@@ -57,15 +57,18 @@ __device__ void load_fcnn_image(const float* __restrict__ pk, int C_row, float* 
         float v = 0.f;
         if (i < HALF) v = pk[k * fin + i];
         else if (i < L::IN1) v = pk[k * fin + C_row + i];
-        img[L::W1 + e] = v;
+        img[L::W1 + e] = TANH_SCALE * v;
     }
-    for (int e = tid; e < H * C_row; e += nt) w1r[e] = pk[(e / C_row) * fin + HALF + (e % C_row)];
+    // Everything that feeds a tanh (layers 1 and 2: weights, biases, row-context columns) is stored multiplied by
+    // 2 log2(e), so the activation is tanh_prescaled(pre-activation): 4 instructions instead of 7.  The backward
+    // carries delta / scale (free: folded into the 1 - h^2 factor) and rescales the weight gradients once on output.
+    for (int e = tid; e < H * C_row; e += nt) w1r[e] = TANH_SCALE * pk[(e / C_row) * fin + HALF + (e % C_row)];
     const float* p = pk + H * fin;
-    for (int e = tid; e < H; e += nt) img[L::B1 + e] = p[e];
+    for (int e = tid; e < H; e += nt) img[L::B1 + e] = TANH_SCALE * p[e];
     p += H;
-    for (int e = tid; e < H * H; e += nt) img[L::W2 + e] = p[e];
+    for (int e = tid; e < H * H; e += nt) img[L::W2 + e] = TANH_SCALE * p[e];
     p += H * H;
-    for (int e = tid; e < H; e += nt) img[L::B2 + e] = p[e];
+    for (int e = tid; e < H; e += nt) img[L::B2 + e] = TANH_SCALE * p[e];
     p += H;
     for (int e = tid; e < HALF * H; e += nt) img[L::W3 + e] = p[e];
     p += HALF * H;
@@ -101,7 +104,7 @@ __device__ __forceinline__ void fcnn_fwd(const float* __restrict__ img, const fl
             if (i + 2 < L::IN1) a = fmaf(w4.z, in[i + 2 < L::IN1 ? i + 2 : 0], a);
             if (i + 3 < L::IN1) a = fmaf(w4.w, in[i + 3 < L::IN1 ? i + 3 : 0], a);
         }
-        h1[k] = tanh_acc(a);
+        h1[k] = tanh_prescaled(a);
     }
     float b2[8];
     ld8(img + L::B2, b2);
@@ -112,7 +115,7 @@ __device__ __forceinline__ void fcnn_fwd(const float* __restrict__ img, const fl
         float a = b2[j];
 #pragma unroll
         for (int k = 0; k < H; ++k) a = fmaf(w[k], h1[k], a);
-        h2[j] = tanh_acc(a);
+        h2[j] = tanh_prescaled(a);
     }
 #pragma unroll
     for (int o = 0; o < HALF; ++o) {
@@ -125,7 +128,8 @@ __device__ __forceinline__ void fcnn_fwd(const float* __restrict__ img, const fl
     }
 }
 
-// FCNN backward (data path): dout -> d2, d1 (pre-activation grads), dc += W1c^T d1, dpc += W1p^T d1.
+// FCNN backward (data path): dout -> d2, d1 = pre-activation grads DIVIDED BY TANH_SCALE (the layer-1/2 images hold
+// scaled weights, so W_s^T (delta / s) = W^T delta exactly); dc += W1c^T delta1, dpc += W1p^T delta1.
 template <int HALF, int CP>
 __device__ __forceinline__ void fcnn_bwd(const float* __restrict__ img, const float (&dout)[HALF], const float (&h1)[H],
                                          const float (&h2)[H], float (&d1)[H], float (&d2)[H], float (&dc)[HALF], float* dpc) {
@@ -141,7 +145,7 @@ __device__ __forceinline__ void fcnn_bwd(const float* __restrict__ img, const fl
         for (int j = 0; j < H; ++j) da2[j] = fmaf(w[j], dout[o], da2[j]);
     }
 #pragma unroll
-    for (int j = 0; j < H; ++j) d2[j] = da2[j] * fmaf(-h2[j], h2[j], 1.0f);
+    for (int j = 0; j < H; ++j) d2[j] = da2[j] * fmaf(-TANH_ISCALE * h2[j], h2[j], TANH_ISCALE);   // delta2 / scale
     float da1[H];
 #pragma unroll
     for (int k = 0; k < H; ++k) da1[k] = 0.f;
@@ -153,7 +157,7 @@ __device__ __forceinline__ void fcnn_bwd(const float* __restrict__ img, const fl
         for (int k = 0; k < H; ++k) da1[k] = fmaf(w[k], d2[j], da1[k]);
     }
 #pragma unroll
-    for (int k = 0; k < H; ++k) d1[k] = da1[k] * fmaf(-h1[k], h1[k], 1.0f);
+    for (int k = 0; k < H; ++k) d1[k] = da1[k] * fmaf(-TANH_ISCALE * h1[k], h1[k], TANH_ISCALE);   // delta1 / scale (W2 image is scaled: W2s^T (d2/s) = W2^T d2)
 #pragma unroll
     for (int k = 0; k < H; ++k) {   // d in = W1^T d1, 128-bit weight loads (rows are zero-padded to a multiple of 4)
         const float* w = img + L::W1 + k * L::S1;
@@ -312,6 +316,10 @@ __device__ __forceinline__ void stage_weight_grads_mma(const float* __restrict__
         if (g + 8 < HALF) acc_f[B3 + g + 8] += c[1][2];
     }
 }
+
+// gradient entries of layers 1 and 2 were accumulated from delta / TANH_SCALE: factor to apply when they are written out
+template <int HALF, int CP>
+__device__ __forceinline__ float grad_out_scale(int e) { return e < H * (HALF + CP) + H + H * H + H ? TANH_SCALE : 1.0f; }
 
 // packed-FCNN offset (row-context columns skipped) of gradient entry e, e in [0, NOUT): the order of acc_f above
 template <int HALF, int CP>

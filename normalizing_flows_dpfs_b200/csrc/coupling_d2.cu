@@ -193,12 +193,12 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
         }
         // per-trajectory layer-1 delta sums: the row-context columns of dW1 and d(row_ctx) are formed from them by
         // rowctx_grad_kernel after this kernel (keeps the 8 x C_row outer products out of the persistent loop)
-        for (int e = tid; e < n_fcnn * H; e += TPD) d1rows[(size_t)e * B + b] = s_d1row[e];   // [f*8+k][b]: coalesced for rowctx_grad
+        for (int e = tid; e < n_fcnn * H; e += TPD) d1rows[(size_t)e * B + b] = TANH_SCALE * s_d1row[e];   // true delta sums, [f*8+k][b]: coalesced for rowctx_grad
         __syncthreads();
     }
     float* out = partials + (size_t)blockIdx.x * n_fcnn * pf;
     for (int e = tid; e < n_fcnn * NACC; e += TPD) {
-        out[(size_t)(e / NACC) * pf + packed_offset<1, 0>(e % NACC, C_row)] = s_acc[e];
+        out[(size_t)(e / NACC) * pf + packed_offset<1, 0>(e % NACC, C_row)] = s_acc[e] * grad_out_scale<1, 0>(e % NACC);
     }
     const int fin = 1 + C_row;
     for (int e = tid; e < n_fcnn * H * C_row; e += TPD)   // row-context columns are produced by rowctx_grad_kernel

@@ -450,7 +450,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         for (int e = tid; e < n_fcnn * RC::NOUT; e += TP) {
             float a = s_acccnf[e];
             for (int w = 1; w < NW; ++w) a += s_acccnf[w * n_fcnn * RC::NOUT + e];
-            out[(size_t)(e / RC::NOUT) * pf + packed_offset<16, 32>(e % RC::NOUT, 0)] = a;
+            out[(size_t)(e / RC::NOUT) * pf + packed_offset<16, 32>(e % RC::NOUT, 0)] = a * grad_out_scale<16, 32>(e % RC::NOUT);
         }
     }
 }
