@@ -7,6 +7,7 @@
 // eight (P,48) concatenations; here the only HBM traffic is particles in, (B,N) vectors out.
 #include "coupling.cuh"
 #include "mma_tile.cuh"
+#include "umma.cuh"
 
 namespace nfdpf {
 
@@ -16,6 +17,94 @@ constexpr int HID = 32;                      // encoding width (args.hiddensize)
 constexpr int PE_W1 = 0, PE_B1 = 32, PE_W2 = 48, PE_B2 = 560, PE_W3 = 592, PE_B3 = 1616, PE_SIZE = 1648;
 using LC = Lay<16, 32>;
 using RC = Rows<16, 32>;
+
+// ---- particle encoder layers 2 and 3 on the tcgen05 tensor cores (umma.cuh) ------------------------------------
+// M = the CTA's 128 particles (TMEM lane = particle = thread), N / K = 16 / 32 features, 3xTF32.  Layer 1 (2 -> 16) and
+// the bias / ReLU epilogues stay in registers.  Shared-memory region (floats): activation tile hi | lo, then the weight
+// tiles hi | lo in both orientations (the transposed ones only in the backward).
+struct PeTc {
+    using A32 = umma::Operand<128, 32>;
+    using A16 = umma::Operand<128, 16>;
+    using W2 = umma::Operand<32, 16>;    // rows j (out), K = k (in)          a2 = W2 a1
+    using W3 = umma::Operand<32, 32>;    // rows o,       K = j               e  = W3 a2
+    using W3T = umma::Operand<32, 32>;   // rows j,       K = o               d a2 = W3^T delta3
+    using W2T = umma::Operand<16, 32>;   // rows k,       K = j               d a1 = W2^T delta2
+    static constexpr int A_HI = 0, A_LO = A_HI + A32::FLOATS, W2_HI = A_LO + A32::FLOATS, W2_LO = W2_HI + W2::FLOATS,
+                         W3_HI = W2_LO + W2::FLOATS, W3_LO = W3_HI + W3::FLOATS, FWD_FLOATS = W3_LO + W3::FLOATS,
+                         W3T_HI = FWD_FLOATS, W3T_LO = W3T_HI + W3T::FLOATS, W2T_HI = W3T_LO + W3T::FLOATS, W2T_LO = W2T_HI + W2T::FLOATS,
+                         BWD_FLOATS = W2T_LO + W2T::FLOATS;
+    float* s;            // region base (128-byte aligned)
+    uint64_t* bar;       // mbarrier: completion of the issued MMAs
+    uint32_t tmem;       // 32 accumulator columns
+    uint32_t parity;
+
+    // split the layer-2 / layer-3 weights into the hi / lo operand tiles (all threads)
+    __device__ void load_weights(const float* __restrict__ pe, bool bwd) {
+        for (int e = threadIdx.x; e < 32 * 16; e += blockDim.x) {
+            const int j = e >> 4, k = e & 15;
+            const float w = pe[PE_W2 + e];
+            W2::store_elem(s + W2_HI, s + W2_LO, j, k, w);
+            if (bwd) W2T::store_elem(s + W2T_HI, s + W2T_LO, k, j, w);
+        }
+        for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+            const int o = e >> 5, j = e & 31;
+            const float w = pe[PE_W3 + e];
+            W3::store_elem(s + W3_HI, s + W3_LO, o, j, w);
+            if (bwd) W3T::store_elem(s + W3T_HI, s + W3T_LO, j, o, w);
+        }
+    }
+    // One product round, called by ALL 128 threads after each has written its row of the activation tile:
+    // publish the tile to the async proxy, one thread issues the 3xTF32 MMAs, everybody waits for their completion.
+    template <int N, int K>
+    __device__ __forceinline__ void round(int w_hi, int w_lo) {
+        umma::fence_smem_to_async();
+        umma::fence_before_sync();      // orders this thread's earlier tcgen05.ld before the barrier (accumulator reuse)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            umma::fence_after_sync();
+            umma::gemm3<N, K>(tmem, s + A_HI, s + A_LO, s + w_hi, s + w_lo);
+            umma::commit(bar);
+        }
+        umma::mbar_wait(bar, parity);
+        parity ^= 1;
+        umma::fence_after_sync();
+    }
+    __device__ __forceinline__ uint32_t lane_addr() const { return tmem + ((uint32_t)(threadIdx.x & ~31) << 16); }
+};
+
+__device__ __forceinline__ void pe_l1(const float* __restrict__ w, float x0, float x1, float (&a1)[16]) {
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+        const float4 q = *reinterpret_cast<const float4*>(w + PE_W1 + 2 * k);
+        const float2 b = *reinterpret_cast<const float2*>(w + PE_B1 + k);
+        a1[k] = fmaxf(fmaf(q.y, x1, fmaf(q.x, x0, b.x)), 0.f);
+        a1[k + 1] = fmaxf(fmaf(q.w, x1, fmaf(q.z, x0, b.y)), 0.f);
+    }
+}
+
+// encoder forward for the particle of this thread; collective over the CTA (contains barriers)
+__device__ __forceinline__ void pe_fwd_tc(PeTc& tc, const float* __restrict__ w, float x0, float x1, float (&a1)[16], float (&a2)[32],
+                                          float (&e)[32]) {
+    const int tid = threadIdx.x;
+    pe_l1(w, x0, x1, a1);
+    PeTc::A16::store_row(tc.s + PeTc::A_HI, tc.s + PeTc::A_LO, tid, a1);
+    tc.round<32, 16>(PeTc::W2_HI, PeTc::W2_LO);
+    umma::ld32(tc.lane_addr(), a2);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(w + PE_B2 + j);
+        a2[j] = fmaxf(a2[j] + b.x, 0.f); a2[j + 1] = fmaxf(a2[j + 1] + b.y, 0.f);
+        a2[j + 2] = fmaxf(a2[j + 2] + b.z, 0.f); a2[j + 3] = fmaxf(a2[j + 3] + b.w, 0.f);
+    }
+    PeTc::A32::store_row(tc.s + PeTc::A_HI, tc.s + PeTc::A_LO, tid, a2);
+    tc.round<32, 32>(PeTc::W3_HI, PeTc::W3_LO);
+    umma::ld32(tc.lane_addr(), e);
+#pragma unroll
+    for (int o = 0; o < 32; o += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(w + PE_B3 + o);
+        e[o] += b.x; e[o + 1] += b.y; e[o + 2] += b.z; e[o + 3] += b.w;
+    }
+}
 
 __device__ __forceinline__ void pe_fwd(const float* __restrict__ w, float x0, float x1, float (&a1)[16], float (&a2)[32],
                                        float (&e)[32]) {
@@ -108,32 +197,44 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                    const float* __restrict__ prior, const float* __restrict__ propose, float add_eps, float* __restrict__ lki,
                    int* __restrict__ argmax, float* __restrict__ logw_out, float* __restrict__ probs_out,
                    float* __restrict__ row_stats, float* __restrict__ z_out) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     __shared__ float s_red[33];
     __shared__ int s_redi[33];
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_tslot;
     const int tid = threadIdx.x, b = blockIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
-    float* s_pe = smem;                       // [1648]
+    float* s_tc = smem;                       // [PeTc::FWD_FLOATS] tensor-core operand tiles
+    float* s_pe = s_tc + PeTc::FWD_FLOATS;    // [1648]
     float* s_enc = s_pe + PE_SIZE;            // [36]
     float* s_img = s_enc + 36;                // [n_fcnn][LC::SIZE]
     float* s_hb = s_img + n_fcnn * LC::SIZE;  // [n_fcnn][8]
     float* s_ll = s_hb + n_fcnn * H;          // [N]
+    if (tid < 32) umma::tmem_alloc<32>(&s_tslot);
+    if (tid == 0) umma::mbar_init(&s_bar, 1);
+    PeTc tc{s_tc, &s_bar, 0u, 0u};
+    tc.load_weights(pe, false);
     for (int e = tid; e < PE_SIZE; e += TP) s_pe[e] = pe[e];
     if (MODE == MODE_CNF) {
         const int pf = packed_fcnn_size(16, 32);
         for (int f = 0; f < n_fcnn; ++f) load_fcnn_image<16, 32>(cnf + (size_t)f * pf, 0, s_img + f * LC::SIZE, nullptr, tid, TP);
     }
     load_enc(enc + (size_t)b * HID, s_enc);
+    umma::fence_before_sync();
     __syncthreads();
+    umma::fence_after_sync();
+    tc.tmem = s_tslot;
     if (MODE == MODE_CNF) hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
     __syncthreads();
     float mx = -INFINITY;
-    for (int n = tid; n < N; n += TP) {
-        asm volatile("" ::: "memory");  // keep the shared-memory weight loads inside the loop (LICM would spill ~1.6k floats)
-        const float2 x = *reinterpret_cast<const float2*>(particles + ((size_t)b * N + n) * 2);
+    for (int n0 = 0; n0 < N; n0 += TP) {      // uniform trip count: the tensor-core rounds are CTA-collective
+        asm volatile("" ::: "memory");  // keep the shared-memory weight loads inside the loop
+        const int n = n0 + tid;
+        const bool live = n < N;
+        const float2 x = live ? *reinterpret_cast<const float2*>(particles + ((size_t)b * N + n) * 2) : make_float2(0.f, 0.f);
         float a1[16], a2[32], e[32], lo[16], up[16];
-        pe_fwd(s_pe, x.x, x.y, a1, a2, e);
+        pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);
         const float ll = loglik<MODE>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
-        if (MODE == MODE_CNF && z_out) {   // the flow output: lets the backward walk the stack from z without re-running it
+        if (MODE == MODE_CNF && z_out && live) {   // the flow output: lets the backward walk the stack from z without re-running it
             float4* zo = reinterpret_cast<float4*>(z_out + ((size_t)b * N + n) * 32);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -141,9 +242,11 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                 zo[4 + i] = make_float4(up[4 * i], up[4 * i + 1], up[4 * i + 2], up[4 * i + 3]);
             }
         }
-        s_ll[n] = ll;
-        mx = fmaxf(mx, ll);
+        if (live) { s_ll[n] = ll; mx = fmaxf(mx, ll); }
     }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_free<32>(tc.tmem);
     float shift = 0.f;
     if (MODE != MODE_COS) {      // likelihood - likelihood.max(dim=-1), models.py:252, 276
         shift = block_allreduce(mx, s_red, OpMax(), -INFINITY);
@@ -457,7 +560,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 
 static size_t fwd_smem(int mode, int n_flows, int N) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    return ((size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + N) * sizeof(float);
+    return ((size_t)PeTc::FWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + N) * sizeof(float);
 }
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;

@@ -1,0 +1,303 @@
+// Stand-alone probe of the tcgen05 building blocks in csrc/umma.cuh (descriptor fields, operand layout, TMEM read-back).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tools/tc_probe tools/tc_probe.cu
+//   tools/tc_probe <test>      test = k32n32 | k16n32 | k32n16 | swap | mn | reuse
+// Prints the max abs error of the 3xTF32 product against an fp64 host product (and of a single TF32 pass for scale).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../normalizing_flows_dpfs_b200/csrc/umma.cuh"
+
+using namespace nfdpf;
+using namespace nfdpf::umma;
+
+namespace nfdpf {
+void set_error(const char*, ...) {}
+int check_launch(const char*) { return 0; }
+int sm_count() { return 148; }
+}  // namespace nfdpf
+
+template <int N, int K, int SWAP, int ROUNDS, int PASSES>
+__global__ void __launch_bounds__(128) probe_kmajor(const float* A, const float* Bw, float* D) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    using OA = Operand<128, K>;
+    using OB = Operand<N, K>;
+    float* a_hi = smem;
+    float* a_lo = a_hi + OA::FLOATS;
+    float* b_hi = a_lo + OA::FLOATS;
+    float* b_lo = b_hi + OB::FLOATS;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc<32>(&tslot);
+    if (tid == 0) mbar_init(&bar, 1);
+    for (int e = tid; e < N * K; e += 128) OB::store_elem(b_hi, b_lo, e / K, e % K, Bw[e]);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tslot;
+    uint32_t parity = 0;
+    for (int round = 0; round < ROUNDS; ++round) {
+        float v[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) v[k] = A[((size_t)round * 128 + tid) * K + k];
+        OA::store_row(a_hi, a_lo, tid, v);
+        fence_smem_to_async();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            if (SWAP == 0 && PASSES == 3) {
+                gemm3<N, K>(tmem, a_hi, a_lo, b_hi, b_lo);
+            } else {
+                constexpr uint32_t idesc = idesc_tf32(128, N);
+                uint32_t acc = 0;
+                for (int k0 = 0; k0 < K; k0 += 8) {
+                    const uint64_t da = SWAP ? smem_desc(smem_u32(a_hi) + (k0 / 4) * OA::CHUNK_BYTES, 128, OA::CHUNK_BYTES) : OA::desc(a_hi, k0);
+                    const uint64_t db = SWAP ? smem_desc(smem_u32(b_hi) + (k0 / 4) * OB::CHUNK_BYTES, 128, OB::CHUNK_BYTES) : OB::desc(b_hi, k0);
+                    mma_tf32_ss(tmem, da, db, idesc, acc);
+                    acc = 1;
+                }
+            }
+            commit(&bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        fence_after_sync();
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+        float out[N];
+        if constexpr (N == 32) ld32(taddr, out); else ld16(taddr, out);
+#pragma unroll
+        for (int n = 0; n < N; ++n) D[((size_t)round * 128 + tid) * N + n] = out[n];
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free<32>(tmem);
+}
+
+// Weight-gradient form: D[m][n] = sum_k A[m][k] B[n][k] with K = 128 particles and both operands written "MN-major"
+// (thread k stores 4 consecutive features with one STS.128):  element (m, k) at byte (k % 8) * 16 + (k / 8) * LBO + (m / 4) * 128 + (m % 4) * 4.
+// Only MA (< 128) rows of A and NB (< 64) rows of B are backed by data; the rest alias whatever follows (garbage rows of D, ignored).
+template <int MA, int NB>
+__global__ void __launch_bounds__(128) probe_mnmajor(const float* A /*[128 k][MA]*/, const float* Bw /*[128 k][NB]*/, float* D /*[128][64]*/) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    constexpr int LBO_A = (MA / 4) * 128, LBO_B = (NB / 4) * 128;
+    float* a_hi = smem;                           // 16 k-blocks x LBO_A bytes
+    float* a_lo = a_hi + 16 * LBO_A / 4;
+    float* b_hi = a_lo + 16 * LBO_A / 4;
+    float* b_lo = b_hi + 16 * LBO_B / 4;
+    float* pad = b_lo + 16 * LBO_B / 4;           // readable slack behind the last operand (aliased garbage rows reach into it)
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc<64>(&tslot);
+    if (tid == 0) mbar_init(&bar, 1);
+    for (int e = tid; e < 4096; e += 128) pad[e] = 0.f;
+    const int k = tid;
+    for (int g = 0; g < MA / 4; ++g) {
+        float4 h, l;
+        split(A[k * MA + 4 * g + 0], h.x, l.x); split(A[k * MA + 4 * g + 1], h.y, l.y);
+        split(A[k * MA + 4 * g + 2], h.z, l.z); split(A[k * MA + 4 * g + 3], h.w, l.w);
+        const int o = ((k & 7) * 16 + (k >> 3) * LBO_A + g * 128) / 4;
+        *reinterpret_cast<float4*>(a_hi + o) = h; *reinterpret_cast<float4*>(a_lo + o) = l;
+    }
+    for (int g = 0; g < NB / 4; ++g) {
+        float4 h, l;
+        split(Bw[k * NB + 4 * g + 0], h.x, l.x); split(Bw[k * NB + 4 * g + 1], h.y, l.y);
+        split(Bw[k * NB + 4 * g + 2], h.z, l.z); split(Bw[k * NB + 4 * g + 3], h.w, l.w);
+        const int o = ((k & 7) * 16 + (k >> 3) * LBO_B + g * 128) / 4;
+        *reinterpret_cast<float4*>(b_hi + o) = h; *reinterpret_cast<float4*>(b_lo + o) = l;
+    }
+    fence_smem_to_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tslot;
+    if (tid == 0) {
+        constexpr uint32_t idesc = idesc_tf32(128, 64, 1, 1);
+        uint32_t acc = 0;
+        for (int pass = 0; pass < 3; ++pass) {
+            const float* a = pass == 0 ? a_lo : a_hi;
+            const float* b = pass == 1 ? b_lo : b_hi;
+            for (int kb = 0; kb < 16; ++kb) {
+                mma_tf32_ss(tmem, smem_desc(smem_u32(a) + kb * LBO_A, LBO_A, 128), smem_desc(smem_u32(b) + kb * LBO_B, LBO_B, 128), idesc, acc);
+                acc = 1;
+            }
+        }
+        commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    fence_after_sync();
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    float o0[32], o1[32];
+    ld32(taddr, o0);
+    ld32(taddr + 32, o1);
+    for (int n = 0; n < 32; ++n) { D[tid * 64 + n] = o0[n]; D[tid * 64 + 32 + n] = o1[n]; }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free<64>(tmem);
+}
+
+static float frand() { return (float)rand() / RAND_MAX * 2.f - 1.f; }
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
+
+template <int N, int K, int SWAP, int ROUNDS, int PASSES>
+int run_k(const char* name) {
+    std::vector<float> A((size_t)ROUNDS * 128 * K), B(N * K), D((size_t)ROUNDS * 128 * N);
+    for (auto& x : A) x = frand();
+    for (auto& x : B) x = frand();
+    float *dA, *dB, *dD;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0, D.size() * 4));
+    const size_t smem = 2 * Operand<128, K>::BYTES + 2 * Operand<N, K>::BYTES;
+    auto kern = probe_kmajor<N, K, SWAP, ROUNDS, PASSES>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, 128, smem>>>(dA, dB, dD);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (int r = 0; r < ROUNDS * 128; ++r)
+        for (int n = 0; n < N; ++n) {
+            double ref = 0;
+            for (int k = 0; k < K; ++k) ref += (double)A[(size_t)r * K + k] * B[n * K + k];
+            maxerr = fmax(maxerr, fabs(ref - D[(size_t)r * N + n]));
+            maxref = fmax(maxref, fabs(ref));
+        }
+    printf("%s: N=%d K=%d swap=%d rounds=%d passes=%d  max|err| = %.3e  (max|ref| = %.3f)  D[0][0..3] = %f %f %f %f\n", name, N, K, SWAP, ROUNDS,
+           PASSES, maxerr, maxref, D[0], D[1], D[2], D[3]);
+    return 0;
+}
+
+int run_mn() {
+    constexpr int MA = 80, NB = 52;
+    std::vector<float> A(128 * MA), B(128 * NB), D(128 * 64);
+    for (auto& x : A) x = frand();
+    for (auto& x : B) x = frand();
+    float *dA, *dB, *dD;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    const size_t smem = 2 * 16 * (MA / 4) * 128 + 2 * 16 * (NB / 4) * 128 + 4096 * 4;
+    auto kern = probe_mnmajor<MA, NB>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<1, 128, smem>>>(dA, dB, dD);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (int m = 0; m < MA; ++m)
+        for (int n = 0; n < NB; ++n) {
+            double ref = 0;
+            for (int k = 0; k < 128; ++k) ref += (double)A[k * MA + m] * B[k * NB + n];
+            maxerr = fmax(maxerr, fabs(ref - D[m * 64 + n]));
+            maxref = fmax(maxref, fabs(ref));
+        }
+    printf("mn-major: M=%d(of 128) N=%d(of 64) K=128  max|err| = %.3e  (max|ref| = %.3f)  D[0][0..3] = %f %f %f %f\n", MA, NB, maxerr, maxref, D[0],
+           D[1], D[2], D[3]);
+    return 0;
+}
+
+int main2(int argc, char** argv);
+int main(int argc, char** argv) {
+    const char* t = argc > 1 ? argv[1] : "k32n32";
+    srand(1234);
+    if (!strcmp(t, "k32n32")) return run_k<32, 32, 0, 1, 3>(t);
+    if (!strcmp(t, "k32n32_1pass")) return run_k<32, 32, 0, 1, 1>(t);
+    if (!strcmp(t, "k16n32")) return run_k<32, 16, 0, 1, 3>(t);
+    if (!strcmp(t, "k32n16")) return run_k<16, 32, 0, 1, 3>(t);
+    if (!strcmp(t, "swap")) return run_k<32, 32, 1, 1, 1>(t);
+    if (!strcmp(t, "reuse")) return run_k<32, 32, 0, 8, 3>(t);
+    if (!strcmp(t, "mn")) return run_mn();
+    return main2(argc, argv);
+}
+
+// ---- layout decoder for MN-major operands: which shared-memory word does the tensor core read for element (mn, k)? ----
+// The MN-major operand region is filled with code values (word index, split into two exactly-representable parts over two
+// runs); the other operand is a K-major identity, so D exposes the words read.
+template <int WHICH /*0: A is MN-major, 1: B is MN-major*/, int BOTH>
+__global__ void __launch_bounds__(128) probe_decode(float* D, int part, uint32_t lbo, uint32_t sbo, int N, int mn_flag) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    constexpr int REG = 16384;                 // 64 KB coded region
+    float* coded = smem;
+    float* ident = smem + REG;                 // K-major identity, 128 rows x K = 8: chunk c at c * 2048 B
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc<64>(&tslot);
+    if (tid == 0) mbar_init(&bar, 1);
+    for (int w = tid; w < REG; w += 128) coded[w] = part == 0 ? (float)(w & 1023) : (float)(w >> 10);
+    for (int e = tid; e < 128 * 8; e += 128) {
+        const int r = e / 8, k = e % 8;
+        ident[(k >> 2) * 512 + r * 4 + (k & 3)] = (r == k) ? 1.f : 0.f;
+    }
+    fence_smem_to_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tslot;
+    if (tid == 0) {
+        const uint64_t dc = smem_desc(smem_u32(coded), lbo, sbo);
+        const uint64_t di = smem_desc(smem_u32(ident), 2048, 128);
+        if (WHICH == 0) mma_tf32_ss(tmem, dc, di, idesc_tf32(128, N, mn_flag, 0), 0);
+        else            mma_tf32_ss(tmem, di, dc, idesc_tf32(128, N, 0, mn_flag), 0);
+        commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    fence_after_sync();
+    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+    float o0[32], o1[32];
+    ld32(taddr, o0);
+    ld32(taddr + 32, o1);
+    for (int n = 0; n < 32; ++n) { D[tid * 64 + n] = o0[n]; D[tid * 64 + 32 + n] = o1[n]; }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free<64>(tmem);
+}
+
+template <int WHICH>
+int run_decode(uint32_t lbo, uint32_t sbo, int N = 64, int mn_flag = 1) {
+    std::vector<float> D0(128 * 64), D1(128 * 64);
+    float* dD;
+    CK(cudaMalloc(&dD, 128 * 64 * 4));
+    const size_t smem = (16384 + 128 * 8 + 1024) * 4;
+    auto kern = probe_decode<WHICH, 0>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int part = 0; part < 2; ++part) {
+        kern<<<1, 128, smem>>>(dD, part, lbo, sbo, N, mn_flag);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(part ? D1.data() : D0.data(), dD, 128 * 64 * 4, cudaMemcpyDeviceToHost));
+    }
+    printf("decode %s mn_flag=%d N=%d, LBO=%u SBO=%u bytes: byte offset read for (mn, k)\n", WHICH ? "B" : "A", mn_flag, N, lbo, sbo);
+    const int mns[] = {0, 1, 2, 3, 4, 5, 7, 8, 12, 16, 32, 63};
+    for (int mn : mns) {
+        printf("  mn=%3d:", mn);
+        for (int k = 0; k < 8; ++k) {
+            // WHICH == 0: D[m][n = k] = A(m, k);   WHICH == 1: D[m = k][n] = B(n, k)
+            const int idx = WHICH == 0 ? mn * 64 + k : k * 64 + mn;
+            const int w = (int)D0[idx] + ((int)D1[idx] << 10);
+            printf(" %6d", w * 4);
+        }
+        printf("\n");
+    }
+    return 0;
+}
+
+int main2(int argc, char** argv) {
+    const char* t = argv[1];
+    if (!strcmp(t, "decodeA")) return run_decode<0>(4096, 256);
+    if (!strcmp(t, "decodeB")) return run_decode<1>(4096, 256);
+    if (!strcmp(t, "decodeA2")) return run_decode<0>(256, 4096);
+    if (!strcmp(t, "decodeA_k64")) return run_decode<0>(2048, 128, 64, 0);   // K-major coded A, N = 64
+    if (!strcmp(t, "decodeA_k32")) return run_decode<0>(2048, 128, 32, 0);   // K-major coded A, N = 32
+    if (!strcmp(t, "decodeA_mn32")) return run_decode<0>(4096, 256, 32, 1);  // MN-major coded A, N = 32
+    if (!strcmp(t, "decodeB_mn32")) return run_decode<1>(4096, 256, 32, 1);
+    if (!strcmp(t, "decodeB_k32")) return run_decode<1>(2048, 128, 32, 0);
+    return 2;
+}
