@@ -29,11 +29,12 @@ struct PeTc {
     using W3 = umma::Operand<32, 32>;    // rows o,       K = j               e  = W3 a2
     using W3T = umma::Operand<32, 32>;   // rows j,       K = o               d a2 = W3^T delta3
     using W2T = umma::Operand<16, 32>;   // rows k,       K = j               d a1 = W2^T delta2
-    static constexpr int A_HI = 0, A_LO = A_HI + A32::FLOATS, W2_HI = A_LO + A32::FLOATS, W2_LO = W2_HI + W2::FLOATS,
-                         W3_HI = W2_LO + W2::FLOATS, W3_LO = W3_HI + W3::FLOATS, FWD_FLOATS = W3_LO + W3::FLOATS,
-                         W3T_HI = FWD_FLOATS, W3T_LO = W3T_HI + W3T::FLOATS, W2T_HI = W3T_LO + W3T::FLOATS, W2T_LO = W2T_HI + W2T::FLOATS,
-                         BWD_FLOATS = W2T_LO + W2T::FLOATS;
-    float* s;            // region base (128-byte aligned)
+    static constexpr int A_HI = 0, A_LO = A_HI + A32::FLOATS, A_FLOATS = 2 * A32::FLOATS;            // offsets from a
+    static constexpr int W2_HI = 0, W2_LO = W2_HI + W2::FLOATS, W3_HI = W2_LO + W2::FLOATS, W3_LO = W3_HI + W3::FLOATS,  // offsets from w
+                         WFWD_FLOATS = W3_LO + W3::FLOATS, W3T_HI = WFWD_FLOATS, W3T_LO = W3T_HI + W3T::FLOATS,
+                         W2T_HI = W3T_LO + W3T::FLOATS, W2T_LO = W2T_HI + W2T::FLOATS, WBWD_FLOATS = W2T_LO + W2T::FLOATS;
+    float* a;            // activation tile hi | lo (128-byte aligned)
+    float* w;            // weight tiles
     uint64_t* bar;       // mbarrier: completion of the issued MMAs
     uint32_t tmem;       // 32 accumulator columns
     uint32_t parity;
@@ -42,15 +43,15 @@ struct PeTc {
     __device__ void load_weights(const float* __restrict__ pe, bool bwd) {
         for (int e = threadIdx.x; e < 32 * 16; e += blockDim.x) {
             const int j = e >> 4, k = e & 15;
-            const float w = pe[PE_W2 + e];
-            W2::store_elem(s + W2_HI, s + W2_LO, j, k, w);
-            if (bwd) W2T::store_elem(s + W2T_HI, s + W2T_LO, k, j, w);
+            const float wv = pe[PE_W2 + e];
+            W2::store_elem(w + W2_HI, w + W2_LO, j, k, wv);
+            if (bwd) W2T::store_elem(w + W2T_HI, w + W2T_LO, k, j, wv);
         }
         for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
             const int o = e >> 5, j = e & 31;
-            const float w = pe[PE_W3 + e];
-            W3::store_elem(s + W3_HI, s + W3_LO, o, j, w);
-            if (bwd) W3T::store_elem(s + W3T_HI, s + W3T_LO, j, o, w);
+            const float wv = pe[PE_W3 + e];
+            W3::store_elem(w + W3_HI, w + W3_LO, o, j, wv);
+            if (bwd) W3T::store_elem(w + W3T_HI, w + W3T_LO, j, o, wv);
         }
     }
     // One product round, called by ALL 128 threads after each has written its row of the activation tile:
@@ -62,7 +63,7 @@ struct PeTc {
         __syncthreads();
         if (threadIdx.x == 0) {
             umma::fence_after_sync();
-            umma::gemm3<N, K>(tmem, s + A_HI, s + A_LO, s + w_hi, s + w_lo);
+            umma::gemm3<N, K>(tmem, a + A_HI, a + A_LO, w + w_hi, w + w_lo);
             umma::commit(bar);
         }
         umma::mbar_wait(bar, parity);
@@ -87,7 +88,7 @@ __device__ __forceinline__ void pe_fwd_tc(PeTc& tc, const float* __restrict__ w,
                                           float (&e)[32]) {
     const int tid = threadIdx.x;
     pe_l1(w, x0, x1, a1);
-    PeTc::A16::store_row(tc.s + PeTc::A_HI, tc.s + PeTc::A_LO, tid, a1);
+    PeTc::A16::store_row(tc.a + PeTc::A_HI, tc.a + PeTc::A_LO, tid, a1);
     tc.round<32, 16>(PeTc::W2_HI, PeTc::W2_LO);
     umma::ld32(tc.lane_addr(), a2);
 #pragma unroll
@@ -96,7 +97,7 @@ __device__ __forceinline__ void pe_fwd_tc(PeTc& tc, const float* __restrict__ w,
         a2[j] = fmaxf(a2[j] + b.x, 0.f); a2[j + 1] = fmaxf(a2[j + 1] + b.y, 0.f);
         a2[j + 2] = fmaxf(a2[j + 2] + b.z, 0.f); a2[j + 3] = fmaxf(a2[j + 3] + b.w, 0.f);
     }
-    PeTc::A32::store_row(tc.s + PeTc::A_HI, tc.s + PeTc::A_LO, tid, a2);
+    PeTc::A32::store_row(tc.a + PeTc::A_HI, tc.a + PeTc::A_LO, tid, a2);
     tc.round<32, 32>(PeTc::W3_HI, PeTc::W3_LO);
     umma::ld32(tc.lane_addr(), e);
 #pragma unroll
@@ -203,15 +204,15 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     __shared__ uint64_t s_bar;
     __shared__ uint32_t s_tslot;
     const int tid = threadIdx.x, b = blockIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
-    float* s_tc = smem;                       // [PeTc::FWD_FLOATS] tensor-core operand tiles
-    float* s_pe = s_tc + PeTc::FWD_FLOATS;    // [1648]
+    float* s_tc = smem;                       // tensor-core operand tiles: activations hi | lo, then weights
+    float* s_pe = s_tc + PeTc::A_FLOATS + PeTc::WFWD_FLOATS;    // [1648]
     float* s_enc = s_pe + PE_SIZE;            // [36]
     float* s_img = s_enc + 36;                // [n_fcnn][LC::SIZE]
     float* s_hb = s_img + n_fcnn * LC::SIZE;  // [n_fcnn][8]
     float* s_ll = s_hb + n_fcnn * H;          // [N]
     if (tid < 32) umma::tmem_alloc<32>(&s_tslot);
     if (tid == 0) umma::mbar_init(&s_bar, 1);
-    PeTc tc{s_tc, &s_bar, 0u, 0u};
+    PeTc tc{s_tc, s_tc + PeTc::A_FLOATS, &s_bar, 0u, 0u};
     tc.load_weights(pe, false);
     for (int e = tid; e < PE_SIZE; e += TP) s_pe[e] = pe[e];
     if (MODE == MODE_CNF) {
@@ -288,17 +289,21 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 }
 
 // ----------------------------------------------------------------------------------------------- backward
-// particle-encoder tile rows (row = feature, column = particle of the CTA batch; stride TSM, see mma_tile.cuh)
+// particle-encoder tile rows (row = feature, column = particle of the CTA batch; stride TSM, see mma_tile.cuh).
+// The weight gradients are contracted in two phases that reuse the same rows (half the tile: two CTAs per SM):
+//   phase A: delta3 x [a2 | 1]                      -> dW3, db3
+//   phase B: delta2 x [a1 | 1], delta1 x [x0 x1 1]  -> dW2, db2, dW1, db1
 struct PR {
-    static constexpr int ONE = 0, ZERO = 1, X = 2, A1 = 4, A2 = 20, D1 = 52, D2 = 68, D3 = 100, COUNT = 132;
+    static constexpr int ONE = 0, ZERO = 1;
+    static constexpr int D3 = 2, A2 = 34;                      // phase A
+    static constexpr int X = 2, A1 = 4, D1 = 20, D2 = 36;      // phase B
+    static constexpr int COUNT = 68;
 };
 
-// Particle-encoder weight gradients on the tensor path (3xTF32): every warp contracts over the 32 particles its own
-// threads staged and adds into ITS OWN accumulator copy accpe[PE_SIZE] (packed PE order) -- no CTA barrier.
-//   dW3 | db3 = delta3 (2 m-tiles) x [a2 (4 n-tiles) | 1];  dW2 | db2 = delta2 (2 m-tiles) x [a1 (2 n-tiles) | 1];
-//   dW1 | db1 = delta1 x [x0 x1 1].   rowsum3 (may be null): per-trajectory sum of delta3 (Gaussian mode: = -d enc).
-__device__ __forceinline__ void pe_weight_grads_mma(const float* __restrict__ s_tile, float* __restrict__ accpe,
-                                                    float* __restrict__ rowsum3) {
+// Particle-encoder weight gradients on the warp-level tensor path (3xTF32 mma.sync): every warp contracts over the 32
+// particles its own threads staged and adds into ITS OWN accumulator copy accpe[PE_SIZE] (packed PE order) -- no CTA barrier.
+// rowsum3 (may be null): per-trajectory sum of delta3 (Gaussian mode: = -d enc).
+__device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_tile, float* __restrict__ accpe, float* __restrict__ rowsum3) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int k0 = 32 * warp;
 #pragma unroll 1
@@ -317,6 +322,10 @@ __device__ __forceinline__ void pe_weight_grads_mma(const float* __restrict__ s_
             if (rowsum3) { rowsum3[o] += c[4][0]; rowsum3[o + 8] += c[4][2]; }
         }
     }
+}
+__device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_tile, float* __restrict__ accpe) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int k0 = 32 * warp;
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
         float c[3][4] = {};
@@ -347,21 +356,33 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                    const float* __restrict__ enc, const float* __restrict__ particles, int B, int N,
                    const float* __restrict__ g_lki, const int* __restrict__ argmax, float* __restrict__ d_particles,
                    float* __restrict__ d_enc, float* __restrict__ part_pe, float* __restrict__ part_cnf, const float* __restrict__ z_saved) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     __shared__ float s_red[33];
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_tslot;
     const int tid = threadIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
-    constexpr int TILE_FLOATS = (MODE == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT) * TSM;
-    float* s_pe = smem;
+    constexpr int TILE_ROWS = MODE == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT;
+    constexpr int TILE_FLOATS = ((TILE_ROWS * TSM > PeTc::A_FLOATS ? TILE_ROWS * TSM : PeTc::A_FLOATS) + 31) & ~31;   // keeps the weight tiles 128-byte aligned
+    // The tensor-core activation tile (hi | lo, 32 KB, at the region base) and the mma.sync gradient tile share the same
+    // memory: within a batch the four encoder rounds finish before the gradient tile is staged, and a CTA barrier
+    // separates the gradient contraction from the next batch's first activation store.
+    float* s_tile = smem;                                    // [TILE_FLOATS]  == PeTc activation tile
+    float* s_tcw = s_tile + TILE_FLOATS;                     // tensor-core weight tiles
+    float* s_pe = s_tcw + PeTc::WBWD_FLOATS;
     float* s_enc = s_pe + PE_SIZE;
     float* s_img = s_enc + 36;
     float* s_hb = s_img + n_fcnn * LC::SIZE;
-    float* s_tile = s_hb + n_fcnn * H;                       // PE tile [PR::COUNT][TSM]; the CNF tile [RC::TROWS][TSM] aliases it
     constexpr int NW = TP / 32;
     const int warp = tid >> 5;
-    float* s_accpe = s_tile + TILE_FLOATS;                   // [NW][1648]   one accumulator copy per warp
+    float* s_accpe = s_hb + n_fcnn * H;                      // [NW][1648]   one accumulator copy per warp
     float* s_acccnf = s_accpe + NW * PE_SIZE;                // [NW][n_fcnn][RC::NOUT]
     float* s_d1row = s_acccnf + NW * n_fcnn * RC::NOUT;      // [NW][n_fcnn][8] (unused sums; C_row = 0)
     float* s_denc = s_d1row + NW * n_fcnn * H + 4;           // [NW][32]
+    static_assert(TILE_FLOATS % 32 == 0, "weight tiles must stay 128-byte aligned");
+    if (tid < 32) umma::tmem_alloc<32>(&s_tslot);
+    if (tid == 0) umma::mbar_init(&s_bar, 1);
+    PeTc tc{s_tile, s_tcw, &s_bar, 0u, 0u};
+    tc.load_weights(pe, true);
     for (int e = tid; e < PE_SIZE; e += TP) {
         s_pe[e] = pe[e];
     }
@@ -372,7 +393,10 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         for (int e = tid; e < NW * n_fcnn * RC::NOUT; e += TP) s_acccnf[e] = 0.f;
         for (int e = tid; e < NW * n_fcnn * H; e += TP) s_d1row[e] = 0.f;
     }
+    umma::fence_before_sync();
     __syncthreads();
+    umma::fence_after_sync();
+    tc.tmem = s_tslot;
     if (MODE == MODE_CNF) hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -393,42 +417,20 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         __syncthreads();
         for (int n0 = 0; n0 < N; n0 += TP) {
             asm volatile("" ::: "memory");  // no LICM of shared-memory weight loads across particles
+            __syncthreads();                // the previous batch's gradient contraction is done with the tile (it aliases the activation tile)
             const int n = n0 + tid;
             const bool live = n < N;
             const size_t p = base + (live ? n : 0);
             const float2 x = *reinterpret_cast<const float2*>(particles + p * 2);
             float g = live ? g_lki[p] : 0.f;
             if (live && n == am) g -= gs;
-            float a1[16], a2[32], e[32], de[32], d2[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) d2[j] = 0.f;
+            float a1[16], a2[32], e[32], de[32];
+            pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);        // tensor-core rounds 1-2: layers 2 and 3 forward
             if (MODE == MODE_GAUSS) {
-                // layer 3 forward fused with its transposed backward: one pass over W3 (rolled: small code, half the LDS);
-                // delta3 goes straight into the tile (free here: the previous batch's mma phase ended with a barrier)
-                pe_fwd_l12(s_pe, x.x, x.y, a1, a2);
                 const float c = live ? g / (p1 * p1) : 0.f;
-#pragma unroll 4
-                for (int o = 0; o < 32; ++o) {
-                    float w[32];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W3 + o * 32 + j);
-                        w[j] = q.x; w[j + 1] = q.y; w[j + 2] = q.z; w[j + 3] = q.w;
-                    }
-                    float e0 = s_pe[PE_B3 + o], e1 = 0.f, e2 = 0.f, e3 = 0.f;   // four chains: the rolled loop has no other ILP
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        e0 = fmaf(w[j], a2[j], e0); e1 = fmaf(w[j + 1], a2[j + 1], e1);
-                        e2 = fmaf(w[j + 2], a2[j + 2], e2); e3 = fmaf(w[j + 3], a2[j + 3], e3);
-                    }
-                    const float eo = (e0 + e1) + (e2 + e3);
-                    const float deo = c * (s_enc[o] - eo - p0);
-                    s_tile[(PR::D3 + o) * TSM + tid] = deo;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) d2[j] = fmaf(w[j], deo, d2[j]);
-                }
+                for (int o = 0; o < 32; ++o) de[o] = c * (s_enc[o] - e[o] - p0);
             } else if (MODE == MODE_COS) {
-                pe_fwd(s_pe, x.x, x.y, a1, a2, e);
                 float ne = 0.f, dot = 0.f;
 #pragma unroll
                 for (int k = 0; k < 32; ++k) { ne = fmaf(e[k], e[k], ne); dot = fmaf(s_enc[k], e[k], dot); }
@@ -438,11 +440,10 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
                     const float ah = s_enc[k] / nenc, bh = e[k] / nrm;
-                    de[k] = c * (ah - ab * bh) / nrm;
+                    de[k] = live ? c * (ah - ab * bh) / nrm : 0.f;
                     denc[k] += c * (bh - ab * ah) / nenc;
                 }
             } else {
-                pe_fwd(s_pe, x.x, x.y, a1, a2, e);
                 float lo[16], up[16], glo[16], gup[16];
                 if (z_saved) {
                     const float4* zi = reinterpret_cast<const float4*>(z_saved + p * 32);
@@ -461,7 +462,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 #pragma unroll
                 for (int k = 0; k < 32; ++k) { de[k] = 0.f; s_tile[(RC::PC + k) * TSM + tid] = e[k]; }
                 s_tile[RC::ONE * TSM + tid] = 1.0f;
-                for (int r = RC::COUNT; r < RC::TROWS; ++r) s_tile[r * TSM + tid] = 0.0f;   // (the PE tile aliases these rows)
+                for (int r = RC::COUNT; r < RC::TROWS; ++r) s_tile[r * TSM + tid] = 0.0f;
                 swap_halves<16>(lo, up); swap_halves<16>(glo, gup);     // the last forward stage had c = upper
 #pragma unroll 1
                 for (int st = 2 * n_flows - 1; st >= 0; --st) {         // walk the forward stages back; one inlined stage body
@@ -475,58 +476,49 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                 if (live) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { denc[i] += glo[i]; denc[16 + i] += gup[i]; }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) de[k] = 0.f;
                 }
+                __syncthreads();            // every warp is done with the CRNVP tile before the activation tile is rewritten
             }
-            // particle-encoder backward (the clobber stops the compiler from keeping the forward's weight loads alive: 6 KB of spills)
-            asm volatile("" ::: "memory");
-            if (MODE != MODE_GAUSS) {
+            // encoder backward, tensor-core rounds 3-4: d a2 = W3^T delta3, d a1 = W2^T delta2
+            float d2[32], d1[16];
+            PeTc::A32::store_row(tc.a + PeTc::A_HI, tc.a + PeTc::A_LO, tid, de);
+            tc.round<32, 32>(PeTc::W3T_HI, PeTc::W3T_LO);
+            umma::ld32(tc.lane_addr(), d2);
 #pragma unroll
-            for (int o = 0; o < 32; ++o) {
-                if (!live) de[o] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W3 + o * 32 + j);
-                    d2[j] = fmaf(q.x, de[o], d2[j]); d2[j + 1] = fmaf(q.y, de[o], d2[j + 1]);
-                    d2[j + 2] = fmaf(q.z, de[o], d2[j + 2]); d2[j + 3] = fmaf(q.w, de[o], d2[j + 3]);
-                }
-            }
-            }
-            float d1[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) d1[k] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                d2[j] = a2[j] > 0.f ? d2[j] : 0.f;
-#pragma unroll
-                for (int k = 0; k < 16; k += 4) {
-                    const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W2 + j * 16 + k);
-                    d1[k] = fmaf(q.x, d2[j], d1[k]); d1[k + 1] = fmaf(q.y, d2[j], d1[k + 1]);
-                    d1[k + 2] = fmaf(q.z, d2[j], d1[k + 2]); d1[k + 3] = fmaf(q.w, d2[j], d1[k + 3]);
-                }
-            }
+            for (int j = 0; j < 32; ++j) d2[j] = a2[j] > 0.f ? d2[j] : 0.f;
+            PeTc::A32::store_row(tc.a + PeTc::A_HI, tc.a + PeTc::A_LO, tid, d2);
+            tc.round<16, 32>(PeTc::W2T_HI, PeTc::W2T_LO);
+            umma::ld16(tc.lane_addr(), d1);
             float dx0 = 0.f, dx1 = 0.f;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
+            for (int k = 0; k < 16; k += 2) {
+                const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W1 + 2 * k);
                 d1[k] = a1[k] > 0.f ? d1[k] : 0.f;
-                dx0 = fmaf(s_pe[PE_W1 + 2 * k], d1[k], dx0);
-                dx1 = fmaf(s_pe[PE_W1 + 2 * k + 1], d1[k], dx1);
+                d1[k + 1] = a1[k + 1] > 0.f ? d1[k + 1] : 0.f;
+                dx0 = fmaf(q.x, d1[k], dx0); dx1 = fmaf(q.y, d1[k], dx1);
+                dx0 = fmaf(q.z, d1[k + 1], dx0); dx1 = fmaf(q.w, d1[k + 1], dx1);
             }
             if (live) *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
-            // stage the PE tile (aliases the CNF tile: all CNF accumulation of this batch ended with a barrier)
+            // weight gradients: the warp contracts over its own 32 tile columns, no CTA barrier between the two phases
+            // (round 4 has completed for every thread that got here, so the activation tile is free to be overwritten)
             s_tile[PR::ONE * TSM + tid] = 1.0f;
             s_tile[PR::ZERO * TSM + tid] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s_tile[(PR::D3 + j) * TSM + tid] = de[j]; s_tile[(PR::A2 + j) * TSM + tid] = a2[j]; }
+            __syncwarp();
+            pe_weight_grads_a(s_tile, s_accpe + warp * PE_SIZE, MODE == MODE_GAUSS ? s_denc + warp * 32 : nullptr);
+            __syncwarp();
             s_tile[(PR::X + 0) * TSM + tid] = x.x;
             s_tile[(PR::X + 1) * TSM + tid] = x.y;
 #pragma unroll
             for (int k = 0; k < 16; ++k) { s_tile[(PR::A1 + k) * TSM + tid] = a1[k]; s_tile[(PR::D1 + k) * TSM + tid] = d1[k]; }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                s_tile[(PR::A2 + j) * TSM + tid] = a2[j];
-                s_tile[(PR::D2 + j) * TSM + tid] = d2[j];
-                if (MODE != MODE_GAUSS) s_tile[(PR::D3 + j) * TSM + tid] = de[j];
-            }
-            __syncwarp();   // the warp contracts over its own 32 tile columns: no CTA barrier in the batch loop
-            pe_weight_grads_mma(s_tile, s_accpe + warp * PE_SIZE, MODE == MODE_GAUSS ? s_denc + warp * 32 : nullptr);
+            for (int j = 0; j < 32; ++j) s_tile[(PR::D2 + j) * TSM + tid] = d2[j];
+            __syncwarp();
+            pe_weight_grads_b(s_tile, s_accpe + warp * PE_SIZE);
             __syncwarp();
         }
         // d_enc[b][k] = sum over the row's particles (deterministic: through the tile)
@@ -544,7 +536,9 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
             }
         }
     }
+    umma::fence_before_sync();
     __syncthreads();
+    if (tid < 32) umma::tmem_free<32>(tc.tmem);
     for (int e = tid; e < PE_SIZE; e += TP)
         part_pe[(size_t)blockIdx.x * PE_SIZE + e] = (s_accpe[e] + s_accpe[PE_SIZE + e]) + (s_accpe[2 * PE_SIZE + e] + s_accpe[3 * PE_SIZE + e]);
     if (MODE == MODE_CNF) {
@@ -560,14 +554,16 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 
 static size_t fwd_smem(int mode, int n_flows, int N) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    return ((size_t)PeTc::FWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + N) * sizeof(float);
+    return ((size_t)PeTc::A_FLOATS + PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + N) * sizeof(float);
 }
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    const size_t tile = (size_t)(mode == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT) * TSM;
+    size_t tile = (size_t)(mode == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT) * TSM;
+    if (tile < (size_t)PeTc::A_FLOATS) tile = PeTc::A_FLOATS;
+    tile = (tile + 31) & ~(size_t)31;
     const int nw = TP / 32;   // per-warp accumulator copies
-    size_t fl = (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + tile + (size_t)nw * PE_SIZE + (size_t)nw * n_fcnn * RC::NOUT +
-                (size_t)nw * n_fcnn * H + 4 + nw * 32;
+    size_t fl = tile + PeTc::WBWD_FLOATS + (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + (size_t)nw * PE_SIZE +
+                (size_t)nw * n_fcnn * RC::NOUT + (size_t)nw * n_fcnn * H + 4 + nw * 32;
     return fl * sizeof(float);
 }
 
