@@ -1,39 +1,48 @@
 // (K1, headline shape) Backward of the D = 2 coupling stack with row-constant context (nf_dyn: C = 4, cond_model: C = 36).
 //
-// The generic backward (coupling.cu) reduces weight gradients through a shared-memory tile and is LDS-bound
-// (2 shared loads per FMA).  Here every weight-gradient product is accumulated in REGISTERS: a CTA owns a
-// trajectory, each thread owns N/128 particles whose state (5 floats) sits in shared memory between stages, and for
-// one FCNN at a time the thread sweeps its particles accumulating the 97 hoisted-layout gradients
-//   dW1[:,x] (8), db1 = sum of layer-1 deltas (8, also drives the row-context columns), dW2 (64), db2 (8), dW3 (8), db3 (1)
-// in registers, then the CTA reduces them once per (trajectory chunk, FCNN): warp butterfly -> per-warp slots -> owner thread.
-// Activations are recomputed from the stage output (couplings are invertible), so nothing but y is read from HBM.
+// Every weight-gradient product is accumulated in REGISTERS (the generic backward of coupling.cu reduces them through a
+// shared-memory tile and is LDS-bound).  Layout of the work:
+//   * a persistent CTA keeps the state (lo, up, g_lo, g_up, g_logdet: 5 floats) of up to E_MAX "entries" (<= 1024 particles
+//     of one trajectory each) resident in shared memory and walks the stack STAGE-OUTER: all resident particles go through
+//     stage st before anybody starts stage st - 1.  A thread therefore keeps the 97 gradient accumulators of ONE net
+//       dW1[:,x] (8), db1 (8, per entry: it also drives the row-context columns), dW2 (64), db2 (8), dW3 (8), db3 (1)
+//     live across ~56 particles and the CTA-wide reduction (warp butterfly -> per-warp slots -> owner thread) runs once per
+//     (resident set, net) instead of once per (trajectory, net);
+//   * the two nets of a stage are split over the two halves of the CTA: threads 0-127 own the t-net, threads 128-255 the
+//     s-net, for the SAME particles.  Each half runs its net forward (activations recomputed from the stage output: couplings
+//     are invertible, nothing but y is read from HBM), the halves exchange t and s through shared memory (one barrier per
+//     128 particles), then each runs its net backward with the activations still in registers -- no activation stash.
 #include "coupling.cuh"
 
 namespace nfdpf {
 
 using L2_ = Lay<1, 0>;
 constexpr int NACC = 97;          // == Rows<1,0>::NOUT, same ordering as packed_offset<1,0>
-constexpr int TPD = 256;          // threads per CTA (8 warps walking the same code: one CTA per SM, instruction-cache friendly)
-constexpr int CHUNK_M = 4;        // particles per thread per chunk (chunk = 1024 particles)
-constexpr int CHUNK = CHUNK_M * TPD;
+constexpr int TPD = 256;          // threads per CTA: two net-groups of four warps, one CTA per SM
+constexpr int GRP = 128;          // threads per net-group == particles per iteration
+constexpr int CHUNK = 1024;       // particles per entry
 constexpr int NWARP = TPD / 32;
+constexpr int E_CAP = 9;          // upper bound of resident entries (the launcher fits E_MAX <= E_CAP into shared memory)
 
 struct D2Smem {
-    static size_t bytes(int n_fcnn, int C_row) {
-        size_t fl = (size_t)n_fcnn * L2_::SIZE + n_fcnn * H + (size_t)n_fcnn * H * C_row   // images, hb, w1r
-                    + 6 * (size_t)CHUNK                                                     // lo, up, glo, gup, gld, ds
-                    + 16 * (size_t)CHUNK                                                    // s-net activations (h1, h2) stash
-                    + NWARP * 100                                                            // per-warp reduction slots
-                    + (size_t)n_fcnn * NACC + n_fcnn * H + C_row + 4;
-        return fl * sizeof(float);
+    static size_t fixed_floats(int n_fcnn, int C_row) {
+        return (size_t)n_fcnn * L2_::SIZE + (size_t)n_fcnn * H * C_row        // images, w1r
+               + 6 * GRP                                                       // exchange: t, s, dc_t (double buffered)
+               + NWARP * 100                                                   // per-warp reduction slots
+               + (size_t)n_fcnn * NACC + 8;                                    // acc
     }
+    static size_t entry_floats(int n_fcnn, int C_row) {
+        return 5 * (size_t)CHUNK                                               // lo, up, glo, gup, gld
+               + 2 * (size_t)n_fcnn * H                                        // hb, d1row
+               + NWARP * H + C_row;                                            // per-warp b1 sums, ctx
+    }
+    static size_t bytes(int n_fcnn, int C_row, int e_max) { return (fixed_floats(n_fcnn, C_row) + e_max * entry_floats(n_fcnn, C_row)) * sizeof(float); }
 };
 
-// Reduce the 97 per-thread accumulators over the CTA and add them to s_acc[f] (and the b1 block to s_d1row[f]).
-// Warp level: transposed butterfly -- in round r the lanes with bit (16 >> r) set keep the upper half of the live
-// values and send the lower half (and vice versa), so 96 values cost 93 shuffles instead of 480; lane L ends up
-// owning the sums of entries 3L..3L+2.  Entry 96 (db3) takes a plain butterfly.
-__device__ __forceinline__ void reduce_flush(float (&acc)[NACC], float* s_part, float* s_acc_f, float* s_d1row_f) {
+// Warp-level transposed butterfly of the 97 per-thread accumulators: in round r the lanes with bit (16 >> r) set keep the
+// upper half of the live values and send the lower half (and vice versa), so 96 values cost 93 shuffles instead of 480;
+// lane L ends up owning the sums of entries 3L..3L+2.  Entry 96 (db3) takes a plain butterfly.  Result -> the warp's slot.
+__device__ __forceinline__ void warp_reduce_to_slot(float (&acc)[NACC], float* s_part) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #define NFDPF_ROUND(HALFN, OFF)                                                         \
     {                                                                                   \
@@ -52,16 +61,28 @@ __device__ __forceinline__ void reduce_flush(float (&acc)[NACC], float* s_part, 
     float* slot = s_part + warp * 100;
     slot[3 * lane] = acc[0]; slot[3 * lane + 1] = acc[1]; slot[3 * lane + 2] = acc[2];
     if (lane == 0) slot[96] = last;
-    __syncthreads();
-    if (threadIdx.x < NACC) {
-        const int k = threadIdx.x;
-        float v = 0.f;
+}
+
+// Warp sums of the 8 layer-1 delta accumulators of one entry -> d1part[warp][8]; the accumulators are cleared.
+__device__ __forceinline__ void warp_reduce_b1(float (&acc)[NACC], float* s_d1part_e) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float v[H];
 #pragma unroll
-        for (int w = 0; w < NWARP; ++w) v += s_part[w * 100 + k];
-        s_acc_f[k] += v;
-        if (k >= H && k < 2 * H) s_d1row_f[k - H] += v;
+    for (int k = 0; k < H; ++k) { v[k] = acc[H + k]; acc[H + k] = 0.f; }
+#define NFDPF_ROUND(HALFN, OFF)                                                         \
+    {                                                                                   \
+        const bool up_ = (lane & OFF) != 0;                                             \
+        _Pragma("unroll") for (int i = 0; i < HALFN; ++i) {                             \
+            const float keep = up_ ? v[i + HALFN] : v[i];                               \
+            const float send = up_ ? v[i] : v[i + HALFN];                               \
+            v[i] = keep + __shfl_xor_sync(FULL, send, OFF);                             \
+        }                                                                               \
     }
-    __syncthreads();
+    NFDPF_ROUND(4, 16) NFDPF_ROUND(2, 8) NFDPF_ROUND(1, 4)
+#undef NFDPF_ROUND
+    v[0] += __shfl_xor_sync(FULL, v[0], 2);
+    v[0] += __shfl_xor_sync(FULL, v[0], 1);
+    if ((lane & 3) == 0) s_d1part_e[warp * H + (lane >> 2)] = v[0];   // lane bits 4,3,2 select the entry index
 }
 
 __device__ __forceinline__ void accumulate(float (&acc)[NACC], const float (&d1)[H], const float (&d2)[H], float dout, float c,
@@ -78,122 +99,156 @@ __device__ __forceinline__ void accumulate(float (&acc)[NACC], const float (&d1)
     acc[4 * H + H * H] += dout;
 }
 
-// One stage (nets t = f_t, s = f_t + 1) for all particles of the chunk.  c/gc: conditioning half and its gradient;
-// v/gv: transformed half (output value on entry, input value on exit) and its gradient.  inv: the stage was run as
-// v_out = (v_in - t) e^{-s} (inverse direction) instead of v_out = t + v_in e^{s}.
-// Sweep 1: both nets forward (s-net activations stashed in shared memory), invert, t-net backward + gradient products.
-// Sweep 2: s-net backward from the stash.  Not inlined: ONE copy of this code serves all stages.
-__device__ __noinline__ void stage_bwd_d2(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s, int f_t, bool inv,
-                                          int m_count, int n_live, const float* s_c, float* s_gc, float* s_v, float* s_gv,
-                                          const float* s_gld, float* s_ds, float* s_stash, float* s_part, float* s_acc, float* s_d1row) {
-    const int tid = threadIdx.x;
-    float acc[NACC];
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-#pragma unroll 1
-    for (int m = 0; m < m_count; ++m) {
-        asm volatile("" ::: "memory");
-        const int q = m * TPD + tid;
-        const bool live = q < n_live;
-        const float c[1] = {s_c[q]};
-        float h1[H], h2[H], t[1], s[1];
-        fcnn_fwd<1, 0>(img_s, hb_s, c, nullptr, h1, h2, s);
-#pragma unroll
-        for (int k = 0; k < H; ++k) { s_stash[k * CHUNK + q] = h1[k]; s_stash[(H + k) * CHUNK + q] = h2[k]; }
-        fcnn_fwd<1, 0>(img_t, hb_t, c, nullptr, h1, h2, t);
-        const float v = s_v[q], gv = s_gv[q], gld = s_gld[q];
-        const float es = expf(s[0]), ies = expf(-s[0]);
-        float dt, ds, vin, gin;
-        if (!inv) { vin = (v - t[0]) * ies; dt = gv; ds = fmaf(gv * vin, es, gld); gin = gv * es; }
-        else      { gin = gv * ies; dt = -gin; ds = -fmaf(gv, v, gld); vin = fmaf(v, es, t[0]); }
-        if (!live) { dt = 0.f; ds = 0.f; }
-        s_v[q] = vin; s_gv[q] = gin; s_ds[q] = ds;
-        float d1[H], d2[H], dc[1] = {0.f};
-        const float dout[1] = {dt};
-        fcnn_bwd<1, 0>(img_t, dout, h1, h2, d1, d2, dc, nullptr);
-        s_gc[q] += dc[0];
-        accumulate(acc, d1, d2, dt, c[0], h1, h2);
-    }
-    reduce_flush(acc, s_part, s_acc + f_t * NACC, s_d1row + f_t * H);
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-#pragma unroll 1
-    for (int m = 0; m < m_count; ++m) {
-        asm volatile("" ::: "memory");
-        const int q = m * TPD + tid;
-        float h1[H], h2[H];
-#pragma unroll
-        for (int k = 0; k < H; ++k) { h1[k] = s_stash[k * CHUNK + q]; h2[k] = s_stash[(H + k) * CHUNK + q]; }
-        const float ds = s_ds[q];
-        float d1[H], d2[H], dc[1] = {0.f};
-        const float dout[1] = {ds};
-        fcnn_bwd<1, 0>(img_s, dout, h1, h2, d1, d2, dc, nullptr);
-        s_gc[q] += dc[0];
-        accumulate(acc, d1, d2, ds, s_c[q], h1, h2);
-    }
-    reduce_flush(acc, s_part, s_acc + (f_t + 1) * NACC, s_d1row + (f_t + 1) * H);
-}
-
 __global__ void __launch_bounds__(TPD)
 coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ y,
                        const float* __restrict__ row_ctx, int flags, int B, int N, const float* __restrict__ g_y,
-                       const float* __restrict__ g_ld, float* __restrict__ d_x, float* __restrict__ d_row_ctx,
-                       float* __restrict__ partials, float* __restrict__ d1rows) {
+                       const float* __restrict__ g_ld, float* __restrict__ d_x, float* __restrict__ partials,
+                       float* __restrict__ d1rows, int e_max) {
     extern __shared__ __align__(16) float smem[];
     const int n_fcnn = 4 * n_flows, tid = threadIdx.x, inverse = flags & 1;
+    const int grp = tid >> 7, gi = tid & (GRP - 1), warp = tid >> 5;
     float* s_img = smem;
-    float* s_hb = s_img + n_fcnn * L2_::SIZE;
-    float* s_w1r = s_hb + n_fcnn * H;
-    float* s_lo = s_w1r + (size_t)n_fcnn * H * C_row;
-    float* s_up = s_lo + CHUNK;
-    float* s_glo = s_up + CHUNK;
-    float* s_gup = s_glo + CHUNK;
-    float* s_gld = s_gup + CHUNK;
-    float* s_ds = s_gld + CHUNK;
-    float* s_stash = s_ds + CHUNK;
-    float* s_part = s_stash + 16 * CHUNK;
-    float* s_acc = s_part + NWARP * 100;
-    float* s_d1row = s_acc + n_fcnn * NACC;
-    float* s_ctx = s_d1row + n_fcnn * H;
+    float* s_w1r = s_img + n_fcnn * L2_::SIZE;
+    float* s_xt = s_w1r + (size_t)n_fcnn * H * C_row;        // [2][GRP] t-net outputs
+    float* s_xs = s_xt + 2 * GRP;                            // [2][GRP] s-net outputs
+    float* s_dct = s_xs + 2 * GRP;                           // [2][GRP] t-net gradient wrt the conditioning half
+    float* s_part = s_dct + 2 * GRP;                         // [NWARP][100]
+    float* s_acc = s_part + NWARP * 100;                     // [n_fcnn][NACC]
+    float* s_lo = s_acc + n_fcnn * NACC + 8;                 // state, [e_max][CHUNK] each
+    float* s_up = s_lo + (size_t)e_max * CHUNK;
+    float* s_glo = s_up + (size_t)e_max * CHUNK;
+    float* s_gup = s_glo + (size_t)e_max * CHUNK;
+    float* s_gld = s_gup + (size_t)e_max * CHUNK;
+    float* s_hb = s_gld + (size_t)e_max * CHUNK;             // [e_max][n_fcnn][H] hoisted layer-1 biases
+    float* s_d1row = s_hb + (size_t)e_max * n_fcnn * H;      // [e_max][n_fcnn][H] per-entry layer-1 delta sums
+    float* s_d1part = s_d1row + (size_t)e_max * n_fcnn * H;  // [e_max][NWARP][H]
+    float* s_ctx = s_d1part + (size_t)e_max * NWARP * H;     // [e_max][C_row]
     const int pf = packed_fcnn_size(1, C_row);
     for (int f = 0; f < n_fcnn; ++f)
         load_fcnn_image<1, 0>(packed + (size_t)f * pf, C_row, s_img + f * L2_::SIZE, s_w1r + (size_t)f * H * C_row, tid, TPD);
     for (int e = tid; e < n_fcnn * NACC; e += TPD) s_acc[e] = 0.f;
     __syncthreads();
 
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
-        for (int e = tid; e < C_row; e += TPD) s_ctx[e] = row_ctx[(size_t)b * C_row + e];
-        for (int e = tid; e < n_fcnn * H; e += TPD) s_d1row[e] = 0.f;
-        __syncthreads();
-        hoist_row_context_par<1, 0>(s_img, s_w1r, s_ctx, C_row, n_fcnn, s_hb);
-        __syncthreads();
-        for (int c0 = 0; c0 < N; c0 += CHUNK) {
+    const int nc = (N + CHUNK - 1) / CHUNK;                                    // entries per trajectory
+    const int n_traj = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_entries = n_traj * nc;
+    for (int e0 = 0; e0 < n_entries; e0 += e_max) {
+        const int ne = min(e_max, n_entries - e0);
+        // ---- load the resident set
+        for (int e = 0; e < ne; ++e) {
+            const int j = e0 + e, b = blockIdx.x + (j / nc) * gridDim.x, c0 = (j % nc) * CHUNK;
             const int n_live = min(CHUNK, N - c0);
-            const int m_count = (n_live + TPD - 1) / TPD;
             const size_t p0 = (size_t)b * N + c0;
-            for (int q = tid; q < m_count * TPD; q += TPD) {   // each thread touches only its own slots q = m*TPD + tid
+            for (int q = tid; q < CHUNK; q += TPD) {
                 const bool live = q < n_live;
                 const float2 yy = live ? reinterpret_cast<const float2*>(y)[p0 + q] : make_float2(0.f, 0.f);
                 const float2 gg = live && g_y ? reinterpret_cast<const float2*>(g_y)[p0 + q] : make_float2(0.f, 0.f);
-                s_lo[q] = yy.x; s_up[q] = yy.y; s_glo[q] = gg.x; s_gup[q] = gg.y;
-                s_gld[q] = live && g_ld ? ((flags & 2) ? -g_ld[p0 + q] : g_ld[p0 + q]) : 0.f;
+                const int o = e * CHUNK + q;
+                s_lo[o] = yy.x; s_up[o] = yy.y; s_glo[o] = gg.x; s_gup[o] = gg.y;
+                s_gld[o] = live && g_ld ? ((flags & 2) ? -g_ld[p0 + q] : g_ld[p0 + q]) : 0.f;
             }
-            // forward pass ran flows 0..n-1 (t1/s1 then t2/s2): walk back n-1..0 (t2/s2 then t1/s1);
-            // inverse pass ran flows n-1..0 (t2/s2 then t1/s1): walk back 0..n-1 (t1/s1 then t2/s2)
-#pragma unroll 1
-            for (int st = 0; st < 2 * n_flows; ++st) {
-                const int f = inverse ? st / 2 : n_flows - 1 - st / 2;
-                const int pair = inverse ? (st & 1) : 1 - (st & 1);       // 0: t1/s1 (c = lower), 1: t2/s2 (c = upper)
-                const float* im = s_img + (4 * f + 2 * pair) * L2_::SIZE;
-                const float* hb = s_hb + (4 * f + 2 * pair) * H;
-                stage_bwd_d2(im, im + L2_::SIZE, hb, hb + H, 4 * f + 2 * pair, inverse != 0, m_count, n_live, pair ? s_up : s_lo,
-                             pair ? s_gup : s_glo, pair ? s_lo : s_up, pair ? s_glo : s_gup, s_gld, s_ds, s_stash, s_part, s_acc, s_d1row);
-            }
-            for (int q = tid; q < n_live; q += TPD) reinterpret_cast<float2*>(d_x)[p0 + q] = make_float2(s_glo[q], s_gup[q]);
+            for (int c = tid; c < C_row; c += TPD) s_ctx[e * C_row + c] = row_ctx[(size_t)b * C_row + c];
         }
-        // per-trajectory layer-1 delta sums: the row-context columns of dW1 and d(row_ctx) are formed from them by
-        // rowctx_grad_kernel after this kernel (keeps the 8 x C_row outer products out of the persistent loop)
-        for (int e = tid; e < n_fcnn * H; e += TPD) d1rows[(size_t)e * B + b] = TANH_SCALE * s_d1row[e];   // true delta sums, [f*8+k][b]: coalesced for rowctx_grad
+        __syncthreads();
+        for (int e = 0; e < ne; ++e) hoist_row_context_par<1, 0>(s_img, s_w1r, s_ctx + e * C_row, C_row, n_fcnn, s_hb + (size_t)e * n_fcnn * H);
+        __syncthreads();
+        // forward pass ran flows 0..n-1 (t1/s1 then t2/s2): walk back n-1..0 (t2/s2 then t1/s1);
+        // inverse pass ran flows n-1..0 (t2/s2 then t1/s1): walk back 0..n-1 (t1/s1 then t2/s2)
+#pragma unroll 1
+        for (int st = 0; st < 2 * n_flows; ++st) {
+            const int f = inverse ? st / 2 : n_flows - 1 - st / 2;
+            const int pair = inverse ? (st & 1) : 1 - (st & 1);       // 0: t1/s1 (c = lower), 1: t2/s2 (c = upper)
+            const int fm = 4 * f + 2 * pair + grp;                    // the net this half of the CTA owns
+            const float* img = s_img + fm * L2_::SIZE;
+            const float* s_c = pair ? s_up : s_lo;                    // conditioning half and its gradient
+            float* s_gc = pair ? s_gup : s_glo;
+            float* s_v = pair ? s_lo : s_up;                          // transformed half (output value -> input value) and its gradient
+            float* s_gv = pair ? s_glo : s_gup;
+            float acc[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+            int it = 0, prev_q = -1;
+#pragma unroll 1
+            for (int e = 0; e < ne; ++e) {
+                const int j = e0 + e, c0 = (j % nc) * CHUNK;
+                const int n_live = min(CHUNK, N - c0), iters = (n_live + GRP - 1) / GRP;
+                const float* hb = s_hb + ((size_t)e * n_fcnn + fm) * H;
+#pragma unroll 1
+                for (int m = 0; m < iters; ++m, ++it) {
+                    asm volatile("" ::: "memory");
+                    const int q = e * CHUNK + m * GRP + gi, par = (it & 1) * GRP;
+                    const bool live = m * GRP + gi < n_live;
+                    const float c[1] = {s_c[q]};
+                    float h1[H], h2[H], out[1];
+                    fcnn_fwd<1, 0>(img, hb, c, nullptr, h1, h2, out);
+                    float gv_old = 0.f;
+                    if (grp == 0) { s_xt[par + gi] = out[0]; gv_old = s_gv[q]; }
+                    else          { s_xs[par + gi] = out[0]; }
+                    __syncthreads();
+                    float d1[H], d2[H], dc[1] = {0.f};
+                    if (grp == 0) {         // t-net: d t = g_v (forward direction) or -g_v e^{-s} (inverse direction)
+                        float dt = inverse ? -gv_old * expf(-s_xs[par + gi]) : gv_old;
+                        if (!live) dt = 0.f;
+                        const float dout[1] = {dt};
+                        fcnn_bwd<1, 0>(img, dout, h1, h2, d1, d2, dc, nullptr);
+                        s_dct[par + gi] = dc[0];
+                        accumulate(acc, d1, d2, dt, c[0], h1, h2);
+                    } else {                // s-net: inverts the stage, owns the state update
+                        if (prev_q >= 0) s_gc[prev_q] += s_dct[(GRP - par) + gi];    // t-net share of the previous iteration
+                        const float t = s_xt[par + gi], s = out[0];
+                        const float v = s_v[q], gv = s_gv[q], gld = s_gld[q];
+                        const float es = expf(s), ies = expf(-s);
+                        float ds, vin, gin;
+                        if (!inverse) { vin = (v - t) * ies; ds = fmaf(gv * vin, es, gld); gin = gv * es; }
+                        else          { gin = gv * ies; ds = -fmaf(gv, v, gld); vin = fmaf(v, es, t); }
+                        if (!live) ds = 0.f;
+                        s_v[q] = vin; s_gv[q] = gin;
+                        const float dout[1] = {ds};
+                        fcnn_bwd<1, 0>(img, dout, h1, h2, d1, d2, dc, nullptr);
+                        s_gc[q] += dc[0];
+                        prev_q = q;
+                        accumulate(acc, d1, d2, ds, c[0], h1, h2);
+                    }
+                }
+                warp_reduce_b1(acc, s_d1part + (size_t)e * NWARP * H);
+            }
+            warp_reduce_to_slot(acc, s_part);
+            __syncthreads();
+            if (grp == 1 && prev_q >= 0) s_gc[prev_q] += s_dct[((it - 1) & 1) * GRP + gi];
+            if (gi < NACC) {               // owner thread per parameter of the group's net: fixed-order sums
+                const int k = gi;
+                float v = 0.f;
+                if (k >= H && k < 2 * H) {     // b1 block: per-entry sums (row-context hoist) and their total
+                    for (int e = 0; e < ne; ++e) {
+                        const float* dp = s_d1part + ((size_t)e * NWARP + 4 * grp) * H + (k - H);
+                        const float r = (dp[0] + dp[H]) + (dp[2 * H] + dp[3 * H]);
+                        s_d1row[((size_t)e * n_fcnn + fm) * H + (k - H)] = r;
+                        v += r;
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) v += s_part[(4 * grp + w) * 100 + k];
+                }
+                s_acc[fm * NACC + k] += v;
+            }
+            __syncthreads();
+        }
+        // ---- store d_x and the per-trajectory layer-1 delta sums (the row-context columns of dW1 and d(row_ctx) are formed
+        // from them by rowctx_grad_kernel: keeps the 8 x C_row outer products out of the persistent loop)
+        for (int e = 0; e < ne; ++e) {
+            const int j = e0 + e, b = blockIdx.x + (j / nc) * gridDim.x, c0 = (j % nc) * CHUNK;
+            const int n_live = min(CHUNK, N - c0);
+            const size_t p0 = (size_t)b * N + c0;
+            for (int q = tid; q < n_live; q += TPD) reinterpret_cast<float2*>(d_x)[p0 + q] = make_float2(s_glo[e * CHUNK + q], s_gup[e * CHUNK + q]);
+        }
+        if (tid < n_fcnn * H) {            // one thread per (net, k): entries in order (chunks of one trajectory add up)
+            for (int e = 0; e < ne; ++e) {
+                const int j = e0 + e, b = blockIdx.x + (j / nc) * gridDim.x, c0 = (j % nc) * CHUNK;
+                const float val = TANH_SCALE * s_d1row[(size_t)e * n_fcnn * H + tid];   // true delta sums, [f*8+k][b]: coalesced for rowctx_grad
+                float* dst = d1rows + (size_t)tid * B + b;
+                *dst = c0 == 0 ? val : *dst + val;
+            }
+        }
         __syncthreads();
     }
     float* out = partials + (size_t)blockIdx.x * n_fcnn * pf;
@@ -233,13 +288,18 @@ int launch_coupling_bwd_d2(const float* packed, int n_flows, int C_row, const fl
                            const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* d_packed, void* workspace,
                            cudaStream_t st) {
     const int n_fcnn = 4 * n_flows;
-    const size_t smem = D2Smem::bytes(n_fcnn, C_row);
-    if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(coupling_bwd_d2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = min(B, sm_count());   // one 8-warp CTA per SM (registers), persistent over trajectories
+    // resident entries: as many as the CTA's share of the work needs, bounded by shared memory
+    const int nc = (N + CHUNK - 1) / CHUNK, need = ((B + grid - 1) / grid) * nc;
+    int e_max = min(E_CAP, need);
+    while (e_max > 1 && D2Smem::bytes(n_fcnn, C_row, e_max) > 220 * 1024) --e_max;
+    const size_t smem = D2Smem::bytes(n_fcnn, C_row, e_max);
+    if (smem > 220 * 1024) { set_error("coupling_bwd_d2: stack too large for shared memory (n_flows=%d, C_row=%d)", n_flows, C_row); return NFDPF_ERR_UNSUPPORTED; }
+    if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(coupling_bwd_d2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int n_params = n_fcnn * packed_fcnn_size(1, C_row);
     float* d1rows = (float*)workspace + (size_t)bwd_grid(B) * n_params;
-    coupling_bwd_d2_kernel<<<grid, TPD, smem, st>>>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx,
-                                                    (float*)workspace, d1rows);
+    coupling_bwd_d2_kernel<<<grid, TPD, smem, st>>>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, (float*)workspace,
+                                                    d1rows, e_max);
     int rc = check_launch("coupling_bwd_d2");
     if (rc) return rc;
     rc = launch_reduce_partials((const float*)workspace, grid, n_params, d_packed, st);
