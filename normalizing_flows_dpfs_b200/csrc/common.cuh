@@ -100,6 +100,18 @@ __device__ __forceinline__ float tanh_prescaled(float a) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
     return fmaf(-2.0f, r, 1.0f);
 }
+// Two tanh for three MUFU ops instead of four: one reciprocal of the product (t_a + 1)(t_b + 1) serves both,
+// 1 / u = v r, 1 / v = u r.  The arguments are clamped at 60 (tanh is exactly 1.0f from 2^a ~ 2^25 on) so the product
+// stays below 2^121.  Costs four more FP32/ALU instructions per pair: used by the SFU-bound forward kernels only.
+__device__ __forceinline__ void tanh_prescaled_pair(float a, float b, float& ta, float& tb) {
+    float ea, eb, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ea) : "f"(fminf(a, 60.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(fminf(b, 60.0f)));
+    const float u = ea + 1.0f, v = eb + 1.0f;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u * v));
+    ta = fmaf(-2.0f * v, r, 1.0f);
+    tb = fmaf(-2.0f * u, r, 1.0f);
+}
 __device__ __forceinline__ float exp_acc(float x) { return __expf(x); }  // ex2.approx(x*log2e): 2 ulp + range error
 
 }  // namespace nfdpf

@@ -81,7 +81,8 @@ __device__ __forceinline__ void ld8(const float* p, float (&w)[8]) {
 }
 
 // FCNN forward.  hb = hoisted layer-1 bias (b1 + row-context contribution).  Keeps h1/h2 for the backward.
-template <int HALF, int CP>
+// PAIRED: activations through tanh_prescaled_pair (3 MUFU per two tanh; the forward-only kernels are SFU-bound).
+template <int HALF, int CP, bool PAIRED = false>
 __device__ __forceinline__ void fcnn_fwd(const float* __restrict__ img, const float* __restrict__ hb, const float (&c)[HALF],
                                          const float* pc, float (&h1)[H], float (&h2)[H], float (&out)[HALF]) {
     using L = Lay<HALF, CP>;
@@ -104,7 +105,11 @@ __device__ __forceinline__ void fcnn_fwd(const float* __restrict__ img, const fl
             if (i + 2 < L::IN1) a = fmaf(w4.z, in[i + 2 < L::IN1 ? i + 2 : 0], a);
             if (i + 3 < L::IN1) a = fmaf(w4.w, in[i + 3 < L::IN1 ? i + 3 : 0], a);
         }
-        h1[k] = tanh_prescaled(a);
+        h1[k] = PAIRED ? a : tanh_prescaled(a);
+    }
+    if (PAIRED) {
+#pragma unroll
+        for (int k = 0; k < H; k += 2) tanh_prescaled_pair(h1[k], h1[k + 1], h1[k], h1[k + 1]);
     }
     float b2[8];
     ld8(img + L::B2, b2);
@@ -115,7 +120,11 @@ __device__ __forceinline__ void fcnn_fwd(const float* __restrict__ img, const fl
         float a = b2[j];
 #pragma unroll
         for (int k = 0; k < H; ++k) a = fmaf(w[k], h1[k], a);
-        h2[j] = tanh_prescaled(a);
+        h2[j] = PAIRED ? a : tanh_prescaled(a);
+    }
+    if (PAIRED) {
+#pragma unroll
+        for (int j = 0; j < H; j += 2) tanh_prescaled_pair(h2[j], h2[j + 1], h2[j], h2[j + 1]);
     }
 #pragma unroll
     for (int o = 0; o < HALF; ++o) {
@@ -207,16 +216,88 @@ __device__ void hoist_row_context_par(const float* __restrict__ imgs, const floa
 }
 
 // One coupling stage, forward evaluation.  inv = false: v = t(c) + v*exp(s(c)); inv = true: v = (v - t(c))*exp(-s(c)).
-template <int HALF, int CP>
+template <int HALF, int CP, bool PAIRED = false>
 __device__ __forceinline__ void stage_fwd(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s, bool inv,
                                           const float (&c)[HALF], const float* pc, float (&v)[HALF], float& ld) {
     float h1[H], h2[H], t[HALF], s[HALF];
-    fcnn_fwd<HALF, CP>(img_t, hb_t, c, pc, h1, h2, t);
-    fcnn_fwd<HALF, CP>(img_s, hb_s, c, pc, h1, h2, s);
+    fcnn_fwd<HALF, CP, PAIRED>(img_t, hb_t, c, pc, h1, h2, t);
+    fcnn_fwd<HALF, CP, PAIRED>(img_s, hb_s, c, pc, h1, h2, s);
 #pragma unroll
     for (int i = 0; i < HALF; ++i) {
         if (!inv) { v[i] = fmaf(v[i], expf(s[i]), t[i]); ld += s[i]; }
         else      { v[i] = (v[i] - t[i]) * expf(-s[i]); ld -= s[i]; }
+    }
+}
+
+// FCNN forward for TWO particles at once (narrow stacks, HALF <= 2): every weight is loaded from shared memory once and
+// used twice, which halves the LDS traffic (LDS and MUFU share the MIO queue the forward kernel stalls on) and doubles the
+// independent work per thread.  PAIRED pairs the two particles' activations in tanh_prescaled_pair.
+template <int HALF, int CP, bool PAIRED>
+__device__ __forceinline__ void fcnn_fwd_x2(const float* __restrict__ img, const float* __restrict__ hb, const float (&c)[2][HALF],
+                                            const float (&pc)[2][CP > 0 ? CP : 1], float (&out)[2][HALF]) {
+    using L = Lay<HALF, CP>;
+    float hbv[8];
+    ld8(hb, hbv);
+    float in[2][L::IN1], h1[2][H], h2[2][H];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) in[q][i] = c[q][i];
+#pragma unroll
+        for (int i = 0; i < CP; ++i) in[q][HALF + i] = pc[q][i];
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        float a0 = hbv[k], a1 = hbv[k];
+        const float* w = img + L::W1 + k * L::S1;
+#pragma unroll
+        for (int i = 0; i < L::S1; i += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(w + i);
+            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (i + u < L::IN1) { a0 = fmaf(wv[u], in[0][i + u < L::IN1 ? i + u : 0], a0); a1 = fmaf(wv[u], in[1][i + u < L::IN1 ? i + u : 0], a1); }
+        }
+        if (PAIRED) tanh_prescaled_pair(a0, a1, h1[0][k], h1[1][k]);
+        else { h1[0][k] = tanh_prescaled(a0); h1[1][k] = tanh_prescaled(a1); }
+    }
+    float b2[8];
+    ld8(img + L::B2, b2);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float w[8];
+        ld8(img + L::W2 + j * H, w);
+        float a0 = b2[j], a1 = b2[j];
+#pragma unroll
+        for (int k = 0; k < H; ++k) { a0 = fmaf(w[k], h1[0][k], a0); a1 = fmaf(w[k], h1[1][k], a1); }
+        if (PAIRED) tanh_prescaled_pair(a0, a1, h2[0][j], h2[1][j]);
+        else { h2[0][j] = tanh_prescaled(a0); h2[1][j] = tanh_prescaled(a1); }
+    }
+#pragma unroll
+    for (int o = 0; o < HALF; ++o) {
+        float w[8];
+        ld8(img + L::W3 + o * H, w);
+        float a0 = img[L::B3 + o], a1 = a0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) { a0 = fmaf(w[j], h2[0][j], a0); a1 = fmaf(w[j], h2[1][j], a1); }
+        out[0][o] = a0; out[1][o] = a1;
+    }
+}
+
+template <int HALF, int CP, bool PAIRED>
+__device__ __forceinline__ void stage_fwd_x2(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s, bool inv,
+                                             const float (&c)[2][HALF], const float (&pc)[2][CP > 0 ? CP : 1], float (&v)[2][HALF],
+                                             float (&ld)[2]) {
+    float t[2][HALF], s[2][HALF];
+    fcnn_fwd_x2<HALF, CP, PAIRED>(img_t, hb_t, c, pc, t);
+    fcnn_fwd_x2<HALF, CP, PAIRED>(img_s, hb_s, c, pc, s);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int i = 0; i < HALF; ++i) {
+            if (!inv) { v[q][i] = fmaf(v[q][i], expf(s[q][i]), t[q][i]); ld[q] += s[q][i]; }
+            else      { v[q][i] = (v[q][i] - t[q][i]) * expf(-s[q][i]); ld[q] -= s[q][i]; }
+        }
     }
 }
 

@@ -139,6 +139,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
             const int j = e0 + e, b = blockIdx.x + (j / nc) * gridDim.x, c0 = (j % nc) * CHUNK;
             const int n_live = min(CHUNK, N - c0);
             const size_t p0 = (size_t)b * N + c0;
+#pragma unroll                    // CHUNK / TPD = 4 independent iterations: all twelve loads in flight before the first store
             for (int q = tid; q < CHUNK; q += TPD) {
                 const bool live = q < n_live;
                 const float2 yy = live ? reinterpret_cast<const float2*>(y)[p0 + q] : make_float2(0.f, 0.f);

@@ -293,6 +293,21 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 // The weight gradients are contracted in two phases that reuse the same rows (half the tile: two CTAs per SM):
 //   phase A: delta3 x [a2 | 1]                      -> dW3, db3
 //   phase B: delta2 x [a1 | 1], delta1 x [x0 x1 1]  -> dW2, db2, dW1, db1
+// per-warp accumulator copy: row strides 40 / 24 (instead of 32 / 16) spread the eight fragment rows a warp adds into at
+// once over all banks (LDS.64 / STS.64 at the two-wavefront minimum)
+struct AC {
+    static constexpr int W3S = 40, W2S = 24;
+    static constexpr int W3 = 0, B3 = W3 + 32 * W3S, W2 = B3 + 32, B2 = W2 + 32 * W2S, W1 = B2 + 32, B1 = W1 + 32, SIZE = B1 + 16;
+    // accumulator index of packed particle-encoder parameter e
+    __device__ static int of_packed(int e) {
+        if (e < PE_B1) return W1 + e;
+        if (e < PE_W2) return B1 + (e - PE_B1);
+        if (e < PE_B2) return W2 + ((e - PE_W2) >> 4) * W2S + ((e - PE_W2) & 15);
+        if (e < PE_W3) return B2 + (e - PE_B2);
+        if (e < PE_B3) return W3 + ((e - PE_W3) >> 5) * W3S + ((e - PE_W3) & 31);
+        return B3 + (e - PE_B3);
+    }
+};
 struct PR {
     static constexpr int ONE = 0, ZERO = 1;
     static constexpr int D3 = 2, A2 = 34;                      // phase A
@@ -314,11 +329,11 @@ __device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_ti
         const int o = 16 * mt + g;
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
-            float* w = accpe + PE_W3 + o * 32 + 8 * n + 2 * t;
-            w[0] += c[n][0]; w[1] += c[n][1]; w[8 * 32] += c[n][2]; w[8 * 32 + 1] += c[n][3];
+            float* w = accpe + AC::W3 + o * AC::W3S + 8 * n + 2 * t;
+            w[0] += c[n][0]; w[1] += c[n][1]; w[8 * AC::W3S] += c[n][2]; w[8 * AC::W3S + 1] += c[n][3];
         }
         if (t == 0) {
-            accpe[PE_B3 + o] += c[4][0]; accpe[PE_B3 + o + 8] += c[4][2];
+            accpe[AC::B3 + o] += c[4][0]; accpe[AC::B3 + o + 8] += c[4][2];
             if (rowsum3) { rowsum3[o] += c[4][0]; rowsum3[o + 8] += c[4][2]; }
         }
     }
@@ -334,19 +349,19 @@ __device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_ti
         const int o = 16 * mt + g;
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
-            float* w = accpe + PE_W2 + o * 16 + 8 * n + 2 * t;
-            w[0] += c[n][0]; w[1] += c[n][1]; w[8 * 16] += c[n][2]; w[8 * 16 + 1] += c[n][3];
+            float* w = accpe + AC::W2 + o * AC::W2S + 8 * n + 2 * t;
+            w[0] += c[n][0]; w[1] += c[n][1]; w[8 * AC::W2S] += c[n][2]; w[8 * AC::W2S + 1] += c[n][3];
         }
-        if (t == 0) { accpe[PE_B2 + o] += c[2][0]; accpe[PE_B2 + o + 8] += c[2][2]; }
+        if (t == 0) { accpe[AC::B2 + o] += c[2][0]; accpe[AC::B2 + o + 8] += c[2][2]; }
     }
     float c1[1][4] = {};
     const int rowX[1] = {g < 2 ? PR::X + g : (g == 2 ? PR::ONE : PR::ZERO)};
     mma_outer<1>(s_tile, PR::D1, rowX, k0, k0 + 32, c1);
     if (t == 0) {          // columns 0,1 = dW1[o][0..1]
-        accpe[PE_W1 + 2 * g] += c1[0][0]; accpe[PE_W1 + 2 * g + 1] += c1[0][1];
-        accpe[PE_W1 + 2 * (g + 8)] += c1[0][2]; accpe[PE_W1 + 2 * (g + 8) + 1] += c1[0][3];
+        accpe[AC::W1 + 2 * g] += c1[0][0]; accpe[AC::W1 + 2 * g + 1] += c1[0][1];
+        accpe[AC::W1 + 2 * (g + 8)] += c1[0][2]; accpe[AC::W1 + 2 * (g + 8) + 1] += c1[0][3];
     } else if (t == 1) {   // column 2 = db1[o]
-        accpe[PE_B1 + g] += c1[0][0]; accpe[PE_B1 + g + 8] += c1[0][2];
+        accpe[AC::B1 + g] += c1[0][0]; accpe[AC::B1 + g + 8] += c1[0][2];
     }
 }
 
@@ -374,8 +389,8 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     float* s_hb = s_img + n_fcnn * LC::SIZE;
     constexpr int NW = TP / 32;
     const int warp = tid >> 5;
-    float* s_accpe = s_hb + n_fcnn * H;                      // [NW][1648]   one accumulator copy per warp
-    float* s_acccnf = s_accpe + NW * PE_SIZE;                // [NW][n_fcnn][RC::NOUT]
+    float* s_accpe = s_hb + n_fcnn * H;                      // [NW][AC::SIZE]   one accumulator copy per warp
+    float* s_acccnf = s_accpe + NW * AC::SIZE;                // [NW][n_fcnn][RC::NOUT]
     float* s_d1row = s_acccnf + NW * n_fcnn * RC::NOUT;      // [NW][n_fcnn][8] (unused sums; C_row = 0)
     float* s_denc = s_d1row + NW * n_fcnn * H + 4;           // [NW][32]
     static_assert(TILE_FLOATS % 32 == 0, "weight tiles must stay 128-byte aligned");
@@ -386,7 +401,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     for (int e = tid; e < PE_SIZE; e += TP) {
         s_pe[e] = pe[e];
     }
-    for (int e = tid; e < NW * PE_SIZE; e += TP) s_accpe[e] = 0.f;
+    for (int e = tid; e < NW * AC::SIZE; e += TP) s_accpe[e] = 0.f;
     if (MODE == MODE_CNF) {
         const int pf = packed_fcnn_size(16, 32);
         for (int f = 0; f < n_fcnn; ++f) load_fcnn_image<16, 32>(cnf + (size_t)f * pf, 0, s_img + f * LC::SIZE, nullptr, tid, TP);
@@ -509,7 +524,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 #pragma unroll
             for (int j = 0; j < 32; ++j) { s_tile[(PR::D3 + j) * TSM + tid] = de[j]; s_tile[(PR::A2 + j) * TSM + tid] = a2[j]; }
             __syncwarp();
-            pe_weight_grads_a(s_tile, s_accpe + warp * PE_SIZE, MODE == MODE_GAUSS ? s_denc + warp * 32 : nullptr);
+            pe_weight_grads_a(s_tile, s_accpe + warp * AC::SIZE, MODE == MODE_GAUSS ? s_denc + warp * 32 : nullptr);
             __syncwarp();
             s_tile[(PR::X + 0) * TSM + tid] = x.x;
             s_tile[(PR::X + 1) * TSM + tid] = x.y;
@@ -518,7 +533,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 #pragma unroll
             for (int j = 0; j < 32; ++j) s_tile[(PR::D2 + j) * TSM + tid] = d2[j];
             __syncwarp();
-            pe_weight_grads_b(s_tile, s_accpe + warp * PE_SIZE);
+            pe_weight_grads_b(s_tile, s_accpe + warp * AC::SIZE);
             __syncwarp();
         }
         // d_enc[b][k] = sum over the row's particles (deterministic: through the tile)
@@ -539,8 +554,10 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     umma::fence_before_sync();
     __syncthreads();
     if (tid < 32) umma::tmem_free<32>(tc.tmem);
-    for (int e = tid; e < PE_SIZE; e += TP)
-        part_pe[(size_t)blockIdx.x * PE_SIZE + e] = (s_accpe[e] + s_accpe[PE_SIZE + e]) + (s_accpe[2 * PE_SIZE + e] + s_accpe[3 * PE_SIZE + e]);
+    for (int e = tid; e < PE_SIZE; e += TP) {
+        const float* a = s_accpe + AC::of_packed(e);
+        part_pe[(size_t)blockIdx.x * PE_SIZE + e] = (a[0] + a[AC::SIZE]) + (a[2 * AC::SIZE] + a[3 * AC::SIZE]);
+    }
     if (MODE == MODE_CNF) {
         const int pf = packed_fcnn_size(16, 32);
         float* out = part_cnf + (size_t)blockIdx.x * n_fcnn * pf;
@@ -562,7 +579,7 @@ static size_t bwd_smem(int mode, int n_flows) {
     if (tile < (size_t)PeTc::A_FLOATS) tile = PeTc::A_FLOATS;
     tile = (tile + 31) & ~(size_t)31;
     const int nw = TP / 32;   // per-warp accumulator copies
-    size_t fl = tile + PeTc::WBWD_FLOATS + (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + (size_t)nw * PE_SIZE +
+    size_t fl = tile + PeTc::WBWD_FLOATS + (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + (size_t)nw * AC::SIZE +
                 (size_t)nw * n_fcnn * RC::NOUT + (size_t)nw * n_fcnn * H + 4 + nw * 32;
     return fl * sizeof(float);
 }

@@ -1,7 +1,7 @@
 // Weight-gradient contractions on the (legacy, warp-level) tensor path: dW[o][i] = sum_p delta[p][o] * act[p][i].
 // K = particles is the long dimension; the deltas / activations of the CTA's batch sit transposed in a shared-memory
 // tile (row = feature, column = particle).  mma.sync.m16n8k8 TF32 with the 3xTF32 split (hi*hi + hi*lo + lo*hi) keeps
-// ~2^-21 relative accuracy, which the rtol 1e-4 gradient bar needs (plain TF32 is 2^-11).  These contractions are the
+// ~2^-20 relative accuracy, which the rtol 1e-4 gradient bar needs (plain TF32 is 2^-11).  These contractions are the
 // only "dense" GEMMs on the path (M,N <= 48); tcgen05 tiles (M >= 64) would be >85 % padding here.
 #pragma once
 #include "common.cuh"
@@ -10,10 +10,13 @@ namespace nfdpf {
 
 constexpr int TSM = 132;  // tile row stride in floats: == 4 (mod 32) makes the m16n8k8 fragment loads conflict-free
 
+// hi = x with the 13 low mantissa bits cleared, lo = the (exact) remainder cut to TF32 the same way: both are valid TF32
+// bit patterns, |lo| < 2^-10 |x|, and what is dropped is < 2^-20 |x|.  Three instructions (LOP3, FADD, LOP3);
+// cvt.rna.tf32.f32 is emulated on sm_100a (VIADD + FSETP + SEL + LOP3 per conversion: nine for the pair) and the split is
+// done once per fragment element, i.e. it used to be almost half of the instructions of the gradient kernels.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
 }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
