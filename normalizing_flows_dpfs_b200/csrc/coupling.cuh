@@ -295,8 +295,8 @@ __device__ __forceinline__ void stage_fwd_x2(const float* img_t, const float* im
     for (int q = 0; q < 2; ++q) {
 #pragma unroll
         for (int i = 0; i < HALF; ++i) {
-            if (!inv) { v[q][i] = fmaf(v[q][i], expf(s[q][i]), t[q][i]); ld[q] += s[q][i]; }
-            else      { v[q][i] = (v[q][i] - t[q][i]) * expf(-s[q][i]); ld[q] -= s[q][i]; }
+            if (!inv) { v[q][i] = fmaf(v[q][i], exp_acc(s[q][i]), t[q][i]); ld[q] += s[q][i]; }
+            else      { v[q][i] = (v[q][i] - t[q][i]) * exp_acc(-s[q][i]); ld[q] -= s[q][i]; }
         }
     }
 }

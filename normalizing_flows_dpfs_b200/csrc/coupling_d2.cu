@@ -181,14 +181,14 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
                     const bool live = m * GRP + gi < n_live;
                     const float c[1] = {s_c[q]};
                     float h1[H], h2[H], out[1];
-                    fcnn_fwd<1, 0>(img, hb, c, nullptr, h1, h2, out);
+                    fcnn_fwd<1, 0, true>(img, hb, c, nullptr, h1, h2, out);
                     float gv_old = 0.f;
                     if (grp == 0) { s_xt[par + gi] = out[0]; gv_old = s_gv[q]; }
                     else          { s_xs[par + gi] = out[0]; }
                     __syncthreads();
                     float d1[H], d2[H], dc[1] = {0.f};
                     if (grp == 0) {         // t-net: d t = g_v (forward direction) or -g_v e^{-s} (inverse direction)
-                        float dt = inverse ? -gv_old * expf(-s_xs[par + gi]) : gv_old;
+                        float dt = inverse ? -gv_old * exp_acc(-s_xs[par + gi]) : gv_old;
                         if (!live) dt = 0.f;
                         const float dout[1] = {dt};
                         fcnn_bwd<1, 0>(img, dout, h1, h2, d1, d2, dc, nullptr);
@@ -198,7 +198,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
                         if (prev_q >= 0) s_gc[prev_q] += s_dct[(GRP - par) + gi];    // t-net share of the previous iteration
                         const float t = s_xt[par + gi], s = out[0];
                         const float v = s_v[q], gv = s_gv[q], gld = s_gld[q];
-                        const float es = expf(s), ies = expf(-s);
+                        const float es = exp_acc(s), ies = exp_acc(-s);
                         float ds, vin, gin;
                         if (!inverse) { vin = (v - t) * ies; ds = fmaf(gv * vin, es, gld); gin = gv * es; }
                         else          { gin = gv * ies; ds = -fmaf(gv, v, gld); vin = fmaf(v, es, t); }
