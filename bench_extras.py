@@ -113,9 +113,10 @@ def kernel_table(a, dpf, dev):
     grads = {(B, N, 2): gy, (B, N): gl}
     pkc, pkd = pk_c.clone().requires_grad_(), pk_d.clone().requires_grad_()
     xr = x.clone().requires_grad_()
-    # 128 tanh (2 MUFU each: ex2 + rcp) + 4 exp per stack pass; the backward re-evaluates every FCNN once
-    add("coupling_D2_C36", lambda: ops.coupling_stack(pkc, xr, ctx36, None, 2, True), 1280, 20, 2560, 40, grads, 1, 1, sfu=260)
-    add("coupling_D2_C4", lambda: ops.coupling_stack(pkd, xr, ctx36[:, :4].contiguous(), None, 2, True), 1280, 20, 2560, 40, grads, 2, 2, sfu=260)
+    # MUFU ops actually needed per stack pass: 128 tanh at 1.5 each (two ex2 + one shared rcp per pair of activations) + 4 exp
+    # (ex2); the backward re-evaluates every FCNN once and needs e^s and e^-s per stage
+    add("coupling_D2_C36", lambda: ops.coupling_stack(pkc, xr, ctx36, None, 2, True), 1280, 20, 2560, 40, grads, 1, 1, sfu=196)
+    add("coupling_D2_C4", lambda: ops.coupling_stack(pkd, xr, ctx36[:, :4].contiguous(), None, 2, True), 1280, 20, 2560, 40, grads, 2, 2, sfu=196)
     per = pe.clone().requires_grad_()
     lw0 = w.log()
     mode = a.measurement

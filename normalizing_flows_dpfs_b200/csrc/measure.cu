@@ -227,11 +227,13 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     if (MODE == MODE_CNF) hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
     __syncthreads();
     float mx = -INFINITY;
+    float2 x_next = *reinterpret_cast<const float2*>(particles + ((size_t)b * N + (tid < N ? tid : 0)) * 2);
     for (int n0 = 0; n0 < N; n0 += TP) {      // uniform trip count: the tensor-core rounds are CTA-collective
         asm volatile("" ::: "memory");  // keep the shared-memory weight loads inside the loop
         const int n = n0 + tid;
         const bool live = n < N;
-        const float2 x = live ? *reinterpret_cast<const float2*>(particles + ((size_t)b * N + n) * 2) : make_float2(0.f, 0.f);
+        const float2 x = x_next;
+        x_next = *reinterpret_cast<const float2*>(particles + ((size_t)b * N + (n + TP < N ? n + TP : 0)) * 2);   // next batch: latency hidden
         float a1[16], a2[32], e[32], lo[16], up[16];
         pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);
         const float ll = loglik<MODE>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
@@ -430,15 +432,22 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         for (int k = 0; k < 32; ++k) denc[k] = 0.f;
         s_denc[tid] = 0.f;   // NW * 32 == TP entries
         __syncthreads();
+        float2 x_next = *reinterpret_cast<const float2*>(particles + (base + (tid < N ? tid : 0)) * 2);
+        float g_next = g_lki[base + (tid < N ? tid : 0)];
         for (int n0 = 0; n0 < N; n0 += TP) {
             asm volatile("" ::: "memory");  // no LICM of shared-memory weight loads across particles
             __syncthreads();                // the previous batch's gradient contraction is done with the tile (it aliases the activation tile)
             const int n = n0 + tid;
             const bool live = n < N;
             const size_t p = base + (live ? n : 0);
-            const float2 x = *reinterpret_cast<const float2*>(particles + p * 2);
-            float g = live ? g_lki[p] : 0.f;
+            const float2 x = x_next;
+            float g = live ? g_next : 0.f;
             if (live && n == am) g -= gs;
+            {   // prefetch the next batch's particle and incoming gradient: their latency hides behind this batch
+                const size_t pn = base + (n + TP < N ? n + TP : 0);
+                x_next = *reinterpret_cast<const float2*>(particles + pn * 2);
+                g_next = g_lki[pn];
+            }
             float a1[16], a2[32], e[32], de[32];
             pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);        // tensor-core rounds 1-2: layers 2 and 3 forward
             if (MODE == MODE_GAUSS) {

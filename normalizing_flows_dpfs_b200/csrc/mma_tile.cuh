@@ -37,7 +37,7 @@ __device__ __forceinline__ void mma_outer(const float* __restrict__ tile, int ro
     const float* a_hi = tile + (rowA + g + 8) * TSM + t;
 #pragma unroll
     for (int k0 = k_begin; k0 < k_end; k0 += 8) {
-        uint32_t ah[4], al[4];
+        uint32_t ah[4], al[4], bh[NT][2], bl[NT][2];
         split_tf32(a_lo[k0], ah[0], al[0]);
         split_tf32(a_hi[k0], ah[1], al[1]);
         split_tf32(a_lo[k0 + 4], ah[2], al[2]);
@@ -45,13 +45,17 @@ __device__ __forceinline__ void mma_outer(const float* __restrict__ tile, int ro
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
             const float* b = tile + rowB[n] * TSM + k0 + t;
-            uint32_t bh[2], bl[2];
-            split_tf32(b[0], bh[0], bl[0]);
-            split_tf32(b[4], bh[1], bl[1]);
-            mma_tf32(c[n], ah, bh);
-            mma_tf32(c[n], ah, bl);
-            mma_tf32(c[n], al, bh);
+            split_tf32(b[0], bh[n][0], bl[n][0]);
+            split_tf32(b[4], bh[n][1], bl[n][1]);
         }
+        // pass-outer: consecutive MMAs hit different accumulator fragments (the asm statements keep their order, and three
+        // back-to-back MMAs into the same fragment would serialise on the tensor-pipe latency)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) mma_tf32(c[n], al, bh[n]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) mma_tf32(c[n], ah, bl[n]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) mma_tf32(c[n], ah, bh[n]);
     }
 }
 

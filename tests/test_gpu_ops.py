@@ -123,7 +123,11 @@ def test_coupling_golden(golden):
 
 @pytest.mark.parametrize("D,C_row,C_part,B,N,inverse", [(2, 4, 0, 5, 300, True), (2, 4, 0, 5, 300, False), (2, 36, 0, 4, 1024, True),
                                                         (32, 0, 32, 3, 200, False), (2, 0, 0, 2, 64, False), (4, 2, 3, 3, 129, True),
-                                                        (32, 5, 0, 2, 100, False)])
+                                                        (32, 5, 0, 2, 100, False),
+                                                        # D = 2 backward, resident-set geometry: several passes over the CTA's entries with a
+                                                        # ragged 128-particle iteration; several 1024-particle entries per trajectory (ragged
+                                                        # last one); both at once with more than one trajectory per CTA
+                                                        (2, 4, 0, 1500, 130, True), (2, 36, 0, 3, 2500, False), (2, 4, 0, 300, 1100, False)])
 def test_coupling_row_context_vs_oracle(D, C_row, C_part, B, N, inverse):
     """row-constant context hoisted into the layer-1 bias == the reference's materialised (P,C) concat."""
     g = torch.Generator().manual_seed(D * 1000 + C_row * 10 + C_part + int(inverse))
