@@ -10,8 +10,8 @@
 //     (resident set, net) instead of once per (trajectory, net);
 //   * the two nets of a stage are split over the two halves of the CTA: threads 0-127 own the t-net, threads 128-255 the
 //     s-net, for the SAME particles.  Each half runs its net forward (activations recomputed from the stage output: couplings
-//     are invertible, nothing but y is read from HBM), the halves exchange t and s through shared memory (one barrier per
-//     128 particles), then each runs its net backward with the activations still in registers -- no activation stash.
+//     are invertible, nothing but y is read from HBM), the halves exchange t and s through shared memory (one 64-thread
+//     named barrier per warp pair and 32 particles), then each runs its net backward with the activations still in registers -- no activation stash.
 #include "coupling.cuh"
 
 namespace nfdpf {
@@ -185,7 +185,9 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
                     float gv_old = 0.f;
                     if (grp == 0) { s_xt[par + gi] = out[0]; gv_old = s_gv[q]; }
                     else          { s_xs[par + gi] = out[0]; }
-                    __syncthreads();
+                    // t-warp w and s-warp w + 4 work on the same 32 particles and exchange only with each other: a 64-thread
+                    // named barrier per warp pair instead of a CTA barrier (the four pairs drift independently within a stage)
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
                     float d1[H], d2[H], dc[1] = {0.f};
                     if (grp == 0) {         // t-net: d t = g_v (forward direction) or -g_v e^{-s} (inverse direction)
                         float dt = inverse ? -gv_old * exp_acc(-s_xs[par + gi]) : gv_old;
