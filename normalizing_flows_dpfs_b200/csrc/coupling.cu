@@ -23,9 +23,7 @@ coupling_fwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     float* s_hb = s_img + n_fcnn * L::SIZE;               // [n_fcnn][8]
     float* s_w1r = s_hb + n_fcnn * H;                     // [n_fcnn][8][C_row]
     const int b = blockIdx.y;
-    const int pf = packed_fcnn_size(HALF, C_row + CP);
-    for (int f = 0; f < n_fcnn; ++f)
-        load_fcnn_image<HALF, CP>(packed + (size_t)f * pf, C_row, s_img + f * L::SIZE, s_w1r + (size_t)f * H * C_row, tid, TPF);
+    load_stack_images<HALF, CP>(packed, n_fcnn, C_row, s_img, s_w1r, tid, TPF);
     __syncthreads();
     hoist_row_context<HALF, CP>(s_img, s_w1r, row_ctx + (size_t)b * C_row, C_row, n_fcnn, s_hb, tid, TPF);
     __syncthreads();

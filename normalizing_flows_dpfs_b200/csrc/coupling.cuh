@@ -75,6 +75,35 @@ __device__ void load_fcnn_image(const float* __restrict__ pk, int C_row, float* 
     for (int e = tid; e < HALF; e += nt) img[L::B3 + e] = p[e];
 }
 
+// All FCNN images of a stack in two flat passes (image words, then row-context columns): every iteration is an independent
+// global load, so a CTA's loads overlap instead of queueing behind seven short loops per net (the one-CTA-per-trajectory
+// forward kernels spend a visible share of their life in this prologue).
+template <int HALF, int CP>
+__device__ void load_stack_images(const float* __restrict__ packed, int n_fcnn, int C_row, float* __restrict__ imgs, float* __restrict__ w1r,
+                                  int tid, int nt) {
+    using L = Lay<HALF, CP>;
+    const int fin = HALF + C_row + CP, pf = packed_fcnn_size(HALF, C_row + CP);
+#pragma unroll 4
+    for (int d = tid; d < n_fcnn * L::SIZE; d += nt) {
+        const int f = d / L::SIZE, o = d % L::SIZE;
+        const float* pk = packed + (size_t)f * pf;
+        float v = 0.f;
+        if (o < L::B1) {                                   // W1 [8][S1]: conditioning half | per-particle context, zero padded
+            const int k = o / L::S1, i = o % L::S1;
+            if (i < HALF) v = TANH_SCALE * pk[k * fin + i];
+            else if (i < L::IN1) v = TANH_SCALE * pk[k * fin + C_row + i];
+        } else if (o < L::W3) v = TANH_SCALE * pk[H * fin + (o - L::B1)];                       // b1, W2, b2: contiguous in both layouts
+        else if (o < L::B3 + HALF) v = pk[H * fin + H + H * H + H + (o - L::W3)];               // W3, b3
+        imgs[d] = v;
+    }
+    const int per = H * C_row;
+#pragma unroll 4
+    for (int e = tid; e < n_fcnn * per; e += nt) {
+        const int f = e / per, r = e - f * per;
+        w1r[e] = TANH_SCALE * packed[(size_t)f * pf + (r / C_row) * fin + HALF + (r % C_row)];
+    }
+}
+
 __device__ __forceinline__ void ld8(const float* p, float (&w)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
