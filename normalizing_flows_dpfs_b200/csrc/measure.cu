@@ -318,57 +318,80 @@ struct PR {
 };
 
 // Particle-encoder weight gradients on the warp-level tensor path (3xTF32 mma.sync): every warp contracts over the 32
-// particles its own threads staged and adds into ITS OWN accumulator copy accpe[PE_SIZE] (packed PE order) -- no CTA barrier.
-// rowsum3 (may be null): per-trajectory sum of delta3 (Gaussian mode: = -d enc).
-__device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_tile, float* __restrict__ accpe, float* __restrict__ rowsum3) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+// particles its own threads staged.  The accumulator fragments are LANE-PRIVATE and live in tensor memory between batches
+// (umma::ld_frag -> mma -> umma::st_frag on the warp's own 32 TMEM lanes): no per-warp shared-memory copies, no CTA barrier.
+// Column map (per lane, after the 32 data-path accumulator columns): phase A m-tile mt: [20 mt, 20 mt + 20) = c[5][4];
+// phase B m-tile mt: 40 + [12 mt, 12 mt + 12) = c[3][4]; delta1 tile: 64 + [0, 4).
+constexpr int TA_A = 32, TA_B = TA_A + 40, TA_D1 = TA_B + 24, TA_END = TA_D1 + 4;   // 100 columns -> 128 allocated
+constexpr int BWD_TMEM_COLS = 128;
+__device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_tile, uint32_t tacc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2;
     const int k0 = 32 * warp;
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
-        float c[5][4] = {};
+        float c[5][4];
+        umma::ld_frag<20>(tacc + TA_A + 20 * mt, &c[0][0]);
         const int rowB[5] = {PR::A2 + g, PR::A2 + 8 + g, PR::A2 + 16 + g, PR::A2 + 24 + g, g == 0 ? PR::ONE : PR::ZERO};
         mma_outer<5>(s_tile, PR::D3 + 16 * mt, rowB, k0, k0 + 32, c);
+        umma::st_frag<20>(tacc + TA_A + 20 * mt, &c[0][0]);
+    }
+}
+__device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_tile, uint32_t tacc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2;
+    const int k0 = 32 * warp;
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+        float c[3][4];
+        umma::ld_frag<12>(tacc + TA_B + 12 * mt, &c[0][0]);
+        const int rowB[3] = {PR::A1 + g, PR::A1 + 8 + g, g == 0 ? PR::ONE : PR::ZERO};
+        mma_outer<3>(s_tile, PR::D2 + 16 * mt, rowB, k0, k0 + 32, c);
+        umma::st_frag<12>(tacc + TA_B + 12 * mt, &c[0][0]);
+    }
+    float c1[1][4];
+    umma::ld_frag<4>(tacc + TA_D1, &c1[0][0]);
+    const int rowX[1] = {g < 2 ? PR::X + g : (g == 2 ? PR::ONE : PR::ZERO)};
+    mma_outer<1>(s_tile, PR::D1, rowX, k0, k0 + 32, c1);
+    umma::st_frag<4>(tacc + TA_D1, &c1[0][0]);
+    umma::wait_st();     // the next batch (or the read-out) loads these columns again
+}
+// Read this warp's accumulated fragments back and scatter them into its accumulator copy accpe[AC::SIZE] (every entry is
+// owned by exactly one lane; bias columns by the t == 0 / t == 1 lanes).
+__device__ __forceinline__ void pe_weight_grads_readout(uint32_t tacc, float* __restrict__ accpe) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int mt = 0; mt < 2; ++mt) {
+        float c[5][4];
+        umma::ld_frag<20>(tacc + TA_A + 20 * mt, &c[0][0]);
         const int o = 16 * mt + g;
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
             float* w = accpe + AC::W3 + o * AC::W3S + 8 * n + 2 * t;
-            w[0] += c[n][0]; w[1] += c[n][1]; w[8 * AC::W3S] += c[n][2]; w[8 * AC::W3S + 1] += c[n][3];
+            w[0] = c[n][0]; w[1] = c[n][1]; w[8 * AC::W3S] = c[n][2]; w[8 * AC::W3S + 1] = c[n][3];
         }
-        if (t == 0) {
-            accpe[AC::B3 + o] += c[4][0]; accpe[AC::B3 + o + 8] += c[4][2];
-            if (rowsum3) { rowsum3[o] += c[4][0]; rowsum3[o + 8] += c[4][2]; }
-        }
+        if (t == 0) { accpe[AC::B3 + o] = c[4][0]; accpe[AC::B3 + o + 8] = c[4][2]; }
     }
-}
-__device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_tile, float* __restrict__ accpe) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const int k0 = 32 * warp;
-#pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
-        float c[3][4] = {};
-        const int rowB[3] = {PR::A1 + g, PR::A1 + 8 + g, g == 0 ? PR::ONE : PR::ZERO};
-        mma_outer<3>(s_tile, PR::D2 + 16 * mt, rowB, k0, k0 + 32, c);
+        float c[3][4];
+        umma::ld_frag<12>(tacc + TA_B + 12 * mt, &c[0][0]);
         const int o = 16 * mt + g;
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
             float* w = accpe + AC::W2 + o * AC::W2S + 8 * n + 2 * t;
-            w[0] += c[n][0]; w[1] += c[n][1]; w[8 * AC::W2S] += c[n][2]; w[8 * AC::W2S + 1] += c[n][3];
+            w[0] = c[n][0]; w[1] = c[n][1]; w[8 * AC::W2S] = c[n][2]; w[8 * AC::W2S + 1] = c[n][3];
         }
-        if (t == 0) { accpe[AC::B2 + o] += c[2][0]; accpe[AC::B2 + o + 8] += c[2][2]; }
+        if (t == 0) { accpe[AC::B2 + o] = c[2][0]; accpe[AC::B2 + o + 8] = c[2][2]; }
     }
-    float c1[1][4] = {};
-    const int rowX[1] = {g < 2 ? PR::X + g : (g == 2 ? PR::ONE : PR::ZERO)};
-    mma_outer<1>(s_tile, PR::D1, rowX, k0, k0 + 32, c1);
+    float c1[4];
+    umma::ld_frag<4>(tacc + TA_D1, c1);
     if (t == 0) {          // columns 0,1 = dW1[o][0..1]
-        accpe[AC::W1 + 2 * g] += c1[0][0]; accpe[AC::W1 + 2 * g + 1] += c1[0][1];
-        accpe[AC::W1 + 2 * (g + 8)] += c1[0][2]; accpe[AC::W1 + 2 * (g + 8) + 1] += c1[0][3];
+        accpe[AC::W1 + 2 * g] = c1[0]; accpe[AC::W1 + 2 * g + 1] = c1[1];
+        accpe[AC::W1 + 2 * (g + 8)] = c1[2]; accpe[AC::W1 + 2 * (g + 8) + 1] = c1[3];
     } else if (t == 1) {   // column 2 = db1[o]
-        accpe[AC::B1 + g] += c1[0][0]; accpe[AC::B1 + g + 8] += c1[0][2];
+        accpe[AC::B1 + g] = c1[0]; accpe[AC::B1 + g + 8] = c1[2];
     }
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(TP)
+__global__ void __launch_bounds__(TP, MODE == MODE_CNF ? 1 : 3)   // gaussian / cos: three CTAs per SM (<= 168 registers, 67 KB)
 measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, int n_flows, float p0, float p1,
                    const float* __restrict__ enc, const float* __restrict__ particles, int B, int N,
                    const float* __restrict__ g_lki, const int* __restrict__ argmax, float* __restrict__ d_particles,
@@ -391,19 +414,19 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     float* s_hb = s_img + n_fcnn * LC::SIZE;
     constexpr int NW = TP / 32;
     const int warp = tid >> 5;
-    float* s_accpe = s_hb + n_fcnn * H;                      // [NW][AC::SIZE]   one accumulator copy per warp
-    float* s_acccnf = s_accpe + NW * AC::SIZE;                // [NW][n_fcnn][RC::NOUT]
+    float* s_accpe = s_tile;                                 // [NW][AC::SIZE]   read-out staging at the very end (the tile is free then)
+    float* s_acccnf = s_hb + n_fcnn * H;                     // [NW][n_fcnn][RC::NOUT]
     float* s_d1row = s_acccnf + NW * n_fcnn * RC::NOUT;      // [NW][n_fcnn][8] (unused sums; C_row = 0)
     float* s_denc = s_d1row + NW * n_fcnn * H + 4;           // [NW][32]
     static_assert(TILE_FLOATS % 32 == 0, "weight tiles must stay 128-byte aligned");
-    if (tid < 32) umma::tmem_alloc<32>(&s_tslot);
+    static_assert(NW * AC::SIZE <= TILE_FLOATS, "read-out staging must fit in the tile");
+    if (tid < 32) umma::tmem_alloc<BWD_TMEM_COLS>(&s_tslot);
     if (tid == 0) umma::mbar_init(&s_bar, 1);
     PeTc tc{s_tile, s_tcw, &s_bar, 0u, 0u};
     tc.load_weights(pe, true);
     for (int e = tid; e < PE_SIZE; e += TP) {
         s_pe[e] = pe[e];
     }
-    for (int e = tid; e < NW * AC::SIZE; e += TP) s_accpe[e] = 0.f;
     if (MODE == MODE_CNF) {
         const int pf = packed_fcnn_size(16, 32);
         for (int f = 0; f < n_fcnn; ++f) load_fcnn_image<16, 32>(cnf + (size_t)f * pf, 0, s_img + f * LC::SIZE, nullptr, tid, TP);
@@ -414,6 +437,15 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     __syncthreads();
     umma::fence_after_sync();
     tc.tmem = s_tslot;
+    const uint32_t tacc = tc.lane_addr();        // this warp's 32 lanes: gradient fragments in columns [TA_A, TA_END)
+    {
+        float z[TA_END - TA_A];
+#pragma unroll
+        for (int i = 0; i < TA_END - TA_A; ++i) z[i] = 0.f;
+        umma::st_frag<TA_END - TA_A>(tacc + TA_A, z);
+        umma::wait_st();
+    }
+    float rs3_prev[4] = {0.f, 0.f, 0.f, 0.f};    // Gaussian mode, t == 0 lanes: running delta3 sums of earlier trajectories
     if (MODE == MODE_CNF) hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
 
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -430,7 +462,6 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         float denc[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) denc[k] = 0.f;
-        s_denc[tid] = 0.f;   // NW * 32 == TP entries
         __syncthreads();
         float2 x_next = *reinterpret_cast<const float2*>(particles + (base + (tid < N ? tid : 0)) * 2);
         float g_next = g_lki[base + (tid < N ? tid : 0)];
@@ -533,7 +564,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 #pragma unroll
             for (int j = 0; j < 32; ++j) { s_tile[(PR::D3 + j) * TSM + tid] = de[j]; s_tile[(PR::A2 + j) * TSM + tid] = a2[j]; }
             __syncwarp();
-            pe_weight_grads_a(s_tile, s_accpe + warp * AC::SIZE, MODE == MODE_GAUSS ? s_denc + warp * 32 : nullptr);
+            pe_weight_grads_a(s_tile, tacc);
             __syncwarp();
             s_tile[(PR::X + 0) * TSM + tid] = x.x;
             s_tile[(PR::X + 1) * TSM + tid] = x.y;
@@ -542,13 +573,26 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 #pragma unroll
             for (int j = 0; j < 32; ++j) s_tile[(PR::D2 + j) * TSM + tid] = d2[j];
             __syncwarp();
-            pe_weight_grads_b(s_tile, s_accpe + warp * AC::SIZE);
+            pe_weight_grads_b(s_tile, tacc);
             __syncwarp();
         }
         // d_enc[b][k] = sum over the row's particles (deterministic: through the tile)
         __syncthreads();   // all warps are done with this trajectory (tile columns, per-warp sums)
-        if (d_enc && MODE == MODE_GAUSS) {
-            if (tid < 32) d_enc[(size_t)b * HID + tid] = -((s_denc[tid] + s_denc[32 + tid]) + (s_denc[64 + tid] + s_denc[96 + tid]));   // -sum_p delta3
+        if (MODE == MODE_GAUSS) {
+            // d_enc = -sum_p delta3: the bias column of phase A holds the warp's RUNNING sum over the trajectories done so far
+            // (t == 0 lanes: entries c[4][0], c[4][2] of both m-tiles); this trajectory's share is the increment
+            float cur[4], c4[4];
+            umma::ld_frag<4>(tacc + TA_A + 16, c4); cur[0] = c4[0]; cur[1] = c4[2];
+            umma::ld_frag<4>(tacc + TA_A + 36, c4); cur[2] = c4[0]; cur[3] = c4[2];
+            if ((tid & 3) == 0) {
+                const int g = (tid & 31) >> 2;
+                s_denc[warp * 32 + g] = cur[0] - rs3_prev[0]; s_denc[warp * 32 + g + 8] = cur[1] - rs3_prev[1];
+                s_denc[warp * 32 + 16 + g] = cur[2] - rs3_prev[2]; s_denc[warp * 32 + 24 + g] = cur[3] - rs3_prev[3];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rs3_prev[i] = cur[i];
+            __syncthreads();
+            if (d_enc && tid < 32) d_enc[(size_t)b * HID + tid] = -((s_denc[tid] + s_denc[32 + tid]) + (s_denc[64 + tid] + s_denc[96 + tid]));
         } else if (d_enc) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) s_tile[k * TSM + tid] = denc[k];
@@ -560,9 +604,13 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
             }
         }
     }
+    __syncthreads();                                   // every warp is done with the tile: it becomes the read-out staging area
+    for (int e = tid; e < NW * AC::SIZE; e += TP) s_accpe[e] = 0.f;
+    __syncthreads();
+    pe_weight_grads_readout(tacc, s_accpe + warp * AC::SIZE);
     umma::fence_before_sync();
     __syncthreads();
-    if (tid < 32) umma::tmem_free<32>(tc.tmem);
+    if (tid < 32) umma::tmem_free<BWD_TMEM_COLS>(tc.tmem);
     for (int e = tid; e < PE_SIZE; e += TP) {
         const float* a = s_accpe + AC::of_packed(e);
         part_pe[(size_t)blockIdx.x * PE_SIZE + e] = (a[0] + a[AC::SIZE]) + (a[2 * AC::SIZE] + a[3 * AC::SIZE]);
@@ -588,7 +636,7 @@ static size_t bwd_smem(int mode, int n_flows) {
     if (tile < (size_t)PeTc::A_FLOATS) tile = PeTc::A_FLOATS;
     tile = (tile + 31) & ~(size_t)31;
     const int nw = TP / 32;   // per-warp accumulator copies
-    size_t fl = tile + PeTc::WBWD_FLOATS + (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + (size_t)nw * AC::SIZE +
+    size_t fl = tile + PeTc::WBWD_FLOATS + (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H +
                 (size_t)nw * n_fcnn * RC::NOUT + (size_t)nw * n_fcnn * H + 4 + nw * 32;
     return fl * sizeof(float);
 }
@@ -606,6 +654,9 @@ static int launch_measure_fwd(const float* pe, const float* cnf, int n_flows, fl
     return check_launch("measure_fwd");
 }
 
+// persistent grid of the backward: three resident CTAs per SM for the gaussian / cos kernels, two waves of one for CRNVP
+static int measure_bwd_grid(int mode, int B) { return min(B, (mode == MODE_CNF ? 2 : 3) * sm_count()); }
+
 template <int MODE>
 static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,
                               int B, int N, const float* g_lki, const int* argmax, float* d_particles, float* d_enc, float* d_pe,
@@ -613,7 +664,7 @@ static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, fl
     const size_t smem = bwd_smem(MODE, n_flows);
     auto kern = measure_bwd_kernel<MODE>;
     if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = bwd_grid(B);
+    const int grid = measure_bwd_grid(MODE, B);
     float* part_pe = (float*)workspace;
     float* part_cnf = part_pe + (size_t)grid * PE_SIZE;
     kern<<<grid, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, part_cnf, z_saved);
@@ -651,7 +702,7 @@ extern "C" int64_t nfdpf_measure_bwd_workspace(int mode, int n_flows, int B, int
     (void)N;
     if (B < 1) return 0;
     int64_t per = PE_SIZE + (mode == MODE_CNF ? 4 * n_flows * packed_fcnn_size(16, 32) : 0);
-    return (int64_t)bwd_grid(B) * per * (int64_t)sizeof(float);
+    return (int64_t)measure_bwd_grid(mode, B) * per * (int64_t)sizeof(float);
 }
 
 extern "C" int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,

@@ -113,6 +113,79 @@ __device__ __forceinline__ void ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- tensor memory as lane-private accumulator storage --------------------------------------------------------
+// A warp's 32 TMEM lanes x N columns hold N floats per thread: the mma.sync gradient fragments live there between batches
+// instead of in per-warp shared-memory copies (tensor memory is 256 KB per SM and otherwise nearly empty on this path).
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void ld4w(uint32_t taddr, float* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+    wait_ld();   // the destination registers are undefined until the wait: nothing may read them earlier
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void ld8w(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void ld16w(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void st4(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])),
+                 "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void st16(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                 "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+                 : "memory");
+}
+// N floats per thread (N a multiple of 4, compile time), starting at column address taddr
+template <int N>
+__device__ __forceinline__ void ld_frag(uint32_t taddr, float* v) {
+    static_assert(N % 4 == 0, "fragment sizes are multiples of 4");
+    constexpr int N16 = N / 16 * 16, R8 = (N - N16) >= 8 ? 8 : 0, R4 = (N - N16 - R8) >= 4 ? 4 : 0;
+#pragma unroll
+    for (int o = 0; o < N16; o += 16) ld16w(taddr + o, v + o);
+    if (R8) ld8w(taddr + N16, v + N16);
+    if (R4) ld4w(taddr + N16 + R8, v + N16 + R8);
+}
+template <int N>
+__device__ __forceinline__ void st_frag(uint32_t taddr, const float* v) {
+    static_assert(N % 4 == 0, "fragment sizes are multiples of 4");
+    constexpr int N16 = N / 16 * 16, R8 = (N - N16) >= 8 ? 8 : 0, R4 = (N - N16 - R8) >= 4 ? 4 : 0;
+#pragma unroll
+    for (int o = 0; o < N16; o += 16) st16(taddr + o, v + o);
+    if (R8) st8(taddr + N16, v + N16);
+    if (R4) st4(taddr + N16 + R8, v + N16 + R8);
+}
+
 // ---- TF32 split ---------------------------------------------------------------------------------------------
 // hi = x with the 13 low mantissa bits cleared (what the tensor core reads of an fp32 word), lo = x - hi (exact).
 __device__ __forceinline__ void split(float x, float& hi, float& lo) {
