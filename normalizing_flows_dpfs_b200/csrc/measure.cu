@@ -12,6 +12,7 @@
 namespace nfdpf {
 
 enum { MODE_GAUSS = 0, MODE_COS = 1, MODE_CNF = 2 };
+constexpr int FWD_TMEM_COLS = 128;   // accumulator 32 + activation hi 32 + lo 32 columns, rounded up to a power of two
 constexpr int HID = 32;                      // encoding width (args.hiddensize)
 // packed particle encoder (state_dict order 0.weight,0.bias,2.weight,2.bias,4.weight,4.bias)
 constexpr int PE_W1 = 0, PE_B1 = 32, PE_W2 = 48, PE_B2 = 560, PE_W3 = 592, PE_B3 = 1616, PE_SIZE = 1648;
@@ -20,26 +21,25 @@ using RC = Rows<16, 32>;
 
 // ---- particle encoder layers 2 and 3 on the tcgen05 tensor cores (umma.cuh) ------------------------------------
 // M = the CTA's 128 particles (TMEM lane = particle = thread), N / K = 16 / 32 features, 3xTF32.  Layer 1 (2 -> 16) and
-// the bias / ReLU epilogues stay in registers.  Shared-memory region (floats): activation tile hi | lo, then the weight
-// tiles hi | lo in both orientations (the transposed ones only in the backward).
+// the bias / ReLU epilogues stay in registers.  The activation operand lives in TENSOR MEMORY: a thread splits its row into
+// TF32 hi / lo and writes both with tcgen05.st into its own lane (columns [32,64) hi, [64,96) lo; the accumulator is
+// columns [0,32)), so activations never touch shared memory; only the weight tiles (hi | lo, both orientations in the
+// backward) are shared-memory operands.
 struct PeTc {
-    using A32 = umma::Operand<128, 32>;
-    using A16 = umma::Operand<128, 16>;
     using W2 = umma::Operand<32, 16>;    // rows j (out), K = k (in)          a2 = W2 a1
     using W3 = umma::Operand<32, 32>;    // rows o,       K = j               e  = W3 a2
     using W3T = umma::Operand<32, 32>;   // rows j,       K = o               d a2 = W3^T delta3
     using W2T = umma::Operand<16, 32>;   // rows k,       K = j               d a1 = W2^T delta2
-    static constexpr int A_HI = 0, A_LO = A_HI + A32::FLOATS, A_FLOATS = 2 * A32::FLOATS;            // offsets from a
     static constexpr int W2_HI = 0, W2_LO = W2_HI + W2::FLOATS, W3_HI = W2_LO + W2::FLOATS, W3_LO = W3_HI + W3::FLOATS,  // offsets from w
                          WFWD_FLOATS = W3_LO + W3::FLOATS, W3T_HI = WFWD_FLOATS, W3T_LO = W3T_HI + W3T::FLOATS,
                          W2T_HI = W3T_LO + W3T::FLOATS, W2T_LO = W2T_HI + W2T::FLOATS, WBWD_FLOATS = W2T_LO + W2T::FLOATS;
-    float* a;            // activation tile hi | lo (128-byte aligned)
-    float* w;            // weight tiles
+    static constexpr int COL_D = 0, COL_AHI = 32, COL_ALO = 64, COLS = 96;     // tensor-memory columns
+    float* w;            // weight tiles (128-byte aligned)
     uint64_t* bar;       // mbarrier: completion of the issued MMAs
-    uint32_t tmem;       // 32 accumulator columns
+    uint32_t tmem;       // base of the CTA's tensor-memory allocation
     uint32_t parity;
 
-    // split the layer-2 / layer-3 weights into the hi / lo operand tiles (all threads)
+    // split the layer-2 / layer-3 weights into the hi / lo operand tiles (all threads; followed by a CTA barrier in the caller)
     __device__ void load_weights(const float* __restrict__ pe, bool bwd) {
         for (int e = threadIdx.x; e < 32 * 16; e += blockDim.x) {
             const int j = e >> 4, k = e & 15;
@@ -53,24 +53,36 @@ struct PeTc {
             W3::store_elem(w + W3_HI, w + W3_LO, o, j, wv);
             if (bwd) W3T::store_elem(w + W3T_HI, w + W3T_LO, j, o, wv);
         }
+        umma::fence_smem_to_async();     // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
     }
-    // One product round, called by ALL 128 threads after each has written its row of the activation tile:
-    // publish the tile to the async proxy, one thread issues the 3xTF32 MMAs, everybody waits for their completion.
+    __device__ __forceinline__ uint32_t lane_addr() const { return tmem + ((uint32_t)(threadIdx.x & ~31) << 16); }
+    // this thread's activation row -> its TMEM lane (hi and lo copies)
+    template <int K>
+    __device__ __forceinline__ void store_row(const float (&v)[K]) {
+        float hi[K], lo[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) umma::split(v[k], hi[k], lo[k]);
+        umma::st_frag<K>(lane_addr() + COL_AHI, hi);
+        umma::st_frag<K>(lane_addr() + COL_ALO, lo);
+    }
+    // One product round, called by ALL 128 threads after store_row: one thread issues the 3xTF32 MMAs, everybody waits for them.
     template <int N, int K>
     __device__ __forceinline__ void round(int w_hi, int w_lo) {
-        umma::fence_smem_to_async();
-        umma::fence_before_sync();      // orders this thread's earlier tcgen05.ld before the barrier (accumulator reuse)
+        umma::wait_st();                // this thread's activation row has landed in tensor memory
+        umma::fence_before_sync();      // ... and is ordered, like its earlier tcgen05.ld of the accumulator, before the barrier
         __syncthreads();
         if (threadIdx.x == 0) {
             umma::fence_after_sync();
-            umma::gemm3<N, K>(tmem, a + A_HI, a + A_LO, w + w_hi, w + w_lo);
+            umma::gemm3_ts<N, K>(tmem + COL_D, tmem + COL_AHI, tmem + COL_ALO, w + w_hi, w + w_lo);
             umma::commit(bar);
         }
+        wait();
+    }
+    __device__ __forceinline__ void wait() {
         umma::mbar_wait(bar, parity);
         parity ^= 1;
         umma::fence_after_sync();
     }
-    __device__ __forceinline__ uint32_t lane_addr() const { return tmem + ((uint32_t)(threadIdx.x & ~31) << 16); }
 };
 
 __device__ __forceinline__ void pe_l1(const float* __restrict__ w, float x0, float x1, float (&a1)[16]) {
@@ -88,7 +100,7 @@ __device__ __forceinline__ void pe_fwd_tc(PeTc& tc, const float* __restrict__ w,
                                           float (&e)[32]) {
     const int tid = threadIdx.x;
     pe_l1(w, x0, x1, a1);
-    PeTc::A16::store_row(tc.a + PeTc::A_HI, tc.a + PeTc::A_LO, tid, a1);
+    tc.store_row<16>(a1);
     tc.round<32, 16>(PeTc::W2_HI, PeTc::W2_LO);
     umma::ld32(tc.lane_addr(), a2);
 #pragma unroll
@@ -97,7 +109,7 @@ __device__ __forceinline__ void pe_fwd_tc(PeTc& tc, const float* __restrict__ w,
         a2[j] = fmaxf(a2[j] + b.x, 0.f); a2[j + 1] = fmaxf(a2[j + 1] + b.y, 0.f);
         a2[j + 2] = fmaxf(a2[j + 2] + b.z, 0.f); a2[j + 3] = fmaxf(a2[j + 3] + b.w, 0.f);
     }
-    PeTc::A32::store_row(tc.a + PeTc::A_HI, tc.a + PeTc::A_LO, tid, a2);
+    tc.store_row<32>(a2);
     tc.round<32, 32>(PeTc::W3_HI, PeTc::W3_LO);
     umma::ld32(tc.lane_addr(), e);
 #pragma unroll
@@ -204,15 +216,15 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     __shared__ uint64_t s_bar;
     __shared__ uint32_t s_tslot;
     const int tid = threadIdx.x, b = blockIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
-    float* s_tc = smem;                       // tensor-core operand tiles: activations hi | lo, then weights
-    float* s_pe = s_tc + PeTc::A_FLOATS + PeTc::WFWD_FLOATS;    // [1648]
+    float* s_tc = smem;                       // tensor-core weight tiles (the activation operand lives in tensor memory)
+    float* s_pe = s_tc + PeTc::WFWD_FLOATS;   // [1648]
     float* s_enc = s_pe + PE_SIZE;            // [36]
     float* s_img = s_enc + 36;                // [n_fcnn][LC::SIZE]
     float* s_hb = s_img + n_fcnn * LC::SIZE;  // [n_fcnn][8]
     float* s_ll = s_hb + n_fcnn * H;          // [N]
-    if (tid < 32) umma::tmem_alloc<32>(&s_tslot);
+    if (tid < 32) umma::tmem_alloc<FWD_TMEM_COLS>(&s_tslot);
     if (tid == 0) umma::mbar_init(&s_bar, 1);
-    PeTc tc{s_tc, s_tc + PeTc::A_FLOATS, &s_bar, 0u, 0u};
+    PeTc tc{s_tc, &s_bar, 0u, 0u};
     tc.load_weights(pe, false);
     for (int e = tid; e < PE_SIZE; e += TP) s_pe[e] = pe[e];
     if (MODE == MODE_CNF) {
@@ -249,7 +261,7 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (tid < 32) umma::tmem_free<32>(tc.tmem);
+    if (tid < 32) umma::tmem_free<FWD_TMEM_COLS>(tc.tmem);
     float shift = 0.f;
     if (MODE != MODE_COS) {      // likelihood - likelihood.max(dim=-1), models.py:252, 276
         shift = block_allreduce(mx, s_red, OpMax(), -INFINITY);
@@ -320,10 +332,10 @@ struct PR {
 // Particle-encoder weight gradients on the warp-level tensor path (3xTF32 mma.sync): every warp contracts over the 32
 // particles its own threads staged.  The accumulator fragments are LANE-PRIVATE and live in tensor memory between batches
 // (umma::ld_frag -> mma -> umma::st_frag on the warp's own 32 TMEM lanes): no per-warp shared-memory copies, no CTA barrier.
-// Column map (per lane, after the 32 data-path accumulator columns): phase A m-tile mt: [20 mt, 20 mt + 20) = c[5][4];
+// Column map (per lane, after the 96 data-path columns): phase A m-tile mt: [20 mt, 20 mt + 20) = c[5][4];
 // phase B m-tile mt: 40 + [12 mt, 12 mt + 12) = c[3][4]; delta1 tile: 64 + [0, 4).
-constexpr int TA_A = 32, TA_B = TA_A + 40, TA_D1 = TA_B + 24, TA_END = TA_D1 + 4;   // 100 columns -> 128 allocated
-constexpr int BWD_TMEM_COLS = 128;
+constexpr int TA_A = PeTc::COLS, TA_B = TA_A + 40, TA_D1 = TA_B + 24, TA_END = TA_D1 + 4;   // 164 columns -> 256 allocated
+constexpr int BWD_TMEM_COLS = 256;
 __device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_tile, uint32_t tacc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2;
     const int k0 = 32 * warp;
@@ -391,7 +403,7 @@ __device__ __forceinline__ void pe_weight_grads_readout(uint32_t tacc, float* __
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(TP, MODE == MODE_CNF ? 1 : 3)   // gaussian / cos: three CTAs per SM (<= 168 registers, 67 KB)
+__global__ void __launch_bounds__(TP, MODE == MODE_CNF ? 1 : 2)   // gaussian / cos: two CTAs per SM (256 tensor-memory columns each)
 measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, int n_flows, float p0, float p1,
                    const float* __restrict__ enc, const float* __restrict__ particles, int B, int N,
                    const float* __restrict__ g_lki, const int* __restrict__ argmax, float* __restrict__ d_particles,
@@ -402,11 +414,10 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     __shared__ uint32_t s_tslot;
     const int tid = threadIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
     constexpr int TILE_ROWS = MODE == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT;
-    constexpr int TILE_FLOATS = ((TILE_ROWS * TSM > PeTc::A_FLOATS ? TILE_ROWS * TSM : PeTc::A_FLOATS) + 31) & ~31;   // keeps the weight tiles 128-byte aligned
-    // The tensor-core activation tile (hi | lo, 32 KB, at the region base) and the mma.sync gradient tile share the same
-    // memory: within a batch the four encoder rounds finish before the gradient tile is staged, and a CTA barrier
-    // separates the gradient contraction from the next batch's first activation store.
-    float* s_tile = smem;                                    // [TILE_FLOATS]  == PeTc activation tile
+    constexpr int TILE_FLOATS = (TILE_ROWS * TSM + 31) & ~31;   // keeps the weight tiles 128-byte aligned
+    // The gradient tile: every thread owns one column (its particle), every warp contracts over its own 32 columns, so the tile
+    // needs no CTA barrier between batches; the CRNVP tile and the encoder tile alias (warp-private columns, __syncwarp).
+    float* s_tile = smem;                                    // [TILE_FLOATS]
     float* s_tcw = s_tile + TILE_FLOATS;                     // tensor-core weight tiles
     float* s_pe = s_tcw + PeTc::WBWD_FLOATS;
     float* s_enc = s_pe + PE_SIZE;
@@ -422,7 +433,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     static_assert(NW * AC::SIZE <= TILE_FLOATS, "read-out staging must fit in the tile");
     if (tid < 32) umma::tmem_alloc<BWD_TMEM_COLS>(&s_tslot);
     if (tid == 0) umma::mbar_init(&s_bar, 1);
-    PeTc tc{s_tile, s_tcw, &s_bar, 0u, 0u};
+    PeTc tc{s_tcw, &s_bar, 0u, 0u};
     tc.load_weights(pe, true);
     for (int e = tid; e < PE_SIZE; e += TP) {
         s_pe[e] = pe[e];
@@ -467,7 +478,6 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         float g_next = g_lki[base + (tid < N ? tid : 0)];
         for (int n0 = 0; n0 < N; n0 += TP) {
             asm volatile("" ::: "memory");  // no LICM of shared-memory weight loads across particles
-            __syncthreads();                // the previous batch's gradient contraction is done with the tile (it aliases the activation tile)
             const int n = n0 + tid;
             const bool live = n < N;
             const size_t p = base + (live ? n : 0);
@@ -535,16 +545,15 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 #pragma unroll
                     for (int k = 0; k < 32; ++k) de[k] = 0.f;
                 }
-                __syncthreads();            // every warp is done with the CRNVP tile before the activation tile is rewritten
             }
             // encoder backward, tensor-core rounds 3-4: d a2 = W3^T delta3, d a1 = W2^T delta2
             float d2[32], d1[16];
-            PeTc::A32::store_row(tc.a + PeTc::A_HI, tc.a + PeTc::A_LO, tid, de);
+            tc.store_row<32>(de);
             tc.round<32, 32>(PeTc::W3T_HI, PeTc::W3T_LO);
             umma::ld32(tc.lane_addr(), d2);
 #pragma unroll
             for (int j = 0; j < 32; ++j) d2[j] = a2[j] > 0.f ? d2[j] : 0.f;
-            PeTc::A32::store_row(tc.a + PeTc::A_HI, tc.a + PeTc::A_LO, tid, d2);
+            tc.store_row<32>(d2);
             tc.round<16, 32>(PeTc::W2T_HI, PeTc::W2T_LO);
             umma::ld16(tc.lane_addr(), d1);
             float dx0 = 0.f, dx1 = 0.f;
@@ -558,7 +567,6 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
             }
             if (live) *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
             // weight gradients: the warp contracts over its own 32 tile columns, no CTA barrier between the two phases
-            // (round 4 has completed for every thread that got here, so the activation tile is free to be overwritten)
             s_tile[PR::ONE * TSM + tid] = 1.0f;
             s_tile[PR::ZERO * TSM + tid] = 0.0f;
 #pragma unroll
@@ -628,12 +636,11 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 
 static size_t fwd_smem(int mode, int n_flows, int N) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    return ((size_t)PeTc::A_FLOATS + PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + N) * sizeof(float);
+    return ((size_t)PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + N) * sizeof(float);
 }
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
     size_t tile = (size_t)(mode == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT) * TSM;
-    if (tile < (size_t)PeTc::A_FLOATS) tile = PeTc::A_FLOATS;
     tile = (tile + 31) & ~(size_t)31;
     const int nw = TP / 32;   // per-warp accumulator copies
     size_t fl = tile + PeTc::WBWD_FLOATS + (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H +
@@ -654,8 +661,8 @@ static int launch_measure_fwd(const float* pe, const float* cnf, int n_flows, fl
     return check_launch("measure_fwd");
 }
 
-// persistent grid of the backward: three resident CTAs per SM for the gaussian / cos kernels, two waves of one for CRNVP
-static int measure_bwd_grid(int mode, int B) { return min(B, (mode == MODE_CNF ? 2 : 3) * sm_count()); }
+// persistent grid of the backward: two resident CTAs per SM for the gaussian / cos kernels, two waves of one for CRNVP
+static int measure_bwd_grid(int mode, int B) { (void)mode; return min(B, 2 * sm_count()); }
 
 template <int MODE>
 static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,

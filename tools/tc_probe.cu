@@ -289,8 +289,148 @@ int run_decode(uint32_t lbo, uint32_t sbo, int N = 64, int mn_flag = 1) {
     return 0;
 }
 
+
+// ---- round latency: store_row -> fence -> barrier -> 12 MMAs (3xTF32, K = 32, N = 32) -> commit -> wait -> tcgen05.ld ----
+__device__ __forceinline__ void mbar_spin_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+template <int WAITMODE>
+__global__ void __launch_bounds__(128) probe_latency(float* D, int rounds, long long* cyc) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    using OA = Operand<128, 32>;
+    using OB = Operand<32, 32>;
+    float* a_hi = smem; float* a_lo = a_hi + OA::FLOATS; float* b_hi = a_lo + OA::FLOATS; float* b_lo = b_hi + OB::FLOATS;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc<32>(&tslot);
+    if (tid == 0) mbar_init(&bar, 1);
+    for (int e = tid; e < 32 * 32; e += 128) OB::store_elem(b_hi, b_lo, e / 32, e % 32, (e % 7) * 0.01f);
+    fence_before_sync(); __syncthreads(); fence_after_sync();
+    const uint32_t tmem = tslot;
+    uint32_t parity = 0;
+    float v[32];
+    for (int k = 0; k < 32; ++k) v[k] = 0.01f * (tid + k);
+    long long t0 = clock64();
+    for (int r = 0; r < rounds; ++r) {
+        OA::store_row(a_hi, a_lo, tid, v);
+        fence_smem_to_async(); fence_before_sync(); __syncthreads();
+        if (tid == 0) { fence_after_sync(); gemm3<32, 32>(tmem, a_hi, a_lo, b_hi, b_lo); commit(&bar); }
+        if (WAITMODE == 0) mbar_wait(&bar, parity); else mbar_spin_test(&bar, parity);
+        parity ^= 1;
+        fence_after_sync();
+        ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = v[k] * 1e-3f + 0.01f;
+    }
+    long long t1 = clock64();
+    if (tid == 0) cyc[blockIdx.x] = t1 - t0;
+    D[blockIdx.x * 128 + tid] = v[0];
+    fence_before_sync(); __syncthreads();
+    if (warp == 0) tmem_free<32>(tmem);
+}
+template <int WAITMODE>
+int run_latency(int ctas) {
+    float* dD; long long* dC;
+    CK(cudaMalloc(&dD, 148 * 8 * 128 * 4)); CK(cudaMalloc(&dC, 148 * 8 * 8));
+    const size_t smem = 2 * Operand<128, 32>::BYTES + 2 * Operand<32, 32>::BYTES;
+    auto kern = probe_latency<WAITMODE>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int rounds = 2000;
+    kern<<<ctas, 128, smem>>>(dD, rounds, dC);
+    CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+    long long c[8]; CK(cudaMemcpy(c, dC, sizeof(c), cudaMemcpyDeviceToHost));
+    printf("latency: waitmode=%d ctas=%d (%d per SM): %.0f cycles per round (CTA 0)\n", WAITMODE, ctas, (ctas + 147) / 148, (double)c[0] / rounds);
+    return 0;
+}
+
+// ---- TS form: the activation operand lives in tensor memory (thread = row writes its K values with tcgen05.st) ----
+template <int TIMED>
+__global__ void __launch_bounds__(128) probe_ts(const float* A, const float* Bw, float* D, int rounds, long long* cyc) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    using OB = Operand<32, 32>;
+    float* b_hi = smem; float* b_lo = b_hi + OB::FLOATS;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc<128>(&tslot);
+    if (tid == 0) mbar_init(&bar, 1);
+    for (int e = tid; e < 32 * 32; e += 128) OB::store_elem(b_hi, b_lo, e / 32, e % 32, Bw[e]);
+    fence_smem_to_async();
+    fence_before_sync(); __syncthreads(); fence_after_sync();
+    const uint32_t tmem = tslot, lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t parity = 0;
+    float v[32], out[32];
+    for (int k = 0; k < 32; ++k) v[k] = A[tid * 32 + k];
+    long long t0 = clock64();
+    for (int r = 0; r < rounds; ++r) {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) split(v[k], hi[k], lo[k]);
+        st_frag<32>(lane_base + 32, hi);
+        st_frag<32>(lane_base + 64, lo);
+        wait_st();
+        fence_before_sync(); __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            constexpr uint32_t idesc = idesc_tf32(128, 32);
+            uint32_t acc = 0;
+            for (int k0 = 0; k0 < 32; k0 += 8) { mma_tf32_ts(tmem, tmem + 64 + k0, OB::desc(b_hi, k0), idesc, acc); acc = 1; }
+            for (int k0 = 0; k0 < 32; k0 += 8) mma_tf32_ts(tmem, tmem + 32 + k0, OB::desc(b_lo, k0), idesc, 1);
+            for (int k0 = 0; k0 < 32; k0 += 8) mma_tf32_ts(tmem, tmem + 32 + k0, OB::desc(b_hi, k0), idesc, 1);
+            commit(&bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        fence_after_sync();
+        ld32(lane_base, out);
+        if (TIMED) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) v[k] = out[k] * 1e-3f + 0.01f;
+        }
+    }
+    long long t1 = clock64();
+    if (tid == 0 && cyc) cyc[blockIdx.x] = t1 - t0;
+    for (int n = 0; n < 32; ++n) D[(size_t)blockIdx.x * 128 * 32 + tid * 32 + n] = out[n];
+    fence_before_sync(); __syncthreads();
+    if (warp == 0) tmem_free<128>(tmem);
+}
+int run_ts() {
+    std::vector<float> A(128 * 32), B(32 * 32), D(128 * 32);
+    for (auto& x : A) x = frand();
+    for (auto& x : B) x = frand();
+    float *dA, *dB, *dD; long long* dC;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, (size_t)148 * 4 * 128 * 32 * 4)); CK(cudaMalloc(&dC, 148 * 4 * 8));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    const size_t smem = 2 * Operand<32, 32>::BYTES;
+    probe_ts<0><<<1, 128, smem>>>(dA, dB, dD, 1, nullptr);
+    CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (int r = 0; r < 128; ++r)
+        for (int n = 0; n < 32; ++n) {
+            double ref = 0;
+            for (int k = 0; k < 32; ++k) ref += (double)A[r * 32 + k] * B[n * 32 + k];
+            maxerr = fmax(maxerr, fabs(ref - D[r * 32 + n])); maxref = fmax(maxref, fabs(ref));
+        }
+    printf("ts: A from TMEM, N=32 K=32 3xTF32: max|err| = %.3e (max|ref| = %.3f) D[0][0..3] = %f %f %f %f\n", maxerr, maxref, D[0], D[1], D[2], D[3]);
+    for (int ctas : {1, 148 * 2, 148 * 4}) {
+        probe_ts<1><<<ctas, 128, smem>>>(dA, dB, dD, 2000, dC);
+        CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+        long long c0; CK(cudaMemcpy(&c0, dC, 8, cudaMemcpyDeviceToHost));
+        printf("ts latency: ctas=%d (%d per SM): %.0f cycles per round\n", ctas, (ctas + 147) / 148, (double)c0 / 2000);
+    }
+    return 0;
+}
+
 int main2(int argc, char** argv) {
     const char* t = argv[1];
+    if (!strcmp(t, "ts")) return run_ts();
+    if (!strcmp(t, "lat")) { run_latency<0>(1); run_latency<1>(1); run_latency<0>(148 * 2); run_latency<1>(148 * 2); run_latency<0>(148 * 4); return run_latency<1>(148 * 4); }
     if (!strcmp(t, "decodeA")) return run_decode<0>(4096, 256);
     if (!strcmp(t, "decodeB")) return run_decode<1>(4096, 256);
     if (!strcmp(t, "decodeA2")) return run_decode<0>(256, 4096);
