@@ -120,6 +120,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     for (int r = R::COUNT; r < R::TROWS; ++r) s_tile[r * TSM + tid] = 0.0f;   // padding rows of the dout tile + the ZERO row
     __syncthreads();
 
+    SmemGradSink sink{s_acc + warp * n_fcnn * R::NOUT, s_d1row + warp * n_fcnn * H};
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         for (int e = tid; e < C_row; e += TP) s_ctx[e] = row_ctx[(size_t)b * C_row + e];
         for (int e = tid; e < NW * n_fcnn * H; e += TP) s_d1row[e] = 0.f;
@@ -152,7 +153,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
                 const float* im = s_img + (4 * f + 2 * pair) * L::SIZE;
                 const float* hb = s_hb + (4 * f + 2 * pair) * H;
                 stage_bwd<HALF, CP>(im, im + L::SIZE, hb, hb + H, 4 * f + 2 * pair, inverse != 0, live, lo, glo, pc, gpc, up, gup, gld,
-                                    s_tile, s_acc + warp * n_fcnn * R::NOUT, s_d1row + warp * n_fcnn * H);
+                                    s_tile, sink);
                 swap_halves<HALF>(lo, up);
                 swap_halves<HALF>(glo, gup);
             }

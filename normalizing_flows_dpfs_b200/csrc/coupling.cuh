@@ -459,11 +459,21 @@ struct BwdSmem {
 
 // Backward of one stage for the particle held by this thread, plus the CTA-wide weight-gradient accumulation.
 // On entry (c, v) are the stage's OUTPUT values with gradients (gc, gv); on exit v / gv are the stage's input.
-template <int HALF, int CP>
+// Where a stage's weight-gradient products go: per-warp shared-memory accumulator copies (the generic backward) ...
+struct SmemGradSink {
+    float* acc;      // this warp's copy [n_fcnn][NOUT]
+    float* d1row;    // this warp's layer-1 delta sums [n_fcnn][8]
+    template <int HALF, int CP>
+    __device__ __forceinline__ void accumulate(const float* __restrict__ s_tile, int f) {
+        stage_weight_grads_mma<HALF, CP>(s_tile, acc + f * Rows<HALF, CP>::NOUT, d1row + f * H);
+    }
+};
+// ... or any type with the same accumulate<HALF, CP>(tile, net) member (measure.cu keeps the fragments in tensor memory).
+
+template <int HALF, int CP, class Sink>
 __device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s, const float* hb_t, const float* hb_s, int f_t,
                                           bool inv, bool live, const float (&c)[HALF], float (&gc)[HALF], const float* pc, float* gpc,
-                                          float (&v)[HALF], float (&gv)[HALF], float gld, float* s_tile, float* s_acc,
-                                          float* s_d1row) {
+                                          float (&v)[HALF], float (&gv)[HALF], float gld, float* s_tile, Sink& sink) {
     using R = Rows<HALF, CP>;
     using L = Lay<HALF, CP>;
     const int tid = threadIdx.x;
@@ -513,7 +523,7 @@ __device__ __forceinline__ void stage_bwd(const float* img_t, const float* img_s
         __syncwarp();   // the warp contracts over its own 32 columns only: no CTA barrier in the gradient phase
         const int f = f_t + net;
         // b1 slots (first after the W1 block) double as the per-trajectory layer-1 delta sums (row-context hoist)
-        stage_weight_grads_mma<HALF, CP>(s_tile, s_acc + f * R::NOUT, s_d1row + f * H);
+        sink.template accumulate<HALF, CP>(s_tile, f);
         __syncwarp();
     }
     (void)sizeof(L);

@@ -9,6 +9,8 @@
 #include "mma_tile.cuh"
 #include "umma.cuh"
 
+#include <type_traits>
+
 namespace nfdpf {
 
 enum { MODE_GAUSS = 0, MODE_COS = 1, MODE_CNF = 2 };
@@ -85,6 +87,43 @@ struct PeTc {
     }
 };
 
+// Twin of PeTc with the activation operand in SHARED memory (SS form: 32 tensor-memory columns instead of 96).  The CRNVP
+// backward keeps 212 columns of gradient fragments per CTA in tensor memory and still wants two CTAs per SM (512 columns).
+struct PeSs {
+    using A32 = umma::Operand<128, 32>;
+    static constexpr int A_HI = 0, A_LO = A32::FLOATS, A_FLOATS = 2 * A32::FLOATS;
+    static constexpr int COL_D = 0, COLS = 32;
+    float* a;            // activation tile hi | lo (128-byte aligned); chunk stride is 128 rows x 16 B for every K
+    float* w;
+    uint64_t* bar;
+    uint32_t tmem;
+    uint32_t parity;
+    __device__ void load_weights(const float* __restrict__ pe, bool bwd) {
+        PeTc t{w, bar, tmem, parity};
+        t.load_weights(pe, bwd);
+    }
+    __device__ __forceinline__ uint32_t lane_addr() const { return tmem + ((uint32_t)(threadIdx.x & ~31) << 16); }
+    template <int K>
+    __device__ __forceinline__ void store_row(const float (&v)[K]) { umma::Operand<128, K>::store_row(a + A_HI, a + A_LO, threadIdx.x, v); }
+    template <int N, int K>
+    __device__ __forceinline__ void round(int w_hi, int w_lo) {
+        umma::fence_smem_to_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            umma::fence_after_sync();
+            umma::gemm3<N, K>(tmem + COL_D, a + A_HI, a + A_LO, w + w_hi, w + w_lo);
+            umma::commit(bar);
+        }
+        wait();
+    }
+    __device__ __forceinline__ void wait() {
+        umma::mbar_wait(bar, parity);
+        parity ^= 1;
+        umma::fence_after_sync();
+    }
+};
+
 __device__ __forceinline__ void pe_l1(const float* __restrict__ w, float x0, float x1, float (&a1)[16]) {
 #pragma unroll
     for (int k = 0; k < 16; k += 2) {
@@ -96,12 +135,13 @@ __device__ __forceinline__ void pe_l1(const float* __restrict__ w, float x0, flo
 }
 
 // encoder forward for the particle of this thread; collective over the CTA (contains barriers)
-__device__ __forceinline__ void pe_fwd_tc(PeTc& tc, const float* __restrict__ w, float x0, float x1, float (&a1)[16], float (&a2)[32],
+template <class Tc>
+__device__ __forceinline__ void pe_fwd_tc(Tc& tc, const float* __restrict__ w, float x0, float x1, float (&a1)[16], float (&a2)[32],
                                           float (&e)[32]) {
     const int tid = threadIdx.x;
     pe_l1(w, x0, x1, a1);
-    tc.store_row<16>(a1);
-    tc.round<32, 16>(PeTc::W2_HI, PeTc::W2_LO);
+    tc.template store_row<16>(a1);
+    tc.template round<32, 16>(PeTc::W2_HI, PeTc::W2_LO);
     umma::ld32(tc.lane_addr(), a2);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -109,8 +149,8 @@ __device__ __forceinline__ void pe_fwd_tc(PeTc& tc, const float* __restrict__ w,
         a2[j] = fmaxf(a2[j] + b.x, 0.f); a2[j + 1] = fmaxf(a2[j + 1] + b.y, 0.f);
         a2[j + 2] = fmaxf(a2[j + 2] + b.z, 0.f); a2[j + 3] = fmaxf(a2[j + 3] + b.w, 0.f);
     }
-    tc.store_row<32>(a2);
-    tc.round<32, 32>(PeTc::W3_HI, PeTc::W3_LO);
+    tc.template store_row<32>(a2);
+    tc.template round<32, 32>(PeTc::W3_HI, PeTc::W3_LO);
     umma::ld32(tc.lane_addr(), e);
 #pragma unroll
     for (int o = 0; o < 32; o += 4) {
@@ -332,10 +372,11 @@ struct PR {
 // Particle-encoder weight gradients on the warp-level tensor path (3xTF32 mma.sync): every warp contracts over the 32
 // particles its own threads staged.  The accumulator fragments are LANE-PRIVATE and live in tensor memory between batches
 // (umma::ld_frag -> mma -> umma::st_frag on the warp's own 32 TMEM lanes): no per-warp shared-memory copies, no CTA barrier.
-// Column map (per lane, after the 96 data-path columns): phase A m-tile mt: [20 mt, 20 mt + 20) = c[5][4];
+// Column map (per lane, relative to tacc = the first column after the data-path ones): phase A m-tile mt: [20 mt, 20 mt + 20) = c[5][4];
 // phase B m-tile mt: 40 + [12 mt, 12 mt + 12) = c[3][4]; delta1 tile: 64 + [0, 4).
-constexpr int TA_A = PeTc::COLS, TA_B = TA_A + 40, TA_D1 = TA_B + 24, TA_END = TA_D1 + 4;   // 164 columns -> 256 allocated
-constexpr int BWD_TMEM_COLS = 256;
+constexpr int TA_A = 0, TA_B = TA_A + 40, TA_D1 = TA_B + 24, TA_END = TA_D1 + 4;   // 68 columns after the data-path columns
+constexpr int TA_CNF = TA_END, CNF_COLS = 18;                                      // CRNVP nets: 18 columns each behind them
+constexpr int BWD_TMEM_COLS = 256;   // gaussian / cos: 96 + 68; CRNVP (SS data path): 32 + 68 + 8 x 18 = 244
 __device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_tile, uint32_t tacc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2;
     const int k0 = 32 * warp;
@@ -402,8 +443,80 @@ __device__ __forceinline__ void pe_weight_grads_readout(uint32_t tacc, float* __
     }
 }
 
+template <class Tc> __device__ __forceinline__ Tc make_tc(float* a_tile, float* w, uint64_t* bar);
+template <> __device__ __forceinline__ PeTc make_tc<PeTc>(float*, float* w, uint64_t* bar) { return PeTc{w, bar, 0u, 0u}; }
+template <> __device__ __forceinline__ PeSs make_tc<PeSs>(float* a_tile, float* w, uint64_t* bar) { return PeSs{a_tile, w, bar, 0u, 0u}; }
+
+// CRNVP stack (nets 48 -> 8 -> 8 -> 16): weight-gradient sink of stage_bwd that keeps the fragments in tensor memory.
+// Per net and lane 18 values: dW1 (six input tiles x 2), dW2 (2), dW3 (4); the bias fragments, which only the t == 0 lanes
+// carry, go to a small per-warp shared-memory block [n_fcnn][32] = b1 (8) | b2 (8) | b3 (16).  Replaces four per-warp
+// shared-memory copies of all eight nets (78 KB), which pinned the kernel to one 4-warp CTA per SM.
+struct CnfTmemSink {
+    uint32_t tcol;     // this warp's lanes, first CRNVP column
+    float* bias;       // this warp's bias block
+    template <int HALF, int CP>
+    __device__ __forceinline__ void accumulate(const float* __restrict__ s_tile, int f) {
+        static_assert(HALF == 16 && CP == 32, "CRNVP measurement stack only");
+        using R = RC;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+        const int k0 = 32 * warp;
+        const uint32_t col = tcol + CNF_COLS * f;
+        float a[CNF_COLS];
+        umma::ld_frag<16>(col, a);
+        umma::ld2w(col + 16, a + 16);
+        {   // A = [delta1; delta2] x input tiles 0..3 -> rows 0-7: dW1[g][8 n + 2 t, +1]
+            float c[4][4];
+            int rowB[4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) { rowB[n] = R::C + 8 * n + g; c[n][0] = a[2 * n]; c[n][1] = a[2 * n + 1]; c[n][2] = 0.f; c[n][3] = 0.f; }
+            mma_outer<4>(s_tile, R::D1, rowB, k0, k0 + 32, c);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) { a[2 * n] = c[n][0]; a[2 * n + 1] = c[n][1]; }
+        }
+        {   // input tiles 4, 5 | ONE (db1 rows 0-7, db2 rows 8-15) | h1 (rows 8-15: dW2[g][2 t, +1])
+            float c[4][4] = {};
+            const int rowB[4] = {R::C + 32 + g, R::C + 40 + g, g == 0 ? R::ONE : R::ZERO, R::H1 + g};
+            c[0][0] = a[8]; c[0][1] = a[9]; c[1][0] = a[10]; c[1][1] = a[11]; c[3][2] = a[12]; c[3][3] = a[13];
+            mma_outer<4>(s_tile, R::D1, rowB, k0, k0 + 32, c);
+            a[8] = c[0][0]; a[9] = c[0][1]; a[10] = c[1][0]; a[11] = c[1][1]; a[12] = c[3][2]; a[13] = c[3][3];
+            if (t == 0) { bias[f * 32 + g] += c[2][0]; bias[f * 32 + 8 + g] += c[2][2]; }
+        }
+        {   // A = d out (16 rows) x [h2 | ONE] -> dW3[g][2 t, +1], dW3[g + 8][..], db3
+            float c[2][4] = {};
+            const int rowB[2] = {R::H2 + g, g == 0 ? R::ONE : R::ZERO};
+            c[0][0] = a[14]; c[0][1] = a[15]; c[0][2] = a[16]; c[0][3] = a[17];
+            mma_outer<2>(s_tile, R::DO, rowB, k0, k0 + 32, c);
+            a[14] = c[0][0]; a[15] = c[0][1]; a[16] = c[0][2]; a[17] = c[0][3];
+            if (t == 0) { bias[f * 32 + 16 + g] += c[1][0]; bias[f * 32 + 24 + g] += c[1][2]; }
+        }
+        umma::st_frag<16>(col, a);
+        umma::st2(col + 16, a + 16);
+        umma::wait_st();
+    }
+    // write this warp's accumulated gradients of all nets into its own partial (packed order; C_row = 0: identity layout)
+    __device__ void readout(int n_fcnn, float* __restrict__ out) const {
+        constexpr int IN = 48, B1 = H * IN, W2 = B1 + H, B2 = W2 + H * H, W3 = B2 + H, B3 = W3 + 16 * H, PF = B3 + 16;
+        const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+        for (int f = 0; f < n_fcnn; ++f) {
+            float a[CNF_COLS];
+            umma::ld_frag<16>(tcol + CNF_COLS * f, a);
+            umma::ld2w(tcol + CNF_COLS * f + 16, a + 16);
+            float* o = out + (size_t)f * PF;
+#pragma unroll
+            for (int n = 0; n < 6; ++n) { o[g * IN + 8 * n + 2 * t] = TANH_SCALE * a[2 * n]; o[g * IN + 8 * n + 2 * t + 1] = TANH_SCALE * a[2 * n + 1]; }
+            o[W2 + g * H + 2 * t] = TANH_SCALE * a[12]; o[W2 + g * H + 2 * t + 1] = TANH_SCALE * a[13];
+            o[W3 + g * H + 2 * t] = a[14]; o[W3 + g * H + 2 * t + 1] = a[15];
+            o[W3 + (g + 8) * H + 2 * t] = a[16]; o[W3 + (g + 8) * H + 2 * t + 1] = a[17];
+            if (t == 0) {
+                o[B1 + g] = TANH_SCALE * bias[f * 32 + g]; o[B2 + g] = TANH_SCALE * bias[f * 32 + 8 + g];
+                o[B3 + g] = bias[f * 32 + 16 + g]; o[B3 + 8 + g] = bias[f * 32 + 24 + g];
+            }
+        }
+    }
+};
+
 template <int MODE>
-__global__ void __launch_bounds__(TP, MODE == MODE_CNF ? 1 : 2)   // gaussian / cos: two CTAs per SM (256 tensor-memory columns each)
+__global__ void __launch_bounds__(TP, 2)   // two CTAs per SM (256 tensor-memory columns each)
 measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, int n_flows, float p0, float p1,
                    const float* __restrict__ enc, const float* __restrict__ particles, int B, int N,
                    const float* __restrict__ g_lki, const int* __restrict__ argmax, float* __restrict__ d_particles,
@@ -413,10 +526,12 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     __shared__ uint64_t s_bar;
     __shared__ uint32_t s_tslot;
     const int tid = threadIdx.x, n_fcnn = MODE == MODE_CNF ? 4 * n_flows : 0;
+    using Tc = typename std::conditional<MODE == MODE_CNF, PeSs, PeTc>::type;   // CRNVP: SS data path (tensor-memory budget)
     constexpr int TILE_ROWS = MODE == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT;
     constexpr int TILE_FLOATS = (TILE_ROWS * TSM + 31) & ~31;   // keeps the weight tiles 128-byte aligned
-    // The gradient tile: every thread owns one column (its particle), every warp contracts over its own 32 columns, so the tile
-    // needs no CTA barrier between batches; the CRNVP tile and the encoder tile alias (warp-private columns, __syncwarp).
+    // The gradient tile: every thread owns one column (its particle), every warp contracts over its own 32 columns; the CRNVP
+    // tile and the encoder tile alias (warp-private columns, __syncwarp).  In the CRNVP kernel the SS activation tile (hi | lo,
+    // 32 KB) aliases it too: there a CTA barrier separates a batch's rounds from the tile uses before and after them.
     float* s_tile = smem;                                    // [TILE_FLOATS]
     float* s_tcw = s_tile + TILE_FLOATS;                     // tensor-core weight tiles
     float* s_pe = s_tcw + PeTc::WBWD_FLOATS;
@@ -426,14 +541,14 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     constexpr int NW = TP / 32;
     const int warp = tid >> 5;
     float* s_accpe = s_tile;                                 // [NW][AC::SIZE]   read-out staging at the very end (the tile is free then)
-    float* s_acccnf = s_hb + n_fcnn * H;                     // [NW][n_fcnn][RC::NOUT]
-    float* s_d1row = s_acccnf + NW * n_fcnn * RC::NOUT;      // [NW][n_fcnn][8] (unused sums; C_row = 0)
-    float* s_denc = s_d1row + NW * n_fcnn * H + 4;           // [NW][32]
+    float* s_cnfbias = s_hb + n_fcnn * H;                    // [NW][n_fcnn][32]  CRNVP bias gradients (t == 0 lanes)
+    float* s_denc = s_cnfbias + NW * n_fcnn * 32 + 4;        // [NW][32]
     static_assert(TILE_FLOATS % 32 == 0, "weight tiles must stay 128-byte aligned");
     static_assert(NW * AC::SIZE <= TILE_FLOATS, "read-out staging must fit in the tile");
+    static_assert(MODE != MODE_CNF || PeSs::A_FLOATS <= TILE_FLOATS, "SS activation tile must fit in the tile");
     if (tid < 32) umma::tmem_alloc<BWD_TMEM_COLS>(&s_tslot);
     if (tid == 0) umma::mbar_init(&s_bar, 1);
-    PeTc tc{s_tcw, &s_bar, 0u, 0u};
+    Tc tc = make_tc<Tc>(s_tile, s_tcw, &s_bar);
     tc.load_weights(pe, true);
     for (int e = tid; e < PE_SIZE; e += TP) {
         s_pe[e] = pe[e];
@@ -441,21 +556,22 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     if (MODE == MODE_CNF) {
         const int pf = packed_fcnn_size(16, 32);
         for (int f = 0; f < n_fcnn; ++f) load_fcnn_image<16, 32>(cnf + (size_t)f * pf, 0, s_img + f * LC::SIZE, nullptr, tid, TP);
-        for (int e = tid; e < NW * n_fcnn * RC::NOUT; e += TP) s_acccnf[e] = 0.f;
-        for (int e = tid; e < NW * n_fcnn * H; e += TP) s_d1row[e] = 0.f;
+        for (int e = tid; e < NW * n_fcnn * 32; e += TP) s_cnfbias[e] = 0.f;
     }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     tc.tmem = s_tslot;
-    const uint32_t tacc = tc.lane_addr();        // this warp's 32 lanes: gradient fragments in columns [TA_A, TA_END)
+    const uint32_t tacc = tc.lane_addr() + Tc::COLS;   // this warp's 32 lanes: gradient fragments behind the data-path columns
     {
-        float z[TA_END - TA_A];
+        float z[16];
 #pragma unroll
-        for (int i = 0; i < TA_END - TA_A; ++i) z[i] = 0.f;
-        umma::st_frag<TA_END - TA_A>(tacc + TA_A, z);
+        for (int i = 0; i < 16; ++i) z[i] = 0.f;
+        const int ncols = TA_END + (MODE == MODE_CNF ? CNF_COLS * n_fcnn : 0);
+        for (int c0 = 0; c0 < ncols; c0 += 4) umma::st4(tacc + c0, z);
         umma::wait_st();
     }
+    CnfTmemSink cnf_sink{tacc + TA_CNF, s_cnfbias + warp * n_fcnn * 32};
     float rs3_prev[4] = {0.f, 0.f, 0.f, 0.f};    // Gaussian mode, t == 0 lanes: running delta3 sums of earlier trajectories
     if (MODE == MODE_CNF) hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
 
@@ -478,6 +594,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         float g_next = g_lki[base + (tid < N ? tid : 0)];
         for (int n0 = 0; n0 < N; n0 += TP) {
             asm volatile("" ::: "memory");  // no LICM of shared-memory weight loads across particles
+            if (MODE == MODE_CNF) __syncthreads();   // SS activation tile aliases the gradient tile the previous batch contracted over
             const int n = n0 + tid;
             const bool live = n < N;
             const size_t p = base + (live ? n : 0);
@@ -533,8 +650,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                 for (int st = 2 * n_flows - 1; st >= 0; --st) {         // walk the forward stages back; one inlined stage body
                     const float* im = s_img + 2 * st * LC::SIZE;
                     const float* hb = s_hb + 2 * st * H;
-                    stage_bwd<16, 32>(im, im + LC::SIZE, hb, hb + H, 2 * st, false, live, lo, glo, e, de, up, gup, g, s_tile,
-                                      s_acccnf + warp * n_fcnn * RC::NOUT, s_d1row + warp * n_fcnn * H);
+                    stage_bwd<16, 32>(im, im + LC::SIZE, hb, hb + H, 2 * st, false, live, lo, glo, e, de, up, gup, g, s_tile, cnf_sink);
                     swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
                 }
                 swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
@@ -545,16 +661,17 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 #pragma unroll
                     for (int k = 0; k < 32; ++k) de[k] = 0.f;
                 }
+                __syncthreads();            // every warp is done with the CRNVP tile before the (aliasing) SS activation tile is rewritten
             }
             // encoder backward, tensor-core rounds 3-4: d a2 = W3^T delta3, d a1 = W2^T delta2
             float d2[32], d1[16];
-            tc.store_row<32>(de);
-            tc.round<32, 32>(PeTc::W3T_HI, PeTc::W3T_LO);
+            tc.template store_row<32>(de);
+            tc.template round<32, 32>(PeTc::W3T_HI, PeTc::W3T_LO);
             umma::ld32(tc.lane_addr(), d2);
 #pragma unroll
             for (int j = 0; j < 32; ++j) d2[j] = a2[j] > 0.f ? d2[j] : 0.f;
-            tc.store_row<32>(d2);
-            tc.round<16, 32>(PeTc::W2T_HI, PeTc::W2T_LO);
+            tc.template store_row<32>(d2);
+            tc.template round<16, 32>(PeTc::W2T_HI, PeTc::W2T_LO);
             umma::ld16(tc.lane_addr(), d1);
             float dx0 = 0.f, dx1 = 0.f;
 #pragma unroll
@@ -616,21 +733,14 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     for (int e = tid; e < NW * AC::SIZE; e += TP) s_accpe[e] = 0.f;
     __syncthreads();
     pe_weight_grads_readout(tacc, s_accpe + warp * AC::SIZE);
+    if (MODE == MODE_CNF)     // every warp writes its own partial: NW partial gradients per CTA
+        cnf_sink.readout(n_fcnn, part_cnf + ((size_t)blockIdx.x * NW + warp) * n_fcnn * packed_fcnn_size(16, 32));
     umma::fence_before_sync();
     __syncthreads();
     if (tid < 32) umma::tmem_free<BWD_TMEM_COLS>(tc.tmem);
     for (int e = tid; e < PE_SIZE; e += TP) {
         const float* a = s_accpe + AC::of_packed(e);
         part_pe[(size_t)blockIdx.x * PE_SIZE + e] = (a[0] + a[AC::SIZE]) + (a[2 * AC::SIZE] + a[3 * AC::SIZE]);
-    }
-    if (MODE == MODE_CNF) {
-        const int pf = packed_fcnn_size(16, 32);
-        float* out = part_cnf + (size_t)blockIdx.x * n_fcnn * pf;
-        for (int e = tid; e < n_fcnn * RC::NOUT; e += TP) {
-            float a = s_acccnf[e];
-            for (int w = 1; w < NW; ++w) a += s_acccnf[w * n_fcnn * RC::NOUT + e];
-            out[(size_t)(e / RC::NOUT) * pf + packed_offset<16, 32>(e % RC::NOUT, 0)] = a * grad_out_scale<16, 32>(e % RC::NOUT);
-        }
     }
 }
 
@@ -640,11 +750,11 @@ static size_t fwd_smem(int mode, int n_flows, int N) {
 }
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    size_t tile = (size_t)(mode == MODE_CNF && RC::TROWS > PR::COUNT ? RC::TROWS : PR::COUNT) * TSM;
+    size_t tile = (size_t)PR::COUNT * TSM;
+    if (mode == MODE_CNF && (size_t)RC::TROWS * TSM > tile) tile = (size_t)RC::TROWS * TSM;
     tile = (tile + 31) & ~(size_t)31;
-    const int nw = TP / 32;   // per-warp accumulator copies
-    size_t fl = tile + PeTc::WBWD_FLOATS + (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H +
-                (size_t)nw * n_fcnn * RC::NOUT + (size_t)nw * n_fcnn * H + 4 + nw * 32;
+    const int nw = TP / 32;
+    size_t fl = tile + PeTc::WBWD_FLOATS + (size_t)PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + (size_t)nw * n_fcnn * 32 + 4 + nw * 32;
     return fl * sizeof(float);
 }
 
@@ -679,7 +789,7 @@ static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, fl
     if (rc) return rc;
     rc = launch_reduce_partials(part_pe, grid, PE_SIZE, d_pe, st);
     if (rc) return rc;
-    if (MODE == MODE_CNF) rc = launch_reduce_partials(part_cnf, grid, 4 * n_flows * packed_fcnn_size(16, 32), d_cnf, st);
+    if (MODE == MODE_CNF) rc = launch_reduce_partials(part_cnf, grid * (TP / 32), 4 * n_flows * packed_fcnn_size(16, 32), d_cnf, st);
     return rc;
 }
 
@@ -708,7 +818,7 @@ extern "C" int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* 
 extern "C" int64_t nfdpf_measure_bwd_workspace(int mode, int n_flows, int B, int N) {
     (void)N;
     if (B < 1) return 0;
-    int64_t per = PE_SIZE + (mode == MODE_CNF ? 4 * n_flows * packed_fcnn_size(16, 32) : 0);
+    int64_t per = PE_SIZE + (mode == MODE_CNF ? (TP / 32) * 4 * n_flows * packed_fcnn_size(16, 32) : 0);   // CRNVP: one partial per warp
     return (int64_t)measure_bwd_grid(mode, B) * per * (int64_t)sizeof(float);
 }
 

@@ -159,6 +159,15 @@ __device__ __forceinline__ void ld16w(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void ld2w(uint32_t taddr, float* v) {
+    uint32_t r[2];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+    wait_ld();
+    v[0] = __uint_as_float(r[0]); v[1] = __uint_as_float(r[1]);
+}
+__device__ __forceinline__ void st2(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])) : "memory");
+}
 __device__ __forceinline__ void st4(uint32_t taddr, const float* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])),
                  "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
