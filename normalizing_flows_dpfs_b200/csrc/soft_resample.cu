@@ -190,17 +190,62 @@ soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __r
     const float c = block_allreduce(part, s_red, OpSum(), 0.f);
     for (int i = tid; i < N; i += nt) s_a[i].x = hard ? 0.f : (s_a[i].x - c) / S2;   // dL/dv_i, v_i = w_is[idx_i]
     __syncthreads();
-    float4* src = s_a;
-    float4* dst = s_b;
-    for (int o = 1; o < N; o <<= 1) {
-        for (int i = tid; i < N; i += nt) {
-            float4 v = src[i];
-            if (i >= o && s_idx[i - o] == s_idx[i]) { const float4 u = src[i - o]; v.x += u.x; v.y += u.y; v.z += u.z; }
-            dst[i] = v;
+    // Segmented inclusive scan of s_a over the runs of equal s_idx, three levels (a Hillis-Steele pass over all N elements cost
+    // log2 N rounds of shared-memory traffic and barriers): (1) every thread scans its own chunk of consecutive destinations in
+    // place; (2) the chunk tails (key of the last element, sum of its run inside the chunk) are scanned across threads with
+    // warp shuffles and one cross-warp step -- a tail continues the previous thread's tail iff the chunk holds a single key
+    // equal to it; (3) the resulting carry is added to the chunk's leading run.  fp32, fixed order.
+    {
+        __shared__ float s_wt[96];                            // cross-warp scratch: [32] x 3 tail sums / run totals
+        __shared__ int s_wi[64];                              // [32] segment-start flags, [32] last keys
+        const int lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
+        const int per = (N + nt - 1) / nt;
+        const int lo = min(tid * per, N), hi = min(lo + per, N);
+        float tx = 0.f, ty = 0.f, tz = 0.f;
+        int kprev = -1;
+        for (int i = lo; i < hi; ++i) {
+            const int k = s_idx[i];
+            float4 v = s_a[i];
+            if (k == kprev) { v.x += tx; v.y += ty; v.z += tz; s_a[i] = v; }
+            tx = v.x; ty = v.y; tz = v.z; kprev = k;
         }
+        const bool has = hi > lo;
+        const int kfirst = has ? s_idx[lo] : -2, klast = has ? kprev : -3;      // empty chunks (only at the end) never match anything
+        if (lane == 31) s_wi[32 + wid] = klast;
         __syncthreads();
-        float4* t = src; src = dst; dst = t;
+        int kleft = __shfl_up_sync(FULL, klast, 1);
+        if (lane == 0) kleft = wid > 0 ? s_wi[32 + wid - 1] : -4;
+        const bool cont = has && kfirst == kleft;                 // the chunk's leading run continues the previous chunk's tail
+        int start = !(cont && kfirst == klast);                   // the tail starts a new segment unless the whole chunk continues it
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float ux = __shfl_up_sync(FULL, tx, o), uy = __shfl_up_sync(FULL, ty, o), uz = __shfl_up_sync(FULL, tz, o);
+            const int us = __shfl_up_sync(FULL, start, o);
+            if (lane >= o && !start) { tx += ux; ty += uy; tz += uz; start = us; }
+        }
+        if (lane == 31) { s_wt[wid] = tx; s_wt[32 + wid] = ty; s_wt[64 + wid] = tz; s_wi[wid] = start; }
+        __syncthreads();
+        if (!start && wid > 0) {                                  // segment reaches back beyond this warp: add the earlier warps' tails
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+            for (int w = wid - 1; w >= 0; --w) {
+                cx += s_wt[w]; cy += s_wt[32 + w]; cz += s_wt[64 + w];
+                if (s_wi[w]) break;
+            }
+            tx += cx; ty += cy; tz += cz;
+        }
+        // (tx, ty, tz) = total of the run that ends with this chunk's tail; the next chunk's leading run continues it
+        float px = __shfl_up_sync(FULL, tx, 1), py = __shfl_up_sync(FULL, ty, 1), pz = __shfl_up_sync(FULL, tz, 1);
+        __syncthreads();                                          // s_wt reuse
+        if (lane == 31) { s_wt[wid] = tx; s_wt[32 + wid] = ty; s_wt[64 + wid] = tz; }
+        __syncthreads();
+        if (lane == 0 && wid > 0) { px = s_wt[wid - 1]; py = s_wt[32 + wid - 1]; pz = s_wt[64 + wid - 1]; }
+        if (cont) {
+            for (int i = lo; i < hi && s_idx[i] == kfirst; ++i) { float4 v = s_a[i]; v.x += px; v.y += py; v.z += pz; s_a[i] = v; }
+        }
+        (void)nwarp;
+        __syncthreads();
     }
+    float4* src = s_a;
     // src[i] = inclusive segmented sums; a run ends at i when the next key differs
     for (int j = tid; j < N; j += nt) {
         d_probs[base + j] = 0.f;
