@@ -113,6 +113,41 @@ __device__ __forceinline__ void tanh_prescaled_pair(float a, float b, float& ta,
     tb = fmaf(-2.0f * u, r, 1.0f);
 }
 // ex2.approx(x * log2e): 2 ulp + |x| 2^-23 relative -- ~5e-7 for the |s| < 5 log-scales of the coupling stages (bar: rtol 1e-4)
+// Packed FP32 pair FMA (Blackwell FFMA2): (a0, a1) += (x0, x1) * (y0, y1) in ONE issue slot -- same FMA rate as two FFMAs
+// (measured, tools/ffma2_probe.cu), half the instructions.  Operands are aligned 64-bit register pairs; the packs / unpacks
+// below vanish when the register allocator keeps the two floats adjacent (accumulators that live in pairs across a loop do).
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long p;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(lo), "f"(hi));
+    return p;
+}
+// (a0, a1) += s * (y0, y1)  and  (a0, a1) += (x0, x1) * (y0, y1)  (the scalar form compiles to FFMA2 with a broadcast operand)
+__device__ __forceinline__ void ffma2_s(float& a0, float& a1, float s, float y0, float y1) {
+    unsigned long long a = pack2(a0, a1);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(pack2(s, s)), "l"(pack2(y0, y1)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+__device__ __forceinline__ void ffma2_p(float& a0, float& a1, float x0, float x1, float y0, float y1) {
+    unsigned long long a = pack2(a0, a1);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(pack2(x0, x1)), "l"(pack2(y0, y1)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+// (r0, r1) = (x0, x1) * (y0, y1) + (z0, z1)
+__device__ __forceinline__ void fma2_p(float& r0, float& r1, float x0, float x1, float y0, float y1, float z0, float z1) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pack2(x0, x1)), "l"(pack2(y0, y1)), "l"(pack2(z0, z1)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+}
+__device__ __forceinline__ void fmul2_p(float& r0, float& r1, float x0, float x1, float y0, float y1) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pack2(x0, x1)), "l"(pack2(y0, y1)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
+}
+__device__ __forceinline__ void ffma2(float& a0, float& a1, unsigned long long x, unsigned long long y) {
+    unsigned long long a = pack2(a0, a1);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(x), "l"(y));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
 __device__ __forceinline__ float exp_acc(float x) { return __expf(x); }
 
 }  // namespace nfdpf

@@ -264,16 +264,18 @@ __device__ __forceinline__ void stage_fwd(const float* img_t, const float* img_s
 template <int HALF, int CP, bool PAIRED>
 __device__ __forceinline__ void fcnn_fwd_x2(const float* __restrict__ img, const float* __restrict__ hb, const float (&c)[2][HALF],
                                             const float (&pc)[2][CP > 0 ? CP : 1], float (&out)[2][HALF]) {
+    // the two particles form the packed FP32 pair of every FMA: (a_p0, a_p1) += w * (x_p0, x_p1) is ONE FFMA2 with the weight
+    // as its broadcast operand -- half the FMA issue slots of the (issue-bound) forward kernel
     using L = Lay<HALF, CP>;
     float hbv[8];
     ld8(hb, hbv);
-    float in[2][L::IN1], h1[2][H], h2[2][H];
+    float in[L::IN1][2], h1[H][2], h2[H][2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
 #pragma unroll
-        for (int i = 0; i < HALF; ++i) in[q][i] = c[q][i];
+        for (int i = 0; i < HALF; ++i) in[i][q] = c[q][i];
 #pragma unroll
-        for (int i = 0; i < CP; ++i) in[q][HALF + i] = pc[q][i];
+        for (int i = 0; i < CP; ++i) in[HALF + i][q] = pc[q][i];
     }
 #pragma unroll
     for (int k = 0; k < H; ++k) {
@@ -285,10 +287,10 @@ __device__ __forceinline__ void fcnn_fwd_x2(const float* __restrict__ img, const
             const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if (i + u < L::IN1) { a0 = fmaf(wv[u], in[0][i + u < L::IN1 ? i + u : 0], a0); a1 = fmaf(wv[u], in[1][i + u < L::IN1 ? i + u : 0], a1); }
+                if (i + u < L::IN1) ffma2_s(a0, a1, wv[u], in[i + u < L::IN1 ? i + u : 0][0], in[i + u < L::IN1 ? i + u : 0][1]);
         }
-        if (PAIRED) tanh_prescaled_pair(a0, a1, h1[0][k], h1[1][k]);
-        else { h1[0][k] = tanh_prescaled(a0); h1[1][k] = tanh_prescaled(a1); }
+        if (PAIRED) tanh_prescaled_pair(a0, a1, h1[k][0], h1[k][1]);
+        else { h1[k][0] = tanh_prescaled(a0); h1[k][1] = tanh_prescaled(a1); }
     }
     float b2[8];
     ld8(img + L::B2, b2);
@@ -298,9 +300,9 @@ __device__ __forceinline__ void fcnn_fwd_x2(const float* __restrict__ img, const
         ld8(img + L::W2 + j * H, w);
         float a0 = b2[j], a1 = b2[j];
 #pragma unroll
-        for (int k = 0; k < H; ++k) { a0 = fmaf(w[k], h1[0][k], a0); a1 = fmaf(w[k], h1[1][k], a1); }
-        if (PAIRED) tanh_prescaled_pair(a0, a1, h2[0][j], h2[1][j]);
-        else { h2[0][j] = tanh_prescaled(a0); h2[1][j] = tanh_prescaled(a1); }
+        for (int k = 0; k < H; ++k) ffma2_s(a0, a1, w[k], h1[k][0], h1[k][1]);
+        if (PAIRED) tanh_prescaled_pair(a0, a1, h2[j][0], h2[j][1]);
+        else { h2[j][0] = tanh_prescaled(a0); h2[j][1] = tanh_prescaled(a1); }
     }
 #pragma unroll
     for (int o = 0; o < HALF; ++o) {
@@ -308,7 +310,7 @@ __device__ __forceinline__ void fcnn_fwd_x2(const float* __restrict__ img, const
         ld8(img + L::W3 + o * H, w);
         float a0 = img[L::B3 + o], a1 = a0;
 #pragma unroll
-        for (int j = 0; j < H; ++j) { a0 = fmaf(w[j], h2[0][j], a0); a1 = fmaf(w[j], h2[1][j], a1); }
+        for (int j = 0; j < H; ++j) ffma2_s(a0, a1, w[j], h2[j][0], h2[j][1]);
         out[0][o] = a0; out[1][o] = a1;
     }
 }

@@ -85,16 +85,96 @@ __device__ __forceinline__ void warp_reduce_b1(float (&acc)[NACC], float* s_d1pa
     if ((lane & 3) == 0) s_d1part_e[warp * H + (lane >> 2)] = v[0];   // lane bits 4,3,2 select the entry index
 }
 
+// FCNN 1 -> 8 -> 8 -> 1 forward / backward for this kernel, on packed FP32 pairs (FFMA2: two FMAs per issue slot; the kernel is
+// short of issue slots and latency, not of FMA throughput).  Same arithmetic as fcnn_fwd / fcnn_bwd<1,0> up to summation order:
+// the 8-term dot products are accumulated as (even, odd) partial sums.
+__device__ __forceinline__ void fwd_d2(const float* __restrict__ img, const float* __restrict__ hb, float c, float (&h1)[H], float (&h2)[H],
+                                       float& out) {
+    using L = L2_;
+    float hbv[8], a[H];
+    ld8(hb, hbv);
+#pragma unroll
+    for (int k = 0; k < H; ++k) a[k] = fmaf(img[L::W1 + k * L::S1], c, hbv[k]);
+#pragma unroll
+    for (int k = 0; k < H; k += 2) tanh_prescaled_pair(a[k], a[k + 1], h1[k], h1[k + 1]);
+    float b2[8];
+    ld8(img + L::B2, b2);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float w[8];
+        ld8(img + L::W2 + j * H, w);
+        float p0 = b2[j], p1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < H; k += 2) ffma2_p(p0, p1, w[k], w[k + 1], h1[k], h1[k + 1]);
+        a[j] = p0 + p1;
+    }
+#pragma unroll
+    for (int j = 0; j < H; j += 2) tanh_prescaled_pair(a[j], a[j + 1], h2[j], h2[j + 1]);
+    float w3[8];
+    ld8(img + L::W3, w3);
+    float p0 = img[L::B3], p1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < H; j += 2) ffma2_p(p0, p1, w3[j], w3[j + 1], h2[j], h2[j + 1]);
+    out = p0 + p1;
+}
+
+// d1 / d2 = pre-activation grads DIVIDED BY TANH_SCALE (scaled layer-1/2 images, see coupling.cuh); dc = d out / d c
+__device__ __forceinline__ void bwd_d2(const float* __restrict__ img, float dout, const float (&h1)[H], const float (&h2)[H], float (&d1)[H],
+                                       float (&d2)[H], float& dc) {
+    using L = L2_;
+    float w3[8];
+    ld8(img + L::W3, w3);
+#pragma unroll
+    for (int j = 0; j < H; j += 2) {
+        float g0, g1, t0, t1;
+        fmul2_p(t0, t1, -TANH_ISCALE, -TANH_ISCALE, h2[j], h2[j + 1]);
+        fma2_p(g0, g1, t0, t1, h2[j], h2[j + 1], TANH_ISCALE, TANH_ISCALE);          // (1 - h2^2) / scale
+        fmul2_p(t0, t1, dout, dout, w3[j], w3[j + 1]);
+        fmul2_p(d2[j], d2[j + 1], t0, t1, g0, g1);
+    }
+    float da[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) da[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float w[8];
+        ld8(img + L::W2 + j * H, w);
+#pragma unroll
+        for (int k = 0; k < H; k += 2) ffma2_s(da[k], da[k + 1], d2[j], w[k], w[k + 1]);
+    }
+    float part = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; k += 2) {
+        float g0, g1, t0, t1;
+        fmul2_p(t0, t1, -TANH_ISCALE, -TANH_ISCALE, h1[k], h1[k + 1]);
+        fma2_p(g0, g1, t0, t1, h1[k], h1[k + 1], TANH_ISCALE, TANH_ISCALE);
+        fmul2_p(d1[k], d1[k + 1], da[k], da[k + 1], g0, g1);
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) part = fmaf(img[L::W1 + k * L::S1], d1[k], part);
+    dc = part;
+}
+
 __device__ __forceinline__ void accumulate(float (&acc)[NACC], const float (&d1)[H], const float (&d2)[H], float dout, float c,
                                            const float (&h1)[H], const float (&h2)[H]) {
 #pragma unroll
-    for (int k = 0; k < H; ++k) { acc[k] = fmaf(d1[k], c, acc[k]); acc[H + k] += d1[k]; }
+    for (int k = 0; k < H; k += 2) {
+        ffma2_s(acc[k], acc[k + 1], c, d1[k], d1[k + 1]);
+        ffma2_s(acc[H + k], acc[H + k + 1], 1.0f, d1[k], d1[k + 1]);
+    }
+    unsigned long long h1p[H / 2];      // (h1[k], h1[k+1]) pairs: packed once, used by all eight rows of dW2
+#pragma unroll
+    for (int k = 0; k < H; k += 2) h1p[k / 2] = pack2(h1[k], h1[k + 1]);
 #pragma unroll
     for (int j = 0; j < H; ++j) {
+        const unsigned long long dj = pack2(d2[j], d2[j]);
 #pragma unroll
-        for (int k = 0; k < H; ++k) acc[2 * H + j * H + k] = fmaf(d2[j], h1[k], acc[2 * H + j * H + k]);
-        acc[2 * H + H * H + j] += d2[j];
-        acc[3 * H + H * H + j] = fmaf(dout, h2[j], acc[3 * H + H * H + j]);
+        for (int k = 0; k < H; k += 2) ffma2(acc[2 * H + j * H + k], acc[2 * H + j * H + k + 1], dj, h1p[k / 2]);
+    }
+#pragma unroll
+    for (int j = 0; j < H; j += 2) {
+        ffma2_s(acc[2 * H + H * H + j], acc[2 * H + H * H + j + 1], 1.0f, d2[j], d2[j + 1]);
+        ffma2_s(acc[3 * H + H * H + j], acc[3 * H + H * H + j + 1], dout, h2[j], h2[j + 1]);
     }
     acc[4 * H + H * H] += dout;
 }
@@ -181,7 +261,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
                     const bool live = m * GRP + gi < n_live;
                     const float c[1] = {s_c[q]};
                     float h1[H], h2[H], out[1];
-                    fcnn_fwd<1, 0, true>(img, hb, c, nullptr, h1, h2, out);
+                    fwd_d2(img, hb, c[0], h1, h2, out[0]);
                     float gv_old = 0.f;
                     if (grp == 0) { s_xt[par + gi] = out[0]; gv_old = s_gv[q]; }
                     else          { s_xs[par + gi] = out[0]; }
@@ -192,8 +272,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
                     if (grp == 0) {         // t-net: d t = g_v (forward direction) or -g_v e^{-s} (inverse direction)
                         float dt = inverse ? -gv_old * exp_acc(-s_xs[par + gi]) : gv_old;
                         if (!live) dt = 0.f;
-                        const float dout[1] = {dt};
-                        fcnn_bwd<1, 0>(img, dout, h1, h2, d1, d2, dc, nullptr);
+                        bwd_d2(img, dt, h1, h2, d1, d2, dc[0]);
                         s_dct[par + gi] = dc[0];
                         accumulate(acc, d1, d2, dt, c[0], h1, h2);
                     } else {                // s-net: inverts the stage, owns the state update
@@ -206,8 +285,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
                         else          { gin = gv * ies; ds = -fmaf(gv, v, gld); vin = fmaf(v, es, t); }
                         if (!live) ds = 0.f;
                         s_v[q] = vin; s_gv[q] = gin;
-                        const float dout[1] = {ds};
-                        fcnn_bwd<1, 0>(img, dout, h1, h2, d1, d2, dc, nullptr);
+                        bwd_d2(img, ds, h1, h2, d1, d2, dc[0]);
                         s_gc[q] += dc[0];
                         prev_q = q;
                         accumulate(acc, d1, d2, ds, c[0], h1, h2);
