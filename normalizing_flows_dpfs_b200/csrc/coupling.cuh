@@ -115,25 +115,27 @@ template <int HALF, int CP, bool PAIRED = false>
 __device__ __forceinline__ void fcnn_fwd(const float* __restrict__ img, const float* __restrict__ hb, const float (&c)[HALF],
                                          const float* pc, float (&h1)[H], float (&h2)[H], float (&out)[HALF]) {
     using L = Lay<HALF, CP>;
+    // dot products on packed FP32 pairs (FFMA2): (even, odd) partial sums over the input index, one horizontal add at the end
     float hbv[8];
     ld8(hb, hbv);
-    float in[L::IN1];
+    float in[L::S1];                       // zero padded like the W1 rows
 #pragma unroll
     for (int i = 0; i < HALF; ++i) in[i] = c[i];
 #pragma unroll
     for (int i = 0; i < CP; ++i) in[HALF + i] = pc[i];
 #pragma unroll
+    for (int i = L::IN1; i < L::S1; ++i) in[i] = 0.f;
+#pragma unroll
     for (int k = 0; k < H; ++k) {
-        float a = hbv[k];
+        float p0 = hbv[k], p1 = 0.f;
         const float* w = img + L::W1 + k * L::S1;
 #pragma unroll
         for (int i = 0; i < L::S1; i += 4) {  // rows are zero-padded to a multiple of 4
             const float4 w4 = *reinterpret_cast<const float4*>(w + i);
-            if (i + 0 < L::IN1) a = fmaf(w4.x, in[i + 0 < L::IN1 ? i + 0 : 0], a);
-            if (i + 1 < L::IN1) a = fmaf(w4.y, in[i + 1 < L::IN1 ? i + 1 : 0], a);
-            if (i + 2 < L::IN1) a = fmaf(w4.z, in[i + 2 < L::IN1 ? i + 2 : 0], a);
-            if (i + 3 < L::IN1) a = fmaf(w4.w, in[i + 3 < L::IN1 ? i + 3 : 0], a);
+            if (i < L::IN1) ffma2_p(p0, p1, w4.x, w4.y, in[i], in[i + 1]);
+            if (i + 2 < L::IN1) ffma2_p(p0, p1, w4.z, w4.w, in[i + 2], in[i + 3]);
         }
+        const float a = p0 + p1;
         h1[k] = PAIRED ? a : tanh_prescaled(a);
     }
     if (PAIRED) {
@@ -146,9 +148,10 @@ __device__ __forceinline__ void fcnn_fwd(const float* __restrict__ img, const fl
     for (int j = 0; j < H; ++j) {
         float w[8];
         ld8(img + L::W2 + j * H, w);
-        float a = b2[j];
+        float p0 = b2[j], p1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < H; ++k) a = fmaf(w[k], h1[k], a);
+        for (int k = 0; k < H; k += 2) ffma2_p(p0, p1, w[k], w[k + 1], h1[k], h1[k + 1]);
+        const float a = p0 + p1;
         h2[j] = PAIRED ? a : tanh_prescaled(a);
     }
     if (PAIRED) {
@@ -159,10 +162,10 @@ __device__ __forceinline__ void fcnn_fwd(const float* __restrict__ img, const fl
     for (int o = 0; o < HALF; ++o) {
         float w[8];
         ld8(img + L::W3 + o * H, w);
-        float a = img[L::B3 + o];
+        float p0 = img[L::B3 + o], p1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < H; ++j) a = fmaf(w[j], h2[j], a);
-        out[o] = a;
+        for (int j = 0; j < H; j += 2) ffma2_p(p0, p1, w[j], w[j + 1], h2[j], h2[j + 1]);
+        out[o] = p0 + p1;
     }
 }
 
@@ -172,6 +175,7 @@ template <int HALF, int CP>
 __device__ __forceinline__ void fcnn_bwd(const float* __restrict__ img, const float (&dout)[HALF], const float (&h1)[H],
                                          const float (&h2)[H], float (&d1)[H], float (&d2)[H], float (&dc)[HALF], float* dpc) {
     using L = Lay<HALF, CP>;
+    // matrix-transpose products on packed FP32 pairs (FFMA2): the delta is the broadcast operand, consecutive weights the pair
     float da2[H];
 #pragma unroll
     for (int j = 0; j < H; ++j) da2[j] = 0.f;
@@ -180,7 +184,7 @@ __device__ __forceinline__ void fcnn_bwd(const float* __restrict__ img, const fl
         float w[8];
         ld8(img + L::W3 + o * H, w);
 #pragma unroll
-        for (int j = 0; j < H; ++j) da2[j] = fmaf(w[j], dout[o], da2[j]);
+        for (int j = 0; j < H; j += 2) ffma2_s(da2[j], da2[j + 1], dout[o], w[j], w[j + 1]);
     }
 #pragma unroll
     for (int j = 0; j < H; ++j) d2[j] = da2[j] * fmaf(-TANH_ISCALE * h2[j], h2[j], TANH_ISCALE);   // delta2 / scale
@@ -192,21 +196,39 @@ __device__ __forceinline__ void fcnn_bwd(const float* __restrict__ img, const fl
         float w[8];
         ld8(img + L::W2 + j * H, w);
 #pragma unroll
-        for (int k = 0; k < H; ++k) da1[k] = fmaf(w[k], d2[j], da1[k]);
+        for (int k = 0; k < H; k += 2) ffma2_s(da1[k], da1[k + 1], d2[j], w[k], w[k + 1]);
     }
 #pragma unroll
     for (int k = 0; k < H; ++k) d1[k] = da1[k] * fmaf(-TANH_ISCALE * h1[k], h1[k], TANH_ISCALE);   // delta1 / scale (W2 image is scaled: W2s^T (d2/s) = W2^T d2)
+    if constexpr (HALF % 2 == 0 && CP % 2 == 0) {   // d in = W1^T d1 straight into the (even-sized) gradient arrays, two inputs per FFMA2
 #pragma unroll
-    for (int k = 0; k < H; ++k) {   // d in = W1^T d1, 128-bit weight loads (rows are zero-padded to a multiple of 4)
-        const float* w = img + L::W1 + k * L::S1;
+        for (int k = 0; k < H; ++k) {
+            const float* w = img + L::W1 + k * L::S1;
 #pragma unroll
-        for (int i = 0; i < L::S1; i += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(w + i);
-            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+            for (int i = 0; i < L::S1; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(w + i);
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (i + u < HALF) dc[i + u < HALF ? i + u : 0] = fmaf(wv[u], d1[k], dc[i + u < HALF ? i + u : 0]);
-                else if (i + u < HALF + CP) dpc[i + u >= HALF ? i + u - HALF : 0] = fmaf(wv[u], d1[k], dpc[i + u >= HALF ? i + u - HALF : 0]);
+                for (int u = 0; u < 4; u += 2) {
+                    if (i + u < HALF) ffma2_s(dc[i + u < HALF ? i + u : 0], dc[i + u < HALF ? i + u + 1 : 1], d1[k], wv[u], wv[u + 1]);
+                    else if (i + u < HALF + CP)
+                        ffma2_s(dpc[i + u >= HALF ? i + u - HALF : 0], dpc[i + u >= HALF ? i + u - HALF + 1 : 1], d1[k], wv[u], wv[u + 1]);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < H; ++k) {   // d in = W1^T d1, 128-bit weight loads (rows are zero-padded to a multiple of 4)
+            const float* w = img + L::W1 + k * L::S1;
+#pragma unroll
+            for (int i = 0; i < L::S1; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(w + i);
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (i + u < HALF) dc[i + u < HALF ? i + u : 0] = fmaf(wv[u], d1[k], dc[i + u < HALF ? i + u : 0]);
+                    else if (i + u < HALF + CP) dpc[i + u >= HALF ? i + u - HALF : 0] = fmaf(wv[u], d1[k], dpc[i + u >= HALF ? i + u - HALF : 0]);
+                }
             }
         }
     }
