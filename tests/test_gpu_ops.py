@@ -194,7 +194,10 @@ def test_measurement_golden(golden):
 
 @pytest.mark.parametrize("mode,B,N,fused", [("gaussian", 3, 200, True), ("cos", 3, 200, True), ("CRNVP", 3, 200, True),
                                             ("gaussian", 2, 50, False), ("CRNVP", 2, 129, False), ("gaussian", 16, 1024, True),
-                                            ("CRNVP", 8, 1024, True)])
+                                            ("CRNVP", 8, 1024, True),
+                                            # more trajectories than persistent CTAs (2 x 148): every CTA walks several trajectories, its
+                                            # tensor-memory gradient accumulators and the per-trajectory d_enc increments carry across them
+                                            ("gaussian", 700, 200, True), ("cos", 650, 130, False), ("CRNVP", 600, 129, True)])
 def test_measure_update_vs_oracle(mode, B, N, fused):
     g = torch.Generator().manual_seed(hash((mode, B, N)) % 1000)
     pe = torch.cat([torch.randn(n, generator=g) * s for n, s in ((32, 0.3), (16, 0.1), (512, 0.3), (32, 0.1), (1024, 0.2), (32, 0.1))])
