@@ -19,7 +19,8 @@ namespace nfdpf {
 using L2_ = Lay<1, 0>;
 constexpr int NACC = 97;          // == Rows<1,0>::NOUT, same ordering as packed_offset<1,0>
 constexpr int TPD = 256;          // threads per CTA: two net-groups of four warps, one CTA per SM
-constexpr int GRP = 128;          // threads per net-group == particles per iteration
+constexpr int GRP = 128;          // threads per net-group
+constexpr int PPI = 2 * GRP;      // particles per iteration: two per thread (q, q + GRP)
 constexpr int CHUNK = 1024;       // particles per entry
 constexpr int NWARP = TPD / 32;
 constexpr int E_CAP = 9;          // upper bound of resident entries (the launcher fits E_MAX <= E_CAP into shared memory)
@@ -27,7 +28,7 @@ constexpr int E_CAP = 9;          // upper bound of resident entries (the launch
 struct D2Smem {
     static size_t fixed_floats(int n_fcnn, int C_row) {
         return (size_t)n_fcnn * L2_::SIZE + (size_t)n_fcnn * H * C_row        // images, w1r
-               + 6 * GRP                                                       // exchange: t, s, dc_t (double buffered)
+               + 12 * GRP                                                      // exchange: t, s, dc_t (two particles per thread, double buffered)
                + NWARP * 100                                                   // per-warp reduction slots
                + (size_t)n_fcnn * NACC + 8;                                    // acc
     }
@@ -155,6 +156,99 @@ __device__ __forceinline__ void bwd_d2(const float* __restrict__ img, float dout
     dc = part;
 }
 
+// Two particles per thread: the pair (particle 0, particle 1) is the packed operand of every FMA, the weight its broadcast
+// scalar -- every weight is loaded once per two particles and no value ever needs re-packing.  Arrays are [unit][particle].
+__device__ __forceinline__ void fwd_d2x2(const float* __restrict__ img, const float* __restrict__ hb, float c0, float c1, float (&h1)[H][2],
+                                         float (&h2)[H][2], float (&out)[2]) {
+    using L = L2_;
+    float hbv[8];
+    ld8(hb, hbv);
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        float a0 = hbv[k], a1 = hbv[k];
+        ffma2_s(a0, a1, img[L::W1 + k * L::S1], c0, c1);
+        tanh_prescaled_pair(a0, a1, h1[k][0], h1[k][1]);
+    }
+    float b2[8];
+    ld8(img + L::B2, b2);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float w[8];
+        ld8(img + L::W2 + j * H, w);
+        float a0 = b2[j], a1 = b2[j];
+#pragma unroll
+        for (int k = 0; k < H; ++k) ffma2_s(a0, a1, w[k], h1[k][0], h1[k][1]);
+        tanh_prescaled_pair(a0, a1, h2[j][0], h2[j][1]);
+    }
+    float w3[8];
+    ld8(img + L::W3, w3);
+    float o0 = img[L::B3], o1 = o0;
+#pragma unroll
+    for (int j = 0; j < H; ++j) ffma2_s(o0, o1, w3[j], h2[j][0], h2[j][1]);
+    out[0] = o0; out[1] = o1;
+}
+
+__device__ __forceinline__ void bwd_d2x2(const float* __restrict__ img, float dout0, float dout1, const float (&h1)[H][2],
+                                         const float (&h2)[H][2], float (&d1)[H][2], float (&d2)[H][2], float (&dc)[2]) {
+    using L = L2_;
+    float w3[8];
+    ld8(img + L::W3, w3);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float g0, g1, t0, t1;
+        fmul2_p(t0, t1, -TANH_ISCALE, -TANH_ISCALE, h2[j][0], h2[j][1]);
+        fma2_p(g0, g1, t0, t1, h2[j][0], h2[j][1], TANH_ISCALE, TANH_ISCALE);          // (1 - h2^2) / scale
+        fmul2_p(t0, t1, w3[j], w3[j], dout0, dout1);
+        fmul2_p(d2[j][0], d2[j][1], t0, t1, g0, g1);
+    }
+    float da[H][2];
+#pragma unroll
+    for (int k = 0; k < H; ++k) { da[k][0] = 0.f; da[k][1] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float w[8];
+        ld8(img + L::W2 + j * H, w);
+#pragma unroll
+        for (int k = 0; k < H; ++k) ffma2_s(da[k][0], da[k][1], w[k], d2[j][0], d2[j][1]);
+    }
+    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        float g0, g1, t0, t1;
+        fmul2_p(t0, t1, -TANH_ISCALE, -TANH_ISCALE, h1[k][0], h1[k][1]);
+        fma2_p(g0, g1, t0, t1, h1[k][0], h1[k][1], TANH_ISCALE, TANH_ISCALE);
+        fmul2_p(d1[k][0], d1[k][1], da[k][0], da[k][1], g0, g1);
+        ffma2_s(p0, p1, img[L::W1 + k * L::S1], d1[k][0], d1[k][1]);
+    }
+    dc[0] = p0; dc[1] = p1;
+}
+
+// gradient products of particle P of the pair
+template <int P>
+__device__ __forceinline__ void accumulate_x2(float (&acc)[NACC], const float (&d1)[H][2], const float (&d2)[H][2], float dout, float c,
+                                              const float (&h1)[H][2], const float (&h2)[H][2]) {
+#pragma unroll
+    for (int k = 0; k < H; k += 2) {
+        ffma2_s(acc[k], acc[k + 1], c, d1[k][P], d1[k + 1][P]);
+        ffma2_s(acc[H + k], acc[H + k + 1], 1.0f, d1[k][P], d1[k + 1][P]);
+    }
+    unsigned long long h1p[H / 2];
+#pragma unroll
+    for (int k = 0; k < H; k += 2) h1p[k / 2] = pack2(h1[k][P], h1[k + 1][P]);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const unsigned long long dj = pack2(d2[j][P], d2[j][P]);
+#pragma unroll
+        for (int k = 0; k < H; k += 2) ffma2(acc[2 * H + j * H + k], acc[2 * H + j * H + k + 1], dj, h1p[k / 2]);
+    }
+#pragma unroll
+    for (int j = 0; j < H; j += 2) {
+        ffma2_s(acc[2 * H + H * H + j], acc[2 * H + H * H + j + 1], 1.0f, d2[j][P], d2[j + 1][P]);
+        ffma2_s(acc[3 * H + H * H + j], acc[3 * H + H * H + j + 1], dout, h2[j][P], h2[j + 1][P]);
+    }
+    acc[4 * H + H * H] += dout;
+}
+
 __device__ __forceinline__ void accumulate(float (&acc)[NACC], const float (&d1)[H], const float (&d2)[H], float dout, float c,
                                            const float (&h1)[H], const float (&h2)[H]) {
 #pragma unroll
@@ -189,10 +283,10 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
     const int grp = tid >> 7, gi = tid & (GRP - 1), warp = tid >> 5;
     float* s_img = smem;
     float* s_w1r = s_img + n_fcnn * L2_::SIZE;
-    float* s_xt = s_w1r + (size_t)n_fcnn * H * C_row;        // [2][GRP] t-net outputs
-    float* s_xs = s_xt + 2 * GRP;                            // [2][GRP] s-net outputs
-    float* s_dct = s_xs + 2 * GRP;                           // [2][GRP] t-net gradient wrt the conditioning half
-    float* s_part = s_dct + 2 * GRP;                         // [NWARP][100]
+    float* s_xt = s_w1r + (size_t)n_fcnn * H * C_row;        // [2][PPI] t-net outputs
+    float* s_xs = s_xt + 2 * PPI;                            // [2][PPI] s-net outputs
+    float* s_dct = s_xs + 2 * PPI;                           // [2][PPI] t-net gradient wrt the conditioning half
+    float* s_part = s_dct + 2 * PPI;                         // [NWARP][100]
     float* s_acc = s_part + NWARP * 100;                     // [n_fcnn][NACC]
     float* s_lo = s_acc + n_fcnn * NACC + 8;                 // state, [e_max][CHUNK] each
     float* s_up = s_lo + (size_t)e_max * CHUNK;
@@ -252,50 +346,55 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
 #pragma unroll 1
             for (int e = 0; e < ne; ++e) {
                 const int j = e0 + e, c0 = (j % nc) * CHUNK;
-                const int n_live = min(CHUNK, N - c0), iters = (n_live + GRP - 1) / GRP;
+                const int n_live = min(CHUNK, N - c0), iters = (n_live + PPI - 1) / PPI;
                 const float* hb = s_hb + ((size_t)e * n_fcnn + fm) * H;
 #pragma unroll 1
                 for (int m = 0; m < iters; ++m, ++it) {
                     asm volatile("" ::: "memory");
-                    const int q = e * CHUNK + m * GRP + gi, par = (it & 1) * GRP;
-                    const bool live = m * GRP + gi < n_live;
-                    const float c[1] = {s_c[q]};
-                    float h1[H], h2[H], out[1];
-                    fwd_d2(img, hb, c[0], h1, h2, out[0]);
-                    float gv_old = 0.f;
-                    if (grp == 0) { s_xt[par + gi] = out[0]; gv_old = s_gv[q]; }
-                    else          { s_xs[par + gi] = out[0]; }
-                    // t-warp w and s-warp w + 4 work on the same 32 particles and exchange only with each other: a 64-thread
+                    const int q = e * CHUNK + m * PPI + gi, par = (it & 1) * PPI;     // this thread's particles: q and q + GRP
+                    const bool live0 = m * PPI + gi < n_live, live1 = m * PPI + GRP + gi < n_live;
+                    const float c0v = s_c[q], c1v = s_c[q + GRP];
+                    float h1[H][2], h2[H][2], out[2];
+                    fwd_d2x2(img, hb, c0v, c1v, h1, h2, out);
+                    float gv0 = 0.f, gv1 = 0.f;
+                    if (grp == 0) { s_xt[par + gi] = out[0]; s_xt[par + GRP + gi] = out[1]; gv0 = s_gv[q]; gv1 = s_gv[q + GRP]; }
+                    else          { s_xs[par + gi] = out[0]; s_xs[par + GRP + gi] = out[1]; }
+                    // t-warp w and s-warp w + 4 work on the same 64 particles and exchange only with each other: a 64-thread
                     // named barrier per warp pair instead of a CTA barrier (the four pairs drift independently within a stage)
                     asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
-                    float d1[H], d2[H], dc[1] = {0.f};
+                    float d1[H][2], d2[H][2], dc[2];
+                    float do0, do1;
                     if (grp == 0) {         // t-net: d t = g_v (forward direction) or -g_v e^{-s} (inverse direction)
-                        float dt = inverse ? -gv_old * exp_acc(-s_xs[par + gi]) : gv_old;
-                        if (!live) dt = 0.f;
-                        bwd_d2(img, dt, h1, h2, d1, d2, dc[0]);
-                        s_dct[par + gi] = dc[0];
-                        accumulate(acc, d1, d2, dt, c[0], h1, h2);
+                        do0 = inverse ? -gv0 * exp_acc(-s_xs[par + gi]) : gv0;
+                        do1 = inverse ? -gv1 * exp_acc(-s_xs[par + GRP + gi]) : gv1;
                     } else {                // s-net: inverts the stage, owns the state update
-                        if (prev_q >= 0) s_gc[prev_q] += s_dct[(GRP - par) + gi];    // t-net share of the previous iteration
-                        const float t = s_xt[par + gi], s = out[0];
-                        const float v = s_v[q], gv = s_gv[q], gld = s_gld[q];
-                        const float es = exp_acc(s), ies = exp_acc(-s);
-                        float ds, vin, gin;
-                        if (!inverse) { vin = (v - t) * ies; ds = fmaf(gv * vin, es, gld); gin = gv * es; }
-                        else          { gin = gv * ies; ds = -fmaf(gv, v, gld); vin = fmaf(v, es, t); }
-                        if (!live) ds = 0.f;
-                        s_v[q] = vin; s_gv[q] = gin;
-                        bwd_d2(img, ds, h1, h2, d1, d2, dc[0]);
-                        s_gc[q] += dc[0];
-                        prev_q = q;
-                        accumulate(acc, d1, d2, ds, c[0], h1, h2);
+                        if (prev_q >= 0) { s_gc[prev_q] += s_dct[(PPI - par) + gi]; s_gc[prev_q + GRP] += s_dct[(PPI - par) + GRP + gi]; }
+#pragma unroll
+                        for (int p = 0; p < 2; ++p) {
+                            const int qq = q + p * GRP;
+                            const float t = s_xt[par + p * GRP + gi], sv = out[p];
+                            const float v = s_v[qq], gv = s_gv[qq], gld = s_gld[qq];
+                            const float es = exp_acc(sv), ies = exp_acc(-sv);
+                            float ds, vin, gin;
+                            if (!inverse) { vin = (v - t) * ies; ds = fmaf(gv * vin, es, gld); gin = gv * es; }
+                            else          { gin = gv * ies; ds = -fmaf(gv, v, gld); vin = fmaf(v, es, t); }
+                            s_v[qq] = vin; s_gv[qq] = gin;
+                            if (p == 0) do0 = ds; else do1 = ds;
+                        }
                     }
+                    if (!live0) do0 = 0.f;
+                    if (!live1) do1 = 0.f;
+                    bwd_d2x2(img, do0, do1, h1, h2, d1, d2, dc);
+                    if (grp == 0) { s_dct[par + gi] = dc[0]; s_dct[par + GRP + gi] = dc[1]; }
+                    else { s_gc[q] += dc[0]; s_gc[q + GRP] += dc[1]; prev_q = q; }
+                    accumulate_x2<0>(acc, d1, d2, do0, c0v, h1, h2);
+                    accumulate_x2<1>(acc, d1, d2, do1, c1v, h1, h2);
                 }
                 warp_reduce_b1(acc, s_d1part + (size_t)e * NWARP * H);
             }
             warp_reduce_to_slot(acc, s_part);
             __syncthreads();
-            if (grp == 1 && prev_q >= 0) s_gc[prev_q] += s_dct[((it - 1) & 1) * GRP + gi];
+            if (grp == 1 && prev_q >= 0) { s_gc[prev_q] += s_dct[((it - 1) & 1) * PPI + gi]; s_gc[prev_q + GRP] += s_dct[((it - 1) & 1) * PPI + GRP + gi]; }
             if (gi < NACC) {               // owner thread per parameter of the group's net: fixed-order sums
                 const int k = gi;
                 float v = 0.f;

@@ -382,11 +382,15 @@ __device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_ti
     const int k0 = 32 * warp;
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
-        float c[5][4];
-        umma::ld_frag<20>(tacc + TA_A + 20 * mt, &c[0][0]);
+        // the MMA chain of a batch starts from zero and is ADDED to the running sum with an IEEE add: the tensor core's own
+        // fp32 accumulate is not round-to-nearest, and chaining hundreds of batches through it biased the gradients (~6e-4)
+        float c[5][4] = {}, r[20];
         const int rowB[5] = {PR::A2 + g, PR::A2 + 8 + g, PR::A2 + 16 + g, PR::A2 + 24 + g, g == 0 ? PR::ONE : PR::ZERO};
         mma_outer<5>(s_tile, PR::D3 + 16 * mt, rowB, k0, k0 + 32, c);
-        umma::st_frag<20>(tacc + TA_A + 20 * mt, &c[0][0]);
+        umma::ld_frag<20>(tacc + TA_A + 20 * mt, r);
+#pragma unroll
+        for (int i = 0; i < 20; ++i) r[i] += c[i >> 2][i & 3];
+        umma::st_frag<20>(tacc + TA_A + 20 * mt, r);
     }
 }
 __device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_tile, uint32_t tacc) {
@@ -394,17 +398,21 @@ __device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_ti
     const int k0 = 32 * warp;
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
-        float c[3][4];
-        umma::ld_frag<12>(tacc + TA_B + 12 * mt, &c[0][0]);
+        float c[3][4] = {}, r[12];
         const int rowB[3] = {PR::A1 + g, PR::A1 + 8 + g, g == 0 ? PR::ONE : PR::ZERO};
         mma_outer<3>(s_tile, PR::D2 + 16 * mt, rowB, k0, k0 + 32, c);
-        umma::st_frag<12>(tacc + TA_B + 12 * mt, &c[0][0]);
+        umma::ld_frag<12>(tacc + TA_B + 12 * mt, r);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r[i] += c[i >> 2][i & 3];
+        umma::st_frag<12>(tacc + TA_B + 12 * mt, r);
     }
-    float c1[1][4];
-    umma::ld_frag<4>(tacc + TA_D1, &c1[0][0]);
+    float c1[1][4] = {}, r1[4];
     const int rowX[1] = {g < 2 ? PR::X + g : (g == 2 ? PR::ONE : PR::ZERO)};
     mma_outer<1>(s_tile, PR::D1, rowX, k0, k0 + 32, c1);
-    umma::st_frag<4>(tacc + TA_D1, &c1[0][0]);
+    umma::ld_frag<4>(tacc + TA_D1, r1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r1[i] += c1[0][i];
+    umma::st_frag<4>(tacc + TA_D1, r1);
     umma::wait_st();     // the next batch (or the read-out) loads these columns again
 }
 // Read this warp's accumulated fragments back and scatter them into its accumulator copy accpe[AC::SIZE] (every entry is
@@ -468,25 +476,23 @@ struct CnfTmemSink {
             float c[4][4];
             int rowB[4];
 #pragma unroll
-            for (int n = 0; n < 4; ++n) { rowB[n] = R::C + 8 * n + g; c[n][0] = a[2 * n]; c[n][1] = a[2 * n + 1]; c[n][2] = 0.f; c[n][3] = 0.f; }
-            mma_outer<4>(s_tile, R::D1, rowB, k0, k0 + 32, c);
+            for (int n = 0; n < 4; ++n) { rowB[n] = R::C + 8 * n + g; c[n][0] = 0.f; c[n][1] = 0.f; c[n][2] = 0.f; c[n][3] = 0.f; }
+            mma_outer<4>(s_tile, R::D1, rowB, k0, k0 + 32, c);       // chains start from zero; IEEE adds into the running sums (see pe_weight_grads_a)
 #pragma unroll
-            for (int n = 0; n < 4; ++n) { a[2 * n] = c[n][0]; a[2 * n + 1] = c[n][1]; }
+            for (int n = 0; n < 4; ++n) { a[2 * n] += c[n][0]; a[2 * n + 1] += c[n][1]; }
         }
         {   // input tiles 4, 5 | ONE (db1 rows 0-7, db2 rows 8-15) | h1 (rows 8-15: dW2[g][2 t, +1])
             float c[4][4] = {};
             const int rowB[4] = {R::C + 32 + g, R::C + 40 + g, g == 0 ? R::ONE : R::ZERO, R::H1 + g};
-            c[0][0] = a[8]; c[0][1] = a[9]; c[1][0] = a[10]; c[1][1] = a[11]; c[3][2] = a[12]; c[3][3] = a[13];
             mma_outer<4>(s_tile, R::D1, rowB, k0, k0 + 32, c);
-            a[8] = c[0][0]; a[9] = c[0][1]; a[10] = c[1][0]; a[11] = c[1][1]; a[12] = c[3][2]; a[13] = c[3][3];
+            a[8] += c[0][0]; a[9] += c[0][1]; a[10] += c[1][0]; a[11] += c[1][1]; a[12] += c[3][2]; a[13] += c[3][3];
             if (t == 0) { bias[f * 32 + g] += c[2][0]; bias[f * 32 + 8 + g] += c[2][2]; }
         }
         {   // A = d out (16 rows) x [h2 | ONE] -> dW3[g][2 t, +1], dW3[g + 8][..], db3
             float c[2][4] = {};
             const int rowB[2] = {R::H2 + g, g == 0 ? R::ONE : R::ZERO};
-            c[0][0] = a[14]; c[0][1] = a[15]; c[0][2] = a[16]; c[0][3] = a[17];
             mma_outer<2>(s_tile, R::DO, rowB, k0, k0 + 32, c);
-            a[14] = c[0][0]; a[15] = c[0][1]; a[16] = c[0][2]; a[17] = c[0][3];
+            a[14] += c[0][0]; a[15] += c[0][1]; a[16] += c[0][2]; a[17] += c[0][3];
             if (t == 0) { bias[f * 32 + 16 + g] += c[1][0]; bias[f * 32 + 24 + g] += c[1][2]; }
         }
         umma::st_frag<16>(col, a);

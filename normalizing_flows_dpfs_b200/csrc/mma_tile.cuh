@@ -10,12 +10,12 @@ namespace nfdpf {
 
 constexpr int TSM = 132;  // tile row stride in floats: == 4 (mod 32) makes the m16n8k8 fragment loads conflict-free
 
-// hi = x with the 13 low mantissa bits cleared, lo = the (exact) remainder cut to TF32 the same way: both are valid TF32
-// bit patterns, |lo| < 2^-10 |x|, and what is dropped is < 2^-20 |x|.  Three instructions (LOP3, FADD, LOP3);
+// hi = x rounded to TF32 (half-ulp add + mask), lo = the (exact, signed) remainder cut to TF32: both are valid TF32 bit
+// patterns, |lo| <= 2^-11 |x|, what is dropped is < 2^-21 |x| and unbiased.  Four instructions (IADD, LOP3, FADD, LOP3);
 // cvt.rna.tf32.f32 is emulated on sm_100a (VIADD + FSETP + SEL + LOP3 per conversion: nine for the pair) and the split is
 // done once per fragment element, i.e. it used to be almost half of the instructions of the gradient kernels.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(x) & 0xffffe000u;
+    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
     lo = __float_as_uint(x - __uint_as_float(hi)) & 0xffffe000u;
 }
 

@@ -1,5 +1,7 @@
 """GPU parity tests: CUDA kernels (through the C-ABI) vs the CPU oracle and the reference-generated goldens.
 Tolerances (BASELINE.json north_star): indices bit-exact; everything else fp32 rtol 1e-4 / atol 1e-5."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -192,6 +194,21 @@ def test_measurement_golden(golden):
     close(ops.measure(pe, cnf, enc, x, "CRNVP", p0=0.0, p1=2.5), G["meas_cnf"], atol=1e-4, what="CRNVP")
 
 
+def _off_the_relu_kinks(x, pe, margin=2e-5):
+    """The encoder's ReLU masks are discontinuous in the pre-activations: a particle whose pre-activation sits within the
+    fp32 / 3xTF32 evaluation error (~5e-7) of zero gets a different mask -- and a finitely different gradient -- from any two
+    correct implementations.  With ~1e5 particles x 48 units a handful always do, so the parity inputs are nudged off the kinks."""
+    W1, b1, W2, b2, _, _ = _pe_tuple(pe)
+    for _ in range(4):
+        p1 = x @ W1.t() + b1
+        p2 = torch.relu(p1) @ W2.t() + b2
+        near = (p1.abs() < margin).any(-1) | (p2.abs() < margin).any(-1)
+        if not bool(near.any()):
+            break
+        x = x + near[..., None] * 0.01
+    return x
+
+
 @pytest.mark.parametrize("mode,B,N,fused", [("gaussian", 3, 200, True), ("cos", 3, 200, True), ("CRNVP", 3, 200, True),
                                             ("gaussian", 2, 50, False), ("CRNVP", 2, 129, False), ("gaussian", 16, 1024, True),
                                             ("CRNVP", 8, 1024, True),
@@ -199,11 +216,12 @@ def test_measurement_golden(golden):
                                             # tensor-memory gradient accumulators and the per-trajectory d_enc increments carry across them
                                             ("gaussian", 700, 200, True), ("cos", 650, 130, False), ("CRNVP", 600, 129, True)])
 def test_measure_update_vs_oracle(mode, B, N, fused):
-    g = torch.Generator().manual_seed(hash((mode, B, N)) % 1000)
+    # deterministic (hash() of a str is salted per process); NFDPF_TEST_SEED shifts it for seed sweeps
+    g = torch.Generator().manual_seed((len(mode) * 7919 + B * 31 + N) % 1000 + int(os.environ.get("NFDPF_TEST_SEED", "0")))
     pe = torch.cat([torch.randn(n, generator=g) * s for n, s in ((32, 0.3), (16, 0.1), (512, 0.3), (32, 0.1), (1024, 0.2), (32, 0.1))])
     cnf = O.init_stack(g, 32, 32, std=0.1, bias_std=0.05) if mode == "CRNVP" else None
     enc = torch.randn(B, 32, generator=g)
-    x = torch.randn(B, N, 2, generator=g) * 3
+    x = _off_the_relu_kinks(torch.randn(B, N, 2, generator=g) * 3, pe)
     lw0 = torch.log_softmax(torch.randn(B, N, generator=g), -1)
     prior, prop = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g)
     p0, p1 = {"gaussian": (1.0, 10.0), "cos": (0.0, 1.0), "CRNVP": (0.0, 2.5)}[mode]
