@@ -11,7 +11,9 @@
 //   * the two nets of a stage are split over the two halves of the CTA: threads 0-127 own the t-net, threads 128-255 the
 //     s-net, for the SAME particles.  Each half runs its net forward (activations recomputed from the stage output: couplings
 //     are invertible, nothing but y is read from HBM), the halves exchange t and s through shared memory (one 64-thread
-//     named barrier per warp pair and 32 particles), then each runs its net backward with the activations still in registers -- no activation stash.
+//     named barrier per warp pair and 64 particles), then each runs its net backward with the activations still in registers -- no activation stash;
+//   * a thread evaluates its net for TWO particles at once: the pair is the packed operand of every FFMA2 (fma.rn.f32x2, the
+//     weight being the broadcast scalar), so every weight is loaded once per two particles and the FMA issue slots halve.
 #include "coupling.cuh"
 
 namespace nfdpf {
@@ -84,76 +86,6 @@ __device__ __forceinline__ void warp_reduce_b1(float (&acc)[NACC], float* s_d1pa
     v[0] += __shfl_xor_sync(FULL, v[0], 2);
     v[0] += __shfl_xor_sync(FULL, v[0], 1);
     if ((lane & 3) == 0) s_d1part_e[warp * H + (lane >> 2)] = v[0];   // lane bits 4,3,2 select the entry index
-}
-
-// FCNN 1 -> 8 -> 8 -> 1 forward / backward for this kernel, on packed FP32 pairs (FFMA2: two FMAs per issue slot; the kernel is
-// short of issue slots and latency, not of FMA throughput).  Same arithmetic as fcnn_fwd / fcnn_bwd<1,0> up to summation order:
-// the 8-term dot products are accumulated as (even, odd) partial sums.
-__device__ __forceinline__ void fwd_d2(const float* __restrict__ img, const float* __restrict__ hb, float c, float (&h1)[H], float (&h2)[H],
-                                       float& out) {
-    using L = L2_;
-    float hbv[8], a[H];
-    ld8(hb, hbv);
-#pragma unroll
-    for (int k = 0; k < H; ++k) a[k] = fmaf(img[L::W1 + k * L::S1], c, hbv[k]);
-#pragma unroll
-    for (int k = 0; k < H; k += 2) tanh_prescaled_pair(a[k], a[k + 1], h1[k], h1[k + 1]);
-    float b2[8];
-    ld8(img + L::B2, b2);
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        float w[8];
-        ld8(img + L::W2 + j * H, w);
-        float p0 = b2[j], p1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < H; k += 2) ffma2_p(p0, p1, w[k], w[k + 1], h1[k], h1[k + 1]);
-        a[j] = p0 + p1;
-    }
-#pragma unroll
-    for (int j = 0; j < H; j += 2) tanh_prescaled_pair(a[j], a[j + 1], h2[j], h2[j + 1]);
-    float w3[8];
-    ld8(img + L::W3, w3);
-    float p0 = img[L::B3], p1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < H; j += 2) ffma2_p(p0, p1, w3[j], w3[j + 1], h2[j], h2[j + 1]);
-    out = p0 + p1;
-}
-
-// d1 / d2 = pre-activation grads DIVIDED BY TANH_SCALE (scaled layer-1/2 images, see coupling.cuh); dc = d out / d c
-__device__ __forceinline__ void bwd_d2(const float* __restrict__ img, float dout, const float (&h1)[H], const float (&h2)[H], float (&d1)[H],
-                                       float (&d2)[H], float& dc) {
-    using L = L2_;
-    float w3[8];
-    ld8(img + L::W3, w3);
-#pragma unroll
-    for (int j = 0; j < H; j += 2) {
-        float g0, g1, t0, t1;
-        fmul2_p(t0, t1, -TANH_ISCALE, -TANH_ISCALE, h2[j], h2[j + 1]);
-        fma2_p(g0, g1, t0, t1, h2[j], h2[j + 1], TANH_ISCALE, TANH_ISCALE);          // (1 - h2^2) / scale
-        fmul2_p(t0, t1, dout, dout, w3[j], w3[j + 1]);
-        fmul2_p(d2[j], d2[j + 1], t0, t1, g0, g1);
-    }
-    float da[H];
-#pragma unroll
-    for (int k = 0; k < H; ++k) da[k] = 0.f;
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        float w[8];
-        ld8(img + L::W2 + j * H, w);
-#pragma unroll
-        for (int k = 0; k < H; k += 2) ffma2_s(da[k], da[k + 1], d2[j], w[k], w[k + 1]);
-    }
-    float part = 0.f;
-#pragma unroll
-    for (int k = 0; k < H; k += 2) {
-        float g0, g1, t0, t1;
-        fmul2_p(t0, t1, -TANH_ISCALE, -TANH_ISCALE, h1[k], h1[k + 1]);
-        fma2_p(g0, g1, t0, t1, h1[k], h1[k + 1], TANH_ISCALE, TANH_ISCALE);
-        fmul2_p(d1[k], d1[k + 1], da[k], da[k + 1], g0, g1);
-    }
-#pragma unroll
-    for (int k = 0; k < H; ++k) part = fmaf(img[L::W1 + k * L::S1], d1[k], part);
-    dc = part;
 }
 
 // Two particles per thread: the pair (particle 0, particle 1) is the packed operand of every FMA, the weight its broadcast
@@ -245,30 +177,6 @@ __device__ __forceinline__ void accumulate_x2(float (&acc)[NACC], const float (&
     for (int j = 0; j < H; j += 2) {
         ffma2_s(acc[2 * H + H * H + j], acc[2 * H + H * H + j + 1], 1.0f, d2[j][P], d2[j + 1][P]);
         ffma2_s(acc[3 * H + H * H + j], acc[3 * H + H * H + j + 1], dout, h2[j][P], h2[j + 1][P]);
-    }
-    acc[4 * H + H * H] += dout;
-}
-
-__device__ __forceinline__ void accumulate(float (&acc)[NACC], const float (&d1)[H], const float (&d2)[H], float dout, float c,
-                                           const float (&h1)[H], const float (&h2)[H]) {
-#pragma unroll
-    for (int k = 0; k < H; k += 2) {
-        ffma2_s(acc[k], acc[k + 1], c, d1[k], d1[k + 1]);
-        ffma2_s(acc[H + k], acc[H + k + 1], 1.0f, d1[k], d1[k + 1]);
-    }
-    unsigned long long h1p[H / 2];      // (h1[k], h1[k+1]) pairs: packed once, used by all eight rows of dW2
-#pragma unroll
-    for (int k = 0; k < H; k += 2) h1p[k / 2] = pack2(h1[k], h1[k + 1]);
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        const unsigned long long dj = pack2(d2[j], d2[j]);
-#pragma unroll
-        for (int k = 0; k < H; k += 2) ffma2(acc[2 * H + j * H + k], acc[2 * H + j * H + k + 1], dj, h1p[k / 2]);
-    }
-#pragma unroll
-    for (int j = 0; j < H; j += 2) {
-        ffma2_s(acc[2 * H + H * H + j], acc[2 * H + H * H + j + 1], 1.0f, d2[j], d2[j + 1]);
-        ffma2_s(acc[3 * H + H * H + j], acc[3 * H + H * H + j + 1], dout, h2[j], h2[j + 1]);
     }
     acc[4 * H + H * H] += dout;
 }
