@@ -204,7 +204,6 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n_params) return;
     double a = 0.0;
-#pragma unroll 8                         // independent loads: all of a lane's partials in flight at once
     for (int c = lane; c < n_parts; c += 32) a += (double)partials[(size_t)c * n_params + i];
     a = warp_sum(a);
     if (lane == 0) d_packed[i] += (float)a;

@@ -357,7 +357,6 @@ __global__ void rowctx_grad_kernel(const float* __restrict__ packed, const float
     if (warp < n_w) {
         const int fk = warp / C_row, c = warp % C_row;
         double a = 0.0;
-#pragma unroll 8                     // independent loads: keep eight in flight per lane (the kernel is pure latency)
         for (int b = lane; b < B; b += 32) a += (double)d1rows[(size_t)fk * B + b] * (double)row_ctx[(size_t)b * C_row + c];
         a = warp_sum(a);
         if (lane == 0) d_packed[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + c] += (float)a;
@@ -366,7 +365,6 @@ __global__ void rowctx_grad_kernel(const float* __restrict__ packed, const float
         if (e >= B * C_row) return;
         const int b = e / C_row, c = e % C_row;
         float a = 0.f;
-#pragma unroll 4
         for (int fk = lane; fk < n_fcnn * H; fk += 32)
             a = fmaf(packed[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + c], d1rows[(size_t)fk * B + b], a);
         a = warp_sum(a);
