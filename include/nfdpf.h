@@ -101,7 +101,9 @@ int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C
  * If logw_prev != NULL the weight update of nfdpf_weight_update_fwd is fused in (prior / propose may be NULL):
  * logw_out (B,N) (may be NULL), probs_out (B,N), row_stats (B,2).
  * z_out (B,N,hidden) or NULL (mode 2 only): the flow output z, which nfdpf_measure_bwd can take as z_saved to walk the
- * stack backwards without re-running it forward (128 B / particle of HBM for ~13 % fewer backward instructions). */
+ * stack backwards without re-running it forward (128 B / particle of HBM for ~13 % fewer backward instructions).
+ * Implementation note: encoder layers 2-3 run on the tcgen05 tensor cores (3xTF32); every CTA of the forward / backward
+ * allocates 128 / 256 tensor-memory columns for its lifetime (sm_100a only). */
 int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
                       const float* enc, const float* particles, int B, int N, int hidden, const float* logw_prev,
                       const float* prior, const float* propose, float add_eps, float* lki, int32_t* argmax,
