@@ -234,6 +234,119 @@ __device__ __forceinline__ float loglik(const float (&e)[32], const float* __res
     }
 }
 
+// ---- CRNVP stack, forward: layer 1 of a stage's t- and s-net on tcgen05 ----------------------------------------------
+// The two nets of a stage read the same 48 inputs [c (16) | particle encoding e (32)]; their layer-1 weights side by side are a
+// [16 x 48] operand, i.e. an M = 128 particles, N = 16, K = 48 product per stage: 2/3 of the stack's FMAs.  The activation row
+// lives in tensor memory like the encoder's (TS form): e is written once per particle (columns [48,80) hi, [96,128) lo), c every
+// stage ([32,48) hi, [80,96) lo); the 16 pre-activations come back in columns [0,16).  Layers 2 and 3 (8 x 8, 8 -> 16) stay in
+// registers.  CnfL1 = the per-stage weight tiles in shared memory (hi | lo, chunk-major K-major, umma.cuh).
+struct CnfL1 {
+    using W = umma::Operand<16, 48>;
+    static constexpr int STAGE_FLOATS = 2 * W::FLOATS;     // hi | lo
+    static constexpr int COL_D = 0, COL_CHI = 32, COL_EHI = 48, COL_CLO = 80, COL_ELO = 96;
+    // build the tiles from the stack's shared-memory images (scaled layer-1 weights): rows 0-7 t-net units, 8-15 s-net units
+    __device__ static void load(const float* __restrict__ s_img, int n_stages, float* __restrict__ s_w) {
+        for (int e = threadIdx.x; e < n_stages * 16 * 48; e += blockDim.x) {
+            const int st = e / (16 * 48), r = (e / 48) % 16, k = e % 48;
+            const float w = s_img[(2 * st + (r >> 3)) * LC::SIZE + LC::W1 + (r & 7) * LC::S1 + k];
+            W::store_elem(s_w + st * STAGE_FLOATS, s_w + st * STAGE_FLOATS + W::FLOATS, r, k, w);
+        }
+        umma::fence_smem_to_async();
+    }
+    // one round: this thread's c half -> tensor memory, 18 MMAs (3xTF32, K = 48), pre-activations back; CTA-collective
+    __device__ static __forceinline__ void round(PeTc& tc, const float* __restrict__ s_w_stage, const float (&c)[16], float (&pre)[16]) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) umma::split(c[i], hi[i], lo[i]);
+        umma::st_frag<16>(tc.lane_addr() + COL_CHI, hi);
+        umma::st_frag<16>(tc.lane_addr() + COL_CLO, lo);
+        umma::wait_st();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            umma::fence_after_sync();
+            constexpr uint32_t idesc = umma::idesc_tf32(128, 16);
+            const float* w_hi = s_w_stage;
+            const float* w_lo = s_w_stage + W::FLOATS;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k0 = 0; k0 < 48; k0 += 8) { umma::mma_tf32_ts(tc.tmem + COL_D, tc.tmem + COL_CLO + k0, W::desc(w_hi, k0), idesc, acc); acc = 1; }
+#pragma unroll
+            for (int k0 = 0; k0 < 48; k0 += 8) umma::mma_tf32_ts(tc.tmem + COL_D, tc.tmem + COL_CHI + k0, W::desc(w_lo, k0), idesc, 1);
+#pragma unroll
+            for (int k0 = 0; k0 < 48; k0 += 8) umma::mma_tf32_ts(tc.tmem + COL_D, tc.tmem + COL_CHI + k0, W::desc(w_hi, k0), idesc, 1);
+            umma::commit(tc.bar);
+        }
+        tc.wait();
+        umma::ld16(tc.lane_addr() + COL_D, pre);
+    }
+};
+
+// layers 2 and 3 of one net from its layer-1 PRE-activations (in place: a1 -> h1); same arithmetic as fcnn_fwd<16, 32, true>
+__device__ __forceinline__ void fcnn_tail16(const float* __restrict__ img, float (&a1)[H], float (&out)[16]) {
+    using L = LC;
+#pragma unroll
+    for (int k = 0; k < H; k += 2) tanh_prescaled_pair(a1[k], a1[k + 1], a1[k], a1[k + 1]);
+    float b2[8], h2[H];
+    ld8(img + L::B2, b2);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float w[8];
+        ld8(img + L::W2 + j * H, w);
+        float p0 = b2[j], p1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < H; k += 2) ffma2_p(p0, p1, w[k], w[k + 1], a1[k], a1[k + 1]);
+        h2[j] = p0 + p1;
+    }
+#pragma unroll
+    for (int j = 0; j < H; j += 2) tanh_prescaled_pair(h2[j], h2[j + 1], h2[j], h2[j + 1]);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        float w[8];
+        ld8(img + L::W3 + o * H, w);
+        float p0 = img[L::B3 + o], p1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; j += 2) ffma2_p(p0, p1, w[j], w[j + 1], h2[j], h2[j + 1]);
+        out[o] = p0 + p1;
+    }
+}
+
+// CRNVP log-likelihood of the particle of this thread (x = observation encoding, context = e), layer 1 on the tensor cores.
+// CTA-collective: every thread of the CTA must call it (dead threads with any finite e).
+__device__ __forceinline__ float loglik_cnf_tc(PeTc& tc, const float (&e)[32], const float* __restrict__ s_enc, float p0, float p1,
+                                               const float* __restrict__ s_img, const float* __restrict__ s_hb,
+                                               const float* __restrict__ s_l1w, int n_flows, float (&lo)[16], float (&up)[16]) {
+    {
+        float hi[32], l[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) umma::split(e[i], hi[i], l[i]);
+        umma::st_frag<32>(tc.lane_addr() + CnfL1::COL_EHI, hi);
+        umma::st_frag<32>(tc.lane_addr() + CnfL1::COL_ELO, l);
+    }
+    float ld = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lo[i] = s_enc[i]; up[i] = s_enc[16 + i]; }
+#pragma unroll 1
+    for (int st = 0; st < 2 * n_flows; ++st) {        // one stage body; the halves swap roles after every stage
+        float pre[16];
+        CnfL1::round(tc, s_l1w + st * CnfL1::STAGE_FLOATS, lo, pre);
+        const float* im = s_img + 2 * st * LC::SIZE;
+        const float* hb = s_hb + 2 * st * H;
+        float a_t[H], a_s[H], t[16], sc[16];
+#pragma unroll
+        for (int k = 0; k < H; ++k) { a_t[k] = pre[k] + hb[k]; a_s[k] = pre[H + k] + hb[H + k]; }
+        fcnn_tail16(im, a_t, t);
+        fcnn_tail16(im + LC::SIZE, a_s, sc);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { up[i] = fmaf(up[i], expf(sc[i]), t[i]); ld += sc[i]; }
+        swap_halves<16>(lo, up);
+    }
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float a = lo[i] - p0, b = up[i] - p0; m = fmaf(a, a, m); m = fmaf(b, b, m); }
+    return -0.5f * m / (p1 * p1) - 32.0f * (logf(p1) + 0.91893853320467274f) + ld;
+}
+
 __device__ void load_enc(const float* __restrict__ enc_row, float* s_enc) {  // s_enc[32] = ||enc|| clamped (cos mode)
     if (threadIdx.x < 32) {
         const float v = enc_row[threadIdx.x];
@@ -261,7 +374,8 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     float* s_enc = s_pe + PE_SIZE;            // [36]
     float* s_img = s_enc + 36;                // [n_fcnn][LC::SIZE]
     float* s_hb = s_img + n_fcnn * LC::SIZE;  // [n_fcnn][8]
-    float* s_ll = s_hb + n_fcnn * H;          // [N]
+    float* s_l1w = s_hb + n_fcnn * H;         // [n_fcnn / 2][CnfL1::STAGE_FLOATS]  layer-1 operand tiles of the CRNVP stages
+    float* s_ll = s_l1w + (n_fcnn / 2) * CnfL1::STAGE_FLOATS;   // [N]
     if (tid < 32) umma::tmem_alloc<FWD_TMEM_COLS>(&s_tslot);
     if (tid == 0) umma::mbar_init(&s_bar, 1);
     PeTc tc{s_tc, &s_bar, 0u, 0u};
@@ -276,7 +390,10 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     __syncthreads();
     umma::fence_after_sync();
     tc.tmem = s_tslot;
-    if (MODE == MODE_CNF) hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
+    if (MODE == MODE_CNF) {
+        hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
+        CnfL1::load(s_img, n_fcnn / 2, s_l1w);
+    }
     __syncthreads();
     float mx = -INFINITY;
     float2 x_next = *reinterpret_cast<const float2*>(particles + ((size_t)b * N + (tid < N ? tid : 0)) * 2);
@@ -288,7 +405,9 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         x_next = *reinterpret_cast<const float2*>(particles + ((size_t)b * N + (n + TP < N ? n + TP : 0)) * 2);   // next batch: latency hidden
         float a1[16], a2[32], e[32], lo[16], up[16];
         pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);
-        const float ll = loglik<MODE>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
+        float ll;
+        if constexpr (MODE == MODE_CNF) ll = loglik_cnf_tc(tc, e, s_enc, p0, p1, s_img, s_hb, s_l1w, n_flows, lo, up);
+        else ll = loglik<MODE>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
         if (MODE == MODE_CNF && z_out && live) {   // the flow output: lets the backward walk the stack from z without re-running it
             float4* zo = reinterpret_cast<float4*>(z_out + ((size_t)b * N + n) * 32);
 #pragma unroll
@@ -752,7 +871,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 
 static size_t fwd_smem(int mode, int n_flows, int N) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    return ((size_t)PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + N) * sizeof(float);
+    return ((size_t)PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + (size_t)(n_fcnn / 2) * CnfL1::STAGE_FLOATS + N) * sizeof(float);
 }
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
