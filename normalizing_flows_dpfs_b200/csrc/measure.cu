@@ -244,11 +244,27 @@ struct CnfL1 {
     using W = umma::Operand<16, 48>;
     static constexpr int STAGE_FLOATS = 2 * W::FLOATS;     // hi | lo
     static constexpr int COL_D = 0, COL_CHI = 32, COL_EHI = 48, COL_CLO = 80, COL_ELO = 96;
-    // build the tiles from the stack's shared-memory images (scaled layer-1 weights): rows 0-7 t-net units, 8-15 s-net units
-    __device__ static void load(const float* __restrict__ s_img, int n_stages, float* __restrict__ s_w) {
-        for (int e = threadIdx.x; e < n_stages * 16 * 48; e += blockDim.x) {
+    // The forward keeps only the TAIL of every FCNN image in shared memory (b1 | W2 | b2 | W3 | b3, laid out exactly as Lay<16,32>
+    // from its B1 offset on): the layer-1 weights live in the operand tiles.  tail_image() returns the pointer that makes the LC
+    // offsets valid (its W1 range is never dereferenced).
+    static constexpr int TAIL = LC::SIZE - LC::B1;         // 224 floats per net instead of 608
+    __device__ static __forceinline__ const float* tail_image(const float* s_tail, int f) { return s_tail + f * TAIL - LC::B1; }
+    // build the tail images and the operand tiles (rows 0-7 t-net units, 8-15 s-net units) from the packed stack; layers 1-2
+    // carry the tanh pre-scale (coupling.cuh)
+    __device__ static void load(const float* __restrict__ cnf, int n_fcnn, float* __restrict__ s_tail, float* __restrict__ s_hb,
+                                float* __restrict__ s_w) {
+        const int pf = packed_fcnn_size(16, 32);
+        for (int e = threadIdx.x; e < n_fcnn * TAIL; e += blockDim.x) {
+            const int f = e / TAIL, o = e % TAIL;
+            float v = 0.f;
+            if (o < pf - H * 48) v = cnf[(size_t)f * pf + H * 48 + o];        // b1 (8) W2 (64) b2 (8) W3 (128) b3 (16): contiguous in both layouts
+            if (o < H + H * H + H) v *= TANH_SCALE;
+            s_tail[e] = v;
+            if (o < H) s_hb[f * H + o] = v;                                       // no row context here: hoisted bias = scaled b1
+        }
+        for (int e = threadIdx.x; e < (n_fcnn / 2) * 16 * 48; e += blockDim.x) {
             const int st = e / (16 * 48), r = (e / 48) % 16, k = e % 48;
-            const float w = s_img[(2 * st + (r >> 3)) * LC::SIZE + LC::W1 + (r & 7) * LC::S1 + k];
+            const float w = TANH_SCALE * cnf[(size_t)(2 * st + (r >> 3)) * pf + (r & 7) * 48 + k];
             W::store_elem(s_w + st * STAGE_FLOATS, s_w + st * STAGE_FLOATS + W::FLOATS, r, k, w);
         }
         umma::fence_smem_to_async();
@@ -314,7 +330,7 @@ __device__ __forceinline__ void fcnn_tail16(const float* __restrict__ img, float
 // CRNVP log-likelihood of the particle of this thread (x = observation encoding, context = e), layer 1 on the tensor cores.
 // CTA-collective: every thread of the CTA must call it (dead threads with any finite e).
 __device__ __forceinline__ float loglik_cnf_tc(PeTc& tc, const float (&e)[32], const float* __restrict__ s_enc, float p0, float p1,
-                                               const float* __restrict__ s_img, const float* __restrict__ s_hb,
+                                               const float* __restrict__ s_img /* tail images */, const float* __restrict__ s_hb,
                                                const float* __restrict__ s_l1w, int n_flows, float (&lo)[16], float (&up)[16]) {
     {
         float hi[32], l[32];
@@ -330,13 +346,12 @@ __device__ __forceinline__ float loglik_cnf_tc(PeTc& tc, const float (&e)[32], c
     for (int st = 0; st < 2 * n_flows; ++st) {        // one stage body; the halves swap roles after every stage
         float pre[16];
         CnfL1::round(tc, s_l1w + st * CnfL1::STAGE_FLOATS, lo, pre);
-        const float* im = s_img + 2 * st * LC::SIZE;
         const float* hb = s_hb + 2 * st * H;
         float a_t[H], a_s[H], t[16], sc[16];
 #pragma unroll
         for (int k = 0; k < H; ++k) { a_t[k] = pre[k] + hb[k]; a_s[k] = pre[H + k] + hb[H + k]; }
-        fcnn_tail16(im, a_t, t);
-        fcnn_tail16(im + LC::SIZE, a_s, sc);
+        fcnn_tail16(CnfL1::tail_image(s_img, 2 * st), a_t, t);
+        fcnn_tail16(CnfL1::tail_image(s_img, 2 * st + 1), a_s, sc);
 #pragma unroll
         for (int i = 0; i < 16; ++i) { up[i] = fmaf(up[i], expf(sc[i]), t[i]); ld += sc[i]; }
         swap_halves<16>(lo, up);
@@ -372,8 +387,8 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     float* s_tc = smem;                       // tensor-core weight tiles (the activation operand lives in tensor memory)
     float* s_pe = s_tc + PeTc::WFWD_FLOATS;   // [1648]
     float* s_enc = s_pe + PE_SIZE;            // [36]
-    float* s_img = s_enc + 36;                // [n_fcnn][LC::SIZE]
-    float* s_hb = s_img + n_fcnn * LC::SIZE;  // [n_fcnn][8]
+    float* s_img = s_enc + 36;                // [n_fcnn][CnfL1::TAIL]  CRNVP tail images (b1 | W2 | b2 | W3 | b3)
+    float* s_hb = s_img + n_fcnn * CnfL1::TAIL;   // [n_fcnn][8]
     float* s_l1w = s_hb + n_fcnn * H;         // [n_fcnn / 2][CnfL1::STAGE_FLOATS]  layer-1 operand tiles of the CRNVP stages
     float* s_ll = s_l1w + (n_fcnn / 2) * CnfL1::STAGE_FLOATS;   // [N]
     if (tid < 32) umma::tmem_alloc<FWD_TMEM_COLS>(&s_tslot);
@@ -381,20 +396,12 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     PeTc tc{s_tc, &s_bar, 0u, 0u};
     tc.load_weights(pe, false);
     for (int e = tid; e < PE_SIZE; e += TP) s_pe[e] = pe[e];
-    if (MODE == MODE_CNF) {
-        const int pf = packed_fcnn_size(16, 32);
-        for (int f = 0; f < n_fcnn; ++f) load_fcnn_image<16, 32>(cnf + (size_t)f * pf, 0, s_img + f * LC::SIZE, nullptr, tid, TP);
-    }
+    if (MODE == MODE_CNF) CnfL1::load(cnf, n_fcnn, s_img, s_hb, s_l1w);
     load_enc(enc + (size_t)b * HID, s_enc);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     tc.tmem = s_tslot;
-    if (MODE == MODE_CNF) {
-        hoist_row_context<16, 32>(s_img, nullptr, nullptr, 0, n_fcnn, s_hb, tid, TP);
-        CnfL1::load(s_img, n_fcnn / 2, s_l1w);
-    }
-    __syncthreads();
     float mx = -INFINITY;
     float2 x_next = *reinterpret_cast<const float2*>(particles + ((size_t)b * N + (tid < N ? tid : 0)) * 2);
     for (int n0 = 0; n0 < N; n0 += TP) {      // uniform trip count: the tensor-core rounds are CTA-collective
@@ -871,7 +878,7 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
 
 static size_t fwd_smem(int mode, int n_flows, int N) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    return ((size_t)PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * LC::SIZE + n_fcnn * H + (size_t)(n_fcnn / 2) * CnfL1::STAGE_FLOATS + N) * sizeof(float);
+    return ((size_t)PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * CnfL1::TAIL + n_fcnn * H + (size_t)(n_fcnn / 2) * CnfL1::STAGE_FLOATS + N) * sizeof(float);
 }
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
