@@ -1,8 +1,10 @@
 // Weight-gradient contractions on the (legacy, warp-level) tensor path: dW[o][i] = sum_p delta[p][o] * act[p][i].
 // K = particles is the long dimension; the deltas / activations of the CTA's batch sit transposed in a shared-memory
 // tile (row = feature, column = particle).  mma.sync.m16n8k8 TF32 with the 3xTF32 split (hi*hi + hi*lo + lo*hi) keeps
-// ~2^-20 relative accuracy, which the rtol 1e-4 gradient bar needs (plain TF32 is 2^-11).  These contractions are the
-// only "dense" GEMMs on the path (M,N <= 48); tcgen05 tiles (M >= 64) would be >85 % padding here.
+// ~2^-21 relative accuracy, which the rtol 1e-4 gradient bar needs (plain TF32 is 2^-11).  These contractions have M, N <= 48
+// with K = particles: on tcgen05 they were measured slower (M is 128 whatever the live rows, the SS operands are re-read from
+// shared memory every K = 8 step, and the TS form needs a thread to write other lanes' rows) -- DESIGN.md 3.  The forward /
+// data-gradient products with M = particles run on tcgen05 instead (umma.cuh).
 #pragma once
 #include "common.cuh"
 
