@@ -1,19 +1,25 @@
-// tcgen05 (5th-generation tensor core) building blocks for the particle-encoder GEMMs of the measurement kernels.
+// tcgen05 (5th-generation tensor core) building blocks for the measurement kernels.
 //
-// The encoder layers (16->32, 32->32, model/models.py:130-139) are the only products on the path whose widths make a
-// dense tile: M = 128 particles of a CTA batch, N = 16 / 32 features, K = 16 / 32.  The operands are produced by the
-// CTA's own threads (one thread = one particle), so there is no TMA: every thread splits its activations into a TF32
-// hi / lo pair, writes them into the canonical no-swizzle K-major shared-memory layout with one STS.128 per four
-// features, and a single thread issues the 3xTF32 product
+// The particle-encoder layers (16->32, 32->32, model/models.py:130-139) and layer 1 of the CRNVP stack's t-/s-net pairs
+// (48 -> 8 + 8) are the products on the path whose widths make a dense tile: M = 128 particles of a CTA batch, N = 16 / 32
+// features, K = 16 / 32 / 48.  The operands are produced by the CTA's own threads (one thread = one particle), so there is no
+// TMA: every thread splits its activations into a TF32 hi / lo pair and a single thread issues the 3xTF32 product
 //     D = A_lo B_hi + A_hi B_lo + A_hi B_hi          (fp32 accumulate in tensor memory)
-// which keeps ~2^-21 relative accuracy (plain TF32, 2^-11, would not hold the rtol-1e-4 parity bar).  The accumulator
+// which keeps ~1e-7 relative accuracy (plain TF32, 2^-11, would not hold the rtol-1e-4 parity bar).  The accumulator
 // comes back with tcgen05.ld (lane = particle row, one register per feature).
+//
+// Two forms of the activation operand A:
+//   TS (default): A lives in tensor memory -- the owning thread writes its row with tcgen05.st (lane = its particle,
+//       K consecutive columns); only the weights are shared-memory operands.  gemm3_ts().
+//   SS: A in shared memory in the same layout as the weights (below).  Kept for the CRNVP backward, whose tensor memory is
+//       full of gradient fragments.  gemm3().  Measured 1.65x slower per round: every K = 8 step re-reads 128 x 32 B of A.
+// Tensor memory also serves as lane-private accumulator storage for mma.sync gradient fragments (ld_frag / st_frag).
 //
 // Shared-memory operand layout (no swizzle, K-major; cute "INTERLEAVE" canonical form ((8,m),(4,2)):((4,SBO),(1,LBO))
 // in fp32 elements): element (row r, k) lives at byte  (k / 4) * LBO + (r / 8) * SBO + (r % 8) * 16 + (k % 4) * 4.
 // We use SBO = 128 (8-row core matrices back to back) and LBO = rows * 16, i.e. "chunk-major": chunk c = k / 4 is a
 // [rows][4] slab, row r of chunk c at byte c * rows * 16 + r * 16 -- consecutive threads write consecutive 16-byte
-// words (conflict-free).
+// words (conflict-free).  16-byte alignment suffices; MN-major TF32 operands in this layout read as zeros (tools/tc_probe.cu).
 #pragma once
 #include "common.cuh"
 
