@@ -142,7 +142,6 @@ __device__ __forceinline__ void pe_l1(const float* __restrict__ w, float x0, flo
 template <class Tc>
 __device__ __forceinline__ void pe_fwd_tc(Tc& tc, const float* __restrict__ w, float x0, float x1, float (&a1)[16], float (&a2)[32],
                                           float (&e)[32]) {
-    const int tid = threadIdx.x;
     pe_l1(w, x0, x1, a1);
     tc.template store_row<16>(a1);
     tc.template round<32, 16>(PeTc::W2_HI, PeTc::W2_LO);

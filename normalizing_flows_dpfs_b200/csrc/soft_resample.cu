@@ -163,8 +163,7 @@ soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __r
                          float* __restrict__ d_particles, float* __restrict__ d_probs, const float* __restrict__ g_logprobs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* s_idx = reinterpret_cast<int*>(smem_raw);                    // [N] local source index per destination
-    float4* s_a = reinterpret_cast<float4*>(s_idx + ((N + 3) & ~3));  // [N] (dL/dv, g_x, g_y, -) ping
-    float4* s_b = s_a + N;                                            // [N] pong
+    float4* s_a = reinterpret_cast<float4*>(s_idx + ((N + 3) & ~3));  // [N] (dL/dv, g_x, g_y, -), scanned in place
     __shared__ float s_red[33];
     const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const float S = saved[2 * b], S2 = saved[2 * b + 1];
@@ -198,7 +197,7 @@ soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __r
     {
         __shared__ float s_wt[96];                            // cross-warp scratch: [32] x 3 tail sums / run totals
         __shared__ int s_wi[64];                              // [32] segment-start flags, [32] last keys
-        const int lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
+        const int lane = tid & 31, wid = tid >> 5;
         const int per = (N + nt - 1) / nt;
         const int lo = min(tid * per, N), hi = min(lo + per, N);
         float tx = 0.f, ty = 0.f, tz = 0.f;
@@ -242,7 +241,6 @@ soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __r
         if (cont) {
             for (int i = lo; i < hi && s_idx[i] == kfirst; ++i) { float4 v = s_a[i]; v.x += px; v.y += py; v.z += pz; s_a[i] = v; }
         }
-        (void)nwarp;
         __syncthreads();
     }
     float4* src = s_a;
@@ -314,8 +312,8 @@ extern "C" int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_
     NFDPF_REQUIRE(probs && idx && saved && d_particles && d_probs, "soft_resample_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_bwd: B, N, d must be positive");
     NFDPF_REQUIRE(alpha > 0.0 && alpha <= 1.0, "soft_resample_bwd: need 0 < alpha <= 1, got %g", alpha);
-    const size_t smem = (size_t)((N + 3) & ~3) * sizeof(int) + (size_t)N * 2 * sizeof(float4);
-    if (smem > 200 * 1024) { set_error("soft_resample_bwd: N=%d exceeds the shared-memory row limit (5600)", N); return NFDPF_ERR_UNSUPPORTED; }
+    const size_t smem = (size_t)((N + 3) & ~3) * sizeof(int) + (size_t)N * sizeof(float4);
+    if (smem > 200 * 1024) { set_error("soft_resample_bwd: N=%d exceeds the shared-memory row limit (10200)", N); return NFDPF_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024)
         NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     soft_resample_bwd_kernel<<<B, pick_threads(N), smem, (cudaStream_t)stream>>>(
