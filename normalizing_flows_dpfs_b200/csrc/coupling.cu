@@ -279,8 +279,10 @@ extern "C" int nfdpf_coupling_fwd(const float* packed, int n_flows, int D, int C
 extern "C" int64_t nfdpf_coupling_bwd_workspace(int n_flows, int D, int C_row, int C_part, int B, int N) {
     (void)N;
     if (n_flows < 1 || D < 2 || B < 1) return 0;
-    // per-CTA partial gradients + per-trajectory layer-1 delta sums (row-context gradient, D = 2 path)
-    return ((int64_t)bwd_grid(B) * 4 * n_flows * packed_fcnn_size(D / 2, C_row + C_part) + (int64_t)B * 4 * n_flows * H) * (int64_t)sizeof(float);
+    if (D == 2 && C_part == 0)   // per-warp partial-gradient rows + per-CTA row-context partials (coupling_d2.cu)
+        return (int64_t)coupling_bwd_d2_workspace_floats(n_flows, C_row, B) * (int64_t)sizeof(float);
+    // per-CTA partial gradients
+    return (int64_t)bwd_grid(B) * 4 * n_flows * packed_fcnn_size(D / 2, C_row + C_part) * (int64_t)sizeof(float);
 }
 
 extern "C" int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C_part, const float* y,

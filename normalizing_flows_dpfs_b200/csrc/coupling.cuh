@@ -24,7 +24,8 @@ constexpr int H = NFDPF_HIDDEN;  // 8
 int bwd_grid(int B);  // persistent grid of the backward kernels (also sizes the partial-gradient workspace)
 // d_packed[i] += sum_c partials[c][i], fixed order, fp64 accumulate (coupling.cu)
 int launch_reduce_partials(const float* partials, int n_parts, int n_params, float* d_packed, cudaStream_t st);
-// register-accumulating backward for D = 2 stacks with row-constant context only (coupling_d2.cu)
+// register-accumulating backward for D = 2 stacks with row-constant context only (coupling_d2.cu) and its workspace size
+size_t coupling_bwd_d2_workspace_floats(int n_flows, int C_row, int B);
 int launch_coupling_bwd_d2(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, int inverse, int B, int N,
                            const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* d_packed, void* workspace,
                            cudaStream_t st);

@@ -1,52 +1,86 @@
 // (K1, headline shape) Backward of the D = 2 coupling stack with row-constant context (nf_dyn: C = 4, cond_model: C = 36).
+// Reference math: nf/flows.py:215-239 (RealNVP_cond forward / inverse), nf/flows.py:101-114 (FCNN), walked backwards from the
+// stack OUTPUT (couplings are invertible: nothing but y is read from HBM, activations are recomputed).
 //
-// Every weight-gradient product is accumulated in REGISTERS (the generic backward of coupling.cu reduces them through a
-// shared-memory tile and is LDS-bound).  Layout of the work:
-//   * a persistent CTA keeps the state (lo, up, g_lo, g_up, g_logdet: 5 floats) of up to E_MAX "entries" (<= 1024 particles
-//     of one trajectory each) resident in shared memory and walks the stack STAGE-OUTER: all resident particles go through
-//     stage st before anybody starts stage st - 1.  A thread therefore keeps the 97 gradient accumulators of ONE net
-//       dW1[:,x] (8), db1 (8, per entry: it also drives the row-context columns), dW2 (64), db2 (8), dW3 (8), db3 (1)
-//     live across ~56 particles and the CTA-wide reduction (warp butterfly -> per-warp slots -> owner thread) runs once per
-//     (resident set, net) instead of once per (trajectory, net);
-//   * the two nets of a stage are split over the two halves of the CTA: threads 0-127 own the t-net, threads 128-255 the
-//     s-net, for the SAME particles.  Each half runs its net forward (activations recomputed from the stage output: couplings
-//     are invertible, nothing but y is read from HBM), the halves exchange t and s through shared memory (one 64-thread
-//     named barrier per warp pair and 64 particles), then each runs its net backward with the activations still in registers -- no activation stash;
-//   * a thread evaluates its net for TWO particles at once: the pair is the packed operand of every FFMA2 (fma.rn.f32x2, the
-//     weight being the broadcast scalar), so every weight is loaded once per two particles and the FMA issue slots halve.
+// Round-2 design (the round-1 kernel: 8 warps per SM, 221 registers, 812 issue slots per particle pair and net, CTA halves
+// exchanging t / s through named barriers):
+//   * FFMA2 packs over adjacent UNITS of one particle, not over a particle pair.  Every activation / delta vector lives as four
+//     (unit 2i, unit 2i+1) register pairs; the weights come from shared memory as ready-made pairs (both W2 and its transpose are
+//     kept: the forward needs columns, the data-gradient rows); scalars enter as the FFMA2 broadcast operand (SASS `R.F32`).
+//     The 97 weight-gradient products then are  acc[j][k:k+2] += d2[j] * h1[k:k+2]  -- natural pairs x broadcast scalar -- and
+//     the ~110 register moves per iteration that re-paired values in the particle-pair form are gone (812 -> ~500 slots).
+//   * tanh: (2^a0, 2^a1) -> FADD2 -> two MUFU.RCP -> FFMA2: three issue slots per activation (the shared-reciprocal pair of
+//     the forward kernel costs six; this kernel is short of issue slots and FMA-pipe cycles, not of MUFU throughput).
+//   * net-sequential passes instead of t-/s-net CTA halves: per stage a warp walks its particles twice, once per net.  One extra
+//     float per particle carries what the second net needs from the first (forward direction: t; inverse direction: e^s).
+//   * WARP-PRIVATE pipelines: a warp owns a contiguous range of tasks (32 x PPT particles) of the CTA's resident set for the whole
+//     launch -- it loads them, runs all 4 n_flows passes over them and stores their d_x.  Particle state in shared memory is
+//     touched by its owner lane only, so there is no barrier between passes and no exchange buffer; warps drift apart, which
+//     spreads the MUFU-heavy forward halves and the FMA-heavy backward halves of the tasks over time.  After a pass the warp
+//     folds its 97 accumulators with a transposed butterfly and writes ITS OWN partial-gradient row to global memory.
+//   * PPT particles per thread share every weight load (PPT = 2, 8 warps: 49 LDS.128 per 64 particles and net; PPT = 1, 12 warps).
+//   * the row-context columns of dW1 (and db1, and d(row_ctx)) are formed per CTA from the per-trajectory layer-1 delta sums;
+//     d2_reduce_kernel sums the per-warp rows and per-CTA row-context partials in a fixed order (fp64): run-to-run deterministic.
+// Measured dead ends of this round are listed in DESIGN.md (weights through constant memory / uniform registers, 16 warps).
+#include <stdlib.h>
+
 #include "coupling.cuh"
 
 namespace nfdpf {
 
-using L2_ = Lay<1, 0>;
-constexpr int NACC = 97;          // == Rows<1,0>::NOUT, same ordering as packed_offset<1,0>
-constexpr int TPD = 256;          // threads per CTA: two net-groups of four warps, one CTA per SM
-constexpr int GRP = 128;          // threads per net-group
-constexpr int PPI = 2 * GRP;      // particles per iteration: two per thread (q, q + GRP)
-constexpr int CHUNK = 1024;       // particles per entry
-constexpr int NWARP = TPD / 32;
+using u64 = unsigned long long;
+constexpr int NACC = 97;          // == Rows<1,0>::NOUT, same ordering as packed_offset<1,0>: dW1 8 | db1 8 | dW2 64 | db2 8 | dW3 8 | db3 1
+constexpr int CHUNK = 1024;       // particle slots per entry (an entry = up to 1024 particles of one trajectory)
 constexpr int E_CAP = 9;          // upper bound of resident entries (the launcher fits E_MAX <= E_CAP into shared memory)
+constexpr int NSTATE = 6;         // lo, up, g_lo, g_up, g_logdet, carry
+constexpr int D2_MAX_WARPS = 12;  // sizes the partial-gradient workspace (nfdpf_coupling_bwd_workspace)
 
-struct D2Smem {
-    static size_t fixed_floats(int n_fcnn, int C_row) {
-        return (size_t)n_fcnn * L2_::SIZE + (size_t)n_fcnn * H * C_row        // images, w1r
-               + 12 * GRP                                                      // exchange: t, s, dc_t (two particles per thread, double buffered)
-               + NWARP * 100                                                   // per-warp reduction slots
-               + (size_t)n_fcnn * NACC + 8;                                    // acc
-    }
-    static size_t entry_floats(int n_fcnn, int C_row) {
-        return 5 * (size_t)CHUNK                                               // lo, up, glo, gup, gld
-               + 2 * (size_t)n_fcnn * H                                        // hb, d1row
-               + NWARP * H + C_row;                                            // per-warp b1 sums, ctx
-    }
-    static size_t bytes(int n_fcnn, int C_row, int e_max) { return (fixed_floats(n_fcnn, C_row) + e_max * entry_floats(n_fcnn, C_row)) * sizeof(float); }
+// Shared-memory image of one 1 -> 8 -> 8 -> 1 net (floats; every block 16-byte aligned).  "s" = multiplied by TANH_SCALE.
+struct Img {
+    static constexpr int W1 = 0;      // [8]      W1s[k]            (conditioning column)
+    static constexpr int W2T = 8;     // [8][8]   W2s[j][k] at [k][j]   forward: a2[j:j+2] += W2T[k][j:j+2] * h1[k]
+    static constexpr int B2 = 72;     // [8]      b2s
+    static constexpr int W3 = 80;     // [8]
+    static constexpr int W3I = 88;    // [8]      W3 * TANH_ISCALE      delta2 / scale = dout * (W3I - W3I h2^2)
+    static constexpr int W2 = 96;     // [8][8]   W2s[j][k] at [j][k]   backward: da1[k:k+2] += W2[j][k:k+2] * d2[j]
+    static constexpr int B3 = 160;    // [1] (+3 pad)
+    static constexpr int SIZE = 164;
 };
+
+// ---- packed FP32 pairs ------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 P2(float lo, float hi) { u64 p; asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(lo), "f"(hi)); return p; }
+__device__ __forceinline__ void U2(u64 p, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ u64 bc(float s) { return P2(s, s); }                      // folds into the broadcast-scalar operand form
+__device__ __forceinline__ u64 neg2(u64 p) { float a, b; U2(p, a, b); return P2(-a, -b); }   // folds into the operand negation
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// accumulate forms: the accumulator is tied to the destination register pair
+__device__ __forceinline__ void acc_fma2(u64& acc, u64 a, u64 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void acc_add2(u64& acc, u64 a) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(a)); }
+template <int I>
+__device__ __forceinline__ float half_of(u64 p) { float a, b; U2(p, a, b); return I ? b : a; }
+__device__ __forceinline__ void ld4(const float* p, u64 (&w)[4]) {                   // eight floats = four pairs, two LDS.128
+    const ulonglong2 a = reinterpret_cast<const ulonglong2*>(p)[0], b = reinterpret_cast<const ulonglong2*>(p)[1];
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+}
+// two tanh of pre-scaled arguments (a = 2 log2(e) x): 1 - 2 / (2^a + 1); ~2e-7 absolute error (common.cuh)
+__device__ __forceinline__ u64 tanh2(u64 a) {
+    float x, y, ex, ey, sx, sy, rx, ry;
+    U2(a, x, y);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(y));
+    U2(add2(P2(ex, ey), bc(1.0f)), sx, sy);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rx) : "f"(sx));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ry) : "f"(sy));
+    return fma2(bc(-2.0f), P2(rx, ry), bc(1.0f));
+}
 
 // Warp-level transposed butterfly of the 97 per-thread accumulators: in round r the lanes with bit (16 >> r) set keep the
 // upper half of the live values and send the lower half (and vice versa), so 96 values cost 93 shuffles instead of 480;
 // lane L ends up owning the sums of entries 3L..3L+2.  Entry 96 (db3) takes a plain butterfly.  Result -> the warp's slot.
-__device__ __forceinline__ void warp_reduce_to_slot(float (&acc)[NACC], float* s_part) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void warp_reduce_to_slot(float (&acc)[NACC], float* slot) {
+    const int lane = threadIdx.x & 31;
 #define NFDPF_ROUND(HALFN, OFF)                                                         \
     {                                                                                   \
         const bool up_ = (lane & OFF) != 0;                                             \
@@ -61,17 +95,16 @@ __device__ __forceinline__ void warp_reduce_to_slot(float (&acc)[NACC], float* s
     float last = acc[96];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) last += __shfl_xor_sync(FULL, last, o);
-    float* slot = s_part + warp * 100;
     slot[3 * lane] = acc[0]; slot[3 * lane + 1] = acc[1]; slot[3 * lane + 2] = acc[2];
     if (lane == 0) slot[96] = last;
 }
 
-// Warp sums of the 8 layer-1 delta accumulators of one entry -> d1part[warp][8]; the accumulators are cleared.
-__device__ __forceinline__ void warp_reduce_b1(float (&acc)[NACC], float* s_d1part_e) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Warp sums of the 8 layer-1 delta accumulators (pairs 4..7) of one entry -> dst[8]; the accumulators are cleared.
+__device__ __forceinline__ void warp_flush_b1(u64 (&A)[48], float* dst) {
+    const int lane = threadIdx.x & 31;
     float v[H];
 #pragma unroll
-    for (int k = 0; k < H; ++k) { v[k] = acc[H + k]; acc[H + k] = 0.f; }
+    for (int k = 0; k < 4; ++k) { U2(A[4 + k], v[2 * k], v[2 * k + 1]); A[4 + k] = 0ull; }
 #define NFDPF_ROUND(HALFN, OFF)                                                         \
     {                                                                                   \
         const bool up_ = (lane & OFF) != 0;                                             \
@@ -85,316 +118,463 @@ __device__ __forceinline__ void warp_reduce_b1(float (&acc)[NACC], float* s_d1pa
 #undef NFDPF_ROUND
     v[0] += __shfl_xor_sync(FULL, v[0], 2);
     v[0] += __shfl_xor_sync(FULL, v[0], 1);
-    if ((lane & 3) == 0) s_d1part_e[warp * H + (lane >> 2)] = v[0];   // lane bits 4,3,2 select the entry index
+    if ((lane & 3) == 0) dst[lane >> 2] = v[0];   // lane bits 4,3,2 select the entry index
 }
 
-// Two particles per thread: the pair (particle 0, particle 1) is the packed operand of every FMA, the weight its broadcast
-// scalar -- every weight is loaded once per two particles and no value ever needs re-packing.  Arrays are [unit][particle].
-__device__ __forceinline__ void fwd_d2x2(const float* __restrict__ img, const float* __restrict__ hb, float c0, float c1, float (&h1)[H][2],
-                                         float (&h2)[H][2], float (&out)[2]) {
-    using L = L2_;
-    float hbv[8];
-    ld8(hb, hbv);
+// The four kinds of pass.  Forward-direction stage out = t + in e^s: the t-net goes first (its delta is g_v, no s needed) and
+// leaves t in the carry slot; the s-net pass then inverts the stage.  Inverse-direction stage out = (in - t) e^-s: the s-net
+// goes first (its delta -(g_v v + g_ld) needs no t), rescales g_v and leaves e^s; the t-net pass then restores the input.
+enum { FWD_T = 0, FWD_S = 1, INV_T = 2, INV_S = 3 };
+
+struct StatePtrs {
+    float* c;     // conditioning half (read only in a stage)
+    float* gc;    // its gradient (+= dc of both nets)
+    float* v;     // transformed half: stage output -> stage input
+    float* gv;    // its gradient
+    float* gld;   // gradient of the log-det (constant along the walk)
+    float* ex;    // carry between the two passes of a stage
+};
+
+// One task: PPT particles per lane (slots q0, q0 + 32, ...), one net.  n_rem = live particles from the lane's first slot on.
+template <int PPT, int KIND>
+__device__ __forceinline__ void net_task(const float* __restrict__ img, const float* __restrict__ hb, const StatePtrs& S, int q0,
+                                         int n_rem, u64 (&A)[48], float& ab3) {
+    float c[PPT];
+    bool live[PPT];
 #pragma unroll
-    for (int k = 0; k < H; ++k) {
-        float a0 = hbv[k], a1 = hbv[k];
-        ffma2_s(a0, a1, img[L::W1 + k * L::S1], c0, c1);
-        tanh_prescaled_pair(a0, a1, h1[k][0], h1[k][1]);
+    for (int u = 0; u < PPT; ++u) { c[u] = S.c[q0 + 32 * u]; live[u] = 32 * u < n_rem; }
+    u64 h1[PPT][4], h2[PPT][4];
+    {   // layer 1: a1[k] = W1s[k] c + hb[k]
+        u64 w1[4], hbp[4];
+        ld4(img + Img::W1, w1);
+        ld4(hb, hbp);
+#pragma unroll
+        for (int u = 0; u < PPT; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h1[u][i] = tanh2(fma2(w1[i], bc(c[u]), hbp[i]));
     }
-    float b2[8];
-    ld8(img + L::B2, b2);
+    {   // layer 2: a2[j] = b2s[j] + sum_k W2s[j][k] h1[k]
+        u64 a2[PPT][4], b2[4];
+        ld4(img + Img::B2, b2);
 #pragma unroll
-    for (int j = 0; j < H; ++j) {
-        float w[8];
-        ld8(img + L::W2 + j * H, w);
-        float a0 = b2[j], a1 = b2[j];
+        for (int u = 0; u < PPT; ++u)
 #pragma unroll
-        for (int k = 0; k < H; ++k) ffma2_s(a0, a1, w[k], h1[k][0], h1[k][1]);
-        tanh_prescaled_pair(a0, a1, h2[j][0], h2[j][1]);
+            for (int i = 0; i < 4; ++i) a2[u][i] = b2[i];
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            u64 wr[4];
+            ld4(img + Img::W2T + 8 * k, wr);
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {
+                const float hk = (k & 1) ? half_of<1>(h1[u][k >> 1]) : half_of<0>(h1[u][k >> 1]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a2[u][i] = fma2(wr[i], bc(hk), a2[u][i]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PPT; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h2[u][i] = tanh2(a2[u][i]);
     }
-    float w3[8];
-    ld8(img + L::W3, w3);
-    float o0 = img[L::B3], o1 = o0;
+    float dout[PPT];
+    {   // layer 3 and the stage algebra
+        u64 w3[4];
+        ld4(img + Img::W3, w3);
+        const float b3 = img[Img::B3];
 #pragma unroll
-    for (int j = 0; j < H; ++j) ffma2_s(o0, o1, w3[j], h2[j][0], h2[j][1]);
-    out[0] = o0; out[1] = o1;
+        for (int u = 0; u < PPT; ++u) {
+            u64 o = fma2(w3[0], h2[u][0], P2(b3, 0.f));
+#pragma unroll
+            for (int i = 1; i < 4; ++i) o = fma2(w3[i], h2[u][i], o);
+            const float out = half_of<0>(o) + half_of<1>(o);
+            const int q = q0 + 32 * u;
+            float d;
+            if (KIND == FWD_T) {            // t-net first: d t = g_v; carry t
+                d = S.gv[q];
+                if (live[u]) S.ex[q] = out;
+            } else if (KIND == FWD_S) {     // s-net second: v_in = (v - t) e^-s, d s = g_v v_in e^s + g_ld, g_in = g_v e^s
+                const float t = S.ex[q], v = S.v[q], gv = S.gv[q], gld = S.gld[q];
+                const float es = exp_acc(out), ies = exp_acc(-out);
+                const float vin = (v - t) * ies;
+                d = fmaf(gv * vin, es, gld);
+                if (live[u]) { S.v[q] = vin; S.gv[q] = gv * es; }
+            } else if (KIND == INV_S) {     // s-net first: g_in = g_v e^-s, d s = -(g_v v + g_ld); carry e^s
+                const float v = S.v[q], gv = S.gv[q], gld = S.gld[q];
+                const float es = exp_acc(out), ies = exp_acc(-out);
+                d = -fmaf(gv, v, gld);
+                if (live[u]) { S.gv[q] = gv * ies; S.ex[q] = es; }
+            } else {                        // INV_T, t-net second: d t = -g_in, v_in = v e^s + t
+                d = -S.gv[q];
+                if (live[u]) S.v[q] = fmaf(S.v[q], S.ex[q], out);
+            }
+            dout[u] = live[u] ? d : 0.f;
+        }
+    }
+    u64 d2[PPT][4];
+    {   // delta2 / scale = dout (W3I - W3I h2^2); dW3 += dout h2; db2 += delta2; db3 += dout
+        u64 w3i[4];
+        ld4(img + Img::W3I, w3i);
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc_fma2(A[44 + i], bc(dout[u]), h2[u][i]);
+                const u64 g = fma2(neg2(mul2(h2[u][i], h2[u][i])), w3i[i], w3i[i]);
+                d2[u][i] = mul2(g, bc(dout[u]));
+                acc_add2(A[40 + i], d2[u][i]);
+            }
+            ab3 += dout[u];
+        }
+    }
+    u64 d1[PPT][4];
+    {   // da1[k] = sum_j W2s[j][k] d2[j]; dW2[j][k] += d2[j] h1[k]
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            u64 wr[4];
+            ld4(img + Img::W2 + 8 * j, wr);
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {
+                const float dj = (j & 1) ? half_of<1>(d2[u][j >> 1]) : half_of<0>(d2[u][j >> 1]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    d1[u][i] = j == 0 ? mul2(wr[i], bc(dj)) : fma2(wr[i], bc(dj), d1[u][i]);
+                    acc_fma2(A[8 + 4 * j + i], bc(dj), h1[u][i]);
+                }
+            }
+        }
+    }
+    {   // delta1 / scale = da1 (ISCALE - ISCALE h1^2); dW1 += c delta1; db1 += delta1; dc = sum_k W1s[k] delta1[k]
+        u64 w1[4];
+        ld4(img + Img::W1, w1);
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            u64 s = 0ull;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const u64 g = fma2(mul2(h1[u][i], h1[u][i]), bc(-TANH_ISCALE), bc(TANH_ISCALE));
+                const u64 dd = mul2(d1[u][i], g);
+                acc_fma2(A[i], bc(c[u]), dd);
+                acc_add2(A[4 + i], dd);
+                s = i == 0 ? mul2(w1[0], dd) : fma2(w1[i], dd, s);
+            }
+            const int q = q0 + 32 * u;
+            if (live[u]) S.gc[q] += half_of<0>(s) + half_of<1>(s);
+        }
+    }
 }
 
-__device__ __forceinline__ void bwd_d2x2(const float* __restrict__ img, float dout0, float dout1, const float (&h1)[H][2],
-                                         const float (&h2)[H][2], float (&d1)[H][2], float (&d2)[H][2], float (&dc)[2]) {
-    using L = L2_;
-    float w3[8];
-    ld8(img + L::W3, w3);
+
+// One pass = one net over the warp's own tasks [t_lo, t_hi).  At an entry boundary the per-entry layer-1 delta sums are flushed
+// (they drive the row-context gradient); at the end the 97 accumulators are folded over the lanes into `slot`.
+template <int PPT, int NW, int KIND>
+__device__ __forceinline__ void net_pass(const float* __restrict__ img, const float* __restrict__ s_hb_net, int hb_stride,
+                                         const StatePtrs& S, const int* __restrict__ s_task, const int* __restrict__ s_nlive,
+                                         int t_lo, int t_hi, int ne, float* __restrict__ s_d1part_net, float* __restrict__ slot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int TASK = 32 * PPT;
+    u64 A[48];
+    float ab3 = 0.f;
 #pragma unroll
-    for (int j = 0; j < H; ++j) {
-        float g0, g1, t0, t1;
-        fmul2_p(t0, t1, -TANH_ISCALE, -TANH_ISCALE, h2[j][0], h2[j][1]);
-        fma2_p(g0, g1, t0, t1, h2[j][0], h2[j][1], TANH_ISCALE, TANH_ISCALE);          // (1 - h2^2) / scale
-        fmul2_p(t0, t1, w3[j], w3[j], dout0, dout1);
-        fmul2_p(d2[j][0], d2[j][1], t0, t1, g0, g1);
+    for (int i = 0; i < 48; ++i) A[i] = 0ull;
+    for (int e = 0; e < ne; ++e)
+        if (lane < H) s_d1part_net[(e * NW + warp) * H + lane] = 0.f;
+    __syncwarp();
+    int t = t_lo;
+#pragma unroll 1
+    while (t < t_hi) {                                       // one segment = the warp's tasks inside one entry
+        const int code = s_task[t], e = code >> 8, m0 = code & 255, n_live = s_nlive[e];
+        const int seg_end = min(t_hi, t + (n_live + TASK - 1) / TASK - m0);
+        const float* hb = s_hb_net + e * hb_stride;
+        int q0 = e * CHUNK + m0 * TASK + lane, n_rem = n_live - m0 * TASK - lane;
+#pragma unroll 1
+        for (; t < seg_end; ++t, q0 += TASK, n_rem -= TASK) {
+            asm volatile("" ::: "memory");                   // keep the weight loads inside the loop (registers)
+            net_task<PPT, KIND>(img, hb, S, q0, n_rem, A, ab3);
+        }
+        warp_flush_b1(A, s_d1part_net + (e * NW + warp) * H);
     }
-    float da[H][2];
+    float acc[NACC];
 #pragma unroll
-    for (int k = 0; k < H; ++k) { da[k][0] = 0.f; da[k][1] = 0.f; }
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        float w[8];
-        ld8(img + L::W2 + j * H, w);
-#pragma unroll
-        for (int k = 0; k < H; ++k) ffma2_s(da[k][0], da[k][1], w[k], d2[j][0], d2[j][1]);
-    }
-    float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-        float g0, g1, t0, t1;
-        fmul2_p(t0, t1, -TANH_ISCALE, -TANH_ISCALE, h1[k][0], h1[k][1]);
-        fma2_p(g0, g1, t0, t1, h1[k][0], h1[k][1], TANH_ISCALE, TANH_ISCALE);
-        fmul2_p(d1[k][0], d1[k][1], da[k][0], da[k][1], g0, g1);
-        ffma2_s(p0, p1, img[L::W1 + k * L::S1], d1[k][0], d1[k][1]);
-    }
-    dc[0] = p0; dc[1] = p1;
+    for (int i = 0; i < 48; ++i) U2(A[i], acc[2 * i], acc[2 * i + 1]);
+    acc[96] = ab3;
+    warp_reduce_to_slot(acc, slot);
 }
 
-// gradient products of particle P of the pair
-template <int P>
-__device__ __forceinline__ void accumulate_x2(float (&acc)[NACC], const float (&d1)[H][2], const float (&d2)[H][2], float dout, float c,
-                                              const float (&h1)[H][2], const float (&h2)[H][2]) {
-#pragma unroll
-    for (int k = 0; k < H; k += 2) {
-        ffma2_s(acc[k], acc[k + 1], c, d1[k][P], d1[k + 1][P]);
-        ffma2_s(acc[H + k], acc[H + k + 1], 1.0f, d1[k][P], d1[k + 1][P]);
+template <int NT>
+struct D2Smem {
+    static constexpr int NW = NT / 32;
+    static size_t fixed_floats(int n_fcnn, int C_row) {
+        return (size_t)n_fcnn * Img::SIZE + (size_t)n_fcnn * H                // images, b1s
+               + (size_t)n_fcnn * H * C_row + (size_t)n_fcnn * H * (C_row + 1) + 3   // w1r, accR (+ bias column, pad)
+               + E_CAP * (CHUNK / 32) + 2 * 16 + 4 * 16;                     // task table, n_live / first-chunk flags, entry particle offsets (64-bit)
     }
-    unsigned long long h1p[H / 2];
-#pragma unroll
-    for (int k = 0; k < H; k += 2) h1p[k / 2] = pack2(h1[k][P], h1[k + 1][P]);
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-        const unsigned long long dj = pack2(d2[j][P], d2[j][P]);
-#pragma unroll
-        for (int k = 0; k < H; k += 2) ffma2(acc[2 * H + j * H + k], acc[2 * H + j * H + k + 1], dj, h1p[k / 2]);
+    static size_t entry_floats(int n_fcnn, int C_row) {
+        return NSTATE * (size_t)CHUNK + 2 * (size_t)n_fcnn * H + (size_t)n_fcnn * NW * H + ((C_row + 3) & ~3);   // state, hb, d1row, d1part, ctx
     }
-#pragma unroll
-    for (int j = 0; j < H; j += 2) {
-        ffma2_s(acc[2 * H + H * H + j], acc[2 * H + H * H + j + 1], 1.0f, d2[j][P], d2[j + 1][P]);
-        ffma2_s(acc[3 * H + H * H + j], acc[3 * H + H * H + j + 1], dout, h2[j][P], h2[j + 1][P]);
-    }
-    acc[4 * H + H * H] += dout;
+    static size_t bytes(int n_fcnn, int C_row, int e_max) { return (fixed_floats(n_fcnn, C_row) + e_max * entry_floats(n_fcnn, C_row)) * sizeof(float); }
+};
+
+// element o of the image of net f (see Img)
+__device__ __forceinline__ float img_value(const float* __restrict__ packed, int f, int o, int C_row) {
+    const int fin = 1 + C_row;
+    const float* pk = packed + (size_t)f * packed_fcnn_size(1, C_row);
+    const float* tail = pk + H * fin;                      // b1 [8] | W2 [8][8] | b2 [8] | W3 [8] | b3
+    if (o < Img::W2T) return TANH_SCALE * pk[o * fin];
+    if (o < Img::B2) { const int k = (o - Img::W2T) >> 3, j = (o - Img::W2T) & 7; return TANH_SCALE * tail[H + j * H + k]; }
+    if (o < Img::W3) return TANH_SCALE * tail[H + H * H + (o - Img::B2)];
+    if (o < Img::W3I) return tail[2 * H + H * H + (o - Img::W3)];
+    if (o < Img::W2) return TANH_ISCALE * tail[2 * H + H * H + (o - Img::W3I)];
+    if (o < Img::B3) return TANH_SCALE * tail[H + (o - Img::W2)];
+    return o == Img::B3 ? tail[3 * H + H * H] : 0.f;
 }
 
-__global__ void __launch_bounds__(TPD)
+// Workspace layout (floats): [grid * NW rows][n_fcnn * NACC] per-warp partial gradients (accumulator order, divided by the tanh
+// scale where grad_out_scale says so), then [grid][n_fcnn * 8 * (C_row + 1)] per-CTA row-context partials (last column: db1).
+template <int PPT, int NT>
+__global__ void __launch_bounds__(NT, 1)
 coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ y,
                        const float* __restrict__ row_ctx, int flags, int B, int N, const float* __restrict__ g_y,
-                       const float* __restrict__ g_ld, float* __restrict__ d_x, float* __restrict__ partials,
-                       float* __restrict__ d1rows, int e_max) {
+                       const float* __restrict__ g_ld, float* __restrict__ d_x, float* __restrict__ warp_rows,
+                       float* __restrict__ ctx_rows, float* __restrict__ d_row_ctx, int e_max) {
     extern __shared__ __align__(16) float smem[];
-    const int n_fcnn = 4 * n_flows, tid = threadIdx.x, inverse = flags & 1;
-    const int grp = tid >> 7, gi = tid & (GRP - 1), warp = tid >> 5;
-    float* s_img = smem;
-    float* s_w1r = s_img + n_fcnn * L2_::SIZE;
-    float* s_xt = s_w1r + (size_t)n_fcnn * H * C_row;        // [2][PPI] t-net outputs
-    float* s_xs = s_xt + 2 * PPI;                            // [2][PPI] s-net outputs
-    float* s_dct = s_xs + 2 * PPI;                           // [2][PPI] t-net gradient wrt the conditioning half
-    float* s_part = s_dct + 2 * PPI;                         // [NWARP][100]
-    float* s_acc = s_part + NWARP * 100;                     // [n_fcnn][NACC]
-    float* s_lo = s_acc + n_fcnn * NACC + 8;                 // state, [e_max][CHUNK] each
-    float* s_up = s_lo + (size_t)e_max * CHUNK;
-    float* s_glo = s_up + (size_t)e_max * CHUNK;
-    float* s_gup = s_glo + (size_t)e_max * CHUNK;
-    float* s_gld = s_gup + (size_t)e_max * CHUNK;
-    float* s_hb = s_gld + (size_t)e_max * CHUNK;             // [e_max][n_fcnn][H] hoisted layer-1 biases
-    float* s_d1row = s_hb + (size_t)e_max * n_fcnn * H;      // [e_max][n_fcnn][H] per-entry layer-1 delta sums
-    float* s_d1part = s_d1row + (size_t)e_max * n_fcnn * H;  // [e_max][NWARP][H]
-    float* s_ctx = s_d1part + (size_t)e_max * NWARP * H;     // [e_max][C_row]
-    const int pf = packed_fcnn_size(1, C_row);
-    for (int f = 0; f < n_fcnn; ++f)
-        load_fcnn_image<1, 0>(packed + (size_t)f * pf, C_row, s_img + f * L2_::SIZE, s_w1r + (size_t)f * H * C_row, tid, TPD);
-    for (int e = tid; e < n_fcnn * NACC; e += TPD) s_acc[e] = 0.f;
+    __shared__ float s_slot[NT / 32][100];
+    constexpr int NW = NT / 32, TASK = 32 * PPT;
+    const int n_fcnn = 4 * n_flows, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, inverse = flags & 1;
+    const int ctx_pad = (C_row + 3) & ~3, C1 = C_row + 1, nR = n_fcnn * H * C_row, nR1 = n_fcnn * H * C1;
+    float* s_img = smem;                                       // [n_fcnn][Img::SIZE]
+    float* s_b1 = s_img + n_fcnn * Img::SIZE;                  // [n_fcnn][8]   b1s
+    float* s_w1r = s_b1 + n_fcnn * H;                          // [n_fcnn][8][C_row]      W1s row-context columns
+    float* s_accR = s_w1r + nR;                                // [n_fcnn][8][C_row + 1]  their gradient (/ scale); last column: db1
+    int* s_task = reinterpret_cast<int*>(s_accR + ((nR1 + 3) & ~3));   // [E_CAP * 32]  (entry << 8) | task-in-entry
+    int* s_nlive = s_task + E_CAP * (CHUNK / 32);              // [16]
+    int* s_first = s_nlive + 16;                               // [16] 1 = first chunk of its trajectory
+    long long* s_p0 = reinterpret_cast<long long*>(s_first + 16);   // [16] first particle (global index), [16] trajectory
+    float* s_state = reinterpret_cast<float*>(s_p0 + 32);      // [NSTATE][e_max][CHUNK]
+    float* s_hb = s_state + (size_t)NSTATE * e_max * CHUNK;    // [e_max][n_fcnn][8]
+    float* s_d1row = s_hb + (size_t)e_max * n_fcnn * H;        // [e_max][n_fcnn][8] per-entry layer-1 delta sums (/ scale)
+    float* s_d1part = s_d1row + (size_t)e_max * n_fcnn * H;    // [n_fcnn][e_max][NW][8]
+    float* s_ctx = s_d1part + (size_t)n_fcnn * e_max * NW * H; // [e_max][ctx_pad]
+    const size_t plane = (size_t)e_max * CHUNK;
+    float* s_lo = s_state, *s_up = s_lo + plane, *s_glo = s_up + plane, *s_gup = s_glo + plane, *s_gld = s_gup + plane, *s_ex = s_gld + plane;
+
+    const int fin = 1 + C_row, pf = packed_fcnn_size(1, C_row);
+    for (int d = tid; d < n_fcnn * Img::SIZE; d += NT) s_img[d] = img_value(packed, d / Img::SIZE, d % Img::SIZE, C_row);
+    for (int e = tid; e < n_fcnn * H; e += NT) s_b1[e] = TANH_SCALE * packed[(size_t)(e / H) * pf + H * fin + (e % H)];
+    for (int e = tid; e < nR; e += NT) {
+        const int f = e / (H * C_row), r = e - f * H * C_row;
+        s_w1r[e] = TANH_SCALE * packed[(size_t)f * pf + (r / C_row) * fin + 1 + (r % C_row)];
+    }
+    for (int e = tid; e < nR1; e += NT) s_accR[e] = 0.f;
     __syncthreads();
 
+    float* my_rows = warp_rows + ((size_t)blockIdx.x * NW + warp) * n_fcnn * NACC;
     const int nc = (N + CHUNK - 1) / CHUNK;                                    // entries per trajectory
     const int n_traj = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_entries = n_traj * nc;
     for (int e0 = 0; e0 < n_entries; e0 += e_max) {
         const int ne = min(e_max, n_entries - e0);
-        // ---- load the resident set
+        if (tid < ne) {
+            const int j = e0 + tid, b = blockIdx.x + (j / nc) * gridDim.x, c0 = (j % nc) * CHUNK;
+            s_nlive[tid] = min(CHUNK, N - c0);
+            s_first[tid] = c0 == 0;
+            s_p0[tid] = (long long)b * N + c0;
+            s_p0[16 + tid] = b;
+        }
+        __syncthreads();
+        for (int i = tid; i < ne * C_row; i += NT) {
+            const int e = i / C_row, c = i - e * C_row;
+            s_ctx[e * ctx_pad + c] = row_ctx[(size_t)s_p0[16 + e] * C_row + c];
+        }
+        // task table: entry e contributes ceil(n_live / TASK) tasks, entries in order
+        int n_tasks = 0;
         for (int e = 0; e < ne; ++e) {
-            const int j = e0 + e, b = blockIdx.x + (j / nc) * gridDim.x, c0 = (j % nc) * CHUNK;
-            const int n_live = min(CHUNK, N - c0);
-            const size_t p0 = (size_t)b * N + c0;
-#pragma unroll                    // CHUNK / TPD = 4 independent iterations: all twelve loads in flight before the first store
-            for (int q = tid; q < CHUNK; q += TPD) {
+            const int te = (s_nlive[e] + TASK - 1) / TASK;
+            for (int m = tid; m < te; m += NT) s_task[n_tasks + m] = (e << 8) | m;
+            n_tasks += te;
+        }
+        __syncthreads();
+        // hoisted layer-1 biases: hb[e][f][k] = b1s + sum_c W1s_r[f][k][c] ctx[e][c]   (four lanes per output)
+        {
+            const int sub = tid & 3, total = ne * n_fcnn * H;
+            for (int o0 = 0; o0 < total; o0 += NT / 4) {
+                const int o = o0 + (tid >> 2);
+                float a = 0.f;
+                if (o < total) {
+                    const int e = o / (n_fcnn * H), fk = o - e * n_fcnn * H;
+                    const float* w = s_w1r + (size_t)fk * C_row;
+                    const float* cx = s_ctx + e * ctx_pad;
+                    for (int c = sub; c < C_row; c += 4) a = fmaf(w[c], cx[c], a);
+                }
+                a += __shfl_xor_sync(FULL, a, 1);
+                a += __shfl_xor_sync(FULL, a, 2);
+                if (o < total && sub == 0) s_hb[o] = a + s_b1[o % (n_fcnn * H)];
+            }
+        }
+        // ---- the warp's own tasks: load (each lane loads exactly the particle slots it will work on)
+        const int t_lo = (warp * n_tasks) / NW, t_hi = ((warp + 1) * n_tasks) / NW;
+#pragma unroll 2
+        for (int t = t_lo; t < t_hi; ++t) {
+            const int code = s_task[t], e = code >> 8, m = code & 255, n_live = s_nlive[e];
+            const size_t p0 = (size_t)s_p0[e];
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {
+                const int q = m * TASK + 32 * u + lane, i = e * CHUNK + q;
                 const bool live = q < n_live;
                 const float2 yy = live ? reinterpret_cast<const float2*>(y)[p0 + q] : make_float2(0.f, 0.f);
                 const float2 gg = live && g_y ? reinterpret_cast<const float2*>(g_y)[p0 + q] : make_float2(0.f, 0.f);
-                const int o = e * CHUNK + q;
-                s_lo[o] = yy.x; s_up[o] = yy.y; s_glo[o] = gg.x; s_gup[o] = gg.y;
-                s_gld[o] = live && g_ld ? ((flags & 2) ? -g_ld[p0 + q] : g_ld[p0 + q]) : 0.f;
+                const float gl = live && g_ld ? g_ld[p0 + q] : 0.f;
+                s_lo[i] = yy.x; s_up[i] = yy.y; s_glo[i] = gg.x; s_gup[i] = gg.y;
+                s_gld[i] = (flags & 2) ? -gl : gl;
+                s_ex[i] = 0.f;
             }
-            for (int c = tid; c < C_row; c += TPD) s_ctx[e * C_row + c] = row_ctx[(size_t)b * C_row + c];
         }
-        __syncthreads();
-        for (int e = 0; e < ne; ++e) hoist_row_context_par<1, 0>(s_img, s_w1r, s_ctx + e * C_row, C_row, n_fcnn, s_hb + (size_t)e * n_fcnn * H);
-        __syncthreads();
+        __syncthreads();          // hb complete (the particle state itself is lane-private)
         // forward pass ran flows 0..n-1 (t1/s1 then t2/s2): walk back n-1..0 (t2/s2 then t1/s1);
         // inverse pass ran flows n-1..0 (t2/s2 then t1/s1): walk back 0..n-1 (t1/s1 then t2/s2)
 #pragma unroll 1
-        for (int st = 0; st < 2 * n_flows; ++st) {
+        for (int ps = 0; ps < 4 * n_flows; ++ps) {
+            const int st = ps >> 1, second = ps & 1;
             const int f = inverse ? st / 2 : n_flows - 1 - st / 2;
             const int pair = inverse ? (st & 1) : 1 - (st & 1);       // 0: t1/s1 (c = lower), 1: t2/s2 (c = upper)
-            const int fm = 4 * f + 2 * pair + grp;                    // the net this half of the CTA owns
-            const float* img = s_img + fm * L2_::SIZE;
-            const float* s_c = pair ? s_up : s_lo;                    // conditioning half and its gradient
-            float* s_gc = pair ? s_gup : s_glo;
-            float* s_v = pair ? s_lo : s_up;                          // transformed half (output value -> input value) and its gradient
-            float* s_gv = pair ? s_glo : s_gup;
-            float acc[NACC];
-#pragma unroll
-            for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-            int it = 0, prev_q = -1;
-#pragma unroll 1
-            for (int e = 0; e < ne; ++e) {
-                const int j = e0 + e, c0 = (j % nc) * CHUNK;
-                const int n_live = min(CHUNK, N - c0), iters = (n_live + PPI - 1) / PPI;
-                const float* hb = s_hb + ((size_t)e * n_fcnn + fm) * H;
-#pragma unroll 1
-                for (int m = 0; m < iters; ++m, ++it) {
-                    asm volatile("" ::: "memory");
-                    const int q = e * CHUNK + m * PPI + gi, par = (it & 1) * PPI;     // this thread's particles: q and q + GRP
-                    const bool live0 = m * PPI + gi < n_live, live1 = m * PPI + GRP + gi < n_live;
-                    const float c0v = s_c[q], c1v = s_c[q + GRP];
-                    float h1[H][2], h2[H][2], out[2];
-                    fwd_d2x2(img, hb, c0v, c1v, h1, h2, out);
-                    float gv0 = 0.f, gv1 = 0.f;
-                    if (grp == 0) { s_xt[par + gi] = out[0]; s_xt[par + GRP + gi] = out[1]; gv0 = s_gv[q]; gv1 = s_gv[q + GRP]; }
-                    else          { s_xs[par + gi] = out[0]; s_xs[par + GRP + gi] = out[1]; }
-                    // t-warp w and s-warp w + 4 work on the same 64 particles and exchange only with each other: a 64-thread
-                    // named barrier per warp pair instead of a CTA barrier (the four pairs drift independently within a stage)
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
-                    float d1[H][2], d2[H][2], dc[2];
-                    float do0, do1;
-                    if (grp == 0) {         // t-net: d t = g_v (forward direction) or -g_v e^{-s} (inverse direction)
-                        do0 = inverse ? -gv0 * exp_acc(-s_xs[par + gi]) : gv0;
-                        do1 = inverse ? -gv1 * exp_acc(-s_xs[par + GRP + gi]) : gv1;
-                    } else {                // s-net: inverts the stage, owns the state update
-                        if (prev_q >= 0) { s_gc[prev_q] += s_dct[(PPI - par) + gi]; s_gc[prev_q + GRP] += s_dct[(PPI - par) + GRP + gi]; }
-#pragma unroll
-                        for (int p = 0; p < 2; ++p) {
-                            const int qq = q + p * GRP;
-                            const float t = s_xt[par + p * GRP + gi], sv = out[p];
-                            const float v = s_v[qq], gv = s_gv[qq], gld = s_gld[qq];
-                            const float es = exp_acc(sv), ies = exp_acc(-sv);
-                            float ds, vin, gin;
-                            if (!inverse) { vin = (v - t) * ies; ds = fmaf(gv * vin, es, gld); gin = gv * es; }
-                            else          { gin = gv * ies; ds = -fmaf(gv, v, gld); vin = fmaf(v, es, t); }
-                            s_v[qq] = vin; s_gv[qq] = gin;
-                            if (p == 0) do0 = ds; else do1 = ds;
-                        }
-                    }
-                    if (!live0) do0 = 0.f;
-                    if (!live1) do1 = 0.f;
-                    bwd_d2x2(img, do0, do1, h1, h2, d1, d2, dc);
-                    if (grp == 0) { s_dct[par + gi] = dc[0]; s_dct[par + GRP + gi] = dc[1]; }
-                    else { s_gc[q] += dc[0]; s_gc[q + GRP] += dc[1]; prev_q = q; }
-                    accumulate_x2<0>(acc, d1, d2, do0, c0v, h1, h2);
-                    accumulate_x2<1>(acc, d1, d2, do1, c1v, h1, h2);
-                }
-                warp_reduce_b1(acc, s_d1part + (size_t)e * NWARP * H);
+            const int net = inverse ? 1 - second : second;            // 0 = t-net, 1 = s-net
+            const int fm = 4 * f + 2 * pair + net;
+            const float* img = s_img + fm * Img::SIZE;
+            StatePtrs S;
+            S.c = pair ? s_up : s_lo;  S.gc = pair ? s_gup : s_glo;
+            S.v = pair ? s_lo : s_up;  S.gv = pair ? s_glo : s_gup;
+            S.gld = s_gld;             S.ex = s_ex;
+            const float* hbn = s_hb + fm * H;
+            const int hbs = n_fcnn * H;
+            float* d1p = s_d1part + (size_t)fm * e_max * NW * H;
+            float* slot = s_slot[warp];       // folded accumulators, then added to the warp's global row (resident sets accumulate)
+            if (!inverse) {
+                if (!net) net_pass<PPT, NW, FWD_T>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot);
+                else      net_pass<PPT, NW, FWD_S>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot);
+            } else {
+                if (net)  net_pass<PPT, NW, INV_S>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot);
+                else      net_pass<PPT, NW, INV_T>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot);
             }
-            warp_reduce_to_slot(acc, s_part);
-            __syncthreads();
-            if (grp == 1 && prev_q >= 0) { s_gc[prev_q] += s_dct[((it - 1) & 1) * PPI + gi]; s_gc[prev_q + GRP] += s_dct[((it - 1) & 1) * PPI + GRP + gi]; }
-            if (gi < NACC) {               // owner thread per parameter of the group's net: fixed-order sums
-                const int k = gi;
-                float v = 0.f;
-                if (k >= H && k < 2 * H) {     // b1 block: per-entry sums (row-context hoist) and their total
-                    for (int e = 0; e < ne; ++e) {
-                        const float* dp = s_d1part + ((size_t)e * NWARP + 4 * grp) * H + (k - H);
-                        const float r = (dp[0] + dp[H]) + (dp[2 * H] + dp[3 * H]);
-                        s_d1row[((size_t)e * n_fcnn + fm) * H + (k - H)] = r;
-                        v += r;
-                    }
-                } else {
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) v += s_part[(4 * grp + w) * 100 + k];
-                }
-                s_acc[fm * NACC + k] += v;
-            }
-            __syncthreads();
+            __syncwarp();
+            float* row = my_rows + fm * NACC;
+            for (int k = lane; k < NACC; k += 32) row[k] = e0 == 0 ? slot[k] : row[k] + slot[k];
+            __syncwarp();
         }
-        // ---- store d_x and the per-trajectory layer-1 delta sums (the row-context columns of dW1 and d(row_ctx) are formed
-        // from them by rowctx_grad_kernel: keeps the 8 x C_row outer products out of the persistent loop)
-        for (int e = 0; e < ne; ++e) {
-            const int j = e0 + e, b = blockIdx.x + (j / nc) * gridDim.x, c0 = (j % nc) * CHUNK;
-            const int n_live = min(CHUNK, N - c0);
-            const size_t p0 = (size_t)b * N + c0;
-            for (int q = tid; q < n_live; q += TPD) reinterpret_cast<float2*>(d_x)[p0 + q] = make_float2(s_glo[e * CHUNK + q], s_gup[e * CHUNK + q]);
-        }
-        if (tid < n_fcnn * H) {            // one thread per (net, k): entries in order (chunks of one trajectory add up)
-            for (int e = 0; e < ne; ++e) {
-                const int j = e0 + e, b = blockIdx.x + (j / nc) * gridDim.x, c0 = (j % nc) * CHUNK;
-                const float val = TANH_SCALE * s_d1row[(size_t)e * n_fcnn * H + tid];   // true delta sums, [f*8+k][b]: coalesced for rowctx_grad
-                float* dst = d1rows + (size_t)tid * B + b;
-                *dst = c0 == 0 ? val : *dst + val;
+        // ---- store the warp's d_x
+#pragma unroll 2
+        for (int t = t_lo; t < t_hi; ++t) {
+            const int code = s_task[t], e = code >> 8, m = code & 255, n_live = s_nlive[e];
+            const size_t p0 = (size_t)s_p0[e];
+#pragma unroll
+            for (int u = 0; u < PPT; ++u) {
+                const int q = m * TASK + 32 * u + lane, i = e * CHUNK + q;
+                if (q < n_live) reinterpret_cast<float2*>(d_x)[p0 + q] = make_float2(s_glo[i], s_gup[i]);
             }
+        }
+        __syncthreads();          // every warp's per-entry layer-1 delta sums are in place
+        for (int o = tid; o < ne * n_fcnn * H; o += NT) {     // fixed-order sums over the warps
+            const int e = o / (n_fcnn * H), fk = o - e * n_fcnn * H, f = fk / H, k = fk - f * H;
+            const float* dp = s_d1part + (((size_t)f * e_max + e) * NW) * H + k;
+            float r = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) r += dp[w * H];
+            s_d1row[o] = r;
+        }
+        __syncthreads();
+        // ---- row-context gradients from the per-entry layer-1 delta sums (scales cancel: W1s_r * (delta / s) = W1_r * delta)
+        for (int o = tid; o < nR1; o += NT) {                     // dW1_r[f][k][c] (/ scale) += sum_e D1[e][f][k] ctx[e][c]; c = C_row: db1
+            const int fk = o / C1, c = o - fk * C1;
+            float a = s_accR[o];
+            for (int e = 0; e < ne; ++e) a = fmaf(s_d1row[(size_t)e * n_fcnn * H + fk], c < C_row ? s_ctx[e * ctx_pad + c] : 1.0f, a);
+            s_accR[o] = a;
+        }
+        if (d_row_ctx) {
+            for (int c = tid; c < C_row; c += NT)                 // d ctx[b][c] = sum_{f,k} W1_r[f][k][c] delta1sum[b][f][k]
+                for (int e = 0; e < ne; ++e) {                    // one thread per column, entries in order: the chunks of one
+                    float a = 0.f;                                // trajectory (all in this CTA, consecutive) add up race-free
+                    for (int fk = 0; fk < n_fcnn * H; ++fk) a = fmaf(s_w1r[(size_t)fk * C_row + c], s_d1row[(size_t)e * n_fcnn * H + fk], a);
+                    float* dst = d_row_ctx + (size_t)s_p0[16 + e] * C_row + c;
+                    *dst = s_first[e] ? a : *dst + a;
+                }
         }
         __syncthreads();
     }
-    float* out = partials + (size_t)blockIdx.x * n_fcnn * pf;
-    for (int e = tid; e < n_fcnn * NACC; e += TPD) {
-        out[(size_t)(e / NACC) * pf + packed_offset<1, 0>(e % NACC, C_row)] = s_acc[e] * grad_out_scale<1, 0>(e % NACC);
-    }
-    const int fin = 1 + C_row;
-    for (int e = tid; e < n_fcnn * H * C_row; e += TPD)   // row-context columns are produced by rowctx_grad_kernel
-        out[(size_t)(e / (H * C_row)) * pf + ((e / C_row) % H) * fin + 1 + (e % C_row)] = 0.f;
+    float* out = ctx_rows + (size_t)blockIdx.x * nR1;
+    for (int e = tid; e < nR1; e += NT) out[e] = s_accR[e];
 }
 
-// dW1[f][k][1 + c] += sum_b D1[b][f][k] * ctx[b][c]   (one warp per output, fp64, fixed order)
-// d_row_ctx[b][c]   = sum_{f,k} W1[f][k][1 + c] * D1[b][f][k]
-__global__ void rowctx_grad_kernel(const float* __restrict__ packed, const float* __restrict__ d1rows, const float* __restrict__ row_ctx,
-                                   int n_fcnn, int C_row, int B, float* __restrict__ d_packed, float* __restrict__ d_row_ctx) {
-    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const int n_w = n_fcnn * H * C_row, pf = packed_fcnn_size(1, C_row), fin = 1 + C_row;
-    if (warp < n_w) {
-        const int fk = warp / C_row, c = warp % C_row;
-        double a = 0.0;
-        for (int b = lane; b < B; b += 32) a += (double)d1rows[(size_t)fk * B + b] * (double)row_ctx[(size_t)b * C_row + c];
-        a = warp_sum(a);
-        if (lane == 0) d_packed[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + c] += (float)a;
-    } else if (d_row_ctx) {
-        const int e = warp - n_w;            // one warp per (b, c)
-        if (e >= B * C_row) return;
-        const int b = e / C_row, c = e % C_row;
-        float a = 0.f;
-        for (int fk = lane; fk < n_fcnn * H; fk += 32)
-            a = fmaf(packed[(size_t)(fk / H) * pf + (fk % H) * fin + 1 + c], d1rows[(size_t)fk * B + b], a);
-        a = warp_sum(a);
-        if (lane == 0) d_row_ctx[(size_t)b * C_row + c] = a;
+// d_packed[target] += fixed-order fp64 column sums of the per-warp rows and the per-CTA row-context partials.  A block owns 32
+// consecutive columns (coalesced 128-byte row segments); its 8 warps take the rows round-robin and the partial sums are added
+// in warp order -- the order depends only on the launch geometry: run-to-run deterministic.
+__global__ void d2_reduce_kernel(const float* __restrict__ warp_rows, int n_rows, const float* __restrict__ ctx_rows, int n_cta,
+                                 int n_fcnn, int C_row, float* __restrict__ d_packed) {
+    __shared__ double s_sum[8][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int fin = 1 + C_row, pf = packed_fcnn_size(1, C_row), C1 = C_row + 1;
+    const int n_acc = n_fcnn * NACC, n_ctx = n_fcnn * H * C1;
+    const int col = blockIdx.x * 32 + lane;                 // column of [warp rows | ctx rows]
+    double a = 0.0;
+    if (col < n_acc) { for (int r = grp; r < n_rows; r += 8) a += (double)warp_rows[(size_t)r * n_acc + col]; }
+    else if (col < n_acc + n_ctx) { for (int r = grp; r < n_cta; r += 8) a += (double)ctx_rows[(size_t)r * n_ctx + (col - n_acc)]; }
+    s_sum[grp][lane] = a;
+    __syncthreads();
+    if (grp != 0 || col >= n_acc + n_ctx) return;
+#pragma unroll
+    for (int g = 1; g < 8; ++g) a += s_sum[g][lane];
+    int target;
+    float scale;
+    if (col < n_acc) {                                      // accumulator entry e of net f (b1 block: produced by the ctx partials)
+        const int f = col / NACC, e = col - f * NACC;
+        if (e >= H && e < 2 * H) return;
+        target = f * pf + packed_offset<1, 0>(e, C_row);
+        scale = grad_out_scale<1, 0>(e);
+    } else {                                                // [f][k][c]: row-context column c of W1 row k, or (c = C_row) b1[k]
+        const int o = col - n_acc, fk = o / C1, c = o - fk * C1, f = fk / H, k = fk - f * H;
+        target = f * pf + (c < C_row ? k * fin + 1 + c : H * fin + k);
+        scale = TANH_SCALE;
     }
+    d_packed[target] += (float)(a * (double)scale);
+}
+
+size_t coupling_bwd_d2_workspace_floats(int n_flows, int C_row, int B) {
+    const int n_fcnn = 4 * n_flows, grid = min(B, sm_count());
+    return (size_t)grid * ((size_t)D2_MAX_WARPS * n_fcnn * NACC + (size_t)n_fcnn * H * (C_row + 1));
+}
+
+template <int PPT, int NT>
+static int launch_cfg(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, int flags, int B, int N,
+                      const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* d_packed, void* workspace,
+                      cudaStream_t st) {
+    static_assert(NT / 32 <= D2_MAX_WARPS, "workspace is sized for D2_MAX_WARPS warps per CTA");
+    const int n_fcnn = 4 * n_flows;
+    const int grid = min(B, sm_count());   // one CTA per SM, persistent over trajectories
+    // resident entries: as many as the CTA's share of the work needs, bounded by shared memory
+    const int nc = (N + CHUNK - 1) / CHUNK, need = ((B + grid - 1) / grid) * nc;
+    int e_max = min(E_CAP, need);
+    using SM = D2Smem<NT>;
+    constexpr size_t STATIC = (NT / 32) * 100 * sizeof(float);
+    while (e_max > 1 && SM::bytes(n_fcnn, C_row, e_max) + STATIC > 226 * 1024) --e_max;
+    const size_t smem = SM::bytes(n_fcnn, C_row, e_max);
+    if (smem + STATIC > 226 * 1024) { set_error("coupling_bwd_d2: stack too large for shared memory (n_flows=%d, C_row=%d)", n_flows, C_row); return NFDPF_ERR_UNSUPPORTED; }
+    auto kern = coupling_bwd_d2_kernel<PPT, NT>;
+    NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float* warp_rows = (float*)workspace;
+    float* ctx_rows = warp_rows + (size_t)grid * (NT / 32) * n_fcnn * NACC;
+    kern<<<grid, NT, smem, st>>>(packed, n_flows, C_row, y, row_ctx, flags, B, N, g_y, g_ld, d_x, warp_rows, ctx_rows, d_row_ctx, e_max);
+    int rc = check_launch("coupling_bwd_d2");
+    if (rc) return rc;
+    const int n_cols = n_fcnn * NACC + n_fcnn * H * (C_row + 1);
+    d2_reduce_kernel<<<(n_cols + 31) / 32, 256, 0, st>>>(warp_rows, grid * (NT / 32), ctx_rows, grid, n_fcnn, C_row, d_packed);
+    return check_launch("d2_reduce");
 }
 
 int launch_coupling_bwd_d2(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, int inverse, int B, int N,
                            const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* d_packed, void* workspace,
                            cudaStream_t st) {
-    const int n_fcnn = 4 * n_flows;
-    const int grid = min(B, sm_count());   // one 8-warp CTA per SM (registers), persistent over trajectories
-    // resident entries: as many as the CTA's share of the work needs, bounded by shared memory
-    const int nc = (N + CHUNK - 1) / CHUNK, need = ((B + grid - 1) / grid) * nc;
-    int e_max = min(E_CAP, need);
-    while (e_max > 1 && D2Smem::bytes(n_fcnn, C_row, e_max) > 220 * 1024) --e_max;
-    const size_t smem = D2Smem::bytes(n_fcnn, C_row, e_max);
-    if (smem > 220 * 1024) { set_error("coupling_bwd_d2: stack too large for shared memory (n_flows=%d, C_row=%d)", n_flows, C_row); return NFDPF_ERR_UNSUPPORTED; }
-    if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(coupling_bwd_d2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int n_params = n_fcnn * packed_fcnn_size(1, C_row);
-    float* d1rows = (float*)workspace + (size_t)bwd_grid(B) * n_params;
-    coupling_bwd_d2_kernel<<<grid, TPD, smem, st>>>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, (float*)workspace,
-                                                    d1rows, e_max);
-    int rc = check_launch("coupling_bwd_d2");
-    if (rc) return rc;
-    rc = launch_reduce_partials((const float*)workspace, grid, n_params, d_packed, st);
-    if (rc || C_row == 0) return rc;
-    const int warps = n_fcnn * H * C_row + (d_row_ctx ? B * C_row : 0);
-    rowctx_grad_kernel<<<(warps + 7) / 8, 256, 0, st>>>(packed, d1rows, row_ctx, n_fcnn, C_row, B, d_packed, d_row_ctx);
-    return check_launch("rowctx_grad");
+    // NFDPF_D2_CFG=1 selects the one-particle-per-thread / 12-warp geometry (A/B measurements); default: two particles, 8 warps
+    static const int cfg = [] { const char* s = getenv("NFDPF_D2_CFG"); return s ? atoi(s) : 0; }();
+    if (cfg == 1)
+        return launch_cfg<1, 384>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st);
+    return launch_cfg<2, 256>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st);
 }
 
 }  // namespace nfdpf
