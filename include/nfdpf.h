@@ -48,13 +48,16 @@ int64_t nfdpf_launch_count(void);
  * Indices are bit-exact with the reference CPU path (ATen cascade row-sum + fp64-accumulated cumsum). */
 int nfdpf_soft_resample_fwd(const float* particles, const float* probs, const float* offsets, const float* markers,
                             double alpha, int B, int N, int d, float* particles_out, float* probs_out,
-                            int64_t* idx_out, float* saved, float* logprobs_out, void* stream);
-/* logprobs_out (B,N) or NULL: log of probs_out (DPFs.py:167), saves the filter loop one elementwise pass.
+                            int64_t* idx_out, float* saved, float* logprobs_out, const int32_t* gate, void* stream);
+/* gate: device int32 or NULL.  The ESS decision of DPFs.py:163-170 taken on the device (nfdpf_ess_gate): when *gate == 0 the
+ * call passes particles / weights through with identity ancestor indices (the `else` branch, DPFs.py:168-170) -- the filter
+ * loop needs no device-to-host synchronisation.  The backward must be given the same gate.
+ * logprobs_out (B,N) or NULL: log of probs_out (DPFs.py:167), saves the filter loop one elementwise pass.
  * backward: g_particles (B,N,d), g_probs (B,N), g_logprobs (B,N) (each may be NULL = zero)
  * -> d_particles (B,N,d), d_probs (B,N) */
 int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_probs, const float* probs, const int64_t* idx,
                             const float* saved, double alpha, int B, int N, int d, float* d_particles,
-                            float* d_probs, const float* g_logprobs, void* stream);
+                            float* d_probs, const float* g_logprobs, const int32_t* gate, void* stream);
 
 /* ---- (K2, weight half) log-weight update + normalisation: DPFs.py:187-192, utils.py:39-44 ----------
  * logw = logw_prev + lki + prior - propose (NULL terms are skipped); probs = softmax_N(logw) + add_eps;
@@ -133,11 +136,18 @@ int nfdpf_row_moments(const float* x, int B, int N, int d, float* out, int out_s
 int64_t nfdpf_ot_workspace(int B, int N);
 int nfdpf_ot_resample_fwd(const float* particles, const float* logw, float eps, float scaling, float threshold,
                           int max_iter, int B, int N, int d, float* particles_out, float* saved, int32_t* iters_out,
-                          void* workspace, void* stream);
+                          void* workspace, const int32_t* gate, void* stream);
 /* backward: d_particles = T^T g_out; the plan itself carries no gradient (transport.backward returns None,
  * resamplers.py:240-245) and neither do the weights. */
 int nfdpf_ot_resample_bwd(const float* g_out, const float* saved, float eps, int B, int N, int d, float* d_particles,
-                          void* stream);
+                          const int32_t* gate, void* stream);
+/* gate (device int32 or NULL) as for soft resampling: when *gate == 0 every Sinkhorn launch exits at once and particles_out =
+ * particles (d_particles = g_out).  The weights after a gated OT resample (1/N when it fired, the old ones otherwise,
+ * DPFs.py:166-170) come from nfdpf_gate_weights_fwd: w_out, logw_out (B,N); backward d_probs = (g_w + g_logw / probs) if the
+ * gate was closed, else 0. */
+int nfdpf_gate_weights_fwd(const float* probs, const int32_t* gate, int B, int N, float* w_out, float* logw_out, void* stream);
+int nfdpf_gate_weights_bwd(const float* g_w, const float* g_logw, const float* probs, const int32_t* gate, int B, int N,
+                           float* d_probs, void* stream);
 
 /* ---- pipe-peak probe (measurement aid for bench.py): launches streams of independent FFMA (kind 0) or
  * ex2.approx (kind 1) instructions; returns the number of instructions issued (time it with CUDA events). */
@@ -156,6 +166,31 @@ int nfdpf_proposal_terms_fwd(const float* back, const float* phys, const float* 
                              float* propose, void* stream);
 int nfdpf_proposal_terms_bwd(const float* g_prior, const float* back, const float* phys, const float* noise, float sigma,
                              int64_t P, float* d_back, float* d_phys, float* neg_g_prior, void* stream);
+
+
+/* ---- host-free step control and random draws (DPFs.py:163-165, model/models.py:199-200, resamplers.py:43,
+ *      utils.py:46-62) ---------------------------------------------------------------------------------------
+ * rng_state: device int64[2] = {seed, step counter}.  Draws are Philox4x32-10 keyed by the seed with counter = (element index,
+ * step counter, consumer tag): reproducible for a given seed, independent of the launch geometry, CUDA-graph replayable (the
+ * state lives on the device).  They are NOT the reference's CPU-generator stream: parity tests inject the reference's draws.
+ * ess_gate: *gate_out = force if force is 0 / 1, else (mean_b ess_inv[b * ess_stride] < N/2) with ess_inv = column 1 of the
+ * (B,2) row_stats of nfdpf_weight_update_fwd / nfdpf_measure_fwd (ess_stride = 2; DPFs.py:163-165); offsets_out (B,) or NULL
+ * receives U(0, 1/N) resampling offsets (resamplers.py:43); if `advance`, the step counter is incremented afterwards (call
+ * once per filter timestep). */
+int nfdpf_ess_gate(const float* ess_inv, int ess_stride, int B, int N, int force, int64_t* rng_state, int advance,
+                   int32_t* gate_out, float* offsets_out, void* stream);
+/* motion_moments with the noise drawn in-kernel: noise_out (B,N,2) ~ N(0, sigma^2), out = (particles + vel_b) + noise_out. */
+int nfdpf_motion_moments_rng(const float* particles, const float* vel, const int64_t* rng_state, float sigma, int B, int N,
+                             int d, float* out, float* noise_out, float* ctx, int ctx_stride, int ctx_off, void* stream);
+/* particle_initialization (utils.py:46-62): uniform on [-width/2, width/2)^2, or start[b, 0:2] + N(0, 1) if true_state. */
+int nfdpf_init_particles_rng(const float* start, int start_stride, const int64_t* rng_state, float width, int true_state, int B,
+                             int N, int d, float* out, void* stream);
+
+/* ---- supervised-loss prediction (losses.py:22): pred[b,:] = sum_n probs[b,n] particles[b,n,:] for one timestep; backward
+ * d_particles = g_pred[b] probs, d_probs = <g_pred[b], particles> (either output may be NULL). */
+int nfdpf_weighted_mean_fwd(const float* particles, const float* probs, int B, int N, int d, float* pred, void* stream);
+int nfdpf_weighted_mean_bwd(const float* g_pred, const float* particles, const float* probs, int B, int N, int d,
+                            float* d_particles, float* d_probs, void* stream);
 
 #ifdef __cplusplus
 }

@@ -44,9 +44,11 @@ class DPF(nn.Module):
         self.injected = None          # dict(init_particles, noise (B,T,N,2), offsets (B,T)) or None
         self.force_resample = None    # None = the reference's ESS gate; True / False = always / never
         self.rng_device = "cpu"       # "cpu": draws come from the CPU generator in the reference's order (seed-compatible);
-                                      # "cuda": motion noise / resampling offsets are drawn on the device (no per-step H2D,
-                                      #         CUDA-graph capturable) -- SURVEY 8(f2)
-        self.fired = []
+                                      # "cuda": initial cloud, motion noise and resampling offsets are drawn in-kernel (Philox,
+                                      #         no per-step H2D, CUDA-graph capturable) -- SURVEY 8(f2)
+        self._fired_host, self._gates = [], None
+        if getattr(args, "fast", False):   # --fast: host-free filter loop (device-side ESS gate + in-kernel random draws)
+            self.rng_device = "cuda"
 
     # ------------------------------------------------------------------------------------------ construction
     def build_model(self):
@@ -82,7 +84,10 @@ class DPF(nn.Module):
         start_image, start_state, image, state, q, visible = inputs
         state, start_state = state.to(device), start_state.to(device)
         image = image.permute(0, 1, 4, 2, 3).to(device)
-        vel = state[:, :, 2:] + torch.normal(0.0, 4.0, state[:, :, 2:].shape).to(device)
+        if self.rng_device == "cuda":
+            vel = state[:, :, 2:] + 4.0 * torch.randn(state[:, :, 2:].shape, device=state.device, dtype=state.dtype)
+        else:
+            vel = state[:, :, 2:] + torch.normal(0.0, 4.0, state[:, :, 2:].shape).to(device)
         (particle_list, particle_weight_list, noise_list, likelihood_list, init_weights_log, index_list, jac_list, prior_list,
          obs_likelihood) = self.filtering_pos(image, start_state, vel)
         mask = self.get_mask() if train else 1.0
@@ -106,96 +111,196 @@ class DPF(nn.Module):
                 image, likelihood_list, noise_list, obs_likelihood)
 
     # ----------------------------------------------------------------------------------------------- hot path
+    @property
+    def fired(self):
+        """Per-timestep ESS-gate decisions of the last filtering_pos call (list of bool).  With the device-side gate they are
+        read back lazily -- asking for them is the only device-to-host synchronisation they ever cause."""
+        if self._fired_host is None and self._gates is not None:
+            self._fired_host = [bool(v) for v in self._gates.tolist()]
+        return self._fired_host if self._fired_host is not None else []
+
+    @fired.setter
+    def fired(self, value):
+        self._fired_host, self._gates = list(value), None
+
+    def _rng_state(self, dev):
+        """Device int64[2] = {seed, step counter} of the in-kernel Philox draws (rng_device = "cuda").  Eager calls re-seed it from
+        torch's CPU generator (so `torch.manual_seed(s)` makes a run reproducible, like the reference's CPU draws) and restart the
+        counter; while a CUDA graph is being captured nothing is written from the host: replays keep advancing the device-side
+        counter, so every replay sees fresh noise."""
+        st = getattr(self, "_rng", None)
+        if st is None or st.device != dev:
+            st = torch.zeros(2, dtype=torch.int64, device=dev)
+            object.__setattr__(self, "_rng", st)     # plain attribute: not a buffer, so state_dict keys stay the reference's
+        if not torch.cuda.is_current_stream_capturing():
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            st.copy_(torch.tensor([seed, 0], dtype=torch.int64), non_blocking=True)
+        return st
+
     def filtering_pos(self, obs, start_state_vs, vel_input):
         """The per-timestep particle update (reference DPFs.py:144-216).  `obs` is (B,T,3,H,W) images, or (B,T,h)
-        precomputed encodings when `self.encoder` is an Identity (benchmarks exclude the CNN)."""
+        precomputed encodings when `self.encoder` is an Identity (benchmarks exclude the CNN).
+
+        Host-free where the reference is not: the whole-batch ESS gate (DPFs.py:163-165) is a device flag the resampling kernels
+        read (no sync per step) unless the reference's CPU-generator draw order has to be reproduced (rng_device = "cpu" with
+        nothing injected: the offsets are only drawn when the gate fires, so the host must know); the per-step outputs are
+        written by the kernels straight into pre-allocated (T,B,...) buffers and returned as transposed views (the reference
+        re-concatenates every list every step); the supervised loss' per-step predictions (losses.py:22) come from a fused
+        kernel and ride along on the returned particle list (see losses.supervised_loss)."""
+        from . import ops
         start_state, vel = start_state_vs[:, :2], start_state_vs[:, 2:]
-        B, N, inj = start_state.shape[0], self.num_particle, self.injected
-        if inj is not None and "init_particles" in inj:   # injected cloud: no host RNG, no H2D copy (graph-capturable)
+        B, N, T, inj = start_state.shape[0], self.num_particle, self.seq_len, self.injected or {}
+        dev = start_state.device
+        device_rng = self.rng_device == "cuda"
+        rng = self._rng_state(dev) if device_rng else None
+        if "init_particles" in inj:   # injected cloud: no host RNG, no H2D copy (graph-capturable)
             particles = inj["init_particles"]
-            init_weights_log = torch.log(torch.ones(B, N, device=particles.device) / N)
+            init_weights_log = torch.log(torch.ones(B, N, device=dev) / N)
+        elif device_rng:
+            particles = ops.init_particles(start_state, self.param.width, N, rng, self.param.init_with_true_state)
+            init_weights_log = torch.log(torch.ones(B, N, device=dev) / N)
         else:
             particles, init_weights_log = particle_initialization(start_state, self.param.width, N, self.state_dim,
                                                                   init_with_true_state=self.param.init_with_true_state)
         _, particle_probs, _, ess_inv = _weight_norm(init_weights_log)
-        identity_idx = torch.arange(B * N, device=particles.device, dtype=torch.int64).reshape(B, N)
         fused = isinstance(self.measurement_model, _FusedMeasurement)
-        lists = {k: [] for k in ("particles", "probs", "noise", "lki", "index", "jac", "prior")}
-        obs_likelihood, self.fired = 0.0, []
-        from . import ops
         soft = self.param.resampler_type == "soft"
-        for step in range(self.seq_len):
-            index_p = identity_idx
-            if self.force_resample is None:
-                fire = bool(ess_inv.mean() < 0.5 * N)          # whole-batch ESS gate, DPFs.py:163-165 (one D2H sync)
+        f32 = dict(dtype=torch.float32, device=dev)
+        buf = {"particles": torch.empty(T, B, N, 2, **f32), "probs": torch.empty(T, B, N, **f32), "lki": torch.empty(T, B, N, **f32),
+               "pred": torch.empty(T, B, 2, **f32)}
+        if "noise" not in inj:
+            buf["noise"] = torch.empty(T, B, N, 2, **f32)
+        if soft:
+            buf["index"] = torch.empty(T, B, N, dtype=torch.int64, device=dev)
+        if self.NF:
+            buf["jac"], buf["prior"] = torch.empty(T, B, N, **f32), torch.empty(T, B, N, **f32)
+        steps = {k: [] for k in ("particles", "probs", "lki", "pred", "jac", "prior")}
+        row_sums = []
+        # gate mode: constant (force_resample), host rule (reference RNG order, one sync per step) or device rule (no sync)
+        host_rule = self.force_resample is None and soft and not device_rng and "offsets" not in inj
+        device_rule = self.force_resample is None and not host_rule
+        self._gates = torch.empty(T, dtype=torch.int32, device=dev) if device_rule else None
+        self._fired_host = None if device_rule else []
+        identity_idx = None
+
+        def put(key, step, t):   # data the kernels could not write in place (non-fused paths) is copied into the list buffer
+            if t.data_ptr() != buf[key][step].data_ptr():
+                buf[key][step].copy_(t.detach())
+
+        for step in range(T):
+            gate = None
+            if device_rule:
+                gate, off_dev = ops.ess_gate(ess_inv, B, N, None, rng, device_rng, soft and device_rng and "offsets" not in inj,
+                                             self._gates[step:step + 1])
+                fire = True        # the kernels decide
             else:
-                fire = bool(self.force_resample)
-            self.fired.append(fire)
+                off_dev = None
+                if self.force_resample is None:
+                    fire = bool(ess_inv.mean() < 0.5 * N)          # whole-batch ESS gate, DPFs.py:163-165 (one D2H sync)
+                else:
+                    fire = bool(self.force_resample)
+                    if device_rng:                                  # keep the step counter of the device RNG moving
+                        _, off_dev = ops.ess_gate(None, B, N, fire, rng, True, soft and fire and "offsets" not in inj)
+                self._fired_host.append(fire)
             if fire and soft:   # one kernel: scan + search + gather + renormalise (+ log of the new weights, DPFs.py:167)
-                off = inj["offsets"][:, step] if inj is not None and "offsets" in inj else None
-                if off is None and self.rng_device == "cuda":
-                    off = torch.rand(B, device=particles.device) / N
-                particles, probs_res, index_p, logw_prev = self.resampler.resampling(particles, particle_probs, random_offset=off,
-                                                                                     want_log=True, **self.resampler.kargs)
+                off = inj["offsets"][:, step] if "offsets" in inj else off_dev
+                particles, probs_res, index_p, logw_prev = self.resampler.resampling(
+                    particles, particle_probs, random_offset=off, want_log=True, gate=gate, out={"index": buf["index"][step]},
+                    **self.resampler.kargs)
             elif fire:
-                particles, probs_res, index_p = self.resampler(particles, particle_probs)
-                logw_prev = probs_res.log()
+                k = self.resampler.kargs
+                particles = ops.ot_resample(particles, particle_probs.log(), k["eps"], k["scaling"], k["threshold"], k["max_iter"], gate)
+                if gate is not None:
+                    probs_res, logw_prev = ops.gate_weights(particle_probs, gate)
+                else:
+                    probs_res = torch.full_like(particle_probs, 1.0 / N)
+                    logw_prev = probs_res.log()
             else:
                 logw_prev = particle_probs.log()
-            noise = inj["noise"][:, step] if inj is not None and "noise" in inj else None
+                if soft:
+                    if identity_idx is None:
+                        identity_idx = torch.arange(B * N, device=dev, dtype=torch.int64).reshape(B, N)
+                    buf["index"][step].copy_(identity_idx)
+            noise = inj["noise"][:, step] if "noise" in inj else None
             encodings = self.encoder(obs[:, step].float())
             if fused:
                 # ---- fused step: 6 libnfdpf launches (motion+moments, 3 coupling stacks, densities, measurement+update)
-                if noise is None and self.rng_device == "cuda":
-                    noise = torch.randn(B, N, 2, device=particles.device) * self.pos_noise
-                elif noise is None:
-                    noise = torch.normal(mean=0.0, std=self.pos_noise, size=(B, N, 2)).to(particles.device, non_blocking=True)
-                ctx_phys = torch.empty(B, 4, dtype=torch.float32, device=particles.device) if self.NF else None
-                particles_physical = ops.motion_moments(particles, vel, noise, ctx_phys, 0)
+                if noise is None and not device_rng:
+                    noise = torch.normal(mean=0.0, std=self.pos_noise, size=(B, N, 2)).to(dev, non_blocking=True)
+                    put("noise", step, noise)
+                ctx_phys = torch.empty(B, 4, **f32) if self.NF else None
+                plain = not self.NF and not self.NFcond             # the moved cloud itself is the step's particle set
+                o = {"noise": buf["noise"][step]} if noise is None else {}
+                if plain:
+                    o["moved"] = buf["particles"][step]
+                particles_physical, noise = ops.motion_moments(particles, vel, noise, ctx_phys, 0, rng, self.pos_noise, o)
                 vel = vel_input[:, step, :]
                 if self.NF:
-                    particles_dynamical, jac = self.nf_dyn.run_stack(particles_physical, row_ctx=ctx_phys, inverse=True, neg_logdet=True)
+                    o = {"log_det": buf["jac"][step]}
+                    if not self.NFcond:
+                        o["y"] = buf["particles"][step]
+                    particles_dynamical, jac = self.nf_dyn.run_stack(particles_physical, row_ctx=ctx_phys, inverse=True, neg_logdet=True, out=o)
                 else:
                     particles_dynamical, jac = particles_physical, None
+                mo = {"lki": buf["lki"][step], "probs": buf["probs"][step]}
                 if self.NFcond:
-                    ctx_prop = torch.empty(B, self.hidden_size + 4, dtype=torch.float32, device=particles.device)
+                    ctx_prop = torch.empty(B, self.hidden_size + 4, **f32)
                     ctx_prop[:, :self.hidden_size] = encodings.detach()      # proposal sees a detached encoding, models.py:360-361
                     ops.row_moments(particles_dynamical, ctx_prop, self.hidden_size)
-                    propose_particle, jac_prop = self.cond_model.run_stack(particles_dynamical, row_ctx=ctx_prop, inverse=True, neg_logdet=True)
+                    propose_particle, jac_prop = self.cond_model.run_stack(particles_dynamical, row_ctx=ctx_prop, inverse=True, neg_logdet=True,
+                                                                           out={"y": buf["particles"][step]})
                     if self.NF:   # push the proposal back through the dynamics flow (context: moments of the physical cloud)
                         back, jac_back = self.nf_dyn.run_stack(propose_particle, row_ctx=ctx_phys, inverse=False, neg_logdet=True)
                     else:
                         back, jac_back = propose_particle, None
-                    prior_log, propose_log = ops.proposal_terms(back, particles_physical, noise, jac_back, jac, jac_prop, self.pos_noise)
+                    prior_log, propose_log = ops.proposal_terms(back, particles_physical, noise, jac_back, jac, jac_prop, self.pos_noise,
+                                                                {"prior": buf["prior"][step]} if self.NF else None)
                     lki_log, logw, particle_probs, row_sum, ess_inv = self.measurement_model.forward_update(
-                        encodings, propose_particle, logw_prev, prior_log, propose_log)
+                        encodings, propose_particle, logw_prev, prior_log, propose_log, out=mo)
                 else:             # prior == proposal density: the two cancel exactly in DPFs.py:187
                     propose_particle = particles_dynamical
                     if self.NF:
-                        _, prior_log = ops.proposal_terms(particles_physical, particles_physical, noise, None, jac, None, self.pos_noise)
+                        _, prior_log = ops.proposal_terms(particles_physical, particles_physical, noise, None, jac, None, self.pos_noise,
+                                                          {"propose": buf["prior"][step]})
                     lki_log, logw, particle_probs, row_sum, ess_inv = self.measurement_model.forward_update(
-                        encodings, propose_particle, logw_prev, None, None)
-                if jac is None:
-                    jac = torch.zeros(B, N, device=particles.device)
-                obs_likelihood = obs_likelihood + row_sum.sum() / (B * N)
+                        encodings, propose_particle, logw_prev, None, None, out=mo)
             else:
                 particles_physical, noise = self.motion_update(particles, vel, pos_noise=self.pos_noise, noise=noise)
+                if "noise" in buf:
+                    put("noise", step, noise)
                 vel = vel_input[:, step, :]
                 particles_dynamical, jac = nf_dynamic_model(self.nf_dyn, particles_physical, particle_probs.shape, NF=self.NF)
                 propose_particle, lki_log, prior_log, propose_log = proposal_likelihood(
                     self.cond_model, self.nf_dyn, self.measurement_model, particles_dynamical, particles_physical, encodings, noise, jac,
                     self.NF, self.NFcond, prototype_density=self.prototype_density)
-                logw, particle_probs, row_sum, ess_inv = _weight_update(logw_prev, lki_log, prior_log, propose_log)
-                obs_likelihood = obs_likelihood + row_sum.sum() / (B * N)
+                logw, particle_probs, row_sum, ess_inv = _weight_update(logw_prev, lki_log, prior_log, propose_log,
+                                                                        out={"probs": buf["probs"][step]})
+                put("lki", step, lki_log)
+                if self.NF:
+                    put("jac", step, jac)
+                    put("prior", step, prior_log)
             particles = propose_particle
-            for k, v in (("particles", particles), ("probs", particle_probs), ("noise", noise), ("lki", lki_log), ("index", index_p)):
-                lists[k].append(v)
+            put("particles", step, particles)
+            row_sums.append(row_sum)
+            pred = ops.weighted_mean(particles, particle_probs, {"pred": buf["pred"][step]})
+            for k, v in (("particles", particles), ("probs", particle_probs), ("lki", lki_log), ("pred", pred)):
+                steps[k].append(v)
             if self.NF:
-                lists["jac"].append(jac)
-                lists["prior"].append(prior_log)
-        stack = lambda k: torch.stack(lists[k], dim=1)
-        return (stack("particles"), stack("probs"), stack("noise"), stack("lki"), init_weights_log, stack("index"),
-                stack("jac") if self.NF else None, stack("prior") if self.NF else None, obs_likelihood)
+                steps["jac"].append(jac)
+                steps["prior"].append(prior_log)
+        obs_likelihood = torch.stack(row_sums).sum() / (B * N)            # sum_t mean_{b,n} logw, DPFs.py:191
+        view = lambda k: ops.list_view(buf[k], steps[k])
+        particle_list, weight_list = view("particles"), view("probs")
+        # the fused per-step predictions ride along: losses.supervised_loss(particle_list, weight_list, ...) picks them up instead
+        # of multiplying and reducing the (B,T,N,2) lists again
+        particle_list._nfdpf_pred = (view("pred"), weight_list)
+        noise_list = inj["noise"] if "noise" in inj else buf["noise"].transpose(0, 1)
+        if soft:
+            index_list = buf["index"].transpose(0, 1)
+        else:   # OT resampling keeps every particle in place: identity ancestors at every step (resamplers.py:68-70), as a view
+            index_list = torch.arange(B * N, device=dev, dtype=torch.int64).reshape(B, 1, N).expand(B, T, N)
+        return (particle_list, weight_list, noise_list, view("lki"), init_weights_log, index_list,
+                view("jac") if self.NF else None, view("prior") if self.NF else None, obs_likelihood)
 
     def get_mask(self):
         n1 = int(self.batch_size * self.seq_len * self.labeledRatio)
@@ -303,9 +408,9 @@ def _weight_norm(logw):
     return ops.weight_update(logw)
 
 
-def _weight_update(logw_prev, lki, prior, propose):
+def _weight_update(logw_prev, lki, prior, propose, out=None):
     from . import ops
-    return ops.weight_update(logw_prev, lki, prior, propose, 1e-12)
+    return ops.weight_update(logw_prev, lki, prior, propose, 1e-12, out)
 
 
 def _dump(path, out, **extra):

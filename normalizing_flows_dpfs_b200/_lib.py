@@ -15,8 +15,8 @@ SIGNATURES = {
     "nfdpf_version": (_I, []),
     "nfdpf_last_error": (C.c_char_p, []),
     "nfdpf_launch_count": (_I64, []),
-    "nfdpf_soft_resample_fwd": (_I, [_P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
-    "nfdpf_soft_resample_bwd": (_I, [_P, _P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P, _P]),
+    "nfdpf_soft_resample_fwd": (_I, [_P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "nfdpf_soft_resample_bwd": (_I, [_P, _P, _P, _P, _P, _D, _I, _I, _I, _P, _P, _P, _P, _P]),
     "nfdpf_motion_moments": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P]),
     "nfdpf_proposal_terms_fwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _I64, _P, _P, _P]),
     "nfdpf_proposal_terms_bwd": (_I, [_P, _P, _P, _P, _F, _I64, _P, _P, _P, _P]),
@@ -24,8 +24,15 @@ SIGNATURES = {
     "nfdpf_weight_update_bwd": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P]),
     "nfdpf_row_moments": (_I, [_P, _I, _I, _I, _P, _I, _I, _P]),
     "nfdpf_ot_workspace": (_I64, [_I, _I]),
-    "nfdpf_ot_resample_fwd": (_I, [_P, _P, _F, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "nfdpf_ot_resample_bwd": (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
+    "nfdpf_ot_resample_fwd": (_I, [_P, _P, _F, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "nfdpf_ot_resample_bwd": (_I, [_P, _P, _F, _I, _I, _I, _P, _P, _P]),
+    "nfdpf_gate_weights_fwd": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "nfdpf_gate_weights_bwd": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "nfdpf_ess_gate": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "nfdpf_motion_moments_rng": (_I, [_P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
+    "nfdpf_init_particles_rng": (_I, [_P, _I, _P, _F, _I, _I, _I, _I, _P, _P]),
+    "nfdpf_weighted_mean_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "nfdpf_weighted_mean_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "nfdpf_peak_probe": (_I64, [_I, _I, _P, _P]),
     "nfdpf_coupling_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "nfdpf_coupling_bwd_workspace": (_I64, [_I, _I, _I, _I, _I, _I]),
@@ -57,6 +64,9 @@ def ptr(t):
     if t is None:
         return None
     assert t.is_cuda and t.is_contiguous(), "libnfdpf needs contiguous CUDA tensors"
+    if t.device.index != torch.cuda.current_device():   # launches go to the current device: a foreign pointer would fault there
+        raise RuntimeError("libnfdpf: tensor lives on cuda:%d but the current device is cuda:%d (use torch.cuda.device(...))"
+                           % (t.device.index, torch.cuda.current_device()))
     return t.data_ptr()
 
 

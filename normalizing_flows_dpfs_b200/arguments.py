@@ -59,6 +59,9 @@ _FLAGS = [
     (("--learn_top",), dict(type=bool, default=False)),
     (("--x_bins",), dict(type=float, default=256.0)),
     (("--y_bins",), dict(type=float, default=256.0)),
+    # extension (not in the reference): host-free filter loop -- device-side ESS gate and in-kernel Philox draws instead of the
+    # CPU generator (statistically equivalent, not the reference's random stream)
+    (("--fast",), dict(action="store_true", default=False)),
 ]
 
 

@@ -27,9 +27,13 @@ __device__ __forceinline__ float lg2f(float x) { float r; asm("lg2.approx.ftz.f3
 // ---- prepare: centre / scale the cloud, epsilon_0 (resamplers.py:72-76, 87-91, 117, 218-222) ----------------
 __global__ void __launch_bounds__(256)
 ot_prepare_kernel(const float* __restrict__ x, int N, float2* __restrict__ sx, float* __restrict__ eps_run,
-                  unsigned* __restrict__ diff, OtCtrl* __restrict__ ctrl, int max_iter) {
+                  unsigned* __restrict__ diff, OtCtrl* __restrict__ ctrl, int max_iter, const int* __restrict__ gate) {
     __shared__ float s_red[33];
     const int b = blockIdx.x, tid = threadIdx.x;
+    if (gate && *gate == 0) {            // device-side ESS gate closed: disarm the whole Sinkhorn chain
+        if (b == 0 && tid == 0) { ctrl->iter = 0; ctrl->go = 0; ctrl->ticket = 0u; ctrl->pad = 1; }
+        return;
+    }
     const float2* xr = reinterpret_cast<const float2*>(x) + (size_t)b * N;
     float sx0 = 0.f, sy0 = 0.f;
     for (int n = tid; n < N; n += 256) { const float2 v = xr[n]; sx0 += v.x; sy0 += v.y; }
@@ -56,7 +60,7 @@ ot_prepare_kernel(const float* __restrict__ x, int N, float2* __restrict__ sx, f
     if (tid == 0) {
         eps_run[b] = (hi - lo) * (hi - lo);
         diff[b] = 0u;
-        if (b == 0) { ctrl->iter = 0; ctrl->go = max_iter - 1 > 0 ? 1 : 0; ctrl->ticket = 0u; }
+        if (b == 0) { ctrl->iter = 0; ctrl->go = max_iter - 1 > 0 ? 1 : 0; ctrl->ticket = 0u; ctrl->pad = 0; }
     }
 }
 
@@ -75,6 +79,7 @@ ot_pass_kernel(const float2* __restrict__ sx, const float* __restrict__ logw, co
     __shared__ int s_last;
     const int b = blockIdx.y, tid = threadIdx.x, i = blockIdx.x * OT_T + tid;
     int cur = 0;
+    if (ctrl->pad) return;               // resampling gated off for this step (ot_prepare_kernel)
     if (MODE == 1) {
         if (!ctrl->go) return;           // the batch-wide stop rule fired in an earlier launch
         cur = ctrl->iter & 1;
@@ -187,8 +192,9 @@ ot_pass_kernel(const float2* __restrict__ sx, const float* __restrict__ logw, co
 // so that T_ij = 2^(F_i + U_j - c2 |x_i - x_j|^2).
 __global__ void __launch_bounds__(OT_T)
 ot_colnorm_kernel(const float2* __restrict__ sx, const float* __restrict__ logw, const float* __restrict__ f,
-                  const float* __restrict__ g, int N, float eps_target, float4* __restrict__ saved) {
+                  const float* __restrict__ g, int N, float eps_target, float4* __restrict__ saved, const int* __restrict__ gate) {
     __shared__ float4 s_j[OT_J];
+    if (gate && *gate == 0) return;
     const int b = blockIdx.y, tid = threadIdx.x, jcol = blockIdx.x * OT_T + tid;
     const size_t row = (size_t)b * N;
     const float inv = 1.0f / eps_target, c2 = 0.5f * LOG2E * inv;
@@ -232,11 +238,16 @@ ot_colnorm_kernel(const float2* __restrict__ sx, const float* __restrict__ logw,
 // ---- apply the plan: out_i = sum_j T_ij v_j (forward: v = particles) or out_j = sum_i T_ij v_i (backward: v = grad) ----
 template <bool TRANSPOSED>
 __global__ void __launch_bounds__(OT_T)
-ot_apply_kernel(const float4* __restrict__ saved, const float* __restrict__ v, int N, float eps_target, float* __restrict__ out) {
+ot_apply_kernel(const float4* __restrict__ saved, const float* __restrict__ v, int N, float eps_target, float* __restrict__ out,
+                const int* __restrict__ gate) {
     __shared__ float4 s_p[OT_J];
     __shared__ float2 s_v[OT_J];
     const int b = blockIdx.y, tid = threadIdx.x, me = blockIdx.x * OT_T + tid;
     const size_t row = (size_t)b * N;
+    if (gate && *gate == 0) {            // resampling gated off: the plan is the identity (forward and transposed)
+        if (me < N) reinterpret_cast<float2*>(out)[row + me] = reinterpret_cast<const float2*>(v)[row + me];
+        return;
+    }
     const float c2 = 0.5f * LOG2E / eps_target;
     const bool live = me < N;
     const float4 mine = saved[row + (live ? me : 0)];
@@ -295,7 +306,7 @@ extern "C" int64_t nfdpf_ot_workspace(int B, int N) { return B > 0 && N > 0 ? (i
 
 extern "C" int nfdpf_ot_resample_fwd(const float* particles, const float* logw, float eps, float scaling, float threshold,
                                      int max_iter, int B, int N, int d, float* particles_out, float* saved, int32_t* iters_out,
-                                     void* workspace, void* stream) {
+                                     void* workspace, const int32_t* gate, void* stream) {
     NFDPF_REQUIRE(particles && logw && particles_out && saved && workspace, "ot_resample_fwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0, "ot_resample_fwd: B and N must be positive");
     NFDPF_REQUIRE(eps > 0.f && scaling > 0.f && scaling < 1.f && max_iter >= 1, "ot_resample_fwd: need eps > 0, 0 < scaling < 1, max_iter >= 1");
@@ -305,7 +316,7 @@ extern "C" int nfdpf_ot_resample_fwd(const float* particles, const float* logw, 
     OtWs w(workspace, B, N);
     const dim3 grid((N + OT_T - 1) / OT_T, B);
     const float s2 = scaling * scaling;
-    ot_prepare_kernel<<<B, 256, 0, st>>>(particles, N, w.sx, w.eps_run, w.diff, w.ctrl, max_iter);
+    ot_prepare_kernel<<<B, 256, 0, st>>>(particles, N, w.sx, w.eps_run, w.diff, w.ctrl, max_iter, gate);
     int rc = check_launch("ot_prepare");
     if (rc) return rc;
     ot_pass_kernel<0><<<grid, OT_T, 0, st>>>(w.sx, logw, w.a, w.b, w.a, w.b, N, w.eps_run, w.eps_run, w.diff, w.ctrl, eps, s2, threshold,
@@ -319,9 +330,9 @@ extern "C" int nfdpf_ot_resample_fwd(const float* particles, const float* logw, 
     ot_pass_kernel<2><<<grid, OT_T, 0, st>>>(w.sx, logw, w.a, w.b, w.f, w.g, N, w.eps_run, w.eps_run, w.diff, w.ctrl, eps, s2, threshold,
                                              max_iter, B);
     if ((rc = check_launch("ot_final"))) return rc;
-    ot_colnorm_kernel<<<grid, OT_T, 0, st>>>(w.sx, logw, w.f, w.g, N, eps, (float4*)saved);
+    ot_colnorm_kernel<<<grid, OT_T, 0, st>>>(w.sx, logw, w.f, w.g, N, eps, (float4*)saved, gate);
     if ((rc = check_launch("ot_colnorm"))) return rc;
-    ot_apply_kernel<false><<<grid, OT_T, 0, st>>>((const float4*)saved, particles, N, eps, particles_out);
+    ot_apply_kernel<false><<<grid, OT_T, 0, st>>>((const float4*)saved, particles, N, eps, particles_out, gate);
     if ((rc = check_launch("ot_apply"))) return rc;
     if (iters_out) {
         ot_iters_kernel<<<1, 1, 0, st>>>(w.ctrl, iters_out);
@@ -331,11 +342,11 @@ extern "C" int nfdpf_ot_resample_fwd(const float* particles, const float* logw, 
 }
 
 extern "C" int nfdpf_ot_resample_bwd(const float* g_out, const float* saved, float eps, int B, int N, int d, float* d_particles,
-                                     void* stream) {
+                                     const int32_t* gate, void* stream) {
     NFDPF_REQUIRE(g_out && saved && d_particles, "ot_resample_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && eps > 0.f, "ot_resample_bwd: bad sizes");
     if (d != 2) { set_error("ot_resample_bwd: kernels are built for state_dim 2, got %d", d); return NFDPF_ERR_UNSUPPORTED; }
     const dim3 grid((N + OT_T - 1) / OT_T, B);
-    ot_apply_kernel<true><<<grid, OT_T, 0, (cudaStream_t)stream>>>((const float4*)saved, g_out, N, eps, d_particles);
+    ot_apply_kernel<true><<<grid, OT_T, 0, (cudaStream_t)stream>>>((const float4*)saved, g_out, N, eps, d_particles, gate);
     return check_launch("ot_apply_T");
 }

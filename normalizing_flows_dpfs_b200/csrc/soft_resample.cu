@@ -85,8 +85,21 @@ soft_resample_fwd_kernel(const float* __restrict__ particles, const float* __res
                          const float* __restrict__ offsets, const float* __restrict__ markers, float alpha_f,
                          float one_minus_alpha_f, int hard, int N, int d, float* __restrict__ particles_out,
                          float* __restrict__ probs_out, int64_t* __restrict__ idx_out, float* __restrict__ saved,
-                         float* __restrict__ logprobs_out) {
+                         float* __restrict__ logprobs_out, const int* __restrict__ gate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (gate && *gate == 0) {   // device-side ESS gate closed (DPFs.py:168-170): particles / weights pass through, identity ancestors
+        const int b = blockIdx.x;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const size_t o = (size_t)b * N + i;
+            for (int k = 0; k < d; ++k) particles_out[o * d + k] = particles[o * d + k];
+            const float w = probs[o];
+            probs_out[o] = w;
+            idx_out[o] = (int64_t)o;
+            if (logprobs_out) logprobs_out[o] = logf(w);
+        }
+        if (threadIdx.x == 0) { saved[2 * b] = 1.f; saved[2 * b + 1] = 1.f; }
+        return;
+    }
     float* s_q = reinterpret_cast<float*>(smem_raw);  // q -> normalised q -> cum
     float* s_wis = s_q + N;                           // importance weights w / q
     __shared__ double s_warp[32];
@@ -128,7 +141,7 @@ soft_resample_fwd_kernel(const float* __restrict__ particles, const float* __res
             const int mid = (lo + hi) >> 1;
             if (s_q[mid] < m) lo = mid + 1; else hi = mid;
         }
-        const int j = lo + (m > 1.0f ? 1 : 0);                     // forced last entry; never true for m <= 1
+        const int j = min(lo + (m > 1.0f ? 1 : 0), N - 1);         // forced last entry (markers beyond 1 only with out-of-range offsets)
         idx_out[(size_t)b * N + i] = (int64_t)j + (int64_t)N * b;  // :52
         const float* src = particles + ((size_t)b * N + j) * d;
         float* dst = particles_out + ((size_t)b * N + i) * d;
@@ -160,8 +173,20 @@ __global__ void __launch_bounds__(1024)
 soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __restrict__ g_probs,
                          const float* __restrict__ probs, const int64_t* __restrict__ idx,
                          const float* __restrict__ saved, float alpha_f, float one_minus_alpha_f, int hard, int N, int d,
-                         float* __restrict__ d_particles, float* __restrict__ d_probs, const float* __restrict__ g_logprobs) {
+                         float* __restrict__ d_particles, float* __restrict__ d_probs, const float* __restrict__ g_logprobs,
+                         const int* __restrict__ gate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (gate && *gate == 0) {   // the forward passed everything through: so do the gradients (+ d log w = g / w)
+        const int b = blockIdx.x;
+        for (int i = threadIdx.x; i < N; i += blockDim.x) {
+            const size_t o = (size_t)b * N + i;
+            for (int k = 0; k < d; ++k) d_particles[o * d + k] = g_particles ? g_particles[o * d + k] : 0.f;
+            float g = g_probs ? g_probs[o] : 0.f;
+            if (g_logprobs) g += g_logprobs[o] / probs[o];
+            d_probs[o] = g;
+        }
+        return;
+    }
     int* s_idx = reinterpret_cast<int*>(smem_raw);                    // [N] local source index per destination
     float4* s_a = reinterpret_cast<float4*>(s_idx + ((N + 3) & ~3));  // [N] (dL/dv, g_x, g_y, -), scanned in place
     __shared__ float s_red[33];
@@ -291,24 +316,28 @@ using namespace nfdpf;
 
 extern "C" int nfdpf_soft_resample_fwd(const float* particles, const float* probs, const float* offsets,
                                        const float* markers, double alpha, int B, int N, int d, float* particles_out,
-                                       float* probs_out, int64_t* idx_out, float* saved, float* logprobs_out, void* stream) {
+                                       float* probs_out, int64_t* idx_out, float* saved, float* logprobs_out, const int32_t* gate,
+                                       void* stream) {
     NFDPF_REQUIRE(particles && probs && offsets && markers && particles_out && probs_out && idx_out && saved,
                   "soft_resample_fwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_fwd: B, N, d must be positive (got %d, %d, %d)", B, N, d);
     NFDPF_REQUIRE(alpha > 0.0 && alpha <= 1.0, "soft_resample_fwd: need 0 < alpha <= 1 (resamplers.py:21), got %g", alpha);
     const size_t smem = (size_t)N * 2 * sizeof(float);
-    if (smem > 200 * 1024) { set_error("soft_resample_fwd: N=%d exceeds the shared-memory row limit (25600)", N); return NFDPF_ERR_UNSUPPORTED; }
+    // the backward keeps 20 B per particle in shared memory: accept only what it can also handle (no forward-only sizes)
+    if ((size_t)((N + 3) & ~3) * sizeof(int) + (size_t)N * sizeof(float4) > 200 * 1024) {
+        set_error("soft_resample_fwd: N=%d exceeds the shared-memory row limit (10200)", N); return NFDPF_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024)
         NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     soft_resample_fwd_kernel<<<B, pick_threads(N), smem, (cudaStream_t)stream>>>(
         particles, probs, offsets, markers, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, d, particles_out,
-        probs_out, idx_out, saved, logprobs_out);
+        probs_out, idx_out, saved, logprobs_out, gate);
     return check_launch("soft_resample_fwd");
 }
 
 extern "C" int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_probs, const float* probs,
                                        const int64_t* idx, const float* saved, double alpha, int B, int N, int d,
-                                       float* d_particles, float* d_probs, const float* g_logprobs, void* stream) {
+                                       float* d_particles, float* d_probs, const float* g_logprobs, const int32_t* gate,
+                                       void* stream) {
     NFDPF_REQUIRE(probs && idx && saved && d_particles && d_probs, "soft_resample_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_bwd: B, N, d must be positive");
     NFDPF_REQUIRE(alpha > 0.0 && alpha <= 1.0, "soft_resample_bwd: need 0 < alpha <= 1, got %g", alpha);
@@ -318,6 +347,6 @@ extern "C" int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_
         NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     soft_resample_bwd_kernel<<<B, pick_threads(N), smem, (cudaStream_t)stream>>>(
         g_particles, g_probs, probs, idx, saved, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, d, d_particles,
-        d_probs, g_logprobs);
+        d_probs, g_logprobs, gate);
     return check_launch("soft_resample_bwd");
 }

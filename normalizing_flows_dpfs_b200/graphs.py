@@ -3,9 +3,10 @@
 The per-timestep update is a chain of ~15 short libnfdpf launches (forward) plus as many in backward; at
 B = N = 1024 each runs 20-400 us, so Python/ctypes/autograd dispatch (~40 us per launch) is comparable to the GPU
 time of the forward pass.  Capturing the step once and replaying it removes the host from the loop: one
-cudaGraphLaunch per training step.  Requirements (checked): the ESS gate must not need the host
-(`force_resample` set), and random draws must be injected or generated on the device.  Drop every reference to the
-outputs / loss of earlier eager steps before capturing (they keep autograd nodes bound to the default stream)."""
+cudaGraphLaunch per training step.  Requirement (checked): random draws must be injected or generated on the device
+(`dpf.rng_device = "cuda"`); the reference's ESS gate is then evaluated on the device (DPF.filtering_pos), so the REAL gate
+is captured -- `force_resample` is not needed.  Drop every reference to the outputs / loss of earlier eager steps before
+capturing (they keep autograd nodes bound to the default stream)."""
 import torch
 from torch.nn.utils.stateless import _reparametrize_module
 
@@ -24,8 +25,9 @@ class GraphedFilterStep:
         self.KEYS = tuple(k for k in self.KEYS if k in batch)   # noise / offsets may be left to the device RNG
         if ("noise" not in batch or "offsets" not in batch) and dpf.rng_device != "cuda":
             raise ValueError("graph capture without injected noise / offsets needs dpf.rng_device = 'cuda'")
-        if dpf.force_resample is None:
-            raise ValueError("graph capture needs a host-free ESS gate: set dpf.force_resample to True or False")
+        soft = dpf.param.resampler_type == "soft"
+        if dpf.force_resample is None and soft and dpf.rng_device != "cuda" and "offsets" not in batch:
+            raise ValueError("graph capture needs a host-free ESS gate: inject the resampling offsets or set dpf.rng_device = 'cuda'")
         self.dpf = dpf
         self.static = {k: batch[k].clone() for k in self.KEYS}
         for m in dpf.modules():   # packed-parameter caches pin autograd state of the stream they were built on

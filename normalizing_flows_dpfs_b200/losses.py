@@ -14,8 +14,14 @@ def autoencoder_loss(image, train, encoder, decoder):
 
 
 def supervised_loss(particle_list, particle_weight_list, true_state, mask, train, labeledRatio=1.0):
-    """RMSE between the weighted particle mean and the true position (reference losses.py:18-31)."""
-    prediction = (particle_list * particle_weight_list[..., None]).sum(dim=2)
+    """RMSE between the weighted particle mean and the true position (reference losses.py:18-31).  Lists that come straight from
+    DPF.filtering_pos carry the per-step predictions a fused kernel already formed (sum_n w_n x_n, with backward): they are used
+    instead of multiplying and reducing the (B,T,N,2) lists again."""
+    fusedp = getattr(particle_list, "_nfdpf_pred", None)
+    if fusedp is not None and fusedp[1] is particle_weight_list:
+        prediction = fusedp[0]
+    else:
+        prediction = (particle_list * particle_weight_list[..., None]).sum(dim=2)
     err2 = (prediction - true_state[:, :, :2]) ** 2
     if not train:
         return torch.sqrt(err2.mean()), prediction

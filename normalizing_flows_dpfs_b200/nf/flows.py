@@ -36,7 +36,7 @@ class _PackCache:
         # the packed tensor carries an autograd node bound to the stream it was built on: never reuse it across
         # streams (CUDA-graph capture runs on a side stream)
         stream = torch.cuda.current_stream().cuda_stream if params and params[0].is_cuda else 0
-        key = (torch.is_grad_enabled(), stream) + tuple((p.data_ptr(), p._version) for p in params)
+        key = (torch.is_grad_enabled(), stream) + tuple((p.data_ptr(), p._version, p.requires_grad) for p in params)
         if key != self.key:
             # drop the old packed tensor FIRST: its cat node keeps the parameters' AccumulateGrad nodes alive, and those
             # are bound to the stream they were first used on (a legacy-stream accumulator breaks graph capture)

@@ -24,9 +24,9 @@ class _FlowChain(nn.Module):
     def packed(self):
         return self._cache.get(list(self.flows))
 
-    def run_stack(self, x, row_ctx=None, part_ctx=None, inverse=False, neg_logdet=False):
+    def run_stack(self, x, row_ctx=None, part_ctx=None, inverse=False, neg_logdet=False, out=None):
         """(B,N,D) entry point used by the filter: row-constant context stays (B,C) and is hoisted in-kernel."""
-        return ops.coupling_stack(self.packed(), x, row_ctx, part_ctx, len(self.flows), inverse, neg_logdet)
+        return ops.coupling_stack(self.packed(), x, row_ctx, part_ctx, len(self.flows), inverse, neg_logdet, out)
 
     def _chain(self, x, obser, inverse):
         P, D = x.shape

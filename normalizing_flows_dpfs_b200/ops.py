@@ -5,6 +5,19 @@ import torch
 from . import _lib as L
 
 
+def _out(out, key, like=None, shape=None, dtype=torch.float32, device=None):
+    """Output tensor of a kernel: the caller's pre-allocated slice `out[key]` (the per-step (T,B,...) list buffers of the filter
+    loop: no torch.stack afterwards) or a fresh allocation.  `out` is a plain dict, invisible to autograd; the kernels write
+    through raw pointers, so returning such a view from a Function is legal."""
+    if out is not None and key in out:
+        t = out[key]
+        assert t.is_contiguous() and t.dtype == dtype, "pre-allocated output %r must be contiguous %s" % (key, dtype)
+        return t
+    if like is not None:
+        return torch.empty_like(like)
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
 def _stack_dims(packed, D, C, n_flows):
     half = D // 2
     per = 8 * (half + C) + 8 + 64 + 8 + half * 8 + half
@@ -14,28 +27,29 @@ def _stack_dims(packed, D, C, n_flows):
 
 
 class SoftResample(torch.autograd.Function):
-    """soft_resampler, resamplers/resamplers.py:20-60 (+ the log of the new weights, DPFs.py:167, when want_log)."""
+    """soft_resampler, resamplers/resamplers.py:20-60 (+ the log of the new weights, DPFs.py:167, when want_log).
+    gate: device int32 tensor or None -- the ESS decision taken on the device (ess_gate); closed gate = pass-through."""
 
     @staticmethod
-    def forward(ctx, particles, probs, offsets, markers, alpha, want_log):
+    def forward(ctx, particles, probs, offsets, markers, alpha, want_log, gate=None, out=None):
         B, N, d = particles.shape
         p, w = L.f32(particles), L.f32(probs)
         off, mk = L.f32(offsets), L.f32(markers)
         p_out = torch.empty_like(p)
         w_out = torch.empty_like(w)
         lw_out = torch.empty_like(w) if want_log else None
-        idx = torch.empty(B, N, dtype=torch.int64, device=p.device)
+        idx = _out(out, "index", shape=(B, N), dtype=torch.int64, device=p.device)
         saved = torch.empty(B, 2, dtype=torch.float32, device=p.device)
         L.call("nfdpf_soft_resample_fwd", L.ptr(p), L.ptr(w), L.ptr(off), L.ptr(mk), float(alpha), B, N, d, L.ptr(p_out),
-               L.ptr(w_out), L.ptr(idx), L.ptr(saved), L.ptr(lw_out), L.stream())
-        ctx.save_for_backward(w, idx, saved)
+               L.ptr(w_out), L.ptr(idx), L.ptr(saved), L.ptr(lw_out), L.ptr(gate), L.stream())
+        ctx.save_for_backward(w, idx, saved, gate)
         ctx.alpha, ctx.shape = float(alpha), (B, N, d)
         ctx.mark_non_differentiable(idx)
         return p_out, w_out, idx, lw_out
 
     @staticmethod
     def backward(ctx, g_p, g_w, _g_idx, g_lw):
-        w, idx, saved = ctx.saved_tensors
+        w, idx, saved, gate = ctx.saved_tensors
         B, N, d = ctx.shape
         g_p = L.f32(g_p) if g_p is not None else None
         g_w = L.f32(g_w) if g_w is not None else None
@@ -43,20 +57,20 @@ class SoftResample(torch.autograd.Function):
         d_p = torch.empty(B, N, d, dtype=torch.float32, device=w.device)
         d_w = torch.empty(B, N, dtype=torch.float32, device=w.device)
         L.call("nfdpf_soft_resample_bwd", L.ptr(g_p), L.ptr(g_w), L.ptr(w), L.ptr(idx), L.ptr(saved), ctx.alpha, B, N, d,
-               L.ptr(d_p), L.ptr(d_w), L.ptr(g_lw), L.stream())
-        return d_p, d_w, None, None, None, None
+               L.ptr(d_p), L.ptr(d_w), L.ptr(g_lw), L.ptr(gate), L.stream())
+        return d_p, d_w, None, None, None, None, None, None
 
 
 class WeightUpdate(torch.autograd.Function):
     """logw = logw_prev + lki + prior - propose; probs = softmax(logw) + eps; row stats (DPFs.py:187-192)."""
 
     @staticmethod
-    def forward(ctx, logw_prev, lki, prior, propose, add_eps):
+    def forward(ctx, logw_prev, lki, prior, propose, add_eps, out=None):
         B, N = logw_prev.shape
         a = L.f32(logw_prev)
         terms = [L.f32(t) if t is not None else None for t in (lki, prior, propose)]
         logw = torch.empty_like(a)
-        probs = torch.empty_like(a)
+        probs = _out(out, "probs", like=a)
         stats = torch.empty(B, 2, dtype=torch.float32, device=a.device)
         L.call("nfdpf_weight_update_fwd", L.ptr(a), L.ptr(terms[0]), L.ptr(terms[1]), L.ptr(terms[2]), float(add_eps), B, N,
                L.ptr(logw), L.ptr(probs), L.ptr(stats), L.stream())
@@ -77,7 +91,7 @@ class WeightUpdate(torch.autograd.Function):
         d = torch.empty_like(probs)
         L.call("nfdpf_weight_update_bwd", L.ptr(g_probs), L.ptr(g_logw), L.ptr(g_rowsum), L.ptr(probs), ctx.add_eps, B, N,
                L.ptr(d), L.stream())
-        return d, (d if ctx.has[0] else None), (d if ctx.has[1] else None), (-d if ctx.has[2] else None), None
+        return d, (d if ctx.has[0] else None), (d if ctx.has[1] else None), (-d if ctx.has[2] else None), None, None
 
 
 class CouplingStack(torch.autograd.Function):
@@ -86,7 +100,7 @@ class CouplingStack(torch.autograd.Function):
     x (B,N,D); row_ctx (B,C_row) or None; part_ctx (B,N,C_part) or None; packed = flat parameters."""
 
     @staticmethod
-    def forward(ctx, packed, x, row_ctx, part_ctx, n_flows, inverse, neg_logdet=False):
+    def forward(ctx, packed, x, row_ctx, part_ctx, n_flows, inverse, neg_logdet=False, out=None):
         B, N, D = x.shape
         C_row = 0 if row_ctx is None else row_ctx.shape[-1]
         C_part = 0 if part_ctx is None else part_ctx.shape[-1]
@@ -94,8 +108,8 @@ class CouplingStack(torch.autograd.Function):
         pk, xx = L.f32(packed), L.f32(x)
         rc = L.f32(row_ctx) if row_ctx is not None else None
         pc = L.f32(part_ctx) if part_ctx is not None else None
-        y = torch.empty_like(xx)
-        ld = torch.empty(B, N, dtype=torch.float32, device=xx.device)
+        y = _out(out, "y", like=xx)
+        ld = _out(out, "log_det", shape=(B, N), device=xx.device)
         flags = int(bool(inverse)) | (2 if neg_logdet else 0)
         L.call("nfdpf_coupling_fwd", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(xx), L.ptr(rc), L.ptr(pc), flags, B, N,
                L.ptr(y), L.ptr(ld), L.stream())
@@ -119,22 +133,23 @@ class CouplingStack(torch.autograd.Function):
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=y.device)
         L.call("nfdpf_coupling_bwd", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(y), L.ptr(rc), L.ptr(pc), inverse, B, N,
                L.ptr(g_y), L.ptr(g_ld), L.ptr(d_x), L.ptr(d_rc), L.ptr(d_pc), L.ptr(d_pk), L.ptr(ws), L.stream())
-        return d_pk, d_x, d_rc, d_pc, None, None, None
+        return d_pk, d_x, d_rc, d_pc, None, None, None, None
 
 
-def soft_resample(particles, probs, offsets, markers, alpha, want_log=False):
+def soft_resample(particles, probs, offsets, markers, alpha, want_log=False, gate=None, out=None):
     """(particles', probs', flat idx) or, with want_log, (particles', probs', flat idx, log probs')."""
-    out = SoftResample.apply(particles, probs, offsets, markers, alpha, want_log)
-    return out if want_log else out[:3]
+    res = SoftResample.apply(particles, probs, offsets, markers, alpha, want_log, gate, out)
+    return res if want_log else res[:3]
 
 
-def weight_update(logw_prev, lki=None, prior=None, propose=None, add_eps=0.0):
-    return WeightUpdate.apply(logw_prev, lki, prior, propose, add_eps)
+def weight_update(logw_prev, lki=None, prior=None, propose=None, add_eps=0.0, out=None):
+    return WeightUpdate.apply(logw_prev, lki, prior, propose, add_eps, out)
 
 
-def coupling_stack(packed, x, row_ctx=None, part_ctx=None, n_flows=2, inverse=False, neg_logdet=False):
-    """(y, log_det) -- or (y, jac = -log_det) with neg_logdet (model/models.py:325, 350)."""
-    return CouplingStack.apply(packed, x, row_ctx, part_ctx, n_flows, inverse, neg_logdet)
+def coupling_stack(packed, x, row_ctx=None, part_ctx=None, n_flows=2, inverse=False, neg_logdet=False, out=None):
+    """(y, log_det) -- or (y, jac = -log_det) with neg_logdet (model/models.py:325, 350).  out: optional dict with
+    pre-allocated "y" / "log_det" tensors."""
+    return CouplingStack.apply(packed, x, row_ctx, part_ctx, n_flows, inverse, neg_logdet, out)
 
 
 MEASURE_MODES = {"gaussian": 0, "cos": 1, "CRNVP": 2}
@@ -147,7 +162,7 @@ class MeasureUpdate(torch.autograd.Function):
     Returns (lki, logw, probs, row_sum, ess_inv); the last four are None-like zeros-size when not fused."""
 
     @staticmethod
-    def forward(ctx, pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows, p0, p1, add_eps):
+    def forward(ctx, pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows, p0, p1, add_eps, out=None):
         B, N, d = particles.shape
         if d != 2:
             raise ValueError("measurement kernels take 2-d particle states (DPFs.py:31), got d=%d" % d)
@@ -161,10 +176,10 @@ class MeasureUpdate(torch.autograd.Function):
         pr = L.f32(prior) if prior is not None else None
         pp = L.f32(propose) if propose is not None else None
         dev = x_.device
-        lki = torch.empty(B, N, dtype=torch.float32, device=dev)
+        lki = _out(out, "lki", shape=(B, N), device=dev)
         argmax = torch.empty(B, dtype=torch.int32, device=dev)
         logw = torch.empty(B, N, dtype=torch.float32, device=dev) if fused else None
-        probs = torch.empty(B, N, dtype=torch.float32, device=dev) if fused else None
+        probs = _out(out, "probs", shape=(B, N), device=dev) if fused else None
         stats = torch.empty(B, 2, dtype=torch.float32, device=dev) if fused else None
         need_grad = any(ctx.needs_input_grad[:4])
         z = torch.empty(B, N, hidden, dtype=torch.float32, device=dev) if (mode == 2 and need_grad) else None   # flow output, for the backward
@@ -175,8 +190,9 @@ class MeasureUpdate(torch.autograd.Function):
         ctx.meta = (mode, n_flows, float(p0), float(p1), float(add_eps), B, N, hidden, fused, prior is not None, propose is not None)
         if not fused:
             return lki, None, None, None, None
-        ctx.mark_non_differentiable(stats[:, 1])
-        return lki, logw, probs, stats[:, 0], stats[:, 1]
+        row_sum, ess_inv = stats[:, 0], stats[:, 1]
+        ctx.mark_non_differentiable(ess_inv)
+        return lki, logw, probs, row_sum, ess_inv
 
     @staticmethod
     def backward(ctx, g_lki, g_logw, g_probs, g_rowsum, _g_ess):
@@ -201,7 +217,7 @@ class MeasureUpdate(torch.autograd.Function):
         L.call("nfdpf_measure_bwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, p0, p1, L.ptr(enc_), L.ptr(x_), B, N, hidden,
                L.ptr(g_total.contiguous()), L.ptr(argmax), L.ptr(d_x), L.ptr(d_enc), L.ptr(d_pe), L.ptr(d_cnf), L.ptr(ws), L.ptr(z), L.stream())
         return (d_pe, d_cnf, d_enc, d_x, d_logw if fused else None, d_logw if has_prior else None,
-                (-d_logw if d_logw is not None else None) if has_prop else None, None, None, None, None, None)
+                (-d_logw if d_logw is not None else None) if has_prop else None, None, None, None, None, None, None)
 
 
 def measure(pe, cnf, enc, particles, mode, n_flows=2, p0=0.0, p1=1.0):
@@ -209,9 +225,9 @@ def measure(pe, cnf, enc, particles, mode, n_flows=2, p0=0.0, p1=1.0):
     return MeasureUpdate.apply(pe, cnf, enc, particles, None, None, None, MEASURE_MODES[mode], n_flows, p0, p1, 0.0)[0]
 
 
-def measure_update(pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows=2, p0=0.0, p1=1.0, add_eps=1e-12):
+def measure_update(pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows=2, p0=0.0, p1=1.0, add_eps=1e-12, out=None):
     """(lki, logw, probs, row_sum_logw, ess_inv) -- measurement + DPFs.py:187-192 in one kernel."""
-    return MeasureUpdate.apply(pe, cnf, enc, particles, logw_prev, prior, propose, MEASURE_MODES[mode], n_flows, p0, p1, add_eps)
+    return MeasureUpdate.apply(pe, cnf, enc, particles, logw_prev, prior, propose, MEASURE_MODES[mode], n_flows, p0, p1, add_eps, out)
 
 
 def row_moments(x, out=None, out_off=0):
@@ -225,12 +241,13 @@ def row_moments(x, out=None, out_off=0):
 
 
 class OtResample(torch.autograd.Function):
-    """particles' = T particles, T = Sinkhorn plan of (particles, logw) (resamplers.py:62-277); d out/d particles = T."""
+    """particles' = T particles, T = Sinkhorn plan of (particles, logw) (resamplers.py:62-277); d out/d particles = T.
+    gate: device int32 tensor or None (closed gate = identity plan, every Sinkhorn launch exits at once)."""
 
     last_iters = None  # device int32 tensor of the most recent call (the reference's total_iter + 2), for tests / reports
 
     @staticmethod
-    def forward(ctx, particles, logw, eps, scaling, threshold, max_iter):
+    def forward(ctx, particles, logw, eps, scaling, threshold, max_iter, gate=None):
         B, N, d = particles.shape
         x, lw = L.f32(particles), L.f32(logw)
         out = torch.empty_like(x)
@@ -238,53 +255,128 @@ class OtResample(torch.autograd.Function):
         iters = torch.zeros(1, dtype=torch.int32, device=x.device)
         ws = torch.empty(L.load().nfdpf_ot_workspace(B, N) // 4 + 1, dtype=torch.float32, device=x.device)
         L.call("nfdpf_ot_resample_fwd", L.ptr(x), L.ptr(lw), float(eps), float(scaling), float(threshold), int(max_iter), B, N, d,
-               L.ptr(out), L.ptr(saved), L.ptr(iters), L.ptr(ws), L.stream())
+               L.ptr(out), L.ptr(saved), L.ptr(iters), L.ptr(ws), L.ptr(gate), L.stream())
         OtResample.last_iters = iters
-        ctx.save_for_backward(saved)
+        ctx.save_for_backward(saved, gate)
         ctx.meta = (float(eps), B, N, d)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        (saved,) = ctx.saved_tensors
+        saved, gate = ctx.saved_tensors
         eps, B, N, d = ctx.meta
         g = L.f32(g_out)
         dx = torch.empty_like(g)
-        L.call("nfdpf_ot_resample_bwd", L.ptr(g), L.ptr(saved), eps, B, N, d, L.ptr(dx), L.stream())
-        return dx, None, None, None, None, None
+        L.call("nfdpf_ot_resample_bwd", L.ptr(g), L.ptr(saved), eps, B, N, d, L.ptr(dx), L.ptr(gate), L.stream())
+        return dx, None, None, None, None, None, None
 
 
-def ot_resample(particles, logw, eps=0.1, scaling=0.75, threshold=1e-3, max_iter=100):
-    return OtResample.apply(particles, logw, eps, scaling, threshold, max_iter)
+def ot_resample(particles, logw, eps=0.1, scaling=0.75, threshold=1e-3, max_iter=100, gate=None):
+    return OtResample.apply(particles, logw, eps, scaling, threshold, max_iter, gate)
 
 
-class MotionMoments(torch.autograd.Function):
-    """x' = (x + vel_b) + noise (model/models.py:191-204); writes the detached [mean | std] context of x' into ctx."""
+class GateWeights(torch.autograd.Function):
+    """Weights after an OT resample under the device gate: (w, log w) = (1/N, -log N) if it fired, (probs, log probs) otherwise
+    (DPFs.py:166-170)."""
 
     @staticmethod
-    def forward(ctx, particles, vel, noise, ctx_buf, ctx_off):
+    def forward(ctx, probs, gate):
+        B, N = probs.shape
+        p = L.f32(probs)
+        w, lw = torch.empty_like(p), torch.empty_like(p)
+        L.call("nfdpf_gate_weights_fwd", L.ptr(p), L.ptr(gate), B, N, L.ptr(w), L.ptr(lw), L.stream())
+        ctx.save_for_backward(p, gate)
+        return w, lw
+
+    @staticmethod
+    def backward(ctx, g_w, g_lw):
+        p, gate = ctx.saved_tensors
+        B, N = p.shape
+        d = torch.empty_like(p)
+        L.call("nfdpf_gate_weights_bwd", L.ptr(L.f32(g_w) if g_w is not None else None), L.ptr(L.f32(g_lw) if g_lw is not None else None),
+               L.ptr(p), L.ptr(gate), B, N, L.ptr(d), L.stream())
+        return d, None
+
+
+def gate_weights(probs, gate):
+    return GateWeights.apply(probs, gate)
+
+
+def ess_gate(ess_inv, B, N, force=None, rng_state=None, advance=False, want_offsets=False, gate_out=None):
+    """Device-side ESS gate (DPFs.py:163-165): int32 flag tensor (and, if asked, U(0, 1/N) offsets (B,) drawn from rng_state).
+    ess_inv: the (B,) 1 / sum p^2 column of the previous weight update (a strided view is fine); force: None (the rule) / bool."""
+    dev = ess_inv.device if ess_inv is not None else rng_state.device
+    gate = gate_out if gate_out is not None else torch.empty(1, dtype=torch.int32, device=dev)
+    offsets = torch.empty(B, dtype=torch.float32, device=dev) if want_offsets else None
+    L.call("nfdpf_ess_gate", None if ess_inv is None else ess_inv.data_ptr(), 0 if ess_inv is None else ess_inv.stride(0), B, N,
+           -1 if force is None else int(bool(force)), L.ptr(rng_state), int(bool(advance)), L.ptr(gate), L.ptr(offsets), L.stream())
+    return gate, offsets
+
+
+class WeightedMean(torch.autograd.Function):
+    """pred (B,2) = sum_n probs[b,n] particles[b,n,:] -- the prediction of the supervised loss for one timestep (losses.py:22)."""
+
+    @staticmethod
+    def forward(ctx, particles, probs, out=None):
         B, N, d = particles.shape
-        x, v, e = L.f32(particles), L.f32(vel), L.f32(noise)
-        out = torch.empty_like(x)
-        L.call("nfdpf_motion_moments", L.ptr(x), L.ptr(v), L.ptr(e), B, N, d, L.ptr(out), L.ptr(ctx_buf),
-               0 if ctx_buf is None else ctx_buf.shape[1], ctx_off, L.stream())
-        return out
+        x, w = L.f32(particles), L.f32(probs)
+        pred = _out(out, "pred", shape=(B, d), device=x.device)
+        L.call("nfdpf_weighted_mean_fwd", L.ptr(x), L.ptr(w), B, N, d, L.ptr(pred), L.stream())
+        ctx.save_for_backward(x, w)
+        return pred
 
     @staticmethod
     def backward(ctx, g):
-        return g, None, None, None, None
+        x, w = ctx.saved_tensors
+        B, N, d = x.shape
+        d_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        d_w = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        if d_x is None and d_w is None:
+            return None, None, None
+        L.call("nfdpf_weighted_mean_bwd", L.ptr(L.f32(g)), L.ptr(x), L.ptr(w), B, N, d, L.ptr(d_x), L.ptr(d_w), L.stream())
+        return d_x, d_w, None
+
+
+def weighted_mean(particles, probs, out=None):
+    return WeightedMean.apply(particles, probs, out)
+
+
+class MotionMoments(torch.autograd.Function):
+    """x' = (x + vel_b) + noise (model/models.py:191-204); writes the detached [mean | std] context of x' into ctx.
+    noise given: injected draws (parity tests).  noise None: drawn in-kernel from rng_state (Philox) as sigma N(0,1) and
+    returned as the second output."""
+
+    @staticmethod
+    def forward(ctx, particles, vel, noise, ctx_buf, ctx_off, rng_state=None, sigma=1.0, out=None):
+        B, N, d = particles.shape
+        x, v = L.f32(particles), L.f32(vel)
+        res = _out(out, "moved", like=x)
+        cs = 0 if ctx_buf is None else ctx_buf.shape[1]
+        if noise is not None:
+            e = L.f32(noise)
+            L.call("nfdpf_motion_moments", L.ptr(x), L.ptr(v), L.ptr(e), B, N, d, L.ptr(res), L.ptr(ctx_buf), cs, ctx_off, L.stream())
+        else:
+            e = _out(out, "noise", like=x)
+            L.call("nfdpf_motion_moments_rng", L.ptr(x), L.ptr(v), L.ptr(rng_state), float(sigma), B, N, d, L.ptr(res), L.ptr(e),
+                   L.ptr(ctx_buf), cs, ctx_off, L.stream())
+        ctx.mark_non_differentiable(e)
+        return res, e
+
+    @staticmethod
+    def backward(ctx, g, _g_noise):
+        return g, None, None, None, None, None, None, None
 
 
 class ProposalTerms(torch.autograd.Function):
     """prior / proposal log-densities of proposal_likelihood (model/models.py:369-376)."""
 
     @staticmethod
-    def forward(ctx, back, phys, noise, jac_back, jac_dyn, jac_prop, sigma):
+    def forward(ctx, back, phys, noise, jac_back, jac_dyn, jac_prop, sigma, out=None):
         bk, ph, nz = L.f32(back), L.f32(phys), L.f32(noise)
         B, N, _ = bk.shape
         jb, jd, jp = (L.f32(t) if t is not None else None for t in (jac_back, jac_dyn, jac_prop))
-        prior = torch.empty(B, N, dtype=torch.float32, device=bk.device)
-        propose = torch.empty_like(prior)
+        prior = _out(out, "prior", shape=(B, N), device=bk.device)
+        propose = _out(out, "propose", shape=(B, N), device=bk.device)
         L.call("nfdpf_proposal_terms_fwd", L.ptr(bk), L.ptr(ph), L.ptr(nz), L.ptr(jb), L.ptr(jd), L.ptr(jp), float(sigma), B * N,
                L.ptr(prior), L.ptr(propose), L.stream())
         ctx.save_for_backward(bk, ph, nz)
@@ -303,12 +395,44 @@ class ProposalTerms(torch.autograd.Function):
             neg = torch.empty_like(gp) if has_b else None
             L.call("nfdpf_proposal_terms_bwd", L.ptr(gp), L.ptr(bk), L.ptr(ph), L.ptr(nz), ctx.sigma, B * N, L.ptr(d_back), L.ptr(d_phys),
                    L.ptr(neg), L.stream())
-        return d_back, d_phys, None, neg, (g_prop if has_d else None), (g_prop if has_p else None), None
+        return d_back, d_phys, None, neg, (g_prop if has_d else None), (g_prop if has_p else None), None, None
 
 
-def motion_moments(particles, vel, noise, ctx_buf=None, ctx_off=0):
-    return MotionMoments.apply(particles, vel, noise, ctx_buf, ctx_off)
+def motion_moments(particles, vel, noise, ctx_buf=None, ctx_off=0, rng_state=None, sigma=1.0, out=None):
+    """(particles', noise).  noise=None draws sigma N(0,1) in-kernel from rng_state (device int64[2] = seed, step counter)."""
+    return MotionMoments.apply(particles, vel, noise, ctx_buf, ctx_off, rng_state, sigma, out)
 
 
-def proposal_terms(back, phys, noise, jac_back, jac_dyn, jac_prop, sigma):
-    return ProposalTerms.apply(back, phys, noise, jac_back, jac_dyn, jac_prop, sigma)
+def proposal_terms(back, phys, noise, jac_back, jac_dyn, jac_prop, sigma, out=None):
+    return ProposalTerms.apply(back, phys, noise, jac_back, jac_dyn, jac_prop, sigma, out)
+
+
+def init_particles(start_state, width, N, rng_state, init_with_true_state=False):
+    """particle_initialization (utils.py:46-62) on the device: (B,N,2) uniform box or start + N(0,1)."""
+    B = start_state.shape[0]
+    st = L.f32(start_state)
+    out = torch.empty(B, N, 2, dtype=torch.float32, device=st.device)
+    L.call("nfdpf_init_particles_rng", L.ptr(st), st.shape[1], L.ptr(rng_state), float(width), int(bool(init_with_true_state)), B, N, 2,
+           L.ptr(out), L.stream())
+    return out
+
+
+class ListView(torch.autograd.Function):
+    """The (B,T,...) list of the filter outputs (DPFs.py:207-214) as a transposed VIEW of the (T,B,...) buffer the step kernels
+    already wrote into -- no torch.stack / torch.cat copy.  Autograd-wise it is stack(steps, dim=1): the backward hands slice t of
+    the incoming gradient to step t."""
+
+    @staticmethod
+    def forward(ctx, buf_holder, *steps):
+        ctx.n = len(steps)
+        return buf_holder[0].transpose(0, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None,) + tuple(g[:, t] for t in range(ctx.n))
+
+
+def list_view(buf, steps):
+    if not any(torch.is_tensor(s) and s.requires_grad for s in steps):
+        return buf.transpose(0, 1)
+    return ListView.apply((buf,), *steps)

@@ -38,9 +38,11 @@ def _markers(n, dev):
     return _marker_cache[key]
 
 
-def soft_resampler(particles, particle_probs, alpha, num_resampled, index=True, device="cuda", random_offset=None, want_log=False):
+def soft_resampler(particles, particle_probs, alpha, num_resampled, index=True, device="cuda", random_offset=None, want_log=False,
+                   gate=None, out=None):
     """Soft (mixture-with-uniform) systematic resampling.  `random_offset` (B,) may be injected; by default it is
-    drawn exactly like the reference does (CPU generator, U(0, 1/N), resamplers.py:43)."""
+    drawn exactly like the reference does (CPU generator, U(0, 1/N), resamplers.py:43).  `gate` (device int32 flag, the
+    filter loop's ESS decision) and `out` (pre-allocated outputs) are extensions used by DPF.filtering_pos."""
     assert 0.0 < alpha <= 1.0
     batch, n = particle_probs.shape
     if num_resampled != n:
@@ -48,10 +50,10 @@ def soft_resampler(particles, particle_probs, alpha, num_resampled, index=True, 
     if random_offset is None:
         random_offset = torch.FloatTensor(batch).uniform_(0.0, 1.0 / num_resampled)
     off = random_offset.to(particles.device, non_blocking=True)
-    out = ops.soft_resample(particles, particle_probs, off, _markers(n, particles.device), alpha, want_log)
+    res = ops.soft_resample(particles, particle_probs, off, _markers(n, particles.device), alpha, want_log, gate, out)
     if want_log:  # (particles, probs, idx, log probs): the filter loop's fused path
-        return out
-    return out if index else out[:2]
+        return res
+    return res if index else res[:2]
 
 
 def resampler_ot(particles, weights, eps=0.1, scaling=0.75, threshold=1e-3, max_iter=100, device="cuda",

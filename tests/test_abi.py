@@ -27,5 +27,5 @@ def test_library_exports_every_declared_symbol():
 def test_error_reporting_without_gpu():
     lib = L.load()
     # argument validation happens before any CUDA call
-    rc = lib.nfdpf_soft_resample_fwd(None, None, None, None, 0.5, 1, 1, 2, None, None, None, None, None, None)
+    rc = lib.nfdpf_soft_resample_fwd(None, None, None, None, 0.5, 1, 1, 2, None, None, None, None, None, None, None)
     assert rc == -1 and b"null pointer" in lib.nfdpf_last_error()

@@ -331,7 +331,7 @@ def test_motion_moments_and_proposal_terms_vs_oracle():
     x, noise = torch.randn(B, N, 2, generator=g) * 30, torch.randn(B, N, 2, generator=g) * 20
     vel = torch.randn(B, 2, generator=g) * 3
     ctx = torch.zeros(B, 9, device="cuda")
-    out = ops.motion_moments(cu(x), cu(vel), cu(noise), ctx, 3)
+    out, _ = ops.motion_moments(cu(x), cu(vel), cu(noise), ctx, 3)
     ref = O.motion_update(x, vel, noise)
     close(out, ref, atol=1e-4, what="motion")
     mean, std = O.row_stats(ref)
