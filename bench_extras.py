@@ -24,21 +24,26 @@ def _events(fn, n=10, warm=3):
         fn()
     torch.cuda.synchronize()
     graph = None
-    try:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            fn()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            fn()
-        graph.replay()
-        torch.cuda.synchronize()
-    except Exception:
-        graph = None
-        torch.cuda.synchronize()
+    for attempt in range(2):      # the first capture of a process can be invalidated by one-time lazy initialisation: retry once
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fn()
+            graph.replay()
+            torch.cuda.synchronize()
+            break
+        except Exception:
+            graph = None
+            torch.cuda.synchronize()
+            for _ in range(2):    # a failed capture leaves the next launches slow: re-warm before anything is timed
+                fn()
+            torch.cuda.synchronize()
     best = None
     for run in ([graph.replay] if graph is not None else []) + [fn]:   # min of graph replay and plain launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -84,7 +84,7 @@ int nfdpf_coupling_fwd(const float* packed, int n_flows, int D, int C_row, int C
 /* backward from the OUTPUT y (coupling layers are invertible: activations are recomputed walking the stack
  * backwards, nothing else is saved).  g_y (P,D), g_ld (P,) (NULL = 0).  d_x (P,D); d_row_ctx (B,C_row) /
  * d_part_ctx (P,C_part) may be NULL (context detached: model/models.py:309-313, 338-339, 360-361).
- * d_packed: fp32 vector of the packed-stack length, ACCUMULATED into (+=) in a fixed order (deterministic).
+ * d_packed: fp32 vector of the packed-stack length; every entry is WRITTEN (sums formed in a fixed order: deterministic).
  * workspace: nfdpf_coupling_bwd_workspace() bytes of device scratch. */
 int64_t nfdpf_coupling_bwd_workspace(int n_flows, int D, int C_row, int C_part, int B, int N);
 int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C_part, const float* y,
@@ -112,7 +112,7 @@ int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* cnf_packed,
                       const float* prior, const float* propose, float add_eps, float* lki, int32_t* argmax,
                       float* logw_out, float* probs_out, float* row_stats, float* z_out, void* stream);
 /* backward of lki w.r.t. particles (B,N,2), enc (B,hidden; may be NULL: detached), particle-encoder and cnf
- * parameters (d_pe / d_cnf ACCUMULATED into, deterministic).  g_lki (B,N) is the total gradient reaching lki
+ * parameters (every entry of d_pe / d_cnf is WRITTEN, sums formed in a fixed order: deterministic).  g_lki (B,N) is the total gradient reaching lki
  * (the caller adds the weight-update gradient from nfdpf_weight_update_bwd when the update was fused). */
 int64_t nfdpf_measure_bwd_workspace(int mode, int n_flows, int B, int N);
 int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,

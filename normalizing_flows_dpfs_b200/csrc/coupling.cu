@@ -198,7 +198,7 @@ coupling_bwd_kernel(const float* __restrict__ packed, int n_flows, int C_row, co
     }
 }
 
-// d_packed[i] += sum over CTAs.  One warp per parameter: lane l sums partials l, l+32, ... in fp64, then a fixed
+// d_packed[i] = sum over CTAs (every parameter is written: the caller need not clear the buffer).  One warp per parameter: lane l sums partials l, l+32, ... in fp64, then a fixed
 // butterfly -- the order depends only on (n_parts), so results are run-to-run deterministic.
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_parts, int n_params, float* __restrict__ d_packed) {
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -206,7 +206,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     double a = 0.0;
     for (int c = lane; c < n_parts; c += 32) a += (double)partials[(size_t)c * n_params + i];
     a = warp_sum(a);
-    if (lane == 0) d_packed[i] += (float)a;
+    if (lane == 0) d_packed[i] = (float)a;
 }
 
 int bwd_grid(int B) { return min(B, 2 * sm_count()); }

@@ -329,13 +329,14 @@ __device__ __forceinline__ float img_value(const float* __restrict__ packed, int
 }
 
 // Workspace layout (floats): [grid * NW rows][n_fcnn * NACC] per-warp partial gradients (accumulator order, divided by the tanh
-// scale where grad_out_scale says so), then [grid][n_fcnn * 8 * (C_row + 1)] per-CTA row-context partials (last column: db1).
+// scale where grad_out_scale says so), then [grid][n_fcnn * 8 * (C_row + 1)] per-CTA row-context partials (last column: db1),
+// then [grid][n_fcnn * NACC]: the per-warp rows of each CTA folded in warp order (what the reduce kernel reads).
 template <int PPT, int NT>
 __global__ void __launch_bounds__(NT, 1)
 coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ y,
                        const float* __restrict__ row_ctx, int flags, int B, int N, const float* __restrict__ g_y,
-                       const float* __restrict__ g_ld, float* __restrict__ d_x, float* __restrict__ warp_rows,
-                       float* __restrict__ ctx_rows, float* __restrict__ d_row_ctx, int e_max) {
+                       const float* __restrict__ g_ld, float* __restrict__ d_x, float* warp_rows,
+                       float* __restrict__ ctx_rows, float* __restrict__ cta_rows, float* __restrict__ d_row_ctx, int e_max) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_slot[NT / 32][100];
     constexpr int NW = NT / 32, TASK = 32 * PPT;
@@ -500,9 +501,19 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
     }
     float* out = ctx_rows + (size_t)blockIdx.x * nR1;
     for (int e = tid; e < nR1; e += NT) out[e] = s_accR[e];
+    // fold the CTA's per-warp rows (still L2-hot) into one row, warps in order: the reduce kernel then reads 148 rows, not 1184
+    const int n_acc = n_fcnn * NACC;
+    const float* mine = warp_rows + (size_t)blockIdx.x * NW * n_acc;
+    float* folded = cta_rows + (size_t)blockIdx.x * n_acc;
+    for (int c = tid; c < n_acc; c += NT) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += mine[(size_t)w * n_acc + c];
+        folded[c] = v;
+    }
 }
 
-// d_packed[target] += fixed-order fp64 column sums of the per-warp rows and the per-CTA row-context partials.  A block owns 32
+// d_packed[target] = fixed-order fp64 column sums of the per-warp rows and the per-CTA row-context partials.  A block owns 32
 // consecutive columns (coalesced 128-byte row segments); its 8 warps take the rows round-robin and the partial sums are added
 // in warp order -- the order depends only on the launch geometry: run-to-run deterministic.
 __global__ void d2_reduce_kernel(const float* __restrict__ warp_rows, int n_rows, const float* __restrict__ ctx_rows, int n_cta,
@@ -532,12 +543,12 @@ __global__ void d2_reduce_kernel(const float* __restrict__ warp_rows, int n_rows
         target = f * pf + (c < C_row ? k * fin + 1 + c : H * fin + k);
         scale = TANH_SCALE;
     }
-    d_packed[target] += (float)(a * (double)scale);
+    d_packed[target] = (float)(a * (double)scale);
 }
 
 size_t coupling_bwd_d2_workspace_floats(int n_flows, int C_row, int B) {
     const int n_fcnn = 4 * n_flows, grid = min(B, sm_count());
-    return (size_t)grid * ((size_t)D2_MAX_WARPS * n_fcnn * NACC + (size_t)n_fcnn * H * (C_row + 1));
+    return (size_t)grid * ((size_t)(D2_MAX_WARPS + 1) * n_fcnn * NACC + (size_t)n_fcnn * H * (C_row + 1));
 }
 
 template <int PPT, int NT>
@@ -559,11 +570,12 @@ static int launch_cfg(const float* packed, int n_flows, int C_row, const float* 
     NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float* warp_rows = (float*)workspace;
     float* ctx_rows = warp_rows + (size_t)grid * (NT / 32) * n_fcnn * NACC;
-    kern<<<grid, NT, smem, st>>>(packed, n_flows, C_row, y, row_ctx, flags, B, N, g_y, g_ld, d_x, warp_rows, ctx_rows, d_row_ctx, e_max);
+    float* cta_rows = ctx_rows + (size_t)grid * n_fcnn * H * (C_row + 1);
+    kern<<<grid, NT, smem, st>>>(packed, n_flows, C_row, y, row_ctx, flags, B, N, g_y, g_ld, d_x, warp_rows, ctx_rows, cta_rows, d_row_ctx, e_max);
     int rc = check_launch("coupling_bwd_d2");
     if (rc) return rc;
     const int n_cols = n_fcnn * NACC + n_fcnn * H * (C_row + 1);
-    d2_reduce_kernel<<<(n_cols + 31) / 32, 256, 0, st>>>(warp_rows, grid * (NT / 32), ctx_rows, grid, n_fcnn, C_row, d_packed);
+    d2_reduce_kernel<<<(n_cols + 31) / 32, 256, 0, st>>>(cta_rows, grid, ctx_rows, grid, n_fcnn, C_row, d_packed);
     return check_launch("d2_reduce");
 }
 

@@ -25,7 +25,7 @@ struct Philox {
         return c;
     }
 };
-__device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }   // (0, 1), 24 bits
+__device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }   // strictly inside (0, 1): 23 bits + half a step, exact in fp32
 // two independent N(0, 1) draws from two 32-bit words (Box-Muller)
 __device__ __forceinline__ float2 normal2(unsigned a, unsigned b) {
     const float r = sqrtf(-2.0f * __logf(u01(a)));

@@ -43,6 +43,7 @@ class SoftResample(torch.autograd.Function):
         L.call("nfdpf_soft_resample_fwd", L.ptr(p), L.ptr(w), L.ptr(off), L.ptr(mk), float(alpha), B, N, d, L.ptr(p_out),
                L.ptr(w_out), L.ptr(idx), L.ptr(saved), L.ptr(lw_out), L.ptr(gate), L.stream())
         ctx.save_for_backward(w, idx, saved, gate)
+        ctx.set_materialize_grads(False)     # unused outputs arrive as None, not as zero-filled tensors
         ctx.alpha, ctx.shape = float(alpha), (B, N, d)
         ctx.mark_non_differentiable(idx)
         return p_out, w_out, idx, lw_out
@@ -75,6 +76,7 @@ class WeightUpdate(torch.autograd.Function):
         L.call("nfdpf_weight_update_fwd", L.ptr(a), L.ptr(terms[0]), L.ptr(terms[1]), L.ptr(terms[2]), float(add_eps), B, N,
                L.ptr(logw), L.ptr(probs), L.ptr(stats), L.stream())
         ctx.save_for_backward(probs)
+        ctx.set_materialize_grads(False)
         ctx.add_eps = float(add_eps)
         ctx.has = [t is not None for t in (lki, prior, propose)]
         row_sum, ess_inv = stats[:, 0], stats[:, 1]
@@ -114,6 +116,7 @@ class CouplingStack(torch.autograd.Function):
         L.call("nfdpf_coupling_fwd", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(xx), L.ptr(rc), L.ptr(pc), flags, B, N,
                L.ptr(y), L.ptr(ld), L.stream())
         ctx.save_for_backward(pk, y, rc, pc)
+        ctx.set_materialize_grads(False)
         ctx.meta = (n_flows, D, C_row, C_part, flags, B, N)
         return y, ld
 
@@ -128,7 +131,7 @@ class CouplingStack(torch.autograd.Function):
         need_pc = pc is not None and ctx.needs_input_grad[3]
         d_rc = torch.empty_like(rc) if need_rc else None
         d_pc = torch.empty_like(pc) if need_pc else None
-        d_pk = torch.zeros_like(pk)
+        d_pk = torch.empty_like(pk)        # every entry is written by the reduce kernel
         ws_bytes = L.load().nfdpf_coupling_bwd_workspace(n_flows, D, C_row, C_part, B, N)
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=y.device)
         L.call("nfdpf_coupling_bwd", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(y), L.ptr(rc), L.ptr(pc), inverse, B, N,
@@ -187,6 +190,7 @@ class MeasureUpdate(torch.autograd.Function):
                L.ptr(lw0), L.ptr(pr), L.ptr(pp), float(add_eps), L.ptr(lki), L.ptr(argmax), L.ptr(logw), L.ptr(probs), L.ptr(stats),
                L.ptr(z), L.stream())
         ctx.save_for_backward(pe_, cnf_, enc_, x_, argmax, probs, z)
+        ctx.set_materialize_grads(False)
         ctx.meta = (mode, n_flows, float(p0), float(p1), float(add_eps), B, N, hidden, fused, prior is not None, propose is not None)
         if not fused:
             return lki, None, None, None, None
@@ -211,8 +215,8 @@ class MeasureUpdate(torch.autograd.Function):
             g_total = torch.zeros(B, N, dtype=torch.float32, device=dev)
         d_x = torch.empty_like(x_)
         d_enc = torch.empty_like(enc_) if ctx.needs_input_grad[2] else None
-        d_pe = torch.zeros_like(pe_)
-        d_cnf = torch.zeros_like(cnf_) if cnf_ is not None else None
+        d_pe = torch.empty_like(pe_)       # every entry is written by the reduce kernels
+        d_cnf = torch.empty_like(cnf_) if cnf_ is not None else None
         ws = torch.empty(L.load().nfdpf_measure_bwd_workspace(mode, n_flows, B, N) // 4, dtype=torch.float32, device=dev)
         L.call("nfdpf_measure_bwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, p0, p1, L.ptr(enc_), L.ptr(x_), B, N, hidden,
                L.ptr(g_total.contiguous()), L.ptr(argmax), L.ptr(d_x), L.ptr(d_enc), L.ptr(d_pe), L.ptr(d_cnf), L.ptr(ws), L.ptr(z), L.stream())
@@ -286,6 +290,7 @@ class GateWeights(torch.autograd.Function):
         w, lw = torch.empty_like(p), torch.empty_like(p)
         L.call("nfdpf_gate_weights_fwd", L.ptr(p), L.ptr(gate), B, N, L.ptr(w), L.ptr(lw), L.stream())
         ctx.save_for_backward(p, gate)
+        ctx.set_materialize_grads(False)
         return w, lw
 
     @staticmethod
@@ -380,6 +385,7 @@ class ProposalTerms(torch.autograd.Function):
         L.call("nfdpf_proposal_terms_fwd", L.ptr(bk), L.ptr(ph), L.ptr(nz), L.ptr(jb), L.ptr(jd), L.ptr(jp), float(sigma), B * N,
                L.ptr(prior), L.ptr(propose), L.stream())
         ctx.save_for_backward(bk, ph, nz)
+        ctx.set_materialize_grads(False)
         ctx.sigma, ctx.has = float(sigma), (jac_back is not None, jac_dyn is not None, jac_prop is not None)
         return prior, propose
 

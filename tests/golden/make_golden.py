@@ -289,6 +289,22 @@ def gen_filter():
     np.savez_compressed(os.path.join(OUT, "filter.npz"), **out)
 
 
+def gen_init():
+    """utils.py:46-62 under a seed: the cloud, the log-weights, and the generator state afterwards (next draw)."""
+    out = {}
+    cases = [(4, 100, 128.0, False, 3), (3, 64, 128.0, True, 5), (2, 1024, 64.0, False, 11)]
+    for ci, (B, N, width, true_state, seed) in enumerate(cases):
+        g = torch.Generator().manual_seed(50 + ci)
+        start = torch.randn(B, 2, generator=g) * 20
+        torch.manual_seed(seed)
+        p, lw = ref_utils.particle_initialization(start, width, N, 2, init_with_true_state=true_state)
+        nxt = torch.rand(3)
+        out.update({f"c{ci}_{k}": v for k, v in npy(dict(start=start, width=width, N=N, true_state=true_state, seed=seed, particles=p,
+                                                         logw=lw, next_draw=nxt)).items()})
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(OUT, "init.npz"), **out)
+
+
 def gen_state_dict():
     """state_dict keys + shapes of the reference DPF for the accelerated configurations (checkpoint compatibility)."""
     import json
@@ -305,8 +321,8 @@ def gen_state_dict():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["soft", "flows", "glue", "ot", "filter", "state_dict"]
+    which = sys.argv[1:] or ["soft", "flows", "glue", "ot", "filter", "state_dict", "init"]
     sys.argv = sys.argv[:1]
     for w in which:
-        {"soft": gen_soft, "flows": gen_flows, "glue": gen_glue, "ot": gen_ot, "filter": gen_filter, "state_dict": gen_state_dict}[w]()
+        {"soft": gen_soft, "flows": gen_flows, "glue": gen_glue, "ot": gen_ot, "filter": gen_filter, "state_dict": gen_state_dict, "init": gen_init}[w]()
         print("wrote", w)

@@ -66,4 +66,6 @@ def test_filter_matches_reference(golden, tag):
         if mod is None or (name == "dyn" and not dpf.NF) or (name == "cond" and not dpf.NFcond):
             continue
         ref = g("d_" + name)
-        close(_flat_grad(mod), ref, rtol=1e-3, atol=(2e-3 if ot else 2e-4) * float(np.abs(ref).max()), what="d_" + name)
+        # whole-filter parameter gradients (sums over B*N*T particle-steps): measured worst 9.6e-6 (soft) / 3.9e-5 (OT, fp32 Sinkhorn
+        # against the reference's fp64) of the tensor's largest magnitude -- profiles/r2_parity_errors.json; round 1 allowed 2e-4 / 2e-3
+        close(_flat_grad(mod), ref, rtol=1e-4, atol=(2e-4 if ot else 5e-5) * float(np.abs(ref).max()), what="d_" + name)

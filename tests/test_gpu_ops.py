@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+import ledger
 import nfdpf_oracle as O
 from normalizing_flows_dpfs_b200 import ops
 
@@ -19,14 +20,22 @@ def close(a, b, rtol=RTOL, atol=ATOL, what=""):
     a = T(a).detach().cpu().double().numpy()
     b = T(b).detach().cpu().double().numpy()
     assert a.shape == b.shape, (what, a.shape, b.shape)
+    ledger.record(what, a, b, rtol, atol)
     err = np.abs(a - b) - (atol + rtol * np.abs(b))
     assert (err <= 0).all(), "%s: max abs diff %.3e (worst excess %.3e)" % (what, np.abs(a - b).max(), err.max())
 
 
-def grad_close(a, b, what=""):
-    """gradients: rtol 1e-4 with atol scaled to the gradient's magnitude (sums of ~1e3..1e6 fp32 terms)."""
+GRAD_FLOOR = float(os.environ.get("NFDPF_GRAD_FLOOR", "0.2"))      # atol = 2e-5 of the gradient tensor's largest magnitude (round 1: 1e-4); measured worst: 6.5e-6
+
+
+def grad_close(a, b, what="", floor=None):
+    """Gradients are sums of 1e3..1e6 fp32 products.  Every entry must hold |err| <= rtol * max(|ref|, floor * max|ref|) with
+    rtol = 1e-4: entries above `floor` of the tensor's largest magnitude are checked at the north-star relative tolerance, smaller
+    ones absolutely against that floor.  The floor is set from the measured errors (profiles/r2_parity_errors.json lists, per
+    comparison, the CUDA-vs-oracle error next to the error of torch's own fp32 evaluation against fp64)."""
+    floor = GRAD_FLOOR if floor is None else floor
     b_ = T(b).detach().cpu().double().numpy()
-    close(a, b, rtol=RTOL, atol=max(ATOL, 1e-4 * float(np.abs(b_).max())), what=what)
+    close(a, b, rtol=RTOL, atol=max(1e-12, RTOL * floor * float(np.abs(b_).max())), what=what)
 
 
 # ------------------------------------------------------------------------------------------ soft resampling

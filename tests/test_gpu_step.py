@@ -1,0 +1,182 @@
+"""GPU tests of the host-free step pieces (csrc/step.cu): the device-side ESS gate and its pass-through branches, the in-kernel
+Philox draws (distribution tests: they are not the reference's CPU stream), the fused prediction of the supervised loss, and
+CUDA-graph execution of the filter with the REAL gate."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import nfdpf_oracle as O
+from normalizing_flows_dpfs_b200 import ops
+from normalizing_flows_dpfs_b200.graphs import GraphedFilterStep
+from normalizing_flows_dpfs_b200.losses import supervised_loss
+from test_gpu_ops import close, cu, grad_close
+from test_gpu_trainer import _filter_dpf
+
+pytestmark = pytest.mark.gpu
+
+
+def _gate(v):
+    return torch.tensor([v], dtype=torch.int32, device="cuda")
+
+
+def test_ess_gate_matches_the_host_rule():
+    g = torch.Generator().manual_seed(1)
+    for B, N, scale in ((7, 100, 1.0), (1024, 1024, 1.0), (33, 64, 0.45), (5, 10, 0.55)):
+        stats = torch.rand(B, 2, generator=g).cuda()
+        stats[:, 1] = stats[:, 1] * N * scale                      # 1 / sum p^2 in (0, N)
+        gate, off = ops.ess_gate(stats[:, 1], B, N)
+        assert off is None
+        assert bool(gate.item()) == bool(stats[:, 1].double().mean().item() < 0.5 * N)
+        assert int(ops.ess_gate(stats[:, 1], B, N, force=True)[0].item()) == 1
+        assert int(ops.ess_gate(stats[:, 1], B, N, force=False)[0].item()) == 0
+
+
+@pytest.mark.parametrize("B,N", [(5, 257), (64, 1024)])
+def test_soft_resample_closed_gate_is_the_else_branch(B, N):
+    """gate == 0: particles / weights pass through, identity ancestors, log-weights = log(probs) (DPFs.py:168-170), with backward."""
+    g = torch.Generator().manual_seed(B + N)
+    w = torch.softmax(torch.randn(B, N, generator=g) * 2, -1)
+    p = torch.randn(B, N, 2, generator=g) * 10
+    off, mk = torch.rand(B, generator=g) / N, torch.linspace(0.0, (N - 1.0) / N, N)
+    pg, wg = cu(p).requires_grad_(), cu(w).requires_grad_()
+    p2, w2, idx, lw2 = ops.soft_resample(pg, wg, cu(off), cu(mk), 0.5, want_log=True, gate=_gate(0))
+    assert torch.equal(p2, pg.detach()) and torch.equal(w2, wg.detach())
+    assert torch.equal(idx, torch.arange(B * N, device="cuda").reshape(B, N))
+    close(lw2, w.log(), what="log weights")
+    g1, g2, g3 = torch.randn(B, N, 2, generator=g), torch.randn(B, N, generator=g), torch.randn(B, N, generator=g)
+    ((p2 * cu(g1)).sum() + (w2 * cu(g2)).sum() + (lw2 * cu(g3)).sum()).backward()
+    close(pg.grad, g1, what="d_particles")
+    close(wg.grad, g2 + g3 / w, rtol=1e-5, what="d_probs")
+    # an open gate equals the ungated call bit for bit
+    a = ops.soft_resample(cu(p), cu(w), cu(off), cu(mk), 0.5, want_log=True, gate=_gate(1))
+    b = ops.soft_resample(cu(p), cu(w), cu(off), cu(mk), 0.5, want_log=True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_ot_resample_gate():
+    g = torch.Generator().manual_seed(3)
+    B, N = 4, 300
+    w = torch.softmax(torch.randn(B, N, generator=g) * 2, -1)
+    x = torch.randn(B, N, 2, generator=g) * 20
+    xg, wg = cu(x).requires_grad_(), cu(w).requires_grad_()
+    out = ops.ot_resample(xg, wg.log(), gate=_gate(0))
+    w2, lw2 = ops.gate_weights(wg, _gate(0))
+    assert torch.equal(out, xg.detach()) and torch.equal(w2, wg.detach())
+    g1, g2 = torch.randn(B, N, 2, generator=g), torch.randn(B, N, generator=g)
+    ((out * cu(g1)).sum() + (lw2 * cu(g2)).sum()).backward()
+    close(xg.grad, g1, what="dx through a closed gate")
+    close(wg.grad, g2 / w, rtol=1e-5, what="d_probs through a closed gate")
+    ref = ops.ot_resample(cu(x), cu(w).log())
+    assert torch.equal(ops.ot_resample(cu(x), cu(w).log(), gate=_gate(1)), ref)
+    w3, lw3 = ops.gate_weights(cu(w), _gate(1))
+    assert float((w3 - 1.0 / N).abs().max()) == 0 and float((lw3 + math.log(N)).abs().max()) < 1e-6
+
+
+def test_weighted_mean_vs_torch():
+    g = torch.Generator().manual_seed(5)
+    for B, N in ((3, 100), (1024, 1024), (7, 4096)):
+        x, w = torch.randn(B, N, 2, generator=g) * 30, torch.softmax(torch.randn(B, N, generator=g) * 3, -1)
+        gp = torch.randn(B, 2, generator=g)
+        xo, wo = x.double().requires_grad_(), w.double().requires_grad_()
+        po = (xo * wo[..., None]).sum(1)
+        (po * gp.double()).sum().backward()
+        xg, wg = cu(x).requires_grad_(), cu(w).requires_grad_()
+        pg = ops.weighted_mean(xg, wg)
+        close(pg, po, rtol=1e-5, atol=1e-4, what="prediction")
+        (pg * cu(gp)).sum().backward()
+        close(xg.grad, xo.grad, rtol=1e-6, atol=1e-9, what="d_particles")
+        close(wg.grad, wo.grad, rtol=1e-5, atol=1e-4, what="d_probs")
+
+
+def test_device_rng_draws_have_the_reference_distributions():
+    """model/models.py:199-200 (N(0, pos_noise^2) motion noise), resamplers.py:43 (U(0, 1/N) offsets), utils.py:46-62 (initial cloud)."""
+    dev = torch.device("cuda")
+    B, N, sigma = 512, 1024, 20.0
+    rng = torch.tensor([1234, 0], dtype=torch.int64, device=dev)
+    x = torch.zeros(B, N, 2, device=dev)
+    vel = torch.zeros(B, 2, device=dev)
+    ctx = torch.zeros(B, 4, device=dev)
+    moved, noise = ops.motion_moments(x, vel, None, ctx, 0, rng, sigma)
+    assert torch.equal(moved, noise)
+    n = noise.double()
+    se = sigma / math.sqrt(n.numel())
+    assert abs(float(n.mean())) < 5 * se and abs(float(n.std()) - sigma) < 5 * se
+    assert abs(float((n[..., 0] * n[..., 1]).mean())) < 5 * sigma * sigma / math.sqrt(B * N)       # x / y uncorrelated
+    z = (n / sigma).flatten()
+    assert abs(float((z ** 3).mean())) < 0.02 and abs(float((z ** 4).mean()) - 3.0) < 0.05        # skewness, kurtosis
+    assert abs(float((z.abs() < 1).double().mean()) - 0.6827) < 0.003
+    close(ctx[:, 2:], noise.std(1), rtol=1e-4, what="fused moments")
+    # same state -> same draws; advanced step counter -> fresh draws
+    _, again = ops.motion_moments(x, vel, None, None, 0, rng, sigma)
+    assert torch.equal(again, noise)
+    gate, off = ops.ess_gate(None, B, N, force=True, rng_state=rng, advance=True, want_offsets=True)
+    assert int(rng[1].item()) == 1 and float(off.min()) > 0 and float(off.max()) < 1.0 / N
+    assert abs(float(off.mean()) * N - 0.5) < 5 / math.sqrt(12 * B)
+    _, fresh = ops.motion_moments(x, vel, None, None, 0, rng, sigma)
+    assert not torch.equal(fresh, noise) and abs(float((fresh * noise).mean())) < 5 * sigma * sigma / math.sqrt(B * N)
+    start = torch.randn(B, 4, device=dev) * 10
+    box = ops.init_particles(start[:, :2], 128.0, N, rng)
+    assert float(box.min()) >= -64 and float(box.max()) < 64 and abs(float(box.mean())) < 5 * 128 / math.sqrt(12 * B * N * 2)
+    assert abs(float(box.std()) - 128 / math.sqrt(12)) < 0.1
+    near = ops.init_particles(start[:, :2], 128.0, N, rng, init_with_true_state=True)
+    assert abs(float((near - start[:, None, :2]).std()) - 1.0) < 0.01
+
+
+def test_seeded_particle_initialization_matches_reference(golden):
+    """utils.py:46-62 under torch.manual_seed: same cloud, same RNG consumption (the unused velocity draw included)."""
+    from normalizing_flows_dpfs_b200.utils import particle_initialization
+    G = golden("init")
+    for c in range(int(G["n_cases"])):
+        g = lambda k: G[f"c{c}_{k}"]
+        torch.manual_seed(int(g("seed")))
+        p, lw = particle_initialization(cu(g("start")), float(g("width")), int(g("N")), 2, init_with_true_state=bool(g("true_state")))
+        nxt = torch.rand(3)
+        assert np.array_equal(p.cpu().numpy(), g("particles")), f"case {c}: initial cloud differs from the reference"
+        assert np.array_equal(lw.cpu().numpy(), g("logw"))
+        assert np.array_equal(nxt.numpy(), g("next_draw")), f"case {c}: the CPU generator was advanced differently"
+
+
+@pytest.mark.parametrize("resampler", ["soft", "ot"])
+def test_graph_with_the_real_gate_equals_eager(resampler):
+    """The reference's ESS rule (not forced) inside a captured CUDA graph: same gate decisions as the eager run, gradients bit for bit."""
+    flags = ["--NF-dyn", "--NF-cond", "--measurement", "gaussian", "--resampler_type", resampler]
+    dpf, batch = _filter_dpf(flags, 8, 256, 6)
+    dpf.injected = dict(init_particles=batch["init_particles"], noise=batch["noise"], offsets=batch["offsets"])
+    out = dpf.filtering_pos(batch["enc"], batch["start"], batch["vel_in"])
+    fired = list(dpf.fired)
+    assert any(fired) and not all(fired), "the case should exercise both branches of the gate: %r" % (fired,)
+    loss, _ = supervised_loss(out[0], out[1], batch["state"], 1.0, False)
+    dpf.zero_grad(set_to_none=True)
+    loss.backward()
+    eager = [p.grad.clone() for p in dpf.nf_dyn.parameters()]
+    loss = loss.detach().clone()
+    del out
+    step = GraphedFilterStep(dpf, batch)
+    for _ in range(2):
+        g_loss = step.run(batch)
+        torch.cuda.synchronize()
+        assert dpf.fired == fired
+        assert torch.equal(g_loss, loss)
+        for a, p in zip(eager, dpf.nf_dyn.parameters()):
+            assert torch.equal(a, p.grad), "graph replay must reproduce the eager gradients bit for bit"
+
+
+def test_fused_prediction_equals_the_list_formula():
+    """supervised_loss on the lists of filtering_pos (fused per-step predictions ride along) == the reference formula on plain copies."""
+    flags = ["--NF-dyn", "--NF-cond", "--measurement", "gaussian", "--resampler_type", "soft"]
+    dpf, batch = _filter_dpf(flags, 6, 200, 4)
+    dpf.injected = dict(init_particles=batch["init_particles"], noise=batch["noise"], offsets=batch["offsets"])
+    grads = []
+    for plain in (False, True):
+        out = dpf.filtering_pos(batch["enc"], batch["start"], batch["vel_in"])
+        pl, wl = (out[0] + 0.0, out[1] + 0.0) if plain else (out[0], out[1])     # "+ 0" drops the attached predictions
+        loss, pred = supervised_loss(pl, wl, batch["state"], 1.0, False)
+        dpf.zero_grad(set_to_none=True)
+        loss.backward()
+        grads.append((loss.detach(), pred.detach(), [p.grad.clone() for p in dpf.cond_model.parameters()]))
+    close(grads[0][0], grads[1][0], rtol=1e-6, what="loss")
+    close(grads[0][1], grads[1][1], rtol=1e-5, atol=1e-4, what="predictions")
+    for a, b in zip(grads[0][2], grads[1][2]):
+        grad_close(a, b, "cond_model gradient")
