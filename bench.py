@@ -213,7 +213,6 @@ def main():
     try:
         if not a.no_graph and not a.inject_noise:
             dpf.force_resample = None
-            del graphed
             g2 = GraphedFilterStep(dpf, resident)
 
             def run_default():
@@ -231,6 +230,15 @@ def main():
     except Exception as e:
         default_path = {"error": repr(e)}
         dpf.force_resample = True
+    configs = None
+    if not a.no_extras and not a.no_graph and (a.B, a.N, a.T, a.measurement, a.resampler) == (1024, 1024, 50, "gaussian", "soft"):
+        try:     # the other BASELINE configurations (C3, C4, C5 shard), a few steps each -- every rank takes part
+            graphed = g2 = None
+            torch.cuda.empty_cache()
+            from bench_configs import extra_configs
+            configs = extra_configs(a, dev, world, timed)
+        except Exception as e:
+            configs = {"error": repr(e)}
     units = a.B * a.N * a.T * world
     if rank != 0:
         return
@@ -243,7 +251,7 @@ def main():
                    "l2": "per-step working set (particles, noise, lists: >300 MB) exceeds the 126 MB L2", "parallelism": "batch-sharded x%d%s" % (world, ", NCCL flat-gradient all-reduce per step" if world > 1 else ""),
                    "execution": "eager launches" if a.no_graph else "one CUDA graph replay per step (forward over T + loss + backward)"},
         "e2e": {"value": units * a.steps / (ms_e2e / 1e3), "unit": "particle-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "e2e_default_path": default_path,
+        "e2e_default_path": default_path, "configs": configs,
         "gpu_launches": int(launches), "clocks": clk,
     }
     try:

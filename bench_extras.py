@@ -78,9 +78,14 @@ def measured_peaks(dev):
         peaks[name] = ops[0] * mult / sec / 1e12
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
-        peaks["hbm_gbs"], peaks["hbm_source"] = json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+        mp = json.load(open(path))
+        peaks["hbm_gbs"], peaks["hbm_source"] = mp["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+        bf16 = mp.get("bf16_tflops", 1590.0)
     else:
-        peaks["hbm_gbs"], peaks["hbm_source"] = 6650.0, "fallback (B200_PROFILING.md)"
+        peaks["hbm_gbs"], peaks["hbm_source"], bf16 = 6650.0, "fallback (B200_PROFILING.md)", 1590.0
+    # dense TF32 runs at half the bf16 rate on the 5th-generation tensor cores (1.1 vs 2.25 PFLOP/s nominal): the measured
+    # cuBLAS bf16 figure / 2 is the denominator for the 3xTF32 tcgen05 / mma.sync products of the measurement kernels
+    peaks["tf32_tensor_tflops"] = bf16 / 2.0
     return peaks
 
 
@@ -102,18 +107,20 @@ def kernel_table(a, dpf, dev):
         pe = pack_parameters([dpf.particle_encoder])
     rows = []
 
-    def add(name, fwd, flops_f, bytes_f, flops_b, bytes_b, grads, per_step_f, per_step_b, sfu=0):
+    def add(name, fwd, flops_f, bytes_f, flops_b, bytes_b, grads, per_step_f, per_step_b, sfu=0, tensor_f=0, tensor_b=0):
         out = fwd()
         outs = [o for o in (out if isinstance(out, tuple) else (out,)) if o is not None and o.requires_grad]
         tf = _events(lambda: fwd(), n=5)
-        rows.append(dict(kernel=name + "_fwd", sec=tf, flops=flops_f * P, bytes=bytes_f * P, sfu_ops=sfu * P, launches_per_step=per_step_f))
+        rows.append(dict(kernel=name + "_fwd", sec=tf, flops=flops_f * P, bytes=bytes_f * P, sfu_ops=sfu * P, tensor_flops=tensor_f * P,
+                         launches_per_step=per_step_f))
         if outs:
             gouts = [grads[tuple(o.shape)] for o in outs]
 
             def bwd():
                 torch.autograd.backward(outs, gouts, retain_graph=True)
             tb = _events(bwd, n=5)
-            rows.append(dict(kernel=name + "_bwd", sec=tb, flops=flops_b * P, bytes=bytes_b * P, sfu_ops=sfu * P, launches_per_step=per_step_b))
+            rows.append(dict(kernel=name + "_bwd", sec=tb, flops=flops_b * P, bytes=bytes_b * P, sfu_ops=sfu * P, tensor_flops=tensor_b * P,
+                             launches_per_step=per_step_b))
 
     grads = {(B, N, 2): gy, (B, N): gl}
     pkc, pkd = pk_c.clone().requires_grad_(), pk_d.clone().requires_grad_()
@@ -132,7 +139,13 @@ def kernel_table(a, dpf, dev):
     def meas():
         o = ops.measure_update(per, cnf, enc, xr, lw0, gl, gl, mode, p0=p0, p1=p1)
         return o[0], o[2]
-    add("measure_update_" + mode, meas, mflop, 28, 2 * mflop, 24, grads, 1, 1)
+    # EXECUTED tensor-core FLOP per particle (3xTF32: every product is issued three times): forward = encoder layers 2-3
+    # (1536 FMA) [+ CRNVP layer 1 of 8 nets, 16 x 48 per stage pair: 4 x 768 FMA]; backward = the two recomputed forward rounds + W3^T d3 +
+    # W2^T d2 (tcgen05) + the dW2 / dW3 contractions (mma.sync), 4608 FMA.  They bound these kernels by tensor-ROUND latency, not by
+    # tensor throughput: the fraction below is what ncu's sm__pipe_tensor_cycles_active shows (19 % / 36 %, profiles/).
+    tf_f = 2 * 3 * (1536 + (3072 if mode == "CRNVP" else 0))
+    tf_b = 2 * 3 * 4608
+    add("measure_update_" + mode, meas, mflop, 28, 2 * mflop, 24, grads, 1, 1, tensor_f=tf_f, tensor_b=tf_b)
     wr = w.clone().requires_grad_()
     if a.resampler == "soft":
         add("soft_resample", lambda: ops.soft_resample(xr, wr, off, mk, 0.5)[:2], 0, 32, 0, 36, grads, 1, 1)
@@ -180,7 +193,11 @@ def roofline_and_cpu(a, dpf, resident, dev, ms_per_step):
     step_sec = ms_per_step * 1e-3 / a.T          # one filter timestep, forward + backward
     for r in rows:
         r["share_of_step"] = r["sec"] * r["launches_per_step"] / step_sec
-        if r["flops"] > 0 and r["flops"] / max(r["bytes"], 1) > 10:   # arithmetic intensity >> machine balance: compute bound
+        if r.get("tensor_flops", 0) > 0:     # tcgen05 / mma.sync kernels: executed 3xTF32 FLOP against the TF32 tensor peak
+            r["frac_fp32_algorithmic"] = r["flops"] / r["sec"] / 1e12 / peaks["fp32_tflops"]   # (round 1 reported this one: most of these
+            r.update(bound="tensor", achieved=r["tensor_flops"] / r["sec"] / 1e12, peak=peaks["tf32_tensor_tflops"],   # FMAs do not run on the FP32 pipe)
+                     unit="TFLOP/s (executed 3xTF32 tensor FLOP; peak = measured bf16 / 2)")
+        elif r["flops"] > 0 and r["flops"] / max(r["bytes"], 1) > 10:   # arithmetic intensity >> machine balance: compute bound
             f_fp32 = r["flops"] / r["sec"] / 1e12 / peaks["fp32_tflops"]
             f_sfu = r.get("sfu_ops", 0) / r["sec"] / 1e12 / peaks["sfu_tops"]
             r["frac_fp32"], r["frac_sfu"] = f_fp32, f_sfu

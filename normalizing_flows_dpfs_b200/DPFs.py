@@ -47,6 +47,8 @@ class DPF(nn.Module):
                                       # "cuda": initial cloud, motion noise and resampling offsets are drawn in-kernel (Philox,
                                       #         no per-step H2D, CUDA-graph capturable) -- SURVEY 8(f2)
         self._fired_host, self._gates = [], None
+        self.dist_group = None        # a torch.distributed group: the ESS gate then uses the mean over EVERY shard's trajectories
+                                      # (one 16-byte all-reduce per timestep) -- see distributed.py
         if getattr(args, "fast", False):   # --fast: host-free filter loop (device-side ESS gate + in-kernel random draws)
             self.rng_device = "cuda"
 
@@ -189,9 +191,16 @@ class DPF(nn.Module):
 
         for step in range(T):
             gate = None
+            if self.dist_group is not None and self.force_resample is None:
+                from .distributed import global_ess_mean
+                ess_inv = global_ess_mean(ess_inv, self.dist_group)     # (1,): the whole-batch mean over all shards
             if device_rule:
-                gate, off_dev = ops.ess_gate(ess_inv, B, N, None, rng, device_rng, soft and device_rng and "offsets" not in inj,
-                                             self._gates[step:step + 1])
+                want_off = soft and device_rng and "offsets" not in inj
+                if ess_inv.numel() == B:
+                    gate, off_dev = ops.ess_gate(ess_inv, B, N, None, rng, device_rng, want_off, self._gates[step:step + 1])
+                else:   # global mean of a sharded run: the rule on one value, then the per-trajectory offsets / counter advance
+                    gate, _ = ops.ess_gate(ess_inv, 1, N, None, None, False, False, self._gates[step:step + 1])
+                    _, off_dev = ops.ess_gate(None, B, N, True, rng, device_rng, want_off) if device_rng else (None, None)
                 fire = True        # the kernels decide
             else:
                 off_dev = None

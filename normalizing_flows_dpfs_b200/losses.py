@@ -13,7 +13,7 @@ def autoencoder_loss(image, train, encoder, decoder):
     return nn.functional.mse_loss(decoder(encoder(frames)), frames)
 
 
-def supervised_loss(particle_list, particle_weight_list, true_state, mask, train, labeledRatio=1.0):
+def supervised_loss(particle_list, particle_weight_list, true_state, mask, train, labeledRatio=1.0, group=None):
     """RMSE between the weighted particle mean and the true position (reference losses.py:18-31).  Lists that come straight from
     DPF.filtering_pos carry the per-step predictions a fused kernel already formed (sum_n w_n x_n, with backward): they are used
     instead of multiplying and reducing the (B,T,N,2) lists again."""
@@ -23,6 +23,15 @@ def supervised_loss(particle_list, particle_weight_list, true_state, mask, train
     else:
         prediction = (particle_list * particle_weight_list[..., None]).sum(dim=2)
     err2 = (prediction - true_state[:, :, :2]) ** 2
+    if group is not None:
+        # batch-sharded run (extension): the mean under the root is taken over the GLOBAL batch -- the squared-error sum is
+        # all-reduced differentiably, so every rank returns the same RMSE and backpropagates its local part of the global gradient
+        # (reduce the parameter gradients with SUM, distributed.GradBucket.allreduce(average=False))
+        from .distributed import global_sum
+        w = err2 if not train else mask[:, :, None] * err2
+        count = global_sum(torch.tensor(float(err2.numel()), device=err2.device), group)
+        mean = global_sum(w.sum(), group) / count
+        return torch.sqrt(mean if not train else mean / labeledRatio), prediction
     if not train:
         return torch.sqrt(err2.mean()), prediction
     if labeledRatio > 0:
