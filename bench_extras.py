@@ -181,9 +181,13 @@ def ot_metric(dev, peaks):
         iters = int(ops.OtResample.last_iters.item())
         pairs = B * N * N * (2 * (iters - 2) + 2 + 2 + 1)
         fwd_s = ev[0].elapsed_time(ev[1]) * 1e-3
+        # round 2: one exponential serves BOTH chains of a pass, so the kernels execute B N^2 (iters + 2) MUFU ops, about half of
+        # the algorithmic pair-evaluation count of SURVEY 8d (one exp per chain and pair): the algorithmic fraction can exceed 1
+        executed = B * N * N * ((iters - 2) + 1 + 1 + 1 + 1)
         out.append({"B": B, "N": N, "sinkhorn_iterations": iters, "fwd_us": fwd_s * 1e6, "bwd_us": ev[1].elapsed_time(ev[2]) * 1e3,
                     "pair_evals": pairs, "achieved_tops": pairs / fwd_s / 1e12, "sfu_peak_tops": peaks["sfu_tops"],
-                    "frac_of_sfu_peak": pairs / fwd_s / 1e12 / peaks["sfu_tops"]})
+                    "frac_of_sfu_peak": pairs / fwd_s / 1e12 / peaks["sfu_tops"], "mufu_ops_executed": executed,
+                    "frac_sfu_executed": executed / fwd_s / 1e12 / peaks["sfu_tops"]})
     return out
 
 
