@@ -47,6 +47,9 @@ class DPF(nn.Module):
                                       # "cuda": initial cloud, motion noise and resampling offsets are drawn in-kernel (Philox,
                                       #         no per-step H2D, CUDA-graph capturable) -- SURVEY 8(f2)
         self._fired_host, self._gates = [], None
+        self.hoist_encoder = bool(getattr(args, "hoist_encoder", False))   # ONE encoder call on all B*T frames before
+                                      # the loop instead of T calls on B frames (DPFs.py:177).  Identical in eval mode; in train
+                                      # mode BatchNorm then normalises with B*T-frame batch statistics instead of per-step ones.
         self.dist_group = None        # a torch.distributed group: the ESS gate then uses the mean over EVERY shard's trajectories
                                       # (one 16-byte all-reduce per timestep) -- see distributed.py
         if getattr(args, "fast", False):   # --fast: host-free filter loop (device-side ESS gate + in-kernel random draws)
@@ -184,6 +187,9 @@ class DPF(nn.Module):
         self._gates = torch.empty(T, dtype=torch.int32, device=dev) if device_rule else None
         self._fired_host = None if device_rule else []
         identity_idx = None
+        enc_all = None
+        if self.hoist_encoder and not isinstance(self.encoder, nn.Identity):
+            enc_all = self.encoder(obs.reshape((B * T,) + tuple(obs.shape[2:])).float()).reshape(B, T, -1)
 
         def put(key, step, t):   # data the kernels could not write in place (non-fused paths) is copied into the list buffer
             if t.data_ptr() != buf[key][step].data_ptr():
@@ -231,7 +237,7 @@ class DPF(nn.Module):
                         identity_idx = torch.arange(B * N, device=dev, dtype=torch.int64).reshape(B, N)
                     buf["index"][step].copy_(identity_idx)
             noise = inj["noise"][:, step] if "noise" in inj else None
-            encodings = self.encoder(obs[:, step].float())
+            encodings = enc_all[:, step] if enc_all is not None else self.encoder(obs[:, step].float())
             if fused:
                 # ---- fused step: 6 libnfdpf launches (motion+moments, 3 coupling stacks, densities, measurement+update)
                 if noise is None and not device_rng:

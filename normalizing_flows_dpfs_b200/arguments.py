@@ -62,6 +62,8 @@ _FLAGS = [
     # extension (not in the reference): host-free filter loop -- device-side ESS gate and in-kernel Philox draws instead of the
     # CPU generator (statistically equivalent, not the reference's random stream)
     (("--fast",), dict(action="store_true", default=False)),
+    # extension: run the image encoder once on all B*T frames before the filter loop
+    (("--hoist-encoder",), dict(dest="hoist_encoder", action="store_true", default=False)),
 ]
 
 

@@ -513,24 +513,30 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
     }
 }
 
-// d_packed[target] = fixed-order fp64 column sums of the per-warp rows and the per-CTA row-context partials.  A block owns 32
-// consecutive columns (coalesced 128-byte row segments); its 8 warps take the rows round-robin and the partial sums are added
-// in warp order -- the order depends only on the launch geometry: run-to-run deterministic.
-__global__ void d2_reduce_kernel(const float* __restrict__ warp_rows, int n_rows, const float* __restrict__ ctx_rows, int n_cta,
+// d_packed[target] = fixed-order fp64 column sums of the per-CTA rows and the per-CTA row-context partials.  A block owns 32
+// consecutive columns (coalesced 128-byte row segments); its 32 warps take the rows round-robin (<= 5 independent loads per
+// thread: the kernel is one round trip to L2 long) and the partial sums are added in warp order -- the order depends only on
+// the launch geometry: run-to-run deterministic.
+constexpr int RED_G = 32;      // row groups per block of the reduce kernel (32 columns x 32 groups = 1024 threads)
+__global__ void __launch_bounds__(32 * RED_G)
+d2_reduce_kernel(const float* __restrict__ warp_rows, int n_rows, const float* __restrict__ ctx_rows, int n_cta,
                                  int n_fcnn, int C_row, float* __restrict__ d_packed) {
-    __shared__ double s_sum[8][32];
+    __shared__ double s_sum[RED_G][32];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int fin = 1 + C_row, pf = packed_fcnn_size(1, C_row), C1 = C_row + 1;
     const int n_acc = n_fcnn * NACC, n_ctx = n_fcnn * H * C1;
     const int col = blockIdx.x * 32 + lane;                 // column of [warp rows | ctx rows]
     double a = 0.0;
-    if (col < n_acc) { for (int r = grp; r < n_rows; r += 8) a += (double)warp_rows[(size_t)r * n_acc + col]; }
-    else if (col < n_acc + n_ctx) { for (int r = grp; r < n_cta; r += 8) a += (double)ctx_rows[(size_t)r * n_ctx + (col - n_acc)]; }
+    const bool is_acc = col < n_acc, is_ctx = !is_acc && col < n_acc + n_ctx;
+    const float* src = is_acc ? warp_rows + col : ctx_rows + (col - n_acc);
+    const int stride = is_acc ? n_acc : n_ctx, count = is_acc ? n_rows : (is_ctx ? n_cta : 0);
+#pragma unroll 4
+    for (int r = grp; r < count; r += RED_G) a += (double)src[(size_t)r * stride];   // independent loads, few per thread
     s_sum[grp][lane] = a;
     __syncthreads();
     if (grp != 0 || col >= n_acc + n_ctx) return;
 #pragma unroll
-    for (int g = 1; g < 8; ++g) a += s_sum[g][lane];
+    for (int g = 1; g < RED_G; ++g) a += s_sum[g][lane];      // groups in order: deterministic
     int target;
     float scale;
     if (col < n_acc) {                                      // accumulator entry e of net f (b1 block: produced by the ctx partials)
@@ -575,7 +581,7 @@ static int launch_cfg(const float* packed, int n_flows, int C_row, const float* 
     int rc = check_launch("coupling_bwd_d2");
     if (rc) return rc;
     const int n_cols = n_fcnn * NACC + n_fcnn * H * (C_row + 1);
-    d2_reduce_kernel<<<(n_cols + 31) / 32, 256, 0, st>>>(cta_rows, grid, ctx_rows, grid, n_fcnn, C_row, d_packed);
+    d2_reduce_kernel<<<(n_cols + 31) / 32, 32 * RED_G, 0, st>>>(cta_rows, grid, ctx_rows, grid, n_fcnn, C_row, d_packed);
     return check_launch("d2_reduce");
 }
 

@@ -77,9 +77,11 @@ ot_prepare_kernel(const float* __restrict__ x, int N, float2* __restrict__ sx, f
 // exponentials and ~12 FP32 instructions of the per-chain online LSE it replaces.  A thread owns OT_R rows, so a staged column
 // (one broadcast LDS.128 = 4 cycles of the SM's shared-memory return path) serves OT_R pairs: without the row blocking the
 // LDS, not the MUFU pipe, would bound the loop.  Range: the j = i column always contributes K = 1, so a row's sum can only
-// underflow entirely if z_i lies more than 126 below the tile maximum in log2 units (87 nats; the filter's weights span 28
-// nats and the potentials ~cost/eps <= 40); such a row is recomputed with the per-row online LSE (ot_safe_row).
+// underflow if z_i lies ~100 below the tile maximum in log2 units (69 nats; the filter's weights span 28 nats, the potentials
+// ~cost/eps: clouds with far outliers at the final eps do get there); such a row is recomputed with the per-row online LSE
+// (ot_safe_row, two exponentials per pair straight from global memory: exact but ~10x slower for that row).
 constexpr int OT_R = 4;        // rows per thread in the pass kernel
+constexpr float OT_TINY = 1e-30f;   // ~2^-100: every term within 2^-24 of such a sum is still a normal fp32 number
 
 __device__ __forceinline__ unsigned long long ot_pack2(float lo, float hi) {
     unsigned long long p;
@@ -200,7 +202,8 @@ ot_pass_kernel(const float2* __restrict__ sx, const float* __restrict__ logw, co
         float s1, s2;
         asm("mov.b64 {%0, %1}, %2;" : "=f"(s1), "=f"(s2) : "l"(acc[r]));
         float lse1 = R1 + lg2f(s1), lse2 = R2 + lg2f(s2);
-        if (live && !(s1 > 0.f && s2 > 0.f && s1 < INFINITY && s2 < INFINITY))      // whole row under / overflowed: safe path
+        // A sum below OT_TINY has lost its leading terms to underflow (and lg2.approx.ftz maps a denormal sum to -inf): safe path
+        if (live && !(s1 > OT_TINY && s2 > OT_TINY && s1 < INFINITY && s2 < INFINITY))
             ot_safe_row<MODE>(sx, logw, a_old, b_old, row, N, i, inv, c2, log_beta, lse1, lse2);
         const float sm1 = -eps * LN2 * lse1, sm2 = -eps * LN2 * lse2;               // softmin = -eps * LSE
         if (MODE != 1) {
@@ -307,7 +310,7 @@ ot_colnorm_kernel(const float2* __restrict__ sx, const float* __restrict__ logw,
         if (j >= N) continue;
         float lse2 = R + lg2f(acc[r]);   // log2-domain LSE_i(f_i/eps - C_ij/eps); g_j/eps cancels inside U
         const float2 xj = sx[row + j];
-        if (!(acc[r] > 0.f && acc[r] < INFINITY)) {      // whole column under / overflowed: per-column online LSE
+        if (!(acc[r] > OT_TINY && acc[r] < INFINITY)) {      // sum (nearly) underflowed: per-column online LSE
             float m = -INFINITY, sacc = 0.f;
             for (int i = 0; i < N; ++i) {
                 const float2 p = sx[row + i];

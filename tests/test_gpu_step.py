@@ -180,3 +180,21 @@ def test_fused_prediction_equals_the_list_formula():
     close(grads[0][1], grads[1][1], rtol=1e-5, atol=1e-4, what="predictions")
     for a, b in zip(grads[0][2], grads[1][2]):
         grad_close(a, b, "cond_model gradient")
+
+
+def test_ot_far_outlier_row_takes_the_safe_path(golden):
+    """A cloud with a far outlier (scaled extent 8.5, met in a C5-shaped run): at the final eps the column exponents span hundreds of
+    log2 units, the shared-exponential sums of most rows underflow and must be recomputed by the per-row online LSE -- the first
+    version of the round-2 pass kernel turned such a row into NaNs (a denormal sum passed `> 0`, lg2.approx.ftz mapped it to -inf).
+    Oracle (fp64): never converges below the threshold, runs to max_iter."""
+    G = golden("ot_outlier")
+    x, lw = cu(G["x"])[None].contiguous(), cu(G["logw"])[None].contiguous()
+    out = ops.ot_resample(x, lw)
+    assert int(ops.OtResample.last_iters.item()) == int(G["iters"]) == 101
+    assert bool(torch.isfinite(out).all())
+    close(out[0], G["p_oracle"], rtol=1e-4, atol=1e-4 * float(np.abs(G["p_oracle"]).max()), what="OT particles, outlier row")
+    # the same row inside a batch must not disturb its neighbours' stop rule bookkeeping: finite everywhere
+    g = torch.Generator().manual_seed(0)
+    xb = torch.cat([x, cu(torch.randn(3, 1024, 2, generator=g) * 20)])
+    lwb = torch.cat([lw, cu(torch.log_softmax(torch.randn(3, 1024, generator=g), -1))])
+    assert bool(torch.isfinite(ops.ot_resample(xb, lwb)).all())

@@ -104,3 +104,26 @@ def test_device_rng_path_runs_and_is_seed_reproducible():
     assert torch.equal(runs[0], runs[1]) and torch.isfinite(runs[0]).all()
     noise = out[2]
     assert abs(float(noise.std()) - 20.0) < 1.0            # N(0, pos_noise^2) drawn on the device
+
+
+def test_encoder_hoist_is_exact_in_eval_mode_and_trains():
+    """one encoder call on all B*T frames == T calls on B frames when BatchNorm uses its running statistics."""
+    torch.manual_seed(0)
+    B, N, T = 3, 64, 4
+    dpf = DPF(parse_args(["--NF-dyn", "--NF-cond", "--measurement", "gaussian", "--resampler_type", "soft", "--num-particles", str(N),
+                          "--batchsize", str(B), "--sequence-length", str(T)])).cuda()
+    g = torch.Generator().manual_seed(1)
+    obs = torch.rand(B, T, 3, 128, 128, generator=g).cuda()
+    start, vel_in = (torch.randn(B, 4, generator=g) * 10).cuda(), (torch.randn(B, T, 2, generator=g) * 3).cuda()
+    dpf.injected = dict(init_particles=(torch.rand(B, N, 2, generator=g) * 128 - 64).cuda(), noise=(torch.randn(B, T, N, 2, generator=g) * 20).cuda(),
+                        offsets=(torch.rand(B, T, generator=g) / N).cuda())
+    dpf.eval()
+    with torch.no_grad():
+        ref = dpf.filtering_pos(obs, start, vel_in)
+        dpf.hoist_encoder = True
+        out = dpf.filtering_pos(obs, start, vel_in)
+    assert torch.allclose(out[0], ref[0], rtol=1e-4, atol=1e-3) and torch.allclose(out[1], ref[1], rtol=1e-3, atol=1e-7)
+    dpf.train()
+    res = dpf.filtering_pos(obs, start, vel_in)
+    supervised_loss(res[0], res[1], torch.randn(B, T, 4, generator=g).cuda(), 1.0, False)[0].backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in dpf.encoder.parameters())
