@@ -192,6 +192,21 @@ int nfdpf_weighted_mean_fwd(const float* particles, const float* probs, int B, i
 int nfdpf_weighted_mean_bwd(const float* g_pred, const float* particles, const float* probs, int B, int N, int d,
                             float* d_particles, float* d_probs, void* stream);
 
+/* ---- block pseudo-likelihood of the semi-supervised objective (losses.py:37-70 compute_block_density_nf; the prior term of
+ * losses.py:73-106 compute_block_density is formed by the caller).  Lists are (B,T,N) with the last dimension contiguous and
+ * arbitrary element strides sb (between trajectories) / st (between steps): the filter's (T,B,N) buffers are read in place.
+ * idx holds the FLAT ancestor indices (j + N*b) the resamplers return.  Q (B,) = (1/nb) sum_{blocks} sum_n w[b,k,n] logyita_k[b,n],
+ * nb = T / block_len, logyita running over blocks WITHOUT a reset (as the reference).  run_saved (nb,B,N): logyita per block
+ * (the backward's input).  bad: device int32, OR-ed with 1 if an ancestor lies in another trajectory (the backward supports only
+ * own-row ancestry, which is what every resampler produces), 2 if an index is out of range.
+ * backward: gQ (B,) -> d_w, d_lik, d_prior, each (B,T,N) written completely, with element strides o_sb / o_st. */
+int nfdpf_block_density_fwd(const float* w, int64_t w_sb, int64_t w_st, const float* lik, int64_t l_sb, int64_t l_st,
+                            const float* prior, int64_t p_sb, int64_t p_st, const int64_t* idx, int64_t i_sb, int64_t i_st,
+                            int B, int T, int N, int block_len, float* Q, float* run_saved, int32_t* bad, void* stream);
+int nfdpf_block_density_bwd(const float* gQ, const float* w, int64_t w_sb, int64_t w_st, const int64_t* idx, int64_t i_sb,
+                            int64_t i_st, const float* run_saved, int B, int T, int N, int block_len, float* d_w, float* d_lik,
+                            float* d_prior, int64_t o_sb, int64_t o_st, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

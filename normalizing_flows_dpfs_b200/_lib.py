@@ -33,6 +33,8 @@ SIGNATURES = {
     "nfdpf_init_particles_rng": (_I, [_P, _I, _P, _F, _I, _I, _I, _I, _P, _P]),
     "nfdpf_weighted_mean_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "nfdpf_weighted_mean_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "nfdpf_block_density_fwd": (_I, [_P, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "nfdpf_block_density_bwd": (_I, [_P, _P, _I64, _I64, _P, _I64, _I64, _P, _I, _I, _I, _I, _P, _P, _P, _I64, _I64, _P]),
     "nfdpf_peak_probe": (_I64, [_I, _I, _P, _P]),
     "nfdpf_coupling_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "nfdpf_coupling_bwd_workspace": (_I64, [_I, _I, _I, _I, _I, _I]),

@@ -1,5 +1,7 @@
-"""Losses consuming the per-step lists of the filter (reference losses.py).  Run once per batch after the filter
-loop -- outside the hot path -- so they stay plain PyTorch on the device tensors."""
+"""Losses consuming the per-step lists of the filter (reference losses.py), run once per batch after the filter loop.
+On the device both hot ones are kernels: the supervised loss picks up the per-step predictions a fused kernel formed inside the
+loop, the block pseudo-likelihood is one launch that walks the ancestry of every block (csrc/losses.cu).  Lists on the CPU
+(oracle-style checks of the mirror against the reference, no GPU involved) take the reference's own gather chain."""
 import math
 
 import torch
@@ -59,6 +61,9 @@ def _trace_blocks(weights, seq_len, block_len, terms_at):
 
 def compute_block_density_nf(particle_weight_list, noise_list, likelihood_list, index_list, jac_list, prior_list, block_len=10):
     B, T, N = particle_weight_list.shape
+    if particle_weight_list.is_cuda:
+        from . import ops
+        return ops.block_density(particle_weight_list, likelihood_list, prior_list, index_list, block_len)
 
     def terms_at(j, anc):
         lik, prior, idx = likelihood_list[:, j, :], prior_list[:, j, :], index_list[:, j, :]
@@ -72,6 +77,12 @@ def compute_block_density_nf(particle_weight_list, noise_list, likelihood_list, 
 def compute_block_density(particle_weight_list, noise_list, likelihood_list, index_list, block_len=10, std_pos=1.0, std_vel=1.0):
     B, T, N = particle_weight_list.shape
     log_c = -0.5 * math.log(2 * math.pi)
+    if particle_weight_list.is_cuda:
+        from . import ops
+        pos, vel = noise_list[..., :2], noise_list[..., 2:]
+        log_prior = (2 * log_c - 2 * math.log(std_pos) - (pos ** 2 / (2 * std_pos ** 2)).sum(-1)) + \
+                    (2 * log_c - 2 * math.log(std_vel) - (vel ** 2 / (2 * std_vel ** 2)).sum(-1))
+        return ops.block_density(particle_weight_list, likelihood_list, log_prior, index_list, block_len)
 
     def terms_at(j, anc):
         lik, idx = likelihood_list[:, j, :], index_list[:, j, :]

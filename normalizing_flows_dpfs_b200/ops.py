@@ -346,6 +346,61 @@ def weighted_mean(particles, probs, out=None):
     return WeightedMean.apply(particles, probs, out)
 
 
+def _list3(t, dtype):
+    """(tensor, sb, st) of a (B,T,N) list whose rows the kernels can read in place (last dimension contiguous); the transposed
+    views of the filter's (T,B,N) buffers qualify, anything else is copied once."""
+    if not t.is_cuda:
+        raise RuntimeError("libnfdpf has no CPU path: tensor is on %s" % t.device)
+    t = t.detach()
+    if t.dtype != dtype or t.stride(2) != 1:
+        t = t.to(dtype).contiguous()
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError("libnfdpf: tensor lives on cuda:%d but the current device is cuda:%d" % (t.device.index, torch.cuda.current_device()))
+    return t, t.stride(0), t.stride(1)
+
+
+class BlockDensity(torch.autograd.Function):
+    """Q (B,) of compute_block_density_nf (reference losses.py:37-70): one launch walks the ancestry of every block; the backward
+    pushes the block-end weights down the (sorted) ancestor runs in a fixed order."""
+
+    @staticmethod
+    def forward(ctx, weights, lik, prior, index, block_len):
+        B, T, N = weights.shape
+        w, wsb, wst = _list3(weights, torch.float32)
+        l, lsb, lst = _list3(lik, torch.float32)
+        p, psb, pst = _list3(prior, torch.float32)
+        i, isb, ist = _list3(index, torch.int64)
+        nb = T // block_len
+        Q = torch.empty(B, device=w.device, dtype=torch.float32)
+        run = torch.empty(max(nb, 1), B, N, device=w.device, dtype=torch.float32)
+        bad = torch.zeros(1, device=w.device, dtype=torch.int32)
+        L.call("nfdpf_block_density_fwd", w.data_ptr(), wsb, wst, l.data_ptr(), lsb, lst, p.data_ptr(), psb, pst, i.data_ptr(), isb, ist,
+               B, T, N, int(block_len), L.ptr(Q), L.ptr(run), L.ptr(bad), L.stream())
+        ctx.save_for_backward(w, i, run, bad)
+        ctx.block_len = int(block_len)
+        return Q
+
+    @staticmethod
+    def backward(ctx, gQ):
+        w, i, run, bad = ctx.saved_tensors
+        B, T, N = w.shape
+        if not torch.cuda.is_current_stream_capturing():
+            flag = int(bad.item())
+            if flag & 2:
+                raise ValueError("block density: ancestor index out of range [0, B*N)")
+            if flag & 1:
+                raise RuntimeError("block density backward: an ancestor index points into another trajectory (unsupported)")
+        # gradients as (T,B,N) buffers: ListView's backward hands contiguous (B,N) slices to the step kernels
+        d_w, d_l, d_p = (torch.empty(T, B, N, device=w.device, dtype=torch.float32) for _ in range(3))
+        L.call("nfdpf_block_density_bwd", L.ptr(L.f32(gQ)), w.data_ptr(), w.stride(0), w.stride(1), i.data_ptr(), i.stride(0), i.stride(1),
+               L.ptr(run), B, T, N, ctx.block_len, L.ptr(d_w), L.ptr(d_l), L.ptr(d_p), N, B * N, L.stream())
+        return d_w.transpose(0, 1), d_l.transpose(0, 1), d_p.transpose(0, 1), None, None
+
+
+def block_density(weights, lik, prior, index, block_len):
+    return BlockDensity.apply(weights, lik, prior, index, block_len)
+
+
 class MotionMoments(torch.autograd.Function):
     """x' = (x + vel_b) + noise (model/models.py:191-204); writes the detached [mean | std] context of x' into ctx.
     noise given: injected draws (parity tests).  noise None: drawn in-kernel from rng_state (Philox) as sigma N(0,1) and

@@ -455,3 +455,42 @@ def supervised_rmse(particle_list, probs_list, true_xy):
     """supervised_loss with mask=1 / eval branch, losses.py:18-31."""
     pred = torch.sum(particle_list * probs_list[..., None], dim=2)
     return torch.sqrt(torch.mean((pred - true_xy) ** 2)), pred
+
+
+# ----------------------------------------------------------------------------------------
+# Semi-supervised objective: block pseudo-likelihood (losses.py:33-70, 73-110)
+# ----------------------------------------------------------------------------------------
+def block_density(weights, lik, prior, index, block_len: int):
+    """compute_block_density_nf, losses.py:37-70, written per trajectory-particle instead of as (B*N,) gather chains:
+    for the end k of every block each particle follows its flat ancestor pointer back through the block and adds the
+    prior + likelihood terms it meets (losses.py:51-64); the running sum is never reset between blocks (losses.py:47, 64);
+    Q[b] = mean over blocks of sum_n w[b,k,n] * running[b,n] (losses.py:65-68).  weights / lik / prior (B,T,N), index (B,T,N)
+    flat int64 ancestors (j + N*b).  Differentiable (torch) in weights, lik and prior."""
+    B, T, N = weights.shape
+    flat = lambda lst, j: lst[:, j, :].reshape(B * N)
+    running = torch.zeros(B, N, dtype=weights.dtype)
+    Q = torch.zeros(B, dtype=weights.dtype)
+    n_blocks = 0
+    for k in range(block_len - 1, T, block_len):
+        pos = torch.arange(B * N)                           # where each walker currently stands (flat)
+        for j in range(k, k - block_len, -1):
+            running = (running + flat(prior, j)[pos].reshape(B, N)) + flat(lik, j)[pos].reshape(B, N)
+            pos = flat(index, j)[pos]
+        Q = Q + (weights[:, k, :] * running).sum(-1)
+        n_blocks += 1
+    return Q / n_blocks
+
+
+def block_prior_from_noise(noise, std_pos: float, std_vel: float):
+    """log-prior term of compute_block_density, losses.py:93-96: two diagonal Gaussians over noise[..., :2] and noise[..., 2:]
+    (the second sum is empty when the noise has two columns)."""
+    log_c = -0.5 * math.log(2 * math.pi)
+    pos, vel = noise[..., :2], noise[..., 2:]
+    return (2 * log_c - 2 * math.log(std_pos) - (pos ** 2 / (2 * std_pos ** 2)).sum(-1)) + \
+           (2 * log_c - 2 * math.log(std_vel) - (vel ** 2 / (2 * std_vel ** 2)).sum(-1))
+
+
+def supervised_loss_train(particle_list, probs_list, true_state, mask, labeled_ratio: float = 1.0):
+    """supervised_loss, train branch with a label mask, losses.py:18-27."""
+    pred = torch.sum(particle_list * probs_list[..., None], dim=2)
+    return torch.sqrt(torch.mean(mask[:, :, None] * (pred - true_state[:, :, :2]) ** 2) / labeled_ratio), pred

@@ -305,6 +305,59 @@ def gen_init():
     np.savez_compressed(os.path.join(OUT, "init.npz"), **out)
 
 
+def gen_losses():
+    """losses.py: block pseudo-likelihood (NF and plain variants) and the masked supervised loss, with gradients."""
+    import losses as ref_losses
+    out = {}
+    cases = [(3, 20, 16, 10, "sorted"), (2, 25, 64, 5, "sorted"), (4, 12, 33, 4, "mixed"), (2, 7, 8, 10, "sorted"), (2, 10, 12, 5, "shuffled")]
+    for ci, (B, T, N, bl, kind) in enumerate(cases):
+        g = torch.Generator().manual_seed(900 + ci)
+        w = torch.softmax(torch.randn(B, T, N, generator=g) * 2, -1)
+        lik = torch.randn(B, T, N, generator=g)
+        prior = torch.randn(B, T, N, generator=g) * 3 - 4
+        jac = torch.randn(B, T, N, generator=g)
+        noise = torch.randn(B, T, N, 4, generator=g)
+        idx = torch.empty(B, T, N, dtype=torch.int64)
+        for b in range(B):
+            for t in range(T):
+                if kind == "shuffled":
+                    a = torch.randint(0, N, (N,), generator=g)
+                elif kind == "mixed" and t % 3 == 0:
+                    a = torch.arange(N)                       # gate closed: identity ancestors
+                else:                                         # what soft resampling returns: sorted, with repeats
+                    a = torch.sort(torch.multinomial(w[b, t], N, replacement=True, generator=g)).values
+                idx[b, t] = a + N * b
+        ww, ll, pp, nn = (x.clone().requires_grad_() for x in (w, lik, prior, noise))
+        Q = ref_losses.compute_block_density_nf(ww, None, ll, idx, jac, pp, bl) if T >= bl else None
+        gq = torch.randn(B, generator=g)
+        if Q is not None:
+            (Q * gq).sum().backward()
+            loss = ref_losses.pseudolikelihood_loss_nf(w, None, lik, idx, jac, prior, bl)
+            Q2 = ref_losses.compute_block_density(w, nn, ll.detach(), idx, bl, 2.0, 0.5)
+            (Q2 * gq).sum().backward()
+        else:   # no complete block: the reference divides 0 by 0 blocks
+            Q, loss, Q2 = torch.zeros(0), torch.zeros(()), torch.zeros(0)
+        z = torch.zeros
+        out.update({f"c{ci}_{k}": v for k, v in npy(dict(
+            block_len=bl, w=w, lik=lik, prior=prior, noise=noise, idx=idx, gq=gq, Q=Q, loss_nf=loss, Q_plain=Q2,
+            d_w=ww.grad if ww.grad is not None else z(0), d_lik=ll.grad if ll.grad is not None else z(0),
+            d_prior=pp.grad if pp.grad is not None else z(0), d_noise=nn.grad if nn.grad is not None else z(0))).items()})
+    out["n_cases"] = len(cases)
+    # supervised loss, train branch with a label mask (losses.py:18-27)
+    g = torch.Generator().manual_seed(990)
+    B, T, N = 4, 6, 32
+    x = (torch.randn(B, T, N, 2, generator=g) * 10).requires_grad_()
+    w = torch.softmax(torch.randn(B, T, N, generator=g), -1).requires_grad_()
+    state = torch.randn(B, T, 4, generator=g) * 10
+    mask = (torch.rand(B, T, generator=g) < 0.6).float()
+    loss, pred = ref_losses.supervised_loss(x, w, state, mask, True, labeledRatio=0.6)
+    loss.backward()
+    loss_eval, _ = ref_losses.supervised_loss(x.detach(), w.detach(), state, 1.0, False)
+    out.update({f"sup_{k}": v for k, v in npy(dict(x=x, w=w, state=state, mask=mask, loss=loss, pred=pred, d_x=x.grad, d_w=w.grad,
+                                                    loss_eval=loss_eval)).items()})
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
+
+
 def gen_state_dict():
     """state_dict keys + shapes of the reference DPF for the accelerated configurations (checkpoint compatibility)."""
     import json
@@ -321,8 +374,8 @@ def gen_state_dict():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["soft", "flows", "glue", "ot", "filter", "state_dict", "init"]
+    which = sys.argv[1:] or ["soft", "flows", "glue", "ot", "filter", "state_dict", "init", "losses"]
     sys.argv = sys.argv[:1]
     for w in which:
-        {"soft": gen_soft, "flows": gen_flows, "glue": gen_glue, "ot": gen_ot, "filter": gen_filter, "state_dict": gen_state_dict, "init": gen_init}[w]()
+        {"soft": gen_soft, "flows": gen_flows, "glue": gen_glue, "ot": gen_ot, "filter": gen_filter, "state_dict": gen_state_dict, "init": gen_init, "losses": gen_losses}[w]()
         print("wrote", w)
