@@ -1,6 +1,8 @@
 // (K3) Soft resampling -- one CTA per trajectory: mixture weights, ATen-order row sum, fp64 block scan,
 // binary search of the caller's markers, gather, renormalise.  Replaces resamplers/resamplers.py:20-60, whose
 // (B,N,N) bool compare (1 GiB at B=N=1024) is never materialised here.  HBM-bound: 32 B / particle forward.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nfdpf {
@@ -304,6 +306,353 @@ soft_resample_bwd_kernel(const float* __restrict__ g_particles, const float* __r
         for (int j = tid; j < N; j += nt) d_probs[base + j] += alpha_f * t3;
 }
 
+// =====================================================================================================================
+// Fast path (round 2): N % 4 == 0, N <= 4096, d == 2.  The kernels above spend 334 instructions per particle (binary search:
+// ~100; run-time-strided loops: addressing, compares and branches around every access) and were ISSUE-bound at 0.28 / 0.21 of
+// the HBM roof.  Here a thread owns FOUR CONSECUTIVE particles for the whole kernel: every global access is a 128-bit load /
+// store, the mixture weights / scan prefixes / ancestor keys stay in registers, and the marker search is INVERTED:
+//   count_i = #{j : cum_j < m_i}  =  #{j : f_j <= i}   with   f_j = min{i : m_i > cum_j}
+// (markers m_i = fl(off + mk_i) are non-decreasing).  f_j comes from one multiply (j's position among N equally spaced markers)
+// plus an exact fix-up against the caller's marker values; a shared-memory histogram of the f_j and one integer block scan
+// give every count -- no per-particle search loop.  Same arithmetic, same bits as the generic kernel and the reference.
+constexpr int V4_MAX_N = 4096;
+
+__device__ __forceinline__ float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4f(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+soft_resample_fwd4_kernel(const float* __restrict__ particles, const float* __restrict__ probs,
+                          const float* __restrict__ offsets, const float* __restrict__ markers, float alpha_f,
+                          float one_minus_alpha_f, int hard, int N, float* __restrict__ particles_out,
+                          float* __restrict__ probs_out, int64_t* __restrict__ idx_out, float* __restrict__ saved,
+                          float* __restrict__ logprobs_out, const int* __restrict__ gate) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_q = reinterpret_cast<float*>(smem_raw);    // [N] q for the ATen-order row sum; then the histogram of f_j
+    int* s_hist = reinterpret_cast<int*>(smem_raw);
+    float* s_wis = s_q + N;                             // [N] importance weights w / q
+    float* s_mk = s_wis + N;                            // [N] the caller's markers
+    __shared__ double s_wd[32];
+    __shared__ int s_wi[32];
+    __shared__ float s_red[33];
+    __shared__ float s_sum;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int e0 = 4 * tid;
+    const bool act = e0 < N;
+    const size_t base = (size_t)b * N + (act ? e0 : 0);
+    if (gate && *gate == 0) {   // ESS gate closed (DPFs.py:168-170): pass through, identity ancestors
+        if (act) {
+            const float4 w = ld4f(probs + base);
+            const float4 x0 = ld4f(particles + base * 2), x1 = ld4f(particles + base * 2 + 4);
+            *reinterpret_cast<float4*>(particles_out + base * 2) = x0;
+            *reinterpret_cast<float4*>(particles_out + base * 2 + 4) = x1;
+            *reinterpret_cast<float4*>(probs_out + base) = w;
+            longlong2* io = reinterpret_cast<longlong2*>(idx_out + base);
+            io[0] = make_longlong2((long long)base, (long long)base + 1);
+            io[1] = make_longlong2((long long)base + 2, (long long)base + 3);
+            if (logprobs_out) st4f(logprobs_out + base, logf(w.x), logf(w.y), logf(w.z), logf(w.w));
+        }
+        if (tid == 0) { saved[2 * b] = 1.f; saved[2 * b + 1] = 1.f; }
+        return;
+    }
+    const float unif = __fdiv_rn(1.0f, (float)N);                  // ones/N, resamplers.py:26
+    const float uterm = __fmul_rn(unif, one_minus_alpha_f);        // uniform_probs*(1-alpha), :31
+    float w[4] = {0.f, 0.f, 0.f, 0.f}, q[4], mk[4] = {0.f, 0.f, 0.f, 0.f};
+    if (act) {
+        const float4 w4 = ld4f(probs + base), m4 = ld4f(markers + e0);
+        w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+        mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) q[u] = hard ? w[u] : __fadd_rn(__fmul_rn(w[u], alpha_f), uterm);
+    if (act) { st4f(s_q + e0, q[0], q[1], q[2], q[3]); st4f(s_mk + e0, mk[0], mk[1], mk[2], mk[3]); }
+    __syncthreads();
+    float S = 1.0f, wis[4];
+    if (!hard) {
+        if (tid < 32) {
+            const float s = aten_row_sum_warp(s_q, N);
+            if (tid == 0) s_sum = s;
+        }
+        __syncthreads();
+        S = s_sum;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            q[u] = __fdiv_rn(q[u], S);                             // q / q.sum, :33
+            wis[u] = __fdiv_rn(w[u], q[u]);                        // w / q, :34
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wis[u] = unif;                 // hard resampling, :36-38
+        __syncthreads();                                           // (s_q is about to become the histogram)
+    }
+    if (act) {
+        st4f(s_wis + e0, wis[0], wis[1], wis[2], wis[3]);
+        *reinterpret_cast<int4*>(s_hist + e0) = make_int4(0, 0, 0, 0);
+    }
+    // cumsum (:45): fp64 running sums, every prefix rounded to fp32 (exact in fp64, see scan_fp64_inplace)
+    float cum[4];
+    {
+        double p[4];
+        p[0] = act ? (double)q[0] : 0.0;
+#pragma unroll
+        for (int u = 1; u < 4; ++u) p[u] = p[u - 1] + (act ? (double)q[u] : 0.0);
+        double inc = p[3];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_wd[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const double t = lane < nwarp ? s_wd[lane] : 0.0;
+            double wi = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(FULL, wi, o);
+                if (lane >= o) wi += v;
+            }
+            if (lane < nwarp) s_wd[lane] = wi - t;
+        }
+        __syncthreads();
+        const double ex = s_wd[warp] + (inc - p[3]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cum[u] = (float)(ex + p[u]);
+    }
+    // f_j = number of markers m_i <= cum_j, for the sorted prefix j < N - 1 (cum[N-1] = 1 is handled below, :47)
+    const float off = offsets[b], Nf = (float)N;
+    if (act) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (e0 + u >= N - 1) continue;
+            const float c = cum[u];
+            int g = (int)floorf((c - off) * Nf) + 1;
+            g = max(0, min(g, N));
+            while (g < N && !(__fadd_rn(off, s_mk[g]) > c)) ++g;           // m_g <= c: the first marker above c lies further right
+            while (g > 0 && __fadd_rn(off, s_mk[g - 1]) > c) --g;
+            if (g < N) atomicAdd(&s_hist[g], 1);
+        }
+    }
+    __syncthreads();
+    int cnt[4];
+    {
+        int4 h = act ? *reinterpret_cast<const int4*>(s_hist + e0) : make_int4(0, 0, 0, 0);
+        cnt[0] = h.x; cnt[1] = cnt[0] + h.y; cnt[2] = cnt[1] + h.z; cnt[3] = cnt[2] + h.w;
+        int inc = cnt[3];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_wi[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int t = lane < nwarp ? s_wi[lane] : 0;
+            int wi = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, wi, o);
+                if (lane >= o) wi += v;
+            }
+            if (lane < nwarp) s_wi[lane] = wi - t;
+        }
+        __syncthreads();
+        const int ex = s_wi[warp] + (inc - cnt[3]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cnt[u] += ex;
+    }
+    float v[4] = {0.f, 0.f, 0.f, 0.f}, part = 0.f;
+    float2 x[4];
+    int jj[4];
+    if (act) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float m = __fadd_rn(off, mk[u]);                         // :44
+            jj[u] = min(cnt[u] + (m > 1.0f ? 1 : 0), N - 1);               // + the forced last entry cum[N-1] = 1 ('>' is strict, :49)
+            x[u] = __ldg(reinterpret_cast<const float2*>(particles) + (size_t)b * N + jj[u]);
+            v[u] = s_wis[jj[u]];
+        }
+        part = (v[0] + v[1]) + (v[2] + v[3]);
+    }
+    const float S2 = block_allreduce(part, s_red, OpSum(), 0.f);
+    if (act) {
+        float pn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) pn[u] = __fdiv_rn(v[u], S2);           // :56
+        *reinterpret_cast<float4*>(particles_out + base * 2) = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+        *reinterpret_cast<float4*>(particles_out + base * 2 + 4) = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+        st4f(probs_out + base, pn[0], pn[1], pn[2], pn[3]);
+        const long long rb = (long long)N * b;
+        longlong2* io = reinterpret_cast<longlong2*>(idx_out + base);
+        io[0] = make_longlong2(rb + jj[0], rb + jj[1]);                    // :52
+        io[1] = make_longlong2(rb + jj[2], rb + jj[3]);
+        if (logprobs_out) st4f(logprobs_out + base, logf(pn[0]), logf(pn[1]), logf(pn[2]), logf(pn[3]));   // DPFs.py:167
+    }
+    if (tid == 0) { saved[2 * b] = S; saved[2 * b + 1] = S2; }
+}
+
+// Backward, same ownership: the sorted ancestor keys of a thread's four destinations and their (dL/dv, g_x, g_y) triples stay in
+// registers; runs of equal keys are summed by a segmented scan (registers -> warp shuffles -> one cross-warp step, fixed order);
+// a run's total lands in its SOURCE's shared-memory slot, and every thread then finishes the four sources it owns: all global
+// traffic is 128-bit and coalesced, nothing is zero-filled and rewritten.
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+soft_resample_bwd4_kernel(const float* __restrict__ g_particles, const float* __restrict__ g_probs,
+                          const float* __restrict__ probs, const int64_t* __restrict__ idx,
+                          const float* __restrict__ saved, float alpha_f, float one_minus_alpha_f, int hard, int N,
+                          float* __restrict__ d_particles, float* __restrict__ d_probs, const float* __restrict__ g_logprobs,
+                          const int* __restrict__ gate) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_w = reinterpret_cast<float*>(smem_raw);    // [N] the row's weights
+    float* s_G = s_w + N;                               // [N] per-source dL/dv run totals
+    float2* s_dp = reinterpret_cast<float2*>(s_G + N);  // [N] per-source particle-gradient run totals
+    __shared__ float s_red[33];
+    __shared__ float s_wt[96];
+    __shared__ int s_wi[64];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int e0 = 4 * tid;
+    const bool act = e0 < N;
+    const size_t base = (size_t)b * N + (act ? e0 : 0);
+    if (gate && *gate == 0) {   // the forward passed everything through: so do the gradients (+ d log w = g / w)
+        if (act) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a, g = a;
+            if (g_particles) { a = ld4f(g_particles + base * 2); c = ld4f(g_particles + base * 2 + 4); }
+            if (g_probs) g = ld4f(g_probs + base);
+            if (g_logprobs) {
+                const float4 gl = ld4f(g_logprobs + base), w = ld4f(probs + base);
+                g.x += gl.x / w.x; g.y += gl.y / w.y; g.z += gl.z / w.z; g.w += gl.w / w.w;
+            }
+            *reinterpret_cast<float4*>(d_particles + base * 2) = a;
+            *reinterpret_cast<float4*>(d_particles + base * 2 + 4) = c;
+            *reinterpret_cast<float4*>(d_probs + base) = g;
+        }
+        return;
+    }
+    const float S = saved[2 * b], S2 = saved[2 * b + 1];
+    const float unif = __fdiv_rn(1.0f, (float)N), uterm = __fmul_rn(unif, one_minus_alpha_f);
+    float wo[4] = {0.f, 0.f, 0.f, 0.f};                 // the weights of the four SOURCES this thread owns
+    int key[4] = {-2, -2, -2, -3};                      // inactive threads never match anything
+    float ax[4] = {0.f, 0.f, 0.f, 0.f}, gx[4] = {0.f, 0.f, 0.f, 0.f}, gy[4] = {0.f, 0.f, 0.f, 0.f};
+    if (act) {
+        const float4 w4 = ld4f(probs + base);
+        wo[0] = w4.x; wo[1] = w4.y; wo[2] = w4.z; wo[3] = w4.w;
+        *reinterpret_cast<float4*>(s_w + e0) = w4;
+        *reinterpret_cast<float4*>(s_G + e0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(s_dp + e0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(s_dp + e0 + 2) = make_float4(0.f, 0.f, 0.f, 0.f);
+        const longlong2* ip = reinterpret_cast<const longlong2*>(idx + base);
+        const longlong2 i0 = ip[0], i1 = ip[1];
+        const long long rb = (long long)N * b;
+        key[0] = (int)(i0.x - rb); key[1] = (int)(i0.y - rb); key[2] = (int)(i1.x - rb); key[3] = (int)(i1.y - rb);
+        if (g_particles) {
+            const float4 a = ld4f(g_particles + base * 2), c = ld4f(g_particles + base * 2 + 4);
+            gx[0] = a.x; gy[0] = a.y; gx[1] = a.z; gy[1] = a.w; gx[2] = c.x; gy[2] = c.y; gx[3] = c.z; gy[3] = c.w;
+        }
+        if (!hard && g_probs) { const float4 g = ld4f(g_probs + base); ax[0] = g.x; ax[1] = g.y; ax[2] = g.z; ax[3] = g.w; }
+    }
+    __syncthreads();
+    float part = 0.f;
+    if (act && !hard && (g_probs || g_logprobs)) {
+        float gl[4] = {0.f, 0.f, 0.f, 0.f};
+        if (g_logprobs) { const float4 g = ld4f(g_logprobs + base); gl[0] = g.x; gl[1] = g.y; gl[2] = g.z; gl[3] = g.w; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float wj = s_w[min(max(key[u], 0), N - 1)];
+            const float wp = (wj * S / __fadd_rn(__fmul_rn(wj, alpha_f), uterm)) / S2;
+            if (g_logprobs) ax[u] += gl[u] / wp;     // total gradient reaching w'_i: direct + through log(w'_i)
+            part += ax[u] * wp;                      // sum_m g_m w'_m
+        }
+    }
+    const float c = block_allreduce(part, s_red, OpSum(), 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ax[u] = hard ? 0.f : (ax[u] - c) / S2;     // dL/dv_i, v_i = w_is[idx_i]
+    // ---- segmented inclusive scan over the runs of equal keys: (1) inside the thread
+#pragma unroll
+    for (int u = 1; u < 4; ++u)
+        if (key[u] == key[u - 1]) { ax[u] += ax[u - 1]; gx[u] += gx[u - 1]; gy[u] += gy[u - 1]; }
+    const int kfirst = key[0], klast = key[3];
+    float tx = ax[3], ty = gx[3], tz = gy[3];
+    // (2) thread tails across the warp and the CTA: a tail continues the previous thread's tail iff the thread holds one key equal to it
+    if (lane == 31) s_wi[32 + wid] = klast;
+    __syncthreads();
+    int kleft = __shfl_up_sync(FULL, klast, 1);
+    if (lane == 0) kleft = wid > 0 ? s_wi[32 + wid - 1] : -4;
+    const bool cont = act && kfirst == kleft;                     // the leading run continues the previous thread's tail
+    int start = !(cont && kfirst == klast);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float ux = __shfl_up_sync(FULL, tx, o), uy = __shfl_up_sync(FULL, ty, o), uz = __shfl_up_sync(FULL, tz, o);
+        const int us = __shfl_up_sync(FULL, start, o);
+        if (lane >= o && !start) { tx += ux; ty += uy; tz += uz; start = us; }
+    }
+    if (lane == 31) { s_wt[wid] = tx; s_wt[32 + wid] = ty; s_wt[64 + wid] = tz; s_wi[wid] = start; }
+    __syncthreads();
+    if (!start && wid > 0) {                                      // the segment reaches back beyond this warp
+        float cx = 0.f, cy = 0.f, cz = 0.f;
+        for (int w = wid - 1; w >= 0; --w) {
+            cx += s_wt[w]; cy += s_wt[32 + w]; cz += s_wt[64 + w];
+            if (s_wi[w]) break;
+        }
+        tx += cx; ty += cy; tz += cz;
+    }
+    // (tx, ty, tz) = total of the run that ends with this thread's tail; (3) hand it to the next thread's leading run
+    float px = __shfl_up_sync(FULL, tx, 1), py = __shfl_up_sync(FULL, ty, 1), pz = __shfl_up_sync(FULL, tz, 1);
+    int knext = __shfl_down_sync(FULL, kfirst, 1);
+    __syncthreads();                                              // s_wt / s_wi reuse
+    if (lane == 31) { s_wt[wid] = tx; s_wt[32 + wid] = ty; s_wt[64 + wid] = tz; }
+    if (lane == 0) s_wi[wid] = kfirst;
+    __syncthreads();
+    if (lane == 0 && wid > 0) { px = s_wt[wid - 1]; py = s_wt[32 + wid - 1]; pz = s_wt[64 + wid - 1]; }
+    if (lane == 31) knext = (wid + 1) < (int)(blockDim.x >> 5) ? s_wi[wid + 1] : -5;
+    if (cont) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (key[u] == kfirst) { ax[u] += px; gx[u] += py; gy[u] += pz; }
+    }
+    // a run ends where the next key differs: its total goes to its source's slot
+    if (act) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int nk = u < 3 ? key[u + 1] : knext;
+            if (nk != key[u]) {
+                const int j = min(max(key[u], 0), N - 1);
+                s_G[j] = ax[u];
+                s_dp[j] = make_float2(gx[u], gy[u]);
+            }
+        }
+    }
+    __syncthreads();
+    float third = 0.f, dq[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 da = make_float4(0.f, 0.f, 0.f, 0.f), dc = da;
+    if (act) {
+        const float4 G4 = *reinterpret_cast<const float4*>(s_G + e0);
+        da = *reinterpret_cast<const float4*>(s_dp + e0);
+        dc = *reinterpret_cast<const float4*>(s_dp + e0 + 2);
+        const float G[4] = {G4.x, G4.y, G4.z, G4.w};
+        if (!hard) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float wj = wo[u], q = __fadd_rn(__fmul_rn(wj, alpha_f), uterm);
+                dq[u] = G[u] * S / q - G[u] * wj * S * alpha_f / (q * q);   // through w_is_j = w_j S / qu_j at fixed S
+                third += G[u] * wj / q;                                      // through S = sum_k qu_k
+            }
+        }
+    }
+    const float t3 = block_allreduce(third, s_red, OpSum(), 0.f);
+    if (act) {
+        *reinterpret_cast<float4*>(d_particles + base * 2) = da;
+        *reinterpret_cast<float4*>(d_particles + base * 2 + 4) = dc;
+        const float a3 = hard ? 0.f : alpha_f * t3;
+        st4f(d_probs + base, dq[0] + a3, dq[1] + a3, dq[2] + a3, dq[3] + a3);
+    }
+}
+
+static int v4_threads(int N) { return ((N / 4) + 31) & ~31; }
+static bool v4_ok(int N, int d) {
+    static const bool generic = getenv("NFDPF_SOFT_GENERIC") != nullptr;    // A/B timing of the two paths (tools/time_soft.py)
+    return !generic && d == 2 && N % 4 == 0 && N >= 4 && N <= V4_MAX_N;
+}
+
 static int pick_threads(int N) {
     int t = 128;
     while (t < 1024 && t * 4 < N) t <<= 1;
@@ -322,6 +671,21 @@ extern "C" int nfdpf_soft_resample_fwd(const float* particles, const float* prob
                   "soft_resample_fwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_fwd: B, N, d must be positive (got %d, %d, %d)", B, N, d);
     NFDPF_REQUIRE(alpha > 0.0 && alpha <= 1.0, "soft_resample_fwd: need 0 < alpha <= 1 (resamplers.py:21), got %g", alpha);
+    if (v4_ok(N, d)) {
+        const size_t sm4 = (size_t)N * 3 * sizeof(float);
+        if (N <= 1024) {     // <= 256 threads: seven rows resident per SM, so B = 1024 rows are ONE wave on 148 SMs
+            soft_resample_fwd4_kernel<256, 7><<<B, v4_threads(N), sm4, (cudaStream_t)stream>>>(
+                particles, probs, offsets, markers, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, particles_out, probs_out,
+                idx_out, saved, logprobs_out, gate);
+        } else {
+            if (sm4 > 40 * 1024)
+                NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_fwd4_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
+            soft_resample_fwd4_kernel<1024, 1><<<B, v4_threads(N), sm4, (cudaStream_t)stream>>>(
+                particles, probs, offsets, markers, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, particles_out, probs_out,
+                idx_out, saved, logprobs_out, gate);
+        }
+        return check_launch("soft_resample_fwd");
+    }
     const size_t smem = (size_t)N * 2 * sizeof(float);
     // the backward keeps 20 B per particle in shared memory: accept only what it can also handle (no forward-only sizes)
     if ((size_t)((N + 3) & ~3) * sizeof(int) + (size_t)N * sizeof(float4) > 200 * 1024) {
@@ -341,6 +705,21 @@ extern "C" int nfdpf_soft_resample_bwd(const float* g_particles, const float* g_
     NFDPF_REQUIRE(probs && idx && saved && d_particles && d_probs, "soft_resample_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0, "soft_resample_bwd: B, N, d must be positive");
     NFDPF_REQUIRE(alpha > 0.0 && alpha <= 1.0, "soft_resample_bwd: need 0 < alpha <= 1, got %g", alpha);
+    if (v4_ok(N, d)) {
+        const size_t sm4 = (size_t)N * 4 * sizeof(float);
+        if (N <= 1024) {     // 48 registers, no spills (a 32-register build spilled and ran 8 % slower)
+            soft_resample_bwd4_kernel<256, 5><<<B, v4_threads(N), sm4, (cudaStream_t)stream>>>(
+                g_particles, g_probs, probs, idx, saved, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, d_particles, d_probs,
+                g_logprobs, gate);
+        } else {
+            if (sm4 > 40 * 1024)
+                NFDPF_CUDA(cudaFuncSetAttribute(soft_resample_bwd4_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4));
+            soft_resample_bwd4_kernel<1024, 1><<<B, v4_threads(N), sm4, (cudaStream_t)stream>>>(
+                g_particles, g_probs, probs, idx, saved, (float)alpha, (float)(1.0 - alpha), alpha >= 1.0 ? 1 : 0, N, d_particles, d_probs,
+                g_logprobs, gate);
+        }
+        return check_launch("soft_resample_bwd");
+    }
     const size_t smem = (size_t)((N + 3) & ~3) * sizeof(int) + (size_t)N * sizeof(float4);
     if (smem > 200 * 1024) { set_error("soft_resample_bwd: N=%d exceeds the shared-memory row limit (10200)", N); return NFDPF_ERR_UNSUPPORTED; }
     if (smem > 48 * 1024)
