@@ -13,6 +13,8 @@
 #include "mma_tile.cuh"
 #include "umma.cuh"
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 namespace nfdpf {
@@ -506,8 +508,8 @@ struct PR {
 constexpr int TA_A = 0, TA_B = TA_A + 40, TA_D1 = TA_B + 24, TA_END = TA_D1 + 4;   // 68 columns after the data-path columns
 constexpr int TA_CNF = TA_END, CNF_COLS = 18;                                      // CRNVP nets: 18 columns each behind them
 constexpr int BWD_TMEM_COLS = 256;   // gaussian / cos: 96 + 68; CRNVP (SS data path): 32 + 68 + 8 x 18 = 244
-__device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_tile, uint32_t tacc) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2;
+__device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_tile, uint32_t tacc, int warp) {
+    const int lane = threadIdx.x & 31, g = lane >> 2;
     const int k0 = 32 * warp;
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
@@ -515,21 +517,24 @@ __device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_ti
         // fp32 accumulate is not round-to-nearest, and chaining hundreds of batches through it biased the gradients (~6e-4)
         float c[5][4] = {}, r[20];
         const int rowB[5] = {PR::A2 + g, PR::A2 + 8 + g, PR::A2 + 16 + g, PR::A2 + 24 + g, g == 0 ? PR::ONE : PR::ZERO};
-        mma_outer<5>(s_tile, PR::D3 + 16 * mt, rowB, k0, k0 + 32, c);
+        mma_outer<5, 1u << 4>(s_tile, PR::D3 + 16 * mt, rowB, k0, k0 + 32, c);
         umma::ld_frag<20>(tacc + TA_A + 20 * mt, r);
 #pragma unroll
         for (int i = 0; i < 20; ++i) r[i] += c[i >> 2][i & 3];
         umma::st_frag<20>(tacc + TA_A + 20 * mt, r);
     }
 }
-__device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_tile, uint32_t tacc) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2;
+__device__ __forceinline__ void pe_weight_grads_a(const float* __restrict__ s_tile, uint32_t tacc) {
+    pe_weight_grads_a(s_tile, tacc, threadIdx.x >> 5);
+}
+__device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_tile, uint32_t tacc, int warp) {
+    const int lane = threadIdx.x & 31, g = lane >> 2;
     const int k0 = 32 * warp;
 #pragma unroll 1
     for (int mt = 0; mt < 2; ++mt) {
         float c[3][4] = {}, r[12];
         const int rowB[3] = {PR::A1 + g, PR::A1 + 8 + g, g == 0 ? PR::ONE : PR::ZERO};
-        mma_outer<3>(s_tile, PR::D2 + 16 * mt, rowB, k0, k0 + 32, c);
+        mma_outer<3, 1u << 2>(s_tile, PR::D2 + 16 * mt, rowB, k0, k0 + 32, c);
         umma::ld_frag<12>(tacc + TA_B + 12 * mt, r);
 #pragma unroll
         for (int i = 0; i < 12; ++i) r[i] += c[i >> 2][i & 3];
@@ -543,6 +548,9 @@ __device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_ti
     for (int i = 0; i < 4; ++i) r1[i] += c1[0][i];
     umma::st_frag<4>(tacc + TA_D1, r1);
     umma::wait_st();     // the next batch (or the read-out) loads these columns again
+}
+__device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_tile, uint32_t tacc) {
+    pe_weight_grads_b(s_tile, tacc, threadIdx.x >> 5);
 }
 // Read this warp's accumulated fragments back and scatter them into its accumulator copy accpe[AC::SIZE] (every entry is
 // owned by exactly one lane; bias columns by the t == 0 / t == 1 lanes).
@@ -879,6 +887,247 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     }
 }
 
+// ---- warp-specialised backward (gaussian / cos) -----------------------------------------------------------------------
+// The kernel above walks a batch through four tcgen05 rounds and then through the two mma.sync weight-gradient phases, all on
+// the same four warps: while a CTA waits for a round nobody contracts, while it contracts the tensor cores' data path idles
+// (ncu: issue slots 35 %, tensor pipe 36 %, 17 % of the samples in the mbarrier spin).  Here a CTA has EIGHT warps: warps 0-3 own
+// the particles (thread = particle = tensor-memory lane: forward rounds, likelihood gradient, data-gradient rounds, d_particles),
+// warps 4-7 own the weight gradients (warp 4 + w contracts over the 32 particles warp w staged; its lane-private fragments live in
+// the same tensor-memory lanes, behind the data-path columns).  The two halves meet only in the gradient tile: per warp pair one
+// `full` and one `empty` mbarrier, alternating between the tile's two (aliased) phases --
+//   data warp:      ... round 2 | wait empty | stage A (delta3, a2) | arrive full | rounds 3-4 | wait empty | stage B | arrive full | next batch
+//   gradient warp:  wait full | phase A (dW3, db3) | arrive empty | wait full | phase B (dW2, db2, dW1, db1) | arrive empty
+// so phase A of a batch overlaps its data-gradient rounds and phase B the next batch's forward rounds.  Two CTAs per SM (16 warps).
+constexpr int WS_THREADS = 256;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void data_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// PeTc whose rounds synchronise the 128 data threads only (named barrier 1)
+struct PeTcWs : PeTc {
+    template <int N, int K>
+    __device__ __forceinline__ void round(int w_hi, int w_lo) {
+        umma::wait_st();
+        umma::fence_before_sync();
+        data_group_sync();
+        if (threadIdx.x == 0) {
+            umma::fence_after_sync();
+            umma::gemm3_ts<N, K>(tmem + COL_D, tmem + COL_AHI, tmem + COL_ALO, w + w_hi, w + w_lo);
+            umma::commit(bar);
+        }
+        wait();
+    }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(WS_THREADS, 2)
+measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const float* __restrict__ enc,
+                      const float* __restrict__ particles, int B, int N, const float* __restrict__ g_lki,
+                      const int* __restrict__ argmax, float* __restrict__ d_particles, float* __restrict__ d_enc,
+                      float* __restrict__ part_pe) {
+    static_assert(MODE == MODE_GAUSS || MODE == MODE_COS, "CRNVP keeps the single-role kernel");
+    extern __shared__ __align__(128) float smem[];
+    __shared__ float s_red[8];
+    __shared__ uint64_t s_bar;
+    __shared__ uint64_t s_full[4], s_empty[4];
+    __shared__ uint32_t s_tslot;
+    constexpr int TILE_FLOATS = (PR::COUNT * TSM + 31) & ~31;
+    constexpr int NWD = 4;                                   // data warps == gradient warps
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_data = warp < NWD;
+    const int pw = warp & 3;                                 // warp pair = tensor-memory lane quarter
+    float* s_tile = smem;                                    // [TILE_FLOATS]
+    float* s_tcw = s_tile + TILE_FLOATS;                     // tensor-core weight tiles
+    float* s_pe = s_tcw + PeTc::WBWD_FLOATS;
+    float* s_enc = s_pe + PE_SIZE;
+    float* s_denc = s_enc + 36;                              // [4][32]
+    float* s_accpe = s_tile;                                 // read-out staging at the very end
+    static_assert(NWD * AC::SIZE <= TILE_FLOATS, "read-out staging must fit in the tile");
+    // (a pre-split hi | lo tile pair -- the data warps splitting once, the gradient warps only loading -- was measured: 279 us
+    //  against 194: twice the shared-memory stores and fragment loads cost more than the 860 split instructions per batch saved)
+    auto stage = [&](int row, float v) { s_tile[row * TSM + tid] = v; };
+    if (is_data) {   // the constant rows of the bias columns, once (no phase aliases them)
+        s_tile[PR::ONE * TSM + tid] = 1.0f;
+        s_tile[PR::ZERO * TSM + tid] = 0.0f;
+    }
+    if (tid < 32) umma::tmem_alloc<BWD_TMEM_COLS>(&s_tslot);
+    if (tid == 0) {
+        umma::mbar_init(&s_bar, 1);
+        for (int w = 0; w < NWD; ++w) { umma::mbar_init(&s_full[w], 32); umma::mbar_init(&s_empty[w], 32); }
+    }
+    PeTcWs tc;
+    tc.w = s_tcw; tc.bar = &s_bar; tc.tmem = 0u; tc.parity = 0u;
+    tc.load_weights(pe, true);
+    for (int e = tid; e < PE_SIZE; e += WS_THREADS) s_pe[e] = pe[e];
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    tc.tmem = s_tslot;
+    const uint32_t tacc = tc.tmem + ((uint32_t)(32 * pw) << 16) + PeTc::COLS;   // the pair's 32 lanes, behind the data-path columns
+    if (is_data) {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c0 = 0; c0 < TA_END; c0 += 4) umma::st4(tacc + c0, z);
+        umma::wait_st();
+    }
+    uint32_t ph_full = 0, ph_empty = 1;                      // the tile starts out empty: the first `empty` wait passes
+    float rs3_prev[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        umma::fence_before_sync();
+        __syncthreads();                                     // S1: previous trajectory is finished everywhere
+        umma::fence_after_sync();
+        const size_t base = (size_t)b * N;
+        if (!is_data) {
+            // ---------------------------------------------------------------- gradient warps
+            for (int n0 = 0; n0 < N; n0 += 128) {
+                umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
+                pe_weight_grads_a(s_tile, tacc, pw);
+                mbar_arrive(&s_empty[pw]);
+                umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
+                pe_weight_grads_b(s_tile, tacc, pw);
+                mbar_arrive(&s_empty[pw]);
+            }
+            umma::wait_st();
+        } else {
+            // ---------------------------------------------------------------- data warps
+            load_enc(enc + (size_t)b * HID, s_enc);
+            float gs = 0.f;
+            if (MODE != MODE_COS) {      // row-max shift: d ll[n] = g[n] - [n == argmax] * sum_m g[m]
+                for (int n = tid; n < N; n += 128) gs += g_lki[base + n];
+                gs = warp_sum(gs);
+                if (lane == 0) s_red[warp] = gs;
+            }
+            data_group_sync();
+            if (MODE != MODE_COS) gs = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+            const int am = MODE != MODE_COS ? argmax[b] : -1;
+            float denc[MODE == MODE_COS ? 32 : 1];
+#pragma unroll
+            for (int k = 0; k < (MODE == MODE_COS ? 32 : 1); ++k) denc[k] = 0.f;
+            float2 x_next = *reinterpret_cast<const float2*>(particles + (base + (tid < N ? tid : 0)) * 2);
+            float g_next = g_lki[base + (tid < N ? tid : 0)];
+            for (int n0 = 0; n0 < N; n0 += 128) {
+                asm volatile("" ::: "memory");
+                const int n = n0 + tid;
+                const bool live = n < N;
+                const size_t p = base + (live ? n : 0);
+                const float2 x = x_next;
+                float g = live ? g_next : 0.f;
+                if (live && n == am) g -= gs;
+                {
+                    const size_t pn = base + (n + 128 < N ? n + 128 : 0);
+                    x_next = *reinterpret_cast<const float2*>(particles + pn * 2);
+                    g_next = g_lki[pn];
+                }
+                float a1[16], a2[32], e[32];
+                pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);        // rounds 1-2: layers 2 and 3 forward
+                if (MODE == MODE_GAUSS) {
+                    const float c = live ? g / (p1 * p1) : 0.f;
+#pragma unroll
+                    for (int o = 0; o < 32; ++o) e[o] = c * (s_enc[o] - e[o] - p0);          // e := delta3
+                } else {
+                    float ne = 0.f, dot = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) { ne = fmaf(e[k], e[k], ne); dot = fmaf(s_enc[k], e[k], dot); }
+                    const float nrm = fmaxf(sqrtf(ne), 1e-12f), nenc = s_enc[32];
+                    const float ab = dot / (nrm * nenc);
+                    const float c = g / (1e-7f + 1.0f - ab);     // d lki / d(ab)
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const float ah = s_enc[k] / nenc, bh = e[k] / nrm;
+                        e[k] = live ? c * (ah - ab * bh) / nrm : 0.f;
+                        denc[k] += c * (bh - ab * ah) / nenc;
+                    }
+                }
+                // stage phase A (the gradient warp has finished phase B of the previous batch)
+                umma::mbar_wait(&s_empty[pw], ph_empty); ph_empty ^= 1;
+                uint32_t m2 = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    stage(PR::D3 + j, e[j]);
+                    stage(PR::A2 + j, a2[j]);
+                    m2 |= (a2[j] > 0.f ? 1u : 0u) << j;
+                }
+                mbar_arrive(&s_full[pw]);
+                // rounds 3-4: d a2 = W3^T delta3, d a1 = W2^T delta2
+                float d2[32], d1[16];
+                tc.template store_row<32>(e);
+                tc.template round<32, 32>(PeTc::W3T_HI, PeTc::W3T_LO);
+                umma::ld32(tc.lane_addr(), d2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) d2[j] = (m2 >> j) & 1u ? d2[j] : 0.f;
+                tc.template store_row<32>(d2);
+                tc.template round<16, 32>(PeTc::W2T_HI, PeTc::W2T_LO);
+                umma::ld16(tc.lane_addr(), d1);
+                float dx0 = 0.f, dx1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; k += 2) {
+                    const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W1 + 2 * k);
+                    d1[k] = a1[k] > 0.f ? d1[k] : 0.f;
+                    d1[k + 1] = a1[k + 1] > 0.f ? d1[k + 1] : 0.f;
+                    dx0 = fmaf(q.x, d1[k], dx0); dx1 = fmaf(q.y, d1[k], dx1);
+                    dx0 = fmaf(q.z, d1[k + 1], dx0); dx1 = fmaf(q.w, d1[k + 1], dx1);
+                }
+                if (live) *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
+                // stage phase B (its rows alias phase A's: the gradient warp has finished phase A)
+                umma::mbar_wait(&s_empty[pw], ph_empty); ph_empty ^= 1;
+                stage(PR::X + 0, x.x);
+                stage(PR::X + 1, x.y);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { stage(PR::A1 + k, a1[k]); stage(PR::D1 + k, d1[k]); }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stage(PR::D2 + j, d2[j]);
+                mbar_arrive(&s_full[pw]);
+            }
+            if (MODE == MODE_COS) {
+                // d_enc[b][k] = sum over the row's particles: through the tile once the gradient warps are done with it
+                umma::mbar_wait(&s_empty[pw], ph_empty);         // (no toggle: phase B of the last batch; the next stage-A wait re-observes it)
+#pragma unroll
+                for (int k = 0; k < 32; ++k) s_tile[(2 + k) * TSM + tid] = denc[k];     // (rows 0-1 hold the constant rows)
+            }
+        }
+        umma::fence_before_sync();
+        __syncthreads();                                     // S2: every fragment of this trajectory is in tensor memory
+        umma::fence_after_sync();
+        if (MODE == MODE_GAUSS) {
+            // d_enc = -sum_p delta3: the bias column of phase A holds the RUNNING sum over the trajectories done so far
+            if (is_data) {
+                float cur[4], c4[4];
+                umma::ld_frag<4>(tacc + TA_A + 16, c4); cur[0] = c4[0]; cur[1] = c4[2];
+                umma::ld_frag<4>(tacc + TA_A + 36, c4); cur[2] = c4[0]; cur[3] = c4[2];
+                if ((tid & 3) == 0) {
+                    const int g = lane >> 2;
+                    s_denc[warp * 32 + g] = cur[0] - rs3_prev[0]; s_denc[warp * 32 + g + 8] = cur[1] - rs3_prev[1];
+                    s_denc[warp * 32 + 16 + g] = cur[2] - rs3_prev[2]; s_denc[warp * 32 + 24 + g] = cur[3] - rs3_prev[3];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rs3_prev[i] = cur[i];
+            }
+            __syncthreads();
+            if (d_enc && tid < 32) d_enc[(size_t)b * HID + tid] = -((s_denc[tid] + s_denc[32 + tid]) + (s_denc[64 + tid] + s_denc[96 + tid]));
+        } else if (d_enc) {
+            if (tid < 32) {
+                float a = 0.f;
+                for (int q = 0; q < 128; ++q) a += s_tile[(2 + tid) * TSM + q];
+                d_enc[(size_t)b * HID + tid] = a;
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();                                   // every warp is done with the tile: it becomes the read-out staging area
+    umma::fence_after_sync();
+    for (int e = tid; e < NWD * AC::SIZE; e += WS_THREADS) s_accpe[e] = 0.f;
+    __syncthreads();
+    if (is_data) pe_weight_grads_readout(tacc, s_accpe + warp * AC::SIZE);
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_free<BWD_TMEM_COLS>(tc.tmem);
+    for (int e = tid; e < PE_SIZE; e += WS_THREADS) {
+        const float* a = s_accpe + AC::of_packed(e);
+        part_pe[(size_t)blockIdx.x * PE_SIZE + e] = (a[0] + a[AC::SIZE]) + (a[2 * AC::SIZE] + a[3 * AC::SIZE]);
+    }
+}
+
 static size_t fwd_smem(int mode, int n_flows, int N) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
     return ((size_t)PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * CnfL1::TAIL + n_fcnn * H + (size_t)(n_fcnn / 2) * CnfL1::STAGE_FLOATS + N) * sizeof(float);
@@ -910,16 +1159,32 @@ static int launch_measure_fwd(const float* pe, const float* cnf, int n_flows, fl
 static int measure_bwd_grid(int mode, int B) { (void)mode; return min(B, 2 * sm_count()); }
 
 template <int MODE>
+static void launch_measure_bwd_ws(const float* pe, float p0, float p1, const float* enc, const float* particles, int B, int N,
+                                  const float* g_lki, const int* argmax, float* d_particles, float* d_enc, float* part_pe, int grid,
+                                  size_t smem, cudaStream_t st) {
+    auto kern = measure_bwd_ws_kernel<MODE>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, WS_THREADS, smem, st>>>(pe, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe);
+}
+
+template <int MODE>
 static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,
                               int B, int N, const float* g_lki, const int* argmax, float* d_particles, float* d_enc, float* d_pe,
                               float* d_cnf, void* workspace, const float* z_saved, cudaStream_t st) {
     const size_t smem = bwd_smem(MODE, n_flows);
-    auto kern = measure_bwd_kernel<MODE>;
-    if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = measure_bwd_grid(MODE, B);
     float* part_pe = (float*)workspace;
     float* part_cnf = part_pe + (size_t)grid * PE_SIZE;
-    kern<<<grid, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, part_cnf, z_saved);
+    static const bool single_role = getenv("NFDPF_MEASURE_BWD_V1") != nullptr;     // A/B timing against the round-1 kernel
+    if (MODE == MODE_GAUSS && !single_role) {     // (cos: its 32 running d_enc sums per thread spill at 128 registers -- measured slower)
+        const size_t ws_smem = smem;
+        launch_measure_bwd_ws<MODE == MODE_CNF ? MODE_GAUSS : MODE>(pe, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe,
+                                                                     grid, ws_smem, st);
+    } else {
+        auto kern = measure_bwd_kernel<MODE>;
+        if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, part_cnf, z_saved);
+    }
     int rc = check_launch("measure_bwd");
     if (rc) return rc;
     rc = launch_reduce_partials(part_pe, grid, PE_SIZE, d_pe, st);

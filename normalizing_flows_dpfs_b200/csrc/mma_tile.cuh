@@ -31,7 +31,9 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 // (tile columns) [k_begin, k_end) (multiples of 8).  rowB[n] is THIS LANE's tile row for column (lane >> 2) of n-tile n --
 // callers build it so that bias / padding columns point at the ONE / ZERO rows of the tile.  Every warp contracts over
 // ITS OWN 32 particles (the columns its threads staged), so the weight-gradient phase needs no CTA barrier.
-template <int NT>
+// EXACT_B: bit n set = the B operand of n-tile n is exactly representable in TF32 (the ONE / ZERO bias rows): its lo part is
+// zero, so the hi x lo product (a third of that tile's MMAs) is skipped.
+template <int NT, unsigned EXACT_B = 0u>
 __device__ __forceinline__ void mma_outer(const float* __restrict__ tile, int rowA, const int (&rowB)[NT], int k_begin, int k_end,
                                           float (&c)[NT][4]) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -55,7 +57,8 @@ __device__ __forceinline__ void mma_outer(const float* __restrict__ tile, int ro
 #pragma unroll
         for (int n = 0; n < NT; ++n) mma_tf32(c[n], al, bh[n]);
 #pragma unroll
-        for (int n = 0; n < NT; ++n) mma_tf32(c[n], ah, bl[n]);
+        for (int n = 0; n < NT; ++n)
+            if (!((EXACT_B >> n) & 1u)) mma_tf32(c[n], ah, bl[n]);
 #pragma unroll
         for (int n = 0; n < NT; ++n) mma_tf32(c[n], ah, bh[n]);
     }
