@@ -67,9 +67,10 @@ int nfdpf_weight_update_fwd(const float* logw_prev, const float* lki, const floa
                             float add_eps, int B, int N, float* logw_out, float* probs_out, float* row_stats,
                             void* stream);
 /* backward: g_probs (B,N) or NULL, g_logw (B,N) or NULL, g_rowsum (B,) or NULL (grad of row_stats[:,0]);
- * probs = the forward output (with add_eps).  d_logw (B,N) is the gradient of every added term (negate for propose). */
+ * probs = the forward output (with add_eps).  d_logw (B,N) is the gradient of every added term; d_neg (B,N) or NULL receives
+ * its negation (the gradient of the subtracted proposal term) in the same pass. */
 int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw, const float* g_rowsum, const float* probs,
-                            float add_eps, int B, int N, float* d_logw, void* stream);
+                            float add_eps, int B, int N, float* d_logw, float* d_neg, void* stream);
 
 /* ---- (K1) fused coupling stack: nf/flows.py:155-179, 215-239; nf/models.py:11-30, 45-61 ---------------
  * x (P,D); context = [row_ctx (B,C_row) broadcast over the N particles of a row | part_ctx (P,C_part)],
@@ -206,6 +207,11 @@ int nfdpf_block_density_fwd(const float* w, int64_t w_sb, int64_t w_st, const fl
 int nfdpf_block_density_bwd(const float* gQ, const float* w, int64_t w_sb, int64_t w_st, const int64_t* idx, int64_t i_sb,
                             int64_t i_st, const float* run_saved, int B, int T, int N, int block_len, float* d_w, float* d_lik,
                             float* d_prior, int64_t o_sb, int64_t o_st, void* stream);
+
+/* ---- fan-out of one tensor to several consumers: out[i] = a[i] + b[i] (+ c[i]) (+ d[i]), n floats; b, c, d may be NULL.
+ * The backward of ops.fanout: the gradients of up to four consumers of one filter tensor are summed in ONE pass (autograd's own
+ * accumulation is a chain of two-operand adds, each a launch and a full read-modify-write). */
+int nfdpf_sum4(const float* a, const float* b, const float* c, const float* d, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -191,6 +191,11 @@ class DPF(nn.Module):
         if self.hoist_encoder and not isinstance(self.encoder, nn.Identity):
             enc_all = self.encoder(obs.reshape((B * T,) + tuple(obs.shape[2:])).float()).reshape(B, T, -1)
 
+        # per-step slices of (B,T,...) inputs are strided views, and every kernel call would first copy them: transpose once
+        vel_steps = vel_input.transpose(0, 1).contiguous()
+        obs_steps = obs.transpose(0, 1).contiguous() if (enc_all is None and obs.dim() == 3) else None   # precomputed encodings
+        enc_steps = enc_all.transpose(0, 1).contiguous() if enc_all is not None else None
+
         def put(key, step, t):   # data the kernels could not write in place (non-fused paths) is copied into the list buffer
             if t.data_ptr() != buf[key][step].data_ptr():
                 buf[key][step].copy_(t.detach())
@@ -237,7 +242,11 @@ class DPF(nn.Module):
                         identity_idx = torch.arange(B * N, device=dev, dtype=torch.int64).reshape(B, N)
                     buf["index"][step].copy_(identity_idx)
             noise = inj["noise"][:, step] if "noise" in inj else None
-            encodings = enc_all[:, step] if enc_all is not None else self.encoder(obs[:, step].float())
+            x_pred = None
+            if enc_steps is not None:
+                encodings = enc_steps[step]
+            else:
+                encodings = self.encoder((obs_steps[step] if obs_steps is not None else obs[:, step]).float())
             if fused:
                 # ---- fused step: 6 libnfdpf launches (motion+moments, 3 coupling stacks, densities, measurement+update)
                 if noise is None and not device_rng:
@@ -249,7 +258,7 @@ class DPF(nn.Module):
                 if plain:
                     o["moved"] = buf["particles"][step]
                 particles_physical, noise = ops.motion_moments(particles, vel, noise, ctx_phys, 0, rng, self.pos_noise, o)
-                vel = vel_input[:, step, :]
+                vel = vel_steps[step]
                 if self.NF:
                     o = {"log_det": buf["jac"][step]}
                     if not self.NFcond:
@@ -264,14 +273,17 @@ class DPF(nn.Module):
                     ops.row_moments(particles_dynamical, ctx_prop, self.hidden_size)
                     propose_particle, jac_prop = self.cond_model.run_stack(particles_dynamical, row_ctx=ctx_prop, inverse=True, neg_logdet=True,
                                                                            out={"y": buf["particles"][step]})
+                    # the proposal has four consumers (dynamics flow, measurement, prediction, next step): one alias each, their
+                    # gradients meet in one summing launch instead of three chained autograd adds
+                    x_back, x_meas, x_pred, propose_particle = ops.fanout(propose_particle, 4)
                     if self.NF:   # push the proposal back through the dynamics flow (context: moments of the physical cloud)
-                        back, jac_back = self.nf_dyn.run_stack(propose_particle, row_ctx=ctx_phys, inverse=False, neg_logdet=True)
+                        back, jac_back = self.nf_dyn.run_stack(x_back, row_ctx=ctx_phys, inverse=False, neg_logdet=True)
                     else:
-                        back, jac_back = propose_particle, None
+                        back, jac_back = x_back, None
                     prior_log, propose_log = ops.proposal_terms(back, particles_physical, noise, jac_back, jac, jac_prop, self.pos_noise,
                                                                 {"prior": buf["prior"][step]} if self.NF else None)
                     lki_log, logw, particle_probs, row_sum, ess_inv = self.measurement_model.forward_update(
-                        encodings, propose_particle, logw_prev, prior_log, propose_log, out=mo)
+                        encodings, x_meas, logw_prev, prior_log, propose_log, out=mo)
                 else:             # prior == proposal density: the two cancel exactly in DPFs.py:187
                     propose_particle = particles_dynamical
                     if self.NF:
@@ -297,7 +309,7 @@ class DPF(nn.Module):
             particles = propose_particle
             put("particles", step, particles)
             row_sums.append(row_sum)
-            pred = ops.weighted_mean(particles, particle_probs, {"pred": buf["pred"][step]})
+            pred = ops.weighted_mean(x_pred if x_pred is not None else particles, particle_probs, {"pred": buf["pred"][step]})
             for k, v in (("particles", particles), ("probs", particle_probs), ("lki", lki_log), ("pred", pred)):
                 steps[k].append(v)
             if self.NF:

@@ -152,9 +152,30 @@ __global__ void weighted_mean_bwd_kernel(const float* __restrict__ g_pred, const
     if (d_w) d_w[i] = fmaf(g.x, p.x, g.y * p.y);
 }
 
+__global__ void sum4_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                            const float* __restrict__ d, size_t n4, size_t n, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        float4 v = reinterpret_cast<const float4*>(a)[i];
+        if (b) { const float4 u = reinterpret_cast<const float4*>(b)[i]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        if (c) { const float4 u = reinterpret_cast<const float4*>(c)[i]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        if (d) { const float4 u = reinterpret_cast<const float4*>(d)[i]; v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+    if (i == 0)
+        for (size_t k = 4 * n4; k < n; ++k) out[k] = a[k] + (b ? b[k] : 0.f) + (c ? c[k] : 0.f) + (d ? d[k] : 0.f);
+}
+
 }  // namespace nfdpf
 
 using namespace nfdpf;
+
+extern "C" int nfdpf_sum4(const float* a, const float* b, const float* c, const float* d, int64_t n, float* out, void* stream) {
+    NFDPF_REQUIRE(a && out && n > 0, "sum4: bad arguments");
+    const size_t n4 = (size_t)n / 4;
+    sum4_kernel<<<(unsigned)((n4 + 255) / 256 + (n4 == 0)), 256, 0, (cudaStream_t)stream>>>(a, b, c, d, n4, (size_t)n, out);
+    return check_launch("sum4");
+}
 
 extern "C" int nfdpf_ess_gate(const float* ess_inv, int ess_stride, int B, int N, int force, int64_t* rng_state, int advance,
                               int32_t* gate_out, float* offsets_out, void* stream) {

@@ -56,7 +56,7 @@ __global__ void weight_update_fwd_kernel(const float* __restrict__ lw0, const fl
 template <bool BLOCK_PER_ROW>
 __global__ void weight_update_bwd_kernel(const float* __restrict__ g_probs, const float* __restrict__ g_logw,
                                          const float* __restrict__ g_rowsum, const float* __restrict__ probs, float add_eps,
-                                         int B, int N, float* __restrict__ d_logw) {
+                                         int B, int N, float* __restrict__ d_logw, float* __restrict__ d_neg) {
     __shared__ float s_red[33];
     const int lane = threadIdx.x & 31;
     const int row = BLOCK_PER_ROW ? blockIdx.x : blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -74,6 +74,7 @@ __global__ void weight_update_bwd_kernel(const float* __restrict__ g_probs, cons
         if (g_probs) v += (probs[base + n] - add_eps) * (g_probs[base + n] - dot);
         if (g_logw) v += g_logw[base + n];
         d_logw[base + n] = v;
+        if (d_neg) d_neg[base + n] = -v;      // the proposal term enters with a minus sign (DPFs.py:187)
     }
 }
 
@@ -99,16 +100,16 @@ extern "C" int nfdpf_weight_update_fwd(const float* logw_prev, const float* lki,
 }
 
 extern "C" int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw, const float* g_rowsum, const float* probs,
-                                       float add_eps, int B, int N, float* d_logw, void* stream) {
+                                       float add_eps, int B, int N, float* d_logw, float* d_neg, void* stream) {
     NFDPF_REQUIRE(probs && d_logw, "weight_update_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0, "weight_update_bwd: B and N must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 1024) {
         const int wpb = 8;
         weight_update_bwd_kernel<false><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N,
-                                                                                  d_logw);
+                                                                                  d_logw, d_neg);
     } else {
-        weight_update_bwd_kernel<true><<<B, 512, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N, d_logw);
+        weight_update_bwd_kernel<true><<<B, 512, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N, d_logw, d_neg);
     }
     return check_launch("weight_update_bwd");
 }

@@ -91,9 +91,10 @@ class WeightUpdate(torch.autograd.Function):
         g_probs = L.f32(g_probs) if g_probs is not None else None
         g_rowsum = L.f32(g_rowsum) if g_rowsum is not None else None
         d = torch.empty_like(probs)
+        dn = torch.empty_like(probs) if ctx.has[2] else None
         L.call("nfdpf_weight_update_bwd", L.ptr(g_probs), L.ptr(g_logw), L.ptr(g_rowsum), L.ptr(probs), ctx.add_eps, B, N,
-               L.ptr(d), L.stream())
-        return d, (d if ctx.has[0] else None), (d if ctx.has[1] else None), (-d if ctx.has[2] else None), None, None
+               L.ptr(d), L.ptr(dn), L.stream())
+        return d, (d if ctx.has[0] else None), (d if ctx.has[1] else None), dn, None, None
 
 
 class CouplingStack(torch.autograd.Function):
@@ -203,13 +204,15 @@ class MeasureUpdate(torch.autograd.Function):
         pe_, cnf_, enc_, x_, argmax, probs, z = ctx.saved_tensors
         mode, n_flows, p0, p1, add_eps, B, N, hidden, fused, has_prior, has_prop = ctx.meta
         dev = x_.device
-        d_logw = None
+        d_logw = d_neg = None
         g_total = L.f32(g_lki) if g_lki is not None else None
         if fused and any(g is not None for g in (g_logw, g_probs, g_rowsum)):
             d_logw = torch.empty(B, N, dtype=torch.float32, device=dev)
+            d_neg = torch.empty(B, N, dtype=torch.float32, device=dev) if has_prop else None
             L.call("nfdpf_weight_update_bwd", L.ptr(L.f32(g_probs) if g_probs is not None else None),
                    L.ptr(L.f32(g_logw) if g_logw is not None else None),
-                   L.ptr(L.f32(g_rowsum) if g_rowsum is not None else None), L.ptr(probs), add_eps, B, N, L.ptr(d_logw), L.stream())
+                   L.ptr(L.f32(g_rowsum) if g_rowsum is not None else None), L.ptr(probs), add_eps, B, N, L.ptr(d_logw), L.ptr(d_neg),
+                   L.stream())
             g_total = d_logw if g_total is None else g_total + d_logw
         if g_total is None:
             g_total = torch.zeros(B, N, dtype=torch.float32, device=dev)
@@ -221,7 +224,7 @@ class MeasureUpdate(torch.autograd.Function):
         L.call("nfdpf_measure_bwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, p0, p1, L.ptr(enc_), L.ptr(x_), B, N, hidden,
                L.ptr(g_total.contiguous()), L.ptr(argmax), L.ptr(d_x), L.ptr(d_enc), L.ptr(d_pe), L.ptr(d_cnf), L.ptr(ws), L.ptr(z), L.stream())
         return (d_pe, d_cnf, d_enc, d_x, d_logw if fused else None, d_logw if has_prior else None,
-                (-d_logw if d_logw is not None else None) if has_prop else None, None, None, None, None, None, None)
+                d_neg if has_prop else None, None, None, None, None, None, None)
 
 
 def measure(pe, cnf, enc, particles, mode, n_flows=2, p0=0.0, p1=1.0):
@@ -344,6 +347,38 @@ class WeightedMean(torch.autograd.Function):
 
 def weighted_mean(particles, probs, out=None):
     return WeightedMean.apply(particles, probs, out)
+
+
+class Fanout(torch.autograd.Function):
+    """n aliases of one tensor, one per consumer.  Forward: nothing is computed or copied.  Backward: the consumers' gradients
+    are summed in ONE launch (nfdpf_sum4) -- autograd's own accumulation would chain n - 1 two-operand adds, each a launch and a
+    full read-modify-write of the (B,N,2) gradient."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.set_materialize_grads(False)
+        return tuple(x.view_as(x) for _ in range(n))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        gs = [L.f32(g) for g in gs if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        out = torch.empty_like(gs[0])
+        while len(gs) > 1:       # up to four operands per pass
+            take, gs = gs[:4], gs[4:]
+            take += [None] * (4 - len(take))
+            L.call("nfdpf_sum4", L.ptr(take[0]), L.ptr(take[1]), L.ptr(take[2]), L.ptr(take[3]), out.numel(), L.ptr(out), L.stream())
+            gs = [out] + gs
+        return out, None
+
+
+def fanout(x, n):
+    if not (torch.is_tensor(x) and x.requires_grad and torch.is_grad_enabled()):
+        return (x,) * n
+    return Fanout.apply(x, n)
 
 
 def _list3(t, dtype):
