@@ -58,11 +58,13 @@ def _events(fn, n=10, warm=3):
 
 
 def _traffic(kernel):
-    """dram__bytes_read + dram__bytes_write per launch from the committed ncu capture (profiles/r1_traffic.json), or None."""
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(kernel)
-    except OSError:
-        return None
+    """dram__bytes_read + dram__bytes_write per launch from the committed ncu capture (profiles/r2_traffic.json), or None."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name))).get(kernel)
+        except OSError:
+            continue
+    return None
 
 
 def measured_peaks(dev):
