@@ -552,6 +552,498 @@ d2_reduce_kernel(const float* __restrict__ warp_rows, int n_rows, const float* _
     d_packed[target] = (float)(a * (double)scale);
 }
 
+// =====================================================================================================================
+// Producer / consumer variant (round 2, second half).  The kernel above runs forward recompute (MUFU-heavy: 64 MUFU per 64-particle
+// task and net) and backward (FMA-heavy: ~210 packed FMAs) back to back in the same warp, two warps per scheduler: the XU pipe is
+// 38 % busy, the FMA pipe 46 %, and the two barely overlap (a warp needs 2860 cycles per task and net for 1250 pipe-cycles of work).
+// Here a CTA has SIXTEEN warps in two roles, and the register file is split between them with setmaxnreg:
+//   * forward warps 0-7 (80 registers): per task and net they recompute h1, h2 and the net output, do the stage algebra (state
+//     update, dout) and hand (h1, h2, dout) to their partner through a shared-memory ring of DEPTH slots;
+//   * backward warps 8-15 (176 registers: the 97 weight-gradient accumulators live only here): delta2, delta1, the 97 products per
+//     particle, d(conditioning half); per-entry layer-1 delta sums and the per-pass fold of the accumulators as before.
+// Pair w = (warp w, warp 8 + w) owns the task range the single-role kernel gave warp w.  Per slot one `full` and one `empty`
+// mbarrier; a per-pair progress counter orders the one cross-role dependency there is: the forward warp may start (pass p, task t)
+// only after the backward warp has finished (pass p - 1, task t) -- the next stage reads (and overwrites) the gradient half the
+// backward pass accumulated into.  A scheduler now holds two MUFU-heavy and two FMA-heavy warps at any time.
+// MEASURED (B = N = 1024): 200 us with a ring of depth 2, 231 us with depth 1, against 161-168 us of the single-role kernel.  ncu
+// (tools/prof_kernels.py coupling, NFDPF_D2_CFG=2): 116 M warp instructions instead of 81 M (ring / progress bookkeeping, the
+// exchange stores and loads, spin loops), issue slots 54 % (44 %), FMA pipe 29 % of instruction peak (28 %), XU 33 % (38 %); the
+// exchange ring costs two resident entries of shared memory, so a CTA's seven trajectories become two resident sets with their own
+// prologue, drain and barrier (barrier stalls 6.5 % of the samples).  The pipes do overlap better, but not by more than the extra
+// instructions cost.  NOT the default; kept selectable (NFDPF_D2_CFG=2) so the comparison can be repeated.
+constexpr int WS_NT = 512, WS_PAIRS = 8, WS_TASK = 64;
+constexpr int XSLOT = 4 * 2 * 32 * 4 + 2 * 32;          // floats per exchange slot: h1 | h2 as 16-byte chunks [chunk][u][lane], dout [u][lane]
+constexpr int WS_REG_F = 80, WS_REG_B = 176;             // 256 x 80 + 256 x 176 = the whole register file
+
+__device__ __forceinline__ void ws_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WSWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WSDONE_%=;\n\t"
+        "bra WSWAIT_%=;\n\t"
+        "WSDONE_%=:\n\t"
+        "}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ int ws_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ws_st_release(int* p, int v) {
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// forward half of net_task: recompute, stage algebra, hand-over
+template <int KIND>
+__device__ __forceinline__ void ws_f_task(const float* __restrict__ img, const float* __restrict__ hb, const StatePtrs& S, int q0, int n_rem,
+                                          float* __restrict__ slot) {
+    const int lane = threadIdx.x & 31;
+    float c[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) { c[u] = S.c[q0 + 32 * u]; live[u] = 32 * u < n_rem; }
+    u64 h1[2][4], h2[2][4];
+    {
+        u64 w1[4], hbp[4];
+        ld4(img + Img::W1, w1);
+        ld4(hb, hbp);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h1[u][i] = tanh2(fma2(w1[i], bc(c[u]), hbp[i]));
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {      // h1 is final: hand it over before layer 2 needs the registers
+        ulonglong2* d = reinterpret_cast<ulonglong2*>(slot) + (0 * 2 + u) * 32 + lane;
+        d[0] = make_ulonglong2(h1[u][0], h1[u][1]);
+        d[2 * 32] = make_ulonglong2(h1[u][2], h1[u][3]);
+    }
+    {
+        u64 a2[2][4], b2[4];
+        ld4(img + Img::B2, b2);
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a2[u][i] = b2[i];
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            u64 wr[4];
+            ld4(img + Img::W2T + 8 * k, wr);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float hk = (k & 1) ? half_of<1>(h1[u][k >> 1]) : half_of<0>(h1[u][k >> 1]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a2[u][i] = fma2(wr[i], bc(hk), a2[u][i]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h2[u][i] = tanh2(a2[u][i]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        ulonglong2* d = reinterpret_cast<ulonglong2*>(slot) + (2 * 2 + u) * 32 + lane;
+        d[0] = make_ulonglong2(h2[u][0], h2[u][1]);
+        d[2 * 32] = make_ulonglong2(h2[u][2], h2[u][3]);
+    }
+    u64 w3[4];
+    ld4(img + Img::W3, w3);
+    const float b3 = img[Img::B3];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        u64 o = fma2(w3[0], h2[u][0], P2(b3, 0.f));
+#pragma unroll
+        for (int i = 1; i < 4; ++i) o = fma2(w3[i], h2[u][i], o);
+        const float out = half_of<0>(o) + half_of<1>(o);
+        const int q = q0 + 32 * u;
+        float d;
+        if (KIND == FWD_T) {
+            d = S.gv[q];
+            if (live[u]) S.ex[q] = out;
+        } else if (KIND == FWD_S) {
+            const float t = S.ex[q], v = S.v[q], gv = S.gv[q], gld = S.gld[q];
+            const float es = exp_acc(out), ies = exp_acc(-out);
+            const float vin = (v - t) * ies;
+            d = fmaf(gv * vin, es, gld);
+            if (live[u]) { S.v[q] = vin; S.gv[q] = gv * es; }
+        } else if (KIND == INV_S) {
+            const float v = S.v[q], gv = S.gv[q], gld = S.gld[q];
+            const float es = exp_acc(out), ies = exp_acc(-out);
+            d = -fmaf(gv, v, gld);
+            if (live[u]) { S.gv[q] = gv * ies; S.ex[q] = es; }
+        } else {
+            d = -S.gv[q];
+            if (live[u]) S.v[q] = fmaf(S.v[q], S.ex[q], out);
+        }
+        slot[4 * 2 * 32 * 4 + 32 * u + lane] = live[u] ? d : 0.f;
+    }
+}
+
+// backward half of net_task (the same for all four kinds of pass): everything downstream of dout
+__device__ __forceinline__ void ws_b_task(const float* __restrict__ img, const StatePtrs& S, int q0, int n_rem,
+                                          const float* __restrict__ slot, u64 (&A)[48], float& ab3) {
+    const int lane = threadIdx.x & 31;
+    float c[2], dout[2];
+    bool live[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) { c[u] = S.c[q0 + 32 * u]; live[u] = 32 * u < n_rem; dout[u] = slot[4 * 2 * 32 * 4 + 32 * u + lane]; }
+    u64 d2[2][4];
+    {
+        u64 w3i[4];
+        ld4(img + Img::W3I, w3i);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(slot) + (2 * 2 + u) * 32 + lane;
+            const ulonglong2 x0 = sp[0], x1 = sp[2 * 32];
+            const u64 h2[4] = {x0.x, x0.y, x1.x, x1.y};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc_fma2(A[44 + i], bc(dout[u]), h2[i]);
+                const u64 g = fma2(neg2(mul2(h2[i], h2[i])), w3i[i], w3i[i]);
+                d2[u][i] = mul2(g, bc(dout[u]));
+                acc_add2(A[40 + i], d2[u][i]);
+            }
+            ab3 += dout[u];
+        }
+    }
+    u64 h1[2][4], d1[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(slot) + (0 * 2 + u) * 32 + lane;
+        const ulonglong2 x0 = sp[0], x1 = sp[2 * 32];
+        h1[u][0] = x0.x; h1[u][1] = x0.y; h1[u][2] = x1.x; h1[u][3] = x1.y;
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        u64 wr[4];
+        ld4(img + Img::W2 + 8 * j, wr);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const float dj = (j & 1) ? half_of<1>(d2[u][j >> 1]) : half_of<0>(d2[u][j >> 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                d1[u][i] = j == 0 ? mul2(wr[i], bc(dj)) : fma2(wr[i], bc(dj), d1[u][i]);
+                acc_fma2(A[8 + 4 * j + i], bc(dj), h1[u][i]);
+            }
+        }
+    }
+    {
+        u64 w1[4];
+        ld4(img + Img::W1, w1);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            u64 s = 0ull;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const u64 g = fma2(mul2(h1[u][i], h1[u][i]), bc(-TANH_ISCALE), bc(TANH_ISCALE));
+                const u64 dd = mul2(d1[u][i], g);
+                acc_fma2(A[i], bc(c[u]), dd);
+                acc_add2(A[4 + i], dd);
+                s = i == 0 ? mul2(w1[0], dd) : fma2(w1[i], dd, s);
+            }
+            const int q = q0 + 32 * u;
+            if (live[u]) S.gc[q] += half_of<0>(s) + half_of<1>(s);
+        }
+    }
+}
+
+struct WsCtx {                      // what both roles need to walk the task list of one pass
+    const int* s_task;
+    const int* s_nlive;
+    int t_lo, t_hi;
+    uint64_t* full;                 // [DEPTH] of this pair
+    uint64_t* empty;                // [DEPTH]
+    int* done;                      // the pair's progress counter (tasks the backward warp finished in this resident set)
+    float* xch;                     // the pair's exchange slots
+};
+
+template <int DEPTH, int KIND>
+__device__ __forceinline__ void ws_f_pass(const float* __restrict__ img, const float* __restrict__ s_hb_net, int hb_stride, const StatePtrs& S,
+                                          const WsCtx& W, int need0, unsigned& fill) {
+    const int lane = threadIdx.x & 31;
+    int t = W.t_lo;
+#pragma unroll 1
+    while (t < W.t_hi) {
+        const int code = W.s_task[t], e = code >> 8, m0 = code & 255, n_live = W.s_nlive[e];
+        const int seg_end = min(W.t_hi, t + (n_live + WS_TASK - 1) / WS_TASK - m0);
+        const float* hb = s_hb_net + e * hb_stride;
+        int q0 = e * CHUNK + m0 * WS_TASK + lane, n_rem = n_live - m0 * WS_TASK - lane;
+#pragma unroll 1
+        for (; t < seg_end; ++t, q0 += WS_TASK, n_rem -= WS_TASK) {
+            asm volatile("" ::: "memory");
+            if (need0 >= 0) {                                  // the backward warp has finished this task in the previous pass
+                const int need = need0 + (t - W.t_lo) + 1;
+                while (ws_ld_acquire(W.done) < need) { }
+            }
+            const unsigned sl = fill % DEPTH;
+            ws_mbar_wait(W.empty + sl, ((fill / DEPTH) & 1u) ^ 1u);
+            ws_f_task<KIND>(img, hb, S, q0, n_rem, W.xch + sl * XSLOT);
+            ws_mbar_arrive(W.full + sl);
+            ++fill;
+        }
+    }
+}
+
+template <int DEPTH>
+__device__ __forceinline__ void ws_b_pass(const float* __restrict__ img, const StatePtrs& S, const WsCtx& W, int ne, int pair,
+                                          float* __restrict__ s_d1part_net, float* __restrict__ slot_row, unsigned& cons, int& done_local) {
+    const int lane = threadIdx.x & 31;
+    u64 A[48];
+    float ab3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 48; ++i) A[i] = 0ull;
+    for (int e = 0; e < ne; ++e)
+        if (lane < H) s_d1part_net[(e * WS_PAIRS + pair) * H + lane] = 0.f;
+    __syncwarp();
+    int t = W.t_lo;
+#pragma unroll 1
+    while (t < W.t_hi) {
+        const int code = W.s_task[t], e = code >> 8, m0 = code & 255, n_live = W.s_nlive[e];
+        const int seg_end = min(W.t_hi, t + (n_live + WS_TASK - 1) / WS_TASK - m0);
+        int q0 = e * CHUNK + m0 * WS_TASK + lane, n_rem = n_live - m0 * WS_TASK - lane;
+#pragma unroll 1
+        for (; t < seg_end; ++t, q0 += WS_TASK, n_rem -= WS_TASK) {
+            asm volatile("" ::: "memory");
+            const unsigned sl = cons % DEPTH;
+            ws_mbar_wait(W.full + sl, (cons / DEPTH) & 1u);
+            ws_b_task(img, S, q0, n_rem, W.xch + sl * XSLOT, A, ab3);
+            ws_mbar_arrive(W.empty + sl);
+            ++cons;
+            __syncwarp();                                      // every lane's state update precedes the published count
+            ++done_local;
+            if (lane == 0) ws_st_release(W.done, done_local);
+        }
+        warp_flush_b1(A, s_d1part_net + (e * WS_PAIRS + pair) * H);
+    }
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) U2(A[i], acc[2 * i], acc[2 * i + 1]);
+    acc[96] = ab3;
+    warp_reduce_to_slot(acc, slot_row);
+}
+
+struct WsArgs {
+    const float* packed; int n_flows, C_row; const float* y; const float* row_ctx; int flags, B, N; const float* g_y; const float* g_ld;
+    float* d_x; float* warp_rows; float* ctx_rows; float* cta_rows; float* d_row_ctx; int e_max;
+};
+struct WsShared {
+    float (*s_slot)[100];
+    uint64_t* s_full; uint64_t* s_empty;     // [WS_PAIRS][DEPTH]
+    int* s_done;
+};
+
+// One role's whole life after the register split.  IS_F is a template parameter on purpose: the two roles must not share a single
+// instruction after setmaxnreg (ptxas allocates a region that both roles can reach for the SMALLER budget).
+template <int DEPTH, bool IS_F>
+__device__ __forceinline__ void ws_role(const WsArgs& a, float* smem, const WsShared& sh) {
+    const float* __restrict__ packed = a.packed; const float* __restrict__ y = a.y; const float* __restrict__ row_ctx = a.row_ctx;
+    const float* __restrict__ g_y = a.g_y; const float* __restrict__ g_ld = a.g_ld;
+    float* __restrict__ d_x = a.d_x; float* warp_rows = a.warp_rows; float* __restrict__ ctx_rows = a.ctx_rows;
+    float* __restrict__ cta_rows = a.cta_rows; float* __restrict__ d_row_ctx = a.d_row_ctx;
+    const int n_flows = a.n_flows, C_row = a.C_row, flags = a.flags, B = a.B, N = a.N, e_max = a.e_max;
+    (void)packed; (void)y; (void)row_ctx; (void)g_y; (void)g_ld; (void)d_x; (void)ctx_rows; (void)cta_rows; (void)d_row_ctx; (void)warp_rows;
+    constexpr bool is_f = IS_F;
+    float (*s_slot)[100] = sh.s_slot;
+    int* s_done = sh.s_done;
+    constexpr int NW = WS_PAIRS, TASK = WS_TASK, NTF = 256;    // NTF: threads of one role
+    const int n_fcnn = 4 * n_flows, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, inverse = flags & 1;
+    const int pair = warp & (WS_PAIRS - 1), rt = tid & (NTF - 1);          // rt: thread index inside the role
+    const int ctx_pad = (C_row + 3) & ~3, C1 = C_row + 1, nR = n_fcnn * H * C_row, nR1 = n_fcnn * H * C1;
+    float* s_img = smem;
+    float* s_b1 = s_img + n_fcnn * Img::SIZE;
+    float* s_w1r = s_b1 + n_fcnn * H;
+    float* s_accR = s_w1r + nR;
+    int* s_task = reinterpret_cast<int*>(s_accR + ((nR1 + 3) & ~3));
+    int* s_nlive = s_task + E_CAP * (CHUNK / 32);
+    int* s_first = s_nlive + 16;
+    long long* s_p0 = reinterpret_cast<long long*>(s_first + 16);
+    float* s_state = reinterpret_cast<float*>(s_p0 + 32);
+    float* s_hb = s_state + (size_t)NSTATE * e_max * CHUNK;
+    float* s_d1row = s_hb + (size_t)e_max * n_fcnn * H;
+    float* s_d1part = s_d1row + (size_t)e_max * n_fcnn * H;
+    float* s_ctx = s_d1part + (size_t)n_fcnn * e_max * NW * H;
+    float* s_xch = s_ctx + (((size_t)e_max * ctx_pad + 3) & ~(size_t)3);   // [WS_PAIRS][DEPTH][XSLOT]
+    const size_t plane = (size_t)e_max * CHUNK;
+    float* s_lo = s_state, *s_up = s_lo + plane, *s_glo = s_up + plane, *s_gup = s_glo + plane, *s_gld = s_gup + plane, *s_ex = s_gld + plane;
+
+    float* my_rows = warp_rows + ((size_t)blockIdx.x * NW + pair) * n_fcnn * NACC;
+    const int nc = (N + CHUNK - 1) / CHUNK;
+    const int n_traj = (B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_entries = n_traj * nc;
+    WsCtx W;
+    W.s_task = s_task; W.s_nlive = s_nlive; W.full = sh.s_full + pair * DEPTH; W.empty = sh.s_empty + pair * DEPTH; W.done = &s_done[pair];
+    W.xch = s_xch + (size_t)pair * DEPTH * XSLOT;
+    unsigned ring = 0;                // tasks produced (forward role) / consumed (backward role) so far: slot and parity of the ring
+    for (int e0 = 0; e0 < n_entries; e0 += e_max) {
+        const int ne = min(e_max, n_entries - e0);
+        if (is_f) {
+            if (rt < ne) {
+                const int j = e0 + rt, b = blockIdx.x + (j / nc) * gridDim.x, c0 = (j % nc) * CHUNK;
+                s_nlive[rt] = min(CHUNK, N - c0);
+                s_first[rt] = c0 == 0;
+                s_p0[rt] = (long long)b * N + c0;
+                s_p0[16 + rt] = b;
+            }
+        } else if (rt < WS_PAIRS) {
+            s_done[rt] = 0;
+        }
+        __syncthreads();                                                           // (1)
+        int n_tasks = 0;
+        for (int e = 0; e < ne; ++e) n_tasks += (s_nlive[e] + TASK - 1) / TASK;
+        if (is_f) {
+            for (int i = rt; i < ne * C_row; i += NTF) {
+                const int e = i / C_row, c = i - e * C_row;
+                s_ctx[e * ctx_pad + c] = row_ctx[(size_t)s_p0[16 + e] * C_row + c];
+            }
+            int nt_ = 0;
+            for (int e = 0; e < ne; ++e) {
+                const int te = (s_nlive[e] + TASK - 1) / TASK;
+                for (int m = rt; m < te; m += NTF) s_task[nt_ + m] = (e << 8) | m;
+                nt_ += te;
+            }
+        }
+        __syncthreads();                                                           // (2)
+        W.t_lo = (pair * n_tasks) / NW; W.t_hi = ((pair + 1) * n_tasks) / NW;
+        const int Tn = W.t_hi - W.t_lo;
+        if (is_f) {
+            {   // hoisted layer-1 biases
+                const int sub = rt & 3, total = ne * n_fcnn * H;
+                for (int o0 = 0; o0 < total; o0 += NTF / 4) {
+                    const int o = o0 + (rt >> 2);
+                    float a = 0.f;
+                    if (o < total) {
+                        const int e = o / (n_fcnn * H), fk = o - e * n_fcnn * H;
+                        const float* w = s_w1r + (size_t)fk * C_row;
+                        const float* cx = s_ctx + e * ctx_pad;
+                        for (int c = sub; c < C_row; c += 4) a = fmaf(w[c], cx[c], a);
+                    }
+                    a += __shfl_xor_sync(FULL, a, 1);
+                    a += __shfl_xor_sync(FULL, a, 2);
+                    if (o < total && sub == 0) s_hb[o] = a + s_b1[o % (n_fcnn * H)];
+                }
+            }
+            // particle state of the pair's own tasks (the forward warp loads what the pair will work on)
+#pragma unroll 2
+            for (int t = W.t_lo; t < W.t_hi; ++t) {
+                const int code = s_task[t], e = code >> 8, m = code & 255, n_live = s_nlive[e];
+                const size_t p0 = (size_t)s_p0[e];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int q = m * TASK + 32 * u + lane, i = e * CHUNK + q;
+                    const bool live = q < n_live;
+                    const float2 yy = live ? reinterpret_cast<const float2*>(y)[p0 + q] : make_float2(0.f, 0.f);
+                    const float2 gg = live && g_y ? reinterpret_cast<const float2*>(g_y)[p0 + q] : make_float2(0.f, 0.f);
+                    const float gl = live && g_ld ? g_ld[p0 + q] : 0.f;
+                    s_lo[i] = yy.x; s_up[i] = yy.y; s_glo[i] = gg.x; s_gup[i] = gg.y;
+                    s_gld[i] = (flags & 2) ? -gl : gl;
+                    s_ex[i] = 0.f;
+                }
+            }
+        }
+        __syncthreads();                                                           // (3) hb complete, state loaded
+        int done_local = 0;
+#pragma unroll 1
+        for (int ps = 0; ps < 4 * n_flows; ++ps) {
+            const int st = ps >> 1, second = ps & 1;
+            const int f = inverse ? st / 2 : n_flows - 1 - st / 2;
+            const int pr = inverse ? (st & 1) : 1 - (st & 1);
+            const int net = inverse ? 1 - second : second;
+            const int fm = 4 * f + 2 * pr + net;
+            const float* img = s_img + fm * Img::SIZE;
+            StatePtrs S;
+            S.c = pr ? s_up : s_lo;  S.gc = pr ? s_gup : s_glo;
+            S.v = pr ? s_lo : s_up;  S.gv = pr ? s_glo : s_gup;
+            S.gld = s_gld;           S.ex = s_ex;
+            if (is_f) {
+                const float* hbn = s_hb + fm * H;
+                const int hbs = n_fcnn * H, need0 = ps ? (ps - 1) * Tn : -1;
+                if (!inverse) {
+                    if (!net) ws_f_pass<DEPTH, FWD_T>(img, hbn, hbs, S, W, need0, ring);
+                    else      ws_f_pass<DEPTH, FWD_S>(img, hbn, hbs, S, W, need0, ring);
+                } else {
+                    if (net)  ws_f_pass<DEPTH, INV_S>(img, hbn, hbs, S, W, need0, ring);
+                    else      ws_f_pass<DEPTH, INV_T>(img, hbn, hbs, S, W, need0, ring);
+                }
+            } else {
+                float* d1p = s_d1part + (size_t)fm * e_max * NW * H;
+                float* slot = s_slot[pair];
+                ws_b_pass<DEPTH>(img, S, W, ne, pair, d1p, slot, ring, done_local);
+                __syncwarp();
+                float* row = my_rows + fm * NACC;
+                for (int k = lane; k < NACC; k += 32) row[k] = e0 == 0 ? slot[k] : row[k] + slot[k];
+                __syncwarp();
+            }
+        }
+        __syncthreads();                                                           // (4) every pass of every pair is finished
+        if (!is_f) {
+            // ---- store the pair's d_x
+#pragma unroll 2
+            for (int t = W.t_lo; t < W.t_hi; ++t) {
+                const int code = s_task[t], e = code >> 8, m = code & 255, n_live = s_nlive[e];
+                const size_t p0 = (size_t)s_p0[e];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int q = m * TASK + 32 * u + lane, i = e * CHUNK + q;
+                    if (q < n_live) reinterpret_cast<float2*>(d_x)[p0 + q] = make_float2(s_glo[i], s_gup[i]);
+                }
+            }
+            for (int o = rt; o < ne * n_fcnn * H; o += NTF) {     // fixed-order sums over the pairs
+                const int e = o / (n_fcnn * H), fk = o - e * n_fcnn * H, f = fk / H, k = fk - f * H;
+                const float* dp = s_d1part + (((size_t)f * e_max + e) * NW) * H + k;
+                float r = 0.f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) r += dp[w * H];
+                s_d1row[o] = r;
+            }
+        }
+        __syncthreads();                                                           // (5)
+        if (!is_f) {
+            for (int o = rt; o < nR1; o += NTF) {
+                const int fk = o / C1, c = o - fk * C1;
+                float a = s_accR[o];
+                for (int e = 0; e < ne; ++e) a = fmaf(s_d1row[(size_t)e * n_fcnn * H + fk], c < C_row ? s_ctx[e * ctx_pad + c] : 1.0f, a);
+                s_accR[o] = a;
+            }
+            if (d_row_ctx) {
+                for (int c = rt; c < C_row; c += NTF)
+                    for (int e = 0; e < ne; ++e) {
+                        float a = 0.f;
+                        for (int fk = 0; fk < n_fcnn * H; ++fk) a = fmaf(s_w1r[(size_t)fk * C_row + c], s_d1row[(size_t)e * n_fcnn * H + fk], a);
+                        float* dst = d_row_ctx + (size_t)s_p0[16 + e] * C_row + c;
+                        *dst = s_first[e] ? a : *dst + a;
+                    }
+            }
+        }
+        __syncthreads();                                                           // (6)
+    }
+    if (!is_f) {
+        float* out = ctx_rows + (size_t)blockIdx.x * nR1;
+        for (int e = rt; e < nR1; e += NTF) out[e] = s_accR[e];
+        const int n_acc = n_fcnn * NACC;
+        const float* mine = warp_rows + (size_t)blockIdx.x * NW * n_acc;
+        float* folded = cta_rows + (size_t)blockIdx.x * n_acc;
+        __syncwarp();
+        asm volatile("bar.sync 2, 256;" ::: "memory");            // every backward warp's global row is written (same-CTA visibility)
+        for (int c = rt; c < n_acc; c += NTF) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += mine[(size_t)w * n_acc + c];
+            folded[c] = v;
+        }
+    }
+}
+
 size_t coupling_bwd_d2_workspace_floats(int n_flows, int C_row, int B) {
     const int n_fcnn = 4 * n_flows, grid = min(B, sm_count());
     return (size_t)grid * ((size_t)(D2_MAX_WARPS + 1) * n_fcnn * NACC + (size_t)n_fcnn * H * (C_row + 1));
@@ -585,11 +1077,90 @@ static int launch_cfg(const float* packed, int n_flows, int C_row, const float* 
     return check_launch("d2_reduce");
 }
 
+
+template <int DEPTH>
+__global__ void __launch_bounds__(WS_NT, 1)
+coupling_bwd_d2_ws_kernel(WsArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_slot[WS_PAIRS][100];
+    __shared__ uint64_t s_full[WS_PAIRS][DEPTH], s_empty[WS_PAIRS][DEPTH];
+    __shared__ int s_done[WS_PAIRS];
+    {
+        const float* __restrict__ packed = a.packed;
+        const int n_flows = a.n_flows, C_row = a.C_row;
+        constexpr int NT = WS_NT;
+        const int n_fcnn = 4 * n_flows, tid = threadIdx.x;
+        const int C1 = C_row + 1, nR = n_fcnn * H * C_row, nR1 = n_fcnn * H * C1;
+        float* s_img = smem;
+        float* s_b1 = s_img + n_fcnn * Img::SIZE;
+        float* s_w1r = s_b1 + n_fcnn * H;
+        float* s_accR = s_w1r + nR;
+    const int fin = 1 + C_row, pf = packed_fcnn_size(1, C_row);
+    for (int d = tid; d < n_fcnn * Img::SIZE; d += NT) s_img[d] = img_value(packed, d / Img::SIZE, d % Img::SIZE, C_row);
+    for (int e = tid; e < n_fcnn * H; e += NT) s_b1[e] = TANH_SCALE * packed[(size_t)(e / H) * pf + H * fin + (e % H)];
+    for (int e = tid; e < nR; e += NT) {
+        const int f = e / (H * C_row), r = e - f * H * C_row;
+        s_w1r[e] = TANH_SCALE * packed[(size_t)f * pf + (r / C_row) * fin + 1 + (r % C_row)];
+    }
+    for (int e = tid; e < nR1; e += NT) s_accR[e] = 0.f;
+    if (tid < WS_PAIRS * DEPTH) { ws_mbar_init(&s_full[0][0] + tid, 32); ws_mbar_init(&s_empty[0][0] + tid, 32); }
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    }
+    const WsShared sh{s_slot, &s_full[0][0], &s_empty[0][0], s_done};
+    // the register file is re-split between the roles; from here on the two roles share no code (only barrier counts)
+    if ((threadIdx.x >> 5) < WS_PAIRS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_F));
+        ws_role<DEPTH, true>(a, smem, sh);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REG_B));
+        ws_role<DEPTH, false>(a, smem, sh);
+    }
+}
+
+template <int DEPTH>
+static int launch_ws(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, int flags, int B, int N,
+                     const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* d_packed, void* workspace,
+                     cudaStream_t st, bool* fits) {
+    const int n_fcnn = 4 * n_flows;
+    const int grid = min(B, sm_count());
+    const int nc = (N + CHUNK - 1) / CHUNK, need = ((B + grid - 1) / grid) * nc;
+    using SM = D2Smem<256>;                                   // same layout as the single-role kernel (eight accumulating warps) ...
+    const size_t xch = (size_t)WS_PAIRS * DEPTH * XSLOT * sizeof(float) + 16;   // ... plus the exchange ring
+    constexpr size_t STATIC = WS_PAIRS * 100 * sizeof(float) + 2 * WS_PAIRS * DEPTH * 8 + 64;
+    int e_max = min(E_CAP, need);
+    while (e_max > 1 && SM::bytes(n_fcnn, C_row, e_max) + xch + STATIC > 226 * 1024) --e_max;
+    const size_t smem = SM::bytes(n_fcnn, C_row, e_max) + xch;
+    *fits = smem + STATIC <= 226 * 1024;
+    if (!*fits) return NFDPF_OK;
+    auto kern = coupling_bwd_d2_ws_kernel<DEPTH>;
+    NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float* warp_rows = (float*)workspace;
+    float* ctx_rows = warp_rows + (size_t)grid * WS_PAIRS * n_fcnn * NACC;
+    float* cta_rows = ctx_rows + (size_t)grid * n_fcnn * H * (C_row + 1);
+    const WsArgs args{packed, n_flows, C_row, y, row_ctx, flags, B, N, g_y, g_ld, d_x, warp_rows, ctx_rows, cta_rows, d_row_ctx, e_max};
+    kern<<<grid, WS_NT, smem, st>>>(args);
+    int rc = check_launch("coupling_bwd_d2_ws");
+    if (rc) return rc;
+    const int n_cols = n_fcnn * NACC + n_fcnn * H * (C_row + 1);
+    d2_reduce_kernel<<<(n_cols + 31) / 32, 32 * RED_G, 0, st>>>(cta_rows, grid, ctx_rows, grid, n_fcnn, C_row, d_packed);
+    return check_launch("d2_reduce");
+}
+
 int launch_coupling_bwd_d2(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, int inverse, int B, int N,
                            const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* d_packed, void* workspace,
                            cudaStream_t st) {
     // NFDPF_D2_CFG=1 selects the one-particle-per-thread / 12-warp geometry (A/B measurements); default: two particles, 8 warps
+    // NFDPF_D2_CFG: 0 = single-role kernel (two particles per thread, 8 warps), 1 = its one-particle / 12-warp geometry,
+    // 2 / 3 = producer / consumer kernel with an exchange ring of depth 2 / 1.  Default 0: the producer / consumer kernel is parity-green
+    // but was measured SLOWER (200 / 231 us against 161-168 us at B = N = 1024) -- it stays selectable for A/B runs.
     static const int cfg = [] { const char* s = getenv("NFDPF_D2_CFG"); return s ? atoi(s) : 0; }();
+    if (cfg >= 2) {
+        bool fits = false;
+        const int rc = cfg == 3 ? launch_ws<1>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st, &fits)
+                                : launch_ws<2>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st, &fits);
+        if (rc || fits) return rc;
+    }
     if (cfg == 1)
         return launch_cfg<1, 384>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st);
     return launch_cfg<2, 256>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st);
