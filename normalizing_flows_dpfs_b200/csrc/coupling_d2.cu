@@ -225,7 +225,16 @@ __device__ __forceinline__ void net_task(const float* __restrict__ img, const fl
             dout[u] = live[u] ? d : 0.f;
         }
     }
-    if (lock) pair_sync(lock == 1 ? bar_x : bar_x + 4);
+    if (lock == 9) {      // DIAGNOSTIC (wrong results): stop after the forward half; the sums keep it alive
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            ab3 += dout[u];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { acc_add2(A[i], h1[u][i]); acc_add2(A[4 + i], h2[u][i]); }
+        }
+        return;
+    }
+    if (lock == 1 || lock == 2) pair_sync(lock == 1 ? bar_x : bar_x + 4);
     u64 d2[PPT][4];
     {   // delta2 / scale = dout (W3I - W3I h2^2); dW3 += dout h2; db2 += delta2; db3 += dout
         u64 w3i[4];
@@ -312,7 +321,7 @@ __device__ __forceinline__ void net_pass(const float* __restrict__ img, const fl
         }
         warp_flush_b1(A, s_d1part_net + (e * NW + warp) * H);
     }
-    if (lock)                                     // the partner has more tasks in this pass: keep its handshakes company
+    if (lock == 1 || lock == 2)                   // the partner has more tasks in this pass: keep its handshakes company
         for (int k = t_hi - t_lo; k < partner_tasks; ++k) { pair_sync(bar_x); pair_sync(bar_x + 4); }
     float acc[NACC];
 #pragma unroll
@@ -436,7 +445,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
         // ---- the warp's own tasks: load (each lane loads exactly the particle slots it will work on)
         const int t_lo = (warp * n_tasks) / NW, t_hi = ((warp + 1) * n_tasks) / NW;
         // phase lock: warps w and w ^ 4 sit on the same scheduler (8 warps); the lower one leads with its forward half
-        const int lock = (phase_lock && NW == 8) ? (warp < 4 ? 1 : 2) : 0;
+        const int lock = phase_lock == 9 ? 9 : (phase_lock && NW == 8) ? (warp < 4 ? 1 : 2) : 0;
         const int pw = warp ^ 4, partner_tasks = ((pw + 1) * n_tasks) / NW - (pw * n_tasks) / NW;
 #pragma unroll 2
         for (int t = t_lo; t < t_hi; ++t) {
@@ -582,23 +591,29 @@ d2_reduce_kernel(const float* __restrict__ warp_rows, int n_rows, const float* _
 // task and net) and backward (FMA-heavy: ~210 packed FMAs) back to back in the same warp, two warps per scheduler: the XU pipe is
 // 38 % busy, the FMA pipe 46 %, and the two barely overlap (a warp needs 2860 cycles per task and net for 1250 pipe-cycles of work).
 // Here a CTA has SIXTEEN warps in two roles, and the register file is split between them with setmaxnreg:
-//   * forward warps 0-7 (80 registers): per task and net they recompute h1, h2 and the net output, do the stage algebra (state
-//     update, dout) and hand (h1, h2, dout) to their partner through a shared-memory ring of DEPTH slots;
-//   * backward warps 8-15 (176 registers: the 97 weight-gradient accumulators live only here): delta2, delta1, the 97 products per
+//   * forward warps (40 registers): per task and net they recompute h1, h2 and the net output, do the stage algebra (state
+//     update, dout) and hand (h1, h2, dout) to their team's backward warp through a shared-memory ring of DEPTH slots;
+//   * backward warps (160 registers: the 97 weight-gradient accumulators live only here): delta2, delta1, the 97 products per
 //     particle, d(conditioning half); per-entry layer-1 delta sums and the per-pass fold of the accumulators as before.
-// Pair w = (warp w, warp 8 + w) owns the task range the single-role kernel gave warp w.  Per slot one `full` and one `empty`
+// Team k = (forward warps 2k and 2k + 1, one half of every 64-particle task each, and backward warp 16 + k) owns the task range the
+// single-role kernel gave warp k.  Per slot one `full` and one `empty`
 // mbarrier; a per-pair progress counter orders the one cross-role dependency there is: the forward warp may start (pass p, task t)
 // only after the backward warp has finished (pass p - 1, task t) -- the next stage reads (and overwrites) the gradient half the
 // backward pass accumulated into.  A scheduler now holds two MUFU-heavy and two FMA-heavy warps at any time.
-// MEASURED (B = N = 1024): 200 us with a ring of depth 2, 231 us with depth 1, against 161-168 us of the single-role kernel.  ncu
+// MEASURED (B = N = 1024), first form -- eight forward warps (two particles per thread, 80 registers) + eight backward warps (176):
+// 200 us with a ring of depth 2, 231 us with depth 1, against 161-168 us of the single-role kernel.  The form below -- SIXTEEN forward
+// warps (one particle per thread, 40 registers; the forward half alone was measured latency-bound: 112-125 us at 8 warps per SM against
+// 66 us for the same arithmetic in the forward kernel at 26) + eight backward warps (160: setmaxnreg.inc can only take what the CTA's
+// own warps released, 512 x (80 - 40) = 256 x (160 - 80); asking for more deadlocks) -- 210-222 us / 238-252 us.  ncu of the first form
 // (tools/prof_kernels.py coupling, NFDPF_D2_CFG=2): 116 M warp instructions instead of 81 M (ring / progress bookkeeping, the
 // exchange stores and loads, spin loops), issue slots 54 % (44 %), FMA pipe 29 % of instruction peak (28 %), XU 33 % (38 %); the
 // exchange ring costs two resident entries of shared memory, so a CTA's seven trajectories become two resident sets with their own
 // prologue, drain and barrier (barrier stalls 6.5 % of the samples).  The pipes do overlap better, but not by more than the extra
 // instructions cost.  NOT the default; kept selectable (NFDPF_D2_CFG=2) so the comparison can be repeated.
-constexpr int WS_NT = 512, WS_PAIRS = 8, WS_TASK = 64;
+constexpr int WS_PAIRS = 8, WS_TASK = 64;                 // eight teams: two forward warps (one particle per thread) + one backward warp
+constexpr int WS_FW = 2 * WS_PAIRS, WS_NT = 32 * (WS_FW + WS_PAIRS);   // 16 forward + 8 backward warps = 768 threads
 constexpr int XSLOT = 4 * 2 * 32 * 4 + 2 * 32;          // floats per exchange slot: h1 | h2 as 16-byte chunks [chunk][u][lane], dout [u][lane]
-constexpr int WS_REG_F = 80, WS_REG_B = 176;             // 256 x 80 + 256 x 176 = the whole register file
+constexpr int WS_REG_F = 40, WS_REG_B = 160;             // the backward warps can only take what the forward warps release: 512 x (80 - 40) = 256 x (160 - 80)
 
 __device__ __forceinline__ void ws_mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
@@ -628,91 +643,72 @@ __device__ __forceinline__ void ws_st_release(int* p, int v) {
     asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
-// forward half of net_task: recompute, stage algebra, hand-over
+// forward half of net_task for ONE particle per thread (slot half u of the team's 64-particle task): recompute, stage algebra,
+// hand-over.  The forward warps are many and light (48 registers) because this half is a chain of MUFU latencies: measured alone it
+// takes 112-125 us in the single-role kernel (8 warps per SM) against 66 us for the same arithmetic in the forward kernel (26 warps).
 template <int KIND>
-__device__ __forceinline__ void ws_f_task(const float* __restrict__ img, const float* __restrict__ hb, const StatePtrs& S, int q0, int n_rem,
-                                          float* __restrict__ slot) {
+__device__ __forceinline__ void ws_f_task(const float* __restrict__ img, const float* __restrict__ hb, const StatePtrs& S, int q, bool live,
+                                          float* __restrict__ slot, int u) {
     const int lane = threadIdx.x & 31;
-    float c[2];
-    bool live[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) { c[u] = S.c[q0 + 32 * u]; live[u] = 32 * u < n_rem; }
-    u64 h1[2][4], h2[2][4];
+    const float c = S.c[q];
+    u64 h1[4], h2[4];
     {
         u64 w1[4], hbp[4];
         ld4(img + Img::W1, w1);
         ld4(hb, hbp);
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h1[u][i] = tanh2(fma2(w1[i], bc(c[u]), hbp[i]));
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {      // h1 is final: hand it over before layer 2 needs the registers
-        ulonglong2* d = reinterpret_cast<ulonglong2*>(slot) + (0 * 2 + u) * 32 + lane;
-        d[0] = make_ulonglong2(h1[u][0], h1[u][1]);
-        d[2 * 32] = make_ulonglong2(h1[u][2], h1[u][3]);
+        for (int i = 0; i < 4; ++i) h1[i] = tanh2(fma2(w1[i], bc(c), hbp[i]));
     }
     {
-        u64 a2[2][4], b2[4];
-        ld4(img + Img::B2, b2);
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a2[u][i] = b2[i];
+        ulonglong2* d = reinterpret_cast<ulonglong2*>(slot) + (0 * 2 + u) * 32 + lane;
+        d[0] = make_ulonglong2(h1[0], h1[1]);
+        d[2 * 32] = make_ulonglong2(h1[2], h1[3]);
+    }
+    {
+        u64 a2[4];
+        ld4(img + Img::B2, a2);
 #pragma unroll
         for (int k = 0; k < H; ++k) {
             u64 wr[4];
             ld4(img + Img::W2T + 8 * k, wr);
+            const float hk = (k & 1) ? half_of<1>(h1[k >> 1]) : half_of<0>(h1[k >> 1]);
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const float hk = (k & 1) ? half_of<1>(h1[u][k >> 1]) : half_of<0>(h1[u][k >> 1]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) a2[u][i] = fma2(wr[i], bc(hk), a2[u][i]);
-            }
+            for (int i = 0; i < 4; ++i) a2[i] = fma2(wr[i], bc(hk), a2[i]);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h2[u][i] = tanh2(a2[u][i]);
+        for (int i = 0; i < 4; ++i) h2[i] = tanh2(a2[i]);
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    {
         ulonglong2* d = reinterpret_cast<ulonglong2*>(slot) + (2 * 2 + u) * 32 + lane;
-        d[0] = make_ulonglong2(h2[u][0], h2[u][1]);
-        d[2 * 32] = make_ulonglong2(h2[u][2], h2[u][3]);
+        d[0] = make_ulonglong2(h2[0], h2[1]);
+        d[2 * 32] = make_ulonglong2(h2[2], h2[3]);
     }
     u64 w3[4];
     ld4(img + Img::W3, w3);
-    const float b3 = img[Img::B3];
+    u64 o = fma2(w3[0], h2[0], P2(img[Img::B3], 0.f));
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        u64 o = fma2(w3[0], h2[u][0], P2(b3, 0.f));
-#pragma unroll
-        for (int i = 1; i < 4; ++i) o = fma2(w3[i], h2[u][i], o);
-        const float out = half_of<0>(o) + half_of<1>(o);
-        const int q = q0 + 32 * u;
-        float d;
-        if (KIND == FWD_T) {
-            d = S.gv[q];
-            if (live[u]) S.ex[q] = out;
-        } else if (KIND == FWD_S) {
-            const float t = S.ex[q], v = S.v[q], gv = S.gv[q], gld = S.gld[q];
-            const float es = exp_acc(out), ies = exp_acc(-out);
-            const float vin = (v - t) * ies;
-            d = fmaf(gv * vin, es, gld);
-            if (live[u]) { S.v[q] = vin; S.gv[q] = gv * es; }
-        } else if (KIND == INV_S) {
-            const float v = S.v[q], gv = S.gv[q], gld = S.gld[q];
-            const float es = exp_acc(out), ies = exp_acc(-out);
-            d = -fmaf(gv, v, gld);
-            if (live[u]) { S.gv[q] = gv * ies; S.ex[q] = es; }
-        } else {
-            d = -S.gv[q];
-            if (live[u]) S.v[q] = fmaf(S.v[q], S.ex[q], out);
-        }
-        slot[4 * 2 * 32 * 4 + 32 * u + lane] = live[u] ? d : 0.f;
+    for (int i = 1; i < 4; ++i) o = fma2(w3[i], h2[i], o);
+    const float out = half_of<0>(o) + half_of<1>(o);
+    float d;
+    if (KIND == FWD_T) {
+        d = S.gv[q];
+        if (live) S.ex[q] = out;
+    } else if (KIND == FWD_S) {
+        const float t = S.ex[q], v = S.v[q], gv = S.gv[q], gld = S.gld[q];
+        const float es = exp_acc(out), ies = exp_acc(-out);
+        const float vin = (v - t) * ies;
+        d = fmaf(gv * vin, es, gld);
+        if (live) { S.v[q] = vin; S.gv[q] = gv * es; }
+    } else if (KIND == INV_S) {
+        const float v = S.v[q], gv = S.gv[q], gld = S.gld[q];
+        const float es = exp_acc(out), ies = exp_acc(-out);
+        d = -fmaf(gv, v, gld);
+        if (live) { S.gv[q] = gv * ies; S.ex[q] = es; }
+    } else {
+        d = -S.gv[q];
+        if (live) S.v[q] = fmaf(S.v[q], S.ex[q], out);
     }
+    slot[4 * 2 * 32 * 4 + 32 * u + lane] = live ? d : 0.f;
 }
 
 // backward half of net_task (the same for all four kinds of pass): everything downstream of dout
@@ -796,16 +792,16 @@ struct WsCtx {                      // what both roles need to walk the task lis
 template <int DEPTH, int KIND>
 __device__ __forceinline__ void ws_f_pass(const float* __restrict__ img, const float* __restrict__ s_hb_net, int hb_stride, const StatePtrs& S,
                                           const WsCtx& W, int need0, unsigned& fill) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, u = (threadIdx.x >> 5) & 1;     // the team's two forward warps take the two halves of a task
     int t = W.t_lo;
 #pragma unroll 1
     while (t < W.t_hi) {
         const int code = W.s_task[t], e = code >> 8, m0 = code & 255, n_live = W.s_nlive[e];
         const int seg_end = min(W.t_hi, t + (n_live + WS_TASK - 1) / WS_TASK - m0);
         const float* hb = s_hb_net + e * hb_stride;
-        int q0 = e * CHUNK + m0 * WS_TASK + lane, n_rem = n_live - m0 * WS_TASK - lane;
+        int q = e * CHUNK + m0 * WS_TASK + 32 * u + lane, n_rem = n_live - m0 * WS_TASK - 32 * u - lane;
 #pragma unroll 1
-        for (; t < seg_end; ++t, q0 += WS_TASK, n_rem -= WS_TASK) {
+        for (; t < seg_end; ++t, q += WS_TASK, n_rem -= WS_TASK) {
             asm volatile("" ::: "memory");
             if (need0 >= 0) {                                  // the backward warp has finished this task in the previous pass
                 const int need = need0 + (t - W.t_lo) + 1;
@@ -813,7 +809,7 @@ __device__ __forceinline__ void ws_f_pass(const float* __restrict__ img, const f
             }
             const unsigned sl = fill % DEPTH;
             ws_mbar_wait(W.empty + sl, ((fill / DEPTH) & 1u) ^ 1u);
-            ws_f_task<KIND>(img, hb, S, q0, n_rem, W.xch + sl * XSLOT);
+            ws_f_task<KIND>(img, hb, S, q, n_rem > 0, W.xch + sl * XSLOT, u);
             ws_mbar_arrive(W.full + sl);
             ++fill;
         }
@@ -881,9 +877,10 @@ __device__ __forceinline__ void ws_role(const WsArgs& a, float* smem, const WsSh
     constexpr bool is_f = IS_F;
     float (*s_slot)[100] = sh.s_slot;
     int* s_done = sh.s_done;
-    constexpr int NW = WS_PAIRS, TASK = WS_TASK, NTF = 256;    // NTF: threads of one role
+    constexpr int NW = WS_PAIRS, TASK = WS_TASK, NTF = IS_F ? 32 * WS_FW : 32 * WS_PAIRS;    // NTF: threads of this role
     const int n_fcnn = 4 * n_flows, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, inverse = flags & 1;
-    const int pair = warp & (WS_PAIRS - 1), rt = tid & (NTF - 1);          // rt: thread index inside the role
+    const int pair = IS_F ? warp >> 1 : warp - WS_FW;                    // team: forward warps 2k, 2k + 1 and backward warp 16 + k
+    const int rt = IS_F ? tid : tid - 32 * WS_FW;                        // thread index inside the role
     const int ctx_pad = (C_row + 3) & ~3, C1 = C_row + 1, nR = n_fcnn * H * C_row, nR1 = n_fcnn * H * C1;
     float* s_img = smem;
     float* s_b1 = s_img + n_fcnn * Img::SIZE;
@@ -958,13 +955,13 @@ __device__ __forceinline__ void ws_role(const WsArgs& a, float* smem, const WsSh
                     if (o < total && sub == 0) s_hb[o] = a + s_b1[o % (n_fcnn * H)];
                 }
             }
-            // particle state of the pair's own tasks (the forward warp loads what the pair will work on)
+            // particle state of the team's own tasks (each forward warp loads the half it will work on)
 #pragma unroll 2
             for (int t = W.t_lo; t < W.t_hi; ++t) {
                 const int code = s_task[t], e = code >> 8, m = code & 255, n_live = s_nlive[e];
                 const size_t p0 = (size_t)s_p0[e];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                {
+                    const int u = warp & 1;
                     const int q = m * TASK + 32 * u + lane, i = e * CHUNK + q;
                     const bool live = q < n_live;
                     const float2 yy = live ? reinterpret_cast<const float2*>(y)[p0 + q] : make_float2(0.f, 0.f);
@@ -1130,13 +1127,13 @@ coupling_bwd_d2_ws_kernel(WsArgs a) {
         s_w1r[e] = TANH_SCALE * packed[(size_t)f * pf + (r / C_row) * fin + 1 + (r % C_row)];
     }
     for (int e = tid; e < nR1; e += NT) s_accR[e] = 0.f;
-    if (tid < WS_PAIRS * DEPTH) { ws_mbar_init(&s_full[0][0] + tid, 32); ws_mbar_init(&s_empty[0][0] + tid, 32); }
+    if (tid < WS_PAIRS * DEPTH) { ws_mbar_init(&s_full[0][0] + tid, 64); ws_mbar_init(&s_empty[0][0] + tid, 32); }   // two forward warps fill a slot
     if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     }
     const WsShared sh{s_slot, &s_full[0][0], &s_empty[0][0], s_done};
     // the register file is re-split between the roles; from here on the two roles share no code (only barrier counts)
-    if ((threadIdx.x >> 5) < WS_PAIRS) {
+    if ((threadIdx.x >> 5) < WS_FW) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_F));
         ws_role<DEPTH, true>(a, smem, sh);
     } else {
@@ -1188,6 +1185,8 @@ int launch_coupling_bwd_d2(const float* packed, int n_flows, int C_row, const fl
                                 : launch_ws<2>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st, &fits);
         if (rc || fits) return rc;
     }
+    if (cfg == 4)      // diagnostic: ONE warp per scheduler (how long does a warp take when it has the pipes to itself?)
+        return launch_cfg<2, 128>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st);
     if (cfg == 1)
         return launch_cfg<1, 384>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st);
     return launch_cfg<2, 256>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, d_packed, workspace, st);
