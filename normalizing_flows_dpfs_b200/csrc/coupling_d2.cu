@@ -136,24 +136,15 @@ struct StatePtrs {
 };
 
 // One task: PPT particles per lane (slots q0, q0 + 32, ...), one net.  n_rem = live particles from the lane's first slot on.
-// Phase lock (LOCK 1 / 2; 0 = off).  A task-and-net is two MUFU-bound stretches (the 2 x 16 tanh of layers 1 and 2: 512 XU cycles
-// per warp) around a short FMA stretch (layer 2), followed by a long FMA-bound stretch (deltas + 97 products: ~600 FMA-pipe cycles).
-// Two warps of one scheduler running this back to back stay IN PHASE -- contention for the pipe they both want slows them equally,
-// so they finish every stretch together -- and the measured time per task is the SUM of the XU time and the FMA time (ncu: XU 38 %,
-// FMA 46 %).  With LOCK the two warps that share a scheduler (warp w and w + 4) handshake twice per task through two 64-thread named
-// barriers so that one warp's forward half always runs against the other's backward half:
-//   warp w     (LOCK 1):  fwd(t) | X | bwd(t) | Y | fwd(t+1) | X | ...
-//   warp w + 4 (LOCK 2):         | X | fwd(t) | Y | bwd(t)   | X | fwd(t+1) ...
-// MEASURED: no gain (171 / 165 / 163 / 170 us without, 178 / 165 / 171 / 170 us with the lock for the four stack passes at
-// B = N = 1024), so the in-phase explanation is not the whole story; tools/ffma2_mix_probe.cu shows that the same packed-FMA block
-// alone reaches 2.4-2.6 cycles per FFMA2 and scheduler (80 % of the pipe) even at one warp per scheduler.  What is left is the order
-// ptxas gives the instructions at 250 registers.  Off by default (NFDPF_D2_LOCK=1 enables it for A/B runs).
-__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
+// Two diagnostics of this task body were run and removed again (they cost the default path 12 us through their run-time branches
+// and the sixteen named barriers they reserved): (a) a PHASE LOCK -- two 64-thread named barriers per task that force warp w's
+// backward half against warp w + 4's forward half (the two warps of a scheduler): 178 / 165 / 171 / 170 us against
+// 171 / 165 / 163 / 170 us without it, no gain; (b) stopping the task after its forward half: 112-125 us of the 165-180 -- the forward
+// half is a per-warp chain of MUFU and shared-memory latencies (~1200 cycles per task and net, of which the XU pipe needs 544), which
+// is why neither the lock nor a second warp per scheduler (one warp per scheduler: 187-202 us) changes much.  DESIGN.md section 3.
 template <int PPT, int KIND>
 __device__ __forceinline__ void net_task(const float* __restrict__ img, const float* __restrict__ hb, const StatePtrs& S, int q0,
-                                         int n_rem, u64 (&A)[48], float& ab3, int lock, int bar_x) {
-    if (lock == 2) pair_sync(bar_x);
+                                         int n_rem, u64 (&A)[48], float& ab3) {
     float c[PPT];
     bool live[PPT];
 #pragma unroll
@@ -225,16 +216,6 @@ __device__ __forceinline__ void net_task(const float* __restrict__ img, const fl
             dout[u] = live[u] ? d : 0.f;
         }
     }
-    if (lock == 9) {      // DIAGNOSTIC (wrong results): stop after the forward half; the sums keep it alive
-#pragma unroll
-        for (int u = 0; u < PPT; ++u) {
-            ab3 += dout[u];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { acc_add2(A[i], h1[u][i]); acc_add2(A[4 + i], h2[u][i]); }
-        }
-        return;
-    }
-    if (lock == 1 || lock == 2) pair_sync(lock == 1 ? bar_x : bar_x + 4);
     u64 d2[PPT][4];
     {   // delta2 / scale = dout (W3I - W3I h2^2); dW3 += dout h2; db2 += delta2; db3 += dout
         u64 w3i[4];
@@ -286,7 +267,6 @@ __device__ __forceinline__ void net_task(const float* __restrict__ img, const fl
             if (live[u]) S.gc[q] += half_of<0>(s) + half_of<1>(s);
         }
     }
-    if (lock == 1) pair_sync(bar_x + 4);
 }
 
 
@@ -295,10 +275,8 @@ __device__ __forceinline__ void net_task(const float* __restrict__ img, const fl
 template <int PPT, int NW, int KIND>
 __device__ __forceinline__ void net_pass(const float* __restrict__ img, const float* __restrict__ s_hb_net, int hb_stride,
                                          const StatePtrs& S, const int* __restrict__ s_task, const int* __restrict__ s_nlive,
-                                         int t_lo, int t_hi, int ne, float* __restrict__ s_d1part_net, float* __restrict__ slot,
-                                         int lock, int partner_tasks) {
+                                         int t_lo, int t_hi, int ne, float* __restrict__ s_d1part_net, float* __restrict__ slot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int bar_x = 1 + (warp & 3);            // named barriers 1-4 (X) and 5-8 (Y) of the four warp pairs
     constexpr int TASK = 32 * PPT;
     u64 A[48];
     float ab3 = 0.f;
@@ -317,12 +295,10 @@ __device__ __forceinline__ void net_pass(const float* __restrict__ img, const fl
 #pragma unroll 1
         for (; t < seg_end; ++t, q0 += TASK, n_rem -= TASK) {
             asm volatile("" ::: "memory");                   // keep the weight loads inside the loop (registers)
-            net_task<PPT, KIND>(img, hb, S, q0, n_rem, A, ab3, lock, bar_x);
+            net_task<PPT, KIND>(img, hb, S, q0, n_rem, A, ab3);
         }
         warp_flush_b1(A, s_d1part_net + (e * NW + warp) * H);
     }
-    if (lock == 1 || lock == 2)                   // the partner has more tasks in this pass: keep its handshakes company
-        for (int k = t_hi - t_lo; k < partner_tasks; ++k) { pair_sync(bar_x); pair_sync(bar_x + 4); }
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < 48; ++i) U2(A[i], acc[2 * i], acc[2 * i + 1]);
@@ -366,8 +342,7 @@ __global__ void __launch_bounds__(NT, 1)
 coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row, const float* __restrict__ y,
                        const float* __restrict__ row_ctx, int flags, int B, int N, const float* __restrict__ g_y,
                        const float* __restrict__ g_ld, float* __restrict__ d_x, float* warp_rows,
-                       float* __restrict__ ctx_rows, float* __restrict__ cta_rows, float* __restrict__ d_row_ctx, int e_max,
-                       int phase_lock) {
+                       float* __restrict__ ctx_rows, float* __restrict__ cta_rows, float* __restrict__ d_row_ctx, int e_max) {
     extern __shared__ __align__(16) float smem[];
     __shared__ float s_slot[NT / 32][100];
     constexpr int NW = NT / 32, TASK = 32 * PPT;
@@ -444,9 +419,6 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
         }
         // ---- the warp's own tasks: load (each lane loads exactly the particle slots it will work on)
         const int t_lo = (warp * n_tasks) / NW, t_hi = ((warp + 1) * n_tasks) / NW;
-        // phase lock: warps w and w ^ 4 sit on the same scheduler (8 warps); the lower one leads with its forward half
-        const int lock = phase_lock == 9 ? 9 : (phase_lock && NW == 8) ? (warp < 4 ? 1 : 2) : 0;
-        const int pw = warp ^ 4, partner_tasks = ((pw + 1) * n_tasks) / NW - (pw * n_tasks) / NW;
 #pragma unroll 2
         for (int t = t_lo; t < t_hi; ++t) {
             const int code = s_task[t], e = code >> 8, m = code & 255, n_live = s_nlive[e];
@@ -483,11 +455,11 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
             float* d1p = s_d1part + (size_t)fm * e_max * NW * H;
             float* slot = s_slot[warp];       // folded accumulators, then added to the warp's global row (resident sets accumulate)
             if (!inverse) {
-                if (!net) net_pass<PPT, NW, FWD_T>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot, lock, partner_tasks);
-                else      net_pass<PPT, NW, FWD_S>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot, lock, partner_tasks);
+                if (!net) net_pass<PPT, NW, FWD_T>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot);
+                else      net_pass<PPT, NW, FWD_S>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot);
             } else {
-                if (net)  net_pass<PPT, NW, INV_S>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot, lock, partner_tasks);
-                else      net_pass<PPT, NW, INV_T>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot, lock, partner_tasks);
+                if (net)  net_pass<PPT, NW, INV_S>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot);
+                else      net_pass<PPT, NW, INV_T>(img, hbn, hbs, S, s_task, s_nlive, t_lo, t_hi, ne, d1p, slot);
             }
             __syncwarp();
             float* row = my_rows + fm * NACC;
@@ -1091,9 +1063,7 @@ static int launch_cfg(const float* packed, int n_flows, int C_row, const float* 
     float* warp_rows = (float*)workspace;
     float* ctx_rows = warp_rows + (size_t)grid * (NT / 32) * n_fcnn * NACC;
     float* cta_rows = ctx_rows + (size_t)grid * n_fcnn * H * (C_row + 1);
-    static const int phase_lock = [] { const char* s = getenv("NFDPF_D2_LOCK"); return s ? atoi(s) : 0; }();   // measured: no gain (see net_task)
-    kern<<<grid, NT, smem, st>>>(packed, n_flows, C_row, y, row_ctx, flags, B, N, g_y, g_ld, d_x, warp_rows, ctx_rows, cta_rows, d_row_ctx, e_max,
-                                 phase_lock);
+    kern<<<grid, NT, smem, st>>>(packed, n_flows, C_row, y, row_ctx, flags, B, N, g_y, g_ld, d_x, warp_rows, ctx_rows, cta_rows, d_row_ctx, e_max);
     int rc = check_launch("coupling_bwd_d2");
     if (rc) return rc;
     const int n_cols = n_fcnn * NACC + n_fcnn * H * (C_row + 1);
