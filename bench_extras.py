@@ -193,6 +193,44 @@ def ot_metric(dev, peaks):
     return out
 
 
+def block_density_metric(dev):
+    """the block pseudo-likelihood of the semi-supervised objective (losses.py:37-70) on filter-shaped lists --
+    (T,B,N) buffers read through transposed views, sorted ancestor rows -- forward + backward: the kernel pair of csrc/losses.cu
+    next to the reference's gather chain (same tensors, same GPU, plain PyTorch)."""
+    from normalizing_flows_dpfs_b200 import losses, ops
+    B, N, T, bl = 1024, 1024, 50, 10
+    g = torch.Generator(device=dev).manual_seed(9)
+    w = torch.softmax(torch.randn(T, B, N, device=dev, generator=g) * 2, -1)
+    lik, prior = torch.randn(T, B, N, device=dev, generator=g), torch.randn(T, B, N, device=dev, generator=g) * 3 - 4
+    idx = torch.sort(torch.randint(0, N, (T, B, N), device=dev, generator=g), dim=-1).values + N * torch.arange(B, device=dev)[None, :, None]
+    lists = [x.transpose(0, 1).requires_grad_() for x in (w, lik, prior)]
+    iv = idx.transpose(0, 1)
+
+    def kern():
+        losses.pseudolikelihood_loss_nf(lists[0], None, lists[1], iv, None, lists[2], bl).backward()
+
+    def chain():
+        Q = losses._trace_blocks(lists[0], T, bl, lambda j, anc: ((lists[2][:, j] + lists[1][:, j]) if anc is None else
+                                                                  (lists[2][:, j].reshape(-1)[anc] + lists[1][:, j].reshape(-1)[anc]),
+                                                                  iv[:, j]))
+        (-Q.mean()).backward()
+    out = {"B": B, "N": N, "T": T, "block_len": bl}
+    for name, fn in (("kernel_us", kern), ("torch_gather_chain_us", chain)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / 3 * 1e3
+    out["bytes_per_particle_step"] = 16 + 12
+    out["kernel_gbs"] = B * N * T * 28 / (out["kernel_us"] * 1e-6) / 1e9
+    return out
+
+
 def roofline_and_cpu(a, dpf, resident, dev, ms_per_step):
     peaks = measured_peaks(dev)
     rows = kernel_table(a, dpf, dev)
@@ -224,6 +262,10 @@ def roofline_and_cpu(a, dpf, resident, dev, ms_per_step):
         out["ot_resample"] = ot_metric(dev, peaks)
     except Exception as e:
         out["ot_resample"] = {"error": repr(e)}
+    try:
+        out["block_density"] = block_density_metric(dev)
+    except Exception as e:  # the headline must not die on an auxiliary measurement
+        out["block_density"] = {"error": repr(e)}
     if not a.no_cpu_baseline:
         from bench_reference import cpu_filter_step, sample_shape
         cores = os.cpu_count() or 1

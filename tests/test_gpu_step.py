@@ -198,3 +198,29 @@ def test_ot_far_outlier_row_takes_the_safe_path(golden):
     xb = torch.cat([x, cu(torch.randn(3, 1024, 2, generator=g) * 20)])
     lwb = torch.cat([lw, cu(torch.log_softmax(torch.randn(3, 1024, generator=g), -1))])
     assert bool(torch.isfinite(ops.ot_resample(xb, lwb)).all())
+
+
+def test_fanout_sums_the_consumers_gradients_in_one_launch():
+    """ops.fanout: n aliases forward (no copy), ONE nfdpf_sum4 launch backward -- equal to autograd's own accumulation."""
+    from normalizing_flows_dpfs_b200 import _lib
+    g = torch.Generator().manual_seed(4)
+    for shape, n in (((64, 100, 2), 4), ((3, 7), 2), ((5, 33, 2), 3), ((2, 2), 6)):
+        x = cu(torch.randn(*shape, generator=g)).requires_grad_()
+        ws = [cu(torch.randn(*shape, generator=g)) for _ in range(n)]
+        parts = ops.fanout(x, n)
+        assert all(p.data_ptr() == x.data_ptr() for p in parts)
+        n0 = _lib.launch_count()
+        sum((p * w).sum() for p, w in zip(parts, ws)).backward()
+        assert _lib.launch_count() - n0 == (1 if n <= 4 else 2)        # four operands per summing pass
+        close(x.grad, sum(ws), rtol=1e-6, atol=1e-6, what="fanout gradient")
+    y = cu(torch.randn(4, 4))
+    assert ops.fanout(y, 3)[1] is y          # nothing to do without a gradient
+
+
+def test_weight_update_backward_writes_the_negated_copy():
+    g = torch.Generator().manual_seed(6)
+    B, N = 9, 257
+    terms = [cu(torch.randn(B, N, generator=g)).requires_grad_() for _ in range(4)]
+    logw, probs, row_sum, _ = ops.weight_update(terms[0], terms[1], terms[2], terms[3], 1e-12)
+    ((probs * cu(torch.randn(B, N, generator=g))).sum() + (logw * cu(torch.randn(B, N, generator=g))).sum() + row_sum.sum()).backward()
+    assert torch.equal(terms[3].grad, -terms[1].grad) and torch.equal(terms[1].grad, terms[2].grad)
