@@ -68,9 +68,12 @@ int nfdpf_weight_update_fwd(const float* logw_prev, const float* lki, const floa
                             void* stream);
 /* backward: g_probs (B,N) or NULL, g_logw (B,N) or NULL, g_rowsum (B,) or NULL (grad of row_stats[:,0]);
  * probs = the forward output (with add_eps).  d_logw (B,N) is the gradient of every added term; d_neg (B,N) or NULL receives
- * its negation (the gradient of the subtracted proposal term) in the same pass. */
+ * its negation (the gradient of the subtracted proposal term) in the same pass.
+ * particles (B,N,2) + g_pred (B,2), both or neither: the gradient of a prediction pred[b] = sum_n probs[b,n] particles[b,n]
+ * (losses.py:22) that the measurement kernel formed in its epilogue reaches probs as <g_pred[b], particles[b,n]>. */
 int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw, const float* g_rowsum, const float* probs,
-                            float add_eps, int B, int N, float* d_logw, float* d_neg, void* stream);
+                            float add_eps, int B, int N, float* d_logw, float* d_neg, const float* particles,
+                            const float* g_pred, void* stream);
 
 /* ---- (K1) fused coupling stack: nf/flows.py:155-179, 215-239; nf/models.py:11-30, 45-61 ---------------
  * x (P,D); context = [row_ctx (B,C_row) broadcast over the N particles of a row | part_ctx (P,C_part)],
@@ -106,20 +109,24 @@ int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C
  * logw_out (B,N) (may be NULL), probs_out (B,N), row_stats (B,2).
  * z_out (B,N,hidden) or NULL (mode 2 only): the flow output z, which nfdpf_measure_bwd can take as z_saved to walk the
  * stack backwards without re-running it forward (128 B / particle of HBM for ~13 % fewer backward instructions).
+ * pred_out (B,2) or NULL (fused update only): the prediction of the supervised loss, sum_n probs[b,n] particles[b,n,:]
+ * (losses.py:22), formed in the kernel's epilogue while the row is still L2-hot.
  * Implementation note: encoder layers 2-3 run on the tcgen05 tensor cores (3xTF32); every CTA of the forward / backward
  * allocates 128 / 256 tensor-memory columns for its lifetime (sm_100a only). */
 int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
                       const float* enc, const float* particles, int B, int N, int hidden, const float* logw_prev,
                       const float* prior, const float* propose, float add_eps, float* lki, int32_t* argmax,
-                      float* logw_out, float* probs_out, float* row_stats, float* z_out, void* stream);
+                      float* logw_out, float* probs_out, float* row_stats, float* z_out, float* pred_out, void* stream);
 /* backward of lki w.r.t. particles (B,N,2), enc (B,hidden; may be NULL: detached), particle-encoder and cnf
  * parameters (every entry of d_pe / d_cnf is WRITTEN, sums formed in a fixed order: deterministic).  g_lki (B,N) is the total gradient reaching lki
- * (the caller adds the weight-update gradient from nfdpf_weight_update_bwd when the update was fused). */
+ * (the caller adds the weight-update gradient from nfdpf_weight_update_bwd when the update was fused).
+ * g_pred (B,2) + probs (B,N), both or neither: the gradient of the fused prediction reaches the particles as g_pred[b] probs[b,n]
+ * and is added to d_particles in the same pass. */
 int64_t nfdpf_measure_bwd_workspace(int mode, int n_flows, int B, int N);
 int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
                       const float* enc, const float* particles, int B, int N, int hidden, const float* g_lki,
                       const int32_t* argmax, float* d_particles, float* d_enc, float* d_pe, float* d_cnf,
-                      void* workspace, const float* z_saved, void* stream);
+                      void* workspace, const float* z_saved, const float* g_pred, const float* probs, void* stream);
 
 /* ---- per-trajectory particle moments: the detached flow context of model/models.py:309-310, 338-339 ----
  * out[b, out_off + k] = mean_n x[b,n,k], out[b, out_off + d + k] = unbiased std_n x[b,n,k]; out has row stride

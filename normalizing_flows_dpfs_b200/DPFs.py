@@ -242,7 +242,7 @@ class DPF(nn.Module):
                         identity_idx = torch.arange(B * N, device=dev, dtype=torch.int64).reshape(B, N)
                     buf["index"][step].copy_(identity_idx)
             noise = inj["noise"][:, step] if "noise" in inj else None
-            x_pred = None
+            pred = None
             if enc_steps is not None:
                 encodings = enc_steps[step]
             else:
@@ -266,31 +266,31 @@ class DPF(nn.Module):
                     particles_dynamical, jac = self.nf_dyn.run_stack(particles_physical, row_ctx=ctx_phys, inverse=True, neg_logdet=True, out=o)
                 else:
                     particles_dynamical, jac = particles_physical, None
-                mo = {"lki": buf["lki"][step], "probs": buf["probs"][step]}
+                mo = {"lki": buf["lki"][step], "probs": buf["probs"][step], "pred": buf["pred"][step]}
                 if self.NFcond:
                     ctx_prop = torch.empty(B, self.hidden_size + 4, **f32)
                     ctx_prop[:, :self.hidden_size] = encodings.detach()      # proposal sees a detached encoding, models.py:360-361
                     ops.row_moments(particles_dynamical, ctx_prop, self.hidden_size)
                     propose_particle, jac_prop = self.cond_model.run_stack(particles_dynamical, row_ctx=ctx_prop, inverse=True, neg_logdet=True,
                                                                            out={"y": buf["particles"][step]})
-                    # the proposal has four consumers (dynamics flow, measurement, prediction, next step): one alias each, their
-                    # gradients meet in one summing launch instead of three chained autograd adds
-                    x_back, x_meas, x_pred, propose_particle = ops.fanout(propose_particle, 4)
+                    # the proposal has three consumers (dynamics flow, measurement + prediction, next step): one alias each, their
+                    # gradients meet in one summing launch instead of chained autograd adds
+                    x_back, x_meas, propose_particle = ops.fanout(propose_particle, 3)
                     if self.NF:   # push the proposal back through the dynamics flow (context: moments of the physical cloud)
                         back, jac_back = self.nf_dyn.run_stack(x_back, row_ctx=ctx_phys, inverse=False, neg_logdet=True)
                     else:
                         back, jac_back = x_back, None
                     prior_log, propose_log = ops.proposal_terms(back, particles_physical, noise, jac_back, jac, jac_prop, self.pos_noise,
                                                                 {"prior": buf["prior"][step]} if self.NF else None)
-                    lki_log, logw, particle_probs, row_sum, ess_inv = self.measurement_model.forward_update(
-                        encodings, x_meas, logw_prev, prior_log, propose_log, out=mo)
+                    lki_log, logw, particle_probs, row_sum, ess_inv, pred = self.measurement_model.forward_update(
+                        encodings, x_meas, logw_prev, prior_log, propose_log, out=mo, want_pred=True)
                 else:             # prior == proposal density: the two cancel exactly in DPFs.py:187
                     propose_particle = particles_dynamical
                     if self.NF:
                         _, prior_log = ops.proposal_terms(particles_physical, particles_physical, noise, None, jac, None, self.pos_noise,
                                                           {"propose": buf["prior"][step]})
-                    lki_log, logw, particle_probs, row_sum, ess_inv = self.measurement_model.forward_update(
-                        encodings, propose_particle, logw_prev, None, None, out=mo)
+                    lki_log, logw, particle_probs, row_sum, ess_inv, pred = self.measurement_model.forward_update(
+                        encodings, propose_particle, logw_prev, None, None, out=mo, want_pred=True)
             else:
                 particles_physical, noise = self.motion_update(particles, vel, pos_noise=self.pos_noise, noise=noise)
                 if "noise" in buf:
@@ -309,7 +309,8 @@ class DPF(nn.Module):
             particles = propose_particle
             put("particles", step, particles)
             row_sums.append(row_sum)
-            pred = ops.weighted_mean(x_pred if x_pred is not None else particles, particle_probs, {"pred": buf["pred"][step]})
+            if pred is None:     # non-fused paths: the prediction of losses.py:22 as its own kernel (fused paths: measurement epilogue)
+                pred = ops.weighted_mean(particles, particle_probs, {"pred": buf["pred"][step]})
             for k, v in (("particles", particles), ("probs", particle_probs), ("lki", lki_log), ("pred", pred)):
                 steps[k].append(v)
             if self.NF:

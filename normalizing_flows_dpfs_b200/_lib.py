@@ -21,7 +21,7 @@ SIGNATURES = {
     "nfdpf_proposal_terms_fwd": (_I, [_P, _P, _P, _P, _P, _P, _F, _I64, _P, _P, _P]),
     "nfdpf_proposal_terms_bwd": (_I, [_P, _P, _P, _P, _F, _I64, _P, _P, _P, _P]),
     "nfdpf_weight_update_fwd": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P]),
-    "nfdpf_weight_update_bwd": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P]),
+    "nfdpf_weight_update_bwd": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P]),
     "nfdpf_sum4": (_I, [_P, _P, _P, _P, _I64, _P, _P]),
     "nfdpf_row_moments": (_I, [_P, _I, _I, _I, _P, _I, _I, _P]),
     "nfdpf_ot_workspace": (_I64, [_I, _I]),
@@ -39,9 +39,9 @@ SIGNATURES = {
     "nfdpf_peak_probe": (_I64, [_I, _I, _P, _P]),
     "nfdpf_coupling_fwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "nfdpf_coupling_bwd_workspace": (_I64, [_I, _I, _I, _I, _I, _I]),
-    "nfdpf_measure_fwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "nfdpf_measure_fwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nfdpf_measure_bwd_workspace": (_I64, [_I, _I, _I, _I]),
-    "nfdpf_measure_bwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nfdpf_measure_bwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nfdpf_coupling_bwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 _lib = None

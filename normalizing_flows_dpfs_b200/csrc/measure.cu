@@ -382,7 +382,7 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                    const float* __restrict__ enc, const float* __restrict__ particles, int N, const float* __restrict__ lw0,
                    const float* __restrict__ prior, const float* __restrict__ propose, float add_eps, float* __restrict__ lki,
                    int* __restrict__ argmax, float* __restrict__ logw_out, float* __restrict__ probs_out,
-                   float* __restrict__ row_stats, float* __restrict__ z_out) {
+                   float* __restrict__ row_stats, float* __restrict__ z_out, float* __restrict__ pred_out) {
     extern __shared__ __align__(128) float smem[];
     __shared__ float s_red[33];
     __shared__ int s_redi[33];
@@ -471,6 +471,17 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     for (int n = tid; n < N; n += TP) { const float p = __fdiv_rn(s_ll[n], se) + add_eps; probs_out[base + n] = p; s2 = fmaf(p, p, s2); }
     s2 = block_allreduce(s2, s_red, OpSum(), 0.f);
     if (tid == 0 && row_stats) { row_stats[2 * b] = sl; row_stats[2 * b + 1] = 1.0f / s2; }
+    if (pred_out) {      // the prediction of the supervised loss, sum_n probs[n] particles[n] (losses.py:22): the row is still L2-hot
+        float px = 0.f, py = 0.f;
+        for (int n = tid; n < N; n += TP) {
+            const float pr = probs_out[base + n];           // written by this thread above
+            const float2 x = *reinterpret_cast<const float2*>(particles + (base + n) * 2);
+            px = fmaf(pr, x.x, px); py = fmaf(pr, x.y, py);
+        }
+        px = block_allreduce(px, s_red, OpSum(), 0.f);
+        py = block_allreduce(py, s_red, OpSum(), 0.f);
+        if (tid == 0) { pred_out[2 * b] = px; pred_out[2 * b + 1] = py; }
+    }
 }
 
 // ----------------------------------------------------------------------------------------------- backward
@@ -663,7 +674,8 @@ __global__ void __launch_bounds__(TP, 2)   // two CTAs per SM (256 tensor-memory
 measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, int n_flows, float p0, float p1,
                    const float* __restrict__ enc, const float* __restrict__ particles, int B, int N,
                    const float* __restrict__ g_lki, const int* __restrict__ argmax, float* __restrict__ d_particles,
-                   float* __restrict__ d_enc, float* __restrict__ part_pe, float* __restrict__ part_cnf, const float* __restrict__ z_saved) {
+                   float* __restrict__ d_enc, float* __restrict__ part_pe, float* __restrict__ part_cnf, const float* __restrict__ z_saved,
+                   const float* __restrict__ g_pred, const float* __restrict__ probs) {
     extern __shared__ __align__(128) float smem[];
     __shared__ float s_red[33];
     __shared__ uint64_t s_bar;
@@ -825,7 +837,13 @@ measure_bwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
                 dx0 = fmaf(q.x, d1[k], dx0); dx1 = fmaf(q.y, d1[k], dx1);
                 dx0 = fmaf(q.z, d1[k + 1], dx0); dx1 = fmaf(q.w, d1[k + 1], dx1);
             }
-            if (live) *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
+            if (live) {
+                if (g_pred) {      // fused prediction (losses.py:22): d pred / d x_n = probs[n]
+                    const float pr = probs[p];
+                    dx0 = fmaf(g_pred[2 * b], pr, dx0); dx1 = fmaf(g_pred[2 * b + 1], pr, dx1);
+                }
+                *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
+            }
             // weight gradients: the warp contracts over its own 32 tile columns, no CTA barrier between the two phases
             s_tile[PR::ONE * TSM + tid] = 1.0f;
             s_tile[PR::ZERO * TSM + tid] = 0.0f;
@@ -925,7 +943,7 @@ __global__ void __launch_bounds__(WS_THREADS, 2)
 measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const float* __restrict__ enc,
                       const float* __restrict__ particles, int B, int N, const float* __restrict__ g_lki,
                       const int* __restrict__ argmax, float* __restrict__ d_particles, float* __restrict__ d_enc,
-                      float* __restrict__ part_pe) {
+                      float* __restrict__ part_pe, const float* __restrict__ g_pred, const float* __restrict__ probs) {
     static_assert(MODE == MODE_GAUSS || MODE == MODE_COS, "CRNVP keeps the single-role kernel");
     extern __shared__ __align__(128) float smem[];
     __shared__ float s_red[8];
@@ -1068,7 +1086,13 @@ measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const fl
                     dx0 = fmaf(q.x, d1[k], dx0); dx1 = fmaf(q.y, d1[k], dx1);
                     dx0 = fmaf(q.z, d1[k + 1], dx0); dx1 = fmaf(q.w, d1[k + 1], dx1);
                 }
-                if (live) *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
+                if (live) {
+                    if (g_pred) {      // fused prediction (losses.py:22): d pred / d x_n = probs[n]
+                        const float pr = probs[p];
+                        dx0 = fmaf(g_pred[2 * b], pr, dx0); dx1 = fmaf(g_pred[2 * b + 1], pr, dx1);
+                    }
+                    *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
+                }
                 // stage phase B (its rows alias phase A's: the gradient warp has finished phase A)
                 umma::mbar_wait(&s_empty[pw], ph_empty); ph_empty ^= 1;
                 stage(PR::X + 0, x.x);
@@ -1145,13 +1169,13 @@ static size_t bwd_smem(int mode, int n_flows) {
 template <int MODE>
 static int launch_measure_fwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,
                               int B, int N, const float* lw0, const float* prior, const float* propose, float add_eps, float* lki,
-                              int* argmax, float* logw_out, float* probs_out, float* row_stats, float* z_out, cudaStream_t st) {
+                              int* argmax, float* logw_out, float* probs_out, float* row_stats, float* z_out, float* pred_out, cudaStream_t st) {
     const size_t smem = fwd_smem(MODE, n_flows, N);
     if (smem > 220 * 1024) { set_error("measure_fwd: N=%d too large for the shared-memory row buffer", N); return NFDPF_ERR_UNSUPPORTED; }
     auto kern = measure_fwd_kernel<MODE>;
     if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, N, lw0, prior, propose, add_eps, lki, argmax, logw_out, probs_out,
-                              row_stats, z_out);
+                              row_stats, z_out, pred_out);
     return check_launch("measure_fwd");
 }
 
@@ -1161,16 +1185,16 @@ static int measure_bwd_grid(int mode, int B) { (void)mode; return min(B, 2 * sm_
 template <int MODE>
 static void launch_measure_bwd_ws(const float* pe, float p0, float p1, const float* enc, const float* particles, int B, int N,
                                   const float* g_lki, const int* argmax, float* d_particles, float* d_enc, float* part_pe, int grid,
-                                  size_t smem, cudaStream_t st) {
+                                  size_t smem, const float* g_pred, const float* probs, cudaStream_t st) {
     auto kern = measure_bwd_ws_kernel<MODE>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, WS_THREADS, smem, st>>>(pe, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe);
+    kern<<<grid, WS_THREADS, smem, st>>>(pe, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, g_pred, probs);
 }
 
 template <int MODE>
 static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,
                               int B, int N, const float* g_lki, const int* argmax, float* d_particles, float* d_enc, float* d_pe,
-                              float* d_cnf, void* workspace, const float* z_saved, cudaStream_t st) {
+                              float* d_cnf, void* workspace, const float* z_saved, const float* g_pred, const float* probs, cudaStream_t st) {
     const size_t smem = bwd_smem(MODE, n_flows);
     const int grid = measure_bwd_grid(MODE, B);
     float* part_pe = (float*)workspace;
@@ -1179,11 +1203,12 @@ static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, fl
     if (MODE == MODE_GAUSS && !single_role) {     // (cos: its 32 running d_enc sums per thread spill at 128 registers -- measured slower)
         const size_t ws_smem = smem;
         launch_measure_bwd_ws<MODE == MODE_CNF ? MODE_GAUSS : MODE>(pe, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe,
-                                                                     grid, ws_smem, st);
+                                                                     grid, ws_smem, g_pred, probs, st);
     } else {
         auto kern = measure_bwd_kernel<MODE>;
         if (smem > 48 * 1024) NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, part_cnf, z_saved);
+        kern<<<grid, TP, smem, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, part_cnf, z_saved,
+                                     g_pred, probs);
     }
     int rc = check_launch("measure_bwd");
     if (rc) return rc;
@@ -1200,15 +1225,16 @@ using namespace nfdpf;
 extern "C" int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
                                  const float* enc, const float* particles, int B, int N, int hidden, const float* logw_prev,
                                  const float* prior, const float* propose, float add_eps, float* lki, int32_t* argmax,
-                                 float* logw_out, float* probs_out, float* row_stats, float* z_out, void* stream) {
+                                 float* logw_out, float* probs_out, float* row_stats, float* z_out, float* pred_out, void* stream) {
     NFDPF_REQUIRE(pe_packed && enc && particles && lki, "measure_fwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0, "measure_fwd: B and N must be positive");
     NFDPF_REQUIRE(mode >= 0 && mode <= 2, "measure_fwd: mode must be 0 (gaussian), 1 (cos) or 2 (CRNVP), got %d", mode);
     NFDPF_REQUIRE(mode != MODE_CNF || (cnf_packed && n_flows >= 1 && n_flows <= 4), "measure_fwd: CRNVP needs a packed stack, 1..4 flows");
     NFDPF_REQUIRE(!logw_prev || probs_out, "measure_fwd: fused update needs probs_out");
+    NFDPF_REQUIRE(!pred_out || logw_prev, "measure_fwd: the fused prediction needs the fused weight update");
     if (hidden != HID) { set_error("measure_fwd: kernels are built for hiddensize 32 (got %d)", hidden); return NFDPF_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
-#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, logw_prev, prior, propose, add_eps, lki, argmax, logw_out, probs_out, row_stats, z_out, st
+#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, logw_prev, prior, propose, add_eps, lki, argmax, logw_out, probs_out, row_stats, z_out, pred_out, st
     if (mode == MODE_GAUSS) return launch_measure_fwd<MODE_GAUSS>(ARGS);
     if (mode == MODE_COS) return launch_measure_fwd<MODE_COS>(ARGS);
     return launch_measure_fwd<MODE_CNF>(ARGS);
@@ -1225,15 +1251,16 @@ extern "C" int64_t nfdpf_measure_bwd_workspace(int mode, int n_flows, int B, int
 extern "C" int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed, int n_flows, float p0, float p1,
                                  const float* enc, const float* particles, int B, int N, int hidden, const float* g_lki,
                                  const int32_t* argmax, float* d_particles, float* d_enc, float* d_pe, float* d_cnf, void* workspace,
-                                 const float* z_saved, void* stream) {
+                                 const float* z_saved, const float* g_pred, const float* probs, void* stream) {
     NFDPF_REQUIRE(pe_packed && enc && particles && g_lki && d_particles && d_pe && workspace, "measure_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0, "measure_bwd: B and N must be positive");
     NFDPF_REQUIRE(mode >= 0 && mode <= 2, "measure_bwd: bad mode %d", mode);
     NFDPF_REQUIRE(mode == MODE_COS || argmax, "measure_bwd: argmax required for max-shifted likelihoods");
+    NFDPF_REQUIRE(!g_pred || probs, "measure_bwd: the fused prediction gradient needs the forward's probs");
     NFDPF_REQUIRE(mode != MODE_CNF || (cnf_packed && d_cnf && n_flows >= 1 && n_flows <= 4), "measure_bwd: CRNVP needs packed stack + gradient buffer");
     if (hidden != HID) { set_error("measure_bwd: kernels are built for hiddensize 32 (got %d)", hidden); return NFDPF_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
-#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, d_pe, d_cnf, workspace, z_saved, st
+#define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, d_pe, d_cnf, workspace, z_saved, g_pred, probs, st
     if (mode == MODE_GAUSS) return launch_measure_bwd<MODE_GAUSS>(ARGS);
     if (mode == MODE_COS) return launch_measure_bwd<MODE_COS>(ARGS);
     return launch_measure_bwd<MODE_CNF>(ARGS);

@@ -56,22 +56,32 @@ __global__ void weight_update_fwd_kernel(const float* __restrict__ lw0, const fl
 template <bool BLOCK_PER_ROW>
 __global__ void weight_update_bwd_kernel(const float* __restrict__ g_probs, const float* __restrict__ g_logw,
                                          const float* __restrict__ g_rowsum, const float* __restrict__ probs, float add_eps,
-                                         int B, int N, float* __restrict__ d_logw, float* __restrict__ d_neg) {
+                                         int B, int N, float* __restrict__ d_logw, float* __restrict__ d_neg,
+                                         const float* __restrict__ particles, const float* __restrict__ g_pred) {
     __shared__ float s_red[33];
     const int lane = threadIdx.x & 31;
     const int row = BLOCK_PER_ROW ? blockIdx.x : blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (!BLOCK_PER_ROW && row >= B) return;
     const int t0 = BLOCK_PER_ROW ? threadIdx.x : lane, stride = BLOCK_PER_ROW ? blockDim.x : 32;
     const size_t base = (size_t)row * N;
+    // gradient reaching probs[n]: the caller's g_probs plus, with the fused prediction (losses.py:22), <g_pred[row], particles[n]>
+    float gx = 0.f, gy = 0.f;
+    if (g_pred) { gx = g_pred[2 * row]; gy = g_pred[2 * row + 1]; }
+    auto gp = [&](int n) {
+        float g = g_probs ? g_probs[base + n] : 0.f;
+        if (g_pred) { const float2 x = *reinterpret_cast<const float2*>(particles + (base + n) * 2); g = fmaf(gx, x.x, fmaf(gy, x.y, g)); }
+        return g;
+    };
+    const bool has_gp = g_probs || g_pred;
     float dot = 0.f;
-    if (g_probs)
-        for (int n = t0; n < N; n += stride) dot += g_probs[base + n] * (probs[base + n] - add_eps);
+    if (has_gp)
+        for (int n = t0; n < N; n += stride) dot += gp(n) * (probs[base + n] - add_eps);
     if (BLOCK_PER_ROW) dot = block_allreduce(dot, s_red, OpSum(), 0.f);
     else dot = warp_sum(dot);
     const float gr = g_rowsum ? g_rowsum[row] : 0.f;
     for (int n = t0; n < N; n += stride) {
         float v = gr;
-        if (g_probs) v += (probs[base + n] - add_eps) * (g_probs[base + n] - dot);
+        if (has_gp) v += (probs[base + n] - add_eps) * (gp(n) - dot);
         if (g_logw) v += g_logw[base + n];
         d_logw[base + n] = v;
         if (d_neg) d_neg[base + n] = -v;      // the proposal term enters with a minus sign (DPFs.py:187)
@@ -100,16 +110,18 @@ extern "C" int nfdpf_weight_update_fwd(const float* logw_prev, const float* lki,
 }
 
 extern "C" int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw, const float* g_rowsum, const float* probs,
-                                       float add_eps, int B, int N, float* d_logw, float* d_neg, void* stream) {
+                                       float add_eps, int B, int N, float* d_logw, float* d_neg, const float* particles, const float* g_pred,
+                                       void* stream) {
     NFDPF_REQUIRE(probs && d_logw, "weight_update_bwd: null pointer");
+    NFDPF_REQUIRE(!g_pred || particles, "weight_update_bwd: the fused prediction gradient needs the particles");
     NFDPF_REQUIRE(B > 0 && N > 0, "weight_update_bwd: B and N must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     if (N <= 1024) {
         const int wpb = 8;
         weight_update_bwd_kernel<false><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N,
-                                                                                  d_logw, d_neg);
+                                                                                  d_logw, d_neg, particles, g_pred);
     } else {
-        weight_update_bwd_kernel<true><<<B, 512, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N, d_logw, d_neg);
+        weight_update_bwd_kernel<true><<<B, 512, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N, d_logw, d_neg, particles, g_pred);
     }
     return check_launch("weight_update_bwd");
 }
@@ -135,11 +147,40 @@ __global__ void row_moments_kernel(const float* __restrict__ x, int B, int N, in
         }
     }
 }
+// d == 2, N <= 8 * 256: the row is read ONCE (float2 per particle, up to eight per thread, kept in registers); both means come out of
+// one pair of block reductions, both variances out of a second one -- two round trips instead of the generic kernel's four passes.
+__global__ void __launch_bounds__(256) row_moments2_kernel(const float* __restrict__ x, int N, float* __restrict__ out, int out_stride,
+                                                           int out_off) {
+    __shared__ float s_red[33];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float2* xr = reinterpret_cast<const float2*>(x) + (size_t)b * N;
+    float2 v[8];
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = tid + 256 * i;
+        v[i] = n < N ? xr[n] : make_float2(0.f, 0.f);
+        sx += v[i].x; sy += v[i].y;
+    }
+    const float mx = block_allreduce(sx, s_red, OpSum(), 0.f) / (float)N, my = block_allreduce(sy, s_red, OpSum(), 0.f) / (float)N;
+    float vx = 0.f, vy = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (tid + 256 * i < N) { const float tx = v[i].x - mx, ty = v[i].y - my; vx = fmaf(tx, tx, vx); vy = fmaf(ty, ty, vy); }
+    vx = block_allreduce(vx, s_red, OpSum(), 0.f);
+    vy = block_allreduce(vy, s_red, OpSum(), 0.f);
+    if (tid == 0) {
+        float* o = out + (size_t)b * out_stride + out_off;
+        o[0] = mx; o[1] = my;
+        o[2] = sqrtf(vx / (float)(N - 1)); o[3] = sqrtf(vy / (float)(N - 1));     // N == 1 -> NaN like torch.std
+    }
+}
 }  // namespace nfdpf
 
 extern "C" int nfdpf_row_moments(const float* x, int B, int N, int d, float* out, int out_stride, int out_off, void* stream) {
     NFDPF_REQUIRE(x && out, "row_moments: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0 && out_stride >= out_off + 2 * d && out_off >= 0, "row_moments: bad sizes");
-    nfdpf::row_moments_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, B, N, d, out, out_stride, out_off);
+    if (d == 2 && N <= 8 * 256) nfdpf::row_moments2_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, N, out, out_stride, out_off);
+    else nfdpf::row_moments_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, B, N, d, out, out_stride, out_off);
     return nfdpf::check_launch("row_moments");
 }

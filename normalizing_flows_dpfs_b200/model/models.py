@@ -180,11 +180,11 @@ class _FusedMeasurement(nn.Module):
         p0, p1, n_flows = self.params()
         return ops.measure(self.pe_packed(), self.cnf_packed(), encodings, update_particles, self.mode, n_flows, p0, p1)
 
-    def forward_update(self, encodings, update_particles, logw_prev, prior_log, propose_log, add_eps=1e-12, out=None):
-        """measurement + DPFs.py:187-192 in one kernel: (lki, logw, probs, row_sum_logw, ess_inv)."""
+    def forward_update(self, encodings, update_particles, logw_prev, prior_log, propose_log, add_eps=1e-12, out=None, want_pred=False):
+        """measurement + DPFs.py:187-192 in one kernel: (lki, logw, probs, row_sum_logw, ess_inv[, prediction of losses.py:22])."""
         p0, p1, n_flows = self.params()
         return ops.measure_update(self.pe_packed(), self.cnf_packed(), encodings, update_particles, logw_prev, prior_log, propose_log,
-                                  self.mode, n_flows, p0, p1, add_eps, out)
+                                  self.mode, n_flows, p0, p1, add_eps, out, want_pred)
 
 
 class measurement_model_cosine_distance(_FusedMeasurement):

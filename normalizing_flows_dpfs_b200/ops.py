@@ -93,7 +93,7 @@ class WeightUpdate(torch.autograd.Function):
         d = torch.empty_like(probs)
         dn = torch.empty_like(probs) if ctx.has[2] else None
         L.call("nfdpf_weight_update_bwd", L.ptr(g_probs), L.ptr(g_logw), L.ptr(g_rowsum), L.ptr(probs), ctx.add_eps, B, N,
-               L.ptr(d), L.ptr(dn), L.stream())
+               L.ptr(d), L.ptr(dn), None, None, L.stream())
         return d, (d if ctx.has[0] else None), (d if ctx.has[1] else None), dn, None, None
 
 
@@ -163,10 +163,11 @@ class MeasureUpdate(torch.autograd.Function):
     """Measurement log-likelihood (model/models.py:206-278) fused with DPFs.py:187-192 when logw_prev is given.
 
     pe: packed particle encoder (1648,), cnf: packed D=32/C=32 stack or None, enc (B,32), particles (B,N,2).
-    Returns (lki, logw, probs, row_sum, ess_inv); the last four are None-like zeros-size when not fused."""
+    Returns (lki, logw, probs, row_sum, ess_inv, pred); all but lki are None when not fused, pred (B,2) = sum_n probs particles
+    (the prediction of the supervised loss, losses.py:22, formed in the kernel's epilogue) is None unless want_pred."""
 
     @staticmethod
-    def forward(ctx, pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows, p0, p1, add_eps, out=None):
+    def forward(ctx, pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows, p0, p1, add_eps, out=None, want_pred=False):
         B, N, d = particles.shape
         if d != 2:
             raise ValueError("measurement kernels take 2-d particle states (DPFs.py:31), got d=%d" % d)
@@ -185,34 +186,36 @@ class MeasureUpdate(torch.autograd.Function):
         logw = torch.empty(B, N, dtype=torch.float32, device=dev) if fused else None
         probs = _out(out, "probs", shape=(B, N), device=dev) if fused else None
         stats = torch.empty(B, 2, dtype=torch.float32, device=dev) if fused else None
+        pred = _out(out, "pred", shape=(B, 2), device=dev) if (fused and want_pred) else None
         need_grad = any(ctx.needs_input_grad[:4])
         z = torch.empty(B, N, hidden, dtype=torch.float32, device=dev) if (mode == 2 and need_grad) else None   # flow output, for the backward
         L.call("nfdpf_measure_fwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, float(p0), float(p1), L.ptr(enc_), L.ptr(x_), B, N, hidden,
                L.ptr(lw0), L.ptr(pr), L.ptr(pp), float(add_eps), L.ptr(lki), L.ptr(argmax), L.ptr(logw), L.ptr(probs), L.ptr(stats),
-               L.ptr(z), L.stream())
+               L.ptr(z), L.ptr(pred), L.stream())
         ctx.save_for_backward(pe_, cnf_, enc_, x_, argmax, probs, z)
         ctx.set_materialize_grads(False)
         ctx.meta = (mode, n_flows, float(p0), float(p1), float(add_eps), B, N, hidden, fused, prior is not None, propose is not None)
         if not fused:
-            return lki, None, None, None, None
+            return lki, None, None, None, None, None
         row_sum, ess_inv = stats[:, 0], stats[:, 1]
         ctx.mark_non_differentiable(ess_inv)
-        return lki, logw, probs, row_sum, ess_inv
+        return lki, logw, probs, row_sum, ess_inv, pred
 
     @staticmethod
-    def backward(ctx, g_lki, g_logw, g_probs, g_rowsum, _g_ess):
+    def backward(ctx, g_lki, g_logw, g_probs, g_rowsum, _g_ess, g_pred):
         pe_, cnf_, enc_, x_, argmax, probs, z = ctx.saved_tensors
         mode, n_flows, p0, p1, add_eps, B, N, hidden, fused, has_prior, has_prop = ctx.meta
         dev = x_.device
         d_logw = d_neg = None
         g_total = L.f32(g_lki) if g_lki is not None else None
-        if fused and any(g is not None for g in (g_logw, g_probs, g_rowsum)):
+        g_pred = L.f32(g_pred) if g_pred is not None else None
+        if fused and any(g is not None for g in (g_logw, g_probs, g_rowsum, g_pred)):
             d_logw = torch.empty(B, N, dtype=torch.float32, device=dev)
             d_neg = torch.empty(B, N, dtype=torch.float32, device=dev) if has_prop else None
             L.call("nfdpf_weight_update_bwd", L.ptr(L.f32(g_probs) if g_probs is not None else None),
                    L.ptr(L.f32(g_logw) if g_logw is not None else None),
                    L.ptr(L.f32(g_rowsum) if g_rowsum is not None else None), L.ptr(probs), add_eps, B, N, L.ptr(d_logw), L.ptr(d_neg),
-                   L.stream())
+                   L.ptr(x_) if g_pred is not None else None, L.ptr(g_pred), L.stream())
             g_total = d_logw if g_total is None else g_total + d_logw
         if g_total is None:
             g_total = torch.zeros(B, N, dtype=torch.float32, device=dev)
@@ -222,19 +225,23 @@ class MeasureUpdate(torch.autograd.Function):
         d_cnf = torch.empty_like(cnf_) if cnf_ is not None else None
         ws = torch.empty(L.load().nfdpf_measure_bwd_workspace(mode, n_flows, B, N) // 4, dtype=torch.float32, device=dev)
         L.call("nfdpf_measure_bwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, p0, p1, L.ptr(enc_), L.ptr(x_), B, N, hidden,
-               L.ptr(g_total.contiguous()), L.ptr(argmax), L.ptr(d_x), L.ptr(d_enc), L.ptr(d_pe), L.ptr(d_cnf), L.ptr(ws), L.ptr(z), L.stream())
+               L.ptr(g_total.contiguous()), L.ptr(argmax), L.ptr(d_x), L.ptr(d_enc), L.ptr(d_pe), L.ptr(d_cnf), L.ptr(ws), L.ptr(z),
+               L.ptr(g_pred), L.ptr(probs) if g_pred is not None else None, L.stream())
         return (d_pe, d_cnf, d_enc, d_x, d_logw if fused else None, d_logw if has_prior else None,
-                d_neg if has_prop else None, None, None, None, None, None, None)
+                d_neg if has_prop else None, None, None, None, None, None, None, None)
 
 
 def measure(pe, cnf, enc, particles, mode, n_flows=2, p0=0.0, p1=1.0):
     """lki (B,N) only -- the measurement_model_*.forward of the reference."""
-    return MeasureUpdate.apply(pe, cnf, enc, particles, None, None, None, MEASURE_MODES[mode], n_flows, p0, p1, 0.0)[0]
+    return MeasureUpdate.apply(pe, cnf, enc, particles, None, None, None, MEASURE_MODES[mode], n_flows, p0, p1, 0.0, None, False)[0]
 
 
-def measure_update(pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows=2, p0=0.0, p1=1.0, add_eps=1e-12, out=None):
-    """(lki, logw, probs, row_sum_logw, ess_inv) -- measurement + DPFs.py:187-192 in one kernel."""
-    return MeasureUpdate.apply(pe, cnf, enc, particles, logw_prev, prior, propose, MEASURE_MODES[mode], n_flows, p0, p1, add_eps, out)
+def measure_update(pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_flows=2, p0=0.0, p1=1.0, add_eps=1e-12, out=None,
+                   want_pred=False):
+    """(lki, logw, probs, row_sum_logw, ess_inv) -- measurement + DPFs.py:187-192 in one kernel; with want_pred a sixth value,
+    the supervised-loss prediction sum_n probs particles (losses.py:22)."""
+    res = MeasureUpdate.apply(pe, cnf, enc, particles, logw_prev, prior, propose, MEASURE_MODES[mode], n_flows, p0, p1, add_eps, out, want_pred)
+    return res if want_pred else res[:5]
 
 
 def row_moments(x, out=None, out_off=0):

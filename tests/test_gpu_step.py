@@ -224,3 +224,40 @@ def test_weight_update_backward_writes_the_negated_copy():
     logw, probs, row_sum, _ = ops.weight_update(terms[0], terms[1], terms[2], terms[3], 1e-12)
     ((probs * cu(torch.randn(B, N, generator=g))).sum() + (logw * cu(torch.randn(B, N, generator=g))).sum() + row_sum.sum()).backward()
     assert torch.equal(terms[3].grad, -terms[1].grad) and torch.equal(terms[1].grad, terms[2].grad)
+
+
+@pytest.mark.parametrize("mode,B,N", [("gaussian", 9, 300), ("cos", 5, 129), ("CRNVP", 3, 200), ("gaussian", 64, 1024)])
+def test_measurement_epilogue_prediction_equals_the_separate_kernel(mode, B, N):
+    """want_pred: the supervised-loss prediction sum_n probs particles (losses.py:22) formed in the measurement kernel's epilogue, its
+    gradient folded into the measurement / weight-update backward -- against weighted_mean on the same tensors through autograd."""
+    g = torch.Generator().manual_seed(B + N)
+    pe = torch.cat([torch.randn(n, generator=g) * s for n, s in ((32, 0.3), (16, 0.1), (512, 0.3), (32, 0.1), (1024, 0.2), (32, 0.1))])
+    cnf = O.init_stack(g, 32, 32, std=0.1, bias_std=0.05) if mode == "CRNVP" else None
+    enc, x = torch.randn(B, 32, generator=g), torch.randn(B, N, 2, generator=g) * 2
+    lw0 = torch.log_softmax(torch.randn(B, N, generator=g), -1)
+    prior, prop = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g)
+    gpred, gprobs = torch.randn(B, 2, generator=g), torch.randn(B, N, generator=g)
+    p0, p1 = (0.0, 2.5) if mode == "CRNVP" else (1.0, 10.0)
+    res = []
+    for fused in (True, False):
+        leaves = [cu(t).requires_grad_() if t is not None else None for t in (pe, cnf, enc, x, lw0, prior, prop)]
+        out = ops.measure_update(*leaves, mode, p0=p0, p1=p1, want_pred=fused)
+        pred = out[5] if fused else ops.weighted_mean(leaves[3], out[2])
+        ((pred * cu(gpred)).sum() + (out[2] * cu(gprobs)).sum()).backward()
+        res.append((pred.detach(), [l.grad for l in leaves if l is not None]))
+    close(res[0][0], res[1][0], rtol=1e-5, atol=1e-5, what="fused prediction")
+    for a, b, name in zip(res[0][1], res[1][1], [n for n, t in zip(("pe", "cnf", "enc", "x", "lw0", "prior", "prop"), (pe, cnf, enc, x, lw0, prior, prop)) if t is not None]):
+        grad_close(a, b, what="fused prediction: d_" + name)
+
+
+@pytest.mark.parametrize("B,N", [(7, 100), (64, 1024), (5, 2048), (3, 4096), (4, 2)])
+def test_row_moments_vs_torch(B, N):
+    """[mean | unbiased std] over the particle axis (model/models.py:309-310, 338-339): the single-pass d = 2 kernel (N <= 2048) and
+    the generic one, written into a wider context row at an offset."""
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(B, N, 2, generator=g) * 30 + 5
+    out = torch.full((B, 9), -7.0, device="cuda")
+    ops.row_moments(cu(x), out, 3)
+    close(out[:, 3:5], x.double().mean(1), rtol=1e-5, atol=1e-5, what="row mean")
+    close(out[:, 5:7], x.double().std(1), rtol=1e-5, atol=1e-5, what="row std")
+    assert bool((out[:, :3] == -7.0).all()) and bool((out[:, 7:] == -7.0).all())
