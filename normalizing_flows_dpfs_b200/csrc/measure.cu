@@ -19,8 +19,12 @@
 
 namespace nfdpf {
 
-enum { MODE_GAUSS = 0, MODE_COS = 1, MODE_CNF = 2 };
+enum { MODE_GAUSS = 0, MODE_COS = 1, MODE_CNF = 2, MODE_NN = 3 };
 constexpr int FWD_TMEM_COLS = 128;   // accumulator 32 + activation hi 32 + lo 32 columns, rounded up to a power of two
+constexpr int FWD_TMEM_COLS_NN = 256;   // NN likelihood head: accumulator 64 + activation hi 64 + lo 64 columns
+// packed likelihood head (build_likelihood, model/models.py:119-128; state_dict order 0.weight,0.bias,2.weight,2.bias,4.weight,4.bias)
+constexpr int NH = 64, NH_W1 = 0, NH_B1 = NH_W1 + NH * NH, NH_W2 = NH_B1 + NH, NH_B2 = NH_W2 + NH * NH, NH_W3 = NH_B2 + NH, NH_B3 = NH_W3 + NH,
+              NH_SIZE = NH_B3 + 1;
 constexpr int HID = 32;                      // encoding width (args.hiddensize)
 // packed particle encoder (state_dict order 0.weight,0.bias,2.weight,2.bias,4.weight,4.bias)
 constexpr int PE_W1 = 0, PE_B1 = 32, PE_W2 = 48, PE_B2 = 560, PE_W3 = 592, PE_B3 = 1616, PE_SIZE = 1648;
@@ -367,6 +371,76 @@ __device__ __forceinline__ float loglik_cnf_tc(PeTc& tc, const float (&e)[32], c
     return -0.5f * m / (p1 * p1) - 32.0f * (logf(p1) + 0.91893853320467274f) + ld;
 }
 
+// ---- NN likelihood (measurement_model_NN, model/models.py:221-235): sigmoid MLP 64 -> 64 -> 64 -> 1 on [enc | e], then log ----------
+// The observation half of layer 1 is row-constant: hb1 = b1 + W1[:, :32] enc is formed once per trajectory.  The particle half
+// (M = 128 particles, N = 64, K = 32) and layer 2 (N = 64, K = 64) are tcgen05 TS rounds like the encoder's (3xTF32): the thread
+// writes its activation row (hi | lo) into its own tensor-memory lane, columns [64,128) / [128,192), the accumulator is [0,64).
+struct NnHead {
+    using W1E = umma::Operand<NH, 32>;   // rows j (out), K = k over the particle-encoding half of the input
+    using W2 = umma::Operand<NH, NH>;    // rows j, K = k
+    static constexpr int W1E_HI = 0, W1E_LO = W1E_HI + W1E::FLOATS, W2_HI = W1E_LO + W1E::FLOATS, W2_LO = W2_HI + W2::FLOATS,
+                         TILE_FLOATS = W2_LO + W2::FLOATS;
+    static constexpr int HB1 = TILE_FLOATS, B2 = HB1 + NH, W3 = B2 + NH, B3 = W3 + NH, FLOATS = B3 + 4;   // vectors behind the tiles
+    static constexpr int COL_D = 0, COL_AHI = 64, COL_ALO = 128;
+    // all threads; followed by a CTA barrier in the caller.  enc_row: the trajectory's observation encoding (global)
+    __device__ static void load(const float* __restrict__ head, const float* __restrict__ enc_row, float* s) {
+        for (int e = threadIdx.x; e < NH * 32; e += blockDim.x) {
+            const int j = e >> 5, k = e & 31;
+            W1E::store_elem(s + W1E_HI, s + W1E_LO, j, k, head[NH_W1 + j * NH + 32 + k]);
+        }
+        for (int e = threadIdx.x; e < NH * NH; e += blockDim.x) W2::store_elem(s + W2_HI, s + W2_LO, e >> 6, e & 63, head[NH_W2 + e]);
+        for (int j = threadIdx.x; j < NH; j += blockDim.x) {
+            float a = head[NH_B1 + j];
+            for (int c = 0; c < 32; ++c) a = fmaf(head[NH_W1 + j * NH + c], enc_row[c], a);
+            s[HB1 + j] = a;
+            s[B2 + j] = head[NH_B2 + j];
+            s[W3 + j] = head[NH_W3 + j];
+        }
+        if (threadIdx.x == 0) s[B3] = head[NH_B3];
+        umma::fence_smem_to_async();
+    }
+};
+
+// One TS round of the head on the CTA's 128 lanes: A = the K values every thread just wrote, D[0,64) = A W^T (3xTF32).
+template <int K>
+__device__ __forceinline__ void nn_round(PeTc& tc, const float (&a)[K], const float* w_hi, const float* w_lo, float (&d)[NH]) {
+    {
+        float hi[K], lo[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) umma::split(a[k], hi[k], lo[k]);
+        umma::st_frag<K>(tc.lane_addr() + NnHead::COL_AHI, hi);
+        umma::st_frag<K>(tc.lane_addr() + NnHead::COL_ALO, lo);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        umma::fence_after_sync();
+        umma::gemm3_ts<NH, K>(tc.tmem + NnHead::COL_D, tc.tmem + NnHead::COL_AHI, tc.tmem + NnHead::COL_ALO, w_hi, w_lo);
+        umma::commit(tc.bar);
+    }
+    tc.wait();
+    float lo32[32], hi32[32];
+    umma::ld32(tc.lane_addr() + NnHead::COL_D, lo32);
+    umma::ld32(tc.lane_addr() + NnHead::COL_D + 32, hi32);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { d[j] = lo32[j]; d[32 + j] = hi32[j]; }
+}
+
+// CTA-collective (every thread calls it, dead threads with any finite e).  Returns log sigmoid(z) as the reference forms it.
+__device__ __forceinline__ float loglik_nn_tc(PeTc& tc, const float (&e)[32], const float* __restrict__ s_nn) {
+    float h[NH];
+    nn_round<32>(tc, e, s_nn + NnHead::W1E_HI, s_nn + NnHead::W1E_LO, h);
+#pragma unroll
+    for (int j = 0; j < NH; ++j) h[j] = fmaxf(h[j] + s_nn[NnHead::HB1 + j], 0.f);
+    float h2[NH];
+    nn_round<NH>(tc, h, s_nn + NnHead::W2_HI, s_nn + NnHead::W2_LO, h2);
+    float z = s_nn[NnHead::B3];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) z = fmaf(s_nn[NnHead::W3 + j], fmaxf(h2[j] + s_nn[NnHead::B2 + j], 0.f), z);
+    return logf(1.0f / (1.0f + expf(-z)));        // likelihood[..., 0].log() of a Sigmoid output, models.py:233-235
+}
+
 __device__ void load_enc(const float* __restrict__ enc_row, float* s_enc) {  // s_enc[32] = ||enc|| clamped (cos mode)
     if (threadIdx.x < 32) {
         const float v = enc_row[threadIdx.x];
@@ -395,13 +469,17 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     float* s_img = s_enc + 36;                // [n_fcnn][CnfL1::TAIL]  CRNVP tail images (b1 | W2 | b2 | W3 | b3)
     float* s_hb = s_img + n_fcnn * CnfL1::TAIL;   // [n_fcnn][8]
     float* s_l1w = s_hb + n_fcnn * H;         // [n_fcnn / 2][CnfL1::STAGE_FLOATS]  layer-1 operand tiles of the CRNVP stages
-    float* s_ll = s_l1w + (n_fcnn / 2) * CnfL1::STAGE_FLOATS;   // [N]
-    if (tid < 32) umma::tmem_alloc<FWD_TMEM_COLS>(&s_tslot);
+    float* s_nn = s_l1w + (n_fcnn / 2) * CnfL1::STAGE_FLOATS;   // [NnHead::FLOATS]  NN likelihood head (mode 3)
+    float* s_ll = s_nn + (MODE == MODE_NN ? NnHead::FLOATS : 0);   // [N]
+    constexpr int TCOLS = MODE == MODE_NN ? FWD_TMEM_COLS_NN : FWD_TMEM_COLS;
+    constexpr bool SHIFT = MODE == MODE_GAUSS || MODE == MODE_CNF;     // likelihood - likelihood.max(dim=-1), models.py:252, 276
+    if (tid < 32) umma::tmem_alloc<TCOLS>(&s_tslot);
     if (tid == 0) umma::mbar_init(&s_bar, 1);
     PeTc tc{s_tc, &s_bar, 0u, 0u};
     tc.load_weights(pe, false);
     for (int e = tid; e < PE_SIZE; e += TP) s_pe[e] = pe[e];
     if (MODE == MODE_CNF) CnfL1::load(cnf, n_fcnn, s_img, s_hb, s_l1w);
+    if (MODE == MODE_NN) NnHead::load(cnf, enc + (size_t)b * HID, s_nn);      // (the `cnf` slot carries the packed head)
     load_enc(enc + (size_t)b * HID, s_enc);
     umma::fence_before_sync();
     __syncthreads();
@@ -419,6 +497,7 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
         pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);
         float ll;
         if constexpr (MODE == MODE_CNF) ll = loglik_cnf_tc(tc, e, s_enc, p0, p1, s_img, s_hb, s_l1w, n_flows, lo, up);
+        else if constexpr (MODE == MODE_NN) ll = loglik_nn_tc(tc, e, s_nn);
         else ll = loglik<MODE>(e, s_enc, p0, p1, s_img, s_hb, n_flows, lo, up);
         if (MODE == MODE_CNF && z_out && live) {   // the flow output: lets the backward walk the stack from z without re-running it
             float4* zo = reinterpret_cast<float4*>(z_out + ((size_t)b * N + n) * 32);
@@ -432,9 +511,9 @@ measure_fwd_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, 
     }
     umma::fence_before_sync();
     __syncthreads();
-    if (tid < 32) umma::tmem_free<FWD_TMEM_COLS>(tc.tmem);
+    if (tid < 32) umma::tmem_free<TCOLS>(tc.tmem);
     float shift = 0.f;
-    if (MODE != MODE_COS) {      // likelihood - likelihood.max(dim=-1), models.py:252, 276
+    if (SHIFT) {
         shift = block_allreduce(mx, s_red, OpMax(), -INFINITY);
         int am = 0x7fffffff;
         for (int n = tid; n < N; n += TP) if (s_ll[n] == shift) am = min(am, n);
@@ -1154,7 +1233,8 @@ measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const fl
 
 static size_t fwd_smem(int mode, int n_flows, int N) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
-    return ((size_t)PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * CnfL1::TAIL + n_fcnn * H + (size_t)(n_fcnn / 2) * CnfL1::STAGE_FLOATS + N) * sizeof(float);
+    return ((size_t)PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * CnfL1::TAIL + n_fcnn * H + (size_t)(n_fcnn / 2) * CnfL1::STAGE_FLOATS +
+            (mode == MODE_NN ? NnHead::FLOATS : 0) + N) * sizeof(float);
 }
 static size_t bwd_smem(int mode, int n_flows) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
@@ -1228,7 +1308,8 @@ extern "C" int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* 
                                  float* logw_out, float* probs_out, float* row_stats, float* z_out, float* pred_out, void* stream) {
     NFDPF_REQUIRE(pe_packed && enc && particles && lki, "measure_fwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0, "measure_fwd: B and N must be positive");
-    NFDPF_REQUIRE(mode >= 0 && mode <= 2, "measure_fwd: mode must be 0 (gaussian), 1 (cos) or 2 (CRNVP), got %d", mode);
+    NFDPF_REQUIRE(mode >= 0 && mode <= 3, "measure_fwd: mode must be 0 (gaussian), 1 (cos), 2 (CRNVP) or 3 (NN), got %d", mode);
+    NFDPF_REQUIRE(mode != MODE_NN || cnf_packed, "measure_fwd: the NN likelihood needs the packed head (8385 floats) in cnf_packed");
     NFDPF_REQUIRE(mode != MODE_CNF || (cnf_packed && n_flows >= 1 && n_flows <= 4), "measure_fwd: CRNVP needs a packed stack, 1..4 flows");
     NFDPF_REQUIRE(!logw_prev || probs_out, "measure_fwd: fused update needs probs_out");
     NFDPF_REQUIRE(!pred_out || logw_prev, "measure_fwd: the fused prediction needs the fused weight update");
@@ -1237,6 +1318,7 @@ extern "C" int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* 
 #define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, logw_prev, prior, propose, add_eps, lki, argmax, logw_out, probs_out, row_stats, z_out, pred_out, st
     if (mode == MODE_GAUSS) return launch_measure_fwd<MODE_GAUSS>(ARGS);
     if (mode == MODE_COS) return launch_measure_fwd<MODE_COS>(ARGS);
+    if (mode == MODE_NN) return launch_measure_fwd<MODE_NN>(ARGS);
     return launch_measure_fwd<MODE_CNF>(ARGS);
 #undef ARGS
 }

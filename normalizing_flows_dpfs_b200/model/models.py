@@ -226,18 +226,23 @@ class measurement_model_cnf(_FusedMeasurement):
         return mean, std, len(self.CNF.flows)
 
 
-class measurement_model_NN(nn.Module):
-    """Learned likelihood head on [obs encoding, particle encoding] (reference models.py:221-235); stock PyTorch."""
+class measurement_model_NN(_FusedMeasurement):
+    """Learned likelihood head on [obs encoding | particle encoding] (reference models.py:221-235): Sigmoid MLP 64-64-64-1, then log.
+    Forward: mode 3 of the fused measurement kernel (the head's two 64-wide layers are tcgen05 rounds behind the encoder's).  Backward:
+    see ops.MeasureUpdate (mode 3)."""
+    mode = "NN"
 
     def __init__(self, particle_encoder, likelihood_estimator):
-        super().__init__()
-        self.particle_encoder = particle_encoder
+        super().__init__(particle_encoder)
         self.likelihood_estimator = likelihood_estimator
+        self._head_cache = _PackCache()
 
-    def forward(self, encodings, update_particles):
-        e = self.particle_encoder.float()(update_particles.float())
-        obs = encodings[:, None, :].expand(-1, update_particles.shape[1], -1)
-        return self.likelihood_estimator(torch.cat([obs, e], dim=-1))[..., 0].log()
+    def cnf_packed(self):     # the kernels' second parameter slot carries the packed head
+        lin = [m for m in self.likelihood_estimator if isinstance(m, nn.Linear)]
+        shape = [tuple(m.weight.shape) for m in lin]
+        if shape != [(64, 64), (64, 64), (1, 64)]:
+            raise ValueError("the fused NN likelihood needs build_likelihood's 64-64-64-1 head (hiddensize 32); got %s" % (shape,))
+        return self._head_cache.get([self.likelihood_estimator])
 
 
 class measurement_model_cglow(nn.Module):

@@ -211,6 +211,28 @@ def measurement_cos(enc, x, pe):
     return (1.0 / (1e-7 + (1.0 - (a * b).sum(-1)))).log()
 
 
+def unpack_likelihood_head(flat):
+    """build_likelihood, model/models.py:119-128: Linear(64,64)-ReLU-Linear(64,64)-ReLU-Linear(64,1)-Sigmoid in state_dict order."""
+    sizes = ((64, 64), (64,), (64, 64), (64,), (1, 64), (1,))
+    out, o = [], 0
+    for sh in sizes:
+        n = int(np.prod(sh))
+        out.append(flat[o:o + n].reshape(sh))
+        o += n
+    assert o == flat.numel()
+    return tuple(out)
+
+
+def measurement_nn(enc, x, pe, head):
+    """measurement_model_NN, model/models.py:221-235: sigmoid MLP on [observation encoding | particle encoding], then log."""
+    W1, b1, W2, b2, W3, b3 = head
+    e = particle_encoder(x, pe)
+    inp = torch.cat([enc[:, None, :].expand(-1, e.shape[1], -1), e], dim=-1)
+    h = torch.relu(inp @ W1.t() + b1)
+    h = torch.relu(h @ W2.t() + b2)
+    return torch.sigmoid(h @ W3.t() + b3)[..., 0].log()
+
+
 def normalize_log_probs(lw):
     """utils.py:39-44."""
     e = (lw - lw.max(dim=1, keepdim=True)[0]).exp()

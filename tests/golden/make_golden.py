@@ -358,6 +358,28 @@ def gen_losses():
     np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
 
 
+def gen_nn():
+    """measurement_model_NN (model/models.py:221-235) on seeded inputs: log-likelihoods and gradients (a file of its own, so that
+    glue.npz keeps regenerating bit for bit)."""
+    out = {}
+    cases = [(3, 40, 0.3, 0.12), (4, 129, 0.5, 0.2), (2, 300, 0.2, 0.1)]
+    for ci, (B, N, pe_std, head_std) in enumerate(cases):
+        g = torch.Generator().manual_seed(700 + ci)
+        pe = ref_models.build_particle_encoder(32, 2)
+        head = ref_models.build_likelihood(32, 2)
+        randomise(pe, g, pe_std, 0.1), randomise(head, g, head_std, 0.1)
+        m = ref_models.measurement_model_NN(pe, head)
+        x = (torch.randn(B, N, 2, generator=g) * 3 + 1).requires_grad_()
+        enc = torch.randn(B, 32, generator=g).requires_grad_()
+        lki = m(enc, x)
+        gl = torch.randn(B, N, generator=g)
+        (lki * gl).sum().backward()
+        out.update({f"c{ci}_{k}": v for k, v in npy(dict(x=x, enc=enc, pe=flat_params(pe), head=flat_params(head), lki=lki, gl=gl,
+                                                         d_x=x.grad, d_enc=enc.grad, d_pe=flat_grads(pe), d_head=flat_grads(head))).items()})
+    out["n_cases"] = len(cases)
+    np.savez_compressed(os.path.join(OUT, "meas_nn.npz"), **out)
+
+
 def gen_state_dict():
     """state_dict keys + shapes of the reference DPF for the accelerated configurations (checkpoint compatibility)."""
     import json
@@ -374,8 +396,8 @@ def gen_state_dict():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["soft", "flows", "glue", "ot", "filter", "state_dict", "init", "losses"]
+    which = sys.argv[1:] or ["soft", "flows", "glue", "ot", "filter", "state_dict", "init", "losses", "nn"]
     sys.argv = sys.argv[:1]
     for w in which:
-        {"soft": gen_soft, "flows": gen_flows, "glue": gen_glue, "ot": gen_ot, "filter": gen_filter, "state_dict": gen_state_dict, "init": gen_init, "losses": gen_losses}[w]()
+        {"soft": gen_soft, "flows": gen_flows, "glue": gen_glue, "ot": gen_ot, "filter": gen_filter, "state_dict": gen_state_dict, "init": gen_init, "losses": gen_losses, "nn": gen_nn}[w]()
         print("wrote", w)
