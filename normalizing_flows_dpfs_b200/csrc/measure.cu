@@ -1231,6 +1231,333 @@ measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const fl
     }
 }
 
+// ---- NN likelihood, backward (mode 3) --------------------------------------------------------------------------------
+// One 128-thread CTA per SM (the head's four operand tiles alone are 96 KB), persistent over trajectories.  Per 128-particle batch:
+//   data path (thread = particle = tensor-memory lane): encoder forward (2 rounds), head forward (2 rounds: N = 64, K = 32 / 64),
+//     dz = g (1 - sigmoid z), delta2, round W2^T -> delta1, round W1e^T -> d e, then the encoder's backward rounds as in the other modes;
+//   head weight gradients on the CUDA cores from the transposed tile (row = feature, column = particle): a thread owns a 4 x 8
+//     block of dW2 and a 4 x 4 block of dW1[:, 32:] IN REGISTERS for the CTA's whole life and walks the batch's 128 particles with
+//     128-bit loads (rows interleaved by 16 / 8 so that a warp's loads are conflict-free); db1 / db2 are row sums of the same tile,
+//     dW3 a transposed warp butterfly of dz h2; the observation half dW1[:, :32] = (sum_p delta1) (x) enc and d_enc = W1[:, :32]^T
+//     (sum_p delta1) are formed once per trajectory.  IEEE adds throughout (no tensor-core accumulation across batches);
+//   encoder weight gradients: the mma.sync phases A / B of the other modes, fragments in tensor memory (columns 192..259: the CTA
+//     owns all 512 columns).
+struct NnB {
+    using W1E = umma::Operand<NH, 32>;
+    using W2 = umma::Operand<NH, NH>;
+    using W2T = umma::Operand<NH, NH>;    // rows k (layer-2 input), K = j:   d h1[k] = sum_j delta2[j] W2[j][k]
+    using W1ET = umma::Operand<32, NH>;   // rows c (encoding index), K = j:  d e[c]  = sum_j delta1[j] W1[j][32 + c]
+    static constexpr int W1E_HI = 0, W1E_LO = W1E_HI + W1E::FLOATS, W2_HI = W1E_LO + W1E::FLOATS, W2_LO = W2_HI + W2::FLOATS,
+                         W2T_HI = W2_LO + W2::FLOATS, W2T_LO = W2T_HI + W2T::FLOATS, W1ET_HI = W2T_LO + W2T::FLOATS,
+                         W1ET_LO = W1ET_HI + W1ET::FLOATS, TILE_FLOATS = W1ET_LO + W1ET::FLOATS;
+    static constexpr int HB1 = TILE_FLOATS, B2 = HB1 + NH, W3 = B2 + NH, B3 = W3 + NH, D1SUM = B3 + 4, ENC = D1SUM + NH, W3ACC = ENC + 32,
+                         FLOATS = W3ACC + 4 * NH;
+    // gradient-tile rows: the encoder phases (PR, rows 0..67) alias rows R_H1.. once the head phases are done
+    static constexpr int R_H1 = 2, R_D = R_H1 + NH, R_E = R_D + NH, ROWS = R_E + 32;
+    static constexpr int TMEM_COLS = 512, TACC = 192;
+};
+
+// acc[r][c] += sum_p tile[rowA0 + jg + 16 r][p] * tile[rowB0 + kg + 8 c][p] over the batch's 128 particles
+template <int NB>
+__device__ __forceinline__ void nn_contract(const float* __restrict__ tile, int rowA0, int rowB0, int jg, int kg, float (&acc)[4][NB]) {
+#pragma unroll 2
+    for (int p = 0; p < 128; p += 4) {
+        float4 a[4], b[NB];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(tile + (rowA0 + jg + 16 * r) * TSM + p);
+#pragma unroll
+        for (int c = 0; c < NB; ++c) b[c] = *reinterpret_cast<const float4*>(tile + (rowB0 + kg + 8 * c) * TSM + p);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < NB; ++c)
+                acc[r][c] += fmaf(a[r].x, b[c].x, fmaf(a[r].y, b[c].y, fmaf(a[r].z, b[c].z, a[r].w * b[c].w)));
+    }
+}
+__device__ __forceinline__ float nn_rowsum(const float* __restrict__ row) {
+    float s = 0.f;
+#pragma unroll 4
+    for (int p = 0; p < 128; p += 4) { const float4 v = *reinterpret_cast<const float4*>(row + p); s += (v.x + v.y) + (v.z + v.w); }
+    return s;
+}
+// one TS round of the head's backward: A = the K values every thread just wrote, D[0, N) = A W^T
+template <int N, int K>
+__device__ __forceinline__ void nn_round_nk(PeTc& tc, const float (&a)[K], const float* w_hi, const float* w_lo, float (&d)[N]) {
+    {
+        float hi[K], lo[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) umma::split(a[k], hi[k], lo[k]);
+        umma::st_frag<K>(tc.lane_addr() + NnHead::COL_AHI, hi);
+        umma::st_frag<K>(tc.lane_addr() + NnHead::COL_ALO, lo);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        umma::fence_after_sync();
+        umma::gemm3_ts<N, K>(tc.tmem + NnHead::COL_D, tc.tmem + NnHead::COL_AHI, tc.tmem + NnHead::COL_ALO, w_hi, w_lo);
+        umma::commit(tc.bar);
+    }
+    tc.wait();
+    float lo32[32];
+    umma::ld32(tc.lane_addr() + NnHead::COL_D, lo32);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) d[j] = lo32[j];
+    if (N == 64) {
+        float hi32[32];
+        umma::ld32(tc.lane_addr() + NnHead::COL_D + 32, hi32);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) d[(N == 64 ? 32 : 0) + j] = hi32[j];
+    }
+}
+
+__global__ void __launch_bounds__(TP, 1)
+measure_bwd_nn_kernel(const float* __restrict__ pe, const float* __restrict__ head, const float* __restrict__ enc,
+                      const float* __restrict__ particles, int B, int N, const float* __restrict__ g_lki,
+                      float* __restrict__ d_particles, float* __restrict__ d_enc, float* __restrict__ part_pe,
+                      float* __restrict__ part_head, const float* __restrict__ g_pred, const float* __restrict__ probs) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_tslot;
+    constexpr int TILE_FLOATS = (NnB::ROWS * TSM + 31) & ~31;
+    constexpr int NW = TP / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* s_tile = smem;                                    // [TILE_FLOATS]
+    float* s_tcw = s_tile + TILE_FLOATS;                     // encoder tensor-core weight tiles
+    float* s_pe = s_tcw + PeTc::WBWD_FLOATS;
+    float* s_nn = s_pe + PE_SIZE;                            // head operand tiles + vectors (NnB)
+    float* s_accpe = s_tile;                                 // read-out staging at the very end
+    static_assert(NW * AC::SIZE <= TILE_FLOATS, "read-out staging must fit in the tile");
+    static_assert((TILE_FLOATS + PeTc::WBWD_FLOATS + PE_SIZE) % 4 == 0, "head tiles must stay 16-byte aligned");
+    if (tid < 32) umma::tmem_alloc<NnB::TMEM_COLS>(&s_tslot);
+    if (tid == 0) umma::mbar_init(&s_bar, 1);
+    PeTc tc{s_tcw, &s_bar, 0u, 0u};
+    tc.load_weights(pe, true);
+    for (int e = tid; e < PE_SIZE; e += TP) s_pe[e] = pe[e];
+    for (int e = tid; e < NH * 32; e += TP) {
+        const int j = e >> 5, c = e & 31;
+        const float wv = head[NH_W1 + j * NH + 32 + c];
+        NnB::W1E::store_elem(s_nn + NnB::W1E_HI, s_nn + NnB::W1E_LO, j, c, wv);
+        NnB::W1ET::store_elem(s_nn + NnB::W1ET_HI, s_nn + NnB::W1ET_LO, c, j, wv);
+    }
+    for (int e = tid; e < NH * NH; e += TP) {
+        const int j = e >> 6, k = e & 63;
+        const float wv = head[NH_W2 + e];
+        NnB::W2::store_elem(s_nn + NnB::W2_HI, s_nn + NnB::W2_LO, j, k, wv);
+        NnB::W2T::store_elem(s_nn + NnB::W2T_HI, s_nn + NnB::W2T_LO, k, j, wv);
+    }
+    for (int j = tid; j < NH; j += TP) { s_nn[NnB::B2 + j] = head[NH_B2 + j]; s_nn[NnB::W3 + j] = head[NH_W3 + j]; }
+    if (tid == 0) s_nn[NnB::B3] = head[NH_B3];
+    s_tile[PR::ONE * TSM + tid] = 1.0f;
+    s_tile[PR::ZERO * TSM + tid] = 0.0f;
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    tc.tmem = s_tslot;
+    const uint32_t tacc = tc.lane_addr() + NnB::TACC;
+    {
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c0 = 0; c0 < TA_END; c0 += 4) umma::st4(tacc + c0, z);
+        umma::wait_st();
+    }
+    // ---- register tiles of the head's weight gradients (this thread's outputs, summed over everything the CTA sees)
+    const int jg = tid >> 3, kg = tid & 7;                   // dW2[jg + 16 r][kg + 8 c], dW1[jg + 16 r][32 + kg + 8 c]
+    const int oj = tid >> 1, oc = (tid & 1) * 16;            // dW1[oj][oc .. oc + 16): the observation half
+    float acc2[4][8], acc1[4][4], acc1o[16], accb1 = 0.f, accb2 = 0.f, acc3a = 0.f, acc3b = 0.f, accb3 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc2[r][c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc1[r][c] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc1o[i] = 0.f;
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        if (tid < 32) s_nn[NnB::ENC + tid] = enc[(size_t)b * HID + tid];
+        __syncthreads();
+        if (tid < NH) {     // observation half of layer 1, once per trajectory
+            float a = head[NH_B1 + tid];
+            for (int c = 0; c < 32; ++c) a = fmaf(head[NH_W1 + tid * NH + c], s_nn[NnB::ENC + c], a);
+            s_nn[NnB::HB1 + tid] = a;
+        }
+        float d1traj = 0.f;                                  // threads < 64: sum_p delta1[tid] over this trajectory
+        const size_t base = (size_t)b * N;
+        __syncthreads();
+        for (int n0 = 0; n0 < N; n0 += TP) {
+            asm volatile("" ::: "memory");
+            const int n = n0 + tid;
+            const bool live = n < N;
+            const size_t p = base + (live ? n : 0);
+            const float2 x = *reinterpret_cast<const float2*>(particles + p * 2);
+            const float g = live ? g_lki[p] : 0.f;
+            float a1[16], a2[32], e[32];
+            __syncthreads();                                 // the previous batch's encoder phases are done with the tile
+            pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) s_tile[(NnB::R_E + k) * TSM + tid] = e[k];
+            uint64_t m1 = 0ull;
+            float dz;
+            float d2[NH];
+            {
+                float h1[NH], h2[NH];
+                nn_round<32>(tc, e, s_nn + NnB::W1E_HI, s_nn + NnB::W1E_LO, h1);
+#pragma unroll
+                for (int j = 0; j < NH; ++j) {
+                    h1[j] = fmaxf(h1[j] + s_nn[NnB::HB1 + j], 0.f);
+                    m1 |= (uint64_t)(h1[j] > 0.f) << j;
+                    s_tile[(NnB::R_H1 + j) * TSM + tid] = h1[j];
+                }
+                nn_round<NH>(tc, h1, s_nn + NnB::W2_HI, s_nn + NnB::W2_LO, h2);
+                float z = s_nn[NnB::B3];
+#pragma unroll
+                for (int j = 0; j < NH; ++j) { h2[j] = fmaxf(h2[j] + s_nn[NnB::B2 + j], 0.f); z = fmaf(s_nn[NnB::W3 + j], h2[j], z); }
+                const float sg = 1.0f / (1.0f + expf(-z));
+                dz = g * (1.0f - sg);                        // d log(sigmoid z) / dz
+#pragma unroll
+                for (int j = 0; j < NH; ++j) { d2[j] = h2[j] > 0.f ? dz * s_nn[NnB::W3 + j] : 0.f; h2[j] *= dz; }
+                // dW3[j] += sum_p dz h2[j]: transposed butterfly over the warp, lane l ends up with entries 2l, 2l + 1
+#define NFDPF_NN_ROUND(HALFN, OFF)                                                     \
+                {                                                                       \
+                    const bool up_ = (lane & OFF) != 0;                                 \
+                    _Pragma("unroll") for (int i = 0; i < HALFN; ++i) {                 \
+                        const float keep = up_ ? h2[i + HALFN] : h2[i];                 \
+                        const float send = up_ ? h2[i] : h2[i + HALFN];                 \
+                        h2[i] = keep + __shfl_xor_sync(FULL, send, OFF);                \
+                    }                                                                   \
+                }
+                NFDPF_NN_ROUND(32, 16) NFDPF_NN_ROUND(16, 8) NFDPF_NN_ROUND(8, 4) NFDPF_NN_ROUND(4, 2) NFDPF_NN_ROUND(2, 1)
+#undef NFDPF_NN_ROUND
+                acc3a += h2[0]; acc3b += h2[1];
+                accb3 += warp_sum(dz);
+            }
+#pragma unroll
+            for (int j = 0; j < NH; ++j) s_tile[(NnB::R_D + j) * TSM + tid] = d2[j];
+            float d1[NH];
+            nn_round_nk<NH, NH>(tc, d2, s_nn + NnB::W2T_HI, s_nn + NnB::W2T_LO, d1);     // (its barrier also publishes the tile rows)
+#pragma unroll
+            for (int j = 0; j < NH; ++j) d1[j] = (m1 >> j) & 1ull ? d1[j] : 0.f;
+            // head weight gradients, phase H2: dW2 += delta2 (x) h1, db2 += sum_p delta2
+            nn_contract<8>(s_tile, NnB::R_D, NnB::R_H1, jg, kg, acc2);
+            if (tid < NH) accb2 += nn_rowsum(s_tile + (NnB::R_D + tid) * TSM);
+            __syncthreads();                                 // everybody has read delta2: the rows take delta1
+#pragma unroll
+            for (int j = 0; j < NH; ++j) s_tile[(NnB::R_D + j) * TSM + tid] = d1[j];
+            float de[32];
+            nn_round_nk<32, NH>(tc, d1, s_nn + NnB::W1ET_HI, s_nn + NnB::W1ET_LO, de);
+            // phase H1: dW1[:, 32:] += delta1 (x) e, db1 += sum_p delta1 (also per trajectory: the observation half)
+            nn_contract<4>(s_tile, NnB::R_D, NnB::R_E, jg, kg, acc1);
+            if (tid < NH) { const float rs = nn_rowsum(s_tile + (NnB::R_D + tid) * TSM); accb1 += rs; d1traj += rs; }
+            __syncthreads();                                 // the head phases are done with the tile: the encoder phases alias it
+            // ---- encoder backward, as in the other modes
+            float ed2[32], ed1[16];
+            tc.template store_row<32>(de);
+            tc.template round<32, 32>(PeTc::W3T_HI, PeTc::W3T_LO);
+            umma::ld32(tc.lane_addr(), ed2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ed2[j] = a2[j] > 0.f ? ed2[j] : 0.f;
+            tc.template store_row<32>(ed2);
+            tc.template round<16, 32>(PeTc::W2T_HI, PeTc::W2T_LO);
+            umma::ld16(tc.lane_addr(), ed1);
+            float dx0 = 0.f, dx1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {
+                const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W1 + 2 * k);
+                ed1[k] = a1[k] > 0.f ? ed1[k] : 0.f;
+                ed1[k + 1] = a1[k + 1] > 0.f ? ed1[k + 1] : 0.f;
+                dx0 = fmaf(q.x, ed1[k], dx0); dx1 = fmaf(q.y, ed1[k], dx1);
+                dx0 = fmaf(q.z, ed1[k + 1], dx0); dx1 = fmaf(q.w, ed1[k + 1], dx1);
+            }
+            if (live) {
+                if (g_pred) {
+                    const float pr = probs[p];
+                    dx0 = fmaf(g_pred[2 * b], pr, dx0); dx1 = fmaf(g_pred[2 * b + 1], pr, dx1);
+                }
+                *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
+            }
+            s_tile[PR::ONE * TSM + tid] = 1.0f;              // (rows 0-1 are not aliased by the head phases; cheap to keep right)
+            s_tile[PR::ZERO * TSM + tid] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s_tile[(PR::D3 + j) * TSM + tid] = de[j]; s_tile[(PR::A2 + j) * TSM + tid] = a2[j]; }
+            __syncwarp();
+            pe_weight_grads_a(s_tile, tacc);
+            __syncwarp();
+            s_tile[(PR::X + 0) * TSM + tid] = x.x;
+            s_tile[(PR::X + 1) * TSM + tid] = x.y;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { s_tile[(PR::A1 + k) * TSM + tid] = a1[k]; s_tile[(PR::D1 + k) * TSM + tid] = ed1[k]; }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s_tile[(PR::D2 + j) * TSM + tid] = ed2[j];
+            __syncwarp();
+            pe_weight_grads_b(s_tile, tacc);
+            __syncwarp();
+        }
+        // ---- per trajectory: the observation half of layer 1
+        __syncthreads();
+        if (tid < NH) s_nn[NnB::D1SUM + tid] = d1traj;
+        __syncthreads();
+        {
+            const float dj = s_nn[NnB::D1SUM + oj];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc1o[i] = fmaf(dj, s_nn[NnB::ENC + oc + i], acc1o[i]);
+        }
+        if (d_enc && tid < 32) {
+            float a = 0.f;
+            for (int j = 0; j < NH; ++j) a = fmaf(head[NH_W1 + j * NH + tid], s_nn[NnB::D1SUM + j], a);
+            d_enc[(size_t)b * HID + tid] = a;
+        }
+    }
+    // ---- write this CTA's partial gradients
+    float* ph = part_head + (size_t)blockIdx.x * NH_SIZE;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ph[NH_W2 + (jg + 16 * r) * NH + kg + 8 * c] = acc2[r][c];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ph[NH_W1 + (jg + 16 * r) * NH + 32 + kg + 8 * c] = acc1[r][c];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ph[NH_W1 + oj * NH + oc + i] = acc1o[i];
+    if (tid < NH) { ph[NH_B1 + tid] = accb1; ph[NH_B2 + tid] = accb2; }
+    __syncthreads();
+    s_nn[NnB::W3ACC + warp * NH + 2 * lane] = acc3a;
+    s_nn[NnB::W3ACC + warp * NH + 2 * lane + 1] = acc3b;
+    if (lane == 0) s_nn[NnB::D1SUM + warp] = accb3;
+    __syncthreads();
+    if (tid < NH) ph[NH_W3 + tid] = (s_nn[NnB::W3ACC + tid] + s_nn[NnB::W3ACC + NH + tid]) + (s_nn[NnB::W3ACC + 2 * NH + tid] + s_nn[NnB::W3ACC + 3 * NH + tid]);
+    if (tid == 0) ph[NH_B3] = (s_nn[NnB::D1SUM] + s_nn[NnB::D1SUM + 1]) + (s_nn[NnB::D1SUM + 2] + s_nn[NnB::D1SUM + 3]);
+    __syncthreads();                                   // every warp is done with the tile: it becomes the read-out staging area
+    for (int e = tid; e < NW * AC::SIZE; e += TP) s_accpe[e] = 0.f;
+    __syncthreads();
+    pe_weight_grads_readout(tacc, s_accpe + warp * AC::SIZE);
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_free<NnB::TMEM_COLS>(tc.tmem);
+    for (int e = tid; e < PE_SIZE; e += TP) {
+        const float* a = s_accpe + AC::of_packed(e);
+        part_pe[(size_t)blockIdx.x * PE_SIZE + e] = (a[0] + a[AC::SIZE]) + (a[2 * AC::SIZE] + a[3 * AC::SIZE]);
+    }
+}
+
+static int launch_measure_bwd_nn(const float* pe, const float* head, const float* enc, const float* particles, int B, int N,
+                                 const float* g_lki, float* d_particles, float* d_enc, float* d_pe, float* d_head, void* workspace,
+                                 const float* g_pred, const float* probs, cudaStream_t st) {
+    const int grid = min(B, sm_count());
+    const size_t smem = ((size_t)((NnB::ROWS * TSM + 31) & ~31) + PeTc::WBWD_FLOATS + PE_SIZE + NnB::FLOATS) * sizeof(float);
+    NFDPF_CUDA(cudaFuncSetAttribute(measure_bwd_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float* part_pe = (float*)workspace;
+    float* part_head = part_pe + (size_t)grid * PE_SIZE;
+    measure_bwd_nn_kernel<<<grid, TP, smem, st>>>(pe, head, enc, particles, B, N, g_lki, d_particles, d_enc, part_pe, part_head, g_pred, probs);
+    int rc = check_launch("measure_bwd_nn");
+    if (rc) return rc;
+    rc = launch_reduce_partials(part_pe, grid, PE_SIZE, d_pe, st);
+    if (rc) return rc;
+    return launch_reduce_partials(part_head, grid, NH_SIZE, d_head, st);
+}
+
 static size_t fwd_smem(int mode, int n_flows, int N) {
     const int n_fcnn = mode == MODE_CNF ? 4 * n_flows : 0;
     return ((size_t)PeTc::WFWD_FLOATS + PE_SIZE + 36 + (size_t)n_fcnn * CnfL1::TAIL + n_fcnn * H + (size_t)(n_fcnn / 2) * CnfL1::STAGE_FLOATS +
@@ -1326,6 +1653,7 @@ extern "C" int nfdpf_measure_fwd(int mode, const float* pe_packed, const float* 
 extern "C" int64_t nfdpf_measure_bwd_workspace(int mode, int n_flows, int B, int N) {
     (void)N;
     if (B < 1) return 0;
+    if (mode == MODE_NN) return (int64_t)min(B, sm_count()) * (PE_SIZE + NH_SIZE) * (int64_t)sizeof(float);
     int64_t per = PE_SIZE + (mode == MODE_CNF ? (TP / 32) * 4 * n_flows * packed_fcnn_size(16, 32) : 0);   // CRNVP: one partial per warp
     return (int64_t)measure_bwd_grid(mode, B) * per * (int64_t)sizeof(float);
 }
@@ -1336,13 +1664,16 @@ extern "C" int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* 
                                  const float* z_saved, const float* g_pred, const float* probs, void* stream) {
     NFDPF_REQUIRE(pe_packed && enc && particles && g_lki && d_particles && d_pe && workspace, "measure_bwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0, "measure_bwd: B and N must be positive");
-    NFDPF_REQUIRE(mode >= 0 && mode <= 2, "measure_bwd: bad mode %d", mode);
-    NFDPF_REQUIRE(mode == MODE_COS || argmax, "measure_bwd: argmax required for max-shifted likelihoods");
+    NFDPF_REQUIRE(mode >= 0 && mode <= 3, "measure_bwd: bad mode %d", mode);
+    NFDPF_REQUIRE(mode == MODE_COS || mode == MODE_NN || argmax, "measure_bwd: argmax required for max-shifted likelihoods");
+    NFDPF_REQUIRE(mode != MODE_NN || (cnf_packed && d_cnf), "measure_bwd: the NN likelihood needs the packed head + its gradient buffer");
     NFDPF_REQUIRE(!g_pred || probs, "measure_bwd: the fused prediction gradient needs the forward's probs");
     NFDPF_REQUIRE(mode != MODE_CNF || (cnf_packed && d_cnf && n_flows >= 1 && n_flows <= 4), "measure_bwd: CRNVP needs packed stack + gradient buffer");
     if (hidden != HID) { set_error("measure_bwd: kernels are built for hiddensize 32 (got %d)", hidden); return NFDPF_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
 #define ARGS pe_packed, cnf_packed, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, d_pe, d_cnf, workspace, z_saved, g_pred, probs, st
+    if (mode == MODE_NN)
+        return launch_measure_bwd_nn(pe_packed, cnf_packed, enc, particles, B, N, g_lki, d_particles, d_enc, d_pe, d_cnf, workspace, g_pred, probs, st);
     if (mode == MODE_GAUSS) return launch_measure_bwd<MODE_GAUSS>(ARGS);
     if (mode == MODE_COS) return launch_measure_bwd<MODE_COS>(ARGS);
     return launch_measure_bwd<MODE_CNF>(ARGS);

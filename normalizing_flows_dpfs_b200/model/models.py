@@ -228,8 +228,8 @@ class measurement_model_cnf(_FusedMeasurement):
 
 class measurement_model_NN(_FusedMeasurement):
     """Learned likelihood head on [obs encoding | particle encoding] (reference models.py:221-235): Sigmoid MLP 64-64-64-1, then log.
-    Forward: mode 3 of the fused measurement kernel (the head's two 64-wide layers are tcgen05 rounds behind the encoder's).  Backward:
-    see ops.MeasureUpdate (mode 3)."""
+    Mode 3 of the fused measurement kernels: the head's 64-wide layers are tcgen05 rounds behind the encoder's, forward and backward;
+    its weight gradients are register tiles on the CUDA cores (csrc/measure.cu, measure_bwd_nn_kernel)."""
     mode = "NN"
 
     def __init__(self, particle_encoder, likelihood_estimator):

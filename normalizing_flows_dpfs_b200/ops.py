@@ -159,18 +159,6 @@ def coupling_stack(packed, x, row_ctx=None, part_ctx=None, n_flows=2, inverse=Fa
 MEASURE_MODES = {"gaussian": 0, "cos": 1, "CRNVP": 2, "NN": 3}
 
 
-def _nn_loglik_torch(pe, head, enc, x):
-    """measurement_model_NN (reference models.py:221-235) from the PACKED parameter vectors, in plain torch: the recompute the
-    mode-3 backward differentiates (library GEMMs; the forward is the fused kernel)."""
-    F = torch.nn.functional
-    W1, b1, W2, b2, W3, b3 = pe[0:32].view(16, 2), pe[32:48], pe[48:560].view(32, 16), pe[560:592], pe[592:1616].view(32, 32), pe[1616:1648]
-    e = F.linear(torch.relu(F.linear(torch.relu(F.linear(x, W1, b1)), W2, b2)), W3, b3)
-    V1, c1, V2, c2, V3, c3 = (head[0:4096].view(64, 64), head[4096:4160], head[4160:8256].view(64, 64), head[8256:8320],
-                              head[8320:8384].view(1, 64), head[8384:8385])
-    h = torch.relu(F.linear(e, V1[:, 32:]) + F.linear(enc, V1[:, :32], c1)[:, None, :])      # observation half is row-constant
-    h = torch.relu(F.linear(h, V2, c2))
-    return torch.sigmoid(F.linear(h, V3, c3))[..., 0].log()
-
 
 class MeasureUpdate(torch.autograd.Function):
     """Measurement log-likelihood (model/models.py:206-278) fused with DPFs.py:187-192 when logw_prev is given.
@@ -234,18 +222,6 @@ class MeasureUpdate(torch.autograd.Function):
             g_total = d_logw if g_total is None else g_total + d_logw
         if g_total is None:
             g_total = torch.zeros(B, N, dtype=torch.float32, device=dev)
-        if mode == 3:
-            # NN likelihood: the forward is the fused kernel; the backward differentiates a recompute of models.py:221-235 in torch
-            # (cuBLAS GEMMs): its weight gradients (64 x 64 and 64 x 32 outer products per particle) do not fit the tensor-memory /
-            # shared-memory budget of the fused backward kernels next to the encoder's -- DESIGN.md section 8
-            with torch.enable_grad():
-                leaves = [t.detach().requires_grad_() for t in (pe_, cnf_, enc_, x_)]
-                lk = _nn_loglik_torch(*leaves)
-                d_pe, d_cnf, d_enc, d_x = torch.autograd.grad(lk, leaves, g_total)
-            if g_pred is not None:
-                d_x = d_x + g_pred[:, None, :] * probs[:, :, None]
-            return (d_pe, d_cnf, d_enc if ctx.needs_input_grad[2] else None, d_x, d_logw if fused else None, d_logw if has_prior else None,
-                    d_neg if has_prop else None, None, None, None, None, None, None, None)
         d_x = torch.empty_like(x_)
         d_enc = torch.empty_like(enc_) if ctx.needs_input_grad[2] else None
         d_pe = torch.empty_like(pe_)       # every entry is written by the reduce kernels

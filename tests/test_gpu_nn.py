@@ -20,6 +20,27 @@ def _pe_tuple(flat):
     return tuple(out)
 
 
+def _off_the_relu_kinks_nn(x, enc, pe, head, margin=2e-5):
+    """Same reasoning as test_gpu_ops._off_the_relu_kinks, extended to the head's two ReLU layers: a particle with a pre-activation
+    within the fp32 / 3xTF32 evaluation error of zero gets a different mask -- and a finitely different gradient -- from any two correct
+    implementations (measured: exactly one such particle among 38 000 with |pre-activation| 6.5e-8 where the typical minimum is 5e-3).
+    Those particles are moved; the parity bar stays rtol 1e-4."""
+    W = _pe_tuple(pe.double())
+    Hd = O.unpack_likelihood_head(head.double())
+    x = x.double()
+    for _ in range(6):
+        p1 = x @ W[0].t() + W[1]
+        p2 = torch.relu(p1) @ W[2].t() + W[3]
+        e = torch.relu(p2) @ W[4].t() + W[5]
+        q1 = torch.cat([enc.double()[:, None, :].expand(-1, x.shape[1], -1), e], -1) @ Hd[0].t() + Hd[1]
+        q2 = torch.relu(q1) @ Hd[2].t() + Hd[3]
+        near = (p1.abs() < margin).any(-1) | (p2.abs() < margin).any(-1) | (q1.abs() < margin).any(-1) | (q2.abs() < margin).any(-1)
+        if not bool(near.any()):
+            break
+        x = x + near[..., None] * 0.013
+    return x.float()
+
+
 def test_nn_likelihood_golden(golden):
     G = golden("meas_nn")
     for c in range(int(G["n_cases"])):
@@ -76,3 +97,32 @@ def test_filter_with_the_nn_likelihood_matches_the_oracle_step():
         pe = tuple(p.detach().cpu() for p in dpf.particle_encoder.parameters())
         head = tuple(p.detach().cpu() for p in dpf.likelihood_est.parameters())
         close(out[3][:, -1], O.measurement_nn(enc_last, x_last, pe, head), rtol=1e-4, atol=1e-5, what="NN lki inside the filter")
+
+
+@pytest.mark.parametrize("B,N", [(9, 300), (16, 1024), (300, 129), (150, 256), (300, 128)])
+def test_nn_likelihood_backward_vs_oracle(B, N):
+    """The fused mode-3 backward (tcgen05 data path, register-tiled head weight gradients, per-trajectory observation half) through the
+    fused weight update and prediction, against torch autograd of the oracle; many trajectories per persistent CTA; run twice (bitwise)."""
+    g = torch.Generator().manual_seed(7 * B + N)
+    pe = torch.cat([torch.randn(n, generator=g) * s for n, s in ((32, 0.3), (16, 0.1), (512, 0.3), (32, 0.1), (1024, 0.2), (32, 0.1))])
+    head = torch.cat([torch.randn(n, generator=g) * s for n, s in ((4096, 0.15), (64, 0.1), (4096, 0.15), (64, 0.1), (64, 0.3), (1, 0.1))])
+    enc, x = torch.randn(B, 32, generator=g), torch.randn(B, N, 2, generator=g) * 3
+    x = _off_the_relu_kinks_nn(x, enc, pe, head)
+    lw0 = torch.log_softmax(torch.randn(B, N, generator=g), -1)
+    prior, prop = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g)
+    gp, gpr, gl = torch.randn(B, N, generator=g), torch.randn(B, 2, generator=g), torch.randn(B, N, generator=g)
+    ol = [t.clone().requires_grad_() for t in (pe, head, enc, x, lw0, prior, prop)]      # (the oracle's encoder casts to fp32, like the reference)
+    lk = O.measurement_nn(ol[2], ol[3], _pe_tuple(ol[0]), O.unpack_likelihood_head(ol[1]))
+    lw = ol[4] + lk + ol[5] - ol[6]
+    pr = O.normalize_log_probs(lw) + 1e-12
+    ((pr * gp).sum() + ((pr[..., None] * ol[3]).sum(1) * gpr).sum() + (lk * gl).sum()).backward()
+    grads = []
+    for _ in range(2):
+        cl = [cu(t).requires_grad_() for t in (pe, head, enc, x, lw0, prior, prop)]
+        lki, logw, probs, row_sum, ess_inv, pred = ops.measure_update(*cl, "NN", want_pred=True)
+        ((probs * cu(gp)).sum() + (pred * cu(gpr)).sum() + (lki * cu(gl)).sum()).backward()
+        grads.append([t.grad.clone() for t in cl])
+    for a, b_ in zip(grads[0], grads[1]):
+        assert torch.equal(a, b_), "the NN backward must be run-to-run deterministic"
+    for a, o, name in zip(grads[0], ol, ("pe", "head", "enc", "x", "lw0", "prior", "prop")):
+        grad_close(a, o.grad, what="NN backward: d_" + name)
