@@ -12,7 +12,7 @@ reference's ESS rule fires 0-2 times in 50 steps and the step would 
 import torch
 
 
-def _build(flags, B, N, T, dev, cnf=False):
+def _build(flags, B, N, T, dev, cnf=False, nn_head=False):
     from normalizing_flows_dpfs_b200.arguments import parse_args
     from normalizing_flows_dpfs_b200.DPFs import DPF
     torch.manual_seed(1234)
@@ -22,6 +22,8 @@ def _build(flags, B, N, T, dev, cnf=False):
     mods = [(dpf.nf_dyn, 0.1, 0.05), (dpf.cond_model, 0.05, 0.05), (dpf.particle_encoder, 0.4, 0.2)]
     if cnf:
         mods.append((dpf.cnf_measurement, 0.1, 0.05))
+    if nn_head:
+        mods.append((dpf.likelihood_est, 0.15, 0.1))
     with torch.no_grad():
         for mod, ws, bs in mods:
             for p in mod.parameters():
@@ -31,12 +33,12 @@ def _build(flags, B, N, T, dev, cnf=False):
     return dpf
 
 
-def _time_config(name, flags, B, N, T, dev, world, timed, steps, bucket_cls=None, cnf=False, force=None):
+def _time_config(name, flags, B, N, T, dev, world, timed, steps, bucket_cls=None, cnf=False, force=None, nn_head=False):
     from bench import synth_batch
     from normalizing_flows_dpfs_b200 import ops
     from normalizing_flows_dpfs_b200.graphs import GraphedFilterStep
     rank = torch.distributed.get_rank() if world > 1 else 0
-    dpf = _build(flags, B, N, T, dev, cnf)
+    dpf = _build(flags, B, N, T, dev, cnf, nn_head)
     dpf.force_resample = force
     host = synth_batch(B, T, N, 300 + rank, pinned=False)
     host.pop("noise"), host.pop("offsets")
@@ -90,4 +92,9 @@ def extra_configs(a, dev, world, timed, peaks=None):
         cfgs["c5"]["global_batch"] = 16384
     except Exception as e:
         cfgs["c5"] = {"error": repr(e)}
+    try:   # not a BASELINE configuration: the NN likelihood, same shape as the headline, T = 10 of the 50 steps
+        cfgs["nn"] = _time_config("--NF-dyn --NF-cond --measurement NN (fused mode 3), soft resampling", nf + ["--measurement", "NN", "--resampler_type", "soft"],
+                                  1024, 1024, 10, dev, world, timed, 2, GradBucket, force=True, nn_head=True)
+    except Exception as e:
+        cfgs["nn"] = {"error": repr(e)}
     return cfgs

@@ -101,6 +101,9 @@ int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C
  *         (DPFs.py:84-86 uses p0 = 1, p1 = 10);  mode 1: measurement_model_cosine_distance, models.py:206-219;
  * mode 2: measurement_model_cnf, models.py:256-278: conditional RealNVP (D = C = hidden = 32, packed stack
  *         cnf_packed, n_flows) with prior N(p0, p1^2 I) (DPFs.py:75-76: p0 = 0, p1 = 2.5).
+ * mode 3: measurement_model_NN, models.py:221-235: log of the Sigmoid MLP build_likelihood (models.py:119-128:
+ *         Linear(64,64)-ReLU-Linear(64,64)-ReLU-Linear(64,1)) on [enc | particle encoding]; its 8385 parameters in
+ *         state_dict order arrive in cnf_packed (and their gradient in d_cnf); no row-max shift, p0 / p1 / n_flows unused.
  * pe_packed: particle encoder Linear(2,16)-ReLU-Linear(16,32)-ReLU-Linear(32,32) (models.py:130-139) in
  * state_dict order (1648 floats).  enc (B,hidden) observation encodings, particles (B,N,2).
  * lki (B,N) = log-likelihood minus its row max (modes 0,2); argmax (B,) int32 = position of that max (needed
