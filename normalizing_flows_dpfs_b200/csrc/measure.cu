@@ -1231,6 +1231,487 @@ measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const fl
     }
 }
 
+// ---- CRNVP backward, warp-specialised (round 2) ----------------------------------------------------------------------
+// The single-role kernel above spends 19 k warp instructions per 128-particle batch at 255 registers with 16.7 M local loads /
+// stores per launch: the 48-wide layer 1 of the eight nets runs on the CUDA cores twice (forward recompute and W1^T delta1) with the
+// particle encoding e and its gradient (64 registers) live across the whole stage loop, and the same four warps then contract the
+// weight gradients.  Here a CTA owns a whole SM (all 512 tensor-memory columns, 170 KB of shared memory) and has EIGHT warps:
+//   warps 0-3 (data; thread = particle = tensor-memory lane): per stage TWO tcgen05 rounds in the TS form --
+//       forward   pre[16]  = [c | e] (K = 48) x W1cat^T   (CnfL1's operand tiles, as in the forward kernel), and
+//       backward  d c[16]  = delta1[t | s] (K = 16) x W1cat[:, :16]   (fresh every stage)
+//                 d e[32] += delta1[t | s]          x W1cat[:, 16:]   (ONE tensor-memory accumulator over all stages and nets),
+//     so e lives in tensor memory (hi | lo), d e is read once per batch, and only the 8-wide tails (layers 2-3, 384 of the 1152
+//     FMAs of a stage) stay in registers; the encoder activations a1 / a2 wait in spare tensor-memory columns during the stage loop;
+//   warps 4-7 (gradient): warp 4 + w contracts over the 32 particles warp w staged (mma.sync 3xTF32, fragments of all eight nets +
+//     the encoder lane-private in tensor memory: 212 columns), one stage (both nets) per hand-over.
+// The halves meet in the gradient tile through one full / one empty mbarrier per warp pair: six hand-overs per batch (four stages,
+// encoder phase A, encoder phase B); the tile is staged while the stage's backward round is in flight.
+struct CnfB {
+    using WB = umma::Operand<48, 16>;                        // rows = layer-1 input i (c 16 | e 32), K = unit (t-net 8 | s-net 8)
+    static constexpr int L1B_STAGE_FLOATS = 2 * WB::FLOATS;  // hi | lo
+    // gradient tile rows (one column per particle): constants, conditioning half, particle encoding, two net blocks
+    static constexpr int ONE = 0, ZERO = 1, C = 2, E = 18, NET = 50, NET_ROWS = 48, ROWS = NET + 2 * NET_ROWS;
+    static constexpr int H1 = 0, H2 = 8, D1 = 16, D2 = 24, DO = 32;   // inside a net block ([D1; D2] and DO are m16 A tiles)
+    // tensor-memory columns: [0,128) = CnfL1's map (pre / d c accumulator, c | delta1 hi / lo, e hi / lo) aliased by the encoder's
+    // rounds (PeTc's map) before and after the stage loop
+    static constexpr int COL_DE = 128, COL_A1 = 160, COL_A2 = 176, COL_FRAG = 208, COL_DENC = 448, TMEM_COLS = 512;
+    static_assert(ROWS >= PR::COUNT, "the encoder phases alias the CRNVP rows");
+    static_assert(COL_FRAG + TA_END + 8 * CNF_COLS <= COL_DENC && COL_DENC + 32 <= TMEM_COLS, "fragments of two flows must fit");
+};
+
+// layers 2 and 3 of one net from its layer-1 PRE-activations (in place: a1 -> h1), keeping h2: fcnn_tail16 for the backward
+__device__ __forceinline__ void cnf_tail_fwd(const float* __restrict__ img, float (&a1)[H], float (&h2)[H], float (&out)[16]) {
+    using L = LC;
+#pragma unroll
+    for (int k = 0; k < H; k += 2) tanh_prescaled_pair(a1[k], a1[k + 1], a1[k], a1[k + 1]);
+    float b2[8];
+    ld8(img + L::B2, b2);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float w[8];
+        ld8(img + L::W2 + j * H, w);
+        float p0 = b2[j], p1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < H; k += 2) ffma2_p(p0, p1, w[k], w[k + 1], a1[k], a1[k + 1]);
+        h2[j] = p0 + p1;
+    }
+#pragma unroll
+    for (int j = 0; j < H; j += 2) tanh_prescaled_pair(h2[j], h2[j + 1], h2[j], h2[j + 1]);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        float w[8];
+        ld8(img + L::W3 + o * H, w);
+        float p0 = img[L::B3 + o], p1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; j += 2) ffma2_p(p0, p1, w[j], w[j + 1], h2[j], h2[j + 1]);
+        out[o] = p0 + p1;
+    }
+}
+// data gradient of the tail: dout -> delta2, delta1 (both divided by TANH_SCALE, as in fcnn_bwd)
+__device__ __forceinline__ void cnf_tail_bwd(const float* __restrict__ img, const float (&dout)[16], const float (&h1)[H],
+                                             const float (&h2)[H], float (&d1)[H], float (&d2)[H]) {
+    using L = LC;
+    float da2[H], da1[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) { da2[j] = 0.f; da1[j] = 0.f; }
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        float w[8];
+        ld8(img + L::W3 + o * H, w);
+#pragma unroll
+        for (int j = 0; j < H; j += 2) ffma2_s(da2[j], da2[j + 1], dout[o], w[j], w[j + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) d2[j] = da2[j] * fmaf(-TANH_ISCALE * h2[j], h2[j], TANH_ISCALE);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float w[8];
+        ld8(img + L::W2 + j * H, w);
+#pragma unroll
+        for (int k = 0; k < H; k += 2) ffma2_s(da1[k], da1[k + 1], d2[j], w[k], w[k + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < H; ++k) d1[k] = da1[k] * fmaf(-TANH_ISCALE * h1[k], h1[k], TANH_ISCALE);
+}
+
+// weight gradients of net f from the tile rows of its block (gradient warp; contracts over the 32 columns of warp pair pw):
+// CnfTmemSink::accumulate with the row map of CnfB
+__device__ __forceinline__ void cnf_accumulate_ws(const float* __restrict__ s_tile, int pw, uint32_t col, float* __restrict__ bias_f,
+                                                  int nb) {
+    using G = CnfB;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int k0 = 32 * pw;
+    float a[CNF_COLS];
+    umma::ld_frag<16>(col, a);
+    umma::ld2w(col + 16, a + 16);
+    {   // A = [delta1; delta2] x input tiles 0..3 -> rows 0-7: dW1[g][8 n + 2 t, +1]
+        float c[4][4];
+        int rowB[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { rowB[n] = G::C + 8 * n + g; c[n][0] = 0.f; c[n][1] = 0.f; c[n][2] = 0.f; c[n][3] = 0.f; }
+        mma_outer<4>(s_tile, nb + G::D1, rowB, k0, k0 + 32, c);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { a[2 * n] += c[n][0]; a[2 * n + 1] += c[n][1]; }
+    }
+    {   // input tiles 4, 5 | ONE (db1 rows 0-7, db2 rows 8-15) | h1 (rows 8-15: dW2[g][2 t, +1])
+        float c[4][4] = {};
+        const int rowB[4] = {G::C + 32 + g, G::C + 40 + g, g == 0 ? G::ONE : G::ZERO, nb + G::H1 + g};
+        mma_outer<4, 1u << 2>(s_tile, nb + G::D1, rowB, k0, k0 + 32, c);
+        a[8] += c[0][0]; a[9] += c[0][1]; a[10] += c[1][0]; a[11] += c[1][1]; a[12] += c[3][2]; a[13] += c[3][3];
+        if (t == 0) { bias_f[g] += c[2][0]; bias_f[8 + g] += c[2][2]; }
+    }
+    {   // A = d out (16 rows) x [h2 | ONE] -> dW3[g][2 t, +1], dW3[g + 8][..], db3
+        float c[2][4] = {};
+        const int rowB[2] = {nb + G::H2 + g, g == 0 ? G::ONE : G::ZERO};
+        mma_outer<2, 1u << 1>(s_tile, nb + G::DO, rowB, k0, k0 + 32, c);
+        a[14] += c[0][0]; a[15] += c[0][1]; a[16] += c[0][2]; a[17] += c[0][3];
+        if (t == 0) { bias_f[16 + g] += c[1][0]; bias_f[24 + g] += c[1][2]; }
+    }
+    umma::st_frag<16>(col, a);
+    umma::st2(col + 16, a + 16);
+    umma::wait_st();
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+measure_bwd_cnf_ws_kernel(const float* __restrict__ pe, const float* __restrict__ cnf, int n_flows, float p0, float p1,
+                          const float* __restrict__ enc, const float* __restrict__ particles, int B, int N,
+                          const float* __restrict__ g_lki, const int* __restrict__ argmax, float* __restrict__ d_particles,
+                          float* __restrict__ d_enc, float* __restrict__ part_pe, float* __restrict__ part_cnf,
+                          const float* __restrict__ z_saved, const float* __restrict__ g_pred, const float* __restrict__ probs) {
+    using G = CnfB;
+    extern __shared__ __align__(128) float smem[];
+    __shared__ float s_red[4];
+    __shared__ uint64_t s_bar;
+    __shared__ uint64_t s_full[4], s_empty[4];
+    __shared__ uint32_t s_tslot;
+    constexpr int TILE_FLOATS = (G::ROWS * TSM + 31) & ~31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool is_data = warp < 4;
+    const int pw = warp & 3;                                 // warp pair = tensor-memory lane quarter
+    const int n_fcnn = 4 * n_flows, n_st = 2 * n_flows;
+    float* s_tile = smem;                                    // [TILE_FLOATS]
+    float* s_tcw = s_tile + TILE_FLOATS;                     // encoder operand tiles
+    float* s_l1f = s_tcw + PeTc::WBWD_FLOATS;                // [n_st] layer-1 operand tiles, forward  ([16 units][48 inputs], hi | lo)
+    float* s_l1b = s_l1f + n_st * CnfL1::STAGE_FLOATS;       // [n_st] layer-1 operand tiles, backward ([48 inputs][16 units], hi | lo)
+    float* s_tail = s_l1b + n_st * G::L1B_STAGE_FLOATS;      // [n_fcnn][CnfL1::TAIL]
+    float* s_hb = s_tail + n_fcnn * CnfL1::TAIL;             // [n_fcnn][8]
+    float* s_pe = s_hb + n_fcnn * H;
+    float* s_enc = s_pe + PE_SIZE;
+    float* s_cnfbias = s_enc + 36;                           // [4][n_fcnn][32]  bias gradients of the gradient warps (t == 0 lanes)
+    float* s_denc = s_cnfbias + 4 * n_fcnn * 32;             // [4][32]
+    float* s_accpe = s_tile;                                 // read-out staging at the very end
+    static_assert(4 * AC::SIZE <= TILE_FLOATS, "read-out staging must fit in the tile");
+    if (is_data) {   // the constant rows of the bias columns, once (nothing aliases them)
+        s_tile[G::ONE * TSM + tid] = 1.0f;
+        s_tile[G::ZERO * TSM + tid] = 0.0f;
+    }
+    if (tid < 32) umma::tmem_alloc<G::TMEM_COLS>(&s_tslot);
+    if (tid == 0) {
+        umma::mbar_init(&s_bar, 1);
+        for (int w = 0; w < 4; ++w) { umma::mbar_init(&s_full[w], 32); umma::mbar_init(&s_empty[w], 32); }
+    }
+    PeTcWs tc;
+    tc.w = s_tcw; tc.bar = &s_bar; tc.tmem = 0u; tc.parity = 0u;
+    tc.load_weights(pe, true);
+    for (int e = tid; e < PE_SIZE; e += WS_THREADS) s_pe[e] = pe[e];
+    CnfL1::load(cnf, n_fcnn, s_tail, s_hb, s_l1f);
+    {
+        const int pf = packed_fcnn_size(16, 32);
+        for (int e = tid; e < n_st * 48 * 16; e += WS_THREADS) {
+            const int st = e / (48 * 16), i = (e >> 4) % 48, u = e & 15;
+            const float w = TANH_SCALE * cnf[(size_t)(2 * st + (u >> 3)) * pf + (u & 7) * 48 + i];
+            G::WB::store_elem(s_l1b + st * G::L1B_STAGE_FLOATS, s_l1b + st * G::L1B_STAGE_FLOATS + G::WB::FLOATS, i, u, w);
+        }
+        for (int e = tid; e < 4 * n_fcnn * 32; e += WS_THREADS) s_cnfbias[e] = 0.f;
+    }
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    tc.tmem = s_tslot;
+    const uint32_t lane_base = tc.tmem + ((uint32_t)(32 * pw) << 16);          // this warp's tensor-memory lanes
+    const uint32_t tacc = lane_base + G::COL_FRAG;                             // the pair's gradient fragments
+    CnfTmemSink sink{tacc + TA_CNF, s_cnfbias + pw * n_fcnn * 32};
+    uint32_t ph_full = 0, ph_empty = 1;                      // the tile starts out empty: the first `empty` wait passes
+
+    if (!is_data) {
+        // ------------------------------------------------------------------------------------ gradient warps
+        {
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c0 = 0; c0 < TA_END + CNF_COLS * n_fcnn; c0 += 4) umma::st4(tacc + c0, z);
+            umma::wait_st();
+        }
+        for (int b = blockIdx.x; b < B; b += gridDim.x) {
+            for (int n0 = 0; n0 < N; n0 += 128) {
+#pragma unroll 1
+                for (int st = n_st - 1; st >= 0; --st) {
+                    umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
+#pragma unroll 1
+                    for (int net = 0; net < 2; ++net)
+                        cnf_accumulate_ws(s_tile, pw, sink.tcol + CNF_COLS * (2 * st + net), sink.bias + (2 * st + net) * 32,
+                                          G::NET + net * G::NET_ROWS);
+                    mbar_arrive(&s_empty[pw]);
+                }
+                umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
+                pe_weight_grads_a(s_tile, tacc, pw);
+                umma::wait_st();
+                mbar_arrive(&s_empty[pw]);
+                umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
+                pe_weight_grads_b(s_tile, tacc, pw);
+                mbar_arrive(&s_empty[pw]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------------------------ data warps
+        auto stage = [&](int row, float v) { s_tile[row * TSM + tid] = v; };
+        for (int b = blockIdx.x; b < B; b += gridDim.x) {
+            data_group_sync();                               // the previous trajectory's readers of s_enc / s_red / s_denc are done
+            load_enc(enc + (size_t)b * HID, s_enc);
+            const size_t base = (size_t)b * N;
+            float gs = 0.f;                                  // row-max shift: d ll[n] = g[n] - [n == argmax] * sum_m g[m]
+            for (int n = tid; n < N; n += 128) gs += g_lki[base + n];
+            gs = warp_sum(gs);
+            if (lane == 0) s_red[warp] = gs;
+            data_group_sync();
+            gs = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+            const int am = argmax[b];
+            {   // this thread's running d_enc sums of the trajectory wait in tensor memory (32 registers less in the stage loop)
+                float z[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) z[k] = 0.f;
+                umma::st_frag<32>(lane_base + G::COL_DENC, z);
+            }
+            float2 x_next = *reinterpret_cast<const float2*>(particles + (base + (tid < N ? tid : 0)) * 2);
+            float g_next = g_lki[base + (tid < N ? tid : 0)];
+            for (int n0 = 0; n0 < N; n0 += 128) {
+                asm volatile("" ::: "memory");
+                const int n = n0 + tid;
+                const bool live = n < N;
+                const size_t p = base + (live ? n : 0);
+                const float2 x = x_next;
+                float g = live ? g_next : 0.f;
+                if (live && n == am) g -= gs;
+                {
+                    const size_t pn = base + (n + 128 < N ? n + 128 : 0);
+                    x_next = *reinterpret_cast<const float2*>(particles + pn * 2);
+                    g_next = g_lki[pn];
+                }
+                float lo[16], up[16], glo[16], gup[16];
+                {
+                    float a1[16], a2[32], e[32];
+                    pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);        // rounds 1-2: encoder layers 2 and 3 forward
+                    umma::st_frag<16>(lane_base + G::COL_A1, a1);    // parked until the encoder's backward
+                    umma::st_frag<32>(lane_base + G::COL_A2, a2);
+                    {
+                        float hi[32], l[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) umma::split(e[i], hi[i], l[i]);
+                        umma::st_frag<32>(lane_base + CnfL1::COL_EHI, hi);
+                        umma::st_frag<32>(lane_base + CnfL1::COL_ELO, l);
+                    }
+                    // the gradient warp has finished the previous batch (its encoder phase B): the tile is this warp's until the
+                    // first stage is handed over
+                    umma::mbar_wait(&s_empty[pw], ph_empty); ph_empty ^= 1;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) stage(G::E + k, e[k]);
+                }
+                {
+                    const float4* zi = reinterpret_cast<const float4*>(z_saved + p * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 a = zi[i], c4 = zi[4 + i];
+                        lo[4 * i] = a.x; lo[4 * i + 1] = a.y; lo[4 * i + 2] = a.z; lo[4 * i + 3] = a.w;
+                        up[4 * i] = c4.x; up[4 * i + 1] = c4.y; up[4 * i + 2] = c4.z; up[4 * i + 3] = c4.w;
+                    }
+                    const float c = -g / (p1 * p1);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { glo[i] = c * (lo[i] - p0); gup[i] = c * (up[i] - p0); }
+                }
+                swap_halves<16>(lo, up); swap_halves<16>(glo, gup);     // the last forward stage had c = upper
+#pragma unroll 1
+                for (int st = n_st - 1; st >= 0; --st) {                // walk the forward stages back
+                    float h1t[H], h2t[H], h1s[H], h2s[H], dt[16], ds[16];
+                    {
+                        // forward round: this thread's conditioning half -> tensor memory, pre = [c | e] W1cat^T
+                        float pre[16];
+                        {
+                            float hi[16], l[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) umma::split(lo[i], hi[i], l[i]);
+                            umma::st_frag<16>(lane_base + CnfL1::COL_CHI, hi);
+                            umma::st_frag<16>(lane_base + CnfL1::COL_CLO, l);
+                        }
+                        umma::wait_st();
+                        umma::fence_before_sync();
+                        data_group_sync();
+                        if (tid == 0) {
+                            umma::fence_after_sync();
+                            constexpr uint32_t idesc = umma::idesc_tf32(128, 16);
+                            const float* w_hi = s_l1f + st * CnfL1::STAGE_FLOATS;
+                            const float* w_lo = w_hi + CnfL1::W::FLOATS;
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (int k0 = 0; k0 < 48; k0 += 8) { umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, tc.tmem + CnfL1::COL_CLO + k0, CnfL1::W::desc(w_hi, k0), idesc, acc); acc = 1; }
+#pragma unroll
+                            for (int k0 = 0; k0 < 48; k0 += 8) umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, tc.tmem + CnfL1::COL_CHI + k0, CnfL1::W::desc(w_lo, k0), idesc, 1);
+#pragma unroll
+                            for (int k0 = 0; k0 < 48; k0 += 8) umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, tc.tmem + CnfL1::COL_CHI + k0, CnfL1::W::desc(w_hi, k0), idesc, 1);
+                            umma::commit(tc.bar);
+                        }
+                        tc.wait();
+                        umma::ld16(lane_base + CnfL1::COL_D, pre);
+                        const float* hb = s_hb + 2 * st * H;
+#pragma unroll
+                        for (int k = 0; k < H; ++k) { h1t[k] = pre[k] + hb[k]; h1s[k] = pre[H + k] + hb[H + k]; }
+                    }
+                    const float* im_t = CnfL1::tail_image(s_tail, 2 * st);
+                    const float* im_s = CnfL1::tail_image(s_tail, 2 * st + 1);
+                    {
+                        float t[16], s[16];
+                        cnf_tail_fwd(im_t, h1t, h2t, t);
+                        cnf_tail_fwd(im_s, h1s, h2s, s);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {                  // out = t + in e^s (coupling.cuh stage_bwd, forward direction)
+                            const float es = expf(s[i]), ies = expf(-s[i]);
+                            const float vin = (up[i] - t[i]) * ies;
+                            dt[i] = live ? gup[i] : 0.f;
+                            ds[i] = live ? fmaf(gup[i] * vin, es, g) : 0.f;
+                            gup[i] = gup[i] * es;
+                            up[i] = vin;
+                        }
+                    }
+                    float d1t[H], d2t[H], d1s[H], d2s[H];
+                    cnf_tail_bwd(im_t, dt, h1t, h2t, d1t, d2t);
+                    cnf_tail_bwd(im_s, ds, h1s, h2s, d1s, d2s);
+                    {   // backward round: delta1 of both nets -> tensor memory (over the conditioning columns)
+                        float hi[16], l[16];
+#pragma unroll
+                        for (int k = 0; k < H; ++k) { umma::split(d1t[k], hi[k], l[k]); umma::split(d1s[k], hi[H + k], l[H + k]); }
+                        umma::st_frag<16>(lane_base + CnfL1::COL_CHI, hi);
+                        umma::st_frag<16>(lane_base + CnfL1::COL_CLO, l);
+                    }
+                    umma::wait_st();
+                    umma::fence_before_sync();
+                    data_group_sync();
+                    if (tid == 0) {
+                        umma::fence_after_sync();
+                        constexpr uint32_t id16 = umma::idesc_tf32(128, 16), id32 = umma::idesc_tf32(128, 32);
+                        const float* b_hi = s_l1b + st * G::L1B_STAGE_FLOATS;
+                        const float* b_lo = b_hi + G::WB::FLOATS;
+                        const uint32_t a_hi = tc.tmem + CnfL1::COL_CHI, a_lo = tc.tmem + CnfL1::COL_CLO;
+                        auto desc = [](const float* base, int r0, int k0) {
+                            return umma::smem_desc(umma::smem_u32(base) + (k0 / 4) * G::WB::CHUNK_BYTES + r0 * 16, G::WB::CHUNK_BYTES, 128);
+                        };
+                        // d c = delta1 W1cat[:, :16]: fresh accumulator (the pre-activation columns, read above)
+                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_lo, desc(b_hi, 0, 0), id16, 0);
+                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_lo + 8, desc(b_hi, 0, 8), id16, 1);
+                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_hi, desc(b_lo, 0, 0), id16, 1);
+                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_hi + 8, desc(b_lo, 0, 8), id16, 1);
+                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_hi, desc(b_hi, 0, 0), id16, 1);
+                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_hi + 8, desc(b_hi, 0, 8), id16, 1);
+                        // d e += delta1 W1cat[:, 16:]: one accumulator over the whole stack
+                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_lo, desc(b_hi, 16, 0), id32, st == n_st - 1 ? 0u : 1u);
+                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_lo + 8, desc(b_hi, 16, 8), id32, 1);
+                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_hi, desc(b_lo, 16, 0), id32, 1);
+                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_hi + 8, desc(b_lo, 16, 8), id32, 1);
+                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_hi, desc(b_hi, 16, 0), id32, 1);
+                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_hi + 8, desc(b_hi, 16, 8), id32, 1);
+                        umma::commit(tc.bar);
+                    }
+                    // hand the stage to the gradient warp while the product is in flight
+                    if (st != n_st - 1) { umma::mbar_wait(&s_empty[pw], ph_empty); ph_empty ^= 1; }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        stage(G::C + i, lo[i]);
+                        stage(G::NET + G::DO + i, dt[i]);
+                        stage(G::NET + G::NET_ROWS + G::DO + i, ds[i]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < H; ++k) {
+                        stage(G::NET + G::H1 + k, h1t[k]); stage(G::NET + G::H2 + k, h2t[k]);
+                        stage(G::NET + G::D1 + k, d1t[k]); stage(G::NET + G::D2 + k, d2t[k]);
+                        stage(G::NET + G::NET_ROWS + G::H1 + k, h1s[k]); stage(G::NET + G::NET_ROWS + G::H2 + k, h2s[k]);
+                        stage(G::NET + G::NET_ROWS + G::D1 + k, d1s[k]); stage(G::NET + G::NET_ROWS + G::D2 + k, d2s[k]);
+                    }
+                    mbar_arrive(&s_full[pw]);
+                    tc.wait();
+                    {
+                        float dc[16];
+                        umma::ld16(lane_base + CnfL1::COL_D, dc);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) glo[i] += dc[i];
+                    }
+                    swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
+                }
+                swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
+                {
+                    float denc[32];
+                    umma::ld32(lane_base + G::COL_DENC, denc);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { denc[i] += live ? glo[i] : 0.f; denc[16 + i] += live ? gup[i] : 0.f; }
+                    umma::st_frag<32>(lane_base + G::COL_DENC, denc);
+                }
+                // encoder backward: delta3 = d e (dead threads: every delta above was zeroed, so the accumulator row is exactly 0)
+                float de[32], a2[32];
+                umma::ld32(lane_base + G::COL_DE, de);
+                umma::ld32(lane_base + G::COL_A2, a2);
+                umma::mbar_wait(&s_empty[pw], ph_empty); ph_empty ^= 1;
+                uint32_t m2 = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    stage(PR::D3 + j, de[j]);
+                    stage(PR::A2 + j, a2[j]);
+                    m2 |= (a2[j] > 0.f ? 1u : 0u) << j;
+                }
+                mbar_arrive(&s_full[pw]);
+                float d2[32], d1[16], a1[16];
+                tc.template store_row<32>(de);
+                tc.template round<32, 32>(PeTc::W3T_HI, PeTc::W3T_LO);
+                umma::ld32(lane_base, d2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) d2[j] = (m2 >> j) & 1u ? d2[j] : 0.f;
+                tc.template store_row<32>(d2);
+                tc.template round<16, 32>(PeTc::W2T_HI, PeTc::W2T_LO);
+                umma::ld16(lane_base, d1);
+                umma::ld16(lane_base + G::COL_A1, a1);
+                float dx0 = 0.f, dx1 = 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; k += 2) {
+                    const float4 q = *reinterpret_cast<const float4*>(s_pe + PE_W1 + 2 * k);
+                    d1[k] = a1[k] > 0.f ? d1[k] : 0.f;
+                    d1[k + 1] = a1[k + 1] > 0.f ? d1[k + 1] : 0.f;
+                    dx0 = fmaf(q.x, d1[k], dx0); dx1 = fmaf(q.y, d1[k], dx1);
+                    dx0 = fmaf(q.z, d1[k + 1], dx0); dx1 = fmaf(q.w, d1[k + 1], dx1);
+                }
+                if (live) {
+                    if (g_pred) {      // fused prediction (losses.py:22): d pred / d x_n = probs[n]
+                        const float pr = probs[p];
+                        dx0 = fmaf(g_pred[2 * b], pr, dx0); dx1 = fmaf(g_pred[2 * b + 1], pr, dx1);
+                    }
+                    *reinterpret_cast<float2*>(d_particles + p * 2) = make_float2(dx0, dx1);
+                }
+                umma::mbar_wait(&s_empty[pw], ph_empty); ph_empty ^= 1;
+                stage(PR::X + 0, x.x);
+                stage(PR::X + 1, x.y);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { stage(PR::A1 + k, a1[k]); stage(PR::D1 + k, d1[k]); }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stage(PR::D2 + j, d2[j]);
+                mbar_arrive(&s_full[pw]);
+            }
+            // d_enc[b][k] = sum over the row's particles of the stack's input gradient (fixed order: butterfly, then warps)
+            if (d_enc) {
+                float denc[32];
+                umma::wait_st();
+                umma::ld32(lane_base + G::COL_DENC, denc);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const float v = warp_sum(denc[k]);
+                    if (lane == 0) s_denc[warp * 32 + k] = v;
+                }
+                data_group_sync();
+                if (tid < 32) d_enc[(size_t)b * HID + tid] = (s_denc[tid] + s_denc[32 + tid]) + (s_denc[64 + tid] + s_denc[96 + tid]);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();                                   // every contraction is done: the tile becomes the read-out staging area
+    umma::fence_after_sync();
+    for (int e = tid; e < 4 * AC::SIZE; e += WS_THREADS) s_accpe[e] = 0.f;
+    __syncthreads();
+    if (!is_data) {
+        pe_weight_grads_readout(tacc, s_accpe + pw * AC::SIZE);
+        sink.readout(n_fcnn, part_cnf + ((size_t)blockIdx.x * 4 + pw) * n_fcnn * packed_fcnn_size(16, 32));
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_free<G::TMEM_COLS>(tc.tmem);
+    for (int e = tid; e < PE_SIZE; e += WS_THREADS) {
+        const float* a = s_accpe + AC::of_packed(e);
+        part_pe[(size_t)blockIdx.x * PE_SIZE + e] = (a[0] + a[AC::SIZE]) + (a[2 * AC::SIZE] + a[3 * AC::SIZE]);
+    }
+}
+
 // ---- NN likelihood, backward (mode 3) --------------------------------------------------------------------------------
 // One 128-thread CTA per SM (the head's four operand tiles alone are 96 KB), persistent over trajectories.  Per 128-particle batch:
 //   data path (thread = particle = tensor-memory lane): encoder forward (2 rounds), head forward (2 rounds: N = 64, K = 32 / 64),
@@ -1573,6 +2054,14 @@ static size_t bwd_smem(int mode, int n_flows) {
     return fl * sizeof(float);
 }
 
+static size_t bwd_cnf_ws_smem(int n_flows) {
+    const int n_fcnn = 4 * n_flows, n_st = 2 * n_flows;
+    const size_t tile = ((size_t)CnfB::ROWS * TSM + 31) & ~(size_t)31;
+    size_t fl = tile + PeTc::WBWD_FLOATS + (size_t)n_st * (CnfL1::STAGE_FLOATS + CnfB::L1B_STAGE_FLOATS) + (size_t)n_fcnn * CnfL1::TAIL + n_fcnn * H +
+                PE_SIZE + 36 + (size_t)4 * n_fcnn * 32 + 4 * 32;
+    return fl * sizeof(float);
+}
+
 template <int MODE>
 static int launch_measure_fwd(const float* pe, const float* cnf, int n_flows, float p0, float p1, const float* enc, const float* particles,
                               int B, int N, const float* lw0, const float* prior, const float* propose, float add_eps, float* lki,
@@ -1607,6 +2096,19 @@ static int launch_measure_bwd(const float* pe, const float* cnf, int n_flows, fl
     float* part_pe = (float*)workspace;
     float* part_cnf = part_pe + (size_t)grid * PE_SIZE;
     static const bool single_role = getenv("NFDPF_MEASURE_BWD_V1") != nullptr;     // A/B timing against the round-1 kernel
+    if (MODE == MODE_CNF && !single_role && z_saved && n_flows <= 2) {
+        // warp-specialised CRNVP kernel: one CTA per SM (all of its tensor memory); walks the stack back from the saved flow output
+        const int g1 = min(B, sm_count());
+        const size_t s1 = bwd_cnf_ws_smem(n_flows);
+        NFDPF_CUDA(cudaFuncSetAttribute(measure_bwd_cnf_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+        measure_bwd_cnf_ws_kernel<<<g1, WS_THREADS, s1, st>>>(pe, cnf, n_flows, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc,
+                                                              part_pe, part_cnf, z_saved, g_pred, probs);
+        int rc1 = check_launch("measure_bwd (CRNVP, warp-specialised)");
+        if (rc1) return rc1;
+        rc1 = launch_reduce_partials(part_pe, g1, PE_SIZE, d_pe, st);
+        if (rc1) return rc1;
+        return launch_reduce_partials(part_cnf, g1 * 4, 4 * n_flows * packed_fcnn_size(16, 32), d_cnf, st);
+    }
     if (MODE == MODE_GAUSS && !single_role) {     // (cos: its 32 running d_enc sums per thread spill at 128 registers -- measured slower)
         const size_t ws_smem = smem;
         launch_measure_bwd_ws<MODE == MODE_CNF ? MODE_GAUSS : MODE>(pe, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe,
