@@ -1236,12 +1236,15 @@ measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const fl
 // stores per launch: the 48-wide layer 1 of the eight nets runs on the CUDA cores twice (forward recompute and W1^T delta1) with the
 // particle encoding e and its gradient (64 registers) live across the whole stage loop, and the same four warps then contract the
 // weight gradients.  Here a CTA owns a whole SM (all 512 tensor-memory columns, 170 KB of shared memory) and has EIGHT warps:
-//   warps 0-3 (data; thread = particle = tensor-memory lane): per stage TWO tcgen05 rounds in the TS form --
+//   warps 0-3 (data; thread = particle = tensor-memory lane): per stage two tcgen05 products in the TS form --
 //       forward   pre[16]  = [c | e] (K = 48) x W1cat^T   (CnfL1's operand tiles, as in the forward kernel), and
-//       backward  d c[16]  = delta1[t | s] (K = 16) x W1cat[:, :16]   (fresh every stage)
-//                 d e[32] += delta1[t | s]          x W1cat[:, 16:]   (ONE tensor-memory accumulator over all stages and nets),
+//       backward  [d c | d e] += delta1[t | s] (K = 16) x W1cat   (N = 48; the thread zeroes its d c columns every stage, d e is ONE
+//                 tensor-memory accumulator over all stages and nets),
 //     so e lives in tensor memory (hi | lo), d e is read once per batch, and only the 8-wide tails (layers 2-3, 384 of the 1152
-//     FMAs of a stage) stay in registers; the encoder activations a1 / a2 wait in spare tensor-memory columns during the stage loop;
+//     FMAs of a stage) stay in registers; the encoder activations a1 / a2 and the thread's d_enc sums wait in spare tensor-memory
+//     columns.  The NEXT stage's conditioning half is this stage's inverted half, known before the tails' backward: the backward
+//     product of stage st and the forward product of stage st - 1 are issued together -- ONE issue -> commit -> wait round per stage
+//     (nine per batch with the encoder's four) instead of two;
 //   warps 4-7 (gradient): warp 4 + w contracts over the 32 particles warp w staged (mma.sync 3xTF32, fragments of all eight nets +
 //     the encoder lane-private in tensor memory: 212 columns), one stage (both nets) per hand-over.
 // The halves meet in the gradient tile through one full / one empty mbarrier per warp pair: six hand-overs per batch (four stages,
@@ -1252,11 +1255,14 @@ struct CnfB {
     // gradient tile rows (one column per particle): constants, conditioning half, particle encoding, two net blocks
     static constexpr int ONE = 0, ZERO = 1, C = 2, E = 18, NET = 50, NET_ROWS = 48, ROWS = NET + 2 * NET_ROWS;
     static constexpr int H1 = 0, H2 = 8, D1 = 16, D2 = 24, DO = 32;   // inside a net block ([D1; D2] and DO are m16 A tiles)
-    // tensor-memory columns: [0,128) = CnfL1's map (pre / d c accumulator, c | delta1 hi / lo, e hi / lo) aliased by the encoder's
-    // rounds (PeTc's map) before and after the stage loop
-    static constexpr int COL_DE = 128, COL_A1 = 160, COL_A2 = 176, COL_FRAG = 208, COL_DENC = 448, TMEM_COLS = 512;
+    // tensor-memory columns: pre-activation accumulator | layer-1 activation row [c | e] hi, lo (K = 48 each) | delta1 hi, lo (K = 16
+    // each) | d c (fresh every stage) and d e (ONE accumulator over the stack), contiguous: one N = 48 product | parked encoder
+    // activations a1, a2 | the thread's running d_enc sums | gradient fragments.  The encoder's rounds (PeTc's map) alias [0,96)
+    // before and after the stage loop.
+    static constexpr int COL_PRE = 0, COL_AHI = 16, COL_ALO = 64, COL_D1HI = 112, COL_D1LO = 128, COL_DC = 144, COL_DE = 160,
+                         COL_A1 = 192, COL_A2 = 208, COL_DENC = 240, COL_FRAG = 272, TMEM_COLS = 512;
     static_assert(ROWS >= PR::COUNT, "the encoder phases alias the CRNVP rows");
-    static_assert(COL_FRAG + TA_END + 8 * CNF_COLS <= COL_DENC && COL_DENC + 32 <= TMEM_COLS, "fragments of two flows must fit");
+    static_assert(COL_FRAG + TA_END + 8 * CNF_COLS <= TMEM_COLS, "fragments of two flows must fit");
 };
 
 // layers 2 and 3 of one net from its layer-1 PRE-activations (in place: a1 -> h1), keeping h2: fcnn_tail16 for the backward
@@ -1477,6 +1483,8 @@ measure_bwd_cnf_ws_kernel(const float* __restrict__ pe, const float* __restrict_
                     g_next = g_lki[pn];
                 }
                 float lo[16], up[16], glo[16], gup[16];
+                // the flow output of the forward (one 128-byte line per thread): on its way while the encoder's rounds run
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(z_saved + p * 32));
                 {
                     float a1[16], a2[32], e[32];
                     pe_fwd_tc(tc, s_pe, x.x, x.y, a1, a2, e);        // rounds 1-2: encoder layers 2 and 3 forward
@@ -1486,8 +1494,11 @@ measure_bwd_cnf_ws_kernel(const float* __restrict__ pe, const float* __restrict_
                         float hi[32], l[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i) umma::split(e[i], hi[i], l[i]);
-                        umma::st_frag<32>(lane_base + CnfL1::COL_EHI, hi);
-                        umma::st_frag<32>(lane_base + CnfL1::COL_ELO, l);
+                        umma::st_frag<32>(lane_base + G::COL_AHI + 16, hi);
+                        umma::st_frag<32>(lane_base + G::COL_ALO + 16, l);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) hi[i] = 0.f;
+                        umma::st_frag<32>(lane_base + G::COL_DE, hi);    // d e accumulates over the stack: starts from zero
                     }
                     // the gradient warp has finished the previous batch (its encoder phase B): the tile is this warp's until the
                     // first stage is handed over
@@ -1503,43 +1514,49 @@ measure_bwd_cnf_ws_kernel(const float* __restrict__ pe, const float* __restrict_
                         lo[4 * i] = a.x; lo[4 * i + 1] = a.y; lo[4 * i + 2] = a.z; lo[4 * i + 3] = a.w;
                         up[4 * i] = c4.x; up[4 * i + 1] = c4.y; up[4 * i + 2] = c4.z; up[4 * i + 3] = c4.w;
                     }
-                    const float c = -g / (p1 * p1);
+                    const float c = -g / (p1 * p1);          // dead threads: g = 0, so glo / gup and every delta below stay exactly 0
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { glo[i] = c * (lo[i] - p0); gup[i] = c * (up[i] - p0); }
                 }
                 swap_halves<16>(lo, up); swap_halves<16>(glo, gup);     // the last forward stage had c = upper
+                // this thread's conditioning half (hi | lo) -> the first 16 columns of the layer-1 activation row
+                auto put_c = [&](const float (&c)[16]) {
+                    float hi[16], l[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) umma::split(c[i], hi[i], l[i]);
+                    umma::st_frag<16>(lane_base + G::COL_AHI, hi);
+                    umma::st_frag<16>(lane_base + G::COL_ALO, l);
+                };
+                // leader: pre = [c | e] W1cat^T of stage st (18 MMAs)
+                auto issue_fwd = [&](int st) {
+                    constexpr uint32_t idesc = umma::idesc_tf32(128, 16);
+                    const float* w_hi = s_l1f + st * CnfL1::STAGE_FLOATS;
+                    const float* w_lo = w_hi + CnfL1::W::FLOATS;
+                    const uint32_t d = tc.tmem + G::COL_PRE, a_hi = tc.tmem + G::COL_AHI, a_lo = tc.tmem + G::COL_ALO;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int k0 = 0; k0 < 48; k0 += 8) { umma::mma_tf32_ts(d, a_lo + k0, CnfL1::W::desc(w_hi, k0), idesc, acc); acc = 1; }
+#pragma unroll
+                    for (int k0 = 0; k0 < 48; k0 += 8) umma::mma_tf32_ts(d, a_hi + k0, CnfL1::W::desc(w_lo, k0), idesc, 1);
+#pragma unroll
+                    for (int k0 = 0; k0 < 48; k0 += 8) umma::mma_tf32_ts(d, a_hi + k0, CnfL1::W::desc(w_hi, k0), idesc, 1);
+                };
+                put_c(lo);
+                umma::wait_st();
+                umma::fence_before_sync();
+                data_group_sync();
+                if (tid == 0) {
+                    umma::fence_after_sync();
+                    issue_fwd(n_st - 1);
+                    umma::commit(tc.bar);
+                }
+                tc.wait();
+                float pre[16];
+                umma::ld16(lane_base + G::COL_PRE, pre);
 #pragma unroll 1
                 for (int st = n_st - 1; st >= 0; --st) {                // walk the forward stages back
-                    float h1t[H], h2t[H], h1s[H], h2s[H], dt[16], ds[16];
+                    float h1t[H], h2t[H], h1s[H], h2s[H], ds[16], d1t[H], d1s[H], d2s[H];
                     {
-                        // forward round: this thread's conditioning half -> tensor memory, pre = [c | e] W1cat^T
-                        float pre[16];
-                        {
-                            float hi[16], l[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) umma::split(lo[i], hi[i], l[i]);
-                            umma::st_frag<16>(lane_base + CnfL1::COL_CHI, hi);
-                            umma::st_frag<16>(lane_base + CnfL1::COL_CLO, l);
-                        }
-                        umma::wait_st();
-                        umma::fence_before_sync();
-                        data_group_sync();
-                        if (tid == 0) {
-                            umma::fence_after_sync();
-                            constexpr uint32_t idesc = umma::idesc_tf32(128, 16);
-                            const float* w_hi = s_l1f + st * CnfL1::STAGE_FLOATS;
-                            const float* w_lo = w_hi + CnfL1::W::FLOATS;
-                            uint32_t acc = 0;
-#pragma unroll
-                            for (int k0 = 0; k0 < 48; k0 += 8) { umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, tc.tmem + CnfL1::COL_CLO + k0, CnfL1::W::desc(w_hi, k0), idesc, acc); acc = 1; }
-#pragma unroll
-                            for (int k0 = 0; k0 < 48; k0 += 8) umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, tc.tmem + CnfL1::COL_CHI + k0, CnfL1::W::desc(w_lo, k0), idesc, 1);
-#pragma unroll
-                            for (int k0 = 0; k0 < 48; k0 += 8) umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, tc.tmem + CnfL1::COL_CHI + k0, CnfL1::W::desc(w_hi, k0), idesc, 1);
-                            umma::commit(tc.bar);
-                        }
-                        tc.wait();
-                        umma::ld16(lane_base + CnfL1::COL_D, pre);
                         const float* hb = s_hb + 2 * st * H;
 #pragma unroll
                         for (int k = 0; k < H; ++k) { h1t[k] = pre[k] + hb[k]; h1s[k] = pre[H + k] + hb[H + k]; }
@@ -1550,66 +1567,63 @@ measure_bwd_cnf_ws_kernel(const float* __restrict__ pe, const float* __restrict_
                         float t[16], s[16];
                         cnf_tail_fwd(im_t, h1t, h2t, t);
                         cnf_tail_fwd(im_s, h1s, h2s, s);
+                        {   // t-net: its d out is the incoming gradient of the transformed half (out = t + in e^s); staged at once
+                            float d2t[H];
+                            cnf_tail_bwd(im_t, gup, h1t, h2t, d1t, d2t);
+                            if (st != n_st - 1) { umma::mbar_wait(&s_empty[pw], ph_empty); ph_empty ^= 1; }
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {                  // out = t + in e^s (coupling.cuh stage_bwd, forward direction)
-                            const float es = expf(s[i]), ies = expf(-s[i]);
+                            for (int i = 0; i < 16; ++i) { stage(G::C + i, lo[i]); stage(G::NET + G::DO + i, gup[i]); }
+#pragma unroll
+                            for (int k = 0; k < H; ++k) {
+                                stage(G::NET + G::H1 + k, h1t[k]); stage(G::NET + G::H2 + k, h2t[k]);
+                                stage(G::NET + G::D1 + k, d1t[k]); stage(G::NET + G::D2 + k, d2t[k]);
+                            }
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {                  // coupling.cuh stage_bwd, forward direction
+                            const float es = exp_acc(s[i]), ies = exp_acc(-s[i]);
                             const float vin = (up[i] - t[i]) * ies;
-                            dt[i] = live ? gup[i] : 0.f;
-                            ds[i] = live ? fmaf(gup[i] * vin, es, g) : 0.f;
+                            ds[i] = fmaf(gup[i] * vin, es, g);
                             gup[i] = gup[i] * es;
                             up[i] = vin;
                         }
                     }
-                    float d1t[H], d2t[H], d1s[H], d2s[H];
-                    cnf_tail_bwd(im_t, dt, h1t, h2t, d1t, d2t);
+                    if (st > 0) put_c(up);          // the next stage conditions on the half just inverted: its forward product rides along
                     cnf_tail_bwd(im_s, ds, h1s, h2s, d1s, d2s);
-                    {   // backward round: delta1 of both nets -> tensor memory (over the conditioning columns)
+                    {   // delta1 of both nets (K = 16) and a zeroed d c accumulator -> tensor memory
                         float hi[16], l[16];
 #pragma unroll
                         for (int k = 0; k < H; ++k) { umma::split(d1t[k], hi[k], l[k]); umma::split(d1s[k], hi[H + k], l[H + k]); }
-                        umma::st_frag<16>(lane_base + CnfL1::COL_CHI, hi);
-                        umma::st_frag<16>(lane_base + CnfL1::COL_CLO, l);
+                        umma::st_frag<16>(lane_base + G::COL_D1HI, hi);
+                        umma::st_frag<16>(lane_base + G::COL_D1LO, l);
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) hi[k] = 0.f;
+                        umma::st_frag<16>(lane_base + G::COL_DC, hi);
                     }
                     umma::wait_st();
                     umma::fence_before_sync();
                     data_group_sync();
                     if (tid == 0) {
                         umma::fence_after_sync();
-                        constexpr uint32_t id16 = umma::idesc_tf32(128, 16), id32 = umma::idesc_tf32(128, 32);
+                        constexpr uint32_t id48 = umma::idesc_tf32(128, 48);
                         const float* b_hi = s_l1b + st * G::L1B_STAGE_FLOATS;
                         const float* b_lo = b_hi + G::WB::FLOATS;
-                        const uint32_t a_hi = tc.tmem + CnfL1::COL_CHI, a_lo = tc.tmem + CnfL1::COL_CLO;
-                        auto desc = [](const float* base, int r0, int k0) {
-                            return umma::smem_desc(umma::smem_u32(base) + (k0 / 4) * G::WB::CHUNK_BYTES + r0 * 16, G::WB::CHUNK_BYTES, 128);
-                        };
-                        // d c = delta1 W1cat[:, :16]: fresh accumulator (the pre-activation columns, read above)
-                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_lo, desc(b_hi, 0, 0), id16, 0);
-                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_lo + 8, desc(b_hi, 0, 8), id16, 1);
-                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_hi, desc(b_lo, 0, 0), id16, 1);
-                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_hi + 8, desc(b_lo, 0, 8), id16, 1);
-                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_hi, desc(b_hi, 0, 0), id16, 1);
-                        umma::mma_tf32_ts(tc.tmem + CnfL1::COL_D, a_hi + 8, desc(b_hi, 0, 8), id16, 1);
-                        // d e += delta1 W1cat[:, 16:]: one accumulator over the whole stack
-                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_lo, desc(b_hi, 16, 0), id32, st == n_st - 1 ? 0u : 1u);
-                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_lo + 8, desc(b_hi, 16, 8), id32, 1);
-                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_hi, desc(b_lo, 16, 0), id32, 1);
-                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_hi + 8, desc(b_lo, 16, 8), id32, 1);
-                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_hi, desc(b_hi, 16, 0), id32, 1);
-                        umma::mma_tf32_ts(tc.tmem + G::COL_DE, a_hi + 8, desc(b_hi, 16, 8), id32, 1);
+                        const uint32_t a_hi = tc.tmem + G::COL_D1HI, a_lo = tc.tmem + G::COL_D1LO, d = tc.tmem + G::COL_DC;
+                        // [d c | d e] += delta1 W1cat
+                        umma::mma_tf32_ts(d, a_lo, G::WB::desc(b_hi, 0), id48, 1);
+                        umma::mma_tf32_ts(d, a_lo + 8, G::WB::desc(b_hi, 8), id48, 1);
+                        umma::mma_tf32_ts(d, a_hi, G::WB::desc(b_lo, 0), id48, 1);
+                        umma::mma_tf32_ts(d, a_hi + 8, G::WB::desc(b_lo, 8), id48, 1);
+                        umma::mma_tf32_ts(d, a_hi, G::WB::desc(b_hi, 0), id48, 1);
+                        umma::mma_tf32_ts(d, a_hi + 8, G::WB::desc(b_hi, 8), id48, 1);
+                        if (st > 0) issue_fwd(st - 1);
                         umma::commit(tc.bar);
                     }
-                    // hand the stage to the gradient warp while the product is in flight
-                    if (st != n_st - 1) { umma::mbar_wait(&s_empty[pw], ph_empty); ph_empty ^= 1; }
+                    // hand the stage to the gradient warp while the products are in flight
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        stage(G::C + i, lo[i]);
-                        stage(G::NET + G::DO + i, dt[i]);
-                        stage(G::NET + G::NET_ROWS + G::DO + i, ds[i]);
-                    }
+                    for (int i = 0; i < 16; ++i) stage(G::NET + G::NET_ROWS + G::DO + i, ds[i]);
 #pragma unroll
                     for (int k = 0; k < H; ++k) {
-                        stage(G::NET + G::H1 + k, h1t[k]); stage(G::NET + G::H2 + k, h2t[k]);
-                        stage(G::NET + G::D1 + k, d1t[k]); stage(G::NET + G::D2 + k, d2t[k]);
                         stage(G::NET + G::NET_ROWS + G::H1 + k, h1s[k]); stage(G::NET + G::NET_ROWS + G::H2 + k, h2s[k]);
                         stage(G::NET + G::NET_ROWS + G::D1 + k, d1s[k]); stage(G::NET + G::NET_ROWS + G::D2 + k, d2s[k]);
                     }
@@ -1617,10 +1631,11 @@ measure_bwd_cnf_ws_kernel(const float* __restrict__ pe, const float* __restrict_
                     tc.wait();
                     {
                         float dc[16];
-                        umma::ld16(lane_base + CnfL1::COL_D, dc);
+                        umma::ld16(lane_base + G::COL_DC, dc);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) glo[i] += dc[i];
                     }
+                    if (st > 0) umma::ld16(lane_base + G::COL_PRE, pre);
                     swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
                 }
                 swap_halves<16>(lo, up); swap_halves<16>(glo, gup);
