@@ -70,6 +70,43 @@ def _time_config(name, flags, B, N, T, dev, world, timed, steps, bucket_cls=None
     return out
 
 
+def crnvp_roofline(dev):
+    """c3's own kernels (BASELINE configs[2]): the CRNVP measurement forward / backward timed alone at B = N = 1024 (CUDA events).
+    Algorithmic FLOP per particle: encoder 3136 + stack 9216 forward, twice that backward.  EXECUTED tensor FLOP per
+    particle (3xTF32: every product is issued three times): forward = encoder layers 2-3 + layer 1 of the eight nets on tcgen05
+    (1536 + 3072 FMA); backward = those again (recompute) + W3^T d3, W2^T d2 + delta1 W1cat of the four stages on tcgen05
+    (4608 + 1536 + 3072 FMA) + the weight-gradient contractions on mma.sync (8 x 608 + 1648 FMA).  Both kernels are bound by the
+    latency of their issue -> commit -> wait rounds and of the legacy mma.sync path, not by either peak: the fractions say how far."""
+    from bench_extras import _events, measured_peaks
+    from normalizing_flows_dpfs_b200 import ops
+    from normalizing_flows_dpfs_b200.nf.flows import pack_parameters
+    B = N = 1024
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = (torch.randn(B, N, 2, device=dev, generator=g) * 2).requires_grad_()
+    gl = torch.randn(B, N, device=dev, generator=g)
+    enc = torch.randn(B, 32, device=dev, generator=g)
+    lw0 = torch.log_softmax(torch.randn(B, N, device=dev, generator=g), -1)
+    dpf = _build(["--NF-dyn", "--NF-cond", "--measurement", "CRNVP", "--resampler_type", "soft"], 8, N, 2, dev, cnf=True)
+    with torch.no_grad():
+        pe = pack_parameters([dpf.particle_encoder]).detach().clone().requires_grad_()
+        cnf = pack_parameters([dpf.cnf_measurement]).detach().clone().requires_grad_()
+    out = ops.measure_update(pe, cnf, enc, x, lw0, gl, gl, "CRNVP", p0=0.0, p1=2.5)
+    tf = _events(lambda: ops.measure_update(pe, cnf, enc, x, lw0, gl, gl, "CRNVP", p0=0.0, p1=2.5), n=5)
+    tb = _events(lambda: torch.autograd.backward([out[0], out[2]], [gl, gl], retain_graph=True), n=5)
+    peaks = measured_peaks(dev)
+    P = B * N
+    alg_f, alg_b = 3136 + 9216, 2 * (3136 + 9216)
+    ten_f = 2 * 3 * (1536 + 3072)
+    ten_b = 2 * 3 * (4608 + 1536 + 3072 + 8 * 608 + 1648)
+    rows = []
+    for name, sec, alg, ten in (("measure_update_CRNVP_fwd", tf, alg_f, ten_f), ("measure_update_CRNVP_bwd", tb, alg_b, ten_b)):
+        rows.append({"kernel": name, "sec": round(sec, 7), "bound": "tensor", "achieved": round(ten * P / sec / 1e12, 3),
+                     "peak": peaks["tf32_tensor_tflops"], "unit": "TFLOP/s (executed 3xTF32 tensor FLOP; peak = measured bf16 / 2)",
+                     "frac": round(ten * P / sec / 1e12 / peaks["tf32_tensor_tflops"], 4),
+                     "frac_fp32_algorithmic": round(alg * P / sec / 1e12 / peaks["fp32_tflops"], 4), "launches_per_step": 50})
+    return rows
+
+
 def extra_configs(a, dev, world, timed, peaks=None):
     """Runs on EVERY rank (collectives inside); the returned dict is printed by rank 0."""
     from normalizing_flows_dpfs_b200.distributed import GradBucket
@@ -78,11 +115,14 @@ def extra_configs(a, dev, world, timed, peaks=None):
     try:
         cfgs["c3"] = _time_config("DPF-CM: --NF-dyn --NF-cond --measurement CRNVP, soft resampling", nf + ["--measurement", "CRNVP", "--resampler_type", "soft"],
                                   1024, 1024, 50, dev, world, timed, 2, GradBucket, cnf=True, force=True)
+        if (torch.distributed.get_rank() if world > 1 else 0) == 0:
+            cfgs["c3"]["roofline_kernels"] = crnvp_roofline(dev)
     except Exception as e:   # never lose the headline line
         cfgs["c3"] = {"error": repr(e)}
     try:
         cfgs["c4"] = _time_config("NF-DPF with OT (Sinkhorn) resampling", nf + ["--measurement", "gaussian", "--resampler_type", "ot"],
                                   256, 4096, 5, dev, world, timed, 2, GradBucket, force=True)
+        cfgs["c4"]["roofline"] = "ot_resample[1] of this line (B = 256, N = 4096): SFU-bound, frac_sfu_executed"
     except Exception as e:
         cfgs["c4"] = {"error": repr(e)}
     try:
