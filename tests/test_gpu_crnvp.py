@@ -87,3 +87,30 @@ def test_crnvp_many_trajectory_randomized_parity():
             worst[name] = max(worst.get(name, 0.0), err)
             grad_close(a.grad, b.grad, "%s (iteration %d, B=%d, N=%d)" % (name, it, B, N))
     print("worst relative-to-max gradient errors over %d launches: %s" % (iters, worst))
+
+
+@pytest.mark.parametrize("n_flows,B,N", [(1, 5, 129), (1, 300, 64), (3, 4, 200)])
+def test_crnvp_other_flow_counts(n_flows, B, N):
+    """One flow runs the warp-specialised backward with two stages; three flows fall back to the single-role kernel.  Outputs and all
+    gradients against the oracle."""
+    g = torch.Generator().manual_seed(4100 + 7 * n_flows + N)
+    pe = torch.cat([torch.randn(n, generator=g) * s for n, s in ((32, 0.3), (16, 0.1), (512, 0.3), (32, 0.1), (1024, 0.2), (32, 0.1))])
+    cnf = O.init_stack(g, 32, 32, std=0.1, n_flows=n_flows, bias_std=0.05)
+    enc = torch.randn(B, 32, generator=g)
+    x = _off_the_relu_kinks(torch.randn(B, N, 2, generator=g) * 3, pe)
+    x = _off_the_argmax_ties(x, lambda xx: O.measurement_cnf(enc, xx, _pe_tuple(pe), O.unpack_stack(cnf, 32, 32, n_flows), 2.5))
+    lw0 = torch.log_softmax(torch.randn(B, N, generator=g), -1)
+    prior, prop = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g)
+    g1, g2, g3 = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g), torch.randn(B, generator=g)
+    lo = [t.clone().requires_grad_() for t in (pe, cnf, enc, x, lw0, prior, prop)]
+    lki_o = O.measurement_cnf(lo[2], lo[3], _pe_tuple(lo[0]), O.unpack_stack(lo[1], 32, 32, n_flows), 2.5)
+    lw_o = lo[4] + lki_o + lo[5] - lo[6]
+    pr_o = O.normalize_log_probs(lw_o) + 1e-12
+    ((lki_o * g1).sum() + (pr_o * g2).sum() * 50 + (lw_o.sum(-1) * g3).sum() * 0.01).backward()
+    gt = [cu(t).requires_grad_() for t in (pe, cnf, enc, x, lw0, prior, prop)]
+    lki, logw, probs, rs, ess = ops.measure_update(*gt, "CRNVP", n_flows=n_flows, p0=0.0, p1=2.5)
+    close(lki, lki_o, atol=1e-4, what="lki")
+    close(probs, pr_o, atol=1e-8, what="probs")
+    ((lki * cu(g1)).sum() + (probs * cu(g2)).sum() * 50 + (rs * cu(g3)).sum() * 0.01).backward()
+    for name, a, b in zip(("d_pe", "d_cnf", "d_enc", "d_x"), gt[:4], lo[:4]):
+        grad_close(a.grad, b.grad, "%s (n_flows=%d)" % (name, n_flows))
