@@ -135,6 +135,10 @@ int nfdpf_measure_bwd(int mode, const float* pe_packed, const float* cnf_packed,
  * out[b, out_off + k] = mean_n x[b,n,k], out[b, out_off + d + k] = unbiased std_n x[b,n,k]; out has row stride
  * out_stride floats (so the moments can be written straight into a wider (B,C_row) context buffer). */
 int nfdpf_row_moments(const float* x, int B, int N, int d, float* out, int out_stride, int out_off, void* stream);
+/* The same with the context row's leading columns filled in the same launch: out[b, :head_dim] = head[b, :head_dim] (the detached
+ * observation encoding of the proposal's context, model/models.py:360-361), moments at out_off = head_dim. */
+int nfdpf_row_moments_head(const float* x, int B, int N, int d, const float* head, int head_dim, float* out, int out_stride,
+                           void* stream);
 
 /* ---- (K4) entropy-regularised OT resampling: resamplers/resamplers.py:62-277 ---------------------------
  * particles (B,N,2), logw (B,N) = log of the (normalised) weights.  Log-domain Sinkhorn with epsilon-scaling

@@ -269,8 +269,8 @@ class DPF(nn.Module):
                 mo = {"lki": buf["lki"][step], "probs": buf["probs"][step], "pred": buf["pred"][step]}
                 if self.NFcond:
                     ctx_prop = torch.empty(B, self.hidden_size + 4, **f32)
-                    ctx_prop[:, :self.hidden_size] = encodings.detach()      # proposal sees a detached encoding, models.py:360-361
-                    ops.row_moments(particles_dynamical, ctx_prop, self.hidden_size)
+                    # proposal sees a detached encoding, models.py:360-361: copied into the context row by the moments launch
+                    ops.row_moments(particles_dynamical, ctx_prop, self.hidden_size, head=encodings.detach())
                     propose_particle, jac_prop = self.cond_model.run_stack(particles_dynamical, row_ctx=ctx_prop, inverse=True, neg_logdet=True,
                                                                            out={"y": buf["particles"][step]})
                     # the proposal has three consumers (dynamics flow, measurement + prediction, next step): one alias each, their

@@ -24,6 +24,7 @@ SIGNATURES = {
     "nfdpf_weight_update_bwd": (_I, [_P, _P, _P, _P, _F, _I, _I, _P, _P, _P, _P, _P]),
     "nfdpf_sum4": (_I, [_P, _P, _P, _P, _I64, _P, _P]),
     "nfdpf_row_moments": (_I, [_P, _I, _I, _I, _P, _I, _I, _P]),
+    "nfdpf_row_moments_head": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P]),
     "nfdpf_ot_workspace": (_I64, [_I, _I]),
     "nfdpf_ot_resample_fwd": (_I, [_P, _P, _F, _F, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "nfdpf_ot_resample_bwd": (_I, [_P, _P, _F, _I, _I, _I, _P, _P, _P]),

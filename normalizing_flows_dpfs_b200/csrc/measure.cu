@@ -642,6 +642,48 @@ __device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_ti
 __device__ __forceinline__ void pe_weight_grads_b(const float* __restrict__ s_tile, uint32_t tacc) {
     pe_weight_grads_b(s_tile, tacc, threadIdx.x >> 5);
 }
+// The same two phases for the warp-specialised kernels' gradient warps: both 16-row delta tiles of a phase in ONE pass over the
+// particles, so the activation fragments are loaded and split once (bit-identical sums; a third fewer instructions per batch).
+__device__ __forceinline__ void pe_weight_grads_a_x2(const float* __restrict__ s_tile, uint32_t tacc, int warp) {
+    const int lane = threadIdx.x & 31, g = lane >> 2;
+    const int k0 = 32 * warp;
+    float c0[5][4] = {}, c1[5][4] = {}, r[20];
+    const int rowB[5] = {PR::A2 + g, PR::A2 + 8 + g, PR::A2 + 16 + g, PR::A2 + 24 + g, g == 0 ? PR::ONE : PR::ZERO};
+    mma_outer2<5, 1u << 4>(s_tile, PR::D3, PR::D3 + 16, rowB, k0, k0 + 32, c0, c1);
+    umma::ld_frag<20>(tacc + TA_A, r);
+#pragma unroll
+    for (int i = 0; i < 20; ++i) r[i] += c0[i >> 2][i & 3];
+    umma::st_frag<20>(tacc + TA_A, r);
+    umma::ld_frag<20>(tacc + TA_A + 20, r);
+#pragma unroll
+    for (int i = 0; i < 20; ++i) r[i] += c1[i >> 2][i & 3];
+    umma::st_frag<20>(tacc + TA_A + 20, r);
+}
+__device__ __forceinline__ void pe_weight_grads_b_x2(const float* __restrict__ s_tile, uint32_t tacc, int warp) {
+    const int lane = threadIdx.x & 31, g = lane >> 2;
+    const int k0 = 32 * warp;
+    {
+        float c0[3][4] = {}, c1[3][4] = {}, r[12];
+        const int rowB[3] = {PR::A1 + g, PR::A1 + 8 + g, g == 0 ? PR::ONE : PR::ZERO};
+        mma_outer2<3, 1u << 2>(s_tile, PR::D2, PR::D2 + 16, rowB, k0, k0 + 32, c0, c1);
+        umma::ld_frag<12>(tacc + TA_B, r);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r[i] += c0[i >> 2][i & 3];
+        umma::st_frag<12>(tacc + TA_B, r);
+        umma::ld_frag<12>(tacc + TA_B + 12, r);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r[i] += c1[i >> 2][i & 3];
+        umma::st_frag<12>(tacc + TA_B + 12, r);
+    }
+    float c1[1][4] = {}, r1[4];
+    const int rowX[1] = {g < 2 ? PR::X + g : (g == 2 ? PR::ONE : PR::ZERO)};
+    mma_outer<1>(s_tile, PR::D1, rowX, k0, k0 + 32, c1);
+    umma::ld_frag<4>(tacc + TA_D1, r1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r1[i] += c1[0][i];
+    umma::st_frag<4>(tacc + TA_D1, r1);
+    umma::wait_st();     // the next batch (or the read-out) loads these columns again
+}
 // Read this warp's accumulated fragments back and scatter them into its accumulator copy accpe[AC::SIZE] (every entry is
 // owned by exactly one lane; bias columns by the t == 0 / t == 1 lanes).
 __device__ __forceinline__ void pe_weight_grads_readout(uint32_t tacc, float* __restrict__ accpe) {
@@ -1079,10 +1121,10 @@ measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const fl
             // ---------------------------------------------------------------- gradient warps
             for (int n0 = 0; n0 < N; n0 += 128) {
                 umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
-                pe_weight_grads_a(s_tile, tacc, pw);
+                pe_weight_grads_a_x2(s_tile, tacc, pw);
                 mbar_arrive(&s_empty[pw]);
                 umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
-                pe_weight_grads_b(s_tile, tacc, pw);
+                pe_weight_grads_b_x2(s_tile, tacc, pw);
                 mbar_arrive(&s_empty[pw]);
             }
             umma::wait_st();
@@ -1439,11 +1481,11 @@ measure_bwd_cnf_ws_kernel(const float* __restrict__ pe, const float* __restrict_
                     mbar_arrive(&s_empty[pw]);
                 }
                 umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
-                pe_weight_grads_a(s_tile, tacc, pw);
+                pe_weight_grads_a_x2(s_tile, tacc, pw);
                 umma::wait_st();
                 mbar_arrive(&s_empty[pw]);
                 umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
-                pe_weight_grads_b(s_tile, tacc, pw);
+                pe_weight_grads_b_x2(s_tile, tacc, pw);
                 mbar_arrive(&s_empty[pw]);
             }
         }

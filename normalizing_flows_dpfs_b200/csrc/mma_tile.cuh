@@ -64,4 +64,43 @@ __device__ __forceinline__ void mma_outer(const float* __restrict__ tile, int ro
     }
 }
 
+// Two A tiles (rowA0, rowA1) against the SAME B tiles: the B fragments are loaded and split once for both (the weight-gradient
+// phases of the particle encoder contract two 16-row delta tiles with the same activation rows).  Every accumulator sees exactly the
+// MMA sequence mma_outer gives it, so the results are bit-identical; twice as many independent accumulators sit between two
+// dependent MMAs.
+template <int NT, unsigned EXACT_B = 0u>
+__device__ __forceinline__ void mma_outer2(const float* __restrict__ tile, int rowA0, int rowA1, const int (&rowB)[NT], int k_begin,
+                                           int k_end, float (&c0)[NT][4], float (&c1)[NT][4]) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const float* a0_lo = tile + (rowA0 + g) * TSM + t;
+    const float* a0_hi = tile + (rowA0 + g + 8) * TSM + t;
+    const float* a1_lo = tile + (rowA1 + g) * TSM + t;
+    const float* a1_hi = tile + (rowA1 + g + 8) * TSM + t;
+#pragma unroll
+    for (int k0 = k_begin; k0 < k_end; k0 += 8) {
+        uint32_t ah0[4], al0[4], ah1[4], al1[4], bh[NT][2], bl[NT][2];
+        split_tf32(a0_lo[k0], ah0[0], al0[0]);
+        split_tf32(a0_hi[k0], ah0[1], al0[1]);
+        split_tf32(a0_lo[k0 + 4], ah0[2], al0[2]);
+        split_tf32(a0_hi[k0 + 4], ah0[3], al0[3]);
+        split_tf32(a1_lo[k0], ah1[0], al1[0]);
+        split_tf32(a1_hi[k0], ah1[1], al1[1]);
+        split_tf32(a1_lo[k0 + 4], ah1[2], al1[2]);
+        split_tf32(a1_hi[k0 + 4], ah1[3], al1[3]);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            const float* b = tile + rowB[n] * TSM + k0 + t;
+            split_tf32(b[0], bh[n][0], bl[n][0]);
+            split_tf32(b[4], bh[n][1], bl[n][1]);
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { mma_tf32(c0[n], al0, bh[n]); mma_tf32(c1[n], al1, bh[n]); }
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+            if (!((EXACT_B >> n) & 1u)) { mma_tf32(c0[n], ah0, bl[n]); mma_tf32(c1[n], ah1, bl[n]); }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) { mma_tf32(c0[n], ah0, bh[n]); mma_tf32(c1[n], ah1, bh[n]); }
+    }
+}
+
 }  // namespace nfdpf

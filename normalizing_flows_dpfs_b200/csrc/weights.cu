@@ -130,9 +130,10 @@ extern "C" int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw
 // out[b, off + k] = mean_n x[b,n,k];  out[b, off + d + k] = std_n x[b,n,k] (unbiased, N-1), k < d.  One warp per row pair.
 namespace nfdpf {
 __global__ void row_moments_kernel(const float* __restrict__ x, int B, int N, int d, float* __restrict__ out, int out_stride,
-                                   int out_off) {
+                                   int out_off, const float* __restrict__ head) {
     __shared__ float s_red[33];
     const int b = blockIdx.x;
+    if (head) for (int k = threadIdx.x; k < out_off; k += blockDim.x) out[(size_t)b * out_stride + k] = head[(size_t)b * out_off + k];
     const float* xr = x + (size_t)b * N * d;
     for (int k = 0; k < d; ++k) {
         float s = 0.f;
@@ -150,9 +151,12 @@ __global__ void row_moments_kernel(const float* __restrict__ x, int B, int N, in
 // d == 2, N <= 8 * 256: the row is read ONCE (float2 per particle, up to eight per thread, kept in registers); both means come out of
 // one pair of block reductions, both variances out of a second one -- two round trips instead of the generic kernel's four passes.
 __global__ void __launch_bounds__(256) row_moments2_kernel(const float* __restrict__ x, int N, float* __restrict__ out, int out_stride,
-                                                           int out_off) {
+                                                           int out_off, const float* __restrict__ head) {
     __shared__ float s_red[33];
     const int b = blockIdx.x, tid = threadIdx.x;
+    // the leading out_off columns of the context row that are not moments (the observation encoding of the proposal's context,
+    // model/models.py:360-361) ride along instead of an ATen slice copy per timestep
+    if (head && tid < out_off) out[(size_t)b * out_stride + tid] = head[(size_t)b * out_off + tid];
     const float2* xr = reinterpret_cast<const float2*>(x) + (size_t)b * N;
     float2 v[8];
     float sx = 0.f, sy = 0.f;
@@ -180,7 +184,16 @@ __global__ void __launch_bounds__(256) row_moments2_kernel(const float* __restri
 extern "C" int nfdpf_row_moments(const float* x, int B, int N, int d, float* out, int out_stride, int out_off, void* stream) {
     NFDPF_REQUIRE(x && out, "row_moments: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0 && d > 0 && out_stride >= out_off + 2 * d && out_off >= 0, "row_moments: bad sizes");
-    if (d == 2 && N <= 8 * 256) nfdpf::row_moments2_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, N, out, out_stride, out_off);
-    else nfdpf::row_moments_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, B, N, d, out, out_stride, out_off);
+    if (d == 2 && N <= 8 * 256) nfdpf::row_moments2_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, N, out, out_stride, out_off, nullptr);
+    else nfdpf::row_moments_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, B, N, d, out, out_stride, out_off, nullptr);
     return nfdpf::check_launch("row_moments");
+}
+
+extern "C" int nfdpf_row_moments_head(const float* x, int B, int N, int d, const float* head, int head_dim, float* out, int out_stride,
+                                      void* stream) {
+    NFDPF_REQUIRE(x && out && head, "row_moments_head: null pointer");
+    NFDPF_REQUIRE(B > 0 && N > 0 && d > 0 && head_dim > 0 && head_dim <= 256 && out_stride >= head_dim + 2 * d, "row_moments_head: bad sizes");
+    if (d == 2 && N <= 8 * 256) nfdpf::row_moments2_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, N, out, out_stride, head_dim, head);
+    else nfdpf::row_moments_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, B, N, d, out, out_stride, head_dim, head);
+    return nfdpf::check_launch("row_moments_head");
 }

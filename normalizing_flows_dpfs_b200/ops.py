@@ -5,6 +5,17 @@ import torch
 from . import _lib as L
 
 
+def _slab_row(packed):
+    """(GradSlab, row) when `packed` comes from a module's pack cache (nf/flows.py): the backward then writes its parameter gradient
+    into that row and returns None for the vector -- the rows are summed once, in the pack's own backward."""
+    if packed is None:
+        return None
+    slab = getattr(packed, "_nfdpf_slab", None)
+    if slab is None or not packed.requires_grad:
+        return None
+    return slab, slab.take()
+
+
 def _out(out, key, like=None, shape=None, dtype=torch.float32, device=None):
     """Output tensor of a kernel: the caller's pre-allocated slice `out[key]` (the per-step (T,B,...) list buffers of the filter
     loop: no torch.stack afterwards) or a fresh allocation.  `out` is a plain dict, invisible to autograd; the kernels write
@@ -119,6 +130,7 @@ class CouplingStack(torch.autograd.Function):
         ctx.save_for_backward(pk, y, rc, pc)
         ctx.set_materialize_grads(False)
         ctx.meta = (n_flows, D, C_row, C_part, flags, B, N)
+        ctx.slab = _slab_row(packed)
         return y, ld
 
     @staticmethod
@@ -132,12 +144,12 @@ class CouplingStack(torch.autograd.Function):
         need_pc = pc is not None and ctx.needs_input_grad[3]
         d_rc = torch.empty_like(rc) if need_rc else None
         d_pc = torch.empty_like(pc) if need_pc else None
-        d_pk = torch.empty_like(pk)        # every entry is written by the reduce kernel
+        d_pk = ctx.slab[0].row(ctx.slab[1]) if ctx.slab else torch.empty_like(pk)        # every entry is written by the reduce kernel
         ws_bytes = L.load().nfdpf_coupling_bwd_workspace(n_flows, D, C_row, C_part, B, N)
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=y.device)
         L.call("nfdpf_coupling_bwd", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(y), L.ptr(rc), L.ptr(pc), inverse, B, N,
                L.ptr(g_y), L.ptr(g_ld), L.ptr(d_x), L.ptr(d_rc), L.ptr(d_pc), L.ptr(d_pk), L.ptr(ws), L.stream())
-        return d_pk, d_x, d_rc, d_pc, None, None, None, None
+        return (None if ctx.slab else d_pk), d_x, d_rc, d_pc, None, None, None, None
 
 
 def soft_resample(particles, probs, offsets, markers, alpha, want_log=False, gate=None, out=None):
@@ -198,6 +210,7 @@ class MeasureUpdate(torch.autograd.Function):
         ctx.save_for_backward(pe_, cnf_, enc_, x_, argmax, probs, z)
         ctx.set_materialize_grads(False)
         ctx.meta = (mode, n_flows, float(p0), float(p1), float(add_eps), B, N, hidden, fused, prior is not None, propose is not None)
+        ctx.slabs = (_slab_row(pe), _slab_row(cnf))
         if not fused:
             return lki, None, None, None, None, None
         row_sum, ess_inv = stats[:, 0], stats[:, 1]
@@ -224,13 +237,14 @@ class MeasureUpdate(torch.autograd.Function):
             g_total = torch.zeros(B, N, dtype=torch.float32, device=dev)
         d_x = torch.empty_like(x_)
         d_enc = torch.empty_like(enc_) if ctx.needs_input_grad[2] else None
-        d_pe = torch.empty_like(pe_)       # every entry is written by the reduce kernels
-        d_cnf = torch.empty_like(cnf_) if cnf_ is not None else None
+        s_pe, s_cnf = ctx.slabs
+        d_pe = s_pe[0].row(s_pe[1]) if s_pe else torch.empty_like(pe_)       # every entry is written by the reduce kernels
+        d_cnf = (s_cnf[0].row(s_cnf[1]) if s_cnf else torch.empty_like(cnf_)) if cnf_ is not None else None
         ws = torch.empty(L.load().nfdpf_measure_bwd_workspace(mode, n_flows, B, N) // 4, dtype=torch.float32, device=dev)
         L.call("nfdpf_measure_bwd", mode, L.ptr(pe_), L.ptr(cnf_), n_flows, p0, p1, L.ptr(enc_), L.ptr(x_), B, N, hidden,
                L.ptr(g_total.contiguous()), L.ptr(argmax), L.ptr(d_x), L.ptr(d_enc), L.ptr(d_pe), L.ptr(d_cnf), L.ptr(ws), L.ptr(z),
                L.ptr(g_pred), L.ptr(probs) if g_pred is not None else None, L.stream())
-        return (d_pe, d_cnf, d_enc, d_x, d_logw if fused else None, d_logw if has_prior else None,
+        return (None if s_pe else d_pe, None if s_cnf else d_cnf, d_enc, d_x, d_logw if fused else None, d_logw if has_prior else None,
                 d_neg if has_prop else None, None, None, None, None, None, None, None)
 
 
@@ -247,13 +261,19 @@ def measure_update(pe, cnf, enc, particles, logw_prev, prior, propose, mode, n_f
     return res if want_pred else res[:5]
 
 
-def row_moments(x, out=None, out_off=0):
-    """[mean | unbiased std] over the particle axis, (B,N,d) -> (B,2d), no autograd (the reference detaches it)."""
+def row_moments(x, out=None, out_off=0, head=None):
+    """[mean | unbiased std] over the particle axis, (B,N,d) -> (B,2d), no autograd (the reference detaches it).  head (B, out_off):
+    written into the leading columns of `out` by the same launch (the proposal context's observation encoding)."""
     B, N, d = x.shape
     xx = L.f32(x)
     if out is None:
-        out = torch.empty(B, 2 * d, dtype=torch.float32, device=xx.device)
-    L.call("nfdpf_row_moments", L.ptr(xx), B, N, d, L.ptr(out), out.shape[1], out_off, L.stream())
+        out = torch.empty(B, out_off + 2 * d, dtype=torch.float32, device=xx.device)
+    if head is not None:
+        hh = L.f32(head)
+        assert hh.shape == (B, out_off), "head must be (B, out_off)"
+        L.call("nfdpf_row_moments_head", L.ptr(xx), B, N, d, L.ptr(hh), out_off, L.ptr(out), out.shape[1], L.stream())
+    else:
+        L.call("nfdpf_row_moments", L.ptr(xx), B, N, d, L.ptr(out), out.shape[1], out_off, L.stream())
     return out
 
 

@@ -261,3 +261,52 @@ def test_row_moments_vs_torch(B, N):
     close(out[:, 3:5], x.double().mean(1), rtol=1e-5, atol=1e-5, what="row mean")
     close(out[:, 5:7], x.double().std(1), rtol=1e-5, atol=1e-5, what="row std")
     assert bool((out[:, :3] == -7.0).all()) and bool((out[:, 7:] == -7.0).all())
+
+
+@pytest.mark.parametrize("B,N", [(7, 100), (64, 1024), (3, 4096)])
+def test_row_moments_writes_the_context_head(B, N):
+    """The proposal's context row [observation encoding | mean | std] (model/models.py:360-361) from ONE launch."""
+    g = torch.Generator().manual_seed(N + 1)
+    x = torch.randn(B, N, 2, generator=g) * 30 + 5
+    head = torch.randn(B, 32, generator=g)
+    out = torch.full((B, 36), -7.0, device="cuda")
+    ops.row_moments(cu(x), out, 32, head=cu(head))
+    assert torch.equal(out[:, :32].cpu(), head), "encoding columns must be copied bit for bit"
+    close(out[:, 32:34], x.double().mean(1), rtol=1e-5, atol=1e-5, what="row mean")
+    close(out[:, 34:36], x.double().std(1), rtol=1e-5, atol=1e-5, what="row std")
+
+
+def test_grad_slab_equals_autograd_accumulation():
+    """Parameter gradients of a module's packed vector: kernel calls write rows of the pack's GradSlab and the pack's backward sums
+    them once (nf/flows.py) -- same gradients as autograd's pairwise accumulation over plain leaf copies, also when one call's output
+    never reaches the loss (its row is never written) and when backward runs twice over a retained graph."""
+    from normalizing_flows_dpfs_b200.nf.flows import RealNVP_cond
+    from normalizing_flows_dpfs_b200.nf.models import NormalizingFlowModel_cond
+    torch.manual_seed(3)
+    g = torch.Generator().manual_seed(11)
+    flows = [RealNVP_cond(dim=2, obser_dim=4) for _ in range(2)]
+    for f in flows:
+        f.zero_initialization(var=0.3)
+    model = NormalizingFlowModel_cond(None, flows, device="cuda").cuda()
+    B, N = 6, 300
+    xs = [cu(torch.randn(B, N, 2, generator=g)) for _ in range(3)]
+    ctx = cu(torch.randn(B, 4, generator=g))
+    gy = cu(torch.randn(B, N, 2, generator=g))
+
+    def run(packed_of):
+        outs = [ops.coupling_stack(packed_of(), x, ctx, None, 2, inverse=bool(i & 1)) for i, x in enumerate(xs)]
+        return (outs[0][0] * gy).sum() + (outs[2][1]).sum() * 0.1        # the second call's outputs are unused
+    packed = model.packed()
+    assert getattr(packed, "_nfdpf_slab", None) is not None
+    loss = run(model.packed)
+    loss.backward(retain_graph=True)
+    first = [p.grad.clone() for p in model.parameters()]
+    for p in model.parameters():
+        p.grad = None
+    loss.backward()
+    again = [p.grad.clone() for p in model.parameters()]
+    leaf = packed.detach().clone().requires_grad_()
+    run(lambda: leaf).backward()
+    flat = torch.cat([t.reshape(-1) for t in first])
+    assert torch.equal(flat, torch.cat([t.reshape(-1) for t in again])), "a second backward over the retained graph must reproduce the first"
+    close(flat, leaf.grad.cpu().double(), rtol=1e-6, atol=1e-7 * float(leaf.grad.abs().max()), what="slab sum vs autograd accumulation")
