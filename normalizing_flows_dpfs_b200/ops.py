@@ -555,6 +555,10 @@ class ListView(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        # the step kernels want contiguous gradients: transpose the (B,T,...) gradient ONCE instead of one strided-slice copy per step
+        if ctx.n > 1 and not g[:, 0].is_contiguous():
+            gt = g.transpose(0, 1).contiguous()
+            return (None,) + tuple(gt[t] for t in range(ctx.n))
         return (None,) + tuple(g[:, t] for t in range(ctx.n))
 
 
