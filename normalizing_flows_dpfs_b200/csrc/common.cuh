@@ -77,6 +77,18 @@ __device__ __forceinline__ T block_allreduce(T v, T* scratch, Op op, T identity)
     __syncthreads();
     return scratch[32];
 }
+// Two sums at once over a 256-thread block (eight warps), fixed order, ONE barrier; s = 16 floats that no other phase of the kernel
+// reuses (so no trailing barrier).  The glue kernels that run one CTA per trajectory spend their time in barrier chains, not in
+// memory traffic: block_allreduce costs three barriers and a serial second stage per scalar.
+__device__ __forceinline__ void block_sum2_256(float& a, float& b, float* __restrict__ s) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s[warp] = a; s[8 + warp] = b; }
+    __syncthreads();
+    a = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    b = ((s[8] + s[9]) + (s[10] + s[11])) + ((s[12] + s[13]) + (s[14] + s[15]));
+}
 struct OpSum {
     template <typename T>
     __device__ __forceinline__ T operator()(T a, T b) const { return a + b; }

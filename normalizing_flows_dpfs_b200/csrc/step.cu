@@ -95,6 +95,51 @@ motion_moments_rng_kernel(const float* __restrict__ x, const float* __restrict__
     }
 }
 
+// N <= 256 NI: the row stays in registers -- every load is issued before the first Philox round (the generic kernel walks the row
+// with one DRAM round trip per iteration), the moved particles are not read back for the variances, two barriers instead of twelve.
+template <int NI>
+__global__ void __launch_bounds__(256)
+motion_moments_rng_reg_kernel(const float* __restrict__ x, const float* __restrict__ vel, const long long* __restrict__ rng_state,
+                              float sigma, int N, float* __restrict__ out, float* __restrict__ noise_out, float* __restrict__ ctx,
+                              int ctx_stride, int ctx_off) {
+    __shared__ float s_a[16], s_b[16];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float2 v = reinterpret_cast<const float2*>(vel)[b];
+    const float2* xr = reinterpret_cast<const float2*>(x) + (size_t)b * N;
+    float2* nr = reinterpret_cast<float2*>(noise_out) + (size_t)b * N;
+    float2* orow = reinterpret_cast<float2*>(out) + (size_t)b * N;
+    float2 p[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) { const int n = tid + 256 * i; p[i] = n < N ? xr[n] : make_float2(0.f, 0.f); }
+    float sx = 0.f, sy = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int n = tid + 256 * i;
+        if (n < N) {
+            const uint4 r = philox_at(rng_state, (unsigned long long)b * N + n, 0x6d0710u);
+            float2 e = normal2(r.x, r.y);
+            e.x *= sigma; e.y *= sigma;
+            const float2 o = make_float2((p[i].x + v.x) + e.x, (p[i].y + v.y) + e.y);   // (particles + vel) + noise, models.py:196-202
+            nr[n] = e;
+            orow[n] = o;
+            p[i] = o;
+            sx += o.x; sy += o.y;
+        }
+    }
+    if (!ctx) return;
+    block_sum2_256(sx, sy, s_a);
+    const float mx = sx / (float)N, my = sy / (float)N;
+    float vx = 0.f, vy = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+        if (tid + 256 * i < N) { vx = fmaf(p[i].x - mx, p[i].x - mx, vx); vy = fmaf(p[i].y - my, p[i].y - my, vy); }
+    block_sum2_256(vx, vy, s_b);
+    if (tid == 0) {
+        float* c = ctx + (size_t)b * ctx_stride + ctx_off;
+        c[0] = mx; c[1] = my; c[2] = sqrtf(vx / (float)(N - 1)); c[3] = sqrtf(vy / (float)(N - 1));
+    }
+}
+
 // utils.py:46-62: uniform box [-width/2, width/2)^2, or start_state + N(0, 1) when init_with_true_state
 __global__ void init_particles_rng_kernel(const float* __restrict__ start, int start_stride, const long long* __restrict__ rng_state,
                                           float width, int true_state, size_t P, int N, float* __restrict__ out) {
@@ -191,8 +236,12 @@ extern "C" int nfdpf_motion_moments_rng(const float* particles, const float* vel
     NFDPF_REQUIRE(B > 0 && N > 0 && sigma >= 0.f, "motion_moments_rng: B and N must be positive");
     NFDPF_REQUIRE(!ctx || (ctx_off >= 0 && ctx_stride >= ctx_off + 4), "motion_moments_rng: context row too short");
     if (d != 2) { set_error("motion_moments_rng: built for state_dim 2, got %d", d); return NFDPF_ERR_UNSUPPORTED; }
-    motion_moments_rng_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(particles, vel, (const long long*)rng_state, sigma, N, out, noise_out, ctx,
-                                                                  ctx_stride, ctx_off);
+    if (N <= 1024)
+        motion_moments_rng_reg_kernel<4><<<B, 256, 0, (cudaStream_t)stream>>>(particles, vel, (const long long*)rng_state, sigma, N, out, noise_out,
+                                                                             ctx, ctx_stride, ctx_off);
+    else
+        motion_moments_rng_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(particles, vel, (const long long*)rng_state, sigma, N, out, noise_out, ctx,
+                                                                      ctx_stride, ctx_off);
     return check_launch("motion_moments_rng");
 }
 

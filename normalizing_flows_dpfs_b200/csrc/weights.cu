@@ -88,6 +88,60 @@ __global__ void weight_update_bwd_kernel(const float* __restrict__ g_probs, cons
     }
 }
 
+// N <= 1024, N % 4 == 0: one warp per row with the row in registers (a lane owns four consecutive entries of each 128-entry chunk):
+// every load is a 128-bit one issued before the first use, probs / g_probs / particles are read ONCE (the kernel above walks the row
+// twice with scalar loads, one dependent round trip per iteration).
+__global__ void __launch_bounds__(256)
+weight_update_bwd_reg_kernel(const float* __restrict__ g_probs, const float* __restrict__ g_logw, const float* __restrict__ g_rowsum,
+                             const float* __restrict__ probs, float add_eps, int B, int N, float* __restrict__ d_logw,
+                             float* __restrict__ d_neg, const float* __restrict__ particles, const float* __restrict__ g_pred) {
+    const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= B) return;
+    const size_t base = (size_t)row * N;
+    float gx = 0.f, gy = 0.f;
+    if (g_pred) { gx = g_pred[2 * row]; gy = g_pred[2 * row + 1]; }
+    float pm[8][4], g[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = 128 * i + 4 * lane;
+        float4 p4 = make_float4(add_eps, add_eps, add_eps, add_eps), g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < N) {
+            p4 = *reinterpret_cast<const float4*>(probs + base + n);
+            if (g_probs) g4 = *reinterpret_cast<const float4*>(g_probs + base + n);
+            if (g_pred) {   // the fused prediction (losses.py:22): d pred / d probs[n] = particles[n]
+                const float4 x0 = *reinterpret_cast<const float4*>(particles + (base + n) * 2);
+                const float4 x1 = *reinterpret_cast<const float4*>(particles + (base + n) * 2 + 4);
+                g4.x = fmaf(gx, x0.x, fmaf(gy, x0.y, g4.x)); g4.y = fmaf(gx, x0.z, fmaf(gy, x0.w, g4.y));
+                g4.z = fmaf(gx, x1.x, fmaf(gy, x1.y, g4.z)); g4.w = fmaf(gx, x1.z, fmaf(gy, x1.w, g4.w));
+            }
+        }
+        pm[i][0] = p4.x - add_eps; pm[i][1] = p4.y - add_eps; pm[i][2] = p4.z - add_eps; pm[i][3] = p4.w - add_eps;
+        g[i][0] = g4.x; g[i][1] = g4.y; g[i][2] = g4.z; g[i][3] = g4.w;
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dot = fmaf(g[i][u], pm[i][u], dot);
+    dot = warp_sum(dot);
+    const float gr = g_rowsum ? g_rowsum[row] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = 128 * i + 4 * lane;
+        if (n < N) {
+            float4 v = make_float4(gr, gr, gr, gr);
+            if (g_logw) {
+                const float4 l = *reinterpret_cast<const float4*>(g_logw + base + n);
+                v.x += l.x; v.y += l.y; v.z += l.z; v.w += l.w;
+            }
+            v.x += pm[i][0] * (g[i][0] - dot); v.y += pm[i][1] * (g[i][1] - dot);
+            v.z += pm[i][2] * (g[i][2] - dot); v.w += pm[i][3] * (g[i][3] - dot);
+            *reinterpret_cast<float4*>(d_logw + base + n) = v;
+            if (d_neg) *reinterpret_cast<float4*>(d_neg + base + n) = make_float4(-v.x, -v.y, -v.z, -v.w);   // DPFs.py:187: minus sign
+        }
+    }
+}
+
 }  // namespace nfdpf
 
 using namespace nfdpf;
@@ -116,7 +170,9 @@ extern "C" int nfdpf_weight_update_bwd(const float* g_probs, const float* g_logw
     NFDPF_REQUIRE(!g_pred || particles, "weight_update_bwd: the fused prediction gradient needs the particles");
     NFDPF_REQUIRE(B > 0 && N > 0, "weight_update_bwd: B and N must be positive");
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 1024) {
+    if (N <= 1024 && N % 4 == 0) {
+        weight_update_bwd_reg_kernel<<<(B + 7) / 8, 256, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N, d_logw, d_neg, particles, g_pred);
+    } else if (N <= 1024) {
         const int wpb = 8;
         weight_update_bwd_kernel<false><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(g_probs, g_logw, g_rowsum, probs, add_eps, B, N,
                                                                                   d_logw, d_neg, particles, g_pred);
@@ -166,13 +222,14 @@ __global__ void __launch_bounds__(256) row_moments2_kernel(const float* __restri
         v[i] = n < N ? xr[n] : make_float2(0.f, 0.f);
         sx += v[i].x; sy += v[i].y;
     }
-    const float mx = block_allreduce(sx, s_red, OpSum(), 0.f) / (float)N, my = block_allreduce(sy, s_red, OpSum(), 0.f) / (float)N;
+    __shared__ float s_a[16], s_b[16];
+    block_sum2_256(sx, sy, s_a);
+    const float mx = sx / (float)N, my = sy / (float)N;
     float vx = 0.f, vy = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
         if (tid + 256 * i < N) { const float tx = v[i].x - mx, ty = v[i].y - my; vx = fmaf(tx, tx, vx); vy = fmaf(ty, ty, vy); }
-    vx = block_allreduce(vx, s_red, OpSum(), 0.f);
-    vy = block_allreduce(vy, s_red, OpSum(), 0.f);
+    block_sum2_256(vx, vy, s_b);
     if (tid == 0) {
         float* o = out + (size_t)b * out_stride + out_off;
         o[0] = mx; o[1] = my;
