@@ -362,7 +362,7 @@ __device__ __forceinline__ float loglik_cnf_tc(PeTc& tc, const float (&e)[32], c
         fcnn_tail16(CnfL1::tail_image(s_img, 2 * st), a_t, t);
         fcnn_tail16(CnfL1::tail_image(s_img, 2 * st + 1), a_s, sc);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { up[i] = fmaf(up[i], expf(sc[i]), t[i]); ld += sc[i]; }
+        for (int i = 0; i < 16; ++i) { up[i] = fmaf(up[i], exp_acc(sc[i]), t[i]); ld += sc[i]; }
         swap_halves<16>(lo, up);
     }
     float m = 0.f;
