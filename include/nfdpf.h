@@ -96,6 +96,18 @@ int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C
                        const float* g_ld, float* d_x, float* d_row_ctx, float* d_part_ctx, float* d_packed,
                        void* workspace, void* stream);
 
+/* Deferred reduction for D = 2 stacks with row-constant context (C_part = 0; the shapes nf_dynamic_model / normalising_flow_propose
+ * run, model/models.py:305-350).  nfdpf_coupling_bwd sums its per-CTA partial parameter gradients with one small launch per call;
+ * a training step makes ~150 such calls on the same parameters.  Here a call leaves its partial rows in `block`
+ * (nfdpf_coupling_bwd_block_floats() floats; 0 = shape not offered) and ONE nfdpf_coupling_bwd_reduce sums the blocks of n_calls
+ * calls (consecutive in memory, same n_flows / C_row / B) into d_packed -- fixed order, fp64 accumulation, every entry written. */
+int64_t nfdpf_coupling_bwd_block_floats(int n_flows, int D, int C_row, int C_part, int B);
+int nfdpf_coupling_bwd_deferred(const float* packed, int n_flows, int D, int C_row, int C_part, const float* y,
+                                const float* row_ctx, int inverse, int B, int N, const float* g_y, const float* g_ld, float* d_x,
+                                float* d_row_ctx, float* block, void* workspace, void* stream);
+int nfdpf_coupling_bwd_reduce(int n_flows, int D, int C_row, int C_part, int B, const float* blocks, int n_calls,
+                              float* d_packed, void* stream);
+
 /* ---- (K2) measurement log-likelihood fused with the log-weight update and normalisation ----------------
  * mode 0: measurement_model_Gaussian, model/models.py:237-254, with MultivariateNormal(loc = p0, cov = p1^2 I)
  *         (DPFs.py:84-86 uses p0 = 1, p1 = 10);  mode 1: measurement_model_cosine_distance, models.py:206-219;

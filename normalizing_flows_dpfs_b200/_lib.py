@@ -44,6 +44,9 @@ SIGNATURES = {
     "nfdpf_measure_bwd_workspace": (_I64, [_I, _I, _I, _I]),
     "nfdpf_measure_bwd": (_I, [_I, _P, _P, _I, _F, _F, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nfdpf_coupling_bwd": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nfdpf_coupling_bwd_block_floats": (_I64, [_I, _I, _I, _I, _I]),
+    "nfdpf_coupling_bwd_deferred": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "nfdpf_coupling_bwd_reduce": (_I, [_I, _I, _I, _I, _I, _P, _I, _P, _P]),
 }
 _lib = None
 

@@ -285,6 +285,29 @@ extern "C" int64_t nfdpf_coupling_bwd_workspace(int n_flows, int D, int C_row, i
     return (int64_t)bwd_grid(B) * 4 * n_flows * packed_fcnn_size(D / 2, C_row + C_part) * (int64_t)sizeof(float);
 }
 
+// ---- deferred reduction for the D = 2 / row-context stacks (the headline shape): see include/nfdpf.h ----------------------------
+extern "C" int64_t nfdpf_coupling_bwd_block_floats(int n_flows, int D, int C_row, int C_part, int B) {
+    if (D != 2 || C_part != 0 || n_flows < 1 || 4 * n_flows > MAX_FCNN || B < 1 || C_row < 0 || C_row > 64) return 0;   // 0 = not offered
+    return (int64_t)coupling_bwd_d2_block_floats(n_flows, C_row, B);
+}
+extern "C" int nfdpf_coupling_bwd_deferred(const float* packed, int n_flows, int D, int C_row, int C_part, const float* y,
+                                           const float* row_ctx, int inverse, int B, int N, const float* g_y, const float* g_ld, float* d_x,
+                                           float* d_row_ctx, float* block, void* workspace, void* stream) {
+    NFDPF_REQUIRE(packed && y && d_x && block && workspace, "coupling_bwd_deferred: null pointer");
+    NFDPF_REQUIRE(D == 2 && C_part == 0, "coupling_bwd_deferred: D = 2 stacks with row-constant context only");
+    NFDPF_REQUIRE(B > 0 && N > 0 && n_flows >= 1 && 4 * n_flows <= MAX_FCNN && C_row >= 0 && C_row <= 64 && (C_row == 0 || row_ctx),
+                  "coupling_bwd_deferred: bad sizes");
+    return launch_coupling_bwd_d2_deferred(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, block, workspace,
+                                           (cudaStream_t)stream);
+}
+extern "C" int nfdpf_coupling_bwd_reduce(int n_flows, int D, int C_row, int C_part, int B, const float* blocks, int n_calls,
+                                         float* d_packed, void* stream) {
+    NFDPF_REQUIRE(blocks && d_packed && n_calls >= 1, "coupling_bwd_reduce: bad arguments");
+    NFDPF_REQUIRE(D == 2 && C_part == 0 && B > 0 && n_flows >= 1 && 4 * n_flows <= MAX_FCNN && C_row >= 0 && C_row <= 64,
+                  "coupling_bwd_reduce: D = 2 stacks with row-constant context only");
+    return launch_coupling_bwd_d2_reduce(n_flows, C_row, B, blocks, n_calls, d_packed, (cudaStream_t)stream);
+}
+
 extern "C" int nfdpf_coupling_bwd(const float* packed, int n_flows, int D, int C_row, int C_part, const float* y,
                                   const float* row_ctx, const float* part_ctx, int inverse, int B, int N, const float* g_y,
                                   const float* g_ld, float* d_x, float* d_row_ctx, float* d_part_ctx, float* d_packed,

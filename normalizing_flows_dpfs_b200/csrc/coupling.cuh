@@ -30,6 +30,14 @@ int launch_coupling_bwd_d2(const float* packed, int n_flows, int C_row, const fl
                            const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* d_packed, void* workspace,
                            cudaStream_t st);
 
+// deferred reduction of the D = 2 backward: a call leaves [row-context partials | folded CTA rows] in the caller's block
+// (coupling_bwd_d2_block_floats); one reduce launch sums the blocks of n_calls calls (same n_flows, C_row, B) into d_packed
+size_t coupling_bwd_d2_block_floats(int n_flows, int C_row, int B);
+int launch_coupling_bwd_d2_deferred(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, int inverse, int B,
+                                    int N, const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* block, void* workspace,
+                                    cudaStream_t st);
+int launch_coupling_bwd_d2_reduce(int n_flows, int C_row, int B, const float* blocks, int n_calls, float* d_packed, cudaStream_t st);
+
 // Aligned shared-memory image of one FCNN (row-context columns of W1 excluded; they live in s_w1r).
 template <int HALF, int CP>
 struct Lay {

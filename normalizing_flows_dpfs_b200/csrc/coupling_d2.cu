@@ -526,7 +526,7 @@ coupling_bwd_d2_kernel(const float* __restrict__ packed, int n_flows, int C_row,
 constexpr int RED_G = 32;      // row groups per block of the reduce kernel (32 columns x 32 groups = 1024 threads)
 __global__ void __launch_bounds__(32 * RED_G)
 d2_reduce_kernel(const float* __restrict__ warp_rows, int n_rows, const float* __restrict__ ctx_rows, int n_cta,
-                                 int n_fcnn, int C_row, float* __restrict__ d_packed) {
+                                 int n_fcnn, int C_row, float* __restrict__ d_packed, int n_calls, size_t call_stride) {
     __shared__ double s_sum[RED_G][32];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int fin = 1 + C_row, pf = packed_fcnn_size(1, C_row), C1 = C_row + 1;
@@ -536,8 +536,16 @@ d2_reduce_kernel(const float* __restrict__ warp_rows, int n_rows, const float* _
     const bool is_acc = col < n_acc, is_ctx = !is_acc && col < n_acc + n_ctx;
     const float* src = is_acc ? warp_rows + col : ctx_rows + (col - n_acc);
     const int stride = is_acc ? n_acc : n_ctx, count = is_acc ? n_rows : (is_ctx ? n_cta : 0);
+    if (n_calls == 1) {
 #pragma unroll 4
-    for (int r = grp; r < count; r += RED_G) a += (double)src[(size_t)r * stride];   // independent loads, few per thread
+        for (int r = grp; r < count; r += RED_G) a += (double)src[(size_t)r * stride];   // independent loads, few per thread
+    } else {            // deferred reduction: the same rows of n_calls launches (blocks call_stride floats apart), calls in order
+#pragma unroll 4
+        for (int i = grp; i < count * n_calls; i += RED_G) {
+            const int c = i / count, r = i - c * count;
+            a += (double)src[(size_t)c * call_stride + (size_t)r * stride];
+        }
+    }
     s_sum[grp][lane] = a;
     __syncthreads();
     if (grp != 0 || col >= n_acc + n_ctx) return;
@@ -1046,7 +1054,7 @@ size_t coupling_bwd_d2_workspace_floats(int n_flows, int C_row, int B) {
 template <int PPT, int NT>
 static int launch_cfg(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, int flags, int B, int N,
                       const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* d_packed, void* workspace,
-                      cudaStream_t st) {
+                      cudaStream_t st, float* block = nullptr) {
     static_assert(NT / 32 <= D2_MAX_WARPS, "workspace is sized for D2_MAX_WARPS warps per CTA");
     const int n_fcnn = 4 * n_flows;
     const int grid = min(B, sm_count());   // one CTA per SM, persistent over trajectories
@@ -1061,13 +1069,15 @@ static int launch_cfg(const float* packed, int n_flows, int C_row, const float* 
     auto kern = coupling_bwd_d2_kernel<PPT, NT>;
     NFDPF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float* warp_rows = (float*)workspace;
-    float* ctx_rows = warp_rows + (size_t)grid * (NT / 32) * n_fcnn * NACC;
+    // the rows the reduction reads ([row-context partials | folded CTA rows]): behind the per-warp rows, or -- deferred reduction --
+    // in the caller's block, where they wait for ONE reduce launch over all the calls of a training step
+    float* ctx_rows = block ? block : warp_rows + (size_t)grid * (NT / 32) * n_fcnn * NACC;
     float* cta_rows = ctx_rows + (size_t)grid * n_fcnn * H * (C_row + 1);
     kern<<<grid, NT, smem, st>>>(packed, n_flows, C_row, y, row_ctx, flags, B, N, g_y, g_ld, d_x, warp_rows, ctx_rows, cta_rows, d_row_ctx, e_max);
     int rc = check_launch("coupling_bwd_d2");
-    if (rc) return rc;
+    if (rc || block) return rc;
     const int n_cols = n_fcnn * NACC + n_fcnn * H * (C_row + 1);
-    d2_reduce_kernel<<<(n_cols + 31) / 32, 32 * RED_G, 0, st>>>(cta_rows, grid, ctx_rows, grid, n_fcnn, C_row, d_packed);
+    d2_reduce_kernel<<<(n_cols + 31) / 32, 32 * RED_G, 0, st>>>(cta_rows, grid, ctx_rows, grid, n_fcnn, C_row, d_packed, 1, 0);
     return check_launch("d2_reduce");
 }
 
@@ -1137,8 +1147,28 @@ static int launch_ws(const float* packed, int n_flows, int C_row, const float* y
     int rc = check_launch("coupling_bwd_d2_ws");
     if (rc) return rc;
     const int n_cols = n_fcnn * NACC + n_fcnn * H * (C_row + 1);
-    d2_reduce_kernel<<<(n_cols + 31) / 32, 32 * RED_G, 0, st>>>(cta_rows, grid, ctx_rows, grid, n_fcnn, C_row, d_packed);
+    d2_reduce_kernel<<<(n_cols + 31) / 32, 32 * RED_G, 0, st>>>(cta_rows, grid, ctx_rows, grid, n_fcnn, C_row, d_packed, 1, 0);
     return check_launch("d2_reduce");
+}
+
+// ---- deferred reduction (one reduce launch per training step instead of one per call) ------------------------------------------
+size_t coupling_bwd_d2_block_floats(int n_flows, int C_row, int B) {
+    const int n_fcnn = 4 * n_flows, grid = min(B, sm_count());
+    return (size_t)grid * ((size_t)n_fcnn * H * (C_row + 1) + (size_t)n_fcnn * NACC);
+}
+int launch_coupling_bwd_d2_deferred(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, int inverse, int B,
+                                    int N, const float* g_y, const float* g_ld, float* d_x, float* d_row_ctx, float* block, void* workspace,
+                                    cudaStream_t st) {
+    return launch_cfg<2, 256>(packed, n_flows, C_row, y, row_ctx, inverse, B, N, g_y, g_ld, d_x, d_row_ctx, nullptr, workspace, st, block);
+}
+int launch_coupling_bwd_d2_reduce(int n_flows, int C_row, int B, const float* blocks, int n_calls, float* d_packed, cudaStream_t st) {
+    const int n_fcnn = 4 * n_flows, grid = min(B, sm_count());
+    const int n_cols = n_fcnn * NACC + n_fcnn * H * (C_row + 1);
+    const float* ctx_rows = blocks;
+    const float* cta_rows = blocks + (size_t)grid * n_fcnn * H * (C_row + 1);
+    d2_reduce_kernel<<<(n_cols + 31) / 32, 32 * RED_G, 0, st>>>(cta_rows, grid, ctx_rows, grid, n_fcnn, C_row, d_packed, n_calls,
+                                                                coupling_bwd_d2_block_floats(n_flows, C_row, B));
+    return check_launch("d2_reduce (deferred)");
 }
 
 int launch_coupling_bwd_d2(const float* packed, int n_flows, int C_row, const float* y, const float* row_ctx, int inverse, int B, int N,

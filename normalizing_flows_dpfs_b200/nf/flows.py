@@ -31,10 +31,13 @@ class GradSlab:
     launch.  Without it autograd adds the per-call gradients pairwise: one tiny ATen launch per call (four per timestep, 1.2 % of
     the device time of a training step)."""
     CHUNK = 256
+    BLOCK_CHUNK = 64     # calls per block tensor of the deferred D = 2 reduction (1.9 MB per call at 148 CTAs, C_row = 36)
 
     def __init__(self, numel, device):
         self.numel, self.device, self.count = numel, device, 0
         self.chunks, self.written = [], set()
+        # deferred reduction (ops.CouplingStack, D = 2): per kernel shape key = (n_flows, D, C_row, B) the calls' partial-row blocks
+        self.bcount, self.bchunks, self.bwritten = {}, {}, {}
 
     def take(self):
         self.count += 1
@@ -48,11 +51,43 @@ class GradSlab:
         self.written.add(i)
         return self.chunks[c][i % self.CHUNK]
 
-    def total(self):
-        """Sum of the written rows (None if there are none).  Rows are consumed: a second backward writes them again."""
-        if not self.written:
-            return None
+    def take_block(self, key):
+        i = self.bcount.get(key, 0)
+        self.bcount[key] = i + 1
+        return i
+
+    def block(self, key, i, block_floats):
+        """Block i of shape `key` (uninitialised until the backward kernel has written it); marks it as written."""
+        chunks = self.bchunks.setdefault(key, [])
+        c = i // self.BLOCK_CHUNK
+        while len(chunks) <= c:
+            chunks.append(torch.empty(self.BLOCK_CHUNK, block_floats, dtype=torch.float32, device=self.device))
+        self.bwritten.setdefault(key, set()).add(i)
+        return chunks[c][i % self.BLOCK_CHUNK]
+
+    def _blocks_total(self):
+        """One reduce launch per run of consecutive written blocks (normally one per 64 calls)."""
         out = None
+        for key, written in self.bwritten.items():
+            for c, chunk in enumerate(self.bchunks[key]):
+                rows = sorted(i - c * self.BLOCK_CHUNK for i in written if i // self.BLOCK_CHUNK == c)
+                k = 0
+                while k < len(rows):
+                    j = k
+                    while j + 1 < len(rows) and rows[j + 1] == rows[j] + 1:
+                        j += 1
+                    part = ops.coupling_bwd_reduce(key, chunk[rows[k]:rows[j] + 1], self.numel)
+                    out = part if out is None else out + part
+                    k = j + 1
+        self.bwritten = {}
+        return out
+
+    def total(self):
+        """Sum of the written rows and blocks (None if there are none).  They are consumed: a second backward writes them again."""
+        blocks = self._blocks_total() if self.bwritten else None
+        if not self.written:
+            return blocks
+        out = blocks
         for c, chunk in enumerate(self.chunks):
             rows = sorted(i - c * self.CHUNK for i in self.written if i // self.CHUNK == c)
             if not rows:

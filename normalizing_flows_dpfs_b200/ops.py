@@ -1,8 +1,13 @@
 """torch.autograd.Function wrappers over the C-ABI.  Each forward/backward is one (or two) kernel launches on
 the current CUDA stream; tensors are allocated by torch, the library only sees raw pointers."""
+import os
+
 import torch
 
 from . import _lib as L
+
+
+_DEFER_D2 = os.environ.get("NFDPF_DEFER_D2", "1") != "0"     # A/B switch of the deferred D = 2 parameter-gradient reduction
 
 
 def _slab_row(packed):
@@ -130,7 +135,17 @@ class CouplingStack(torch.autograd.Function):
         ctx.save_for_backward(pk, y, rc, pc)
         ctx.set_materialize_grads(False)
         ctx.meta = (n_flows, D, C_row, C_part, flags, B, N)
-        ctx.slab = _slab_row(packed)
+        ctx.slab = ctx.block = None
+        slab = getattr(packed, "_nfdpf_slab", None) if packed.requires_grad else None
+        if slab is not None:
+            # D = 2 stacks with row context: the call's partial gradient rows wait in a block of the slab for ONE reduce launch per
+            # training step (nfdpf_coupling_bwd_deferred / _reduce) instead of one small reduce launch per call
+            bf = L.load().nfdpf_coupling_bwd_block_floats(n_flows, D, C_row, C_part, B) if _DEFER_D2 else 0
+            if bf > 0:
+                key = (n_flows, D, C_row, B)
+                ctx.block = (slab, key, slab.take_block(key), bf)
+            else:
+                ctx.slab = (slab, slab.take())
         return y, ld
 
     @staticmethod
@@ -144,12 +159,27 @@ class CouplingStack(torch.autograd.Function):
         need_pc = pc is not None and ctx.needs_input_grad[3]
         d_rc = torch.empty_like(rc) if need_rc else None
         d_pc = torch.empty_like(pc) if need_pc else None
-        d_pk = ctx.slab[0].row(ctx.slab[1]) if ctx.slab else torch.empty_like(pk)        # every entry is written by the reduce kernel
         ws_bytes = L.load().nfdpf_coupling_bwd_workspace(n_flows, D, C_row, C_part, B, N)
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=y.device)
+        if ctx.block:
+            slab, key, i, bf = ctx.block
+            blk = slab.block(key, i, bf)
+            L.call("nfdpf_coupling_bwd_deferred", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(y), L.ptr(rc), inverse, B, N,
+                   L.ptr(g_y), L.ptr(g_ld), L.ptr(d_x), L.ptr(d_rc), L.ptr(blk), L.ptr(ws), L.stream())
+            return None, d_x, d_rc, d_pc, None, None, None, None
+        d_pk = ctx.slab[0].row(ctx.slab[1]) if ctx.slab else torch.empty_like(pk)        # every entry is written by the reduce kernel
         L.call("nfdpf_coupling_bwd", L.ptr(pk), n_flows, D, C_row, C_part, L.ptr(y), L.ptr(rc), L.ptr(pc), inverse, B, N,
                L.ptr(g_y), L.ptr(g_ld), L.ptr(d_x), L.ptr(d_rc), L.ptr(d_pc), L.ptr(d_pk), L.ptr(ws), L.stream())
         return (None if ctx.slab else d_pk), d_x, d_rc, d_pc, None, None, None, None
+
+
+def coupling_bwd_reduce(key, blocks, numel):
+    """Parameter gradient of `blocks.shape[0]` deferred D = 2 backward calls of shape key = (n_flows, D, C_row, B): one launch."""
+    n_flows, D, C_row, B = key
+    assert blocks.is_contiguous()
+    d_pk = torch.empty(numel, dtype=torch.float32, device=blocks.device)
+    L.call("nfdpf_coupling_bwd_reduce", n_flows, D, C_row, 0, B, L.ptr(blocks), blocks.shape[0], L.ptr(d_pk), L.stream())
+    return d_pk
 
 
 def soft_resample(particles, probs, offsets, markers, alpha, want_log=False, gate=None, out=None):
