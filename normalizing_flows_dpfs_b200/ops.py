@@ -515,6 +515,7 @@ class MotionMoments(torch.autograd.Function):
             L.call("nfdpf_motion_moments_rng", L.ptr(x), L.ptr(v), L.ptr(rng_state), float(sigma), B, N, d, L.ptr(res), L.ptr(e),
                    L.ptr(ctx_buf), cs, ctx_off, L.stream())
         ctx.mark_non_differentiable(e)
+        ctx.set_materialize_grads(False)     # (autograd zero-filled a (B,N,2) gradient for the noise output on every backward call)
         return res, e
 
     @staticmethod
