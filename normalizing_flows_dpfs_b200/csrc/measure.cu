@@ -1059,7 +1059,7 @@ struct PeTcWs : PeTc {
     }
 };
 
-template <int MODE, int DIAG = 0>
+template <int MODE>
 __global__ void __launch_bounds__(WS_THREADS, 2)
 measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const float* __restrict__ enc,
                       const float* __restrict__ particles, int B, int N, const float* __restrict__ g_lki,
@@ -1121,10 +1121,10 @@ measure_bwd_ws_kernel(const float* __restrict__ pe, float p0, float p1, const fl
             // ---------------------------------------------------------------- gradient warps
             for (int n0 = 0; n0 < N; n0 += 128) {
                 umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
-                if (DIAG != 1) pe_weight_grads_a_x2(s_tile, tacc, pw);
+                pe_weight_grads_a_x2(s_tile, tacc, pw);
                 mbar_arrive(&s_empty[pw]);
                 umma::mbar_wait(&s_full[pw], ph_full); ph_full ^= 1;
-                if (DIAG != 1) pe_weight_grads_b_x2(s_tile, tacc, pw);
+                pe_weight_grads_b_x2(s_tile, tacc, pw);
                 mbar_arrive(&s_empty[pw]);
             }
             umma::wait_st();
@@ -2139,8 +2139,7 @@ template <int MODE>
 static void launch_measure_bwd_ws(const float* pe, float p0, float p1, const float* enc, const float* particles, int B, int N,
                                   const float* g_lki, const int* argmax, float* d_particles, float* d_enc, float* part_pe, int grid,
                                   size_t smem, const float* g_pred, const float* probs, cudaStream_t st) {
-    static const char* diag = getenv("NFDPF_WS_DIAG");     // timing diagnostics only (wrong gradients): 1 = gradient warps idle
-    auto kern = (diag && diag[0] == '1') ? measure_bwd_ws_kernel<MODE, 1> : measure_bwd_ws_kernel<MODE, 0>;
+    auto kern = measure_bwd_ws_kernel<MODE>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, WS_THREADS, smem, st>>>(pe, p0, p1, enc, particles, B, N, g_lki, argmax, d_particles, d_enc, part_pe, g_pred, probs);
 }

@@ -1,4 +1,4 @@
-"""Time the gaussian measurement forward / backward ops at B = N = 1024 with CUDA events (NFDPF_WS_DIAG=1: gradient warps idle)."""
+"""Time the gaussian measurement forward / backward ops at B = N = 1024 with CUDA events."""
 import json
 import os
 import sys
@@ -28,4 +28,4 @@ for it in range(10):
     torch.cuda.synchronize()
     fwd.append(e[0].elapsed_time(e[1]))
     bwd.append(e[1].elapsed_time(e[2]))
-print(json.dumps({"diag": os.environ.get("NFDPF_WS_DIAG"), "fwd_ms": min(fwd), "bwd_ms": min(bwd)}))
+print(json.dumps({"fwd_ms": min(fwd), "bwd_ms": min(bwd)}))
