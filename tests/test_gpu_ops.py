@@ -221,18 +221,21 @@ def _off_the_relu_kinks(x, pe, margin=2e-5):
 def _off_the_argmax_ties(x, lki_fn, margin=1e-3):
     """`likelihood - likelihood.max(-1)` (models.py:252, 276) routes -sum(g) to the argmax particle: two particles within the
     evaluation error of the row maximum make the two implementations pick different ones.  Runner-ups closer than `margin` are moved."""
-    for _ in range(3):
+    if x.shape[1] < 2:
+        return x
+    for it in range(40):
         with torch.no_grad():
-            top2 = lki_fn(x).topk(min(2, x.shape[1]), dim=-1)
-        if x.shape[1] < 2:
-            break
+            top2 = lki_fn(x).topk(2, dim=-1)
         tie = (top2.values[:, 0] - top2.values[:, 1]) < margin
         if not bool(tie.any()):
-            break
+            return x
         x = x.clone()
         rows = torch.nonzero(tie).flatten()
-        x[rows, top2.indices[rows, 1]] += 0.05
-    return x
+        # growing displacement: where the likelihood is nearly flat in x (freshly initialised CRNVP stacks) a fixed 0.05 step does not
+        # separate the pair -- three such rounds left a 3.8e-6 tie in NFDPF_TEST_SEED=1, iteration 12 of the randomized CRNVP loop,
+        # the "5e-2 d_pe mismatch" of round 1 (CUDA and oracle picked different argmax particles)
+        x[rows, top2.indices[rows, 1]] += 0.05 * (1 + it)
+    raise AssertionError("could not separate the two most likely particles of every trajectory by %g" % margin)
 
 
 @pytest.mark.parametrize("mode,B,N,fused", [("gaussian", 3, 200, True), ("cos", 3, 200, True), ("CRNVP", 3, 200, True),
