@@ -5,10 +5,11 @@
 //   -> row max shift -> logw = logw_prev + lki + prior - propose (DPFs.py:187) -> softmax + eps, ESS term, sum logw.
 // The reference materialises the (B,N,32) encodings, the repeated (B,N,32) observation encodings and, for CRNVP,
 // eight (P,48) concatenations; here the only HBM traffic is particles in, (B,N) vectors out.
-// Tensor cores (umma.cuh): encoder layers 2-3 (forward and data gradient) and, in the forward, layer 1 of the CRNVP stages run
-// as 3xTF32 tcgen05 products over batches of 128 particles (thread = particle = tensor-memory lane); the backward's weight
-// gradients are mma.sync 3xTF32 contractions whose fragments accumulate in tensor memory.  Layer 1 of the encoder, the 8-wide
-// layers of the stack, activations and the likelihood algebra stay in registers.
+// Tensor cores (umma.cuh): encoder layers 2-3 (forward and data gradient) and layer 1 of the CRNVP stages (forward, and in the
+// warp-specialised backward also its recompute and W1^T delta1) run as 3xTF32 tcgen05 products over batches of 128 particles
+// (thread = particle = tensor-memory lane); the backward's weight gradients are mma.sync 3xTF32 contractions whose fragments
+// accumulate in tensor memory.  Layer 1 of the encoder, the 8-wide layers of the stack, activations and the likelihood algebra
+// stay in registers.
 #include "coupling.cuh"
 #include "mma_tile.cuh"
 #include "umma.cuh"
