@@ -52,6 +52,62 @@ __global__ void weight_update_fwd_kernel(const float* __restrict__ lw0, const fl
     if (t0 == 0 && row_stats) { row_stats[2 * row] = sl; row_stats[2 * row + 1] = 1.0f / s2; }
 }
 
+// N <= 1024, N % 4 == 0: one warp per row, the row in registers (a lane owns four consecutive entries of each 128-entry chunk): 128-bit
+// loads issued up front, every tensor read and written ONCE (the kernel above stashes the row in probs_out and re-reads it twice:
+// 25 us cold for 12.6 MB at B = N = 1024).
+__global__ void __launch_bounds__(256)
+weight_update_fwd_reg_kernel(const float* __restrict__ lw0, const float* __restrict__ lki, const float* __restrict__ prior,
+                             const float* __restrict__ propose, float add_eps, int B, int N, float* __restrict__ logw_out,
+                             float* __restrict__ probs_out, float* __restrict__ row_stats) {
+    const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= B) return;
+    const size_t base = (size_t)row * N;
+    float v[8][4];
+    float mx = -INFINITY, sl = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = 128 * i + 4 * lane;
+        if (n < N) {
+            float4 a = *reinterpret_cast<const float4*>(lw0 + base + n);
+            if (lki) { const float4 t = *reinterpret_cast<const float4*>(lki + base + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            if (prior) { const float4 t = *reinterpret_cast<const float4*>(prior + base + n); a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            if (propose) { const float4 t = *reinterpret_cast<const float4*>(propose + base + n); a.x -= t.x; a.y -= t.y; a.z -= t.z; a.w -= t.w; }
+            if (logw_out) *reinterpret_cast<float4*>(logw_out + base + n) = a;     // (logw + lki + prior) - propose, DPFs.py:187
+            v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+            mx = fmaxf(fmaxf(mx, fmaxf(a.x, a.y)), fmaxf(a.z, a.w));
+            sl += (a.x + a.y) + (a.z + a.w);
+        } else {
+            v[i][0] = v[i][1] = v[i][2] = v[i][3] = -INFINITY;
+        }
+    }
+    mx = warp_max(mx);
+    sl = warp_sum(sl);
+    float se = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float e = 128 * i + 4 * lane < N ? expf(v[i][u] - mx) : 0.f;
+            v[i][u] = e;
+            se += e;
+        }
+    se = warp_sum(se);
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int n = 128 * i + 4 * lane;
+        if (n < N) {
+            float4 p;
+            p.x = __fdiv_rn(v[i][0], se) + add_eps; p.y = __fdiv_rn(v[i][1], se) + add_eps;      // utils.py:43, DPFs.py:192
+            p.z = __fdiv_rn(v[i][2], se) + add_eps; p.w = __fdiv_rn(v[i][3], se) + add_eps;
+            *reinterpret_cast<float4*>(probs_out + base + n) = p;
+            s2 += (p.x * p.x + p.y * p.y) + (p.z * p.z + p.w * p.w);
+        }
+    }
+    s2 = warp_sum(s2);
+    if (lane == 0 && row_stats) { row_stats[2 * row] = sl; row_stats[2 * row + 1] = 1.0f / s2; }
+}
+
 // d logw = p (g - sum g p) + g_logw + g_rowsum, with p = softmax (the forward output minus add_eps).
 template <bool BLOCK_PER_ROW>
 __global__ void weight_update_bwd_kernel(const float* __restrict__ g_probs, const float* __restrict__ g_logw,
@@ -152,7 +208,9 @@ extern "C" int nfdpf_weight_update_fwd(const float* logw_prev, const float* lki,
     NFDPF_REQUIRE(logw_prev && probs_out, "weight_update_fwd: null pointer");
     NFDPF_REQUIRE(B > 0 && N > 0, "weight_update_fwd: B and N must be positive (got %d, %d)", B, N);
     cudaStream_t st = (cudaStream_t)stream;
-    if (N <= 1024) {
+    if (N <= 1024 && N % 4 == 0) {
+        weight_update_fwd_reg_kernel<<<(B + 7) / 8, 256, 0, st>>>(logw_prev, lki, prior, propose, add_eps, B, N, logw_out, probs_out, row_stats);
+    } else if (N <= 1024) {
         const int wpb = 8;
         weight_update_fwd_kernel<false><<<(B + wpb - 1) / wpb, wpb * 32, 0, st>>>(logw_prev, lki, prior, propose, add_eps, B, N,
                                                                                   logw_out, probs_out, row_stats);
